@@ -1,0 +1,335 @@
+// avcer_contract: host launcher of the tcgen05 implicit-GEMM kernel (bf16) and the SIMT fp32
+// kernel ("fp32 mode"), both driven by the same avcer_contract_desc geometry.
+#include "common.h"
+#include "tc_gemm.cuh"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace avcer {
+
+// ------------------------------------------------------------------ tensor-map encoding
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box,
+                      CUtensorMapSwizzle swz) {
+  auto fn = get_encode_fn();
+  if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable");
+  uint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims,
+                  strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return set_error(
+        "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u] "
+        "stride1 %llu base %p",
+        (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+        (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+        (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+        rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0, (unsigned long long)strides_bytes[0], base);
+  }
+  return 0;
+}
+
+// Pick the box (bw, bh, bn), bw*bh*bn <= 128, that covers W x H x NB with the fewest M tiles.
+static void choose_box(int W, int H, int NB, int* bw, int* bh, int* bn) {
+  long long best = -1;
+  int rb = 0;
+  for (int w = 1; w <= 128 && w <= W; ++w) {
+    for (int h = 1; h * w <= 128 && h <= H; ++h) {
+      int n = 128 / (w * h);
+      if (n > NB) n = NB;
+      if (n > 256) n = 256;
+      const long long tiles = (long long)((W + w - 1) / w) * ((H + h - 1) / h) * ((NB + n - 1) / n);
+      const int r = w * h * n;
+      // fewer tiles first; then fuller boxes of wider rows (better locality of the TMA box)
+      if (best < 0 || tiles < best || (tiles == best && (w > *bw || (w == *bw && r > rb)))) {
+        best = tiles; *bw = w; *bh = h; *bn = n; rb = r;
+      }
+    }
+  }
+}
+
+template <int BN, int BK, bool OUT_F32>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcGemmParams& p, int grid,
+                     cudaStream_t st) {
+  using Cfg = TcGemmCfg<BN, BK>;
+  auto kern = tc_gemm_kernel<BN, BK, OUT_F32>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AVCER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_done = true;
+  }
+  kern<<<grid, 256, Cfg::SMEM, st>>>(ta, tb, p);
+  return check_launch("tc_gemm_kernel");
+}
+
+static int num_sms_cached() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
+  AVCER_REQUIRE(d->a_stride[0] == 1, "contract: a_stride[0] must be 1");
+  const int BK = (d->cin % 64 == 0) ? 64 : 32;
+  AVCER_REQUIRE(d->cin % BK == 0, "contract(bf16): cin=%d must be a multiple of 32", d->cin);
+  AVCER_REQUIRE(d->cout % 32 == 0, "contract(bf16): cout=%d must be a multiple of 32", d->cout);
+  AVCER_REQUIRE((reinterpret_cast<uintptr_t>(d->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->wt) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
+                "contract(bf16): a/wt/out must be 16-byte aligned");
+  int BN;
+  if (d->group_cin_shift != 0) BN = 64;
+  else if (d->cout % 128 == 0) BN = 128;
+  else if (d->cout % 64 == 0) BN = 64;
+  else BN = 32;
+  if (BK == 32 && BN > 64) BN = 64;   // stem: Cout = 64
+
+  TcGemmParams p{};
+  choose_box(d->W, d->H, d->NB, &p.bw, &p.bh, &p.bn);
+  p.tw = (d->W + p.bw - 1) / p.bw;
+  p.th = (d->H + p.bh - 1) / p.bh;
+  p.tn = (d->NB + p.bn - 1) / p.bn;
+  p.tiles_n = (d->cout + BN - 1) / BN;
+  const long long nt = (long long)p.tw * p.th * p.tn * p.tiles_n;
+  AVCER_REQUIRE(nt < (1ll << 31), "contract: too many tiles");
+  p.num_tiles = (int)nt;
+  p.W = d->W; p.H = d->H; p.NB = d->NB;
+  p.taps_w = d->taps_w; p.taps_h = d->taps_h; p.off_w = d->off_w; p.off_h = d->off_h;
+  p.tap_h_in_dim4 = d->tap_h_in_dim4;
+  p.kchunks = d->cin / BK;
+  p.a_c0_per_ntile = d->group_cin_shift;   // BN == 64 == one group per N tile
+  p.Cout = d->cout;
+  p.out_sw = d->out_stride[0]; p.out_sh = d->out_stride[1]; p.out_sn = d->out_stride[2];
+  p.res_sw = d->res_stride[0]; p.res_sh = d->res_stride[1]; p.res_sn = d->res_stride[2];
+  p.bias = d->bias;
+  p.residual = static_cast<const __nv_bfloat16*>(d->residual);
+  p.out = d->out;
+  p.act = d->act;
+  p.res_after_act = d->res_after_act;
+  if (p.num_tiles == 0) return 0;
+
+  const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[5], strides[4];
+    for (int i = 0; i < 5; ++i) dims[i] = (uint64_t)d->a_dim[i];
+    for (int i = 1; i < 5; ++i) {
+      AVCER_REQUIRE(d->a_stride[i] % 8 == 0, "contract(bf16): a_stride[%d]=%lld must be a multiple of 8 elements",
+                    i, (long long)d->a_stride[i]);
+      strides[i - 1] = (uint64_t)d->a_stride[i] * 2;
+    }
+    uint32_t box[5] = {(uint32_t)BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, 1u};
+    if (encode_map(&ta, d->a, 5, dims, strides, box, swz)) return 1;
+  }
+  {
+    const uint64_t ktot = (uint64_t)d->taps_w * d->taps_h * d->cin;
+    uint64_t dims[2] = {ktot, (uint64_t)d->cout};
+    uint64_t strides[1] = {ktot * 2};
+    AVCER_REQUIRE((ktot * 2) % 16 == 0, "contract: weight row pitch must be a multiple of 16 bytes");
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    if (encode_map(&tb, d->wt, 2, dims, strides, box, swz)) return 1;
+  }
+  const int grid = p.num_tiles < num_sms_cached() ? p.num_tiles : num_sms_cached();
+  const bool f32 = d->out_f32 != 0;
+#define AVCER_TC_CASE(bn, bk)                                                         \
+  if (BN == bn && BK == bk)                                                           \
+    return f32 ? launch_tc<bn, bk, true>(ta, tb, p, grid, st) : launch_tc<bn, bk, false>(ta, tb, p, grid, st);
+  AVCER_TC_CASE(128, 64)
+  AVCER_TC_CASE(64, 64)
+  AVCER_TC_CASE(32, 64)
+  AVCER_TC_CASE(64, 32)
+  AVCER_TC_CASE(32, 32)
+#undef AVCER_TC_CASE
+  return set_error("contract: no tensor-core instantiation for BN=%d BK=%d", BN, BK);
+}
+
+// ------------------------------------------------------------------ SIMT fp32 path
+struct SimtParams {
+  const float* a;
+  long long a_dim[5], a_stride[5];
+  const float* wt;
+  const float* bias;
+  const float* residual;
+  float* out;
+  long long out_stride[3], res_stride[3];
+  int W, H, NB, cin, cout, taps_w, taps_h, off_w, off_h, tap_h_in_dim4, group_cin_shift, act, res_after_act;
+  long long M;
+  int Ktot;
+  int vec4;   // cin % 4 == 0 and every address 16-byte aligned
+};
+
+__global__ void __launch_bounds__(256) simt_contract_kernel(const SimtParams p) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int cshift = (n0 / 64) * p.group_cin_shift;
+
+  // loader mapping: 64 rows x 4 quads of k
+  const int lrow = tid >> 2;
+  const int lk = (tid & 3) * 4;
+  const long long m = m0 + lrow;
+  const bool mvalid = m < p.M;
+  int ow = 0, oh = 0, on = 0;
+  if (mvalid) {
+    ow = (int)(m % p.W);
+    oh = (int)((m / p.W) % p.H);
+    on = (int)(m / ((long long)p.W * p.H));
+  }
+  const int bcol = n0 + lrow;
+  const bool bvalid = bcol < p.cout;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int ty = tid >> 4, tx = tid & 15;
+  for (int k0 = 0; k0 < p.Ktot; k0 += BK) {
+    float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+    const int kk = k0 + lk;
+    if (mvalid && kk < p.Ktot) {
+      if (p.vec4) {
+        const int tap = kk / p.cin, c = kk % p.cin;
+        const int tyy = tap / p.taps_w, txx = tap % p.taps_w;
+        const long long cw = ow + p.off_w + txx;
+        const long long ch = oh + p.off_h + (p.tap_h_in_dim4 ? 0 : tyy);
+        const long long ct = p.tap_h_in_dim4 ? tyy : 0;
+        const long long cc = c + cshift;
+        if (cw >= 0 && cw < p.a_dim[1] && ch >= 0 && ch < p.a_dim[2] && on < p.a_dim[3] && ct < p.a_dim[4] &&
+            cc + 3 < p.a_dim[0]) {
+          const float4 v = *reinterpret_cast<const float4*>(p.a + cc + cw * p.a_stride[1] + ch * p.a_stride[2] +
+                                                            on * p.a_stride[3] + ct * p.a_stride[4]);
+          av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = kk + j;
+          if (k < p.Ktot) {
+            const int tap = k / p.cin, c = k % p.cin;
+            const int tyy = tap / p.taps_w, txx = tap % p.taps_w;
+            const long long cw = ow + p.off_w + txx;
+            const long long ch = oh + p.off_h + (p.tap_h_in_dim4 ? 0 : tyy);
+            const long long ct = p.tap_h_in_dim4 ? tyy : 0;
+            const long long cc = c + cshift;
+            if (cw >= 0 && cw < p.a_dim[1] && ch >= 0 && ch < p.a_dim[2] && on < p.a_dim[3] && ct < p.a_dim[4] &&
+                cc < p.a_dim[0])
+              av[j] = p.a[cc + cw * p.a_stride[1] + ch * p.a_stride[2] + on * p.a_stride[3] + ct * p.a_stride[4]];
+          }
+        }
+      }
+    }
+    if (bvalid && kk < p.Ktot) {
+      if (p.vec4) {
+        const float4 v = *reinterpret_cast<const float4*>(p.wt + (long long)bcol * p.Ktot + kk);
+        bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (kk + j < p.Ktot) bv[j] = p.wt[(long long)bcol * p.Ktot + kk + j];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      As[lk + j][lrow] = av[j];
+      Bs[lk + j][lrow] = bv[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long mm = m0 + ty * 4 + i;
+    if (mm >= p.M) continue;
+    const int w = (int)(mm % p.W);
+    const int h = (int)((mm / p.W) % p.H);
+    const int n = (int)(mm / ((long long)p.W * p.H));
+    const long long oo = w * p.out_stride[0] + h * p.out_stride[1] + n * p.out_stride[2];
+    const long long ro = w * p.res_stride[0] + h * p.res_stride[1] + n * p.res_stride[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = n0 + tx * 4 + j;
+      if (co >= p.cout) continue;
+      float v = acc[i][j];
+      if (p.bias) v += p.bias[co];
+      if (p.residual && !p.res_after_act) v += p.residual[ro + co];
+      if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
+      else if (p.act == ACT_GELU) v = gelu_erf(v);
+      if (p.residual && p.res_after_act) v += p.residual[ro + co];
+      p.out[oo + co] = v;
+    }
+  }
+}
+
+static int contract_simt(const avcer_contract_desc* d, cudaStream_t st) {
+  SimtParams p{};
+  p.a = static_cast<const float*>(d->a);
+  for (int i = 0; i < 5; ++i) { p.a_dim[i] = d->a_dim[i]; p.a_stride[i] = d->a_stride[i]; }
+  p.wt = static_cast<const float*>(d->wt);
+  p.bias = d->bias;
+  p.residual = static_cast<const float*>(d->residual);
+  p.out = static_cast<float*>(d->out);
+  for (int i = 0; i < 3; ++i) { p.out_stride[i] = d->out_stride[i]; p.res_stride[i] = d->res_stride[i]; }
+  p.W = d->W; p.H = d->H; p.NB = d->NB; p.cin = d->cin; p.cout = d->cout;
+  p.taps_w = d->taps_w; p.taps_h = d->taps_h; p.off_w = d->off_w; p.off_h = d->off_h;
+  p.tap_h_in_dim4 = d->tap_h_in_dim4; p.group_cin_shift = d->group_cin_shift; p.act = d->act; p.res_after_act = d->res_after_act;
+  p.M = (long long)d->W * d->H * d->NB;
+  p.Ktot = d->taps_w * d->taps_h * d->cin;
+  AVCER_REQUIRE(d->group_cin_shift == 0 || d->cout % 64 == 0, "contract(f32): grouped conv needs cout %% 64 == 0");
+  bool v = (d->cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(d->a) & 15) == 0) &&
+           ((reinterpret_cast<uintptr_t>(d->wt) & 15) == 0) && (d->group_cin_shift % 4 == 0);
+  for (int i = 1; i < 5; ++i) v = v && (d->a_stride[i] % 4 == 0);
+  p.vec4 = v ? 1 : 0;
+  if (p.M == 0) return 0;
+  const long long gx = (p.M + 63) / 64;
+  AVCER_REQUIRE(gx < (1ll << 31), "contract(f32): M too large");
+  dim3 grid((unsigned)gx, (unsigned)((d->cout + 63) / 64));
+  simt_contract_kernel<<<grid, 256, 0, st>>>(p);
+  return check_launch("simt_contract_kernel");
+}
+
+}  // namespace avcer
+
+extern "C" int avcer_contract(const avcer_contract_desc* d, void* stream) {
+  using namespace avcer;
+  AVCER_REQUIRE(d != nullptr, "contract: null descriptor");
+  AVCER_REQUIRE(d->W > 0 && d->H > 0 && d->NB >= 0 && d->cin > 0 && d->cout > 0 && d->taps_w > 0 && d->taps_h > 0,
+                "contract: bad geometry");
+  if (d->dtype == AVCER_BF16) return contract_tc(d, as_stream(stream));
+  if (d->dtype == AVCER_F32) return contract_simt(d, as_stream(stream));
+  return set_error("contract: unknown dtype %d", d->dtype);
+}

@@ -1,0 +1,258 @@
+// K4 and the alignment glue around it: probability fusion -> compound-expression rule -> argmax
+// (reference: src/run.py:105-165, src/data/utils.py:125-127,222-241), per-frame mean of audio
+// window logits (run.py:90 groupby.mean + get_prob_audio_8_cl.py:94-101) and row gathers
+// (carry-forward of get_prob_video.py:157-178, column permutation run.py:85-88).
+//
+// Bit-exactness contract of K4: the reference computes in numpy with IEEE binary64 (binary32
+// when no weight matrix is given) using separate multiply and add instructions.  The kernel
+// uses the *_rn intrinsics so the compiler can never contract them into FMAs.
+#include "common.h"
+
+namespace avcer {
+
+// Compound expressions as pairs of basic-emotion indices in audio order (run.py:66-74).
+__constant__ int c_pair[7][2] = {{3, 6}, {4, 6}, {5, 6}, {2, 6}, {1, 6}, {3, 5}, {1, 5}};
+
+struct FuseParams {
+  double w[3][7];      // weights_1[m][c] (unused when !has_w1)
+  double w2[3];        // weights_2[m]
+  double ce_w[7][2];   // rule-2 pair weights (1,1 when !ce_weights_type)
+  int has_w1, ce_mask;
+};
+
+template <typename TC> struct Arith;
+template <> struct Arith<double> {
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double div3(double a) { return __ddiv_rn(a, 3.0); }
+  static __device__ __forceinline__ double thr() { return 1.0 / 7.0; }
+};
+template <> struct Arith<float> {
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float div3(float a) { return __fdiv_rn(a, 3.0f); }
+  static __device__ __forceinline__ float thr() { return (float)(1.0 / 7.0); }
+};
+
+// numpy argmax over the 7 compound scores: first maximum, NaN is "largest".
+template <typename TC>
+__device__ __forceinline__ long long compound_argmax(const TC (&s)[7], const FuseParams& p) {
+  using A = Arith<TC>;
+  TC v[7];
+#pragma unroll
+  for (int c = 0; c < 7; ++c) v[c] = p.ce_mask ? (s[c] > A::thr() ? s[c] : (TC)0) : s[c];
+  TC best = (TC)0;
+  int bi = 0;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const TC a = A::mul(v[c_pair[k][0]], (TC)p.ce_w[k][0]);
+    const TC b = A::mul(v[c_pair[k][1]], (TC)p.ce_w[k][1]);
+    const TC pr = A::add(a, b);
+    if (k == 0) { best = pr; bi = 0; }
+    else if (pr > best || (pr != pr && best == best)) { best = pr; bi = k; }
+  }
+  return bi;
+}
+
+constexpr int FUSE_THREADS = 256;
+
+// Each warp owns 32 consecutive frames: the three [frames,7] tiles are staged through shared
+// memory with fully coalesced loads, then every lane finishes one frame.
+template <typename TIn, typename TC>
+__global__ void __launch_bounds__(FUSE_THREADS)
+fuse_compound_kernel(const TIn* __restrict__ pvs, const TIn* __restrict__ pvd, const TIn* __restrict__ pa,
+                     long long n, const FuseParams p, long long* __restrict__ labels) {
+  using A = Arith<TC>;
+  __shared__ TIn sm[3][FUSE_THREADS * 7];
+  for (long long base = (long long)blockIdx.x * FUSE_THREADS; base < n; base += (long long)gridDim.x * FUSE_THREADS) {
+    const long long cnt = (n - base < FUSE_THREADS ? n - base : FUSE_THREADS) * 7;
+    const TIn* src[3] = {pvs + base * 7, pvd + base * 7, pa + base * 7};
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+      for (int i = threadIdx.x; i < cnt; i += FUSE_THREADS) sm[m][i] = __ldg(src[m] + i);
+    __syncthreads();
+    const long long f = base + threadIdx.x;
+    if (f < n) {
+      TC x[3][7];
+#pragma unroll
+      for (int m = 0; m < 3; ++m)
+#pragma unroll
+        for (int c = 0; c < 7; ++c) x[m][c] = (TC)sm[m][threadIdx.x * 7 + c];
+      TC av[7];
+      if (p.has_w1) {
+        // predictions[m] * weights_1[m] * weights_2[m], summed left to right (run.py:108-111)
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+          for (int c = 0; c < 7; ++c) x[m][c] = A::mul(A::mul(x[m][c], (TC)p.w[m][c]), (TC)p.w2[m]);
+#pragma unroll
+        for (int c = 0; c < 7; ++c) av[c] = A::add(A::add(x[0][c], x[1][c]), x[2][c]);
+      } else {
+        // np.sum(predictions, axis=0) / 3 (run.py:113-114)
+#pragma unroll
+        for (int c = 0; c < 7; ++c) av[c] = A::div3(A::add(A::add(x[0][c], x[1][c]), x[2][c]));
+      }
+      labels[f] = compound_argmax<TC>(av, p);
+      labels[n + f] = compound_argmax<TC>(x[0], p);
+      labels[2 * n + f] = compound_argmax<TC>(x[1], p);
+      labels[3 * n + f] = compound_argmax<TC>(x[2], p);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void softmax7_kernel(const T* __restrict__ x, long long n, int ld, T* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T v[7];
+#pragma unroll
+  for (int c = 0; c < 7; ++c) v[c] = x[i * ld + c];
+  // np.max propagates NaN
+  T m = v[0];
+#pragma unroll
+  for (int c = 1; c < 7; ++c) m = (v[c] > m || v[c] != v[c]) ? v[c] : m;
+  T s = (T)0;
+#pragma unroll
+  for (int c = 0; c < 7; ++c) {
+    v[c] = sizeof(T) == 4 ? (T)expf((float)(v[c] - m)) : (T)exp((double)(v[c] - m));
+  }
+  // np.sum over 7 contiguous elements: plain left-to-right (below the pairwise threshold)
+#pragma unroll
+  for (int c = 0; c < 7; ++c) s = s + v[c];
+#pragma unroll
+  for (int c = 0; c < 7; ++c) y[i * 7 + c] = v[c] / s;
+}
+
+// pandas group_mean for float32: Kahan-compensated float32 sum in row order, NaN skipped,
+// divided by the float32 count; nobs == 0 -> NaN.
+__global__ void window_to_frame_mean_kernel(const float* __restrict__ logits, int n_win, int ncls,
+                                            const int* __restrict__ f_lo, const int* __restrict__ f_hi,
+                                            long long n_frames, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_frames * ncls) return;
+  const long long f = i / ncls;
+  const int c = (int)(i % ncls);
+  // first window with f_hi > f (f_hi is non-decreasing)
+  int lo = 0, hi = n_win;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((long long)f_hi[mid] > f) hi = mid; else lo = mid + 1;
+  }
+  float sum = 0.f, comp = 0.f, nobs = 0.f;
+  for (int w = lo; w < n_win && (long long)f_lo[w] <= f; ++w) {
+    if ((long long)f_hi[w] <= f) continue;
+    const float val = logits[(long long)w * ncls + c];
+    if (val == val) {
+      nobs = __fadd_rn(nobs, 1.0f);
+      const float y = __fsub_rn(val, comp);
+      const float t = __fadd_rn(sum, y);
+      comp = __fsub_rn(__fsub_rn(t, sum), y);
+      if (comp != comp) comp = 0.f;
+      sum = t;
+    }
+  }
+  out[i] = nobs == 0.f ? __int_as_float(0x7fc00000) : __fdiv_rn(sum, nobs);
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, long long n_out,
+                                   int ncols, const int* __restrict__ perm, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out * ncols) return;
+  const long long r = i / ncols;
+  const int c = (int)(i % ncols);
+  const int s = idx ? idx[r] : (int)r;
+  out[i] = s >= 0 ? src[(long long)s * ncols + (perm ? perm[c] : c)] : 0.f;
+}
+
+}  // namespace avcer
+
+using namespace avcer;
+
+template <typename TIn>
+static int fuse_compound_impl(const TIn* p_vs, const TIn* p_vd, const TIn* p_a, int64_t n, const double* w1_host,
+                              const double* w2_host, int ce_weights_type, int ce_mask, int64_t* labels,
+                              void* stream) {
+  AVCER_REQUIRE(n >= 0, "fuse_compound: negative n");
+  if (n == 0) return 0;
+  FuseParams p{};
+  p.has_w1 = w1_host != nullptr;
+  p.ce_mask = ce_mask != 0;
+  if (p.has_w1) {
+    AVCER_REQUIRE(w2_host != nullptr, "fuse_compound: weights_2 required with weights_1");
+    for (int m = 0; m < 3; ++m) {
+      for (int c = 0; c < 7; ++c) p.w[m][c] = w1_host[m * 7 + c];
+      p.w2[m] = w2_host[m];
+    }
+  }
+  // Rule-2 weights d[i]/(d[i1]+d[i2]) with d = {1:5,2:6,3:5,4:6,5:4,6:2} (run.py:116-123, utils.py:228-231)
+  static const double dict_w[7] = {0, 5, 6, 5, 6, 4, 2};
+  static const int pairs[7][2] = {{3, 6}, {4, 6}, {5, 6}, {2, 6}, {1, 6}, {3, 5}, {1, 5}};
+  for (int k = 0; k < 7; ++k) {
+    if (ce_weights_type) {
+      const double s = dict_w[pairs[k][0]] + dict_w[pairs[k][1]];
+      p.ce_w[k][0] = dict_w[pairs[k][0]] / s;
+      p.ce_w[k][1] = dict_w[pairs[k][1]] / s;
+    } else {
+      p.ce_w[k][0] = 1.0;
+      p.ce_w[k][1] = 1.0;
+    }
+  }
+  const long long blocks_needed = (n + FUSE_THREADS - 1) / FUSE_THREADS;
+  const long long cap = 148ll * 8;
+  const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+  cudaStream_t st = as_stream(stream);
+  // numpy promotes to float64 as soon as the (Python-float) weight lists take part; without
+  // them the arithmetic stays in the dtype of the probability arrays.
+  if (p.has_w1 || sizeof(TIn) == 8)
+    fuse_compound_kernel<TIn, double><<<grid, FUSE_THREADS, 0, st>>>(p_vs, p_vd, p_a, n, p, (long long*)labels);
+  else
+    fuse_compound_kernel<TIn, float><<<grid, FUSE_THREADS, 0, st>>>(p_vs, p_vd, p_a, n, p, (long long*)labels);
+  return check_launch("fuse_compound_kernel");
+}
+
+extern "C" int avcer_fuse_compound(const float* p_vs, const float* p_vd, const float* p_a, int64_t n,
+                                   const double* w1_host, const double* w2_host, int ce_weights_type, int ce_mask,
+                                   int64_t* labels, void* stream) {
+  return fuse_compound_impl<float>(p_vs, p_vd, p_a, n, w1_host, w2_host, ce_weights_type, ce_mask, labels, stream);
+}
+
+extern "C" int avcer_fuse_compound_f64(const double* p_vs, const double* p_vd, const double* p_a, int64_t n,
+                                       const double* w1_host, const double* w2_host, int ce_weights_type,
+                                       int ce_mask, int64_t* labels, void* stream) {
+  return fuse_compound_impl<double>(p_vs, p_vd, p_a, n, w1_host, w2_host, ce_weights_type, ce_mask, labels, stream);
+}
+
+extern "C" int avcer_softmax7_f64(const double* x, int64_t n, int ld, double* y, void* stream) {
+  AVCER_REQUIRE(n >= 0 && ld >= 7, "softmax7: bad shape");
+  if (n == 0) return 0;
+  softmax7_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(x, n, ld, y);
+  return check_launch("softmax7_kernel");
+}
+
+extern "C" int avcer_softmax7(const float* x, int64_t n, int ld, float* y, void* stream) {
+  AVCER_REQUIRE(n >= 0 && ld >= 7, "softmax7: bad shape");
+  if (n == 0) return 0;
+  softmax7_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(x, n, ld, y);
+  return check_launch("softmax7_kernel");
+}
+
+extern "C" int avcer_window_to_frame_mean(const float* logits, int n_win, int ncls, const int32_t* f_lo,
+                                          const int32_t* f_hi, int64_t n_frames, float* out, void* stream) {
+  AVCER_REQUIRE(n_win >= 0 && ncls > 0 && n_frames >= 0, "window_to_frame_mean: bad shape");
+  const long long tot = n_frames * ncls;
+  if (tot == 0) return 0;
+  window_to_frame_mean_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, as_stream(stream)>>>(logits, n_win, ncls, f_lo,
+                                                                                             f_hi, n_frames, out);
+  return check_launch("window_to_frame_mean_kernel");
+}
+
+extern "C" int avcer_gather_rows(const float* src, const int32_t* src_index, int64_t n_out, int ncols,
+                                 const int32_t* perm, float* out, void* stream) {
+  AVCER_REQUIRE(n_out >= 0 && ncols > 0, "gather_rows: bad shape");
+  const long long tot = n_out * ncols;
+  if (tot == 0) return 0;
+  gather_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, as_stream(stream)>>>(src, src_index, n_out, ncols, perm,
+                                                                                   out);
+  return check_launch("gather_rows_kernel");
+}

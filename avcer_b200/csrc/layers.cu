@@ -1,0 +1,564 @@
+// Memory-bound and small layers of the VS / VD / A networks, channels-last, templated on the
+// storage type (bf16 in the default mode, fp32 in "fp32 mode").  Arithmetic is always fp32.
+// Reference call sites are cited per kernel.
+#include "common.h"
+
+namespace avcer {
+
+constexpr int ACT_GELU_L = AVCER_ACT_GELU;
+
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// 8-element vector access helpers
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+
+// ------------------------------------------------------------------ max pool 3x3/2, no padding (video.py:103)
+template <typename T>
+__global__ void maxpool3x3s2_kernel(const T* __restrict__ x, int n, int h, int w, int c, int ho, int wo, T* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c8 = c / 8;
+  const long long total = (long long)n * ho * wo * c8;
+  if (i >= total) return;
+  const int cc = (int)(i % c8) * 8;
+  const int ox = (int)((i / c8) % wo);
+  const int oy = (int)((i / ((long long)c8 * wo)) % ho);
+  const int b = (int)(i / ((long long)c8 * wo * ho));
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      float v[8];
+      Vec8<T>::load(x + (((long long)b * h + (2 * oy + dy)) * w + (2 * ox + dx)) * c + cc, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+    }
+  Vec8<T>::store(y + (((long long)b * ho + oy) * wo + ox) * c + cc, m);
+}
+
+// ------------------------------------------------------------------ global average pool (video.py:124)
+template <typename T>
+__global__ void avgpool_kernel(const T* __restrict__ x, int n, int hw, int c, T* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c8 = c / 8;
+  if (i >= (long long)n * c8) return;
+  const int cc = (int)(i % c8) * 8;
+  const int b = (int)(i / c8);
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = 0; p < hw; ++p) {
+    float v[8];
+    Vec8<T>::load(x + ((long long)b * hw + p) * c + cc, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += v[j];
+  }
+  const float inv = 1.0f / (float)hw;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] *= inv;
+  Vec8<T>::store(y + (long long)b * c + cc, s);
+}
+
+// ------------------------------------------------------------------ tiny Linear (+softmax): warp per row
+template <typename T>
+__global__ void small_linear_kernel(const T* __restrict__ x, long long n, int k, const float* __restrict__ w,
+                                    const float* __restrict__ b, int m, int softmax, float* __restrict__ y) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = lane; i < k; i += 32) {
+    const float xv = to_f32(x[row * k + i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < m) acc[j] = fmaf(xv, w[(long long)j * k + i], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = warp_sum(acc[j]);
+  if (lane == 0) {
+    float mx = -INFINITY;
+    for (int j = 0; j < m; ++j) { acc[j] += b ? b[j] : 0.f; mx = fmaxf(mx, acc[j]); }
+    if (softmax) {
+      float s = 0.f;
+      for (int j = 0; j < m; ++j) { acc[j] = expf(acc[j] - mx); s += acc[j]; }
+      for (int j = 0; j < m; ++j) acc[j] /= s;
+    }
+    for (int j = 0; j < m; ++j) y[row * m + j] = acc[j];
+  }
+}
+
+// ------------------------------------------------------------------ LSTM cell (PyTorch gate order i,f,g,o; video.py:169-185)
+template <typename T>
+__global__ void lstm_cell_kernel(const float* __restrict__ xproj, const int* __restrict__ xidx,
+                                 const float* __restrict__ hproj, float* __restrict__ c, T* __restrict__ h_out,
+                                 long long ldh, long long n, int hidden, int first) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * hidden) return;
+  const long long r = i / hidden;
+  const int j = (int)(i % hidden);
+  float g[4] = {0.f, 0.f, 0.f, 0.f};
+  if (xproj) {
+    const long long xr = xidx ? xidx[r] : r;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g[q] = xproj[xr * 4 * hidden + q * hidden + j];
+  }
+  if (hproj) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g[q] += hproj[r * 4 * hidden + q * hidden + j];
+  }
+  const float ig = sigmoid_f(g[0]), fg = sigmoid_f(g[1]), gg = tanhf(g[2]), og = sigmoid_f(g[3]);
+  const float cprev = first ? 0.f : c[i];
+  const float cn = fg * cprev + ig * gg;
+  c[i] = cn;
+  h_out[r * ldh + j] = from_f32<T>(og * tanhf(cn));
+}
+
+// ------------------------------------------------------------------ K5a audio window gather + pad + zero-mean/unit-var
+// (get_prob_audio_8_cl.py:78-90, data/utils.py:63-89, HF zero_mean_unit_var_norm: (x-mean)/sqrt(var+1e-7))
+__global__ void __launch_bounds__(512)
+audio_normalize_kernel(const float* __restrict__ wav, long long L, const long long* __restrict__ starts, int win,
+                       int pad_mode, float* __restrict__ out) {
+  __shared__ double red[16];
+  __shared__ double bc[2];
+  const int wi = blockIdx.x;
+  const long long s0 = starts[wi];
+  long long len = L - s0;
+  if (len > win) len = win;
+  if (len < 0) len = 0;
+  const float* src = wav + s0;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  auto block_sum = [&](double v) -> double {
+    v = warp_sum_d(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    if (tid == 0) { double t = 0; for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i]; bc[0] = t; }
+    __syncthreads();
+    return bc[0];
+  };
+  // pad value
+  float padv = 0.f;
+  double csum = 0;
+  for (long long i = tid; i < len; i += blockDim.x) csum += (double)src[i];
+  csum = block_sum(csum);
+  if (pad_mode == 0) padv = len > 0 ? (float)(csum / (double)len) : __int_as_float(0x7fc00000);
+  auto value = [&](long long i) -> float {
+    if (i < len) return src[i];
+    if (pad_mode == 2) return len > 0 ? src[i % len] : 0.f;
+    return padv;
+  };
+  double tsum = 0;
+  for (long long i = tid; i < win; i += blockDim.x) tsum += (double)value(i);
+  tsum = block_sum(tsum);
+  const double mean = tsum / (double)win;
+  double vs = 0;
+  for (long long i = tid; i < win; i += blockDim.x) { const double d = (double)value(i) - mean; vs += d * d; }
+  vs = block_sum(vs);
+  const float meanf = (float)mean;
+  const float inv = 1.0f / sqrtf((float)(vs / (double)win) + 1e-7f);
+  float* o = out + (long long)wi * win;
+  for (long long i = tid; i < win; i += blockDim.x) o[i] = (value(i) - meanf) * inv;
+}
+
+// ------------------------------------------------------------------ K5b wav2vec2 conv0 (Cin=1,k=10,s=5,bias) + LayerNorm(512) + GELU
+// (HF Wav2Vec2LayerNormConvLayer #0).  One warp per output time step; lane owns channels
+// {128*q + 4*lane + e}.
+template <typename T>
+__global__ void __launch_bounds__(256)
+w2v_conv0_kernel(const float* __restrict__ x, int n, int t_in, int t_out, const float* __restrict__ w,
+                 const float* __restrict__ b, const float* __restrict__ g, const float* __restrict__ be,
+                 T* __restrict__ y, long long y_pitch_rows) {
+  __shared__ __align__(16) float sw[10][512];
+  __shared__ __align__(16) float sb[512], sg[512], sbe[512];
+  for (int i = threadIdx.x; i < 5120; i += blockDim.x) sw[i % 10][i / 10] = w[i];   // w is [512][1][10]
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) { sb[i] = b[i]; sg[i] = g[i]; sbe[i] = be[i]; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int batch = blockIdx.y;
+  const float* xb = x + (long long)batch * t_in;
+  for (int t = blockIdx.x * 8 + wid; t < t_out; t += gridDim.x * 8) {
+    float xv[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) xv[k] = __ldg(xb + 5 * t + k);
+    float v[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c0 = 128 * q + 4 * lane;
+      float4 a = *reinterpret_cast<const float4*>(&sb[c0]);
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {
+        const float4 wk = *reinterpret_cast<const float4*>(&sw[k][c0]);
+        a.x = fmaf(wk.x, xv[k], a.x); a.y = fmaf(wk.y, xv[k], a.y); a.z = fmaf(wk.z, xv[k], a.z); a.w = fmaf(wk.w, xv[k], a.w);
+      }
+      v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.0f / 512.0f);
+    float q2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; q2 = fmaf(d, d, q2); }
+    const float rstd = rsqrtf(warp_sum(q2) * (1.0f / 512.0f) + 1e-5f);
+    T* yr = y + ((long long)batch * y_pitch_rows + t) * 512;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c0 = 128 * q + 4 * lane;
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = gelu_erf_f((v[4 * q + e] - mean) * rstd * sg[c0 + e] + sbe[c0 + e]);
+      if (sizeof(T) == 2) {
+        uint2 u;
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+        h2[0] = __floats2bfloat162_rn(o[0], o[1]);
+        h2[1] = __floats2bfloat162_rn(o[2], o[3]);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(yr) + c0) = u;
+      } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(yr) + c0) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm rows (warp per row), optional pre-add and GELU
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const T* __restrict__ x, long long rows, int c, long long ldx, const T* __restrict__ add,
+                 long long add_rows, const float* __restrict__ g, const float* __restrict__ b, float eps, int act,
+                 T* __restrict__ y, long long ldy) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int chunks = c / 256;   // c in {256,512,768,1024}
+  float v[4][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < chunks) {
+      Vec8<T>::load(x + row * ldx + j * 256 + lane * 8, v[j]);
+      if (add) {
+        float a[8];
+        Vec8<T>::load(add + (row % add_rows) * c + j * 256 + lane * 8, a);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[j][e] += a[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[j][e];
+    }
+  }
+  const float mean = warp_sum(s) / (float)c;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < chunks)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = v[j][e] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) / (float)c + eps);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < chunks) {
+      float o[8];
+      const int c0 = j * 256 + lane * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float t = (v[j][e] - mean) * rstd * g[c0 + e] + b[c0 + e];
+        o[e] = act == ACT_GELU_L ? gelu_erf_f(t) : t;
+      }
+      Vec8<T>::store(y + row * ldy + c0, o);
+    }
+  }
+}
+
+template <typename T>
+__global__ void add_rows_kernel(const T* __restrict__ x, long long rows, int c, const T* __restrict__ add,
+                                long long add_rows, T* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c8 = c / 8;
+  if (i >= rows * c8) return;
+  const long long r = i / c8;
+  const int cc = (int)(i % c8) * 8;
+  float a[8], bb[8];
+  Vec8<T>::load(x + r * c + cc, a);
+  Vec8<T>::load(add + (r % add_rows) * c + cc, bb);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] += bb[e];
+  Vec8<T>::store(y + r * c + cc, a);
+}
+
+// ------------------------------------------------------------------ multi-head self-attention, T tokens, no mask
+// (HF Wav2Vec2Attention eval path; attention_layers.py:10-38).  One CTA per (window, head, 32-query
+// tile); K and V of the head live in shared memory as fp32 (K rows padded by 1 float so that the
+// per-lane key reads are bank-conflict free); one warp finishes one query at a time.
+template <typename T, int DH>
+__global__ void __launch_bounds__(256)
+attention_kernel(const T* __restrict__ qkv, int t, int heads, float scale, T* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* sk = sm;                                  // [t][DH+1]
+  float* sv = sm + (size_t)t * (DH + 1);           // [t][DH]
+  float* sq = sv + (size_t)t * DH;                 // [8 warps][DH]
+  float* sp = sq + 8 * DH;                         // [8 warps][t rounded to 32]
+  const int tp = (t + 31) & ~31;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long row_stride = 3ll * heads * DH;
+  const T* base = qkv + (long long)b * t * row_stride;
+  for (int i = threadIdx.x; i < t * DH; i += blockDim.x) {
+    const int j = i / DH, d = i % DH;
+    sk[j * (DH + 1) + d] = to_f32(base[j * row_stride + (long long)(heads + head) * DH + d]);
+    sv[j * DH + d] = to_f32(base[j * row_stride + (long long)(2 * heads + head) * DH + d]);
+  }
+  __syncthreads();
+  const int q_end = min(t, (int)(blockIdx.x + 1) * 32);
+  for (int qi = blockIdx.x * 32 + wid; qi < q_end; qi += 8) {
+    for (int d = lane; d < DH; d += 32) sq[wid * DH + d] = to_f32(base[qi * row_stride + (long long)head * DH + d]) * scale;
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j < tp; j += 32) {
+      float s = -INFINITY;
+      if (j < t) {
+        s = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < DH; ++d) s = fmaf(sq[wid * DH + d], sk[j * (DH + 1) + d], s);
+      }
+      sp[wid * tp + j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < tp; j += 32) {
+      const float e = j < t ? expf(sp[wid * tp + j] - mx) : 0.f;
+      sp[wid * tp + j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = 1.0f / sum;
+    for (int d = lane; d < DH; d += 32) {
+      float o = 0.f;
+      for (int j = 0; j < t; ++j) o = fmaf(sp[wid * tp + j], sv[j * DH + d], o);
+      out[((long long)b * t + qi) * heads * DH + head * DH + d] = from_f32<T>(o * inv);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ audio head pools (audio_8_cl.py:146-159)
+template <typename T>
+__global__ void maxpool1d5_relu_kernel(const T* __restrict__ x, int n, int t, int c, int to, T* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * to * c) return;
+  const int cc = (int)(i % c);
+  const int ot = (int)((i / c) % to);
+  const int b = (int)(i / ((long long)c * to));
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) m = fmaxf(m, to_f32(x[((long long)b * t + ot * 5 + k) * c + cc]));
+  y[i] = from_f32<T>(fmaxf(m, 0.f));
+}
+template <typename T>
+__global__ void avgpool1d_relu_kernel(const T* __restrict__ x, int n, int t, int c, T* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * c) return;
+  const int cc = (int)(i % c);
+  const int b = (int)(i / c);
+  float s = 0.f;
+  for (int k = 0; k < t; ++k) s += to_f32(x[((long long)b * t + k) * c + cc]);
+  y[i] = from_f32<T>(fmaxf(s / (float)t, 0.f));
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ x, long long n, TD* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = from_f32<TD>(to_f32(x[i]));
+}
+
+}  // namespace avcer
+
+using namespace avcer;
+typedef __nv_bfloat16 bf16;
+
+#define AVCER_DISPATCH(dtype, ...)                                              \
+  do {                                                                          \
+    if ((dtype) == AVCER_BF16) { using T = bf16; __VA_ARGS__; }                 \
+    else if ((dtype) == AVCER_F32) { using T = float; __VA_ARGS__; }            \
+    else return set_error("unknown dtype %d", (int)(dtype));                    \
+  } while (0)
+
+static inline unsigned blocks_for(long long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
+
+extern "C" int avcer_maxpool3x3s2(const void* x, int n, int h, int w, int c, void* y, int dtype, void* stream) {
+  AVCER_REQUIRE(c % 8 == 0 && h >= 3 && w >= 3, "maxpool3x3s2: bad shape");
+  const int ho = (h - 3) / 2 + 1, wo = (w - 3) / 2 + 1;
+  const long long total = (long long)n * ho * wo * (c / 8);
+  if (total == 0) return 0;
+  AVCER_DISPATCH(dtype, (maxpool3x3s2_kernel<T><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(
+                            (const T*)x, n, h, w, c, ho, wo, (T*)y)));
+  return check_launch("maxpool3x3s2");
+}
+
+extern "C" int avcer_avgpool(const void* x, int n, int hw, int c, void* y, int dtype, void* stream) {
+  AVCER_REQUIRE(c % 8 == 0 && hw > 0, "avgpool: bad shape");
+  const long long total = (long long)n * (c / 8);
+  if (total == 0) return 0;
+  AVCER_DISPATCH(dtype, (avgpool_kernel<T><<<blocks_for(total, 128), 128, 0, as_stream(stream)>>>((const T*)x, n, hw, c, (T*)y)));
+  return check_launch("avgpool");
+}
+
+extern "C" int avcer_small_linear(const void* x, int64_t n, int k, const float* w, const float* b, int m, int softmax,
+                                  float* y, int dtype, void* stream) {
+  AVCER_REQUIRE(m >= 1 && m <= 8 && k > 0, "small_linear: m must be in [1,8]");
+  if (n == 0) return 0;
+  AVCER_DISPATCH(dtype, (small_linear_kernel<T><<<blocks_for(n * 32, 256), 256, 0, as_stream(stream)>>>(
+                            (const T*)x, n, k, w, b, m, softmax, y)));
+  return check_launch("small_linear");
+}
+
+extern "C" int avcer_lstm_cell(const float* xproj, const int32_t* xidx, const float* hproj, float* c, void* h_out,
+                               int64_t ldh, int64_t n, int hidden, int first, int dtype, void* stream) {
+  AVCER_REQUIRE(hidden > 0 && ldh >= hidden, "lstm_cell: bad shape");
+  const long long total = n * hidden;
+  if (total == 0) return 0;
+  AVCER_DISPATCH(dtype, (lstm_cell_kernel<T><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(
+                            xproj, xidx, hproj, c, (T*)h_out, ldh, n, hidden, first)));
+  return check_launch("lstm_cell");
+}
+
+extern "C" int avcer_audio_normalize_windows(const float* wav, int64_t L, const int64_t* starts, int n_win, int win,
+                                             int pad_mode, float* out, void* stream) {
+  AVCER_REQUIRE(pad_mode >= 0 && pad_mode <= 2 && win > 0, "audio_normalize_windows: bad arguments");
+  if (n_win == 0) return 0;
+  audio_normalize_kernel<<<n_win, 512, 0, as_stream(stream)>>>(wav, L, (const long long*)starts, win, pad_mode, out);
+  return check_launch("audio_normalize_windows");
+}
+
+extern "C" int avcer_w2v_conv0_ln_gelu(const float* x, int n, int t_in, const float* w, const float* b,
+                                       const float* ln_g, const float* ln_b, void* y, int64_t y_pitch_rows, int dtype,
+                                       void* stream) {
+  AVCER_REQUIRE(t_in >= 10, "w2v_conv0: t_in too small");
+  const int t_out = (t_in - 10) / 5 + 1;
+  AVCER_REQUIRE(y_pitch_rows >= t_out, "w2v_conv0: y pitch too small");
+  if (n == 0) return 0;
+  int gx = (t_out + 7) / 8;
+  if (gx > 400) gx = 400;
+  dim3 grid(gx, n);
+  AVCER_DISPATCH(dtype, (w2v_conv0_kernel<T><<<grid, 256, 0, as_stream(stream)>>>(x, n, t_in, t_out, w, b, ln_g, ln_b,
+                                                                                 (T*)y, y_pitch_rows)));
+  return check_launch("w2v_conv0");
+}
+
+extern "C" int avcer_layernorm(const void* x, int64_t rows, int c, int64_t ldx, const void* add, int64_t add_rows,
+                               const float* g, const float* b, float eps, int act, void* y, int64_t ldy, int dtype,
+                               void* stream) {
+  AVCER_REQUIRE(c % 256 == 0 && c <= 1024, "layernorm: c must be a multiple of 256, at most 1024");
+  AVCER_REQUIRE(add == nullptr || add_rows > 0, "layernorm: add_rows must be > 0 with add");
+  if (rows == 0) return 0;
+  AVCER_DISPATCH(dtype, (layernorm_kernel<T><<<blocks_for(rows * 32, 256), 256, 0, as_stream(stream)>>>(
+                            (const T*)x, rows, c, ldx, (const T*)add, add_rows > 0 ? add_rows : 1, g, b, eps, act,
+                            (T*)y, ldy)));
+  return check_launch("layernorm");
+}
+
+extern "C" int avcer_add_rows(const void* x, int64_t rows, int c, const void* add, int64_t add_rows, void* y,
+                              int dtype, void* stream) {
+  AVCER_REQUIRE(c % 8 == 0 && add_rows > 0, "add_rows: bad shape");
+  const long long total = rows * (c / 8);
+  if (total == 0) return 0;
+  AVCER_DISPATCH(dtype, (add_rows_kernel<T><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(
+                            (const T*)x, rows, c, (const T*)add, add_rows, (T*)y)));
+  return check_launch("add_rows");
+}
+
+template <typename T, int DH>
+static int launch_attention(const void* qkv, int n, int t, int heads, float scale, void* out, cudaStream_t st) {
+  const int tp = (t + 31) & ~31;
+  const size_t smem = ((size_t)t * (DH + 1) + (size_t)t * DH + 8 * DH + 8 * tp) * sizeof(float);
+  AVCER_REQUIRE(smem <= 220 * 1024, "attention: T=%d too long for the shared-memory kernel", t);
+  auto kern = attention_kernel<T, DH>;
+  AVCER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((t + 31) / 32, heads, n);
+  kern<<<grid, 256, smem, st>>>((const T*)qkv, t, heads, scale, (T*)out);
+  return check_launch("attention");
+}
+
+extern "C" int avcer_attention(const void* qkv, int n, int t, int heads, int dh, float scale, void* out, int dtype,
+                               void* stream) {
+  AVCER_REQUIRE(dh == 32 || dh == 64, "attention: head dim must be 32 or 64");
+  if (n == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == AVCER_BF16) return dh == 64 ? launch_attention<bf16, 64>(qkv, n, t, heads, scale, out, st)
+                                           : launch_attention<bf16, 32>(qkv, n, t, heads, scale, out, st);
+  if (dtype == AVCER_F32) return dh == 64 ? launch_attention<float, 64>(qkv, n, t, heads, scale, out, st)
+                                          : launch_attention<float, 32>(qkv, n, t, heads, scale, out, st);
+  return set_error("attention: unknown dtype %d", dtype);
+}
+
+extern "C" int avcer_maxpool1d5_relu(const void* x, int n, int t, int c, void* y, int dtype, void* stream) {
+  const int to = t / 5;
+  const long long total = (long long)n * to * c;
+  if (total == 0) return 0;
+  AVCER_DISPATCH(dtype, (maxpool1d5_relu_kernel<T><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(
+                            (const T*)x, n, t, c, to, (T*)y)));
+  return check_launch("maxpool1d5_relu");
+}
+
+extern "C" int avcer_avgpool1d_relu(const void* x, int n, int t, int c, void* y, int dtype, void* stream) {
+  const long long total = (long long)n * c;
+  if (total == 0) return 0;
+  AVCER_DISPATCH(dtype, (avgpool1d_relu_kernel<T><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(
+                            (const T*)x, n, t, c, (T*)y)));
+  return check_launch("avgpool1d_relu");
+}
+
+extern "C" int avcer_cast(const void* x, int64_t n, int src_dtype, void* y, int dst_dtype, void* stream) {
+  if (n == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  const unsigned g = blocks_for(n, 256);
+  if (src_dtype == AVCER_F32 && dst_dtype == AVCER_BF16) cast_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)x, n, (bf16*)y);
+  else if (src_dtype == AVCER_BF16 && dst_dtype == AVCER_F32) cast_kernel<bf16, float><<<g, 256, 0, st>>>((const bf16*)x, n, (float*)y);
+  else if (src_dtype == AVCER_F32 && dst_dtype == AVCER_F32) cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)x, n, (float*)y);
+  else if (src_dtype == AVCER_BF16 && dst_dtype == AVCER_BF16) cast_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16*)x, n, (bf16*)y);
+  else return set_error("cast: unknown dtypes %d -> %d", src_dtype, dst_dtype);
+  return check_launch("cast");
+}

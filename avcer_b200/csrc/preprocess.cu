@@ -1,0 +1,153 @@
+// K1: face-crop preprocessing (reference: src/data/utils.py:19-39 pth_processing, called per frame
+// at src/get_prob_video.py:95-99, followed by the H2D copy at :108).
+//
+//   PIL resize((224,224), NEAREST) -> CHW u8 -> float32 -> channel flip (undoes the BGR2RGB of
+//   get_prob_video.py:97, so the tensor is in cv2's BGR byte order) -> subtract
+//   [91.4953, 103.8827, 131.0912] -> (no /255).
+//
+// The nearest-neighbour source index follows Pillow's affine-scale loop exactly: with
+// a = in/224.0 (double), o = a*0.5, idx[x] = (int)o, o += a  -- an incremental double
+// accumulation (not floor((x+.5)*a)), restated in resize_maps_kernel.
+//
+// Memory-bound: one CTA converts 4 output rows of one crop; source rows are staged through shared
+// memory with 16-byte loads and every global store is a fully coalesced 16-byte vector.
+#include "common.h"
+
+namespace avcer {
+
+constexpr int OUT = 224;
+constexpr int PADW = 232;     // padded row pitch (pixels) of layouts 1/2
+constexpr int PADH = 232;
+constexpr int PAD0 = 2;       // TF-"same" leading pad of the 7x7/2 stem (video.py:65-81)
+constexpr int ROWS = 4;       // output rows per CTA
+constexpr int MAX_STAGE_W = 1024;
+
+__constant__ float c_mean[3] = {91.4953f, 103.8827f, 131.0912f};
+
+__global__ void resize_maps_kernel(const int* __restrict__ src_h, const int* __restrict__ src_w, int n,
+                                   short* __restrict__ maps /*[n][2][224]: y map then x map*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 2) return;
+  const int crop = i >> 1, axis = i & 1;
+  const int in = axis == 0 ? src_h[crop] : src_w[crop];
+  const double a = (double)in / 224.0;
+  double o = __dmul_rn(a, 0.5);
+  short* m = maps + (size_t)crop * 2 * OUT + axis * OUT;
+  for (int x = 0; x < OUT; ++x) {
+    int v = (int)o;
+    if (v >= in) v = in - 1;          // Pillow skips such pixels; cannot happen for in >= 1
+    m[x] = (short)v;
+    o = __dadd_rn(o, a);
+  }
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256)
+preprocess_kernel(const uint8_t* __restrict__ src, const long long* __restrict__ offs, const int* __restrict__ src_h,
+                  const int* __restrict__ src_w, const short* __restrict__ maps, void* __restrict__ dst) {
+  __shared__ __align__(16) uint8_t rows[ROWS][MAX_STAGE_W * 3];
+  __shared__ short xmap[OUT];
+  const int crop = blockIdx.y;
+  const int y0 = blockIdx.x * ROWS;
+  const int sw = src_w ? src_w[crop] : OUT;
+  const int sh = src_h ? src_h[crop] : OUT;
+  (void)sh;
+  const uint8_t* base = src + (offs ? offs[crop] : (long long)crop * OUT * OUT * 3);
+  const short* cm = maps ? maps + (size_t)crop * 2 * OUT : nullptr;
+  const bool staged = sw <= MAX_STAGE_W;
+  const int row_bytes = sw * 3;
+
+  if (cm) for (int x = threadIdx.x; x < OUT; x += blockDim.x) xmap[x] = cm[OUT + x];
+  if (staged) {
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int sy = cm ? cm[y0 + r] : (y0 + r);
+      const uint8_t* rp = base + (long long)sy * row_bytes;
+      if (((reinterpret_cast<uintptr_t>(rp) & 15) == 0) && (row_bytes % 16 == 0)) {
+        const uint4* rp4 = reinterpret_cast<const uint4*>(rp);
+        uint4* sp4 = reinterpret_cast<uint4*>(rows[r]);
+        for (int i = threadIdx.x; i < row_bytes / 16; i += blockDim.x) sp4[i] = __ldg(rp4 + i);
+      } else {
+        for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) rows[r][i] = __ldg(rp + i);
+      }
+    }
+  }
+  __syncthreads();
+
+  auto fetch = [&](int r, int x, float (&v)[3]) {
+    const int sx = cm ? xmap[x] : x;
+    if (staged) {
+      const uint8_t* px = &rows[r][sx * 3];
+      v[0] = (float)px[0] - c_mean[0]; v[1] = (float)px[1] - c_mean[1]; v[2] = (float)px[2] - c_mean[2];
+    } else {
+      const int sy = cm ? cm[y0 + r] : (y0 + r);
+      const uint8_t* px = base + ((long long)sy * sw + sx) * 3;
+      v[0] = (float)__ldg(px) - c_mean[0]; v[1] = (float)__ldg(px + 1) - c_mean[1]; v[2] = (float)__ldg(px + 2) - c_mean[2];
+    }
+  };
+
+  if (LAYOUT == 1) {
+    // bf16 NHWC4, zero border: two pixels per 16-byte store
+    __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst) + (size_t)crop * PADH * PADW * 4;
+    for (int t = threadIdx.x; t < ROWS * (OUT / 2); t += blockDim.x) {
+      const int r = t / (OUT / 2), q = t % (OUT / 2);
+      float a[3], b[3];
+      fetch(r, 2 * q, a);
+      fetch(r, 2 * q + 1, b);
+      uint4 u;
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+      h2[0] = __floats2bfloat162_rn(a[0], a[1]);
+      h2[1] = __floats2bfloat162_rn(a[2], 0.f);
+      h2[2] = __floats2bfloat162_rn(b[0], b[1]);
+      h2[3] = __floats2bfloat162_rn(b[2], 0.f);
+      *reinterpret_cast<uint4*>(d + ((size_t)(y0 + r + PAD0) * PADW + PAD0 + 2 * q) * 4) = u;
+    }
+  } else if (LAYOUT == 2) {
+    float* d = static_cast<float*>(dst) + (size_t)crop * PADH * PADW * 4;
+    for (int t = threadIdx.x; t < ROWS * OUT; t += blockDim.x) {
+      const int r = t / OUT, x = t % OUT;
+      float a[3];
+      fetch(r, x, a);
+      *reinterpret_cast<float4*>(d + ((size_t)(y0 + r + PAD0) * PADW + PAD0 + x) * 4) = make_float4(a[0], a[1], a[2], 0.f);
+    }
+  } else {
+    // fp32 NCHW: the reference tensor itself
+    float* d = static_cast<float*>(dst) + (size_t)crop * 3 * OUT * OUT;
+    for (int t = threadIdx.x; t < ROWS * OUT * 3; t += blockDim.x) {
+      const int c = t / (ROWS * OUT), rem = t % (ROWS * OUT);
+      const int r = rem / OUT, x = rem % OUT;
+      float a[3];
+      fetch(r, x, a);
+      d[(size_t)c * OUT * OUT + (size_t)(y0 + r) * OUT + x] = a[c];
+    }
+  }
+}
+
+}  // namespace avcer
+
+using namespace avcer;
+
+extern "C" int avcer_preprocess_maps(const int32_t* src_h, const int32_t* src_w, int n, int16_t* maps, void* stream) {
+  AVCER_REQUIRE(n >= 0, "preprocess_maps: negative n");
+  if (n == 0) return 0;
+  resize_maps_kernel<<<(2 * n + 63) / 64, 64, 0, as_stream(stream)>>>(src_h, src_w, n, maps);
+  return check_launch("resize_maps_kernel");
+}
+
+extern "C" int avcer_preprocess_u8(const uint8_t* src, const int64_t* src_offsets, const int32_t* src_h,
+                                   const int32_t* src_w, const int16_t* maps, int n, void* dst, int dst_layout,
+                                   void* stream) {
+  AVCER_REQUIRE(n >= 0, "preprocess: negative n");
+  AVCER_REQUIRE(dst_layout >= 0 && dst_layout <= 2, "preprocess: unknown layout %d", dst_layout);
+  AVCER_REQUIRE((src_h == nullptr) == (src_w == nullptr) && (src_h == nullptr) == (maps == nullptr),
+                "preprocess: src_h, src_w and maps must be given together (or all NULL for packed 224x224 crops)");
+  if (n == 0) return 0;
+  dim3 grid(OUT / ROWS, n);
+  AVCER_REQUIRE(n <= 65535, "preprocess: at most 65535 crops per call");
+  cudaStream_t st = as_stream(stream);
+  const long long* offs = reinterpret_cast<const long long*>(src_offsets);
+  if (dst_layout == 0) preprocess_kernel<0><<<grid, 256, 0, st>>>(src, offs, src_h, src_w, maps, dst);
+  else if (dst_layout == 1) preprocess_kernel<1><<<grid, 256, 0, st>>>(src, offs, src_h, src_w, maps, dst);
+  else preprocess_kernel<2><<<grid, 256, 0, st>>>(src, offs, src_h, src_w, maps, dst);
+  return check_launch("preprocess_kernel");
+}

@@ -1,0 +1,264 @@
+// tcgen05 implicit-GEMM kernel for sm_100a: one kernel serves every dense contraction on the
+// hot path -- ResNet-50 1x1 / strided 1x1 / 3x3 "same" / 7x7 stem convolutions (reference:
+// src/architectures/video.py:13-35,98-100,141-148), the wav2vec2 conv1d feature extractor,
+// grouped positional conv and all Linear layers (audio_8_cl.py:131-190, attention_layers.py:80-144).
+//
+//   D[row, co] = act( sum_{tap, c} A[row @ tap, c] * Wt[co, tap*Cin + c] + bias[co] (+ residual[row, co]) )
+//
+// * A (activations, channels-last bf16) is fetched by TMA through a rank-5 tiled tensor map
+//   (c, w, h, n, t).  An M tile is a *box* of bw*bh*bn <= 128 output positions; filter taps are
+//   coordinate offsets, and "same" zero padding is TMA out-of-bounds zero fill.
+// * Wt (weights, [Cout, taps*Cin] bf16, K contiguous) is fetched by a rank-2 TMA.
+// * Both land in shared memory in the 128B (or 64B) swizzled K-major layout that
+//   tcgen05.mma consumes directly; accumulators live in TMEM (2 x BN fp32 columns, double
+//   buffered so the epilogue of tile i overlaps the MMAs of tile i+1).
+// * Warp roles: warp0 = TMA producer, warp1 = MMA issuer (one elected lane), warp2 = TMEM
+//   allocator, warps4-7 = epilogue (tcgen05.ld -> bias/residual/activation -> global).
+// * Persistent: grid = min(#tiles, #SM); tiles are strided across CTAs, N fastest so CTAs of
+//   one wave share the same activation box in L2.
+#pragma once
+#include "ptx.cuh"
+
+namespace avcer {
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+struct TcGemmParams {
+  int num_tiles, tiles_n;
+  int bw, bh, bn;          // box extents of one M tile (bw*bh*bn <= 128)
+  int tw, th, tn;          // tiles along w / h / n
+  int W, H, NB;            // valid output extents (epilogue mask)
+  int taps_w, taps_h;      // filter taps
+  int off_w, off_h;        // coordinate offset of tap (0,0)  (= -padding)
+  int tap_h_in_dim4;       // 1: the h-tap index is coordinate 4 of the A map (stem: strided rows)
+  int kchunks;             // K chunks (of BK) per tap
+  int a_c0_per_ntile;      // channel-coordinate shift per N tile (grouped conv), else 0
+  int Cout;
+  long long out_sw, out_sh, out_sn;   // output element strides of (w, h, n); channels contiguous
+  long long res_sw, res_sh, res_sn;   // residual strides (same meaning)
+  const float* bias;                  // [Cout] or nullptr
+  const __nv_bfloat16* residual;      // or nullptr
+  void* out;                          // bf16 (or fp32 when OUT_F32)
+  int act;
+  int res_after_act;     // 0: act(acc + bias + res)   1: act(acc + bias) + res
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+template <int BN, int BK>
+struct TcGemmCfg {
+  static constexpr int BM = 128;
+  static constexpr int A_STAGE = BM * BK * 2;
+  static constexpr int B_STAGE = BN * BK * 2;
+  static constexpr int STAGE = A_STAGE + B_STAGE;
+  static constexpr int BUDGET = 200 * 1024;
+  static constexpr int STAGES = (BUDGET / STAGE) > 8 ? 8 : (BUDGET / STAGE);
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr uint32_t LAYOUT = (BK == 64) ? 2u : 4u;      // SWIZZLE_128B : SWIZZLE_64B
+  static constexpr uint32_t SBO = 8u * BK * 2u;                 // 8-row group pitch
+  static_assert(BK == 64 || BK == 32, "BK must be one swizzle row");
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "");
+};
+
+template <int BN, int BK, bool OUT_F32>
+__global__ void __launch_bounds__(256, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcGemmParams p) {
+  using Cfg = TcGemmCfg<BN, BK>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 4];
+  __shared__ uint32_t tmem_slot_s;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + Cfg::STAGES * Cfg::A_STAGE;
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rows = p.bw * p.bh * p.bn;
+  const int k_iters = p.taps_w * p.taps_h * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);   // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&tmem_slot_s), Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_s);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = static_cast<uint32_t>(rows) * BK * 2 + Cfg::B_STAGE;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n;
+        const int mt = tile / p.tiles_n;
+        const int w0 = (mt % p.tw) * p.bw;
+        const int h0 = ((mt / p.tw) % p.th) * p.bh;
+        const int n0 = (mt / (p.tw * p.th)) * p.bn;
+        const int c_shift = nt * p.a_c0_per_ntile;
+        int kcol = 0;
+        for (int ty = 0; ty < p.taps_h; ++ty) {
+          for (int tx = 0; tx < p.taps_w; ++tx) {
+            for (int kc = 0; kc < p.kchunks; ++kc, kcol += BK) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+              tma_load_5d(a_base + stage * Cfg::A_STAGE, &tmA, full_bar(stage), kc * BK + c_shift,
+                          w0 + p.off_w + tx, h0 + p.off_h + (p.tap_h_in_dim4 ? 0 : ty), n0,
+                          p.tap_h_in_dim4 ? ty : 0);
+              tma_load_2d(b_base + stage * Cfg::B_STAGE, &tmB, full_bar(stage), kcol, nt * BN);
+              if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_kmajor(a_base + stage * Cfg::A_STAGE, Cfg::SBO, Cfg::LAYOUT);
+          const uint64_t bdesc = umma_desc_kmajor(b_base + stage * Cfg::B_STAGE, Cfg::SBO, Cfg::LAYOUT);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 B per K=16 step inside the swizzle row: start-address field += 2
+            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;               // row of the tile owned by this thread
+    const int dw = r % p.bw;
+    const int dh = (r / p.bw) % p.bh;
+    const int dn = r / (p.bw * p.bh);
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1u;
+      const int nt = tile % p.tiles_n;
+      const int mt = tile / p.tiles_n;
+      const int w = (mt % p.tw) * p.bw + dw;
+      const int h = ((mt / p.tw) % p.th) * p.bh + dh;
+      const int n = (mt / (p.tw * p.th)) * p.bn + dn;
+      const bool valid = (r < rows) && (w < p.W) && (h < p.H) && (n < p.NB);
+      const long long out_off = w * p.out_sw + h * p.out_sh + n * p.out_sn;
+      const long long res_off = w * p.res_sw + h * p.res_sh + n * p.res_sn;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
+        tmem_ld_wait();
+        const int co = nt * BN + c * 32;
+        if (valid && co < p.Cout) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co + j));
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            }
+          }
+          auto apply_act = [&]() {
+            if (p.act == ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+            } else if (p.act == ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            }
+          };
+          if (p.res_after_act) apply_act();
+          if (p.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + res_off + co);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = __ldg(rp + j);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t = __bfloat1622float2(h2[e]);
+                f[j * 8 + e * 2] += t.x;
+                f[j * 8 + e * 2 + 1] += t.y;
+              }
+            }
+          }
+          if (!p.res_after_act) apply_act();
+          if (OUT_F32) {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + co);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_off + co);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
+              op[j] = u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace avcer

@@ -1,0 +1,300 @@
+"""Tensor-level wrappers over the C ABI (torch tensors in, torch tensors out).
+
+PyTorch is plumbing here: it owns device memory and streams; every computation below is a
+hand-written kernel of libavcer_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32, ContractDesc, check
+
+__all__ = [
+    "F32", "BF16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "dtype_code", "torch_dtype", "contract", "conv2d_nhwc",
+    "linear", "preprocess", "fuse_compound", "softmax7", "window_to_frame_mean", "gather_rows", "maxpool3x3s2",
+    "avgpool", "small_linear", "lstm_cell", "audio_normalize_windows", "w2v_conv0_ln_gelu", "layernorm", "add_rows",
+    "attention", "maxpool1d5_relu", "avgpool1d_relu", "cast",
+]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.bfloat16:
+        return BF16
+    if dt == torch.float32:
+        return F32
+    raise TypeError(f"unsupported dtype {dt}")
+
+
+def torch_dtype(code: int) -> torch.dtype:
+    return torch.bfloat16 if code == BF16 else torch.float32
+
+
+def _cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise _lib.AvcerError(f"{name} must be a CUDA tensor (avcer_b200 has no CPU path)")
+
+
+# ----------------------------------------------------------------------------------------- contraction
+def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], wt: torch.Tensor,
+             bias: Optional[torch.Tensor], out: torch.Tensor, out_stride: Sequence[int], W: int, H: int, NB: int,
+             cin: int, cout: int, taps_w: int = 1, taps_h: int = 1, off_w: int = 0, off_h: int = 0,
+             tap_h_in_dim4: bool = False, group_cin_shift: int = 0, residual: Optional[torch.Tensor] = None,
+             res_stride: Optional[Sequence[int]] = None, act: int = ACT_NONE, res_after_act: bool = False,
+             a_offset: int = 0) -> torch.Tensor:
+    """Generic implicit GEMM (see avcer_contract in include/avcer_b200.h)."""
+    _cuda(a, "a")
+    d = ContractDesc()
+    code = dtype_code(a.dtype)
+    d.a = a.data_ptr() + a_offset * a.element_size()
+    for i in range(5):
+        d.a_dim[i] = int(a_dim[i])
+        d.a_stride[i] = int(a_stride[i])
+    assert wt.dtype == a.dtype and wt.is_contiguous()
+    d.wt = wt.data_ptr()
+    d.bias = _ptr(bias)
+    d.residual = _ptr(residual)
+    d.out = out.data_ptr()
+    rs = res_stride if res_stride is not None else out_stride
+    for i in range(3):
+        d.out_stride[i] = int(out_stride[i])
+        d.res_stride[i] = int(rs[i])
+    d.W, d.H, d.NB, d.cin, d.cout = W, H, NB, cin, cout
+    d.taps_w, d.taps_h, d.off_w, d.off_h = taps_w, taps_h, off_w, off_h
+    d.tap_h_in_dim4 = int(tap_h_in_dim4)
+    d.group_cin_shift = group_cin_shift
+    d.act = act
+    d.res_after_act = int(res_after_act)
+    d.dtype = code
+    d.out_f32 = int(code == BF16 and out.dtype == torch.float32)
+    check(_lib.load().avcer_contract(ctypes.byref(d), _stream()))
+    return out
+
+
+def conv2d_nhwc(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, kh: int, kw: int, stride: int = 1,
+                pad_h: int = 0, pad_w: int = 0, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: [N,H,W,C] contiguous; wt: [Cout, kh*kw*C] (tap-major, channel-minor)."""
+    n, h, w, c = x.shape
+    cout = wt.shape[0]
+    assert wt.shape[1] == kh * kw * c
+    ho = (h + 2 * pad_h - kh) // stride + 1
+    wo = (w + 2 * pad_w - kw) // stride + 1
+    if out is None:
+        out = torch.empty((n, ho, wo, cout), device=x.device, dtype=x.dtype)
+    if stride == 1:
+        a_dim = (c, w, h, n, 1)
+        a_stride = (1, c, w * c, h * w * c, n * h * w * c)
+    else:
+        assert kh == 1 and kw == 1 and pad_h == 0 and pad_w == 0, "strided conv only for 1x1"
+        a_dim = (c, wo, ho, n, 1)
+        a_stride = (1, stride * c, stride * w * c, h * w * c, n * h * w * c)
+    return contract(a=x, a_dim=a_dim, a_stride=a_stride, wt=wt, bias=bias, out=out,
+                    out_stride=(cout, wo * cout, ho * wo * cout), W=wo, H=ho, NB=n, cin=c, cout=cout, taps_w=kw,
+                    taps_h=kh, off_w=-pad_w, off_h=-pad_h, residual=residual, act=act)
+
+
+def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, residual: Optional[torch.Tensor] = None,
+           act: int = ACT_NONE, res_after_act: bool = False, out: Optional[torch.Tensor] = None,
+           out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """x: [M, K] (row pitch = x.stride(0)), wt: [N, K]; returns [M, N]."""
+    m, k = x.shape
+    n = wt.shape[0]
+    assert x.stride(1) == 1
+    ld = x.stride(0)
+    if out is None:
+        out = torch.empty((m, n), device=x.device, dtype=out_dtype or x.dtype)
+    big = max(ld * m, 8)
+    return contract(a=x, a_dim=(k, m, 1, 1, 1), a_stride=(1, ld, big, big, big), wt=wt, bias=bias, out=out,
+                    out_stride=(out.stride(0), 0, 0), W=m, H=1, NB=1, cin=k, cout=n, residual=residual,
+                    res_stride=None if residual is None else (residual.stride(0), 0, 0), act=act,
+                    res_after_act=res_after_act)
+
+
+# ----------------------------------------------------------------------------------------- K1
+PAD_HW = 232
+
+
+def preprocess(src: torch.Tensor, n: int, dst: torch.Tensor, layout: int, *, offsets: Optional[torch.Tensor] = None,
+               heights: Optional[torch.Tensor] = None, widths: Optional[torch.Tensor] = None,
+               maps: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """src: flat uint8 device buffer of BGR HWC crops. layout 0: f32 NCHW, 1: bf16 NHWC4 padded, 2: f32 NHWC4 padded."""
+    _cuda(src, "src")
+    lib = _lib.load()
+    if heights is not None and maps is None:
+        maps = torch.empty((n, 2, 224), device=src.device, dtype=torch.int16)
+        check(lib.avcer_preprocess_maps(heights.data_ptr(), widths.data_ptr(), n, maps.data_ptr(), _stream()))
+    check(lib.avcer_preprocess_u8(src.data_ptr(), _ptr(offsets), _ptr(heights), _ptr(widths), _ptr(maps), n,
+                                  dst.data_ptr(), layout, _stream()))
+    return dst
+
+
+# ----------------------------------------------------------------------------------------- K4 + glue
+def fuse_compound(p_vs: torch.Tensor, p_vd: torch.Tensor, p_a: torch.Tensor, weights_1, weights_2,
+                  ce_weights_type: bool, ce_mask: bool, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Returns int64 labels [4, n] = (AV, VS, VD, A) compound-expression argmax."""
+    _cuda(p_vs, "p_vs")
+    n = p_vs.shape[0]
+    assert p_vs.shape == p_vd.shape == p_a.shape == (n, 7)
+    assert p_vs.dtype == p_vd.dtype == p_a.dtype
+    for t in (p_vs, p_vd, p_a):
+        assert t.is_contiguous()
+    if labels is None:
+        labels = torch.empty((4, n), device=p_vs.device, dtype=torch.int64)
+    w1 = w2 = None
+    if weights_1:
+        w1a = np.ascontiguousarray(np.asarray(weights_1, dtype=np.float64).reshape(3, 7))
+        w2a = np.ascontiguousarray(np.asarray(weights_2, dtype=np.float64).reshape(3))
+        w1 = w1a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        w2 = w2a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    lib = _lib.load()
+    fn = lib.avcer_fuse_compound if p_vs.dtype == torch.float32 else lib.avcer_fuse_compound_f64
+    check(fn(p_vs.data_ptr(), p_vd.data_ptr(), p_a.data_ptr(), n, w1, w2, int(bool(ce_weights_type)),
+             int(bool(ce_mask)), labels.data_ptr(), _stream()))
+    return labels
+
+
+def softmax7(x: torch.Tensor) -> torch.Tensor:
+    """Row softmax over the first 7 columns of x [n, >=7] (f32 or f64)."""
+    _cuda(x, "x")
+    n, ld = x.shape
+    assert x.is_contiguous()
+    y = torch.empty((n, 7), device=x.device, dtype=x.dtype)
+    lib = _lib.load()
+    fn = lib.avcer_softmax7 if x.dtype == torch.float32 else lib.avcer_softmax7_f64
+    check(fn(x.data_ptr(), n, ld, y.data_ptr(), _stream()))
+    return y
+
+
+def window_to_frame_mean(logits: torch.Tensor, f_lo: torch.Tensor, f_hi: torch.Tensor, n_frames: int) -> torch.Tensor:
+    _cuda(logits, "logits")
+    n_win, ncls = logits.shape
+    out = torch.empty((n_frames, ncls), device=logits.device, dtype=torch.float32)
+    check(_lib.load().avcer_window_to_frame_mean(logits.data_ptr(), n_win, ncls, f_lo.data_ptr(), f_hi.data_ptr(),
+                                                 n_frames, out.data_ptr(), _stream()))
+    return out
+
+
+def gather_rows(src: torch.Tensor, index: Optional[torch.Tensor], n_out: int, perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(src, "src")
+    ncols = src.shape[1] if perm is None else perm.numel()
+    assert perm is None or ncols == src.shape[1]
+    out = torch.empty((n_out, ncols), device=src.device, dtype=torch.float32)
+    check(_lib.load().avcer_gather_rows(src.data_ptr(), _ptr(index), n_out, ncols, _ptr(perm), out.data_ptr(), _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------- small layers
+def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = x.shape
+    y = torch.empty((n, (h - 3) // 2 + 1, (w - 3) // 2 + 1, c), device=x.device, dtype=x.dtype)
+    check(_lib.load().avcer_maxpool3x3s2(x.data_ptr(), n, h, w, c, y.data_ptr(), dtype_code(x.dtype), _stream()))
+    return y
+
+
+def avgpool(x: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = x.shape
+    y = torch.empty((n, c), device=x.device, dtype=x.dtype)
+    check(_lib.load().avcer_avgpool(x.data_ptr(), n, h * w, c, y.data_ptr(), dtype_code(x.dtype), _stream()))
+    return y
+
+
+def small_linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], softmax: bool = False) -> torch.Tensor:
+    n, k = x.shape
+    m = w.shape[0]
+    assert x.is_contiguous() and w.dtype == torch.float32 and w.is_contiguous()
+    y = torch.empty((n, m), device=x.device, dtype=torch.float32)
+    check(_lib.load().avcer_small_linear(x.data_ptr(), n, k, w.data_ptr(), _ptr(b), m, int(softmax), y.data_ptr(),
+                                         dtype_code(x.dtype), _stream()))
+    return y
+
+
+def lstm_cell(xproj: Optional[torch.Tensor], xidx: Optional[torch.Tensor], hproj: Optional[torch.Tensor],
+              c: torch.Tensor, h_out: torch.Tensor, hidden: int, first: bool) -> None:
+    n = c.shape[0]
+    check(_lib.load().avcer_lstm_cell(_ptr(xproj), _ptr(xidx), _ptr(hproj), c.data_ptr(), h_out.data_ptr(),
+                                      h_out.stride(0), n, hidden, int(first), dtype_code(h_out.dtype), _stream()))
+
+
+PAD_MODES = {"mean": 0, "constant": 1, "repeat": 2}
+
+
+def audio_normalize_windows(wav: torch.Tensor, starts: torch.Tensor, win: int, pad_mode: str) -> torch.Tensor:
+    _cuda(wav, "wav")
+    n_win = starts.numel()
+    out = torch.empty((n_win, win), device=wav.device, dtype=torch.float32)
+    check(_lib.load().avcer_audio_normalize_windows(wav.data_ptr(), wav.numel(), starts.data_ptr(), n_win, win,
+                                                    PAD_MODES[pad_mode], out.data_ptr(), _stream()))
+    return out
+
+
+def w2v_conv0_ln_gelu(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, g: torch.Tensor, be: torch.Tensor,
+                      y: torch.Tensor) -> torch.Tensor:
+    n, t_in = x.shape
+    check(_lib.load().avcer_w2v_conv0_ln_gelu(x.data_ptr(), n, t_in, w.data_ptr(), b.data_ptr(), g.data_ptr(),
+                                              be.data_ptr(), y.data_ptr(), y.shape[1], dtype_code(y.dtype), _stream()))
+    return y
+
+
+def layernorm(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, eps: float, *, act: int = ACT_NONE,
+              add: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: [rows, c] with row pitch x.stride(0)."""
+    rows, c = x.shape
+    if out is None:
+        out = torch.empty((rows, c), device=x.device, dtype=x.dtype)
+    check(_lib.load().avcer_layernorm(x.data_ptr(), rows, c, x.stride(0), _ptr(add), 0 if add is None else add.shape[0],
+                                      g.data_ptr(), b.data_ptr(), eps, act, out.data_ptr(), out.stride(0),
+                                      dtype_code(x.dtype), _stream()))
+    return out
+
+
+def add_rows(x: torch.Tensor, add: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    rows, c = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.load().avcer_add_rows(x.data_ptr(), rows, c, add.data_ptr(), add.shape[0], out.data_ptr(),
+                                     dtype_code(x.dtype), _stream()))
+    return out
+
+
+def attention(qkv: torch.Tensor, n: int, t: int, heads: int, dh: int, scale: float,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qkv: [n*t, 3*heads*dh] packed (q | k | v); returns [n*t, heads*dh]."""
+    assert qkv.is_contiguous()
+    if out is None:
+        out = torch.empty((n * t, heads * dh), device=qkv.device, dtype=qkv.dtype)
+    check(_lib.load().avcer_attention(qkv.data_ptr(), n, t, heads, dh, scale, out.data_ptr(), dtype_code(qkv.dtype), _stream()))
+    return out
+
+
+def maxpool1d5_relu(x: torch.Tensor) -> torch.Tensor:
+    n, t, c = x.shape
+    y = torch.empty((n, t // 5, c), device=x.device, dtype=x.dtype)
+    check(_lib.load().avcer_maxpool1d5_relu(x.data_ptr(), n, t, c, y.data_ptr(), dtype_code(x.dtype), _stream()))
+    return y
+
+
+def avgpool1d_relu(x: torch.Tensor) -> torch.Tensor:
+    n, t, c = x.shape
+    y = torch.empty((n, c), device=x.device, dtype=x.dtype)
+    check(_lib.load().avcer_avgpool1d_relu(x.data_ptr(), n, t, c, y.data_ptr(), dtype_code(x.dtype), _stream()))
+    return y
+
+
+def cast(x: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
+    y = torch.empty(x.shape, device=x.device, dtype=dt)
+    check(_lib.load().avcer_cast(x.data_ptr(), x.numel(), dtype_code(x.dtype), y.data_ptr(), dtype_code(dt), _stream()))
+    return y

@@ -1,0 +1,238 @@
+"""Seeded synthetic weights and inputs of the named architectures (no network, no checkpoints).
+
+The reference loads `src/weights/FER_static_ResNet50_AffectNet.pt`, `FER_dinamic_LSTM_Aff-Wild2.pt`
+(get_prob_video.py:22-25,51-54) and `epoch_63.pth` / `epoch_51.pth` (get_prob_audio_8_cl.py:58-65);
+none of them ship with the repository.  These generators produce state_dicts with exactly the
+reference's keys and shapes so that the same dict can be loaded into the
+reference classes (oracle validation) and packed for the CUDA path.
+
+init="default" mimics PyTorch's default initialisers (nearly input-independent outputs);
+init="spread" uses He-normal convolutions, perturbed BatchNorm statistics and scaled heads so that
+the per-frame probabilities actually vary with the input.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict
+
+import numpy as np
+import torch
+
+VS_BLOCKS = (3, 4, 6, 3)
+VS_PLANES = (64, 128, 256, 512)
+
+
+def _gen(seed: int) -> torch.Generator:
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    return g
+
+
+def _kaiming_uniform(shape, fan_in, g):
+    # PyTorch default for conv/linear weights: U(-1/sqrt(fan_in), 1/sqrt(fan_in))
+    bound = 1.0 / math.sqrt(fan_in)
+    return (torch.rand(shape, generator=g) * 2 - 1) * bound
+
+
+def _bn(prefix, c, sd, g, init, gamma_scale=1.0, var=1.0):
+    if init == "default":
+        sd[prefix + ".weight"] = torch.ones(c)
+        sd[prefix + ".bias"] = torch.zeros(c)
+        sd[prefix + ".running_mean"] = torch.zeros(c)
+        sd[prefix + ".running_var"] = torch.ones(c)
+    else:
+        sd[prefix + ".weight"] = (0.8 + 0.4 * torch.rand(c, generator=g)) * gamma_scale
+        sd[prefix + ".bias"] = 0.1 * torch.randn(c, generator=g)
+        sd[prefix + ".running_mean"] = 0.1 * math.sqrt(var) * torch.randn(c, generator=g)
+        sd[prefix + ".running_var"] = var * (0.8 + 0.4 * torch.rand(c, generator=g))
+    sd[prefix + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+
+def _conv(name, cout, cin, k, sd, g, init):
+    fan_in = cin * k * k
+    if init == "default":
+        sd[name] = _kaiming_uniform((cout, cin, k, k), fan_in, g)
+    else:
+        sd[name] = torch.randn((cout, cin, k, k), generator=g) * math.sqrt(2.0 / fan_in)
+
+
+def make_vs_state_dict(seed: int = 0, init: str = "spread") -> "OrderedDict[str, torch.Tensor]":
+    """ResNet50(7, channels=3) of architectures/video.py:93-166."""
+    g = _gen(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    _conv("conv_layer_s2_same.weight", 64, 3, 7, sd, g, init)
+    # raw pixels minus mean are O(70): normalise them in the stem BN like a trained net would
+    _bn("batch_norm1", 64, sd, g, init, var=2.0 * 70.0 ** 2)
+    cin = 64
+    for li, (planes, blocks) in enumerate(zip(VS_PLANES, VS_BLOCKS), start=1):
+        for b in range(blocks):
+            p = f"layer{li}.{b}"
+            _conv(p + ".conv1.weight", planes, cin, 1, sd, g, init)
+            _bn(p + ".batch_norm1", planes, sd, g, init)
+            _conv(p + ".conv2.weight", planes, planes, 3, sd, g, init)
+            _bn(p + ".batch_norm2", planes, sd, g, init)
+            _conv(p + ".conv3.weight", planes * 4, planes, 1, sd, g, init)
+            _bn(p + ".batch_norm3", planes * 4, sd, g, init, gamma_scale=0.5)
+            if b == 0:
+                _conv(p + ".i_downsample.0.weight", planes * 4, cin, 1, sd, g, init)
+                _bn(p + ".i_downsample.1", planes * 4, sd, g, init, gamma_scale=0.7)
+            cin = planes * 4
+    if init == "default":
+        sd["fc1.weight"] = _kaiming_uniform((512, 2048), 2048, g)
+        sd["fc1.bias"] = _kaiming_uniform((512,), 2048, g)
+        sd["fc2.weight"] = _kaiming_uniform((7, 512), 512, g)
+        sd["fc2.bias"] = _kaiming_uniform((7,), 512, g)
+    else:
+        sd["fc1.weight"] = torch.randn((512, 2048), generator=g) * math.sqrt(2.0 / 2048)
+        sd["fc1.bias"] = 0.1 * torch.randn((512,), generator=g)
+        sd["fc2.weight"] = torch.randn((7, 512), generator=g) * (1.0 / math.sqrt(512))
+        sd["fc2.bias"] = 0.1 * torch.randn((7,), generator=g)
+    return sd
+
+
+def make_vd_state_dict(seed: int = 1, init: str = "spread") -> "OrderedDict[str, torch.Tensor]":
+    """LSTMPyTorch of architectures/video.py:169-185 (gate order i,f,g,o)."""
+    g = _gen(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    scale = 1.0 if init == "default" else 2.0
+
+    def u(shape, hidden):
+        return (torch.rand(shape, generator=g) * 2 - 1) * (scale / math.sqrt(hidden))
+
+    sd["lstm1.weight_ih_l0"] = u((2048, 512), 512)
+    sd["lstm1.weight_hh_l0"] = u((2048, 512), 512)
+    sd["lstm1.bias_ih_l0"] = u((2048,), 512)
+    sd["lstm1.bias_hh_l0"] = u((2048,), 512)
+    sd["lstm2.weight_ih_l0"] = u((1024, 512), 256)
+    sd["lstm2.weight_hh_l0"] = u((1024, 256), 256)
+    sd["lstm2.bias_ih_l0"] = u((1024,), 256)
+    sd["lstm2.bias_hh_l0"] = u((1024,), 256)
+    sd["fc.weight"] = u((7, 256), 256) * (1.0 if init == "default" else 4.0)
+    sd["fc.bias"] = u((7,), 256)
+    return sd
+
+
+W2V_CONV_KERNEL = (10, 3, 3, 3, 3, 2, 2)
+W2V_CONV_STRIDE = (5, 2, 2, 2, 2, 2, 2)
+
+
+def _positional_encoding(d_model: int = 1024, max_len: int = 5000) -> torch.Tensor:
+    # attention_layers.py:194-213 (buffer `pe`, shape [1, max_len, d_model])
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(max_len, 1, d_model)
+    pe[:, 0, 0::2] = torch.sin(position * div_term)
+    pe[:, 0, 1::2] = torch.cos(position * div_term)
+    return pe.permute(1, 0, 2).contiguous()
+
+
+def make_audio_state_dict(seed: int = 2, num_classes: int = 8, init: str = "spread",
+                          num_layers: int = 12) -> "OrderedDict[str, torch.Tensor]":
+    """ExprModelV3 / ExprModelV2 (audio_8_cl.py:131-161, audio_7_cl.py:75-128): wav2vec2-large-robust
+    (12 layers, stable layer norm) + tl1 + tl2 + time_downsample + feature_downsample."""
+    g = _gen(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    spread = init != "default"
+
+    def lin(prefix, out_f, in_f, bias=True, std=None):
+        s = std if std is not None else (1.0 / math.sqrt(in_f) if spread else 0.02)
+        sd[prefix + ".weight"] = torch.randn((out_f, in_f), generator=g) * s
+        if bias:
+            sd[prefix + ".bias"] = (0.02 * torch.randn((out_f,), generator=g)) if spread else torch.zeros(out_f)
+
+    def ln(prefix, c):
+        if spread:
+            sd[prefix + ".weight"] = 0.9 + 0.2 * torch.rand(c, generator=g)
+            sd[prefix + ".bias"] = 0.05 * torch.randn(c, generator=g)
+        else:
+            sd[prefix + ".weight"] = torch.ones(c)
+            sd[prefix + ".bias"] = torch.zeros(c)
+
+    sd["wav2vec2.masked_spec_embed"] = torch.rand(1024, generator=g)
+    cin = 1
+    for i, k in enumerate(W2V_CONV_KERNEL):
+        p = f"wav2vec2.feature_extractor.conv_layers.{i}"
+        sd[p + ".conv.weight"] = torch.randn((512, cin, k), generator=g) * math.sqrt(2.0 / (cin * k))
+        sd[p + ".conv.bias"] = 0.02 * torch.randn(512, generator=g) if spread else torch.zeros(512)
+        ln(p + ".layer_norm", 512)
+        cin = 512
+    ln("wav2vec2.feature_projection.layer_norm", 512)
+    lin("wav2vec2.feature_projection.projection", 1024, 512)
+    sd["wav2vec2.encoder.pos_conv_embed.conv.bias"] = torch.zeros(1024)
+    v = torch.randn((1024, 64, 128), generator=g) * (2.0 * math.sqrt(4.0 / (128 * 1024)))
+    sd["wav2vec2.encoder.pos_conv_embed.conv.parametrizations.weight.original0"] = (
+        v.norm(p=2, dim=(0, 1), keepdim=True) * (0.5 + torch.rand((1, 1, 128), generator=g) if spread else 1.0))
+    sd["wav2vec2.encoder.pos_conv_embed.conv.parametrizations.weight.original1"] = v
+    ln("wav2vec2.encoder.layer_norm", 1024)
+    for i in range(num_layers):
+        p = f"wav2vec2.encoder.layers.{i}"
+        for nm in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            lin(f"{p}.attention.{nm}", 1024, 1024, std=(0.5 / math.sqrt(1024)) if spread else None)
+        ln(p + ".layer_norm", 1024)
+        lin(p + ".feed_forward.intermediate_dense", 4096, 1024)
+        lin(p + ".feed_forward.output_dense", 1024, 4096, std=(0.5 / math.sqrt(4096)) if spread else None)
+        ln(p + ".final_layer_norm", 1024)
+    pe = _positional_encoding()
+    for t in ("tl1", "tl2"):
+        for nm in ("query_w", "keys_w", "values_w", "ff_layer_after_concat"):
+            lin(f"{t}.self_attention.{nm}", 1024, 1024, bias=False)
+        lin(f"{t}.feed_forward.layer_1", 1024, 1024)
+        lin(f"{t}.feed_forward.layer_2", 1024, 1024)
+        ln(f"{t}.feed_forward.layer_norm", 1024)           # present in the state_dict, unused in forward
+        ln(f"{t}.add_norm_after_attention.layer_norm", 1024)
+        ln(f"{t}.add_norm_after_ff.layer_norm", 1024)
+        sd[f"{t}.positional_encoding.pe"] = pe.clone()
+
+    def bn1d(prefix, c):
+        if spread:
+            sd[prefix + ".weight"] = 0.8 + 0.4 * torch.rand(c, generator=g)
+            sd[prefix + ".bias"] = 0.1 * torch.randn(c, generator=g)
+            sd[prefix + ".running_mean"] = 0.1 * torch.randn(c, generator=g)
+            sd[prefix + ".running_var"] = 0.8 + 0.4 * torch.rand(c, generator=g)
+        else:
+            sd[prefix + ".weight"] = torch.ones(c)
+            sd[prefix + ".bias"] = torch.zeros(c)
+            sd[prefix + ".running_mean"] = torch.zeros(c)
+            sd[prefix + ".running_var"] = torch.ones(c)
+        sd[prefix + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    sd["time_downsample.0.weight"] = torch.randn((1024, 1024, 5), generator=g) * math.sqrt(1.0 / (1024 * 5))
+    sd["time_downsample.0.bias"] = 0.02 * torch.randn(1024, generator=g)
+    bn1d("time_downsample.1", 1024)
+    sd["time_downsample.4.weight"] = torch.randn((1024, 1024, 3), generator=g) * math.sqrt(2.0 / (1024 * 3))
+    sd["time_downsample.4.bias"] = 0.02 * torch.randn(1024, generator=g)
+    bn1d("time_downsample.5", 1024)
+    lin("feature_downsample", num_classes, 1024, std=(3.0 / math.sqrt(1024)) if spread else None)
+    return sd
+
+
+# ------------------------------------------------------------------------------------------------ inputs
+def make_crops(seed: int, n: int, size: int = 224) -> np.ndarray:
+    """n pre-cropped faces, uint8 BGR HWC (what cv2.imread returns), smooth + noise so that the
+    network sees structured inputs."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:size, 0:size].astype(np.float32) / size
+    out = np.empty((n, size, size, 3), dtype=np.uint8)
+    for i in range(n):
+        f = rng.uniform(0.5, 4.0, size=(3, 2)).astype(np.float32)
+        ph = rng.uniform(0, 2 * np.pi, size=(3, 2)).astype(np.float32)
+        amp = rng.uniform(20, 90, size=3).astype(np.float32)
+        base = rng.uniform(60, 190, size=3).astype(np.float32)
+        img = np.stack([base[c] + amp[c] * np.sin(2 * np.pi * f[c, 0] * xx + ph[c, 0]) * np.cos(2 * np.pi * f[c, 1] * yy + ph[c, 1])
+                        for c in range(3)], axis=-1)
+        img += rng.normal(0, 12, size=img.shape).astype(np.float32)
+        out[i] = np.clip(img, 0, 255).astype(np.uint8)
+    return out
+
+
+def make_wav(seed: int, n_samples: int) -> np.ndarray:
+    """16 kHz mono float32 waveform: a few drifting tones plus noise, |x| ~ 0.1."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n_samples, dtype=np.float64) / 16000.0
+    x = np.zeros(n_samples, dtype=np.float64)
+    for _ in range(4):
+        f0 = rng.uniform(80, 900)
+        x += rng.uniform(0.02, 0.06) * np.sin(2 * np.pi * f0 * t * (1 + 0.05 * np.sin(2 * np.pi * rng.uniform(0.1, 1.0) * t)) + rng.uniform(0, 6.28))
+    x += rng.normal(0, 0.03, size=n_samples)
+    return x.astype(np.float32)

@@ -1,0 +1,191 @@
+/*
+ * avcer_b200 -- C ABI of the B200-native (sm_100a) kernels behind AVCER's batched
+ * inference-and-fusion path.
+ *
+ * The reference (ElenaRyumina/AVCER) is pure Python/PyTorch and has no FFI layer; its boundary
+ * is the Python function surface.  The Python package `avcer_b200`
+ * keeps those entry points and calls the functions below through ctypes.  Every entry point
+ * names the reference call site (file:line under src/) whose device work it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - the caller owns every buffer (no allocation, no hidden synchronisation inside);
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value 0 = ok, non-zero = error; the message is available from avcer_last_error();
+ *   - activations are channels-last ("NHWC" / [B, T, C]); dtype codes: AVCER_BF16 or AVCER_F32.
+ */
+#ifndef AVCER_B200_H_
+#define AVCER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVCER_F32 0
+#define AVCER_BF16 1
+
+#define AVCER_ACT_NONE 0
+#define AVCER_ACT_RELU 1
+#define AVCER_ACT_GELU 2 /* exact erf GELU (HF wav2vec2 "gelu") */
+
+const char* avcer_last_error(void);
+int avcer_version(void);
+/* 0 when a CUDA device of compute capability 10.x is usable; error otherwise (no CPU fallback). */
+int avcer_device_check(void);
+int avcer_num_sms(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  face-crop preprocessing.
+ * Replaces data/utils.py:19-39 (pth_processing: PIL NEAREST resize to 224x224, RGB->BGR flip,
+ * per-channel mean subtraction, no /255) + the H2D copy at get_prob_video.py:108.
+ * src: u8 crops, HWC with 3 channels in the order cv2.imread delivers (BGR); crop i starts at
+ *      src + src_offsets[i] and is src_h[i] x src_w[i] (row pitch src_w*3).
+ * dst layout 0: fp32 NCHW [n,3,224,224] (bit-exact restatement of the reference tensor);
+ * dst layout 1: bf16 zero-bordered NHWC4 [n, 232, 232, 4] with the image at rows/cols 2..225
+ *               (TF-"same" padding 2|3 of the stem, architectures/video.py:63-90, materialised
+ *               once; channel 3 is zero) -- the layout the tensor-core stem consumes;
+ * dst layout 2: fp32, same geometry as layout 1 (fp32 mode).
+ * The border of layouts 1/2 must have been zeroed once by the caller.
+ */
+int avcer_preprocess_u8(const uint8_t* src, const int64_t* src_offsets, const int32_t* src_h,
+                        const int32_t* src_w, const int16_t* maps, int n, void* dst, int dst_layout,
+                        void* stream);
+/* Nearest-neighbour source-index tables of Pillow's resize for every crop: maps[n][2][224]
+ * (y table, then x table).  src_offsets/src_h/src_w/maps may all be NULL in avcer_preprocess_u8
+ * when every crop is a packed 224x224 image (resize = identity). */
+int avcer_preprocess_maps(const int32_t* src_h, const int32_t* src_w, int n, int16_t* maps,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Generic dense contraction (implicit GEMM): every convolution and Linear on the path.
+ * Replaces the cuDNN/cuBLAS calls issued by architectures/video.py:46-58,116,124-133,
+ * HF Wav2Vec2 conv/linear layers and attention_layers.py:92-97,45-55.
+ *
+ *   out[w,h,n, co] = act( sum_{ty,tx,c} A[c + g(co), w+off_w+tx, h+off_h+ty, n] * Wt[co, (ty*taps_w+tx)*cin + c]
+ *                         + bias[co] + residual[w,h,n,co] )
+ *
+ * A is described as a rank-5 strided view (c, w, h, n, t) with c contiguous; reads outside
+ * [0,a_dim) return 0 (this is the zero padding).  If tap_h_in_dim4 != 0 the ty tap indexes
+ * dimension 4 instead of shifting h (strided / dilated row taps).
+ * dtype AVCER_BF16: A, Wt, residual bf16; bias fp32; tcgen05 tensor-core kernel (TMA + TMEM).
+ *                   cin must be a multiple of 32 and Cout a multiple of 32.
+ * dtype AVCER_F32 : everything fp32; SIMT kernel (the "fp32 mode" of the north star).
+ */
+typedef struct {
+  const void* a;
+  int64_t a_dim[5];          /* extents of (c, w, h, n, t) */
+  int64_t a_stride[5];       /* element strides; a_stride[0] must be 1 */
+  const void* wt;            /* [cout, taps_h*taps_w*cin] row-major */
+  const float* bias;         /* [cout] or NULL */
+  const void* residual;      /* or NULL */
+  void* out;
+  int64_t out_stride[3];     /* element strides of (w, h, n) in out; channels contiguous */
+  int64_t res_stride[3];
+  int32_t W, H, NB;          /* output extents */
+  int32_t cin, cout;         /* cin = contraction channels per tap */
+  int32_t taps_w, taps_h, off_w, off_h, tap_h_in_dim4;
+  int32_t group_cin_shift;   /* grouped conv: channel shift per 64 output channels, else 0 */
+  int32_t act;
+  int32_t res_after_act;     /* 0: act(acc+bias+res); 1: act(acc+bias)+res */
+  int32_t dtype;             /* AVCER_BF16 / AVCER_F32 (operands) */
+  int32_t out_f32;           /* bf16 path only: write fp32 output */
+} avcer_contract_desc;
+
+int avcer_contract(const avcer_contract_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  probability fusion + compound-expression rule + argmax, one warp-cooperative pass.
+ * Replaces run.py:105-165 and data/utils.py:222-241 (numpy float64, CPU).
+ * p_vs: [n,7] f32 VS probabilities (audio emotion order), p_vd / p_a: [n,7] f32 probabilities.
+ * w1: [3][7] f64 per-class weights or NULL (=> mean of the three, run.py:115-116),
+ * w2: [3] f64 per-model weights.  ce_weights_type / ce_mask as in run.py:31-32.
+ * labels: [4][n] int64 (AV, VS, VD, A).  Arithmetic is IEEE double, left-to-right, no FMA
+ * contraction; argmax returns the first maximum (numpy semantics, NaN counts as maximum).
+ */
+int avcer_fuse_compound(const float* p_vs, const float* p_vd, const float* p_a, int64_t n,
+                        const double* w1_host, const double* w2_host, int ce_weights_type,
+                        int ce_mask, int64_t* labels, void* stream);
+/* Same with float64 probability inputs (the reference DataFrames become float64 when a zero row
+ * was appended, get_prob_video.py:89,160-178); arithmetic is then float64 in every branch. */
+int avcer_fuse_compound_f64(const double* p_vs, const double* p_vd, const double* p_a, int64_t n,
+                            const double* w1_host, const double* w2_host, int ce_weights_type,
+                            int ce_mask, int64_t* labels, void* stream);
+
+/* Row softmax over 7 classes in fp32, exactly data/utils.py:125-127 (max-subtract, exp, sum, div).
+ * `ld` = row pitch of the input in floats (8 for the 8-class audio logits: "Other" is dropped
+ * before the softmax, run.py:96). */
+int avcer_softmax7(const float* x, int64_t n, int ld, float* y, void* stream);
+int avcer_softmax7_f64(const double* x, int64_t n, int ld, double* y, void* stream);
+
+/* Frame alignment (run.py:90-103 + get_prob_audio_8_cl.py:94-101): per-frame mean over all audio
+ * windows whose frame range [f_lo[w], f_hi[w]) covers the frame, NaN windows skipped (pandas
+ * groupby.mean skipna), accumulated in window order in fp32... see DESIGN.md for the rounding
+ * contract.  logits: [n_win, ncls]; out: [n_frames, ncls]; frames never covered get NaN. */
+int avcer_window_to_frame_mean(const float* logits, int n_win, int ncls, const int32_t* f_lo,
+                               const int32_t* f_hi, int64_t n_frames, float* out, void* stream);
+
+/* Gather rows: out[i,:] = src_index[i] >= 0 ? src[src_index[i], :] : 0   (carry-forward / gap
+ * expansion of get_prob_video.py:157-178, and column permutation to audio order run.py:85-88
+ * when `perm` is non-NULL: out[i, j] = src[idx, perm[j]]). */
+int avcer_gather_rows(const float* src, const int32_t* src_index, int64_t n_out, int ncols,
+                      const int32_t* perm, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small layers of the VS / VD / A networks (channels-last).  `dtype` selects bf16 or fp32 storage.
+ */
+/* 3x3 stride-2 un-padded max pool, NHWC (architectures/video.py:103,117). */
+int avcer_maxpool3x3s2(const void* x, int n, int h, int w, int c, void* y, int dtype, void* stream);
+/* Global average pool NHWC -> [n, c] (video.py:124). */
+int avcer_avgpool(const void* x, int n, int hw, int c, void* y, int dtype, void* stream);
+/* Tiny Linear (+ optional softmax) with fp32 weights and fp32 output: fc2 + F.softmax
+ * (video.py:133 + get_prob_video.py:107), LSTM fc (video.py:184), feature_downsample
+ * (audio_8_cl.py:189).  x: [n, k] (dtype), w: [m, k] f32, b: [m] f32, y: [n, m] f32; m <= 8. */
+int avcer_small_linear(const void* x, int64_t n, int k, const float* w, const float* b, int m,
+                       int softmax, float* y, int dtype, void* stream);
+/* LSTM cell pointwise step (PyTorch gate order i,f,g,o; video.py:169-185):
+ * gates = xproj[xidx[r]] + hproj[r] (both [*, 4H] fp32, biases already folded into xproj);
+ * c,h updated in place; c is fp32 [n,H]; h_out (dtype) feeds the next recurrent GEMM.
+ * hproj may be NULL for the first step (h_{-1} = 0), xproj may be NULL when the input
+ * projection is folded into hproj; ldh = row pitch of h_out in elements. */
+int avcer_lstm_cell(const float* xproj, const int32_t* xidx, const float* hproj, float* c,
+                    void* h_out, int64_t ldh, int64_t n, int hidden, int first, int dtype,
+                    void* stream);
+
+/* K5a: gather audio windows [start, start+win) from wav (length L), pad the tail with the chunk
+ * mean ("mean"), zeros ("constant") or by tiling ("repeat") (data/utils.py:63-89), then HF
+ * zero-mean/unit-variance normalisation over all `win` samples (population variance, eps 1e-7).
+ * out: [n_win, win] fp32.  pad_mode: 0 mean, 1 constant, 2 repeat. */
+int avcer_audio_normalize_windows(const float* wav, int64_t L, const int64_t* starts, int n_win,
+                                  int win, int pad_mode, float* out, void* stream);
+/* K5b: wav2vec2 conv layer 0 (Cin=1, k=10, s=5, bias) + LayerNorm(512) + GELU fused.
+ * x: [n, t_in] fp32; y: [n, t_out_pitch, 512] (dtype), t_out = (t_in-10)/5+1 rows written. */
+int avcer_w2v_conv0_ln_gelu(const float* x, int n, int t_in, const float* w, const float* b,
+                            const float* ln_g, const float* ln_b, void* y, int64_t y_pitch_rows,
+                            int dtype, void* stream);
+/* Row LayerNorm over `c` channels (eps given) with optional fused GELU and optional additive
+ * term (positional encoding / residual) applied BEFORE the norm: y = act(LN(x + add)).
+ * Rows are addressed as x + r*ldx; add row index = r % add_rows (add_rows = 0: no add). */
+int avcer_layernorm(const void* x, int64_t rows, int c, int64_t ldx, const void* add,
+                    int64_t add_rows, const float* g, const float* b, float eps, int act, void* y,
+                    int64_t ldy, int dtype, void* stream);
+/* y = x + add[r % add_rows]  (sinusoidal positional encoding, attention_layers.py:216). */
+int avcer_add_rows(const void* x, int64_t rows, int c, const void* add, int64_t add_rows, void* y,
+                   int dtype, void* stream);
+/* Multi-head self-attention over T tokens (no mask): softmax(Q K^T * scale) V.
+ * qkv: [n, T, 3, heads, dh] (dtype) packed projections; out: [n, T, heads*dh]. */
+int avcer_attention(const void* qkv, int n, int t, int heads, int dh, float scale, void* out,
+                    int dtype, void* stream);
+/* Audio head tail (audio_8_cl.py:146-159): MaxPool1d(5)+ReLU after conv/BN, and
+ * AdaptiveAvgPool1d(1)+ReLU; x: [n, t, c] -> y: [n, t/5, c] resp. [n, c]. */
+int avcer_maxpool1d5_relu(const void* x, int n, int t, int c, void* y, int dtype, void* stream);
+int avcer_avgpool1d_relu(const void* x, int n, int t, int c, void* y, int dtype, void* stream);
+/* dtype conversion helpers (fp32 <-> bf16). */
+int avcer_cast(const void* x, int64_t n, int src_dtype, void* y, int dst_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVCER_B200_H_ */

@@ -103,14 +103,14 @@ __global__ void avgpool_kernel(const T* __restrict__ x, int n, int hw, int c, T*
 
 // ------------------------------------------------------------------ tiny Linear (+softmax): warp per row
 template <typename T>
-__global__ void small_linear_kernel(const T* __restrict__ x, long long n, int k, const float* __restrict__ w,
+__global__ void small_linear_kernel(const T* __restrict__ x, long long n, int k, long long ldx, const float* __restrict__ w,
                                     const float* __restrict__ b, int m, int softmax, float* __restrict__ y) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = lane; i < k; i += 32) {
-    const float xv = to_f32(x[row * k + i]);
+    const float xv = to_f32(x[row * ldx + i]);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (j < m) acc[j] = fmaf(xv, w[(long long)j * k + i], acc[j]);
@@ -446,12 +446,12 @@ extern "C" int avcer_avgpool(const void* x, int n, int hw, int c, void* y, int d
   return check_launch("avgpool");
 }
 
-extern "C" int avcer_small_linear(const void* x, int64_t n, int k, const float* w, const float* b, int m, int softmax,
-                                  float* y, int dtype, void* stream) {
+extern "C" int avcer_small_linear(const void* x, int64_t n, int k, int64_t ldx, const float* w, const float* b, int m,
+                                  int softmax, float* y, int dtype, void* stream) {
   AVCER_REQUIRE(m >= 1 && m <= 8 && k > 0, "small_linear: m must be in [1,8]");
   if (n == 0) return 0;
   AVCER_DISPATCH(dtype, (small_linear_kernel<T><<<blocks_for(n * 32, 256), 256, 0, as_stream(stream)>>>(
-                            (const T*)x, n, k, w, b, m, softmax, y)));
+                            (const T*)x, n, k, ldx, w, b, m, softmax, y)));
   return check_launch("small_linear");
 }
 

@@ -1,0 +1,223 @@
+"""Device-side forward passes of the three single-modality networks, expressed as sequences of
+libavcer_b200 kernel launches (host orchestration only -- no torch math on the data path).
+
+  VSNet : ResNet-50 static visual model          (reference src/architectures/video.py:93-166)
+  VDNet : 2-layer LSTM over sliding windows      (reference src/architectures/video.py:169-185)
+  ANet  : wav2vec2-large-robust + 2 TL + head    (reference src/architectures/audio_8_cl.py:131-190)
+
+precision "bf16": bf16 storage, tcgen05 tensor-core contractions with fp32 accumulation.
+precision "fp32": fp32 storage, SIMT contractions (the tolerance-check mode of the north star).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import ops, weights
+from ._lib import require_device
+
+PAD = ops.PAD_HW          # 232: padded rows/cols of the stem input
+_BIG = 1 << 30
+
+
+def _dtype(precision: str) -> torch.dtype:
+    if precision == "bf16":
+        return torch.bfloat16
+    if precision == "fp32":
+        return torch.float32
+    raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+
+
+class VSNet:
+    """Static visual ResNet-50.  forward(x) with x = zero-bordered NHWC4 crops [n,232,232,4]
+    (layout 1/2 of avcer_preprocess_u8) -> (probabilities [n,7] fp32, relu(fc1) features [n,512])."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], precision: str = "bf16", device: str = "cuda:0"):
+        require_device()
+        self.dtype = _dtype(precision)
+        self.precision = precision
+        self.device = torch.device(device)
+        self.w = weights.pack_vs(state_dict, self.device, self.dtype)
+
+    @property
+    def input_layout(self) -> int:
+        return 1 if self.dtype == torch.bfloat16 else 2
+
+    def alloc_input(self, n: int) -> torch.Tensor:
+        """Zero-bordered input buffer; the border is written once here, K1 only fills the interior."""
+        return torch.zeros((n, PAD, PAD, 4), device=self.device, dtype=self.dtype)
+
+    def stem(self, x: torch.Tensor) -> torch.Tensor:
+        n = x.shape[0]
+        st = self.w["stem"]
+        y = torch.empty((n, 112, 112, 64), device=self.device, dtype=self.dtype)
+        # A view: (8 pixels x 4 ch = 32, ox stride 2 px, oy stride 2 rows, n, ky stride 1 row)
+        ops.contract(a=x, a_dim=(32, 112, 112, n, 7), a_stride=(1, 8, 2 * PAD * 4, PAD * PAD * 4, PAD * 4),
+                     wt=st.wt, bias=st.bias, out=y, out_stride=(64, 112 * 64, 112 * 112 * 64), W=112, H=112, NB=n,
+                     cin=32, cout=64, taps_w=1, taps_h=7, tap_h_in_dim4=True, act=ops.ACT_RELU)
+        return y
+
+    def _conv(self, x: torch.Tensor, pc: weights.PackedConv, act: int, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        pad = (pc.k - 1) // 2
+        return ops.conv2d_nhwc(x, pc.wt, pc.bias, kh=pc.k, kw=pc.k, stride=pc.stride, pad_h=pad, pad_w=pad,
+                               residual=residual, act=act)
+
+    def forward(self, x: torch.Tensor, taps: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        assert x.shape[1:] == (PAD, PAD, 4) and x.dtype == self.dtype
+        y = self.stem(x)
+        if taps is not None:
+            taps["stem"] = y
+        y = ops.maxpool3x3s2(y)
+        if taps is not None:
+            taps["pool"] = y
+        for bi, blk in enumerate(self.w["blocks"]):
+            identity = self._conv(y, blk["ds"], ops.ACT_NONE) if "ds" in blk else y
+            t = self._conv(y, blk["conv1"], ops.ACT_RELU)
+            t = self._conv(t, blk["conv2"], ops.ACT_RELU)
+            y = self._conv(t, blk["conv3"], ops.ACT_RELU, residual=identity)
+            if taps is not None:
+                taps[f"block{bi}"] = y
+        pooled = ops.avgpool(y)
+        fc1 = self.w["fc1"]
+        feat = ops.linear(pooled, fc1.wt, fc1.bias, act=ops.ACT_RELU)      # relu(fc1): VD input and fc2 input
+        probs = ops.small_linear(feat, self.w["fc2_w"], self.w["fc2_b"], softmax=True)
+        return probs, feat
+
+
+class VDNet:
+    """Dynamic visual LSTM over sliding windows of VS features.  All windows are advanced together,
+    one recurrent GEMM per step; the layer-1 input projection is computed once per unique feature."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], precision: str = "bf16", device: str = "cuda:0"):
+        require_device()
+        self.dtype = _dtype(precision)
+        self.device = torch.device(device)
+        self.w = weights.pack_vd(state_dict, self.device, self.dtype)
+
+    def forward(self, feats: torch.Tensor, windows_t: torch.Tensor) -> torch.Tensor:
+        """feats: [U,512] relu(fc1) features (dtype); windows_t: int32 [10, M] positions into feats
+        (time-major).  Returns VD logits [M,7] fp32."""
+        steps, m = windows_t.shape
+        if m == 0:
+            return torch.empty((0, 7), device=self.device, dtype=torch.float32)
+        w = self.w
+        xproj = ops.linear(feats, w["w_ih1"], w["b1"], out_dtype=torch.float32)            # [U, 2048]
+        hcat = torch.zeros((m, 768), device=self.device, dtype=self.dtype)                   # [h1_t | h2_{t-1}]
+        c1 = torch.empty((m, 512), device=self.device, dtype=torch.float32)
+        c2 = torch.empty((m, 256), device=self.device, dtype=torch.float32)
+        h1, h2 = hcat[:, :512], hcat[:, 512:]
+        hproj = torch.empty((m, 2048), device=self.device, dtype=torch.float32)
+        g2 = torch.empty((m, 1024), device=self.device, dtype=torch.float32)
+        for t in range(steps):
+            if t > 0:
+                ops.linear(h1, w["w_hh1"], None, out=hproj)
+            ops.lstm_cell(xproj, windows_t[t], hproj if t > 0 else None, c1, h1, 512, first=(t == 0))
+            ops.linear(hcat, w["w_cat2"], w["b2"], out=g2)
+            ops.lstm_cell(None, None, g2, c2, h2, 256, first=(t == 0))
+        return ops.small_linear(h2, w["fc_w"], w["fc_b"], softmax=False)
+
+
+W2V_LENGTHS = (12799, 6399, 3199, 1599, 799, 399, 199)     # conv output lengths for 64000 samples
+W2V_KERNELS = (10, 3, 3, 3, 3, 2, 2)
+
+
+class ANet:
+    """Audio emotion network over normalised 4 s windows: x [B,64000] fp32 -> logits [B,ncls] fp32."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], precision: str = "bf16", device: str = "cuda:0"):
+        require_device()
+        self.dtype = _dtype(precision)
+        self.device = torch.device(device)
+        self.w = weights.pack_audio(state_dict, self.device, self.dtype)
+        self.num_classes = self.w["num_classes"]
+
+    def _conv1d_s2(self, x: torch.Tensor, t_in: int, k: int, wt, bias) -> torch.Tensor:
+        """[B, t_in, 512] -> [B, t_out, 512], stride 2, no padding: the k taps of one output step are
+        contiguous in memory, so the layer is a plain GEMM over an overlapping strided view."""
+        b = x.shape[0]
+        t_out = (t_in - k) // 2 + 1
+        y = torch.empty((b, t_out, 512), device=self.device, dtype=self.dtype)
+        ops.contract(a=x, a_dim=(k * 512, t_out, 1, b, 1), a_stride=(1, 2 * 512, _BIG, t_in * 512, _BIG), wt=wt, bias=bias,
+                     out=y, out_stride=(512, 0, t_out * 512), W=t_out, H=1, NB=b, cin=k * 512, cout=512)
+        return y
+
+    def _encoder_layer(self, h: torch.Tensor, L: dict, b: int, t: int) -> torch.Tensor:
+        a = ops.layernorm(h, *L["ln1"], 1e-5)
+        qkv = ops.linear(a, L["wqkv"], L["bqkv"])
+        att = ops.attention(qkv, b, t, 16, 64, 0.125)
+        h = ops.linear(att, L["wo"], L["bo"], residual=h)
+        f = ops.layernorm(h, *L["ln2"], 1e-5)
+        f = ops.linear(f, L["w1"], L["b1"], act=ops.ACT_GELU)
+        return ops.linear(f, L["w2"], L["b2"], residual=h)
+
+    def _transformer_layer(self, h: torch.Tensor, T: dict, b: int, t: int) -> torch.Tensor:
+        heads = T["heads"]
+        dh = 1024 // heads
+        xp = ops.add_rows(h, T["pe"][:t])
+        qkv = ops.linear(xp, T["wqkv"], None)
+        att = ops.attention(qkv, b, t, heads, dh, 1.0 / math.sqrt(dh))
+        y = ops.linear(att, T["wo"], None, residual=xp)
+        y = ops.layernorm(y, *T["ln1"], 1e-5)
+        f = ops.linear(y, T["w1"], T["b1"], act=ops.ACT_RELU)
+        f = ops.linear(f, T["w2"], T["b2"], residual=y)
+        return ops.layernorm(f, *T["ln2"], 1e-5)
+
+    def forward(self, x: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+        assert x.dtype == torch.float32 and x.shape[1] == 64000
+        b = x.shape[0]
+        w = self.w
+        t0 = W2V_LENGTHS[0]
+        h = torch.empty((b, t0, 512), device=self.device, dtype=self.dtype)
+        ops.w2v_conv0_ln_gelu(x, w["conv0_w"], w["conv0_b"], *w["conv_ln"][0], h)
+        if taps is not None:
+            taps["conv0"] = h
+        t = t0
+        for i in range(1, 7):
+            wt, bias = w["convs"][i - 1]
+            h = self._conv1d_s2(h, t, W2V_KERNELS[i], wt, bias)
+            t = h.shape[1]
+            g, be = w["conv_ln"][i]
+            h2 = h.view(b * t, 512)
+            ops.layernorm(h2, g, be, 1e-5, act=ops.ACT_GELU, out=h2)
+        if taps is not None:
+            taps["conv6"] = h
+        rows = h.view(b * t, 512)
+        rows = ops.layernorm(rows, *w["fp_ln"], 1e-5)
+        h = ops.linear(rows, w["fp_w"], w["fp_b"])                                       # [b*t, 1024]
+        if taps is not None:
+            taps["proj"] = h
+        # grouped positional conv (k=128, pad 64, 16 groups), last frame dropped, GELU, added to h
+        h2 = torch.empty_like(h)
+        ops.contract(a=h, a_dim=(1024, t, 1, b, 1), a_stride=(1, 1024, _BIG, t * 1024, _BIG), wt=w["pos_w"], bias=w["pos_b"],
+                     out=h2, out_stride=(1024, 0, t * 1024), W=t, H=1, NB=b, cin=64, cout=1024, taps_w=128, off_w=-64,
+                     group_cin_shift=64, residual=h, act=ops.ACT_GELU, res_after_act=True)
+        h = h2
+        if taps is not None:
+            taps["posconv"] = h
+        for li, L in enumerate(w["layers"]):
+            h = self._encoder_layer(h, L, b, t)
+            if taps is not None:
+                taps[f"layer{li}"] = h
+        h = ops.layernorm(h, *w["enc_ln"], 1e-5)
+        if taps is not None:
+            taps["w2v"] = h
+        h = self._transformer_layer(h, w["tl1"], b, t)
+        h = self._transformer_layer(h, w["tl2"], b, t)
+        if taps is not None:
+            taps["tl2"] = h
+        # time_downsample: Conv1d(k5,s3,d2)+BN -> MaxPool1d(5) -> ReLU -> Conv1d(k3)+BN -> mean -> ReLU
+        t1 = (t - 2 * 4 - 1) // 3 + 1
+        y = torch.empty((b, t1, 1024), device=self.device, dtype=self.dtype)
+        ops.contract(a=h, a_dim=(1024, t1, 1, b, 5), a_stride=(1, 3 * 1024, _BIG, t * 1024, 2 * 1024), wt=w["td0_w"],
+                     bias=w["td0_b"], out=y, out_stride=(1024, 0, t1 * 1024), W=t1, H=1, NB=b, cin=1024, cout=1024,
+                     taps_w=1, taps_h=5, tap_h_in_dim4=True)
+        y = ops.maxpool1d5_relu(y)
+        t2 = y.shape[1]
+        t3 = t2 - 2
+        z = torch.empty((b, t3, 1024), device=self.device, dtype=self.dtype)
+        ops.contract(a=y, a_dim=(3 * 1024, t3, 1, b, 1), a_stride=(1, 1024, _BIG, t2 * 1024, _BIG), wt=w["td4_w"],
+                     bias=w["td4_b"], out=z, out_stride=(1024, 0, t3 * 1024), W=t3, H=1, NB=b, cin=3 * 1024, cout=1024)
+        z = ops.avgpool1d_relu(z)
+        return ops.small_linear(z, w["fd_w"], w["fd_b"], softmax=False)

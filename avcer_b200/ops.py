@@ -116,7 +116,7 @@ def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, r
     ld = x.stride(0)
     if out is None:
         out = torch.empty((m, n), device=x.device, dtype=out_dtype or x.dtype)
-    big = max(ld * m, 8)
+    big = (max(ld * m, 8) + 7) // 8 * 8
     return contract(a=x, a_dim=(k, m, 1, 1, 1), a_stride=(1, ld, big, big, big), wt=wt, bias=bias, out=out,
                     out_stride=(out.stride(0), 0, 0), W=m, H=1, NB=1, cin=k, cout=n, residual=residual,
                     res_stride=None if residual is None else (residual.stride(0), 0, 0), act=act,
@@ -214,9 +214,9 @@ def avgpool(x: torch.Tensor) -> torch.Tensor:
 def small_linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], softmax: bool = False) -> torch.Tensor:
     n, k = x.shape
     m = w.shape[0]
-    assert x.is_contiguous() and w.dtype == torch.float32 and w.is_contiguous()
+    assert x.stride(1) == 1 and w.dtype == torch.float32 and w.is_contiguous()
     y = torch.empty((n, m), device=x.device, dtype=torch.float32)
-    check(_lib.load().avcer_small_linear(x.data_ptr(), n, k, w.data_ptr(), _ptr(b), m, int(softmax), y.data_ptr(),
+    check(_lib.load().avcer_small_linear(x.data_ptr(), n, k, x.stride(0), w.data_ptr(), _ptr(b), m, int(softmax), y.data_ptr(),
                                          dtype_code(x.dtype), _stream()))
     return y
 

@@ -1,0 +1,250 @@
+"""Batched inference-and-fusion engine: the per-frame / per-window Python loops of the reference
+(src/get_prob_video.py:91-180, src/get_prob_audio_8_cl.py:78-101, src/run.py:76-165) restated as
+index plans (host, integer bookkeeping) + batched kernel launches (device).
+
+Vocabulary follows the reference: a *clip* has N frames (face crops, some may be missing) and one
+16 kHz waveform; VS rows are per-frame probabilities, VD rows per-frame logits carried forward from
+the latest 10-slot window, A rows per-frame means of the logits of all 4 s windows covering the frame.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from .nets import ANet, VDNet, VSNet
+
+VIDEO_ORDER = ["Neutral", "Happiness", "Sadness", "Surprise", "Fear", "Disgust", "Anger"]     # get_prob_video.py:56-64
+AUDIO_ORDER = ["Neutral", "Anger", "Disgust", "Fear", "Happiness", "Sadness", "Surprise", "Other"]  # run.py:56-65
+VIDEO_TO_AUDIO = [0, 6, 5, 4, 1, 2, 3]          # audio-order column j = video column VIDEO_TO_AUDIO[j]
+
+
+# =========================================================================================== host index plans
+def vd_step(fps: float) -> int:
+    """get_prob_video.py:77 -- Python round() (half to even)."""
+    return round((5 * fps) / 25)
+
+
+@dataclass
+class VideoPlan:
+    samples: np.ndarray     # [M] frame indices feeding the LSTM
+    windows: np.ndarray     # [M,10] positions into `samples`
+    stat_src: np.ndarray    # [N] frame index whose VS row is shown, -1 = zero row
+    dyn_src: np.ndarray     # [N] window index whose VD row is shown, -1 = zero row
+
+
+def plan_video(exists: Sequence[bool], step: int) -> VideoPlan:
+    """Closed-form equivalent of the frame loop of get_prob_video.py:91-178.
+
+    * an existing frame i with i % step == 0 is a *sample*; any missing frame resets the 10-slot
+      window (:169), so windows never reach across a gap; the first sample of a gap-free segment
+      is repeated on the left (:117-118);
+    * every frame shows the VD output of the latest sample at or before it, across gaps
+      (`last_output` survives, :158-159), zeros before the first one;
+    * a missing frame repeats the previous VS row once a VD output exists, otherwise both of its
+      rows are zero (:170-178).
+    """
+    ex = np.asarray(exists, dtype=bool)
+    n = ex.shape[0]
+    idx = np.arange(n)
+    is_sample = ex & (idx % step == 0)
+    samples = idx[is_sample]
+    m = samples.shape[0]
+    seg_of_frame = np.cumsum(~ex)                          # segment id grows at every missing frame
+    seg = seg_of_frame[samples]
+    pos = np.arange(m)
+    seg_start = np.zeros(m, dtype=np.int64)
+    if m:
+        new_seg = np.r_[True, seg[1:] != seg[:-1]]
+        seg_start = np.maximum.accumulate(np.where(new_seg, pos, 0))
+    windows = np.maximum(pos[:, None] - 9 + np.arange(10)[None, :], seg_start[:, None]).astype(np.int64)
+    last = np.cumsum(is_sample) - 1                        # latest window index at or before frame i
+    prev_existing = np.maximum.accumulate(np.where(ex, idx, -1))
+    stat_src = np.where(ex, idx, np.where(last >= 0, prev_existing, -1)).astype(np.int64)
+    dyn_src = last.astype(np.int64)
+    return VideoPlan(samples.astype(np.int64), windows.reshape(-1, 10), stat_src, dyn_src)
+
+
+@dataclass
+class AudioPlan:
+    starts: np.ndarray      # [Wn] window start sample
+    ends: np.ndarray        # [Wn] window end sample (exclusive, clipped to L)
+    f_lo: np.ndarray        # [Wn] first covered frame id
+    f_hi: np.ndarray        # [Wn] one past the last covered frame id
+
+
+def plan_audio(n_samples: int, fps: float, step: float = 0.5, window: int = 4, sr: int = 16000) -> AudioPlan:
+    """Window schedule of get_prob_audio_8_cl.py:70-101: starts 0, step_a, ... <= L (the last window
+    may be empty); frames range(round(start/sr*fps), round(end/sr*fps + 1)) with Python rounding."""
+    win = window * sr
+    step_a = int(step * sr)
+    starts = np.arange(0, n_samples + 1, step_a, dtype=np.int64)
+    ends = np.minimum(starts + win, n_samples)
+    f_lo = np.rint(starts / sr * fps).astype(np.int64)
+    f_hi = np.rint(ends / sr * fps + 1).astype(np.int64)
+    return AudioPlan(starts, ends, f_lo, f_hi)
+
+
+# =========================================================================================== engine
+@dataclass
+class Clip:
+    """One clip of synthetic or decoded input, host side."""
+    frames: np.ndarray                 # uint8 [n_present, 224, 224, 3] BGR crops (only the present ones)
+    exists: np.ndarray                 # bool [N]
+    fps: float
+    wav: Optional[np.ndarray]          # float32 [L] 16 kHz mono
+
+
+class Engine:
+    """Holds the three packed networks and runs clips through K1 -> VS -> VD, A, alignment and K4."""
+
+    def __init__(self, sd_vs=None, sd_vd=None, sd_a=None, precision: str = "bf16", device: str = "cuda:0",
+                 vs_batch: int = 256, a_batch: int = 32):
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.precision = precision
+        self.vs = VSNet(sd_vs, precision, device) if sd_vs is not None else None
+        self.vd = VDNet(sd_vd, precision, device) if sd_vd is not None else None
+        self.a = ANet(sd_a, precision, device) if sd_a is not None else None
+        self.vs_batch = vs_batch
+        self.a_batch = a_batch
+        self._vs_in: Optional[torch.Tensor] = None
+        self._perm = torch.tensor(VIDEO_TO_AUDIO, device=self.device, dtype=torch.int32)
+
+    # ------------------------------------------------------------------ VS over packed 224x224 crops
+    def _vs_input(self, n: int) -> torch.Tensor:
+        if self._vs_in is None or self._vs_in.shape[0] < n:
+            self._vs_in = self.vs.alloc_input(max(n, self.vs_batch))
+        return self._vs_in[:n]
+
+    def vs_forward_u8(self, crops_u8: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """crops_u8: device uint8 [n,224,224,3] BGR.  Returns (probs [n,7] fp32, features [n,512])."""
+        n = crops_u8.shape[0]
+        probs = torch.empty((n, 7), device=self.device, dtype=torch.float32)
+        feats = torch.empty((n, 512), device=self.device, dtype=self.vs.dtype)
+        for s in range(0, n, self.vs_batch):
+            e = min(n, s + self.vs_batch)
+            x = self._vs_input(e - s)
+            ops.preprocess(crops_u8[s:e], e - s, x, self.vs.input_layout)
+            p, f = self.vs.forward(x)
+            probs[s:e].copy_(p)
+            feats[s:e].copy_(f)
+        return probs, feats
+
+    def vs_forward_ragged(self, flat_u8: torch.Tensor, offsets: np.ndarray, heights: np.ndarray, widths: np.ndarray):
+        """Crops of arbitrary size packed back to back in `flat_u8` (K1 does the NEAREST resize)."""
+        n = len(offsets)
+        probs = torch.empty((n, 7), device=self.device, dtype=torch.float32)
+        feats = torch.empty((n, 512), device=self.device, dtype=self.vs.dtype)
+        off = torch.from_numpy(np.asarray(offsets, dtype=np.int64)).to(self.device)
+        hh = torch.from_numpy(np.asarray(heights, dtype=np.int32)).to(self.device)
+        ww = torch.from_numpy(np.asarray(widths, dtype=np.int32)).to(self.device)
+        for s in range(0, n, self.vs_batch):
+            e = min(n, s + self.vs_batch)
+            x = self._vs_input(e - s)
+            ops.preprocess(flat_u8, e - s, x, self.vs.input_layout, offsets=off[s:e], heights=hh[s:e], widths=ww[s:e])
+            p, f = self.vs.forward(x)
+            probs[s:e].copy_(p)
+            feats[s:e].copy_(f)
+        return probs, feats
+
+    # ------------------------------------------------------------------ video branch of a set of clips
+    def video_rows(self, probs: torch.Tensor, feats: torch.Tensor, exists_list: Sequence[np.ndarray],
+                   fps_list: Sequence[float]) -> Tuple[torch.Tensor, torch.Tensor, List[VideoPlan]]:
+        """probs/feats hold the VS outputs of the present frames of all clips, clip after clip.
+        Returns per-frame (stat [sumN,7] VS probabilities, dyn [sumN,7] VD logits) in VIDEO_ORDER
+        with the reference's carry-forward / gap semantics, plus the per-clip plans."""
+        plans = []
+        stat_idx, dyn_idx, win_all, sample_rows = [], [], [], []
+        present_base = 0      # row offset of this clip in probs/feats
+        sample_base = 0       # offset of this clip's samples in the gathered unique-feature list
+        for ex, fps in zip(exists_list, fps_list):
+            ex = np.asarray(ex, dtype=bool)
+            plan = plan_video(ex, vd_step(fps))
+            plans.append(plan)
+            row_of_frame = np.cumsum(ex) - 1                           # present-row index of an existing frame
+            stat_idx.append(np.where(plan.stat_src >= 0, present_base + row_of_frame[np.maximum(plan.stat_src, 0)], -1))
+            dyn_idx.append(np.where(plan.dyn_src >= 0, sample_base + plan.dyn_src, -1))
+            win_all.append(plan.windows + sample_base)
+            sample_rows.append(present_base + row_of_frame[plan.samples])
+            present_base += int(ex.sum())
+            sample_base += plan.samples.shape[0]
+        dev = self.device
+        stat_idx_t = torch.from_numpy(np.concatenate(stat_idx).astype(np.int32)).to(dev)
+        dyn_idx_t = torch.from_numpy(np.concatenate(dyn_idx).astype(np.int32)).to(dev)
+        n_total = stat_idx_t.numel()
+        stat = ops.gather_rows(probs, stat_idx_t, n_total)
+        windows = np.concatenate(win_all, axis=0) if win_all else np.zeros((0, 10), dtype=np.int64)
+        if windows.shape[0]:
+            # windows index the sample list; map them to rows of `feats` so no feature copy is needed
+            rows = np.concatenate(sample_rows)
+            win_rows = torch.from_numpy(np.ascontiguousarray(rows[windows].T).astype(np.int32)).to(dev)   # [10, M]
+            vd_logits = self.vd.forward(feats, win_rows)
+        else:
+            vd_logits = torch.zeros((1, 7), device=dev, dtype=torch.float32)
+        dyn = ops.gather_rows(vd_logits, dyn_idx_t, n_total)
+        return stat, dyn, plans
+
+    # ------------------------------------------------------------------ audio branch
+    def audio_window_logits(self, wav: torch.Tensor, plan: AudioPlan, padding: str, win: int) -> torch.Tensor:
+        """wav: device fp32 [L].  Returns per-window logits [Wn, ncls] fp32."""
+        if padding == "repeat" and bool((plan.ends - plan.starts == 0).any()):
+            raise ZeroDivisionError("integer division or modulo by zero")      # data/utils.py:66 on the empty tail window
+        if padding not in ops.PAD_MODES:
+            raise UnboundLocalError("cannot access local variable 'a_fss' where it is not associated with a value")
+        starts = torch.from_numpy(plan.starts).to(self.device)
+        wn = plan.starts.shape[0]
+        out = torch.empty((wn, self.a.num_classes), device=self.device, dtype=torch.float32)
+        for s in range(0, wn, self.a_batch):
+            e = min(wn, s + self.a_batch)
+            x = ops.audio_normalize_windows(wav, starts[s:e], win, padding)
+            out[s:e].copy_(self.a.forward(x))
+        return out
+
+    def audio_frame_means(self, logits: torch.Tensor, f_lo: np.ndarray, f_hi: np.ndarray, n_frames: int) -> torch.Tensor:
+        lo = torch.from_numpy(np.asarray(f_lo, dtype=np.int32)).to(self.device)
+        hi = torch.from_numpy(np.asarray(f_hi, dtype=np.int32)).to(self.device)
+        return ops.window_to_frame_mean(logits, lo, hi, n_frames)
+
+    # ------------------------------------------------------------------ K4 on aligned per-frame rows
+    def fuse(self, stat_video_order: torch.Tensor, dyn_video_order: torch.Tensor, audio_mean_logits: torch.Tensor,
+             weights_1, weights_2, ce_weights_type: bool, ce_mask: bool) -> torch.Tensor:
+        """run.py:85-165 on device: permute the video columns into audio order, softmax the VD logits and
+        the audio mean logits (first 7 classes), then K4.  Returns int64 labels [4, n]."""
+        n = stat_video_order.shape[0]
+        p_vs = ops.gather_rows(stat_video_order, None, n, perm=self._perm)
+        p_vd = ops.softmax7(ops.gather_rows(dyn_video_order, None, n, perm=self._perm))
+        p_a = ops.softmax7(audio_mean_logits)
+        return ops.fuse_compound(p_vs, p_vd, p_a, weights_1, weights_2, ce_weights_type, ce_mask)
+
+    # ------------------------------------------------------------------ whole clips, batched
+    def run_clips(self, crops_u8: torch.Tensor, exists_list: Sequence[np.ndarray], fps_list: Sequence[float],
+                  wavs: Sequence[torch.Tensor], weights_1, weights_2, ce_weights_type: bool, ce_mask: bool,
+                  step: float = 0.5, window: int = 4, sr: int = 16000, padding: str = "mean") -> Dict[str, torch.Tensor]:
+        """All clips at once.  crops_u8: device uint8 [sum present frames, 224,224,3]; wavs: device fp32.
+        Audio frames beyond a clip's last covered frame repeat the last audio row (run.py:99-103)."""
+        probs, feats = self.vs_forward_u8(crops_u8)
+        stat, dyn, plans = self.video_rows(probs, feats, exists_list, fps_list)
+        # audio: one global window list over all clips, frame ranges shifted into the global frame index
+        n_frames = [len(e) for e in exists_list]
+        base = np.r_[0, np.cumsum(n_frames)]
+        win_logits, lo_all, hi_all, tail_src = [], [], [], []
+        for ci, (wav, fps) in enumerate(zip(wavs, fps_list)):
+            ap = plan_audio(int(wav.numel()), fps, step, window, sr)
+            win_logits.append(self.audio_window_logits(wav, ap, padding, window * sr))
+            nf = n_frames[ci]
+            lo_all.append(base[ci] + np.minimum(ap.f_lo, nf))
+            hi_all.append(base[ci] + np.minimum(ap.f_hi, nf))          # frame ids >= N are dropped by the isin filter (run.py:96)
+            covered = int(min(nf, ap.f_hi.max()))
+            src = np.arange(nf)
+            src[covered:] = max(covered - 1, 0)
+            tail_src.append(base[ci] + src)
+        logits = torch.cat(win_logits, dim=0)
+        a_mean = self.audio_frame_means(logits, np.concatenate(lo_all), np.concatenate(hi_all), int(base[-1]))
+        tail = torch.from_numpy(np.concatenate(tail_src).astype(np.int32)).to(self.device)
+        a_rows = ops.gather_rows(a_mean, tail, int(base[-1]))
+        labels = self.fuse(stat, dyn, a_rows, weights_1, weights_2, ce_weights_type, ce_mask)
+        return {"labels": labels, "stat": stat, "dyn": dyn, "audio_mean": a_rows, "window_logits": logits}

@@ -1,0 +1,165 @@
+"""Weight packer: reference state_dicts -> kernel-native layouts.
+
+Input contract = the state_dict keys/shapes of the reference classes:
+ResNet50(7) and LSTMPyTorch (src/architectures/video.py:93-185), ExprModelV3/V2
+(src/architectures/audio_8_cl.py:131-161, audio_7_cl.py:75-128).
+
+Packing rules
+  * BatchNorm (eval, running stats) is folded into the preceding bias-free convolution:
+      s = gamma / sqrt(var + eps);  w' = w * s;  b' = beta - mean * s      (eps 1e-3 for VS, 1e-5 for A)
+  * convolution weights become [Cout, taps * Cin] (tap-major, channel-minor), the K-contiguous
+    operand layout of avcer_contract;
+  * the 7x7/2 stem becomes [64, 7 rows, 8 pixels x 4 channels] to match the zero-bordered NHWC4
+    input (pixel 7 and channel 3 carry zero weights);
+  * weight_norm of the wav2vec2 positional conv is folded: w = g * v / ||v||_(0,1);
+  * q/k/v projections are concatenated into one [3*1024, 1024] matrix;
+  * storage dtype is bf16 (default) or fp32 ("fp32 mode"); biases and the small heads stay fp32.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+VS_BLOCKS = (3, 4, 6, 3)
+VS_PLANES = (64, 128, 256, 512)
+
+
+def _fold_bn(w: torch.Tensor, sd, p: str, eps: float, conv_bias: Optional[torch.Tensor] = None):
+    s = sd[p + ".weight"].double() / torch.sqrt(sd[p + ".running_var"].double() + eps)
+    shape = [-1] + [1] * (w.dim() - 1)
+    w2 = w.double() * s.view(shape)
+    b = sd[p + ".bias"].double() - sd[p + ".running_mean"].double() * s
+    if conv_bias is not None:
+        b = b + conv_bias.double() * s
+    return w2.float(), b.float()
+
+
+def _tap_major(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, *k] -> [Cout, prod(k) * Cin]."""
+    cout, cin = w.shape[:2]
+    if w.dim() == 4:
+        return w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+    if w.dim() == 3:
+        return w.permute(0, 2, 1).reshape(cout, -1).contiguous()
+    return w.contiguous()
+
+
+class PackedConv:
+    __slots__ = ("wt", "bias", "cin", "cout", "k", "stride")
+
+    def __init__(self, wt, bias, cin, cout, k, stride):
+        self.wt, self.bias, self.cin, self.cout, self.k, self.stride = wt, bias, cin, cout, k, stride
+
+
+def pack_vs(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
+    """ResNet-50 VS: returns {'stem': PackedConv, 'blocks': [dict], 'fc1': PackedConv, 'fc2_w','fc2_b'}."""
+    eps = 1e-3
+
+    def dev(t, dt=None):
+        return t.to(device=device, dtype=dt or dtype).contiguous()
+
+    out = {}
+    w, b = _fold_bn(sd["conv_layer_s2_same.weight"], sd, "batch_norm1", eps)
+    stem = torch.zeros(64, 7, 8, 4)
+    stem[:, :, :7, :3] = w.permute(0, 2, 3, 1)          # [co, ky, kx, c]
+    out["stem"] = PackedConv(dev(stem.reshape(64, 7 * 32)), dev(b, torch.float32), 32, 64, 7, 2)
+    blocks: List[dict] = []
+    cin = 64
+    for li, (planes, nblocks) in enumerate(zip(VS_PLANES, VS_BLOCKS), start=1):
+        for bi in range(nblocks):
+            p = f"layer{li}.{bi}"
+            stride = 2 if (li > 1 and bi == 0) else 1
+            blk = {}
+            for j, (k, ci, co, st) in enumerate([(1, cin, planes, stride), (3, planes, planes, 1), (1, planes, planes * 4, 1)], start=1):
+                w, b = _fold_bn(sd[f"{p}.conv{j}.weight"], sd, f"{p}.batch_norm{j}", eps)
+                blk[f"conv{j}"] = PackedConv(dev(_tap_major(w)), dev(b, torch.float32), ci, co, k, st)
+            if bi == 0:
+                w, b = _fold_bn(sd[f"{p}.i_downsample.0.weight"], sd, f"{p}.i_downsample.1", eps)
+                blk["ds"] = PackedConv(dev(_tap_major(w)), dev(b, torch.float32), cin, planes * 4, 1, stride)
+            blocks.append(blk)
+            cin = planes * 4
+    out["blocks"] = blocks
+    out["fc1"] = PackedConv(dev(sd["fc1.weight"]), dev(sd["fc1.bias"], torch.float32), 2048, 512, 1, 1)
+    out["fc2_w"] = dev(sd["fc2.weight"], torch.float32)
+    out["fc2_b"] = dev(sd["fc2.bias"], torch.float32)
+    return out
+
+
+def pack_vd(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
+    """LSTM(512->512) -> LSTM(512->256) -> Linear(256->7).  Layer 2's input and recurrent matrices
+    are concatenated along K so one GEMM over [h1_t | h2_{t-1}] yields its gate pre-activations."""
+    def dev(t, dt=None):
+        return t.to(device=device, dtype=dt or dtype).contiguous()
+
+    return {
+        "w_ih1": dev(sd["lstm1.weight_ih_l0"]),
+        "w_hh1": dev(sd["lstm1.weight_hh_l0"]),
+        "b1": dev(sd["lstm1.bias_ih_l0"] + sd["lstm1.bias_hh_l0"], torch.float32),
+        "w_cat2": dev(torch.cat([sd["lstm2.weight_ih_l0"], sd["lstm2.weight_hh_l0"]], dim=1)),
+        "b2": dev(sd["lstm2.bias_ih_l0"] + sd["lstm2.bias_hh_l0"], torch.float32),
+        "fc_w": dev(sd["fc.weight"], torch.float32),
+        "fc_b": dev(sd["fc.bias"], torch.float32),
+    }
+
+
+def pack_audio(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
+    """ExprModelV3 / V2 (wav2vec2-large-robust 12L + tl1 + tl2 + head)."""
+    def dev(t, dt=None):
+        return t.to(device=device, dtype=dt or dtype).contiguous()
+
+    f32 = torch.float32
+    p = "wav2vec2."
+    out = {}
+    fe = p + "feature_extractor.conv_layers."
+    out["conv0_w"] = dev(sd[fe + "0.conv.weight"].reshape(512, 10), f32)
+    out["conv0_b"] = dev(sd[fe + "0.conv.bias"], f32)
+    out["conv_ln"] = [(dev(sd[f"{fe}{i}.layer_norm.weight"], f32), dev(sd[f"{fe}{i}.layer_norm.bias"], f32)) for i in range(7)]
+    out["convs"] = [(dev(_tap_major(sd[f"{fe}{i}.conv.weight"])), dev(sd[f"{fe}{i}.conv.bias"], f32)) for i in range(1, 7)]
+    out["fp_ln"] = (dev(sd[p + "feature_projection.layer_norm.weight"], f32), dev(sd[p + "feature_projection.layer_norm.bias"], f32))
+    out["fp_w"] = dev(sd[p + "feature_projection.projection.weight"])
+    out["fp_b"] = dev(sd[p + "feature_projection.projection.bias"], f32)
+    g = sd[p + "encoder.pos_conv_embed.conv.parametrizations.weight.original0"].double()
+    v = sd[p + "encoder.pos_conv_embed.conv.parametrizations.weight.original1"].double()
+    w = (v * (g / v.norm(p=2, dim=(0, 1), keepdim=True))).float()          # [1024, 64, 128]
+    out["pos_w"] = dev(_tap_major(w))                                       # [1024, 128*64]
+    out["pos_b"] = dev(sd[p + "encoder.pos_conv_embed.conv.bias"], f32)
+    layers = []
+    i = 0
+    while f"{p}encoder.layers.{i}.layer_norm.weight" in sd:
+        q = f"{p}encoder.layers.{i}."
+        layers.append({
+            "ln1": (dev(sd[q + "layer_norm.weight"], f32), dev(sd[q + "layer_norm.bias"], f32)),
+            "wqkv": dev(torch.cat([sd[q + "attention.q_proj.weight"], sd[q + "attention.k_proj.weight"], sd[q + "attention.v_proj.weight"]], 0)),
+            "bqkv": dev(torch.cat([sd[q + "attention.q_proj.bias"], sd[q + "attention.k_proj.bias"], sd[q + "attention.v_proj.bias"]], 0), f32),
+            "wo": dev(sd[q + "attention.out_proj.weight"]),
+            "bo": dev(sd[q + "attention.out_proj.bias"], f32),
+            "ln2": (dev(sd[q + "final_layer_norm.weight"], f32), dev(sd[q + "final_layer_norm.bias"], f32)),
+            "w1": dev(sd[q + "feed_forward.intermediate_dense.weight"]),
+            "b1": dev(sd[q + "feed_forward.intermediate_dense.bias"], f32),
+            "w2": dev(sd[q + "feed_forward.output_dense.weight"]),
+            "b2": dev(sd[q + "feed_forward.output_dense.bias"], f32),
+        })
+        i += 1
+    out["layers"] = layers
+    out["enc_ln"] = (dev(sd[p + "encoder.layer_norm.weight"], f32), dev(sd[p + "encoder.layer_norm.bias"], f32))
+    for t, heads in (("tl1", 32), ("tl2", 16)):
+        a = f"{t}.self_attention."
+        out[t] = {
+            "heads": heads,
+            "pe": dev(sd[f"{t}.positional_encoding.pe"][0, :512]),          # first 512 positions are plenty (T = 199)
+            "wqkv": dev(torch.cat([sd[a + "query_w.weight"], sd[a + "keys_w.weight"], sd[a + "values_w.weight"]], 0)),
+            "wo": dev(sd[a + "ff_layer_after_concat.weight"]),
+            "ln1": (dev(sd[f"{t}.add_norm_after_attention.layer_norm.weight"], f32), dev(sd[f"{t}.add_norm_after_attention.layer_norm.bias"], f32)),
+            "w1": dev(sd[f"{t}.feed_forward.layer_1.weight"]), "b1": dev(sd[f"{t}.feed_forward.layer_1.bias"], f32),
+            "w2": dev(sd[f"{t}.feed_forward.layer_2.weight"]), "b2": dev(sd[f"{t}.feed_forward.layer_2.bias"], f32),
+            "ln2": (dev(sd[f"{t}.add_norm_after_ff.layer_norm.weight"], f32), dev(sd[f"{t}.add_norm_after_ff.layer_norm.bias"], f32)),
+        }
+    w, b = _fold_bn(sd["time_downsample.0.weight"], sd, "time_downsample.1", 1e-5, sd["time_downsample.0.bias"])
+    out["td0_w"], out["td0_b"] = dev(_tap_major(w)), dev(b, f32)
+    w, b = _fold_bn(sd["time_downsample.4.weight"], sd, "time_downsample.5", 1e-5, sd["time_downsample.4.bias"])
+    out["td4_w"], out["td4_b"] = dev(_tap_major(w)), dev(b, f32)
+    out["fd_w"] = dev(sd["feature_downsample.weight"], f32)
+    out["fd_b"] = dev(sd["feature_downsample.bias"], f32)
+    out["num_classes"] = int(sd["feature_downsample.weight"].shape[0])
+    return out

@@ -142,9 +142,9 @@ int avcer_maxpool3x3s2(const void* x, int n, int h, int w, int c, void* y, int d
 int avcer_avgpool(const void* x, int n, int hw, int c, void* y, int dtype, void* stream);
 /* Tiny Linear (+ optional softmax) with fp32 weights and fp32 output: fc2 + F.softmax
  * (video.py:133 + get_prob_video.py:107), LSTM fc (video.py:184), feature_downsample
- * (audio_8_cl.py:189).  x: [n, k] (dtype), w: [m, k] f32, b: [m] f32, y: [n, m] f32; m <= 8. */
-int avcer_small_linear(const void* x, int64_t n, int k, const float* w, const float* b, int m,
-                       int softmax, float* y, int dtype, void* stream);
+ * (audio_8_cl.py:189).  x: [n, k] (dtype, row pitch ldx), w: [m, k] f32, b: [m] f32, y: [n, m] f32; m <= 8. */
+int avcer_small_linear(const void* x, int64_t n, int k, int64_t ldx, const float* w, const float* b,
+                       int m, int softmax, float* y, int dtype, void* stream);
 /* LSTM cell pointwise step (PyTorch gate order i,f,g,o; video.py:169-185):
  * gates = xproj[xidx[r]] + hproj[r] (both [*, 4H] fp32, biases already folded into xproj);
  * c,h updated in place; c is fp32 [n,H]; h_out (dtype) feeds the next recurrent GEMM.

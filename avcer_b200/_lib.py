@@ -62,6 +62,7 @@ _SIGNATURES = {
     "avcer_contract": (c_int, [POINTER(ContractDesc), c_void_p]),
     "avcer_fuse_compound": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_int, c_void_p, c_void_p]),
     "avcer_fuse_compound_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_int, c_void_p, c_void_p]),
+    "avcer_compound_scores": (c_int, [c_void_p, c_int64, c_int, c_int, POINTER(c_int32), POINTER(c_double), c_int, c_int, c_void_p, c_void_p]),
     "avcer_softmax7": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "avcer_softmax7_f64": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "avcer_window_to_frame_mean": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
@@ -70,7 +71,7 @@ _SIGNATURES = {
     "avcer_avgpool": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "avcer_small_linear": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "avcer_lstm_cell": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
-    "avcer_audio_normalize_windows": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "avcer_audio_normalize_windows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "avcer_w2v_conv0_ln_gelu": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "avcer_layernorm": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_int, c_void_p, c_int64, c_int, c_void_p]),
     "avcer_add_rows": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p]),

@@ -1,0 +1,78 @@
+"""Run-time configuration of the drop-in modules (precision, device, weights).
+
+The reference loads its checkpoints at import time from CWD-relative paths
+(src/get_prob_video.py:22-25,51-54; src/get_prob_audio_8_cl.py:52-66).  Here loading is lazy:
+`set_state_dicts` injects state_dicts directly (tests, synthetic runs); otherwise the same files
+are read on first use and a missing file raises FileNotFoundError like the reference.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional
+
+import torch
+
+PATH_STATIC = "src/weights/FER_static_ResNet50_AffectNet.pt"       # get_prob_video.py:22
+PATH_DYNAMIC = "src/weights/FER_dinamic_LSTM_Aff-Wild2.pt"         # get_prob_video.py:51
+
+_state: Dict[str, object] = {"precision": "bf16", "device": "cuda:0", "vs": None, "vd": None, "audio": {},
+                             "engine": None, "audio_nets": {}}
+
+
+def set_precision(precision: str) -> None:
+    assert precision in ("bf16", "fp32")
+    _state["precision"] = precision
+    reset()
+
+
+def set_device(device: str) -> None:
+    _state["device"] = device
+    reset()
+
+
+def set_state_dicts(vs=None, vd=None, audio: Optional[dict] = None) -> None:
+    """audio: {model_name or num_classes: state_dict}."""
+    if vs is not None:
+        _state["vs"] = vs
+    if vd is not None:
+        _state["vd"] = vd
+    if audio is not None:
+        _state["audio"].update(audio)
+    reset()
+
+
+def reset() -> None:
+    _state["engine"] = None
+    _state["audio_nets"] = {}
+
+
+def precision() -> str:
+    return _state["precision"]
+
+
+def device() -> str:
+    return _state["device"]
+
+
+def video_engine():
+    """Engine with VS + VD loaded (built once)."""
+    from .pipeline import Engine
+
+    if _state["engine"] is None:
+        vs = _state["vs"] if _state["vs"] is not None else torch.load(PATH_STATIC, map_location="cpu")
+        vd = _state["vd"] if _state["vd"] is not None else torch.load(PATH_DYNAMIC, map_location="cpu")
+        _state["engine"] = Engine(vs, vd, None, precision=_state["precision"], device=_state["device"])
+    return _state["engine"]
+
+
+def audio_net(model_name: str, num_classes: int, root_path: str, epoch: int, device: Optional[str] = None):
+    from .nets import ANet
+
+    key = (model_name, device or _state["device"])
+    if key not in _state["audio_nets"]:
+        sd = _state["audio"].get(model_name, _state["audio"].get(num_classes))
+        if sd is None:
+            ckpt = torch.load(os.path.join(root_path, f"epoch_{epoch}.pth"), map_location="cpu")
+            sd = ckpt["model_state_dict"]
+        _state["audio_nets"][key] = ANet(sd, _state["precision"], device or _state["device"])
+    return _state["audio_nets"][key]

@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(256) simt_contract_kernel(const SimtParams p) 
       float v = acc[i][j];
       if (p.bias) v += p.bias[co];
       if (p.residual && !p.res_after_act) v += p.residual[ro + co];
-      if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
+      if (p.act == ACT_RELU) v = v < 0.f ? 0.f : v;
       else if (p.act == ACT_GELU) v = gelu_erf(v);
       if (p.residual && p.res_after_act) v += p.residual[ro + co];
       p.out[oo + co] = v;

@@ -165,6 +165,29 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __r
   out[i] = s >= 0 ? src[(long long)s * ncols + (perm ? perm[c] : c)] : 0.f;
 }
 
+// data/utils.py:222-241 as a stand-alone op (the reference exposes it as a function): arbitrary
+// pair table, scores returned as float64 like the reference's np.zeros((n, k)) result array.
+struct PairTable {
+  int i1[16], i2[16];
+  double w1[16], w2[16];
+  int k;
+};
+template <typename TC>
+__global__ void compound_scores_kernel(const TC* __restrict__ pred, long long n, int ncols, const PairTable t,
+                                       int ce_mask, double* __restrict__ out) {
+  using A = Arith<TC>;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * t.k) return;
+  const long long r = i / t.k;
+  const int k = (int)(i % t.k);
+  TC a = pred[r * ncols + t.i1[k]], b = pred[r * ncols + t.i2[k]];
+  if (ce_mask) {
+    a = a > A::thr() ? a : (TC)0;
+    b = b > A::thr() ? b : (TC)0;
+  }
+  out[i] = (double)A::add(A::mul(a, (TC)t.w1[k]), A::mul(b, (TC)t.w2[k]));
+}
+
 }  // namespace avcer
 
 using namespace avcer;
@@ -255,4 +278,22 @@ extern "C" int avcer_gather_rows(const float* src, const int32_t* src_index, int
   gather_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, as_stream(stream)>>>(src, src_index, n_out, ncols, perm,
                                                                                    out);
   return check_launch("gather_rows_kernel");
+}
+
+extern "C" int avcer_compound_scores(const void* pred, int64_t n, int ncols, int pred_f64, const int32_t* pairs_host,
+                                     const double* w_host, int k, int ce_mask, double* out, void* stream) {
+  AVCER_REQUIRE(k >= 1 && k <= 16 && ncols >= 1 && n >= 0, "compound_scores: bad shape");
+  if (n == 0) return 0;
+  PairTable t{};
+  t.k = k;
+  for (int i = 0; i < k; ++i) {
+    t.i1[i] = pairs_host[2 * i]; t.i2[i] = pairs_host[2 * i + 1];
+    AVCER_REQUIRE(t.i1[i] >= 0 && t.i1[i] < ncols && t.i2[i] >= 0 && t.i2[i] < ncols, "compound_scores: pair index out of range");
+    t.w1[i] = w_host[2 * i]; t.w2[i] = w_host[2 * i + 1];
+  }
+  const long long tot = n * k;
+  const unsigned g = (unsigned)((tot + 255) / 256);
+  if (pred_f64) compound_scores_kernel<double><<<g, 256, 0, as_stream(stream)>>>((const double*)pred, n, ncols, t, ce_mask, out);
+  else compound_scores_kernel<float><<<g, 256, 0, as_stream(stream)>>>((const float*)pred, n, ncols, t, ce_mask, out);
+  return check_launch("compound_scores_kernel");
 }

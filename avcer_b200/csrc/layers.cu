@@ -75,7 +75,7 @@ __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, int n, int h, int w
       float v[8];
       Vec8<T>::load(x + (((long long)b * h + (2 * oy + dy)) * w + (2 * ox + dx)) * c + cc, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+      for (int j = 0; j < 8; ++j) m[j] = (v[j] > m[j] || v[j] != v[j]) ? v[j] : m[j];   // NaN-propagating like torch
     }
   Vec8<T>::store(y + (((long long)b * ho + oy) * wo + ox) * c + cc, m);
 }
@@ -158,13 +158,13 @@ __global__ void lstm_cell_kernel(const float* __restrict__ xproj, const int* __r
 // ------------------------------------------------------------------ K5a audio window gather + pad + zero-mean/unit-var
 // (get_prob_audio_8_cl.py:78-90, data/utils.py:63-89, HF zero_mean_unit_var_norm: (x-mean)/sqrt(var+1e-7))
 __global__ void __launch_bounds__(512)
-audio_normalize_kernel(const float* __restrict__ wav, long long L, const long long* __restrict__ starts, int win,
-                       int pad_mode, float* __restrict__ out) {
+audio_normalize_kernel(const float* __restrict__ wav, const long long* __restrict__ starts,
+                       const long long* __restrict__ ends, int win, int pad_mode, float* __restrict__ out) {
   __shared__ double red[16];
   __shared__ double bc[2];
   const int wi = blockIdx.x;
   const long long s0 = starts[wi];
-  long long len = L - s0;
+  long long len = ends[wi] - s0;
   if (len > win) len = win;
   if (len < 0) len = 0;
   const float* src = wav + s0;
@@ -394,8 +394,11 @@ __global__ void maxpool1d5_relu_kernel(const T* __restrict__ x, int n, int t, in
   const int b = (int)(i / ((long long)c * to));
   float m = -INFINITY;
 #pragma unroll
-  for (int k = 0; k < 5; ++k) m = fmaxf(m, to_f32(x[((long long)b * t + ot * 5 + k) * c + cc]));
-  y[i] = from_f32<T>(fmaxf(m, 0.f));
+  for (int k = 0; k < 5; ++k) {
+    const float v = to_f32(x[((long long)b * t + ot * 5 + k) * c + cc]);
+    m = (v > m || v != v) ? v : m;
+  }
+  y[i] = from_f32<T>(m < 0.f ? 0.f : m);
 }
 template <typename T>
 __global__ void avgpool1d_relu_kernel(const T* __restrict__ x, int n, int t, int c, T* __restrict__ y) {
@@ -405,7 +408,8 @@ __global__ void avgpool1d_relu_kernel(const T* __restrict__ x, int n, int t, int
   const int b = (int)(i / c);
   float s = 0.f;
   for (int k = 0; k < t; ++k) s += to_f32(x[((long long)b * t + k) * c + cc]);
-  y[i] = from_f32<T>(fmaxf(s / (float)t, 0.f));
+  const float a = s / (float)t;
+  y[i] = from_f32<T>(a < 0.f ? 0.f : a);
 }
 
 template <typename TS, typename TD>
@@ -465,11 +469,11 @@ extern "C" int avcer_lstm_cell(const float* xproj, const int32_t* xidx, const fl
   return check_launch("lstm_cell");
 }
 
-extern "C" int avcer_audio_normalize_windows(const float* wav, int64_t L, const int64_t* starts, int n_win, int win,
-                                             int pad_mode, float* out, void* stream) {
+extern "C" int avcer_audio_normalize_windows(const float* wav, const int64_t* starts, const int64_t* ends, int n_win,
+                                             int win, int pad_mode, float* out, void* stream) {
   AVCER_REQUIRE(pad_mode >= 0 && pad_mode <= 2 && win > 0, "audio_normalize_windows: bad arguments");
   if (n_win == 0) return 0;
-  audio_normalize_kernel<<<n_win, 512, 0, as_stream(stream)>>>(wav, L, (const long long*)starts, win, pad_mode, out);
+  audio_normalize_kernel<<<n_win, 512, 0, as_stream(stream)>>>(wav, (const long long*)starts, (const long long*)ends, win, pad_mode, out);
   return check_launch("audio_normalize_windows");
 }
 

@@ -1,0 +1,70 @@
+"""Drop-in for the reference's src/get_prob_video.py: same entry point, same DataFrames / CSVs;
+the per-frame loop (:91-180) is replaced by one index plan + batched K1 -> VS -> VD launches.
+"""
+from __future__ import annotations
+
+import os
+
+import cv2
+import numpy as np
+import pandas as pd
+import torch
+
+from . import config
+from .pipeline import vd_step
+
+DICT_EMO_VIDEO = {0: "Neutral", 1: "Happiness", 2: "Sadness", 3: "Surprise", 4: "Fear", 5: "Disgust", 6: "Anger"}
+
+
+def _load_crops(path_images: str, total_frames: int):
+    """Reads face track "00" exactly as the reference does (get_prob_video.py:79,93-95): frame i is
+    present iff `00/{i:06d}.jpg` exists.  Returns (flat uint8 buffer, offsets, heights, widths, exists)."""
+    folder = os.path.join(path_images, "00")
+    names = set(os.listdir(folder))
+    exists = np.zeros(total_frames, dtype=bool)
+    chunks, offsets, hs, ws = [], [], [], []
+    off = 0
+    for i in range(total_frames):
+        name = str(i).zfill(6) + ".jpg"
+        if name in names:
+            img = cv2.imread(os.path.join(folder, name))           # BGR uint8, what pth_processing ends up consuming
+            exists[i] = True
+            h, w, _ = img.shape
+            chunks.append(np.ascontiguousarray(img).reshape(-1))
+            offsets.append(off)
+            hs.append(h)
+            ws.append(w)
+            off += (h * w * 3 + 15) // 16 * 16                       # keep every crop 16-byte aligned
+    flat = np.zeros(max(off, 16), dtype=np.uint8)
+    for c, o in zip(chunks, offsets):
+        flat[o:o + c.size] = c
+    return flat, np.asarray(offsets, dtype=np.int64), np.asarray(hs, dtype=np.int32), np.asarray(ws, dtype=np.int32), exists
+
+
+def preprocess_video_and_predict(path_images="", save_path="", fps=30, total_frames=[], flag_save_prob=False,
+                                 flag_heatmaps=False, model_heatmaps=None):
+    """Returns (df_dynamic, df_static): one row per frame index, columns DICT_EMO_VIDEO; VS rows are
+    softmax probabilities, VD rows raw logits (reference :182-187)."""
+    if flag_heatmaps:
+        raise NotImplementedError("Grad-CAM heatmaps need a backward pass and are outside the accelerated path")
+    eng = config.video_engine()
+    flat, offsets, hs, ws, exists = _load_crops(path_images, total_frames)
+    n_present = int(exists.sum())
+    if n_present:
+        probs, feats = eng.vs_forward_ragged(torch.from_numpy(flat).to(eng.device), offsets, hs, ws)
+    else:
+        probs = torch.zeros((1, 7), device=eng.device)
+        feats = torch.zeros((1, 512), device=eng.device, dtype=eng.vs.dtype)
+    stat, dyn, plans = eng.video_rows(probs, feats, [exists], [fps])
+    plan = plans[0]
+    # np.array() over a list mixing float32 rows and float64 zero rows promotes to float64 (:89,182-187)
+    has_zero_row = bool((plan.stat_src < 0).any() or (plan.dyn_src < 0).any())
+    dt = np.float64 if has_zero_row else np.float32
+    cols = list(DICT_EMO_VIDEO.values())
+    df_dynamic = pd.DataFrame(dyn.cpu().numpy().astype(dt), columns=cols)
+    df_static = pd.DataFrame(stat.cpu().numpy().astype(dt), columns=cols)
+    if flag_save_prob:
+        os.makedirs(save_path, exist_ok=True)
+        df_dynamic.to_csv(os.path.join(save_path, "dynamic__{}.csv".format(os.path.basename(path_images))), index=False)
+        df_static.to_csv(os.path.join(save_path, "static__{}.csv".format(os.path.basename(path_images))), index=False)
+    return df_dynamic, df_static

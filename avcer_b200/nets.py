@@ -56,7 +56,8 @@ class VSNet:
         # A view: (8 pixels x 4 ch = 32, ox stride 2 px, oy stride 2 rows, n, ky stride 1 row)
         ops.contract(a=x, a_dim=(32, 112, 112, n, 7), a_stride=(1, 8, 2 * PAD * 4, PAD * PAD * 4, PAD * 4),
                      wt=st.wt, bias=st.bias, out=y, out_stride=(64, 112 * 64, 112 * 112 * 64), W=112, H=112, NB=n,
-                     cin=32, cout=64, taps_w=1, taps_h=7, tap_h_in_dim4=True, act=ops.ACT_RELU)
+                     cin=32, cout=64, taps_w=1, taps_h=7, tap_h_in_dim4=True, act=ops.ACT_RELU,
+                     algo_k=147)          # 7x7x3 real taps; the padded pixel/channel carry zero weights
         return y
 
     def _conv(self, x: torch.Tensor, pc: weights.PackedConv, act: int, residual: Optional[torch.Tensor] = None) -> torch.Tensor:

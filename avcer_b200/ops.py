@@ -12,7 +12,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32, ContractDesc, check
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32, ContractDesc
+from ._lib import check as _check
 
 __all__ = [
     "F32", "BF16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "dtype_code", "torch_dtype", "contract", "conv2d_nhwc",
@@ -24,6 +25,39 @@ __all__ = [
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+# Launch accounting (bench.py's `gpu_launches`) and optional per-kernel CUDA-event timing on the
+# launching stream (bench.py's roofline): PROFILE is None or a list receiving (tag, work, ev0, ev1).
+STATS = {"launches": 0}
+PROFILE = None
+
+
+def check(rc: int) -> None:
+    """Every C-ABI call below launches exactly one kernel (the _Timed ones count themselves)."""
+    STATS["launches"] += 1
+    _check(rc)
+
+
+class _Timed:
+    __slots__ = ("tag", "work", "e0")
+
+    def __init__(self, tag: str, work: float, launches: int = 1):
+        STATS["launches"] += launches
+        self.tag, self.work, self.e0 = tag, work, None
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.tag, self.work, self.e0, e1))
+        return False
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -53,7 +87,7 @@ def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], 
              cin: int, cout: int, taps_w: int = 1, taps_h: int = 1, off_w: int = 0, off_h: int = 0,
              tap_h_in_dim4: bool = False, group_cin_shift: int = 0, residual: Optional[torch.Tensor] = None,
              res_stride: Optional[Sequence[int]] = None, act: int = ACT_NONE, res_after_act: bool = False,
-             a_offset: int = 0) -> torch.Tensor:
+             a_offset: int = 0, algo_k: Optional[int] = None) -> torch.Tensor:
     """Generic implicit GEMM (see avcer_contract in include/avcer_b200.h)."""
     _cuda(a, "a")
     d = ContractDesc()
@@ -79,7 +113,9 @@ def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], 
     d.res_after_act = int(res_after_act)
     d.dtype = code
     d.out_f32 = int(code == BF16 and out.dtype == torch.float32)
-    check(_lib.load().avcer_contract(ctypes.byref(d), _stream()))
+    k_real = algo_k if algo_k is not None else taps_w * taps_h * cin
+    with _Timed("contract_bf16" if code == BF16 else "contract_f32", 2.0 * W * H * NB * cout * k_real):
+        _check(_lib.load().avcer_contract(ctypes.byref(d), _stream()))
     return out
 
 
@@ -136,8 +172,11 @@ def preprocess(src: torch.Tensor, n: int, dst: torch.Tensor, layout: int, *, off
     if heights is not None and maps is None:
         maps = torch.empty((n, 2, 224), device=src.device, dtype=torch.int16)
         check(lib.avcer_preprocess_maps(heights.data_ptr(), widths.data_ptr(), n, maps.data_ptr(), _stream()))
-    check(lib.avcer_preprocess_u8(src.data_ptr(), _ptr(offsets), _ptr(heights), _ptr(widths), _ptr(maps), n,
-                                  dst.data_ptr(), layout, _stream()))
+    # algorithmic bytes per frame: u8 in + bf16 NHWC C=3 out (fp32: 4 B/elem), SURVEY.md section 8d
+    work = n * (150528 + 150528 * (2 if layout == 1 else 4))
+    with _Timed("preprocess", work):
+        _check(lib.avcer_preprocess_u8(src.data_ptr(), _ptr(offsets), _ptr(heights), _ptr(widths), _ptr(maps), n,
+                                      dst.data_ptr(), layout, _stream()))
     return dst
 
 
@@ -161,8 +200,9 @@ def fuse_compound(p_vs: torch.Tensor, p_vd: torch.Tensor, p_a: torch.Tensor, wei
         w2 = w2a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
     lib = _lib.load()
     fn = lib.avcer_fuse_compound if p_vs.dtype == torch.float32 else lib.avcer_fuse_compound_f64
-    check(fn(p_vs.data_ptr(), p_vd.data_ptr(), p_a.data_ptr(), n, w1, w2, int(bool(ce_weights_type)),
-             int(bool(ce_mask)), labels.data_ptr(), _stream()))
+    with _Timed("fuse_compound", n * 116.0):      # 84 B in + 32 B of int64 labels out per frame
+        _check(fn(p_vs.data_ptr(), p_vd.data_ptr(), p_a.data_ptr(), n, w1, w2, int(bool(ce_weights_type)),
+                 int(bool(ce_mask)), labels.data_ptr(), _stream()))
     return labels
 
 
@@ -231,11 +271,15 @@ def lstm_cell(xproj: Optional[torch.Tensor], xidx: Optional[torch.Tensor], hproj
 PAD_MODES = {"mean": 0, "constant": 1, "repeat": 2}
 
 
-def audio_normalize_windows(wav: torch.Tensor, starts: torch.Tensor, win: int, pad_mode: str) -> torch.Tensor:
+def audio_normalize_windows(wav: torch.Tensor, starts: torch.Tensor, win: int, pad_mode: str,
+                            ends: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """wav: device fp32 buffer; chunk i = wav[starts[i]:ends[i]] (ends default: min(start+win, len(wav)))."""
     _cuda(wav, "wav")
     n_win = starts.numel()
+    if ends is None:
+        ends = torch.clamp(starts + win, max=wav.numel())
     out = torch.empty((n_win, win), device=wav.device, dtype=torch.float32)
-    check(_lib.load().avcer_audio_normalize_windows(wav.data_ptr(), wav.numel(), starts.data_ptr(), n_win, win,
+    check(_lib.load().avcer_audio_normalize_windows(wav.data_ptr(), starts.data_ptr(), ends.data_ptr(), n_win, win,
                                                     PAD_MODES[pad_mode], out.data_ptr(), _stream()))
     return out
 

@@ -189,18 +189,20 @@ class Engine:
         return stat, dyn, plans
 
     # ------------------------------------------------------------------ audio branch
-    def audio_window_logits(self, wav: torch.Tensor, plan: AudioPlan, padding: str, win: int) -> torch.Tensor:
-        """wav: device fp32 [L].  Returns per-window logits [Wn, ncls] fp32."""
-        if padding == "repeat" and bool((plan.ends - plan.starts == 0).any()):
+    def audio_window_logits(self, wav: torch.Tensor, starts: np.ndarray, ends: np.ndarray, padding: str, win: int) -> torch.Tensor:
+        """wav: device fp32 buffer (one clip, or several clips back to back with global starts/ends).
+        Returns per-window logits [Wn, ncls] fp32."""
+        if padding == "repeat" and bool((ends - starts == 0).any()):
             raise ZeroDivisionError("integer division or modulo by zero")      # data/utils.py:66 on the empty tail window
         if padding not in ops.PAD_MODES:
             raise UnboundLocalError("cannot access local variable 'a_fss' where it is not associated with a value")
-        starts = torch.from_numpy(plan.starts).to(self.device)
-        wn = plan.starts.shape[0]
+        st = torch.from_numpy(np.ascontiguousarray(starts, dtype=np.int64)).to(self.device)
+        en = torch.from_numpy(np.ascontiguousarray(ends, dtype=np.int64)).to(self.device)
+        wn = int(st.numel())
         out = torch.empty((wn, self.a.num_classes), device=self.device, dtype=torch.float32)
         for s in range(0, wn, self.a_batch):
             e = min(wn, s + self.a_batch)
-            x = ops.audio_normalize_windows(wav, starts[s:e], win, padding)
+            x = ops.audio_normalize_windows(wav, st[s:e], win, padding, ends=en[s:e])
             out[s:e].copy_(self.a.forward(x))
         return out
 
@@ -208,6 +210,29 @@ class Engine:
         lo = torch.from_numpy(np.asarray(f_lo, dtype=np.int32)).to(self.device)
         hi = torch.from_numpy(np.asarray(f_hi, dtype=np.int32)).to(self.device)
         return ops.window_to_frame_mean(logits, lo, hi, n_frames)
+
+    def audio_rows(self, wav_cat: torch.Tensor, wav_lens: Sequence[int], fps_list: Sequence[float], n_frames: Sequence[int],
+                   step: float = 0.5, window: int = 4, sr: int = 16000, padding: str = "mean"):
+        """Audio branch of several clips whose waveforms are concatenated in `wav_cat`.  Returns
+        (per-frame mean logits [sum N, ncls] with the tail rule of run.py:99-103 applied, window logits)."""
+        base = np.r_[0, np.cumsum(n_frames)]
+        woff = np.r_[0, np.cumsum(wav_lens)]
+        st_all, en_all, lo_all, hi_all, tail_src = [], [], [], [], []
+        for ci, (L, fps) in enumerate(zip(wav_lens, fps_list)):
+            ap = plan_audio(int(L), fps, step, window, sr)
+            st_all.append(ap.starts + woff[ci])
+            en_all.append(ap.ends + woff[ci])
+            nf = n_frames[ci]
+            lo_all.append(base[ci] + np.minimum(ap.f_lo, nf))
+            hi_all.append(base[ci] + np.minimum(ap.f_hi, nf))          # frame ids >= N are dropped by the isin filter (run.py:96)
+            covered = int(min(nf, ap.f_hi.max()))
+            src = np.arange(nf)
+            src[covered:] = max(covered - 1, 0)
+            tail_src.append(base[ci] + src)
+        logits = self.audio_window_logits(wav_cat, np.concatenate(st_all), np.concatenate(en_all), padding, window * sr)
+        a_mean = self.audio_frame_means(logits, np.concatenate(lo_all), np.concatenate(hi_all), int(base[-1]))
+        tail = torch.from_numpy(np.concatenate(tail_src).astype(np.int32)).to(self.device)
+        return ops.gather_rows(a_mean, tail, int(base[-1])), logits
 
     # ------------------------------------------------------------------ K4 on aligned per-frame rows
     def fuse(self, stat_video_order: torch.Tensor, dyn_video_order: torch.Tensor, audio_mean_logits: torch.Tensor,
@@ -222,29 +247,16 @@ class Engine:
 
     # ------------------------------------------------------------------ whole clips, batched
     def run_clips(self, crops_u8: torch.Tensor, exists_list: Sequence[np.ndarray], fps_list: Sequence[float],
-                  wavs: Sequence[torch.Tensor], weights_1, weights_2, ce_weights_type: bool, ce_mask: bool,
+                  wav_cat: torch.Tensor, wav_lens: Sequence[int], weights_1, weights_2, ce_weights_type: bool, ce_mask: bool,
                   step: float = 0.5, window: int = 4, sr: int = 16000, padding: str = "mean") -> Dict[str, torch.Tensor]:
-        """All clips at once.  crops_u8: device uint8 [sum present frames, 224,224,3]; wavs: device fp32.
-        Audio frames beyond a clip's last covered frame repeat the last audio row (run.py:99-103)."""
+        """All clips at once.  crops_u8: uint8 [sum present frames, 224,224,3] BGR; wav_cat: fp32 waveforms
+        back to back.  Host (pinned) tensors are copied to the device first; device tensors are used as is."""
+        if not crops_u8.is_cuda:
+            crops_u8 = crops_u8.to(self.device, non_blocking=True)
+        if not wav_cat.is_cuda:
+            wav_cat = wav_cat.to(self.device, non_blocking=True)
         probs, feats = self.vs_forward_u8(crops_u8)
         stat, dyn, plans = self.video_rows(probs, feats, exists_list, fps_list)
-        # audio: one global window list over all clips, frame ranges shifted into the global frame index
-        n_frames = [len(e) for e in exists_list]
-        base = np.r_[0, np.cumsum(n_frames)]
-        win_logits, lo_all, hi_all, tail_src = [], [], [], []
-        for ci, (wav, fps) in enumerate(zip(wavs, fps_list)):
-            ap = plan_audio(int(wav.numel()), fps, step, window, sr)
-            win_logits.append(self.audio_window_logits(wav, ap, padding, window * sr))
-            nf = n_frames[ci]
-            lo_all.append(base[ci] + np.minimum(ap.f_lo, nf))
-            hi_all.append(base[ci] + np.minimum(ap.f_hi, nf))          # frame ids >= N are dropped by the isin filter (run.py:96)
-            covered = int(min(nf, ap.f_hi.max()))
-            src = np.arange(nf)
-            src[covered:] = max(covered - 1, 0)
-            tail_src.append(base[ci] + src)
-        logits = torch.cat(win_logits, dim=0)
-        a_mean = self.audio_frame_means(logits, np.concatenate(lo_all), np.concatenate(hi_all), int(base[-1]))
-        tail = torch.from_numpy(np.concatenate(tail_src).astype(np.int32)).to(self.device)
-        a_rows = ops.gather_rows(a_mean, tail, int(base[-1]))
+        a_rows, logits = self.audio_rows(wav_cat, wav_lens, fps_list, [len(e) for e in exists_list], step, window, sr, padding)
         labels = self.fuse(stat, dyn, a_rows, weights_1, weights_2, ce_weights_type, ce_mask)
         return {"labels": labels, "stat": stat, "dyn": dyn, "audio_mean": a_rows, "window_logits": logits}

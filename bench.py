@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Benchmark of the batched inference-and-fusion path (BASELINE.json metric: end-to-end frames/sec,
+VS+VD+A+fusion).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels through the C ABI)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores
+
+A *step* = one pass of the whole path over the rank's shard of synthetic clips (BASELINE config 4,
+weak scaling: `--clips-per-gpu` clips of 60 s / 25 fps = 1500 face crops 224x224 + 960 000 audio
+samples each).  `value` is device-timed with inputs resident in HBM; `e2e` goes through the public
+call (Engine.run_clips) with pinned HOST buffers, H2D of crops + waveforms and D2H of the labels inside
+the timed region.  The inputs of one step (>= 1.8 GB of crops) are far larger than the 126 MB L2, so
+successive steps cannot be served from cache.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_FRAME_VS = 7.667e9
+METRIC = "end_to_end_frames_per_sec_vs_vd_a_fusion"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tf_burst": p["bf16_tflops"], "tf_sustained": p["bf16_tflops_sustained"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons DURING the timed region (pynvml, 100 ms period)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+                time.sleep(0.1)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_baseline(clip_frames: int, clip_windows: int, frames_sample: int = 32, windows_sample: int = 4):
+    """The oracle port of the reference algorithm on the host cores, bounded sample scaled to one clip."""
+    from avcer_b200 import get_weights_matrices as gwm, synthetic as syn
+    from oracle import audio as oa, fusion as of, video as ov
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd_vs, sd_vd = syn.make_vs_state_dict(0, "default"), syn.make_vd_state_dict(1)
+    sd_a = syn.make_audio_state_dict(2, 8, "spread", 12)
+    crops = syn.make_crops(1, frames_sample)
+    wav = syn.make_wav(2, int(16000 * (4 + 0.5 * (windows_sample - 1))) - 160)
+    ov.predict_video([crops[0]], 25, sd_vs, sd_vd)                                  # warm-up
+    t0 = time.perf_counter()
+    ov.predict_video(list(crops), 25, sd_vs, sd_vd)
+    t_frame = (time.perf_counter() - t0) / frames_sample
+    xs = np.stack([oa.zero_mean_unit_var(oa.pad_window(wav[i * 8000:i * 8000 + 64000], 64000, "mean")) for i in range(windows_sample)])
+    oa.audio_model_forward(sd_a, torch.from_numpy(xs[:1]))
+    t0 = time.perf_counter()
+    oa.audio_model_forward(sd_a, torch.from_numpy(xs))
+    t_win = (time.perf_counter() - t0) / windows_sample
+    rng = np.random.default_rng(0)
+    ps = [rng.dirichlet(np.ones(7), size=clip_frames).astype(np.float32) for _ in range(3)]
+    t0 = time.perf_counter()
+    of.fuse_labels(ps[0], ps[1], ps[2], gwm.class_weights(gwm.weights_3), [1, 1, 1], False, True)
+    t_fuse = time.perf_counter() - t0
+    per_clip = clip_frames * t_frame + clip_windows * t_win + t_fuse
+    return {"value": clip_frames / per_clip, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"oracle port (torch CPU fp32, batched): VS+VD on {frames_sample} frames, A on {windows_sample} windows, "
+                      f"fusion on {clip_frames} frames; scaled to a {clip_frames}-frame / {clip_windows}-window clip",
+            "ms_per_frame_vs_vd": t_frame * 1e3, "ms_per_window_a": t_win * 1e3}
+
+
+def run_reference_arm(args, workload):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(workload["frames_per_clip"], workload["windows_per_clip"], 16, 2)
+        if i >= args.warmup:
+            vals.append(r)
+    v = statistics.median(x["value"] for x in vals)
+    base = dict(vals[-1], value=v)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * workload["frames_per_clip"] / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload, "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips-per-gpu", type=int, default=8)
+    ap.add_argument("--clip-seconds", type=int, default=60)
+    ap.add_argument("--fps", type=int, default=25)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    args = ap.parse_args()
+
+    n_frames = args.clip_seconds * args.fps
+    n_samples = args.clip_seconds * 16000
+    from avcer_b200.pipeline import plan_audio
+
+    n_windows = len(plan_audio(n_samples, args.fps).starts)
+    workload = {"workload": f"BASELINE config 4 shard: {args.clips_per_gpu} clips/GPU x {args.clip_seconds} s @ {args.fps} fps "
+                            f"({n_frames} crops 224x224 + {n_samples} audio samples, {n_windows} windows of 4 s / step 0.5 s per clip), "
+                            "VS ResNet-50 + VD LSTM + A wav2vec2-L12 (8 classes) + fusion Rule 1 with the AV-8cl weight matrix",
+                "clips_per_gpu": args.clips_per_gpu, "frames_per_clip": n_frames, "windows_per_clip": n_windows,
+                "parallelism": f"clip-sharded x{args.gpus}", "l2_policy": "inputs (>=1.8 GB/step) larger than L2", "weights": "random-init, seeded"}
+    if args.impl == "reference":
+        return run_reference_arm(args, workload)
+
+    from avcer_b200 import dist as adist, get_weights_matrices as gwm, ops, synthetic as syn
+    from avcer_b200.pipeline import Engine
+
+    rank, world, local_rank = adist.init_from_env()
+    dev = f"cuda:{local_rank}"
+    torch.cuda.set_device(local_rank)
+    peaks = load_peaks()
+    eng = Engine(syn.make_vs_state_dict(0, "default"), syn.make_vd_state_dict(1), syn.make_audio_state_dict(2, 8, "spread", 12),
+                 precision=args.precision, device=dev, vs_batch=256, a_batch=32)
+    w1, w2 = gwm.class_weights(gwm.weights_3), [1, 1, 1]
+
+    # synthetic shard of this rank (seeded by the global clip index)
+    c = args.clips_per_gpu
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    crops_dev = torch.randint(0, 256, (c * n_frames, 224, 224, 3), dtype=torch.uint8, device=dev, generator=g)
+    wav_dev = (torch.randn(c * n_samples, device=dev, generator=g) * 0.1).contiguous()
+    exists = [np.ones(n_frames, dtype=bool) for _ in range(c)]
+    fps_list = [float(args.fps)] * c
+    wav_lens = [n_samples] * c
+    counts = [c * n_frames] * world
+
+    def step(crops, wav):
+        out = eng.run_clips(crops, exists, fps_list, wav, wav_lens, w1, w2, False, True)
+        labels = out["labels"].t().contiguous()                       # [frames, 4]
+        return adist.allgather_rows(labels, counts) if world > 1 else labels
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(crops_dev, wav_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ops.STATS["launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof = []
+    e0.record()
+    for i in range(args.steps):
+        if i == args.steps - 1:
+            ops.PROFILE = prof                                        # per-kernel events on the last timed step
+        step(crops_dev, wav_dev)
+    ops.PROFILE = None
+    e1.record()
+    barrier()
+    launches = ops.STATS["launches"] - launches0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item())
+    total_frames = world * c * n_frames
+    value = total_frames * args.steps / (ms / 1e3)
+
+    # per-kernel roofline from the profiled step
+    agg = {}
+    for tag, work, a, b in prof:
+        d = agg.setdefault(tag, [0.0, 0.0, 0])
+        d[0] += work
+        d[1] += a.elapsed_time(b)
+        d[2] += 1
+    kern = {k: {"work": v[0], "ms": v[1], "launches": v[2]} for k, v in agg.items()}
+    step_ms = ms / args.steps
+    roofline = None
+    tc = kern.get("contract_bf16") or kern.get("contract_f32")
+    if tc:
+        ach = tc["work"] / (tc["ms"] / 1e3) / 1e12
+        roofline = {"kernel": "tc_gemm_kernel (tcgen05 implicit GEMM: all VS/VD/A contractions)", "bound": "tensor", "achieved": ach,
+                    "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
+                    "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)", "traffic": None,
+                    "launches_per_step": tc["launches"], "avg_launch_us": 1e3 * tc["ms"] / tc["launches"],
+                    "share_of_step": tc["ms"] / step_ms, "algorithmic_flop_per_step": tc["work"]}
+    extra = {}
+    for tag, name in (("preprocess", "k1_preprocess"), ("fuse_compound", "k4_fusion")):
+        if tag in kern:
+            gbs = kern[tag]["work"] / (kern[tag]["ms"] / 1e3) / 1e9
+            extra[name] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                           "launches_per_step": kern[tag]["launches"], "avg_launch_us": 1e3 * kern[tag]["ms"] / kern[tag]["launches"]}
+
+    # end to end through the public call with pinned host buffers (H2D + D2H inside the timed region)
+    e2e = None
+    if not args.skip_e2e:
+        crops_host = torch.empty(crops_dev.shape, dtype=torch.uint8, pin_memory=True)
+        crops_host.copy_(crops_dev)
+        wav_host = torch.empty(wav_dev.shape, dtype=torch.float32, pin_memory=True)
+        wav_host.copy_(wav_dev)
+        del crops_dev
+        torch.cuda.empty_cache()
+        labels_host = None
+        for _ in range(max(1, args.warmup - 1)):
+            labels_host = step(crops_host, wav_host).cpu()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            labels_host = step(crops_host, wav_host).cpu()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e = {"value": total_frames * args.steps / (float(t.item()) / 1e3), "unit": "frames/s",
+               "h2d_bytes_per_step": int(crops_host.numel() + wav_host.numel() * 4),
+               "d2h_bytes_per_step": int(labels_host.numel() * 8), "api": "avcer_b200.pipeline.Engine.run_clips (host pinned inputs)"}
+        crops_dev = crops_host.to(dev)
+
+    # BASELINE config 2: VS alone, batch 256, bf16 (K1 + ResNet-50), L2 flushed between iterations
+    vs_alone = None
+    if rank == 0:
+        x256 = crops_dev[:256].contiguous()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        times = []
+        for i in range(8):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.vs_forward_u8(x256)
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                times.append(a.elapsed_time(b))
+        tm = statistics.median(times)
+        tf = 256 * FLOP_PER_FRAME_VS / (tm / 1e3) / 1e12
+        vs_alone = {"workload": "VS ResNet-50 alone, batch 256 crops 224x224, K1 + forward", "ms": tm, "frames_per_s": 256 / (tm / 1e3),
+                    "tflops": tf, "frac_of_bf16_burst_peak": tf / peaks["tf_burst"], "l2_policy": "256 MB flush between iterations"}
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.skip_cpu_baseline:
+        cpu = cpu_baseline(n_frames, n_windows)
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": workload,
+            "audio_seconds_per_sec": world * c * args.clip_seconds * args.steps / (ms / 1e3),
+            "roofline": roofline, "kernels": extra, "vs_resnet50_b256": vs_alone, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -114,6 +114,12 @@ int avcer_fuse_compound_f64(const double* p_vs, const double* p_vd, const double
                             const double* w1_host, const double* w2_host, int ce_weights_type,
                             int ce_mask, int64_t* labels, void* stream);
 
+/* data/utils.py:222-241 (get_compound_expression) as a stand-alone op: pred [n,ncols] (f32 or f64),
+ * k pairs (i1,i2) with weights (w1,w2) given on the host, optional 1/7 mask; out [n,k] f64. */
+int avcer_compound_scores(const void* pred, int64_t n, int ncols, int pred_f64,
+                          const int32_t* pairs_host, const double* w_host, int k, int ce_mask,
+                          double* out, void* stream);
+
 /* Row softmax over 7 classes in fp32, exactly data/utils.py:125-127 (max-subtract, exp, sum, div).
  * `ld` = row pitch of the input in floats (8 for the 8-class audio logits: "Other" is dropped
  * before the softmax, run.py:96). */
@@ -154,12 +160,13 @@ int avcer_lstm_cell(const float* xproj, const int32_t* xidx, const float* hproj,
                     void* h_out, int64_t ldh, int64_t n, int hidden, int first, int dtype,
                     void* stream);
 
-/* K5a: gather audio windows [start, start+win) from wav (length L), pad the tail with the chunk
- * mean ("mean"), zeros ("constant") or by tiling ("repeat") (data/utils.py:63-89), then HF
+/* K5a: gather audio chunks wav[starts[i], ends[i]) (at most `win` samples; chunks of several clips
+ * may live in one concatenated buffer), pad the tail to `win` with the chunk mean ("mean"), zeros
+ * ("constant") or by tiling ("repeat") (data/utils.py:63-89), then HF
  * zero-mean/unit-variance normalisation over all `win` samples (population variance, eps 1e-7).
  * out: [n_win, win] fp32.  pad_mode: 0 mean, 1 constant, 2 repeat. */
-int avcer_audio_normalize_windows(const float* wav, int64_t L, const int64_t* starts, int n_win,
-                                  int win, int pad_mode, float* out, void* stream);
+int avcer_audio_normalize_windows(const float* wav, const int64_t* starts, const int64_t* ends,
+                                  int n_win, int win, int pad_mode, float* out, void* stream);
 /* K5b: wav2vec2 conv layer 0 (Cin=1, k=10, s=5, bias) + LayerNorm(512) + GELU fused.
  * x: [n, t_in] fp32; y: [n, t_out_pitch, 512] (dtype), t_out = (t_in-10)/5+1 rows written. */
 int avcer_w2v_conv0_ln_gelu(const float* x, int n, int t_in, const float* w, const float* b,

@@ -1,0 +1,234 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) in the build
+container, and pins the oracle restatements against it on the way (asserts below).
+
+    python -m oracle.make_golden            # from the repo root; needs /root/reference
+
+Everything is seeded; inputs are regenerated from seeds by the tests (avcer_b200.synthetic), so the
+fixtures only hold reference OUTPUTS (plus small inputs where a seed is not enough).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from avcer_b200 import get_weights_matrices as gwm  # noqa: E402
+from avcer_b200 import synthetic as syn  # noqa: E402
+from oracle import audio as oa  # noqa: E402
+from oracle import fusion as of  # noqa: E402
+from oracle import harness  # noqa: E402
+from oracle import video as ov  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+FUSION_CONFIGS = [("w3", True, False), ("w3", False, True), ("w3", True, True), ("w3", False, False),
+                  ("w2", False, True), ("w2", True, False), ("none", False, True), ("none", True, False),
+                  ("none", False, False)]
+
+
+def fusion_weights(tag):
+    if tag == "w3":
+        return gwm.class_weights(gwm.weights_3), [1, 1, 1]
+    if tag == "w2":
+        return gwm.class_weights(gwm.weights_2), gwm.model_weights(gwm.weights_2)
+    return None, [1, 1, 1]
+
+
+def synthetic_fusion_inputs(seed=7, n=300, fps=25):
+    """DataFrames shaped like the drivers' outputs, with edge cases baked in."""
+    rng = np.random.default_rng(seed)
+    stat = rng.dirichlet(np.ones(7) * 0.7, size=n).astype(np.float32)
+    dyn = (rng.standard_normal((n, 7)) * 1.5).astype(np.float32)
+    stat[5] = 1.0 / 7.0                      # exactly on the Rule-1 threshold (float32(1/7) < 1/7 -> masked)
+    stat[6] = 0.0                            # zero row
+    dyn[7] = 0.0                             # zero logits -> uniform 1/7
+    stat[8] = stat[9]                        # duplicates -> argmax ties
+    L = int(n / fps * 16000)
+    sched = oa.window_schedule(L, fps, 0.5)
+    rows, frames = [], []
+    for (s, e, lo, hi) in sched:
+        logit = (rng.standard_normal(8) * 1.2).astype(np.float32)
+        if e - s == 0:
+            logit[:] = np.nan               # the trailing empty window of the "mean" padding
+        for f in range(lo, hi):
+            rows.append(logit)
+            frames.append(str(f).zfill(6) + ".jpg")
+    stat_df = pd.DataFrame(stat, columns=of.VIDEO_ORDER)
+    dyn_df = pd.DataFrame(dyn, columns=of.VIDEO_ORDER)
+    audio_df = pd.DataFrame(np.asarray(rows), columns=of.AUDIO_ORDER)
+    audio_df["frames"] = frames
+    return stat_df, dyn_df, audio_df
+
+
+def make_fusion():
+    import run as ref_run
+    from data.utils import get_compound_expression as ref_gce
+    from data.utils import softmax as ref_softmax
+
+    stat_df, dyn_df, audio_df = synthetic_fusion_inputs()
+    out = {"stat": stat_df.values, "dyn": dyn_df.values, "audio_rows": audio_df[of.AUDIO_ORDER].values,
+           "audio_frames": np.asarray([int(f[:-4]) for f in audio_df["frames"]], dtype=np.int64)}
+    p_vs, p_vd, p_a, loc = of.align_streams(stat_df.copy(), dyn_df.copy(), audio_df.copy(), "clip")
+    out.update(p_vs=p_vs, p_vd=p_vd, p_a=p_a)
+    assert np.array_equal(ref_softmax(dyn_df[of.AUDIO_ORDER[:7]].values), p_vd)
+    for tag, cwt, cm in FUSION_CONFIGS:
+        w1, w2 = fusion_weights(tag)
+        ref = ref_run.get_c_expr_db_pred(stat_df.copy(), dyn_df.copy(), audio_df.copy(), "clip", w1, w2, cwt, cm, False)
+        mine = of.get_c_expr_db_pred(stat_df, dyn_df, audio_df, "clip", w1, w2, cwt, cm)
+        for a, b in zip(ref[:4], mine[:4]):
+            assert np.array_equal(a, b), (tag, cwt, cm)
+        assert ref[4] == mine[4]
+        out[f"labels_{tag}_{int(cwt)}_{int(cm)}"] = np.stack(ref[:4])
+        # compound score arrays of the reference function itself, on the weighted AV stream
+        if w1:
+            fused = p_vs * w1[0] * w2[0] + p_vd * w1[1] * w2[1] + p_a * w1[2] * w2[2]
+            sc = ref_gce(fused, ref_run_com_emo(), {1: 5, 2: 6, 3: 5, 4: 6, 5: 4, 6: 2}, cwt, cm)
+            assert np.array_equal(sc, of.compound_scores(fused, cwt, cm), equal_nan=True)
+            out[f"scores_{tag}_{int(cwt)}_{int(cm)}"] = sc
+    # float64 DataFrames (zero rows appended by the video driver)
+    ref64 = ref_run.get_c_expr_db_pred(stat_df.astype(np.float64), dyn_df.astype(np.float64), audio_df.copy(), "clip",
+                                       None, [1, 1, 1], False, True, False)
+    out["labels_none_f64_0_1"] = np.stack(ref64[:4])
+    np.savez_compressed(os.path.join(OUT, "fusion.npz"), **out)
+    print("fusion.npz", len(loc), "frames")
+
+
+def ref_run_com_emo():
+    return {"Fearfully Surprised": [3, 6], "Happily Surprised": [4, 6], "Sadly Surprised": [5, 6],
+            "Disgustedly Surprised": [2, 6], "Angrily Surprised": [1, 6], "Sadly Fearful": [3, 5], "Sadly Angry": [1, 5]}
+
+
+def make_preprocess():
+    from PIL import Image
+
+    from data.utils import pth_processing as ref_pp
+    import cv2
+
+    sizes = sorted(set([1, 2, 3, 7, 64, 100, 111, 112, 150, 200, 223, 224, 225, 256, 300, 333, 448, 449, 480, 512, 640,
+                        720, 777, 1000, 1080, 1279, 1280, 1920, 2047] + list(np.random.default_rng(0).integers(8, 2000, 30))))
+    tables = np.zeros((len(sizes), 224), dtype=np.int32)
+    for i, s in enumerate(sizes):
+        ramp = np.arange(s, dtype=np.int32)
+        lo = Image.fromarray((ramp % 256).astype(np.uint8)[None, :].repeat(2, 0))
+        hi = Image.fromarray((ramp // 256).astype(np.uint8)[None, :].repeat(2, 0))
+        lo = np.asarray(lo.resize((224, 224), Image.Resampling.NEAREST))[0].astype(np.int32)
+        hi = np.asarray(hi.resize((224, 224), Image.Resampling.NEAREST))[0].astype(np.int32)
+        tables[i] = hi * 256 + lo
+        assert np.array_equal(tables[i], ov.nearest_index_table(int(s))), s
+    shapes = [(224, 224), (100, 150), (480, 640), (77, 333), (225, 223), (1080, 1920)]
+    digests = []
+    rng = np.random.default_rng(1)
+    for (h, w) in shapes:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = ref_pp(Image.fromarray(cv2.cvtColor(img, cv2.COLOR_BGR2RGB))).numpy()
+        assert np.array_equal(ref, ov.pth_processing(img)), (h, w)
+        digests.append(hashlib.sha256(ref.tobytes()).hexdigest())
+    np.savez_compressed(os.path.join(OUT, "preprocess.npz"), sizes=np.asarray(sizes, dtype=np.int32), tables=tables,
+                        shapes=np.asarray(shapes, dtype=np.int32), digests=np.asarray(digests))
+    print("preprocess.npz", len(sizes), "sizes")
+
+
+def make_video(workdir):
+    import cv2
+
+    out = {}
+    crops = syn.make_crops(11, 6)
+    x = torch.from_numpy(np.concatenate([ov.pth_processing(c) for c in crops]))
+    for init in ("spread", "default"):
+        sd = syn.make_vs_state_dict(0, init)
+        m = harness.reference_resnet(sd)
+        with torch.no_grad():
+            feat = m.extract_features(x)
+            logits = m(x)
+        o_logits, o_feat = ov.resnet50_forward(sd, x)
+        assert torch.equal(o_logits, logits) and torch.equal(o_feat, feat)
+        out[f"vs_{init}_probs"] = torch.softmax(logits, 1).numpy()
+        out[f"vs_{init}_feat"] = feat.numpy()
+    sd_vd = syn.make_vd_state_dict(1)
+    lm = harness.reference_lstm(sd_vd)
+    g = torch.Generator().manual_seed(5)
+    xw = torch.relu(torch.randn(12, 10, 512, generator=g))
+    with torch.no_grad():
+        vd = lm(xw)
+    assert (ov.lstm_forward(sd_vd, xw) - vd).abs().max() < 5e-6
+    out["vd_logits"] = vd.numpy()
+    # the stock per-frame driver on JPEG crops with gaps (two scenarios)
+    sd_vs = syn.make_vs_state_dict(0, "spread")
+    harness.save_video_weights(workdir, sd_vs, sd_vd)
+    import get_prob_video as ref_gpv   # loads the weights at import
+
+    for tag, n, fps, missing, size in (("a", 24, 25, {7, 8, 15}, 160), ("b", 20, 30, {0, 1, 11}, 224)):
+        frames = syn.make_crops(21 + len(tag), n, size)
+        clip = os.path.join(workdir, f"clip_{tag}")
+        os.makedirs(os.path.join(clip, "00"), exist_ok=True)
+        for i in range(n):
+            if i not in missing:
+                cv2.imwrite(os.path.join(clip, "00", f"{i:06d}.jpg"), frames[i])
+        df_dyn, df_stat = ref_gpv.preprocess_video_and_predict(path_images=clip, save_path=workdir, fps=fps, total_frames=n)
+        decoded = [cv2.imread(os.path.join(clip, "00", f"{i:06d}.jpg")) if i not in missing else None for i in range(n)]
+        o_dyn, o_stat = ov.predict_video(decoded, fps, sd_vs, sd_vd)
+        assert o_dyn.dtype == df_dyn.values.dtype and o_stat.dtype == df_stat.values.dtype, (o_dyn.dtype, df_dyn.values.dtype)
+        assert np.abs(o_stat - df_stat.values).max() < 1e-5 and np.abs(o_dyn - df_dyn.values).max() < 1e-4
+        out[f"drv_{tag}_dyn"] = df_dyn.values
+        out[f"drv_{tag}_stat"] = df_stat.values
+        out[f"drv_{tag}_meta"] = np.asarray([n, fps, size] + sorted(missing), dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "video.npz"), **out)
+    print("video.npz")
+
+
+def make_audio():
+    from transformers import Wav2Vec2FeatureExtractor
+
+    out = {}
+    for ncls, mod in ((8, "get_prob_audio_8_cl"), (7, "get_prob_audio_7_cl")):
+        sd = syn.make_audio_state_dict(2, ncls, "spread", 12)
+        model = harness.reference_audio_model(sd, ncls, 12)
+        ref_mod = __import__(mod)
+        for tag, L, fps, padding, step in (("a", 52800 + 123, 25, "mean", 0.5), ("b", 48000, 30, "mean", 1), ("c", 40000 - 160, 25, "repeat", 1)):
+            wav = syn.make_wav(31, L)
+            er = ref_mod.EmotionRecognition.__new__(ref_mod.EmotionRecognition)
+            er.step, er.window, er.sr, er.device, er.padding, er.flag_save_prob = step, 4, 16000, "cpu", padding, False
+            er.model_params, er.save_path = {"model_name": "m"}, ""
+            er.processor = Wav2Vec2FeatureExtractor(feature_size=1, sampling_rate=16000, padding_value=0.0, do_normalize=True,
+                                                    return_attention_mask=True)
+            er.audio_model = model
+            ref_mod.convert_mp4_to_mp3 = lambda path, sr, _w=wav: torch.from_numpy(_w)
+            df = er.load_audio_features("clip.mp4", fps)
+            rows, ids, logits = oa.predict_audio(wav, fps, sd, step=step, padding=padding)
+            ref_rows = df[of.AUDIO_ORDER[:ncls]].values
+            assert [int(f[:-4]) for f in df["frames"]] == ids.tolist()
+            assert np.nanmax(np.abs(ref_rows - rows)) < 2e-5, np.nanmax(np.abs(ref_rows - rows))
+            assert np.array_equal(np.isnan(ref_rows), np.isnan(rows))
+            # per-window logits of the reference = first row of each window's run
+            sched = oa.window_schedule(L, fps, step)
+            firsts = np.cumsum([0] + [max(hi - lo, 0) for (_, _, lo, hi) in sched])[:-1]
+            out[f"a{ncls}_{tag}_window_logits"] = ref_rows[firsts]
+            out[f"a{ncls}_{tag}_meta"] = np.asarray([L, fps, {"mean": 0, "constant": 1, "repeat": 2}[padding], int(step * 1000)], dtype=np.int64)
+            # pandas groupby mean of the reference table (what run.py:90 computes)
+            gm = df.groupby(["frames"]).mean().reset_index()
+            out[f"a{ncls}_{tag}_frame_ids"] = np.asarray([int(f[:-4]) for f in gm["frames"]], dtype=np.int64)
+            out[f"a{ncls}_{tag}_frame_means"] = gm[of.AUDIO_ORDER[:ncls]].values
+    np.savez_compressed(os.path.join(OUT, "audio.npz"), **out)
+    print("audio.npz")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with harness.reference_env() as wd:
+        # run.py imports get_prob_video, which loads the (CWD-relative) weight files at import time
+        harness.save_video_weights(wd, syn.make_vs_state_dict(0, "spread"), syn.make_vd_state_dict(1))
+        make_fusion()
+        make_preprocess()
+        make_video(wd)
+        make_audio()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,76 @@
+"""GPU: the reference's Python entry points (drop-in modules) against outputs of the unmodified
+reference drivers recorded in tests/golden (JPEG crops with gaps; waveform windows with the NaN tail)."""
+import os
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from avcer_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_preprocess_video_and_predict_dropin(cuda_lib, golden, tmp_path, tag):
+    from avcer_b200 import config, get_prob_video
+
+    g = golden["video"]
+    meta = g[f"drv_{tag}_meta"].tolist()
+    n, fps, size, missing = meta[0], meta[1], meta[2], set(meta[3:])
+    frames = syn.make_crops(21 + len(tag), n, size)
+    clip = tmp_path / f"clip_{tag}"
+    os.makedirs(clip / "00")
+    for i in range(n):
+        if i not in missing:
+            cv2.imwrite(str(clip / "00" / f"{i:06d}.jpg"), frames[i])
+    config.set_precision("fp32")
+    config.set_state_dicts(vs=syn.make_vs_state_dict(0, "spread"), vd=syn.make_vd_state_dict(1))
+    df_dyn, df_stat = get_prob_video.preprocess_video_and_predict(path_images=str(clip), save_path=str(tmp_path), fps=fps,
+                                                                  total_frames=n, flag_save_prob=True)
+    assert list(df_dyn.columns) == ["Neutral", "Happiness", "Sadness", "Surprise", "Fear", "Disgust", "Anger"]
+    assert df_stat.values.dtype == g[f"drv_{tag}_stat"].dtype and df_dyn.values.dtype == g[f"drv_{tag}_dyn"].dtype
+    assert np.abs(df_stat.values - g[f"drv_{tag}_stat"]).max() < 1e-5
+    assert np.abs(df_dyn.values - g[f"drv_{tag}_dyn"]).max() < 1e-4
+    assert os.path.exists(tmp_path / f"static__clip_{tag}.csv") and os.path.exists(tmp_path / f"dynamic__clip_{tag}.csv")
+    # bf16 mode on the same clip
+    config.set_precision("bf16")
+    df_dyn16, df_stat16 = get_prob_video.preprocess_video_and_predict(path_images=str(clip), fps=fps, total_frames=n)
+    assert np.abs(df_stat16.values - g[f"drv_{tag}_stat"]).max() < 6e-3
+    config.reset()
+
+
+@pytest.mark.parametrize("ncls,tag", [(8, "a"), (8, "b"), (7, "c")])
+def test_audio_driver_dropin(cuda_lib, golden, ncls, tag, monkeypatch):
+    from avcer_b200 import config, get_prob_audio_7_cl, get_prob_audio_8_cl
+
+    g = golden["audio"]
+    L, fps, pad, step = (int(v) for v in g[f"a{ncls}_{tag}_meta"])
+    padding = ["mean", "constant", "repeat"][pad]
+    wav = syn.make_wav(31, L)
+    mod = get_prob_audio_8_cl if ncls == 8 else get_prob_audio_7_cl
+    monkeypatch.setattr(get_prob_audio_8_cl, "convert_mp4_to_mp3", lambda path, sr: torch.from_numpy(wav))
+    config.set_precision("fp32")
+    config.set_state_dicts(audio={ncls: syn.make_audio_state_dict(2, ncls, "spread", 12)})
+    df = mod.preprocess_audio_and_predict(path_video="clip.mp4", path_weights="w", fps=fps, step=step / 1000, padding=padding,
+                                          flag_save_prob=False)
+    names = ["Neutral", "Anger", "Disgust", "Fear", "Happiness", "Sadness", "Surprise", "Other"][:ncls]
+    assert list(df.columns) == names + ["frames"]
+    gm = df.groupby(["frames"]).mean().reset_index()
+    assert [int(f[:-4]) for f in gm["frames"]] == g[f"a{ncls}_{tag}_frame_ids"].tolist()
+    ref = g[f"a{ncls}_{tag}_frame_means"]
+    assert np.array_equal(np.isnan(gm[names].values), np.isnan(ref))
+    assert np.nanmax(np.abs(gm[names].values - ref)) < 1e-4
+    config.reset()
+
+
+def test_audio_driver_repeat_padding_raises_like_reference(cuda_lib, monkeypatch):
+    from avcer_b200 import config, get_prob_audio_8_cl
+
+    wav = syn.make_wav(1, 48000)        # multiple of step_a -> empty tail window -> ZeroDivisionError (data/utils.py:66)
+    monkeypatch.setattr(get_prob_audio_8_cl, "convert_mp4_to_mp3", lambda path, sr: torch.from_numpy(wav))
+    config.set_state_dicts(audio={8: syn.make_audio_state_dict(2, 8, "spread", 1)})
+    with pytest.raises(ZeroDivisionError):
+        get_prob_audio_8_cl.preprocess_audio_and_predict(path_video="clip.mp4", path_weights="w", fps=25, step=1, padding="repeat")
+    config.reset()

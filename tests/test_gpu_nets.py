@@ -1,0 +1,142 @@
+"""GPU parity of the VS / VD / A device forwards (all contractions through avcer_contract) against
+the oracle on identical seeded weights and inputs, and against the reference golden outputs.
+
+Tolerances (per-class probabilities, absolute):
+  fp32 mode : 1e-5   (north star)
+  bf16 mode : 2e-3   (north star) with PyTorch-default random init -- the init the north star names;
+              6e-3 with the deliberately wide "spread" init (logit range ~5), where
+              bf16 storage of ~50 stacked layers is simply coarser than 2e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+from avcer_b200 import synthetic as syn
+from oracle import audio as oa
+from oracle import video as ov
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = {("fp32", "spread"): 1e-5, ("fp32", "default"): 1e-5, ("bf16", "default"): 2e-3, ("bf16", "spread"): 6e-3}
+
+
+def _vs_probs(sd, prec, crops):
+    from avcer_b200 import nets, ops
+
+    net = nets.VSNet(sd, prec, DEV)
+    x = net.alloc_input(len(crops))
+    ops.preprocess(torch.from_numpy(crops).to(DEV), len(crops), x, net.input_layout)
+    probs, feat = net.forward(x)
+    return probs.cpu().numpy(), feat.float().cpu().numpy()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("init", ["spread", "default"])
+def test_vs_matches_reference_golden(cuda_lib, golden, prec, init):
+    g = golden["video"]
+    crops = syn.make_crops(11, 6)
+    probs, feat = _vs_probs(syn.make_vs_state_dict(0, init), prec, crops)
+    err = np.abs(probs - g[f"vs_{init}_probs"]).max()
+    assert err < TOL[(prec, init)], err
+    ref_feat = np.maximum(g[f"vs_{init}_feat"], 0)
+    assert np.abs(feat - ref_feat).max() < (2e-4 if prec == "fp32" else 0.15)
+
+
+def test_vs_batch_invariance_and_tails(cuda_lib):
+    """Size-independent property: a crop's output does not depend on its batch position or batch size
+    (M-tile boxes, tail tiles and persistent scheduling must not leak between images)."""
+    crops = syn.make_crops(5, 37)
+    sd = syn.make_vs_state_dict(0, "spread")
+    p_all, f_all = _vs_probs(sd, "bf16", crops)
+    p_one, f_one = _vs_probs(sd, "bf16", crops[7:8])
+    p_rev, _ = _vs_probs(sd, "bf16", crops[::-1].copy())
+    assert np.array_equal(p_all[7:8], p_one) and np.array_equal(f_all[7:8], f_one)
+    assert np.array_equal(p_all[::-1], p_rev)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_vd_matches_reference_golden(cuda_lib, golden, prec):
+    from avcer_b200 import nets
+
+    gen = torch.Generator().manual_seed(5)
+    xw = torch.relu(torch.randn(12, 10, 512, generator=gen))
+    net = nets.VDNet(syn.make_vd_state_dict(1), prec, DEV)
+    feats = xw.reshape(120, 512).to(DEV).to(net.dtype)
+    wins = torch.arange(120, dtype=torch.int32).view(12, 10).t().contiguous().to(DEV)
+    out = net.forward(feats, wins).cpu()
+    ref = torch.from_numpy(golden["video"]["vd_logits"])
+    perr = (torch.softmax(out, 1) - torch.softmax(ref, 1)).abs().max().item()
+    assert perr < (1e-5 if prec == "fp32" else 4e-3), perr
+    assert (out - ref).abs().max().item() < (2e-5 if prec == "fp32" else 0.03)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("ncls", [8, 7])
+def test_audio_matches_reference_golden(cuda_lib, golden, prec, ncls):
+    from avcer_b200 import nets, ops, pipeline
+
+    g = golden["audio"]
+    L, fps, pad, step = (int(v) for v in g[f"a{ncls}_a_meta"])
+    wav = syn.make_wav(31, L)
+    net = nets.ANet(syn.make_audio_state_dict(2, ncls, "spread", 12), prec, DEV)
+    ap = pipeline.plan_audio(L, fps, step / 1000)
+    x = ops.audio_normalize_windows(torch.from_numpy(wav).to(DEV), torch.from_numpy(ap.starts).to(DEV), 64000, "mean")
+    out = net.forward(x).cpu().numpy()
+    ref = g[f"a{ncls}_a_window_logits"]
+    assert out.shape == ref.shape
+    p = torch.softmax(torch.from_numpy(out[:, :7]), 1).numpy()
+    pr = torch.softmax(torch.from_numpy(ref[:, :7]), 1).numpy()
+    assert np.abs(p - pr).max() < (1e-5 if prec == "fp32" else 6e-3), np.abs(p - pr).max()
+    assert np.abs(out - ref).max() < (1e-4 if prec == "fp32" else 0.06)
+
+
+def test_audio_padding_modes_and_nan_window(cuda_lib, golden):
+    from avcer_b200 import ops, pipeline
+
+    g = golden["audio"]
+    L, fps, pad, step = (int(v) for v in g["a8_b_meta"])                    # L multiple of step_a -> trailing empty window
+    wav = syn.make_wav(31, L)
+    ap = pipeline.plan_audio(L, fps, step / 1000)
+    wd = torch.from_numpy(wav).to(DEV)
+    st = torch.from_numpy(ap.starts).to(DEV)
+    for mode in ("mean", "constant"):
+        x = ops.audio_normalize_windows(wd, st, 64000, mode).cpu().numpy()
+        for i, (s, e) in enumerate(zip(ap.starts, ap.ends)):
+            ref = oa.zero_mean_unit_var(oa.pad_window(wav[s:e], 64000, mode))
+            if np.isnan(ref).any():
+                assert np.isnan(x[i]).all()
+            else:
+                assert np.abs(x[i] - ref).max() < 5e-6 * max(1.0, np.abs(ref).max())
+    L2 = 40000 - 160
+    wav2 = syn.make_wav(31, L2)
+    ap2 = pipeline.plan_audio(L2, 25, 1)
+    x = ops.audio_normalize_windows(torch.from_numpy(wav2).to(DEV), torch.from_numpy(ap2.starts).to(DEV), 64000, "repeat").cpu().numpy()
+    for i, (s, e) in enumerate(zip(ap2.starts, ap2.ends)):
+        ref = oa.zero_mean_unit_var(oa.pad_window(wav2[s:e], 64000, "repeat"))
+        assert np.abs(x[i] - ref).max() < 2e-5
+
+
+def test_contract_against_oracle_conv(cuda_lib):
+    """avcer_contract unit cases vs torch CPU fp32 convolutions: odd spatial sizes, tail tiles,
+    stride-2 views, residual + ReLU, both backends."""
+    import torch.nn.functional as F
+    from avcer_b200 import ops
+
+    gen = torch.Generator().manual_seed(0)
+    for dtype, tol in ((torch.float32, 2e-4), (torch.bfloat16, 0.05)):
+        for (n, h, w, cin, cout, k, stride, res) in ((3, 55, 55, 64, 64, 3, 1, False), (2, 28, 28, 128, 512, 1, 1, True),
+                                                     (5, 55, 55, 256, 128, 1, 2, False), (7, 7, 7, 512, 512, 3, 1, False),
+                                                     (1, 14, 14, 256, 256, 3, 1, True)):
+            x = torch.randn(n, h, w, cin, generator=gen).to(dtype)
+            w4 = (torch.randn(cout, cin, k, k, generator=gen) / (cin * k * k) ** 0.5).to(dtype)
+            b = torch.randn(cout, generator=gen)
+            pad = (k - 1) // 2
+            ref = F.conv2d(x.float().permute(0, 3, 1, 2), w4.float(), b, stride=stride, padding=pad).permute(0, 2, 3, 1)
+            r = torch.randn(ref.shape, generator=gen).to(dtype) if res else None
+            if res:
+                ref = ref + r.float()
+            ref = F.relu(ref)
+            wt = w4.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+            got = ops.conv2d_nhwc(x.to(DEV), wt.to(DEV), b.to(DEV), kh=k, kw=k, stride=stride, pad_h=pad, pad_w=pad,
+                                  residual=None if r is None else r.to(DEV), act=ops.ACT_RELU).float().cpu()
+            assert (got - ref).abs().max().item() < tol, (dtype, n, h, w, cin, cout, k, stride)

@@ -1,0 +1,107 @@
+"""CPU: host-side index plans, weight packer and the C-ABI surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from avcer_b200 import _lib, pipeline, synthetic as syn, weights
+from oracle import audio as oa
+from oracle import video as ov
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_plan_video_matches_frame_loop():
+    rng = np.random.default_rng(0)
+    for _ in range(400):
+        n = int(rng.integers(1, 90))
+        step = int(rng.integers(1, 13))
+        ex = rng.random(n) >= rng.choice([0.0, 0.05, 0.3, 0.8, 1.0])
+        a = pipeline.plan_video(ex, step)
+        s, w, ss, ds = ov.plan_video(list(ex), step)
+        assert np.array_equal(a.samples, s) and np.array_equal(a.windows, w)
+        assert np.array_equal(a.stat_src, ss) and np.array_equal(a.dyn_src, ds)
+
+
+def test_plan_video_edge_cases():
+    p = pipeline.plan_video(np.zeros(7, bool), 5)          # no crop at all: all zero rows, no windows
+    assert p.windows.shape == (0, 10) and (p.stat_src == -1).all() and (p.dyn_src == -1).all()
+    p = pipeline.plan_video(np.ones(11, bool), 5)
+    assert p.samples.tolist() == [0, 5, 10] and p.windows[0].tolist() == [0] * 10 and p.windows[2].tolist() == [0] * 8 + [1, 2]
+    assert pipeline.vd_step(25) == 5 and pipeline.vd_step(30) == 6 and pipeline.vd_step(24) == 5 and pipeline.vd_step(60) == 12
+
+
+def test_plan_audio_matches_window_loop():
+    for L in [0, 1, 7999, 8000, 64000, 160000, 159840, 960000, 123457]:
+        for fps in [25, 30, 24, 29.97, 60]:
+            for step in [0.5, 1]:
+                ap = pipeline.plan_audio(L, fps, step)
+                sch = oa.window_schedule(L, fps, step)
+                got = [tuple(int(v) for v in x) for x in zip(ap.starts, ap.ends, ap.f_lo, ap.f_hi)]
+                assert got == [tuple(x) for x in sch]
+    # C1 of BASELINE.json: 10 s clip -> 21 windows, the last one empty
+    ap = pipeline.plan_audio(160000, 25)
+    assert len(ap.starts) == 21 and ap.starts[-1] == ap.ends[-1] == 160000
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "avcer_b200.h")).read()
+    declared = set(re.findall(r"\b(avcer_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("avcer_contract_desc")
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/avcer_b200.h but not exported"
+    assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
+    assert _lib.load().avcer_version() >= 100
+
+
+def test_no_cpu_fallback_without_device():
+    if torch.cuda.is_available():
+        pytest.skip("a device is visible")
+    with pytest.raises(_lib.AvcerError):
+        _lib.require_device()
+    from avcer_b200 import ops
+
+    with pytest.raises(_lib.AvcerError):
+        ops.softmax7(torch.zeros(4, 7))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "avcer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_bn_fold_and_tap_major_layout():
+    sd = syn.make_vs_state_dict(0, "spread")
+    w = weights.pack_vs(sd, "cpu", torch.float32)
+    x = torch.randn(2, 64, 9, 9)
+    blk = w["blocks"][0]
+    ref = F.batch_norm(F.conv2d(x, sd["layer1.0.conv2.weight"], padding=1), sd["layer1.0.batch_norm2.running_mean"],
+                       sd["layer1.0.batch_norm2.running_var"], sd["layer1.0.batch_norm2.weight"], sd["layer1.0.batch_norm2.bias"],
+                       False, eps=1e-3)
+    w4 = blk["conv2"].wt.view(64, 3, 3, 64).permute(0, 3, 1, 2)
+    got = F.conv2d(x, w4, blk["conv2"].bias, padding=1)
+    assert (got - ref).abs().max() < 1e-4
+    # stem layout [64][7 rows][8 px][4 ch] with zero pixel 7 / channel 3
+    st = w["stem"].wt.view(64, 7, 8, 4)
+    assert st[:, :, 7].abs().max() == 0 and st[:, :, :, 3].abs().max() == 0
+    assert len(w["blocks"]) == 16 and sum("ds" in b for b in w["blocks"]) == 4
+
+
+def test_audio_pack_shapes():
+    sd = syn.make_audio_state_dict(2, 8, "spread", 2)
+    w = weights.pack_audio(sd, "cpu", torch.float32)
+    assert w["pos_w"].shape == (1024, 128 * 64) and w["convs"][0][0].shape == (512, 3 * 512)
+    assert w["layers"][0]["wqkv"].shape == (3072, 1024) and w["td0_w"].shape == (1024, 5 * 1024) and w["num_classes"] == 8
+    # weight-norm fold equals the oracle's
+    eff = oa.pos_conv_weight(sd)
+    assert (w["pos_w"].view(1024, 128, 64).permute(0, 2, 1) - eff).abs().max() < 1e-6

@@ -1,0 +1,106 @@
+"""CPU: the oracle restatements against the golden vectors produced by the unmodified reference
+(oracle/make_golden.py).  These pin the checker that the GPU parity tests rely on."""
+import hashlib
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from avcer_b200 import get_weights_matrices as gwm
+from avcer_b200 import synthetic as syn
+from oracle import audio as oa
+from oracle import fusion as of
+from oracle import video as ov
+from oracle.make_golden import FUSION_CONFIGS, fusion_weights, synthetic_fusion_inputs
+
+
+def test_fusion_labels_match_reference(golden):
+    g = golden["fusion"]
+    stat_df, dyn_df, audio_df = synthetic_fusion_inputs()
+    assert np.array_equal(stat_df.values, g["stat"]) and np.array_equal(dyn_df.values, g["dyn"])
+    for tag, cwt, cm in FUSION_CONFIGS:
+        w1, w2 = fusion_weights(tag)
+        got = of.get_c_expr_db_pred(stat_df, dyn_df, audio_df, "clip", w1, w2, cwt, cm)
+        assert np.array_equal(np.stack(got[:4]), g[f"labels_{tag}_{int(cwt)}_{int(cm)}"]), (tag, cwt, cm)
+
+
+def test_fusion_float64_frames(golden):
+    g = golden["fusion"]
+    stat_df, dyn_df, audio_df = synthetic_fusion_inputs()
+    got = of.get_c_expr_db_pred(stat_df.astype(np.float64), dyn_df.astype(np.float64), audio_df, "clip", None, [1, 1, 1], False, True)
+    assert np.array_equal(np.stack(got[:4]), g["labels_none_f64_0_1"])
+
+
+def test_compound_scores_match_reference(golden):
+    g = golden["fusion"]
+    for tag, cwt, cm in FUSION_CONFIGS:
+        w1, w2 = fusion_weights(tag)
+        if not w1:
+            continue
+        fused = g["p_vs"] * w1[0] * w2[0] + g["p_vd"] * w1[1] * w2[1] + g["p_a"] * w1[2] * w2[2]
+        assert np.array_equal(of.compound_scores(fused, cwt, cm), g[f"scores_{tag}_{int(cwt)}_{int(cm)}"], equal_nan=True)
+
+
+def test_weight_tables_match_run_py():
+    # run.py:316-344 literal == weights_3[:7].T
+    w = gwm.class_weights(gwm.weights_3)
+    assert w[0][0] == 0.89900098 and w[1][3] == 0.93791526 and w[2][5] == 0.48672896
+    assert gwm.model_weights(gwm.weights_3) == [0.16000000000000003, 0.36000000000000004, 0.01]
+
+
+def test_nearest_tables_match_pillow(golden):
+    g = golden["preprocess"]
+    for s, t in zip(g["sizes"], g["tables"]):
+        assert np.array_equal(ov.nearest_index_table(int(s)), t), s
+
+
+def test_preprocess_digests(golden):
+    g = golden["preprocess"]
+    rng = np.random.default_rng(1)
+    for (h, w), d in zip(g["shapes"], g["digests"]):
+        img = rng.integers(0, 256, (int(h), int(w), 3), dtype=np.uint8)
+        assert hashlib.sha256(ov.pth_processing(img).tobytes()).hexdigest() == str(d)
+
+
+@pytest.mark.parametrize("init", ["spread", "default"])
+def test_vs_oracle_matches_reference(golden, init):
+    g = golden["video"]
+    crops = syn.make_crops(11, 6)[:3]
+    x = torch.from_numpy(np.concatenate([ov.pth_processing(c) for c in crops]))
+    logits, feat = ov.resnet50_forward(syn.make_vs_state_dict(0, init), x)
+    assert np.abs(torch.softmax(logits, 1).numpy() - g[f"vs_{init}_probs"][:3]).max() < 1e-6
+    assert np.abs(feat.numpy() - g[f"vs_{init}_feat"][:3]).max() < 1e-4
+
+
+def test_vd_oracle_matches_reference(golden):
+    gen = torch.Generator().manual_seed(5)
+    xw = torch.relu(torch.randn(12, 10, 512, generator=gen))
+    out = ov.lstm_forward(syn.make_vd_state_dict(1), xw).numpy()
+    assert np.abs(out - golden["video"]["vd_logits"]).max() < 1e-5
+
+
+def test_audio_oracle_matches_reference(golden):
+    g = golden["audio"]
+    L, fps, pad, step = (int(v) for v in g["a8_a_meta"])
+    wav = syn.make_wav(31, L)
+    rows, ids, logits = oa.predict_audio(wav, fps, syn.make_audio_state_dict(2, 8, "spread", 12), step=step / 1000, padding="mean")
+    assert np.nanmax(np.abs(logits - g["a8_a_window_logits"])) < 5e-5
+    df = pd.DataFrame(rows)
+    df["frames"] = [str(i).zfill(6) + ".jpg" for i in ids]
+    gm = df.groupby("frames").mean().reset_index()
+    assert [int(f[:-4]) for f in gm["frames"]] == g["a8_a_frame_ids"].tolist()
+    assert np.nanmax(np.abs(gm[list(range(8))].values - g["a8_a_frame_means"])) < 5e-5
+
+
+def test_audio_schedule_nan_window(golden):
+    # L multiple of step_a: trailing empty window -> NaN logits for exactly one extra frame id
+    g = golden["audio"]
+    L, fps, pad, step = (int(v) for v in g["a8_b_meta"])
+    assert L % int(step / 1000 * 16000) == 0
+    wl = g["a8_b_window_logits"]
+    assert np.isnan(wl[-1]).all() and not np.isnan(wl[:-1]).any()
+    sched = oa.window_schedule(L, fps, step / 1000)
+    assert sched[-1][0] == sched[-1][1] == L
+    with pytest.raises(ZeroDivisionError):
+        oa.pad_window(np.zeros(0, np.float32), 64000, "repeat")

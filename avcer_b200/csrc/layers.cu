@@ -526,13 +526,16 @@ static int launch_attention(const void* qkv, int n, int t, int heads, float scal
   return check_launch("attention");
 }
 
+namespace avcer {
+int attention_tc(const void* qkv, int n, int t, int heads, int dh, float scale, void* out, cudaStream_t st);   // attention_tc.cu
+}
+
 extern "C" int avcer_attention(const void* qkv, int n, int t, int heads, int dh, float scale, void* out, int dtype,
                                void* stream) {
   AVCER_REQUIRE(dh == 32 || dh == 64, "attention: head dim must be 32 or 64");
   if (n == 0) return 0;
   cudaStream_t st = as_stream(stream);
-  if (dtype == AVCER_BF16) return dh == 64 ? launch_attention<bf16, 64>(qkv, n, t, heads, scale, out, st)
-                                           : launch_attention<bf16, 32>(qkv, n, t, heads, scale, out, st);
+  if (dtype == AVCER_BF16) return attention_tc(qkv, n, t, heads, dh, scale, out, st);
   if (dtype == AVCER_F32) return dh == 64 ? launch_attention<float, 64>(qkv, n, t, heads, scale, out, st)
                                           : launch_attention<float, 32>(qkv, n, t, heads, scale, out, st);
   return set_error("attention: unknown dtype %d", dtype);

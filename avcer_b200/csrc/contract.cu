@@ -62,17 +62,17 @@ static void choose_box(int W, int H, int NB, int* bw, int* bh, int* bn) {
   }
 }
 
-template <int BN, int BK, bool OUT_F32>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcGemmParams& p, int grid,
-                     cudaStream_t st) {
-  using Cfg = TcGemmCfg<BN, BK>;
-  auto kern = tc_gemm_kernel<BN, BK, OUT_F32>;
+template <int BN, int BK, int MODE>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
+                     const TcGemmParams& p, int grid, cudaStream_t st) {
+  using Cfg = TcGemmCfg<BN, BK, MODE>;
+  auto kern = tc_gemm_kernel<BN, BK, MODE>;
   static bool attr_done = false;
   if (!attr_done) {
     AVCER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done = true;
   }
-  kern<<<grid, 256, Cfg::SMEM, st>>>(ta, tb, p);
+  kern<<<grid, 256, Cfg::SMEM, st>>>(ta, tb, tc, tr, p);
   return check_launch("tc_gemm_kernel");
 }
 
@@ -91,16 +91,13 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   AVCER_REQUIRE(d->a_stride[0] == 1, "contract: a_stride[0] must be 1");
   const int BK = (d->cin % 64 == 0) ? 64 : 32;
   AVCER_REQUIRE(d->cin % BK == 0, "contract(bf16): cin=%d must be a multiple of 32", d->cin);
-  AVCER_REQUIRE(d->cout % 32 == 0, "contract(bf16): cout=%d must be a multiple of 32", d->cout);
+  AVCER_REQUIRE(d->cout % 64 == 0, "contract(bf16): cout=%d must be a multiple of 64", d->cout);
+  AVCER_REQUIRE(!(d->out_f32 && d->residual), "contract(bf16): fp32 output does not take a residual");
   AVCER_REQUIRE((reinterpret_cast<uintptr_t>(d->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->wt) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
                 "contract(bf16): a/wt/out must be 16-byte aligned");
-  int BN;
-  if (d->group_cin_shift != 0) BN = 64;
-  else if (d->cout % 128 == 0) BN = 128;
-  else if (d->cout % 64 == 0) BN = 64;
-  else BN = 32;
-  if (BK == 32 && BN > 64) BN = 64;   // stem: Cout = 64
+  int BN = (d->group_cin_shift != 0 || d->cout % 128 != 0) ? 64 : 128;
+  if (BK == 32) BN = 64;   // stem: Cout = 64
 
   TcGemmParams p{};
   choose_box(d->W, d->H, d->NB, &p.bw, &p.bh, &p.bn);
@@ -118,9 +115,7 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   p.a_c0_per_ntile = d->group_cin_shift;   // BN == 64 == one group per N tile
   p.Cout = d->cout;
   p.out_sw = d->out_stride[0]; p.out_sh = d->out_stride[1]; p.out_sn = d->out_stride[2];
-  p.res_sw = d->res_stride[0]; p.res_sh = d->res_stride[1]; p.res_sn = d->res_stride[2];
   p.bias = d->bias;
-  p.residual = static_cast<const __nv_bfloat16*>(d->residual);
   p.out = d->out;
   p.act = d->act;
   p.res_after_act = d->res_after_act;
@@ -147,16 +142,39 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
     uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
     if (encode_map(&tb, d->wt, 2, dims, strides, box, swz)) return 1;
   }
+  // output / residual maps: (cout, w, h, n) boxes of the same shape as the activation box
+  CUtensorMap tc = ta, tr = ta;
+  const int mode = d->out_f32 ? OUT_DIRECT_F32 : (d->residual ? OUT_TMA_RES : OUT_TMA);
+  if (mode != OUT_DIRECT_F32) {
+    const int64_t ext[3] = {d->W, d->H, d->NB};
+    auto make_out_map = [&](CUtensorMap* m, const void* base, const int64_t* str) -> int {
+      uint64_t dims[5] = {(uint64_t)d->cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->NB, 1};
+      uint64_t strides[4];
+      for (int i = 0; i < 3; ++i) {
+        int64_t sv = ext[i] > 1 ? str[i] : (int64_t)1 << 24;          // extent-1 dims: any legal pitch
+        if (sv % 8 != 0 || sv <= 0) return set_error("contract(bf16): out/residual stride[%d]=%lld must be a positive multiple of 8", i, (long long)sv);
+        strides[i] = (uint64_t)sv * 2;
+      }
+      strides[3] = (uint64_t)1 << 30;
+      uint32_t box[5] = {64u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, 1u};
+      return encode_map(m, base, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    };
+    if (make_out_map(&tc, d->out, d->out_stride)) return 1;
+    if (mode == OUT_TMA_RES) {
+      AVCER_REQUIRE((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0, "contract(bf16): residual must be 16-byte aligned");
+      if (make_out_map(&tr, d->residual, d->res_stride)) return 1;
+    }
+  }
   const int grid = p.num_tiles < num_sms_cached() ? p.num_tiles : num_sms_cached();
-  const bool f32 = d->out_f32 != 0;
-#define AVCER_TC_CASE(bn, bk)                                                         \
-  if (BN == bn && BK == bk)                                                           \
-    return f32 ? launch_tc<bn, bk, true>(ta, tb, p, grid, st) : launch_tc<bn, bk, false>(ta, tb, p, grid, st);
+#define AVCER_TC_CASE(bn, bk)                                                                     \
+  if (BN == bn && BK == bk) {                                                                     \
+    if (mode == OUT_TMA) return launch_tc<bn, bk, OUT_TMA>(ta, tb, tc, tr, p, grid, st);          \
+    if (mode == OUT_TMA_RES) return launch_tc<bn, bk, OUT_TMA_RES>(ta, tb, tc, tr, p, grid, st);  \
+    return launch_tc<bn, bk, OUT_DIRECT_F32>(ta, tb, tc, tr, p, grid, st);                        \
+  }
   AVCER_TC_CASE(128, 64)
   AVCER_TC_CASE(64, 64)
-  AVCER_TC_CASE(32, 64)
   AVCER_TC_CASE(64, 32)
-  AVCER_TC_CASE(32, 32)
 #undef AVCER_TC_CASE
   return set_error("contract: no tensor-core instantiation for BN=%d BK=%d", BN, BK);
 }

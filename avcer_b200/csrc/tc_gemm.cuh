@@ -12,8 +12,13 @@
 // * Both land in shared memory in the 128B (or 64B) swizzled K-major layout that
 //   tcgen05.mma consumes directly; accumulators live in TMEM (2 x BN fp32 columns, double
 //   buffered so the epilogue of tile i overlaps the MMAs of tile i+1).
+// * Epilogue (bf16 output): the residual tile is prefetched by TMA into shared memory while the
+//   MMAs run; 4 warps read the accumulator with tcgen05.ld, add bias / residual, apply the
+//   activation, and write the bf16 tile into a 128B-swizzled staging buffer (bank-conflict free);
+//   one thread hands it to a TMA store (cp.async.bulk.tensor ... bulk_group), which clips partial
+//   boxes at the tensor border -- no per-row masks, every global transaction is a full line.
 // * Warp roles: warp0 = TMA producer, warp1 = MMA issuer (one elected lane), warp2 = TMEM
-//   allocator, warps4-7 = epilogue (tcgen05.ld -> bias/residual/activation -> global).
+//   allocator, warps4-7 = epilogue.
 // * Persistent: grid = min(#tiles, #SM); tiles are strided across CTAs, N fastest so CTAs of
 //   one wave share the same activation box in L2.
 #pragma once
@@ -22,23 +27,23 @@
 namespace avcer {
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+// Output modes of the kernel template
+enum OutMode : int { OUT_TMA = 0, OUT_TMA_RES = 1, OUT_DIRECT_F32 = 2 };
 
 struct TcGemmParams {
   int num_tiles, tiles_n;
   int bw, bh, bn;          // box extents of one M tile (bw*bh*bn <= 128)
   int tw, th, tn;          // tiles along w / h / n
-  int W, H, NB;            // valid output extents (epilogue mask)
+  int W, H, NB;            // valid output extents (direct-store epilogue mask)
   int taps_w, taps_h;      // filter taps
   int off_w, off_h;        // coordinate offset of tap (0,0)  (= -padding)
   int tap_h_in_dim4;       // 1: the h-tap index is coordinate 4 of the A map (stem: strided rows)
   int kchunks;             // K chunks (of BK) per tap
   int a_c0_per_ntile;      // channel-coordinate shift per N tile (grouped conv), else 0
   int Cout;
-  long long out_sw, out_sh, out_sn;   // output element strides of (w, h, n); channels contiguous
-  long long res_sw, res_sh, res_sn;   // residual strides (same meaning)
+  long long out_sw, out_sh, out_sn;   // output element strides of (w, h, n)   (direct-store mode)
   const float* bias;                  // [Cout] or nullptr
-  const __nv_bfloat16* residual;      // or nullptr
-  void* out;                          // bf16 (or fp32 when OUT_F32)
+  void* out;                          // fp32 output (direct-store mode)
   int act;
   int res_after_act;     // 0: act(acc + bias + res)   1: act(acc + bias) + res
 };
@@ -47,38 +52,48 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-template <int BN, int BK>
+template <int BN, int BK, int MODE>
 struct TcGemmCfg {
   static constexpr int BM = 128;
   static constexpr int A_STAGE = BM * BK * 2;
   static constexpr int B_STAGE = BN * BK * 2;
   static constexpr int STAGE = A_STAGE + B_STAGE;
-  static constexpr int BUDGET = 200 * 1024;
-  static constexpr int STAGES = (BUDGET / STAGE) > 8 ? 8 : (BUDGET / STAGE);
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/;
+  static constexpr int C_TILE = BM * BN * 2;                                   // one bf16 staging tile
+  static constexpr int C_BYTES = (MODE == OUT_DIRECT_F32) ? 0 : 2 * C_TILE;    // double buffered
+  static constexpr int R_BYTES = (MODE == OUT_TMA_RES) ? 2 * C_TILE : 0;
+  static constexpr int BUDGET = 224 * 1024;
+  static constexpr int FIT = (BUDGET - C_BYTES - R_BYTES) / STAGE;
+  static constexpr int STAGES = FIT > 8 ? 8 : FIT;
+  static constexpr int SMEM = STAGES * STAGE + C_BYTES + R_BYTES + 1024 /*align slack*/;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr uint32_t LAYOUT = (BK == 64) ? 2u : 4u;      // SWIZZLE_128B : SWIZZLE_64B
   static constexpr uint32_t SBO = 8u * BK * 2u;                 // 8-row group pitch
   static_assert(BK == 64 || BK == 32, "BK must be one swizzle row");
-  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "");
+  static_assert(BN == 64 || BN == 128, "BN must be 64 or 128");
+  static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
 
-template <int BN, int BK, bool OUT_F32>
+template <int BN, int BK, int MODE>
 __global__ void __launch_bounds__(256, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                const TcGemmParams p) {
-  using Cfg = TcGemmCfg<BN, BK>;
+  using Cfg = TcGemmCfg<BN, BK, MODE>;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 4];
+  __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 8];
   __shared__ uint32_t tmem_slot_s;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + Cfg::STAGES * Cfg::A_STAGE;
+  const uint32_t c_base = smem_base + Cfg::STAGES * Cfg::STAGE;
+  const uint32_t r_base = c_base + Cfg::C_BYTES;
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
+  auto rfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + a); };
+  auto rfree_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 6 + a); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -88,6 +103,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (MODE != OUT_DIRECT_F32) tma_prefetch_desc(&tmC);
+    if (MODE == OUT_TMA_RES) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -97,6 +114,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 4);   // one arrive per epilogue warp
+      mbar_init(rfull_bar(a), 1);
+      mbar_init(rfree_bar(a), 4);
     }
     fence_mbar_init();
   }
@@ -115,12 +134,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = static_cast<uint32_t>(rows) * BK * 2 + Cfg::B_STAGE;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int local = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
         const int nt = tile % p.tiles_n;
         const int mt = tile / p.tiles_n;
         const int w0 = (mt % p.tw) * p.bw;
         const int h0 = ((mt / p.tw) % p.th) * p.bh;
         const int n0 = (mt / (p.tw * p.th)) * p.bn;
+        if (MODE == OUT_TMA_RES) {
+          // residual tile of this output tile -> staging buffer, long before the epilogue needs it
+          const int a = local & 1;
+          mbar_wait(rfree_bar(a), ((local >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(rfull_bar(a), static_cast<uint32_t>(rows) * BN * 2);
+#pragma unroll
+          for (int hf = 0; hf < BN / 64; ++hf)
+            tma_load_5d(r_base + a * Cfg::C_TILE + hf * (Cfg::BM * 128), &tmR, rfull_bar(a), nt * BN + hf * 64, w0, h0, n0, 0);
+        }
         const int c_shift = nt * p.a_c0_per_ntile;
         int kcol = 0;
         for (int ty = 0; ty < p.taps_h; ++ty) {
@@ -171,55 +200,71 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------ epilogue
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;               // row of the tile owned by this thread
-    const int dw = r % p.bw;
-    const int dh = (r / p.bw) % p.bh;
-    const int dn = r / (p.bw * p.bh);
+    const bool store_thread = (threadIdx.x == 128);
     int local = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1u;
       const int nt = tile % p.tiles_n;
       const int mt = tile / p.tiles_n;
-      const int w = (mt % p.tw) * p.bw + dw;
-      const int h = ((mt / p.tw) % p.th) * p.bh + dh;
-      const int n = (mt / (p.tw * p.th)) * p.bn + dn;
-      const bool valid = (r < rows) && (w < p.W) && (h < p.H) && (n < p.NB);
-      const long long out_off = w * p.out_sw + h * p.out_sh + n * p.out_sn;
-      const long long res_off = w * p.res_sw + h * p.res_sh + n * p.res_sn;
+      const int w0 = (mt % p.tw) * p.bw;
+      const int h0 = ((mt / p.tw) % p.th) * p.bh;
+      const int n0 = (mt / (p.tw * p.th)) * p.bn;
+
+      if (MODE != OUT_DIRECT_F32) {
+        // the staging buffer `acc` was last read by the TMA store of tile local-2
+        if (store_thread) bulk_wait_group_read<1>();
+        named_bar_sync(1, 128);
+        if (MODE == OUT_TMA_RES) mbar_wait(rfull_bar(acc), acc_phase);
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      const uint32_t cbuf = c_base + acc * Cfg::C_TILE;
+      const uint32_t rbuf = r_base + acc * Cfg::C_TILE;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
         tmem_ld_wait();
         const int co = nt * BN + c * 32;
-        if (valid && co < p.Cout) {
-          float f[32];
+        float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias != nullptr) {
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr && co < p.Cout) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co + j));
-              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-            }
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co + j));
+            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
           }
-          auto apply_act = [&]() {
-            if (p.act == ACT_RELU) {
+        }
+        auto apply_act = [&]() {
+          if (p.act == ACT_RELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = f[j] < 0.0f ? 0.0f : f[j];   // NaN-propagating like torch.relu
-            } else if (p.act == ACT_GELU) {
+            for (int j = 0; j < 32; ++j) f[j] = f[j] < 0.0f ? 0.0f : f[j];   // NaN-propagating like torch.relu
+          } else if (p.act == ACT_GELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-            }
-          };
-          if (p.res_after_act) apply_act();
-          if (p.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + res_off + co);
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+          }
+        };
+        if (MODE == OUT_DIRECT_F32) {
+          apply_act();
+          const int dw = r % p.bw, dh = (r / p.bw) % p.bh, dn = r / (p.bw * p.bh);
+          const int w = w0 + dw, h = h0 + dh, n = n0 + dn;
+          if ((r < rows) && (w < p.W) && (h < p.H) && (n < p.NB) && co < p.Cout) {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + w * p.out_sw + h * p.out_sh + n * p.out_sn + co);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
+        } else {
+          // 32 columns = four 16-byte chunks of this row inside one 64-column (128 B) swizzled half tile
+          const uint32_t half_off = (c >> 1) * (Cfg::BM * 128) + r * 128;
+          const int j0 = (c & 1) * 4;
+          if (MODE == OUT_TMA_RES) {
+            if (p.res_after_act) apply_act();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 u = __ldg(rp + j);
+              uint4 u;
+              ld_shared_v4(rbuf + half_off + (((j0 + j) ^ (r & 7)) << 4), u);
               const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -228,29 +273,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 f[j * 8 + e * 2 + 1] += t.y;
               }
             }
-          }
-          if (!p.res_after_act) apply_act();
-          if (OUT_F32) {
-            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + co);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            if (!p.res_after_act) apply_act();
           } else {
-            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_off + co);
+            apply_act();
+          }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u;
-              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
-              op[j] = u;
-            }
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
+            st_shared_v4(cbuf + half_off + (((j0 + j) ^ (r & 7)) << 4), u);
           }
         }
       }
+      // accumulator (and residual buffer) are free again
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        mbar_arrive(tempty_bar(acc));
+        if (MODE == OUT_TMA_RES) mbar_arrive(rfree_bar(acc));
+      }
+      if (MODE != OUT_DIRECT_F32) {
+        fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
+        named_bar_sync(2, 128);
+        if (store_thread) {
+#pragma unroll
+          for (int hf = 0; hf < BN / 64; ++hf)
+            if (nt * BN + hf * 64 < p.Cout)
+              tma_store_5d(&tmC, cbuf + hf * (Cfg::BM * 128), nt * BN + hf * 64, w0, h0, n0, 0);
+          bulk_commit_group();
+        }
+      }
     }
+    if (MODE != OUT_DIRECT_F32 && store_thread) bulk_wait_group<0>();
   }
 
   tc_fence_before();

@@ -72,7 +72,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     AVCER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done = true;
   }
-  kern<<<grid, 256, Cfg::SMEM, st>>>(ta, tb, tc, tr, p);
+  kern<<<grid, 384, Cfg::SMEM, st>>>(ta, tb, tc, tr, p);
   return check_launch("tc_gemm_kernel");
 }
 

@@ -54,50 +54,107 @@ __device__ __forceinline__ long long compound_argmax(const TC (&s)[7], const Fus
   return bi;
 }
 
-constexpr int FUSE_THREADS = 256;
+constexpr int FUSE_THREADS = 128;
 
-// Each warp owns 32 consecutive frames: the three [frames,7] tiles are staged through shared
-// memory with fully coalesced loads, then every lane finishes one frame.
+template <typename TIn, typename TC>
+__device__ __forceinline__ void fuse_one(const TIn (&a)[7], const TIn (&b)[7], const TIn (&c)[7], const FuseParams& p,
+                                         long long (&lab)[4]) {
+  using A = Arith<TC>;
+  TC x[3][7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) { x[0][k] = (TC)a[k]; x[1][k] = (TC)b[k]; x[2][k] = (TC)c[k]; }
+  TC av[7];
+  if (p.has_w1) {
+    // predictions[m] * weights_1[m] * weights_2[m], summed left to right (run.py:108-111)
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+      for (int k = 0; k < 7; ++k) x[m][k] = A::mul(A::mul(x[m][k], (TC)p.w[m][k]), (TC)p.w2[m]);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) av[k] = A::add(A::add(x[0][k], x[1][k]), x[2][k]);
+  } else {
+    // np.sum(predictions, axis=0) / 3 (run.py:113-114)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) av[k] = A::div3(A::add(A::add(x[0][k], x[1][k]), x[2][k]));
+  }
+  lab[0] = compound_argmax<TC>(av, p);
+  lab[1] = compound_argmax<TC>(x[0], p);
+  lab[2] = compound_argmax<TC>(x[1], p);
+  lab[3] = compound_argmax<TC>(x[2], p);
+}
+
+// Warp-cooperative streaming pass: every lane owns FPT consecutive frames (FPT*7 values per stream are
+// a whole number of 16-byte vectors, so all loads are aligned 128-bit loads and a warp covers one
+// contiguous span of each stream); 21 independent vector loads are in flight per lane before any math;
+// labels leave as 128-bit stores.  No shared memory, no barriers.
 template <typename TIn, typename TC>
 __global__ void __launch_bounds__(FUSE_THREADS)
 fuse_compound_kernel(const TIn* __restrict__ pvs, const TIn* __restrict__ pvd, const TIn* __restrict__ pa,
                      long long n, const FuseParams p, long long* __restrict__ labels) {
-  using A = Arith<TC>;
-  __shared__ TIn sm[3][FUSE_THREADS * 7];
-  for (long long base = (long long)blockIdx.x * FUSE_THREADS; base < n; base += (long long)gridDim.x * FUSE_THREADS) {
-    const long long cnt = (n - base < FUSE_THREADS ? n - base : FUSE_THREADS) * 7;
-    const TIn* src[3] = {pvs + base * 7, pvd + base * 7, pa + base * 7};
+  constexpr int FPT = 16 / sizeof(TIn);            // frames per thread: 4 (f32) or 2 (f64)
+  constexpr int NV = 7;                            // 16-byte vectors per stream per thread
+  const long long groups = n / FPT;
+  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += (long long)gridDim.x * blockDim.x) {
+    const long long f0 = gidx * FPT;
+    uint4 v[3][NV];
+    const TIn* src[3] = {pvs, pvd, pa};
 #pragma unroll
     for (int m = 0; m < 3; ++m)
-      for (int i = threadIdx.x; i < cnt; i += FUSE_THREADS) sm[m][i] = __ldg(src[m] + i);
-    __syncthreads();
-    const long long f = base + threadIdx.x;
-    if (f < n) {
-      TC x[3][7];
 #pragma unroll
-      for (int m = 0; m < 3; ++m)
+      for (int k = 0; k < NV; ++k) v[m][k] = __ldg(reinterpret_cast<const uint4*>(src[m] + f0 * 7) + k);
+    long long lab[FPT][4];
 #pragma unroll
-        for (int c = 0; c < 7; ++c) x[m][c] = (TC)sm[m][threadIdx.x * 7 + c];
-      TC av[7];
-      if (p.has_w1) {
-        // predictions[m] * weights_1[m] * weights_2[m], summed left to right (run.py:108-111)
+    for (int j = 0; j < FPT; ++j) {
+      TIn a[7], b[7], c[7];
 #pragma unroll
-        for (int m = 0; m < 3; ++m)
-#pragma unroll
-          for (int c = 0; c < 7; ++c) x[m][c] = A::mul(A::mul(x[m][c], (TC)p.w[m][c]), (TC)p.w2[m]);
-#pragma unroll
-        for (int c = 0; c < 7; ++c) av[c] = A::add(A::add(x[0][c], x[1][c]), x[2][c]);
-      } else {
-        // np.sum(predictions, axis=0) / 3 (run.py:113-114)
-#pragma unroll
-        for (int c = 0; c < 7; ++c) av[c] = A::div3(A::add(A::add(x[0][c], x[1][c]), x[2][c]));
+      for (int k = 0; k < 7; ++k) {
+        a[k] = reinterpret_cast<const TIn*>(&v[0][0])[j * 7 + k];
+        b[k] = reinterpret_cast<const TIn*>(&v[1][0])[j * 7 + k];
+        c[k] = reinterpret_cast<const TIn*>(&v[2][0])[j * 7 + k];
       }
-      labels[f] = compound_argmax<TC>(av, p);
-      labels[n + f] = compound_argmax<TC>(x[0], p);
-      labels[2 * n + f] = compound_argmax<TC>(x[1], p);
-      labels[3 * n + f] = compound_argmax<TC>(x[2], p);
+      fuse_one<TIn, TC>(a, b, c, p, lab[j]);
     }
-    __syncthreads();
+    if ((n & 1) == 0) {              // every label row starts 16-byte aligned
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int j = 0; j < FPT; j += 2) {
+          longlong2 o = make_longlong2(lab[j][s], lab[j + 1][s]);
+          *reinterpret_cast<longlong2*>(labels + s * n + f0 + j) = o;
+        }
+    } else {
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int j = 0; j < FPT; ++j) labels[s * n + f0 + j] = lab[j][s];
+    }
+  }
+  // tail frames (n % FPT) by the first threads of block 0
+  if (blockIdx.x == 0 && threadIdx.x < n - groups * FPT) {
+    const long long f = groups * FPT + threadIdx.x;
+    TIn a[7], b[7], c[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { a[k] = pvs[f * 7 + k]; b[k] = pvd[f * 7 + k]; c[k] = pa[f * 7 + k]; }
+    long long lab[4];
+    fuse_one<TIn, TC>(a, b, c, p, lab);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) labels[s * n + f] = lab[s];
+  }
+}
+
+// Same arithmetic for buffers that are not 16-byte aligned (views into larger tensors): one frame per thread.
+template <typename TIn, typename TC>
+__global__ void __launch_bounds__(FUSE_THREADS)
+fuse_compound_scalar_kernel(const TIn* __restrict__ pvs, const TIn* __restrict__ pvd, const TIn* __restrict__ pa,
+                            long long n, const FuseParams p, long long* __restrict__ labels) {
+  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += (long long)gridDim.x * blockDim.x) {
+    TIn a[7], b[7], c[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { a[k] = pvs[f * 7 + k]; b[k] = pvd[f * 7 + k]; c[k] = pa[f * 7 + k]; }
+    long long lab[4];
+    fuse_one<TIn, TC>(a, b, c, p, lab);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) labels[s * n + f] = lab[s];
   }
 }
 
@@ -221,16 +278,25 @@ static int fuse_compound_impl(const TIn* p_vs, const TIn* p_vd, const TIn* p_a, 
       p.ce_w[k][1] = 1.0;
     }
   }
-  const long long blocks_needed = (n + FUSE_THREADS - 1) / FUSE_THREADS;
-  const long long cap = 148ll * 8;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(p_vs) | reinterpret_cast<uintptr_t>(p_vd) | reinterpret_cast<uintptr_t>(p_a) |
+                         reinterpret_cast<uintptr_t>(labels)) & 15) == 0;
+  constexpr int kFpt = 16 / sizeof(TIn);
+  const long long work = aligned ? n / kFpt : n;
+  const long long blocks_needed = (work + FUSE_THREADS - 1) / FUSE_THREADS + 1;
+  const long long cap = 148ll * 16;
   const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
   cudaStream_t st = as_stream(stream);
   // numpy promotes to float64 as soon as the (Python-float) weight lists take part; without
   // them the arithmetic stays in the dtype of the probability arrays.
-  if (p.has_w1 || sizeof(TIn) == 8)
-    fuse_compound_kernel<TIn, double><<<grid, FUSE_THREADS, 0, st>>>(p_vs, p_vd, p_a, n, p, (long long*)labels);
-  else
-    fuse_compound_kernel<TIn, float><<<grid, FUSE_THREADS, 0, st>>>(p_vs, p_vd, p_a, n, p, (long long*)labels);
+  const bool f64 = p.has_w1 || sizeof(TIn) == 8;
+  long long* lab = reinterpret_cast<long long*>(labels);
+  if (aligned) {
+    if (f64) fuse_compound_kernel<TIn, double><<<grid, FUSE_THREADS, 0, st>>>(p_vs, p_vd, p_a, n, p, lab);
+    else fuse_compound_kernel<TIn, float><<<grid, FUSE_THREADS, 0, st>>>(p_vs, p_vd, p_a, n, p, lab);
+  } else {
+    if (f64) fuse_compound_scalar_kernel<TIn, double><<<grid, FUSE_THREADS, 0, st>>>(p_vs, p_vd, p_a, n, p, lab);
+    else fuse_compound_scalar_kernel<TIn, float><<<grid, FUSE_THREADS, 0, st>>>(p_vs, p_vd, p_a, n, p, lab);
+  }
   return check_launch("fuse_compound_kernel");
 }
 

@@ -2,12 +2,13 @@
 // storage type (bf16 in the default mode, fp32 in "fp32 mode").  Arithmetic is always fp32.
 // Reference call sites are cited per kernel.
 #include "common.h"
+#include "ptx.cuh"
 
 namespace avcer {
 
 constexpr int ACT_GELU_L = AVCER_ACT_GELU;
 
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+template <typename T> __device__ __forceinline__ float gelu_for(float x) { return sizeof(T) == 2 ? gelu_erf_fast(x) : gelu_erf(x); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -248,7 +249,7 @@ w2v_conv0_kernel(const float* __restrict__ x, int n, int t_in, int t_out, const 
       const int c0 = 128 * q + 4 * lane;
       float o[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = gelu_erf_f((v[4 * q + e] - mean) * rstd * sg[c0 + e] + sbe[c0 + e]);
+      for (int e = 0; e < 4; ++e) o[e] = gelu_for<T>((v[4 * q + e] - mean) * rstd * sg[c0 + e] + sbe[c0 + e]);
       if (sizeof(T) == 2) {
         uint2 u;
         __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
@@ -263,51 +264,51 @@ w2v_conv0_kernel(const float* __restrict__ x, int n, int t_in, int t_out, const 
 }
 
 // ------------------------------------------------------------------ LayerNorm rows (warp per row), optional pre-add and GELU
-template <typename T>
+template <typename T, int CHUNKS>
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const T* __restrict__ x, long long rows, int c, long long ldx, const T* __restrict__ add,
+layernorm_kernel(const T* __restrict__ x, long long rows, long long ldx, const T* __restrict__ add,
                  long long add_rows, const float* __restrict__ g, const float* __restrict__ b, float eps, int act,
                  T* __restrict__ y, long long ldy) {
+  constexpr int C = CHUNKS * 256;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const int chunks = c / 256;   // c in {256,512,768,1024}
-  float v[4][8];
+  float v[CHUNKS][8];
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (j < chunks) {
-      Vec8<T>::load(x + row * ldx + j * 256 + lane * 8, v[j]);
-      if (add) {
-        float a[8];
-        Vec8<T>::load(add + (row % add_rows) * c + j * 256 + lane * 8, a);
+  for (int j = 0; j < CHUNKS; ++j) Vec8<T>::load(x + row * ldx + j * 256 + lane * 8, v[j]);
+  if (add) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[j][e] += a[e];
-      }
+    for (int j = 0; j < CHUNKS; ++j) {
+      float a[8];
+      Vec8<T>::load(add + (row % add_rows) * C + j * 256 + lane * 8, a);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s += v[j][e];
+      for (int e = 0; e < 8; ++e) v[j][e] += a[e];
     }
   }
-  const float mean = warp_sum(s) / (float)c;
+#pragma unroll
+  for (int j = 0; j < CHUNKS; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += v[j][e];
+  const float mean = warp_sum(s) * (1.0f / (float)C);
   float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (j < chunks)
+  for (int j = 0; j < CHUNKS; ++j)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { const float d = v[j][e] - mean; q = fmaf(d, d, q); }
-  const float rstd = rsqrtf(warp_sum(q) / (float)c + eps);
+    for (int e = 0; e < 8; ++e) { const float d = v[j][e] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / (float)C) + eps);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (j < chunks) {
-      float o[8];
-      const int c0 = j * 256 + lane * 8;
+  for (int j = 0; j < CHUNKS; ++j) {
+    const int c0 = j * 256 + lane * 8;
+    float gg[8], bb[8], o[8];
+    Vec8<float>::load(g + c0, gg);
+    Vec8<float>::load(b + c0, bb);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float t = (v[j][e] - mean) * rstd * g[c0 + e] + b[c0 + e];
-        o[e] = act == ACT_GELU_L ? gelu_erf_f(t) : t;
-      }
-      Vec8<T>::store(y + row * ldy + c0, o);
+    for (int e = 0; e < 8; ++e) {
+      const float t = (v[j][e] - mean) * rstd * gg[e] + bb[e];
+      o[e] = act == ACT_GELU_L ? gelu_for<T>(t) : t;
     }
+    Vec8<T>::store(y + row * ldy + c0, o);
   }
 }
 
@@ -498,9 +499,14 @@ extern "C" int avcer_layernorm(const void* x, int64_t rows, int c, int64_t ldx, 
   AVCER_REQUIRE(c % 256 == 0 && c <= 1024, "layernorm: c must be a multiple of 256, at most 1024");
   AVCER_REQUIRE(add == nullptr || add_rows > 0, "layernorm: add_rows must be > 0 with add");
   if (rows == 0) return 0;
-  AVCER_DISPATCH(dtype, (layernorm_kernel<T><<<blocks_for(rows * 32, 256), 256, 0, as_stream(stream)>>>(
-                            (const T*)x, rows, c, ldx, (const T*)add, add_rows > 0 ? add_rows : 1, g, b, eps, act,
-                            (T*)y, ldy)));
+#define AVCER_LN_CASE(ch)                                                                                         \
+  if (c == ch * 256) {                                                                                            \
+    AVCER_DISPATCH(dtype, (layernorm_kernel<T, ch><<<blocks_for(rows * 32, 256), 256, 0, as_stream(stream)>>>(  \
+                              (const T*)x, rows, ldx, (const T*)add, add_rows > 0 ? add_rows : 1, g, b, eps, act, \
+                              (T*)y, ldy)));                                                                      \
+  }
+  AVCER_LN_CASE(1) AVCER_LN_CASE(2) AVCER_LN_CASE(3) AVCER_LN_CASE(4)
+#undef AVCER_LN_CASE
   return check_launch("layernorm");
 }
 

@@ -123,6 +123,58 @@ preprocess_kernel(const uint8_t* __restrict__ src, const long long* __restrict__
   }
 }
 
+// Fast path for packed 224x224 crops (resize = identity; BASELINE configs): one CTA converts 16 rows.
+// 10752 contiguous input bytes are staged with three 16-byte loads in flight per thread, then every
+// thread emits seven fully coalesced 16-byte stores (two bf16 NHWC4 pixels each).
+constexpr int ROWS_I = 16;
+template <int LAYOUT>
+__global__ void __launch_bounds__(256)
+preprocess_identity_kernel(const uint8_t* __restrict__ src, void* __restrict__ dst) {
+  __shared__ __align__(16) uint8_t sm[ROWS_I * OUT * 3];
+  const int crop = blockIdx.y;
+  const int y0 = blockIdx.x * ROWS_I;
+  const uint4* g = reinterpret_cast<const uint4*>(src + (size_t)crop * OUT * OUT * 3 + (size_t)y0 * OUT * 3);
+  constexpr int NV = ROWS_I * OUT * 3 / 16;      // 672
+  uint4 tmp[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < NV) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(tmp[k].x), "=r"(tmp[k].y), "=r"(tmp[k].z), "=r"(tmp[k].w) : "l"(g + i));
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < NV) reinterpret_cast<uint4*>(sm)[i] = tmp[k];
+  }
+  __syncthreads();
+  const unsigned short* s16 = reinterpret_cast<const unsigned short*>(sm);
+  if (LAYOUT == 1) {
+    __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst) + (size_t)crop * PADH * PADW * 4;
+#pragma unroll
+    for (int it = 0; it < ROWS_I * (OUT / 2) / 256; ++it) {
+      const int t = threadIdx.x + it * 256;
+      const int r = t / (OUT / 2), q = t % (OUT / 2);
+      const unsigned short* px = s16 + r * (OUT * 3 / 2) + q * 3;        // 6 bytes = 2 BGR pixels
+      const unsigned a = px[0], b = px[1], c = px[2];
+      uint4 u;
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+      h2[0] = __floats2bfloat162_rn((float)(a & 0xff) - c_mean[0], (float)(a >> 8) - c_mean[1]);
+      h2[1] = __floats2bfloat162_rn((float)(b & 0xff) - c_mean[2], 0.f);
+      h2[2] = __floats2bfloat162_rn((float)(b >> 8) - c_mean[0], (float)(c & 0xff) - c_mean[1]);
+      h2[3] = __floats2bfloat162_rn((float)(c >> 8) - c_mean[2], 0.f);
+      *reinterpret_cast<uint4*>(d + ((size_t)(y0 + r + PAD0) * PADW + PAD0 + 2 * q) * 4) = u;
+    }
+  } else {
+    float* d = static_cast<float*>(dst) + (size_t)crop * PADH * PADW * 4;
+    for (int t = threadIdx.x; t < ROWS_I * OUT; t += 256) {
+      const int r = t / OUT, x = t % OUT;
+      const uint8_t* px = sm + (r * OUT + x) * 3;
+      *reinterpret_cast<float4*>(d + ((size_t)(y0 + r + PAD0) * PADW + PAD0 + x) * 4) =
+          make_float4((float)px[0] - c_mean[0], (float)px[1] - c_mean[1], (float)px[2] - c_mean[2], 0.f);
+    }
+  }
+}
+
 }  // namespace avcer
 
 using namespace avcer;
@@ -146,6 +198,12 @@ extern "C" int avcer_preprocess_u8(const uint8_t* src, const int64_t* src_offset
   AVCER_REQUIRE(n <= 65535, "preprocess: at most 65535 crops per call");
   cudaStream_t st = as_stream(stream);
   const long long* offs = reinterpret_cast<const long long*>(src_offsets);
+  if (src_offsets == nullptr && src_h == nullptr && dst_layout != 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    dim3 gi(OUT / ROWS_I, n);
+    if (dst_layout == 1) preprocess_identity_kernel<1><<<gi, 256, 0, st>>>(src, dst);
+    else preprocess_identity_kernel<2><<<gi, 256, 0, st>>>(src, dst);
+    return check_launch("preprocess_identity_kernel");
+  }
   if (dst_layout == 0) preprocess_kernel<0><<<grid, 256, 0, st>>>(src, offs, src_h, src_w, maps, dst);
   else if (dst_layout == 1) preprocess_kernel<1><<<grid, 256, 0, st>>>(src, offs, src_h, src_w, maps, dst);
   else preprocess_kernel<2><<<grid, 256, 0, st>>>(src, offs, src_h, src_w, maps, dst);

@@ -8,6 +8,24 @@
 
 namespace avcer {
 
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)), the "gelu" of HF wav2vec2 (erf form, not the tanh form).
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+// Same function with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. far below one
+// bf16 ulp): one MUFU.RCP + one MUFU.EX2 + a 5-term Horner instead of libdevice erff.  Used where
+// the result is stored as bf16; the fp32 mode keeps erff.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.0f - poly * t * __expf(-z * z);        // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

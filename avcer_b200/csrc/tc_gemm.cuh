@@ -18,7 +18,7 @@
 //   one thread hands it to a TMA store (cp.async.bulk.tensor ... bulk_group), which clips partial
 //   boxes at the tensor border -- no per-row masks, every global transaction is a full line.
 // * Warp roles: warp0 = TMA producer, warp1 = MMA issuer (one elected lane), warp2 = TMEM
-//   allocator, warps4-7 = epilogue.
+//   allocator, warps4-11 = epilogue (two warps per TMEM lane quarter, interleaved column chunks).
 // * Persistent: grid = min(#tiles, #SM); tiles are strided across CTAs, N fastest so CTAs of
 //   one wave share the same activation box in L2.
 #pragma once
@@ -48,10 +48,6 @@ struct TcGemmParams {
   int res_after_act;     // 0: act(acc + bias + res)   1: act(acc + bias) + res
 };
 
-__device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-}
-
 template <int BN, int BK, int MODE>
 struct TcGemmCfg {
   static constexpr int BM = 128;
@@ -74,7 +70,7 @@ struct TcGemmCfg {
 };
 
 template <int BN, int BK, int MODE>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                const TcGemmParams p) {
@@ -113,9 +109,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);   // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), 8);   // one arrive per epilogue warp
       mbar_init(rfull_bar(a), 1);
-      mbar_init(rfree_bar(a), 4);
+      mbar_init(rfree_bar(a), 8);
     }
     fence_mbar_init();
   }
@@ -199,6 +195,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int grp = (warp - 4) >> 2;           // two warps share a quarter: even / odd 32-column chunks
     const int r = q * 32 + lane;               // row of the tile owned by this thread
     const bool store_thread = (threadIdx.x == 128);
     int local = 0;
@@ -214,7 +211,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (MODE != OUT_DIRECT_F32) {
         // the staging buffer `acc` was last read by the TMA store of tile local-2
         if (store_thread) bulk_wait_group_read<1>();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         if (MODE == OUT_TMA_RES) mbar_wait(rfull_bar(acc), acc_phase);
       }
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -222,7 +219,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t cbuf = c_base + acc * Cfg::C_TILE;
       const uint32_t rbuf = r_base + acc * Cfg::C_TILE;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = grp; c < BN / 32; c += 2) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
         tmem_ld_wait();
@@ -243,7 +240,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) f[j] = f[j] < 0.0f ? 0.0f : f[j];   // NaN-propagating like torch.relu
           } else if (p.act == ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            for (int j = 0; j < 32; ++j) f[j] = (MODE == OUT_DIRECT_F32) ? gelu_erf(f[j]) : gelu_erf_fast(f[j]);
           }
         };
         if (MODE == OUT_DIRECT_F32) {
@@ -296,7 +293,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (MODE != OUT_DIRECT_F32) {
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
-        named_bar_sync(2, 128);
+        named_bar_sync(2, 256);
         if (store_thread) {
 #pragma unroll
           for (int hf = 0; hf < BN / 64; ++hf)

@@ -154,7 +154,9 @@ def make_audio_state_dict(seed: int = 2, num_classes: int = 8, init: str = "spre
     for i, k in enumerate(W2V_CONV_KERNEL):
         p = f"wav2vec2.feature_extractor.conv_layers.{i}"
         sd[p + ".conv.weight"] = torch.randn((512, cin, k), generator=g) * math.sqrt(2.0 / (cin * k))
-        sd[p + ".conv.bias"] = 0.02 * torch.randn(512, generator=g) if spread else torch.zeros(512)
+        # HF Wav2Vec2PreTrainedModel._init_weights: Conv1d bias ~ U(-k, k), k = sqrt(groups / (in_channels * kernel))
+        kb = math.sqrt(1.0 / (cin * k))
+        sd[p + ".conv.bias"] = 0.02 * torch.randn(512, generator=g) if spread else (torch.rand(512, generator=g) * 2 - 1) * kb
         ln(p + ".layer_norm", 512)
         cin = 512
     ln("wav2vec2.feature_projection.layer_norm", 512)

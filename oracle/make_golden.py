@@ -214,6 +214,16 @@ def make_audio():
             gm = df.groupby(["frames"]).mean().reset_index()
             out[f"a{ncls}_{tag}_frame_ids"] = np.asarray([int(f[:-4]) for f in gm["frames"]], dtype=np.int64)
             out[f"a{ncls}_{tag}_frame_means"] = gm[of.AUDIO_ORDER[:ncls]].values
+    # PyTorch-default-like random init (the init the north star names) for the bf16 2e-3 check
+    sd = syn.make_audio_state_dict(2, 8, "default", 12)
+    model = harness.reference_audio_model(sd, 8, 12)
+    wav = syn.make_wav(31, 52800 + 123)
+    sched = oa.window_schedule(len(wav), 25, 0.5)
+    xs = np.stack([oa.zero_mean_unit_var(oa.pad_window(wav[s:e], 64000, "mean")) for (s, e, _, _) in sched])
+    with torch.no_grad():
+        ref = model(torch.from_numpy(xs)).numpy()
+    assert np.abs(oa.audio_model_forward(sd, torch.from_numpy(xs)).numpy() - ref).max() < 2e-5
+    out["a8_default_window_logits"] = ref
     np.savez_compressed(os.path.join(OUT, "audio.npz"), **out)
     print("audio.npz")
 

@@ -5,6 +5,7 @@
 
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace avcer {
 
@@ -98,6 +99,16 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
                 "contract(bf16): a/wt/out must be 16-byte aligned");
   int BN = (d->group_cin_shift != 0 || d->cout % 128 != 0) ? 64 : 128;
   if (BK == 32) BN = 64;   // stem: Cout = 64
+  // 128x256 tiles halve the shared-memory operand traffic per MMA (measured 1.45x the MMA rate of 128x128);
+  // pick them when the wave-quantised time estimate is lower.
+  if (BN == 128 && BK == 64 && d->cout % 256 == 0 && !d->out_f32) {
+    const long long mt = ((long long)d->W * d->H * d->NB + 127) / 128;
+    const long long sms = num_sms_cached();
+    const long long waves128 = (mt * (d->cout / 128) + sms - 1) / sms;
+    const long long waves256 = (mt * (d->cout / 256) + sms - 1) / sms;
+    if (waves256 * 2.0 / 1.4 < (double)waves128) BN = 256;
+  }
+  if (getenv("AVCER_NO_BN256") && BN == 256) BN = 128;
 
   TcGemmParams p{};
   choose_box(d->W, d->H, d->NB, &p.bw, &p.bh, &p.bn);
@@ -172,6 +183,7 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
     if (mode == OUT_TMA_RES) return launch_tc<bn, bk, OUT_TMA_RES>(ta, tb, tc, tr, p, grid, st);  \
     return launch_tc<bn, bk, OUT_DIRECT_F32>(ta, tb, tc, tr, p, grid, st);                        \
   }
+  AVCER_TC_CASE(256, 64)
   AVCER_TC_CASE(128, 64)
   AVCER_TC_CASE(64, 64)
   AVCER_TC_CASE(64, 32)

@@ -54,18 +54,19 @@ struct TcGemmCfg {
   static constexpr int A_STAGE = BM * BK * 2;
   static constexpr int B_STAGE = BN * BK * 2;
   static constexpr int STAGE = A_STAGE + B_STAGE;
-  static constexpr int C_TILE = BM * BN * 2;                                   // one bf16 staging tile
-  static constexpr int C_BYTES = (MODE == OUT_DIRECT_F32) ? 0 : 2 * C_TILE;    // double buffered
-  static constexpr int R_BYTES = (MODE == OUT_TMA_RES) ? 2 * C_TILE : 0;
+  static constexpr int HALF = BM * 128;                                        // 128 rows x 64 bf16 columns, 128B-swizzled
+  static constexpr int C_SLOTS = (MODE == OUT_DIRECT_F32) ? 0 : 2;             // output staging ring (64-column halves)
+  static constexpr int R_SLOTS = (MODE == OUT_TMA_RES) ? 2 : 0;                // residual prefetch ring
   static constexpr int BUDGET = 224 * 1024;
-  static constexpr int FIT = (BUDGET - C_BYTES - R_BYTES) / STAGE;
+  static constexpr int FIT = (BUDGET - (C_SLOTS + R_SLOTS) * HALF) / STAGE;
   static constexpr int STAGES = FIT > 8 ? 8 : FIT;
-  static constexpr int SMEM = STAGES * STAGE + C_BYTES + R_BYTES + 1024 /*align slack*/;
+  static constexpr int SMEM = STAGES * STAGE + (C_SLOTS + R_SLOTS) * HALF + 1024 /*align slack*/;
   static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int HALVES = BN / 64;
   static constexpr uint32_t LAYOUT = (BK == 64) ? 2u : 4u;      // SWIZZLE_128B : SWIZZLE_64B
   static constexpr uint32_t SBO = 8u * BK * 2u;                 // 8-row group pitch
   static_assert(BK == 64 || BK == 32, "BK must be one swizzle row");
-  static_assert(BN == 64 || BN == 128, "BN must be 64 or 128");
+  static_assert(BN == 64 || BN == 128 || BN == 256, "BN must be 64, 128 or 256");
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
 
@@ -82,7 +83,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + Cfg::STAGES * Cfg::A_STAGE;
   const uint32_t c_base = smem_base + Cfg::STAGES * Cfg::STAGE;
-  const uint32_t r_base = c_base + Cfg::C_BYTES;
+  const uint32_t r_base = c_base + Cfg::C_SLOTS * Cfg::HALF;
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
@@ -137,15 +138,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int w0 = (mt % p.tw) * p.bw;
         const int h0 = ((mt / p.tw) % p.th) * p.bh;
         const int n0 = (mt / (p.tw * p.th)) * p.bn;
-        if (MODE == OUT_TMA_RES) {
-          // residual tile of this output tile -> staging buffer, long before the epilogue needs it
-          const int a = local & 1;
-          mbar_wait(rfree_bar(a), ((local >> 1) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(rfull_bar(a), static_cast<uint32_t>(rows) * BN * 2);
-#pragma unroll
-          for (int hf = 0; hf < BN / 64; ++hf)
-            tma_load_5d(r_base + a * Cfg::C_TILE + hf * (Cfg::BM * 128), &tmR, rfull_bar(a), nt * BN + hf * 64, w0, h0, n0, 0);
-        }
         const int c_shift = nt * p.a_c0_per_ntile;
         int kcol = 0;
         for (int ty = 0; ty < p.taps_h; ++ty) {
@@ -192,12 +184,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit(tfull_bar(acc));
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------ residual producer (own warp: never blocks A/B loads)
+    if (MODE == OUT_TMA_RES && lane == 0) {
+      uint32_t hcount = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n;
+        const int mt = tile / p.tiles_n;
+        const int w0 = (mt % p.tw) * p.bw;
+        const int h0 = ((mt / p.tw) % p.th) * p.bh;
+        const int n0 = (mt / (p.tw * p.th)) * p.bn;
+        for (int hf = 0; hf < Cfg::HALVES; ++hf, ++hcount) {
+          const int slot = hcount & 1;
+          mbar_wait(rfree_bar(slot), ((hcount >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(rfull_bar(slot), static_cast<uint32_t>(rows) * 128);
+          tma_load_5d(r_base + slot * Cfg::HALF, &tmR, rfull_bar(slot), nt * BN + hf * 64, w0, h0, n0, 0);
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int grp = (warp - 4) >> 2;           // two warps share a quarter: even / odd 32-column chunks
     const int r = q * 32 + lane;               // row of the tile owned by this thread
     const bool store_thread = (threadIdx.x == 128);
+    uint32_t hcount = 0;                       // 64-column halves handled so far (ring positions)
     int local = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
@@ -207,24 +218,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int w0 = (mt % p.tw) * p.bw;
       const int h0 = ((mt / p.tw) % p.th) * p.bh;
       const int n0 = (mt / (p.tw * p.th)) * p.bn;
-
-      if (MODE != OUT_DIRECT_F32) {
-        // the staging buffer `acc` was last read by the TMA store of tile local-2
-        if (store_thread) bulk_wait_group_read<1>();
-        named_bar_sync(1, 256);
-        if (MODE == OUT_TMA_RES) mbar_wait(rfull_bar(acc), acc_phase);
-      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t cbuf = c_base + acc * Cfg::C_TILE;
-      const uint32_t rbuf = r_base + acc * Cfg::C_TILE;
-#pragma unroll 1
-      for (int c = grp; c < BN / 32; c += 2) {
+
+      auto load_chunk = [&](int c, float (&f)[32]) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
         tmem_ld_wait();
         const int co = nt * BN + c * 32;
-        float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         if (p.bias != nullptr && co < p.Cout) {
@@ -234,34 +235,53 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
           }
         }
-        auto apply_act = [&]() {
-          if (p.act == ACT_RELU) {
+      };
+      auto apply_act = [&](float (&f)[32]) {
+        if (p.act == ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = f[j] < 0.0f ? 0.0f : f[j];   // NaN-propagating like torch.relu
-          } else if (p.act == ACT_GELU) {
+          for (int j = 0; j < 32; ++j) f[j] = f[j] < 0.0f ? 0.0f : f[j];   // NaN-propagating like torch.relu
+        } else if (p.act == ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = (MODE == OUT_DIRECT_F32) ? gelu_erf(f[j]) : gelu_erf_fast(f[j]);
-          }
-        };
-        if (MODE == OUT_DIRECT_F32) {
-          apply_act();
-          const int dw = r % p.bw, dh = (r / p.bw) % p.bh, dn = r / (p.bw * p.bh);
-          const int w = w0 + dw, h = h0 + dh, n = n0 + dn;
-          if ((r < rows) && (w < p.W) && (h < p.H) && (n < p.NB) && co < p.Cout) {
+          for (int j = 0; j < 32; ++j) f[j] = (MODE == OUT_DIRECT_F32) ? gelu_erf(f[j]) : gelu_erf_fast(f[j]);
+        }
+      };
+
+      if (MODE == OUT_DIRECT_F32) {
+        const int dw = r % p.bw, dh = (r / p.bw) % p.bh, dn = r / (p.bw * p.bh);
+        const int w = w0 + dw, h = h0 + dh, n = n0 + dn;
+        const bool valid = (r < rows) && (w < p.W) && (h < p.H) && (n < p.NB);
+#pragma unroll 1
+        for (int c = grp; c < BN / 32; c += 2) {
+          float f[32];
+          load_chunk(c, f);
+          apply_act(f);
+          const int co = nt * BN + c * 32;
+          if (valid && co < p.Cout) {
             float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + w * p.out_sw + h * p.out_sh + n * p.out_sn + co);
 #pragma unroll
             for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           }
-        } else {
-          // 32 columns = four 16-byte chunks of this row inside one 64-column (128 B) swizzled half tile
-          const uint32_t half_off = (c >> 1) * (Cfg::BM * 128) + r * 128;
-          const int j0 = (c & 1) * 4;
+        }
+      } else {
+#pragma unroll 1
+        for (int hf = 0; hf < Cfg::HALVES; ++hf, ++hcount) {
+          const int slot = hcount & 1;
+          // staging slot `slot` was last read by the TMA store issued two halves ago
+          if (store_thread) bulk_wait_group_read<1>();
+          named_bar_sync(1, 256);
+          const uint32_t cbuf = c_base + slot * Cfg::HALF;
+          const uint32_t rbuf = r_base + slot * Cfg::HALF;
+          float f[32];
+          load_chunk(2 * hf + grp, f);           // the two warp groups take the two 32-column chunks of this half
+          const uint32_t row_off = r * 128;
+          const int j0 = grp * 4;                // first 16-byte chunk of this thread inside the 128 B row
           if (MODE == OUT_TMA_RES) {
-            if (p.res_after_act) apply_act();
+            if (p.res_after_act) apply_act(f);
+            mbar_wait(rfull_bar(slot), (hcount >> 1) & 1u);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 u;
-              ld_shared_v4(rbuf + half_off + (((j0 + j) ^ (r & 7)) << 4), u);
+              ld_shared_v4(rbuf + row_off + (((j0 + j) ^ (r & 7)) << 4), u);
               const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -270,9 +290,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 f[j * 8 + e * 2 + 1] += t.y;
               }
             }
-            if (!p.res_after_act) apply_act();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(rfree_bar(slot));
+            if (!p.res_after_act) apply_act(f);
           } else {
-            apply_act();
+            apply_act(f);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -280,28 +302,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
             for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
-            st_shared_v4(cbuf + half_off + (((j0 + j) ^ (r & 7)) << 4), u);
+            st_shared_v4(cbuf + row_off + (((j0 + j) ^ (r & 7)) << 4), u);
+          }
+          fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
+          named_bar_sync(2, 256);
+          if (store_thread) {
+            if (nt * BN + hf * 64 < p.Cout) tma_store_5d(&tmC, cbuf, nt * BN + hf * 64, w0, h0, n0, 0);
+            bulk_commit_group();
           }
         }
       }
-      // accumulator (and residual buffer) are free again
+      // accumulator is free again
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(tempty_bar(acc));
-        if (MODE == OUT_TMA_RES) mbar_arrive(rfree_bar(acc));
-      }
-      if (MODE != OUT_DIRECT_F32) {
-        fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
-        named_bar_sync(2, 256);
-        if (store_thread) {
-#pragma unroll
-          for (int hf = 0; hf < BN / 64; ++hf)
-            if (nt * BN + hf * 64 < p.Cout)
-              tma_store_5d(&tmC, cbuf + hf * (Cfg::BM * 128), nt * BN + hf * 64, w0, h0, n0, 0);
-          bulk_commit_group();
-        }
-      }
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
     if (MODE != OUT_DIRECT_F32 && store_thread) bulk_wait_group<0>();
   }

@@ -272,13 +272,14 @@ PAD_MODES = {"mean": 0, "constant": 1, "repeat": 2}
 
 
 def audio_normalize_windows(wav: torch.Tensor, starts: torch.Tensor, win: int, pad_mode: str,
-                            ends: Optional[torch.Tensor] = None) -> torch.Tensor:
+                            ends: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """wav: device fp32 buffer; chunk i = wav[starts[i]:ends[i]] (ends default: min(start+win, len(wav)))."""
     _cuda(wav, "wav")
     n_win = starts.numel()
     if ends is None:
         ends = torch.clamp(starts + win, max=wav.numel())
-    out = torch.empty((n_win, win), device=wav.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((n_win, win), device=wav.device, dtype=torch.float32)
     check(_lib.load().avcer_audio_normalize_windows(wav.data_ptr(), starts.data_ptr(), ends.data_ptr(), n_win, win,
                                                     PAD_MODES[pad_mode], out.data_ptr(), _stream()))
     return out

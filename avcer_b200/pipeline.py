@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .nets import ANet, VDNet, VSNet
+from .nets import ANet, GraphedForward, VDNet, VSNet
 
 VIDEO_ORDER = ["Neutral", "Happiness", "Sadness", "Surprise", "Fear", "Disgust", "Anger"]     # get_prob_video.py:56-64
 AUDIO_ORDER = ["Neutral", "Anger", "Disgust", "Fear", "Happiness", "Sadness", "Surprise", "Other"]  # run.py:56-65
@@ -101,8 +101,13 @@ class Clip:
 class Engine:
     """Holds the three packed networks and runs clips through K1 -> VS -> VD, A, alignment and K4."""
 
+    def _upload(self, a: np.ndarray, dtype) -> torch.Tensor:
+        """Host index array -> device through pinned memory, asynchronously (no stream sync)."""
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).pin_memory()
+        return t.to(self.device, non_blocking=True)
+
     def __init__(self, sd_vs=None, sd_vd=None, sd_a=None, precision: str = "bf16", device: str = "cuda:0",
-                 vs_batch: int = 256, a_batch: int = 32):
+                 vs_batch: int = 256, a_batch: int = 64, use_graphs: bool = True):
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         self.precision = precision
@@ -112,7 +117,22 @@ class Engine:
         self.vs_batch = vs_batch
         self.a_batch = a_batch
         self._vs_in: Optional[torch.Tensor] = None
+        self._a_in: Optional[torch.Tensor] = None
         self._perm = torch.tensor(VIDEO_TO_AUDIO, device=self.device, dtype=torch.int32)
+        # CUDA graphs for the two fixed-shape forwards (disabled while ops.PROFILE records per-kernel events)
+        self.use_graphs = use_graphs
+        self._vs_graph = GraphedForward(lambda x: self.vs.forward(x)) if self.vs is not None else None
+        self._a_graph = GraphedForward(lambda x: self.a.forward(x)) if self.a is not None else None
+
+    def _vs_fwd(self, x: torch.Tensor):
+        if self.use_graphs and ops.PROFILE is None:
+            return self._vs_graph(x)
+        return self.vs.forward(x)
+
+    def _a_fwd(self, x: torch.Tensor):
+        if self.use_graphs and ops.PROFILE is None:
+            return self._a_graph(x)
+        return self.a.forward(x)
 
     # ------------------------------------------------------------------ VS over packed 224x224 crops
     def _vs_input(self, n: int) -> torch.Tensor:
@@ -129,9 +149,52 @@ class Engine:
             e = min(n, s + self.vs_batch)
             x = self._vs_input(e - s)
             ops.preprocess(crops_u8[s:e], e - s, x, self.vs.input_layout)
-            p, f = self.vs.forward(x)
+            p, f = self._vs_fwd(x)
             probs[s:e].copy_(p)
             feats[s:e].copy_(f)
+        return probs, feats
+
+    def vs_forward_host(self, crops_host: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Same as vs_forward_u8 for crops in pinned HOST memory: the H2D copy of batch i+1 runs on a
+        copy stream while batch i is preprocessed and classified (double-buffered device staging)."""
+        n = crops_host.shape[0]
+        bs = self.vs_batch
+        probs = torch.empty((n, 7), device=self.device, dtype=torch.float32)
+        feats = torch.empty((n, 512), device=self.device, dtype=self.vs.dtype)
+        if not hasattr(self, "_stage"):
+            self._stage = [torch.empty((bs, 224, 224, 3), device=self.device, dtype=torch.uint8) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._ready = [torch.cuda.Event() for _ in range(2)]
+            self._free = [torch.cuda.Event() for _ in range(2)]
+        cur = torch.cuda.current_stream()
+        starts = list(range(0, n, bs))
+
+        def issue_copy(i):
+            s0 = starts[i]
+            e0 = min(n, s0 + bs)
+            k = i & 1
+            if i >= 2:
+                self._copy_stream.wait_event(self._free[k])
+            else:
+                self._copy_stream.wait_stream(cur)
+            with torch.cuda.stream(self._copy_stream):
+                self._stage[k][: e0 - s0].copy_(crops_host[s0:e0], non_blocking=True)
+                self._ready[k].record(self._copy_stream)
+
+        if starts:
+            issue_copy(0)
+        for i, s0 in enumerate(starts):
+            e0 = min(n, s0 + bs)
+            if i + 1 < len(starts):
+                issue_copy(i + 1)
+            k = i & 1
+            cur.wait_event(self._ready[k])
+            x = self._vs_input(e0 - s0)
+            ops.preprocess(self._stage[k][: e0 - s0], e0 - s0, x, self.vs.input_layout)
+            self._free[k].record(cur)
+            p, f = self._vs_fwd(x)
+            probs[s0:e0].copy_(p)
+            feats[s0:e0].copy_(f)
         return probs, feats
 
     def vs_forward_ragged(self, flat_u8: torch.Tensor, offsets: np.ndarray, heights: np.ndarray, widths: np.ndarray):
@@ -146,7 +209,7 @@ class Engine:
             e = min(n, s + self.vs_batch)
             x = self._vs_input(e - s)
             ops.preprocess(flat_u8, e - s, x, self.vs.input_layout, offsets=off[s:e], heights=hh[s:e], widths=ww[s:e])
-            p, f = self.vs.forward(x)
+            p, f = self._vs_fwd(x)
             probs[s:e].copy_(p)
             feats[s:e].copy_(f)
         return probs, feats
@@ -173,15 +236,15 @@ class Engine:
             present_base += int(ex.sum())
             sample_base += plan.samples.shape[0]
         dev = self.device
-        stat_idx_t = torch.from_numpy(np.concatenate(stat_idx).astype(np.int32)).to(dev)
-        dyn_idx_t = torch.from_numpy(np.concatenate(dyn_idx).astype(np.int32)).to(dev)
+        stat_idx_t = self._upload(np.concatenate(stat_idx), np.int32)
+        dyn_idx_t = self._upload(np.concatenate(dyn_idx), np.int32)
         n_total = stat_idx_t.numel()
         stat = ops.gather_rows(probs, stat_idx_t, n_total)
         windows = np.concatenate(win_all, axis=0) if win_all else np.zeros((0, 10), dtype=np.int64)
         if windows.shape[0]:
             # windows index the sample list; map them to rows of `feats` so no feature copy is needed
             rows = np.concatenate(sample_rows)
-            win_rows = torch.from_numpy(np.ascontiguousarray(rows[windows].T).astype(np.int32)).to(dev)   # [10, M]
+            win_rows = self._upload(rows[windows].T, np.int32)   # [10, M]
             vd_logits = self.vd.forward(feats, win_rows)
         else:
             vd_logits = torch.zeros((1, 7), device=dev, dtype=torch.float32)
@@ -196,19 +259,21 @@ class Engine:
             raise ZeroDivisionError("integer division or modulo by zero")      # data/utils.py:66 on the empty tail window
         if padding not in ops.PAD_MODES:
             raise UnboundLocalError("cannot access local variable 'a_fss' where it is not associated with a value")
-        st = torch.from_numpy(np.ascontiguousarray(starts, dtype=np.int64)).to(self.device)
-        en = torch.from_numpy(np.ascontiguousarray(ends, dtype=np.int64)).to(self.device)
+        st = self._upload(starts, np.int64)
+        en = self._upload(ends, np.int64)
         wn = int(st.numel())
         out = torch.empty((wn, self.a.num_classes), device=self.device, dtype=torch.float32)
         for s in range(0, wn, self.a_batch):
             e = min(wn, s + self.a_batch)
-            x = ops.audio_normalize_windows(wav, st[s:e], win, padding, ends=en[s:e])
-            out[s:e].copy_(self.a.forward(x))
+            if self._a_in is None or self._a_in.shape[0] < self.a_batch or self._a_in.shape[1] != win:
+                self._a_in = torch.empty((self.a_batch, win), device=self.device, dtype=torch.float32)
+            x = ops.audio_normalize_windows(wav, st[s:e], win, padding, ends=en[s:e], out=self._a_in[:e - s])
+            out[s:e].copy_(self._a_fwd(x))
         return out
 
     def audio_frame_means(self, logits: torch.Tensor, f_lo: np.ndarray, f_hi: np.ndarray, n_frames: int) -> torch.Tensor:
-        lo = torch.from_numpy(np.asarray(f_lo, dtype=np.int32)).to(self.device)
-        hi = torch.from_numpy(np.asarray(f_hi, dtype=np.int32)).to(self.device)
+        lo = self._upload(f_lo, np.int32)
+        hi = self._upload(f_hi, np.int32)
         return ops.window_to_frame_mean(logits, lo, hi, n_frames)
 
     def audio_rows(self, wav_cat: torch.Tensor, wav_lens: Sequence[int], fps_list: Sequence[float], n_frames: Sequence[int],
@@ -231,7 +296,7 @@ class Engine:
             tail_src.append(base[ci] + src)
         logits = self.audio_window_logits(wav_cat, np.concatenate(st_all), np.concatenate(en_all), padding, window * sr)
         a_mean = self.audio_frame_means(logits, np.concatenate(lo_all), np.concatenate(hi_all), int(base[-1]))
-        tail = torch.from_numpy(np.concatenate(tail_src).astype(np.int32)).to(self.device)
+        tail = self._upload(np.concatenate(tail_src), np.int32)
         return ops.gather_rows(a_mean, tail, int(base[-1])), logits
 
     # ------------------------------------------------------------------ K4 on aligned per-frame rows
@@ -251,11 +316,9 @@ class Engine:
                   step: float = 0.5, window: int = 4, sr: int = 16000, padding: str = "mean") -> Dict[str, torch.Tensor]:
         """All clips at once.  crops_u8: uint8 [sum present frames, 224,224,3] BGR; wav_cat: fp32 waveforms
         back to back.  Host (pinned) tensors are copied to the device first; device tensors are used as is."""
-        if not crops_u8.is_cuda:
-            crops_u8 = crops_u8.to(self.device, non_blocking=True)
         if not wav_cat.is_cuda:
             wav_cat = wav_cat.to(self.device, non_blocking=True)
-        probs, feats = self.vs_forward_u8(crops_u8)
+        probs, feats = self.vs_forward_u8(crops_u8) if crops_u8.is_cuda else self.vs_forward_host(crops_u8)
         stat, dyn, plans = self.video_rows(probs, feats, exists_list, fps_list)
         a_rows, logits = self.audio_rows(wav_cat, wav_lens, fps_list, [len(e) for e in exists_list], step, window, sr, padding)
         labels = self.fuse(stat, dyn, a_rows, weights_1, weights_2, ce_weights_type, ce_mask)

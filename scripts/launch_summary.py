@@ -59,5 +59,5 @@ def section(start_prefix, specs, title, brief):
         if not n.startswith('tc_gemm'): other[n[:40]] += t
     for k, v in sorted(other.items(), key=lambda kv: -kv[1]): print(f"  {v:9.1f} us  {k}")
 
-section('preprocess_kernel', vs_specs(), "VS forward, batch 256", False)
+section('preprocess', vs_specs(), "VS forward, batch 256", False)
 section('audio_normalize', a_specs(), "A forward, 32 windows", True)

@@ -44,6 +44,8 @@ class ContractDesc(ctypes.Structure):
         ("off_h", c_int32),
         ("tap_h_in_dim4", c_int32),
         ("group_cin_shift", c_int32),
+        ("a_strip", c_int32),
+        ("wt_packed", c_void_p),
         ("act", c_int32),
         ("res_after_act", c_int32),
         ("dtype", c_int32),

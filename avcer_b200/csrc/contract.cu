@@ -63,17 +63,19 @@ static void choose_box(int W, int H, int NB, int* bw, int* bh, int* bn) {
   }
 }
 
-template <int BN, int BK, int MODE>
+template <int BN, int BK, int MODE, int KSUB, int OCC>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
                      const TcGemmParams& p, int grid, cudaStream_t st) {
-  using Cfg = TcGemmCfg<BN, BK, MODE>;
-  auto kern = tc_gemm_kernel<BN, BK, MODE>;
+  using Cfg = TcGemmCfg<BN, BK, MODE, KSUB, OCC>;
+  auto kern = tc_gemm_kernel<BN, BK, MODE, KSUB, OCC>;
   static bool attr_done = false;
   if (!attr_done) {
     AVCER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done = true;
   }
-  kern<<<grid, 384, Cfg::SMEM, st>>>(ta, tb, tc, tr, p);
+  int g = grid * OCC;                     // persistent: OCC CTAs per SM
+  if (g > p.num_tiles) g = p.num_tiles;
+  kern<<<g, Cfg::THREADS, Cfg::SMEM, st>>>(ta, tb, tc, tr, p);
   return check_launch("tc_gemm_kernel");
 }
 
@@ -111,7 +113,22 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   if (getenv("AVCER_NO_BN256") && BN == 256) BN = 128;
 
   TcGemmParams p{};
-  choose_box(d->W, d->H, d->NB, &p.bw, &p.bh, &p.bn);
+  if (d->a_strip) {
+    const int64_t strip_elems = d->a_dim[0] * d->a_dim[1];
+    AVCER_REQUIRE(d->a_dim[0] % 8 == 0 && d->a_dim[0] <= 64 && d->W <= 128 && d->taps_w == 1 && d->tap_h_in_dim4 &&
+                      d->cin == BK && strip_elems >= 8 * (int64_t)(d->W - 1) + BK && d->a_dim[1] <= 256 &&
+                      d->a_stride[1] == d->a_dim[0] && d->group_cin_shift == 0 && d->wt_packed != nullptr,
+                  "contract(bf16): bad strip geometry");
+    p.bw = d->W; p.bh = 1; p.bn = 1;
+    p.a_strip = 1;
+    p.a_bytes = (unsigned)(strip_elems * 2);
+    p.b_packed = d->wt_packed;
+    AVCER_REQUIRE(p.a_bytes <= 128u * BK * 2u, "contract(bf16): strip larger than the A stage");
+    AVCER_REQUIRE(16 * 127 + BK * 2 <= 128 * BK * 2, "contract(bf16): strip exceeds the A stage");
+  } else {
+    choose_box(d->W, d->H, d->NB, &p.bw, &p.bh, &p.bn);
+    p.a_bytes = (unsigned)(p.bw * p.bh * p.bn) * BK * 2;
+  }
   p.tw = (d->W + p.bw - 1) / p.bw;
   p.th = (d->H + p.bh - 1) / p.bh;
   p.tn = (d->NB + p.bn - 1) / p.bn;
@@ -143,7 +160,8 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
       strides[i - 1] = (uint64_t)d->a_stride[i] * 2;
     }
     uint32_t box[5] = {(uint32_t)BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, 1u};
-    if (encode_map(&ta, d->a, 5, dims, strides, box, swz)) return 1;
+    if (d->a_strip) { box[0] = (uint32_t)d->a_dim[0]; box[1] = (uint32_t)d->a_dim[1]; box[2] = 1; box[3] = 1; }
+    if (encode_map(&ta, d->a, 5, dims, strides, box, d->a_strip ? CU_TENSOR_MAP_SWIZZLE_NONE : swz)) return 1;
   }
   {
     const uint64_t ktot = (uint64_t)d->taps_w * d->taps_h * d->cin;
@@ -176,17 +194,19 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
       if (make_out_map(&tr, d->residual, d->res_stride)) return 1;
     }
   }
-  const int grid = p.num_tiles < num_sms_cached() ? p.num_tiles : num_sms_cached();
-#define AVCER_TC_CASE(bn, bk)                                                                     \
-  if (BN == bn && BK == bk) {                                                                     \
-    if (mode == OUT_TMA) return launch_tc<bn, bk, OUT_TMA>(ta, tb, tc, tr, p, grid, st);          \
-    if (mode == OUT_TMA_RES) return launch_tc<bn, bk, OUT_TMA_RES>(ta, tb, tc, tr, p, grid, st);  \
-    return launch_tc<bn, bk, OUT_DIRECT_F32>(ta, tb, tc, tr, p, grid, st);                        \
+  const int grid = num_sms_cached();
+  // K chunks per pipeline stage: small tiles (little MMA work per chunk) batch several chunks per barrier
+#define AVCER_TC_CASE(bn, bk, occ)                                                                         \
+  if (BN == bn && BK == bk) {                                                                              \
+    if (mode == OUT_TMA) return launch_tc<bn, bk, OUT_TMA, 1, occ>(ta, tb, tc, tr, p, grid, st);           \
+    if (mode == OUT_TMA_RES) return launch_tc<bn, bk, OUT_TMA_RES, 1, occ>(ta, tb, tc, tr, p, grid, st);   \
+    return launch_tc<bn, bk, OUT_DIRECT_F32, 1, 1>(ta, tb, tc, tr, p, grid, st);                           \
   }
-  AVCER_TC_CASE(256, 64)
-  AVCER_TC_CASE(128, 64)
-  AVCER_TC_CASE(64, 64)
-  AVCER_TC_CASE(64, 32)
+  static const int occ128 = getenv("AVCER_OCC128") ? atoi(getenv("AVCER_OCC128")) : 1;
+  static const int occ64 = getenv("AVCER_OCC64") ? atoi(getenv("AVCER_OCC64")) : 2;
+  AVCER_TC_CASE(256, 64, 1)
+  if (occ128 == 2) { AVCER_TC_CASE(128, 64, 2) } else { AVCER_TC_CASE(128, 64, 1) }
+  if (occ64 == 2) { AVCER_TC_CASE(64, 64, 2) AVCER_TC_CASE(64, 32, 2) } else { AVCER_TC_CASE(64, 64, 1) AVCER_TC_CASE(64, 32, 1) }
 #undef AVCER_TC_CASE
   return set_error("contract: no tensor-core instantiation for BN=%d BK=%d", BN, BK);
 }

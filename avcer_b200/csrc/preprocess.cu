@@ -16,7 +16,7 @@
 namespace avcer {
 
 constexpr int OUT = 224;
-constexpr int PADW = 232;     // padded row pitch (pixels) of layouts 1/2
+constexpr int PADW = 240;     // padded row pitch (pixels) of layouts 1/2: 1920 B = 15 x 128 B per bf16 row
 constexpr int PADH = 232;
 constexpr int PAD0 = 2;       // TF-"same" leading pad of the 7x7/2 stem (video.py:65-81)
 constexpr int ROWS = 4;       // output rows per CTA

@@ -40,6 +40,11 @@ struct TcGemmParams {
   int tap_h_in_dim4;       // 1: the h-tap index is coordinate 4 of the A map (stem: strided rows)
   int kchunks;             // K chunks (of BK) per tap
   int a_c0_per_ntile;      // channel-coordinate shift per N tile (grouped conv), else 0
+  int a_strip;             // 1: A box is an un-swizzled contiguous strip whose rows overlap (row r starts 16 B after
+                           //    row r-1): the im2col of a strided conv row, expressed in the UMMA descriptor alone
+  unsigned a_bytes;        // bytes delivered by one A TMA load
+  const void* b_packed;    // strip mode: weights pre-packed per K chunk in UMMA no-swizzle core-matrix order
+                           //   [k/8][n/8][8 rows][8 elems]; one 1-D bulk copy per chunk instead of a 2-D TMA box
   int Cout;
   long long out_sw, out_sh, out_sn;   // output element strides of (w, h, n)   (direct-store mode)
   const float* bias;                  // [Cout] or nullptr
@@ -48,16 +53,21 @@ struct TcGemmParams {
   int res_after_act;     // 0: act(acc + bias + res)   1: act(acc + bias) + res
 };
 
-template <int BN, int BK, int MODE>
+template <int BN, int BK, int MODE, int KSUB, int OCC>
 struct TcGemmCfg {
   static constexpr int BM = 128;
   static constexpr int A_STAGE = BM * BK * 2;
   static constexpr int B_STAGE = BN * BK * 2;
-  static constexpr int STAGE = A_STAGE + B_STAGE;
+  static constexpr int SUB = A_STAGE + B_STAGE;                                 // one K chunk (BK) of A and B
+  static constexpr int STAGE = KSUB * SUB;                                      // one pipeline stage = KSUB chunks
   static constexpr int HALF = BM * 128;                                        // 128 rows x 64 bf16 columns, 128B-swizzled
-  static constexpr int C_SLOTS = (MODE == OUT_DIRECT_F32) ? 0 : 2;             // output staging ring (64-column halves)
-  static constexpr int R_SLOTS = (MODE == OUT_TMA_RES) ? 2 : 0;                // residual prefetch ring
-  static constexpr int BUDGET = 224 * 1024;
+  // OCC = CTAs per SM.  OCC 2 (small tiles): two independent pipelines share an SM, so the epilogue of one
+  // CTA overlaps the loads / MMAs of the other; 4 epilogue warps, single staging slots, half the budget.
+  static constexpr int EPI_WARPS = (OCC == 2) ? 4 : 8;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+  static constexpr int C_SLOTS = (MODE == OUT_DIRECT_F32) ? 0 : (OCC == 2 ? 1 : 2);   // output staging ring (64-column halves)
+  static constexpr int R_SLOTS = (MODE == OUT_TMA_RES) ? (OCC == 2 ? 1 : 2) : 0;      // residual prefetch ring
+  static constexpr int BUDGET = (OCC == 2) ? 111 * 1024 : 224 * 1024;
   static constexpr int FIT = (BUDGET - (C_SLOTS + R_SLOTS) * HALF) / STAGE;
   static constexpr int STAGES = FIT > 8 ? 8 : FIT;
   static constexpr int SMEM = STAGES * STAGE + (C_SLOTS + R_SLOTS) * HALF + 1024 /*align slack*/;
@@ -67,21 +77,23 @@ struct TcGemmCfg {
   static constexpr uint32_t SBO = 8u * BK * 2u;                 // 8-row group pitch
   static_assert(BK == 64 || BK == 32, "BK must be one swizzle row");
   static_assert(BN == 64 || BN == 128 || BN == 256, "BN must be 64, 128 or 256");
+  static_assert(OCC == 1 || TMEM_COLS <= 256, "two CTAs per SM share the 512 TMEM columns");
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
 
-template <int BN, int BK, int MODE>
-__global__ void __launch_bounds__(384, 1)
+template <int BN, int BK, int MODE, int KSUB, int OCC>
+__global__ void __launch_bounds__(128 + ((OCC == 2) ? 128 : 256), OCC)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                const TcGemmParams p) {
-  using Cfg = TcGemmCfg<BN, BK, MODE>;
+  using Cfg = TcGemmCfg<BN, BK, MODE, KSUB, OCC>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 8];
   __shared__ uint32_t tmem_slot_s;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // stage s, chunk j: A at a_base + (s*KSUB + j)*A_STAGE, B at b_base + (s*KSUB + j)*B_STAGE
   const uint32_t a_base = smem_base;
-  const uint32_t b_base = smem_base + Cfg::STAGES * Cfg::A_STAGE;
+  const uint32_t b_base = smem_base + Cfg::STAGES * KSUB * Cfg::A_STAGE;
   const uint32_t c_base = smem_base + Cfg::STAGES * Cfg::STAGE;
   const uint32_t r_base = c_base + Cfg::C_SLOTS * Cfg::HALF;
   const uint32_t bar_base = smem_u32(bars);
@@ -110,9 +122,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);   // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), Cfg::EPI_WARPS);   // one arrive per epilogue warp
       mbar_init(rfull_bar(a), 1);
-      mbar_init(rfree_bar(a), 8);
+      mbar_init(rfree_bar(a), Cfg::EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -130,7 +142,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = static_cast<uint32_t>(rows) * BK * 2 + Cfg::B_STAGE;
+      const uint32_t tx_bytes = p.a_bytes + Cfg::B_STAGE;
       int local = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
         const int nt = tile % p.tiles_n;
@@ -139,19 +151,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int h0 = ((mt / p.tw) % p.th) * p.bh;
         const int n0 = (mt / (p.tw * p.th)) * p.bn;
         const int c_shift = nt * p.a_c0_per_ntile;
-        int kcol = 0;
-        for (int ty = 0; ty < p.taps_h; ++ty) {
-          for (int tx = 0; tx < p.taps_w; ++tx) {
-            for (int kc = 0; kc < p.kchunks; ++kc, kcol += BK) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
-              mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-              tma_load_5d(a_base + stage * Cfg::A_STAGE, &tmA, full_bar(stage), kc * BK + c_shift,
-                          w0 + p.off_w + tx, h0 + p.off_h + (p.tap_h_in_dim4 ? 0 : ty), n0,
-                          p.tap_h_in_dim4 ? ty : 0);
-              tma_load_2d(b_base + stage * Cfg::B_STAGE, &tmB, full_bar(stage), kcol, nt * BN);
-              if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
-            }
+        // K iterations are (ty, tx, kc) flattened; one stage carries up to KSUB of them under one barrier so
+        // that the single-thread MMA issue loop pays its wait/commit latency once per KSUB chunks
+        for (int it = 0; it < k_iters; it += KSUB) {
+          const int nsub = (k_iters - it) < KSUB ? (k_iters - it) : KSUB;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), static_cast<uint32_t>(nsub) * (p.a_bytes + Cfg::B_STAGE));
+          for (int j = 0; j < nsub; ++j) {
+            const int kk = it + j;
+            const int kc = kk % p.kchunks;
+            const int tap = kk / p.kchunks;
+            const int tx = tap % p.taps_w, ty = tap / p.taps_w;
+            tma_load_5d(a_base + (stage * KSUB + j) * Cfg::A_STAGE, &tmA, full_bar(stage), p.a_strip ? 0 : kc * BK + c_shift,
+                        p.a_strip ? 0 : w0 + p.off_w + tx, h0 + p.off_h + (p.tap_h_in_dim4 ? 0 : ty), n0,
+                        p.tap_h_in_dim4 ? ty : 0);
+            if (p.b_packed != nullptr)
+              bulk_load_1d(b_base + (stage * KSUB + j) * Cfg::B_STAGE,
+                           static_cast<const uint8_t*>(p.b_packed) + (size_t)(nt * k_iters + kk) * Cfg::B_STAGE, Cfg::B_STAGE,
+                           full_bar(stage));
+            else
+              tma_load_2d(b_base + (stage * KSUB + j) * Cfg::B_STAGE, &tmB, full_bar(stage), kk * BK, nt * BN);
           }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -168,15 +189,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int it = 0; it < k_iters; ++it) {
+        for (int it = 0; it < k_iters; it += KSUB) {
+          const int nsub = (k_iters - it) < KSUB ? (k_iters - it) : KSUB;
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_kmajor(a_base + stage * Cfg::A_STAGE, Cfg::SBO, Cfg::LAYOUT);
-          const uint64_t bdesc = umma_desc_kmajor(b_base + stage * Cfg::B_STAGE, Cfg::SBO, Cfg::LAYOUT);
+          for (int j = 0; j < nsub; ++j) {
+            const uint32_t a_addr = a_base + (stage * KSUB + j) * Cfg::A_STAGE;
+            // strip mode: SWIZZLE_NONE K-major core matrices (8 rows x 16 B, rows 16 B apart), LBO = 16 B, SBO = 128 B
+            const uint64_t adesc = p.a_strip ? umma_desc_nosw(a_addr, 16u, 128u) : umma_desc_kmajor(a_addr, Cfg::SBO, Cfg::LAYOUT);
+            const uint32_t b_addr = b_base + (stage * KSUB + j) * Cfg::B_STAGE;
+            // packed B: core matrices [k/8][n/8]: LBO (next k core) = BN/8 * 128 B, SBO (next n core) = 128 B
+            const uint64_t bdesc = p.b_packed != nullptr ? umma_desc_nosw(b_addr, BN * 16u, 128u)
+                                                         : umma_desc_kmajor(b_addr, Cfg::SBO, Cfg::LAYOUT);
+            const uint32_t b_step = p.b_packed != nullptr ? (2u * BN * 16u) >> 4 : 2u;   // K=16 = two k cores
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // +32 B per K=16 step inside the swizzle row: start-address field += 2
-            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (it | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // swizzled operands: +32 B per K=16 step inside the swizzle row (start-address field += 2)
+              umma_bf16(d_tmem, adesc + 2u * k, bdesc + b_step * k, idesc, (it | j | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(empty_bar(stage));
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
@@ -195,8 +225,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int h0 = ((mt / p.tw) % p.th) * p.bh;
         const int n0 = (mt / (p.tw * p.th)) * p.bn;
         for (int hf = 0; hf < Cfg::HALVES; ++hf, ++hcount) {
-          const int slot = hcount & 1;
-          mbar_wait(rfree_bar(slot), ((hcount >> 1) & 1u) ^ 1u);
+          constexpr int RS = Cfg::R_SLOTS > 0 ? Cfg::R_SLOTS : 1;
+          const int slot = hcount % RS;
+          mbar_wait(rfree_bar(slot), ((hcount / RS) & 1u) ^ 1u);
           mbar_arrive_expect_tx(rfull_bar(slot), static_cast<uint32_t>(rows) * 128);
           tma_load_5d(r_base + slot * Cfg::HALF, &tmR, rfull_bar(slot), nt * BN + hf * 64, w0, h0, n0, 0);
         }
@@ -205,7 +236,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int grp = (warp - 4) >> 2;           // two warps share a quarter: even / odd 32-column chunks
+    const int grp = (warp - 4) >> 2;           // OCC 1: two warps share a quarter (even / odd 32-column chunks)
+    constexpr int EPI_THREADS = Cfg::EPI_WARPS * 32;
+    constexpr int CPW = 8 / Cfg::EPI_WARPS;    // 32-column chunks of a 64-column half handled by one warp
     const int r = q * 32 + lane;               // row of the tile owned by this thread
     const bool store_thread = (threadIdx.x == 128);
     uint32_t hcount = 0;                       // 64-column halves handled so far (ring positions)
@@ -251,7 +284,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int w = w0 + dw, h = h0 + dh, n = n0 + dn;
         const bool valid = (r < rows) && (w < p.W) && (h < p.H) && (n < p.NB);
 #pragma unroll 1
-        for (int c = grp; c < BN / 32; c += 2) {
+        for (int c = grp; c < BN / 32; c += 2 / CPW) {
           float f[32];
           load_chunk(c, f);
           apply_act(f);
@@ -265,47 +298,56 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else {
 #pragma unroll 1
         for (int hf = 0; hf < Cfg::HALVES; ++hf, ++hcount) {
-          const int slot = hcount & 1;
-          // staging slot `slot` was last read by the TMA store issued two halves ago
-          if (store_thread) bulk_wait_group_read<1>();
-          named_bar_sync(1, 256);
+          constexpr int CS = Cfg::C_SLOTS > 0 ? Cfg::C_SLOTS : 1;
+          constexpr int RS = Cfg::R_SLOTS > 0 ? Cfg::R_SLOTS : 1;
+          const int slot = hcount % CS;
+          const int rslot = hcount % RS;
+          // staging slot `slot` was last read by the TMA store issued CS halves ago
+          if (store_thread) bulk_wait_group_read<CS - 1>();
+          named_bar_sync(1, EPI_THREADS);
           const uint32_t cbuf = c_base + slot * Cfg::HALF;
-          const uint32_t rbuf = r_base + slot * Cfg::HALF;
-          float f[32];
-          load_chunk(2 * hf + grp, f);           // the two warp groups take the two 32-column chunks of this half
+          const uint32_t rbuf = r_base + rslot * Cfg::HALF;
           const uint32_t row_off = r * 128;
-          const int j0 = grp * 4;                // first 16-byte chunk of this thread inside the 128 B row
-          if (MODE == OUT_TMA_RES) {
-            if (p.res_after_act) apply_act(f);
-            mbar_wait(rfull_bar(slot), (hcount >> 1) & 1u);
+          if (MODE == OUT_TMA_RES) mbar_wait(rfull_bar(rslot), (hcount / RS) & 1u);
+#pragma unroll
+          for (int cc = 0; cc < CPW; ++cc) {
+            const int sub = (CPW == 1) ? grp : cc;   // which 32-column chunk of this half
+            float f[32];
+            load_chunk(2 * hf + sub, f);
+            const int j0 = sub * 4;                  // first 16-byte chunk of this thread inside the 128 B row
+            if (MODE == OUT_TMA_RES) {
+              if (p.res_after_act) apply_act(f);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 u;
+                ld_shared_v4(rbuf + row_off + (((j0 + j) ^ (r & 7)) << 4), u);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t = __bfloat1622float2(h2[e]);
+                  f[j * 8 + e * 2] += t.x;
+                  f[j * 8 + e * 2 + 1] += t.y;
+                }
+              }
+              if (!p.res_after_act) apply_act(f);
+            } else {
+              apply_act(f);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 u;
-              ld_shared_v4(rbuf + row_off + (((j0 + j) ^ (r & 7)) << 4), u);
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 t = __bfloat1622float2(h2[e]);
-                f[j * 8 + e * 2] += t.x;
-                f[j * 8 + e * 2 + 1] += t.y;
-              }
+              for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
+              st_shared_v4(cbuf + row_off + (((j0 + j) ^ (r & 7)) << 4), u);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(rfree_bar(slot));
-            if (!p.res_after_act) apply_act(f);
-          } else {
-            apply_act(f);
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
-            st_shared_v4(cbuf + row_off + (((j0 + j) ^ (r & 7)) << 4), u);
+          if (MODE == OUT_TMA_RES) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(rfree_bar(rslot));
           }
           fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
-          named_bar_sync(2, 256);
+          named_bar_sync(2, EPI_THREADS);
           if (store_thread) {
             if (nt * BN + hf * 64 < p.Cout) tma_store_5d(&tmC, cbuf, nt * BN + hf * 64, w0, h0, n0, 0);
             bulk_commit_group();

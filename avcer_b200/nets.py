@@ -18,7 +18,7 @@ import torch
 from . import ops, weights
 from ._lib import require_device
 
-PAD = ops.PAD_HW          # 232: padded rows/cols of the stem input
+PAD_H, PAD = ops.PAD_H, ops.PAD_W      # 232 rows x 240-pixel pitch of the zero-bordered stem input
 _BIG = 1 << 30
 
 
@@ -65,7 +65,7 @@ def _dtype(precision: str) -> torch.dtype:
 
 
 class VSNet:
-    """Static visual ResNet-50.  forward(x) with x = zero-bordered NHWC4 crops [n,232,232,4]
+    """Static visual ResNet-50.  forward(x) with x = zero-bordered NHWC4 crops [n,232,240,4]
     (layout 1/2 of avcer_preprocess_u8) -> (probabilities [n,7] fp32, relu(fc1) features [n,512])."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], precision: str = "bf16", device: str = "cuda:0"):
@@ -81,17 +81,25 @@ class VSNet:
 
     def alloc_input(self, n: int) -> torch.Tensor:
         """Zero-bordered input buffer; the border is written once here, K1 only fills the interior."""
-        return torch.zeros((n, PAD, PAD, 4), device=self.device, dtype=self.dtype)
+        return torch.zeros((n, PAD_H, PAD, 4), device=self.device, dtype=self.dtype)
 
     def stem(self, x: torch.Tensor) -> torch.Tensor:
         n = x.shape[0]
         st = self.w["stem"]
         y = torch.empty((n, 112, 112, 64), device=self.device, dtype=self.dtype)
-        # A view: (8 pixels x 4 ch = 32, ox stride 2 px, oy stride 2 rows, n, ky stride 1 row)
-        ops.contract(a=x, a_dim=(32, 112, 112, n, 7), a_stride=(1, 8, 2 * PAD * 4, PAD * PAD * 4, PAD * 4),
-                     wt=st.wt, bias=st.bias, out=y, out_stride=(64, 112 * 64, 112 * 112 * 64), W=112, H=112, NB=n,
-                     cin=32, cout=64, taps_w=1, taps_h=7, tap_h_in_dim4=True, act=ops.ACT_RELU,
-                     algo_k=147)          # 7x7x3 real taps; the padded pixel/channel carry zero weights
+        if self.dtype == torch.bfloat16:
+            # Strip mode: one padded image row (240 px x 4 ch = 1920 B = 15 x 128 B) is fetched once per (oy, ky);
+            # output ox reads the 32 elements starting 16 B * ox into it (overlap expressed in the MMA descriptor).
+            ops.contract(a=x, a_dim=(64, PAD * 4 // 64, 112, n, 7), a_stride=(1, 64, 2 * PAD * 4, PAD_H * PAD * 4, PAD * 4),
+                         wt=st.wt, bias=st.bias, out=y, out_stride=(64, 112 * 64, 112 * 112 * 64), W=112, H=112, NB=n,
+                         cin=32, cout=64, taps_w=1, taps_h=7, tap_h_in_dim4=True, act=ops.ACT_RELU, algo_k=147,
+                         a_strip=True, wt_packed=self.w["stem_packed"])
+        else:
+            # A view: (8 pixels x 4 ch = 32, ox stride 2 px, oy stride 2 rows, n, ky stride 1 row)
+            ops.contract(a=x, a_dim=(32, 112, 112, n, 7), a_stride=(1, 8, 2 * PAD * 4, PAD_H * PAD * 4, PAD * 4),
+                         wt=st.wt, bias=st.bias, out=y, out_stride=(64, 112 * 64, 112 * 112 * 64), W=112, H=112, NB=n,
+                         cin=32, cout=64, taps_w=1, taps_h=7, tap_h_in_dim4=True, act=ops.ACT_RELU,
+                         algo_k=147)          # 7x7x3 real taps; the padded pixel/channel carry zero weights
         return y
 
     def _conv(self, x: torch.Tensor, pc: weights.PackedConv, act: int, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -100,7 +108,7 @@ class VSNet:
                                residual=residual, act=act)
 
     def forward(self, x: torch.Tensor, taps: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        assert x.shape[1:] == (PAD, PAD, 4) and x.dtype == self.dtype
+        assert x.shape[1:] == (PAD_H, PAD, 4) and x.dtype == self.dtype
         y = self.stem(x)
         if taps is not None:
             taps["stem"] = y

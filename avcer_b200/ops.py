@@ -87,7 +87,8 @@ def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], 
              cin: int, cout: int, taps_w: int = 1, taps_h: int = 1, off_w: int = 0, off_h: int = 0,
              tap_h_in_dim4: bool = False, group_cin_shift: int = 0, residual: Optional[torch.Tensor] = None,
              res_stride: Optional[Sequence[int]] = None, act: int = ACT_NONE, res_after_act: bool = False,
-             a_offset: int = 0, algo_k: Optional[int] = None) -> torch.Tensor:
+             a_offset: int = 0, algo_k: Optional[int] = None, a_strip: bool = False,
+             wt_packed: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Generic implicit GEMM (see avcer_contract in include/avcer_b200.h)."""
     _cuda(a, "a")
     d = ContractDesc()
@@ -109,6 +110,8 @@ def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], 
     d.taps_w, d.taps_h, d.off_w, d.off_h = taps_w, taps_h, off_w, off_h
     d.tap_h_in_dim4 = int(tap_h_in_dim4)
     d.group_cin_shift = group_cin_shift
+    d.a_strip = int(a_strip)
+    d.wt_packed = _ptr(wt_packed)
     d.act = act
     d.res_after_act = int(res_after_act)
     d.dtype = code
@@ -160,7 +163,7 @@ def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, r
 
 
 # ----------------------------------------------------------------------------------------- K1
-PAD_HW = 232
+PAD_H, PAD_W = 232, 240      # zero-bordered stem input: rows x row pitch (pixels); 240 px = 15 x 128 B
 
 
 def preprocess(src: torch.Tensor, n: int, dst: torch.Tensor, layout: int, *, offsets: Optional[torch.Tensor] = None,

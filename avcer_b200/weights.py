@@ -64,6 +64,8 @@ def pack_vs(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
     stem = torch.zeros(64, 7, 8, 4)
     stem[:, :, :7, :3] = w.permute(0, 2, 3, 1)          # [co, ky, kx, c]
     out["stem"] = PackedConv(dev(stem.reshape(64, 7 * 32)), dev(b, torch.float32), 32, 64, 7, 2)
+    # the same weights per filter row in UMMA core-matrix order [ky][k/8][cout/8][8 cout][8 k] (strip-mode B operand)
+    out["stem_packed"] = dev(stem.reshape(8, 8, 7, 4, 8).permute(2, 3, 0, 1, 4).contiguous().reshape(-1))
     blocks: List[dict] = []
     cin = 64
     for li, (planes, nblocks) in enumerate(zip(VS_PLANES, VS_BLOCKS), start=1):

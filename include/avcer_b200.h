@@ -44,7 +44,7 @@ int avcer_num_sms(void);
  * src: u8 crops, HWC with 3 channels in the order cv2.imread delivers (BGR); crop i starts at
  *      src + src_offsets[i] and is src_h[i] x src_w[i] (row pitch src_w*3).
  * dst layout 0: fp32 NCHW [n,3,224,224] (bit-exact restatement of the reference tensor);
- * dst layout 1: bf16 zero-bordered NHWC4 [n, 232, 232, 4] with the image at rows/cols 2..225
+ * dst layout 1: bf16 zero-bordered NHWC4 [n, 232, 240, 4] (row pitch 240 px) with the image at rows/cols 2..225
  *               (TF-"same" padding 2|3 of the stem, architectures/video.py:63-90, materialised
  *               once; channel 3 is zero) -- the layout the tensor-core stem consumes;
  * dst layout 2: fp32, same geometry as layout 1 (fp32 mode).
@@ -88,6 +88,11 @@ typedef struct {
   int32_t cin, cout;         /* cin = contraction channels per tap */
   int32_t taps_w, taps_h, off_w, off_h, tap_h_in_dim4;
   int32_t group_cin_shift;   /* grouped conv: channel shift per 64 output channels, else 0 */
+  int32_t a_strip;           /* bf16 only. 1: a_dim = (e, chunks, h, n, taps_h) describes, for every (h, n, tap), ONE
+                              * contiguous strip of e*chunks elements; output position w reads the cin elements that
+                              * start 16 bytes * w into the strip (overlapping windows: a strided conv row).  The
+                              * strip is fetched once per tap; the overlap lives in the MMA descriptor (no im2col). */
+  const void* wt_packed;     /* strip mode: weights per K chunk in UMMA core-matrix order [k/8][cout/8][8][8] */
   int32_t act;
   int32_t res_after_act;     /* 0: act(acc+bias+res); 1: act(acc+bias)+res */
   int32_t dtype;             /* AVCER_BF16 / AVCER_F32 (operands) */

@@ -54,7 +54,7 @@ def test_k1_packed_layouts(cuda_lib):
     ref = np.concatenate([ov.pth_processing(c) for c in crops])
     assert np.array_equal(nchw.cpu().numpy(), ref)
     for layout, dt in ((1, torch.bfloat16), (2, torch.float32)):
-        pad = torch.zeros((5, 232, 232, 4), device=DEV, dtype=dt)
+        pad = torch.zeros((5, 232, 240, 4), device=DEV, dtype=dt)
         ops.preprocess(src, 5, pad, layout)
         inner = pad[:, 2:226, 2:226, :3].permute(0, 3, 1, 2).float().cpu()
         assert torch.equal(inner, torch.from_numpy(ref).to(dt).float())          # one rounding, nothing else

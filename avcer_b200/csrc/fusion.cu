@@ -11,13 +11,17 @@
 namespace avcer {
 
 // Compound expressions as pairs of basic-emotion indices in audio order (run.py:66-74).
-__constant__ int c_pair[7][2] = {{3, 6}, {4, 6}, {5, 6}, {2, 6}, {1, 6}, {3, 5}, {1, 5}};
+// constexpr (not __constant__): the indices must fold at compile time so that the 7-value rows stay in registers
+__host__ __device__ constexpr int pair_a(int k) { return k == 0 ? 3 : k == 1 ? 4 : k == 2 ? 5 : k == 3 ? 2 : k == 4 ? 1 : k == 5 ? 3 : 1; }
+__host__ __device__ constexpr int pair_b(int k) { return k < 5 ? 6 : 5; }
 
 struct FuseParams {
   double w[3][7];      // weights_1[m][c] (unused when !has_w1)
   double w2[3];        // weights_2[m]
   double ce_w[7][2];   // rule-2 pair weights (1,1 when !ce_weights_type)
   int has_w1, ce_mask;
+  int w2_one, cew_one;   // every weights_2[m] == 1 / every rule weight == 1: the exact no-op multiplies are skipped
+                         // (B200's vector FP64 rate, not HBM, bounds this kernel)
 };
 
 template <typename TC> struct Arith;
@@ -45,8 +49,11 @@ __device__ __forceinline__ long long compound_argmax(const TC (&s)[7], const Fus
   int bi = 0;
 #pragma unroll
   for (int k = 0; k < 7; ++k) {
-    const TC a = A::mul(v[c_pair[k][0]], (TC)p.ce_w[k][0]);
-    const TC b = A::mul(v[c_pair[k][1]], (TC)p.ce_w[k][1]);
+    TC a = v[pair_a(k)], b = v[pair_b(k)];
+    if (!p.cew_one) {                      // x * 1 == x bit-for-bit (NaN, inf and -0 included)
+      a = A::mul(a, (TC)p.ce_w[k][0]);
+      b = A::mul(b, (TC)p.ce_w[k][1]);
+    }
     const TC pr = A::add(a, b);
     if (k == 0) { best = pr; bi = 0; }
     else if (pr > best || (pr != pr && best == best)) { best = pr; bi = k; }
@@ -69,7 +76,10 @@ __device__ __forceinline__ void fuse_one(const TIn (&a)[7], const TIn (&b)[7], c
 #pragma unroll
     for (int m = 0; m < 3; ++m)
 #pragma unroll
-      for (int k = 0; k < 7; ++k) x[m][k] = A::mul(A::mul(x[m][k], (TC)p.w[m][k]), (TC)p.w2[m]);
+      for (int k = 0; k < 7; ++k) {
+        x[m][k] = A::mul(x[m][k], (TC)p.w[m][k]);
+        if (!p.w2_one) x[m][k] = A::mul(x[m][k], (TC)p.w2[m]);
+      }
 #pragma unroll
     for (int k = 0; k < 7; ++k) av[k] = A::add(A::add(x[0][k], x[1][k]), x[2][k]);
   } else {
@@ -83,25 +93,38 @@ __device__ __forceinline__ void fuse_one(const TIn (&a)[7], const TIn (&b)[7], c
   lab[3] = compound_argmax<TC>(x[2], p);
 }
 
-// Warp-cooperative streaming pass: every lane owns FPT consecutive frames (FPT*7 values per stream are
-// a whole number of 16-byte vectors, so all loads are aligned 128-bit loads and a warp covers one
-// contiguous span of each stream); 21 independent vector loads are in flight per lane before any math;
-// labels leave as 128-bit stores.  No shared memory, no barriers.
+// Warp-cooperative streaming pass.  A warp owns 32*FPT consecutive frames (FPT = 4 for f32, 2 for f64 inputs):
+// each of the three probability streams is fetched with seven fully coalesced 128-bit loads per lane (one
+// contiguous 3584-byte span per stream), staged in a warp-private shared-memory tile (conflict-free both ways,
+// __syncwarp only -- no block barrier), then every lane finishes its FPT frames and the labels leave as
+// coalesced 128-bit stores.
 template <typename TIn, typename TC>
 __global__ void __launch_bounds__(FUSE_THREADS)
 fuse_compound_kernel(const TIn* __restrict__ pvs, const TIn* __restrict__ pvd, const TIn* __restrict__ pa,
                      long long n, const FuseParams p, long long* __restrict__ labels) {
-  constexpr int FPT = 16 / sizeof(TIn);            // frames per thread: 4 (f32) or 2 (f64)
-  constexpr int NV = 7;                            // 16-byte vectors per stream per thread
-  const long long groups = n / FPT;
-  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += (long long)gridDim.x * blockDim.x) {
-    const long long f0 = gidx * FPT;
+  constexpr int FPT = 16 / sizeof(TIn);            // frames per lane
+  constexpr int NV = 7;                            // 16-byte vectors per lane per stream
+  constexpr int WARPS = FUSE_THREADS / 32;
+  __shared__ uint4 tile[WARPS][32 * NV];       // one stream at a time: 3.5 KB per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long groups = n / (32 * FPT);         // full warp-chunks
+  const TIn* src[3] = {pvs, pvd, pa};
+  for (long long g = (long long)blockIdx.x * WARPS + warp; g < groups; g += (long long)gridDim.x * WARPS) {
+    const long long f0 = g * 32 * FPT;
     uint4 v[3][NV];
-    const TIn* src[3] = {pvs, pvd, pa};
 #pragma unroll
     for (int m = 0; m < 3; ++m)
 #pragma unroll
-      for (int k = 0; k < NV; ++k) v[m][k] = __ldg(reinterpret_cast<const uint4*>(src[m] + f0 * 7) + k);
+      for (int k = 0; k < NV; ++k) v[m][k] = __ldg(reinterpret_cast<const uint4*>(src[m] + f0 * 7) + lane + 32 * k);
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {          // lane-strided (coalesced) order -> frame-major order, through the tile
+#pragma unroll
+      for (int k = 0; k < NV; ++k) tile[warp][lane + 32 * k] = v[m][k];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < NV; ++k) v[m][k] = tile[warp][lane * NV + k];
+      __syncwarp();
+    }
     long long lab[FPT][4];
 #pragma unroll
     for (int j = 0; j < FPT; ++j) {
@@ -114,24 +137,25 @@ fuse_compound_kernel(const TIn* __restrict__ pvs, const TIn* __restrict__ pvd, c
       }
       fuse_one<TIn, TC>(a, b, c, p, lab[j]);
     }
+    const long long fl = f0 + (long long)lane * FPT;
     if ((n & 1) == 0) {              // every label row starts 16-byte aligned
 #pragma unroll
       for (int s = 0; s < 4; ++s)
 #pragma unroll
         for (int j = 0; j < FPT; j += 2) {
           longlong2 o = make_longlong2(lab[j][s], lab[j + 1][s]);
-          *reinterpret_cast<longlong2*>(labels + s * n + f0 + j) = o;
+          *reinterpret_cast<longlong2*>(labels + s * n + fl + j) = o;
         }
     } else {
 #pragma unroll
       for (int s = 0; s < 4; ++s)
 #pragma unroll
-        for (int j = 0; j < FPT; ++j) labels[s * n + f0 + j] = lab[j][s];
+        for (int j = 0; j < FPT; ++j) labels[s * n + fl + j] = lab[j][s];
     }
   }
-  // tail frames (n % FPT) by the first threads of block 0
-  if (blockIdx.x == 0 && threadIdx.x < n - groups * FPT) {
-    const long long f = groups * FPT + threadIdx.x;
+  // tail frames (n % (32*FPT)) one per thread, by block 0
+  const long long tail0 = groups * 32 * FPT;
+  for (long long f = tail0 + threadIdx.x + (long long)blockIdx.x * blockDim.x; f < n; f += (long long)gridDim.x * blockDim.x) {
     TIn a[7], b[7], c[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) { a[k] = pvs[f * 7 + k]; b[k] = pvd[f * 7 + k]; c[k] = pa[f * 7 + k]; }
@@ -278,12 +302,15 @@ static int fuse_compound_impl(const TIn* p_vs, const TIn* p_vd, const TIn* p_a, 
       p.ce_w[k][1] = 1.0;
     }
   }
+  p.w2_one = p.has_w1 && p.w2[0] == 1.0 && p.w2[1] == 1.0 && p.w2[2] == 1.0;
+  p.cew_one = !ce_weights_type;
   const bool aligned = ((reinterpret_cast<uintptr_t>(p_vs) | reinterpret_cast<uintptr_t>(p_vd) | reinterpret_cast<uintptr_t>(p_a) |
                          reinterpret_cast<uintptr_t>(labels)) & 15) == 0;
   constexpr int kFpt = 16 / sizeof(TIn);
   const long long work = aligned ? n / kFpt : n;
   const long long blocks_needed = (work + FUSE_THREADS - 1) / FUSE_THREADS + 1;
-  const long long cap = 148ll * 16;
+  (void)kFpt;
+  const long long cap = 1ll << 20;           // one warp-chunk per warp: no second, mostly empty round
   const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
   cudaStream_t st = as_stream(stream);
   // numpy promotes to float64 as soon as the (Python-float) weight lists take part; without

@@ -46,7 +46,15 @@ def section(start_prefix, specs, title, brief):
     idx = [i for i, (n, _) in enumerate(seq) if n.startswith(start_prefix)]
     if len(idx) < 2: return
     part = seq[idx[0]:idx[1]]
-    tc = [(n, t) for n, t in part if n.startswith('tc_gemm')]
+    # graph warm-up runs the forward twice back to back: keep the first pass only
+    ntc = 0
+    for j, (n, _) in enumerate(part):
+        if n.startswith('tc_gemm'):
+            ntc += 1
+            if ntc == len(specs):
+                part = part[:j + 1 + next((k for k, (m, _) in enumerate(part[j + 1:]) if m.startswith('tc_gemm')), len(part))]
+                break
+    tc = [(n, t) for n, t in part if n.startswith('tc_gemm')][:len(specs)]
     print(f"\n== {title}: {sum(t for _, t in part):.0f} us total, {sum(t for _, t in tc):.0f} us in tc_gemm ({len(tc)} launches, {len(specs)} expected)")
     totf = 0
     for (n, t), (name, M, N, K) in zip(tc, specs):
@@ -60,4 +68,5 @@ def section(start_prefix, specs, title, brief):
     for k, v in sorted(other.items(), key=lambda kv: -kv[1]): print(f"  {v:9.1f} us  {k}")
 
 section('preprocess', vs_specs(), "VS forward, batch 256", False)
-section('audio_normalize', a_specs(), "A forward, 32 windows", True)
+ab = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+section('audio_normalize', a_specs(ab), f"A forward, {ab} windows", True)

@@ -157,3 +157,47 @@ def test_contract_against_oracle_conv(cuda_lib):
             got = ops.conv2d_nhwc(x.to(DEV), wt.to(DEV), b.to(DEV), kh=k, kw=k, stride=stride, pad_h=pad, pad_w=pad,
                                   residual=None if r is None else r.to(DEV), act=ops.ACT_RELU).float().cpu()
             assert (got - ref).abs().max().item() < tol, (dtype, n, h, w, cin, cout, k, stride)
+
+
+def test_stem_strip_mode_matches_oracle_conv(cuda_lib):
+    """The 7x7/2 "TF-same" stem as an implicit GEMM whose A operand is one contiguous padded image row per
+    filter row (overlapping windows expressed in the UMMA descriptor, no im2col): against F.conv2d on CPU."""
+    import torch.nn.functional as F
+    from avcer_b200 import nets, ops
+
+    sd = syn.make_vs_state_dict(0, "spread")
+    crops = syn.make_crops(3, 3)
+    ref_in = torch.from_numpy(np.concatenate([ov.pth_processing(c) for c in crops]))
+    s = sd["batch_norm1.weight"] / torch.sqrt(sd["batch_norm1.running_var"] + 1e-3)
+    ref = F.conv2d(F.pad(ref_in, [2, 3, 2, 3]), sd["conv_layer_s2_same.weight"], stride=2)
+    ref = F.relu(ref * s.view(1, -1, 1, 1) + (sd["batch_norm1.bias"] - sd["batch_norm1.running_mean"] * s).view(1, -1, 1, 1))
+    for prec, tol in (("fp32", 2e-4), ("bf16", 0.06)):
+        net = nets.VSNet(sd, prec, DEV)
+        x = net.alloc_input(3)
+        ops.preprocess(torch.from_numpy(crops).to(DEV), 3, x, net.input_layout)
+        y = net.stem(x).float().cpu().permute(0, 3, 1, 2)
+        assert y.shape == ref.shape == (3, 64, 112, 112)
+        assert (y - ref).abs().max().item() < tol, prec
+
+
+def test_gemm_tile_flavours_agree(cuda_lib):
+    """128x256 / 128x128 / 128x64 tiles, one or two CTAs per SM, fp32-out direct epilogue: same GEMM, same answer."""
+    from avcer_b200 import ops
+
+    gen = torch.Generator().manual_seed(1)
+    for (m, k, n) in ((40000, 256, 512), (999, 1024, 256), (5000, 64, 64), (70000, 128, 128), (300, 512, 2048)):
+        x = torch.randn(m, k, generator=gen).bfloat16()
+        w = (torch.randn(n, k, generator=gen) / k ** 0.5).bfloat16()
+        b = torch.randn(n, generator=gen)
+        r = torch.randn(m, n, generator=gen).bfloat16()
+        ref = x.float() @ w.float().t() + b
+        got = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV)).float().cpu()
+        assert (got - ref).abs().max().item() < 0.05, (m, k, n)
+        got = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), residual=r.to(DEV), act=ops.ACT_GELU).float().cpu()
+        assert (got - F_gelu(ref + r.float())).abs().max().item() < 0.06, (m, k, n)
+        got = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), out_dtype=torch.float32).cpu()
+        assert (got - ref).abs().max().item() < 2e-3, (m, k, n)
+
+
+def F_gelu(t):
+    return torch.nn.functional.gelu(t)

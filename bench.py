@@ -231,6 +231,10 @@ def main():
     kern = {k: {"work": v[0], "ms": v[1], "launches": v[2]} for k, v in agg.items()}
     step_ms = ms / args.steps
     roofline = None
+    traffic = None
+    digest = os.path.join(ROOT, "profiles", "r01_kernel_digest.json")
+    if os.path.exists(digest):          # dram__bytes_read.sum + dram__bytes_write.sum per tc_gemm launch (ncu, same workload at 1 clip)
+        traffic = json.load(open(digest)).get("tc_gemm_kernel", {}).get("dram_bytes_per_launch")
     prof_note = ("per-launch CUDA events on one extra eager step run right after the timed region "
                  f"(that step: {profiled_step_ms:.1f} ms; timed steps replay CUDA graphs: {step_ms:.1f} ms)")
     tc = kern.get("contract_bf16") or kern.get("contract_f32")
@@ -238,7 +242,8 @@ def main():
         ach = tc["work"] / (tc["ms"] / 1e3) / 1e12
         roofline = {"kernel": "tc_gemm_kernel (tcgen05 implicit GEMM: all VS/VD/A contractions)", "bound": "tensor", "achieved": ach,
                     "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
-                    "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)", "traffic": None,
+                    "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)", "traffic": traffic,
+                    "traffic_note": "mean DRAM bytes per tc_gemm launch from profiles/r01_kernel_digest.json (ncu, 1-clip run of this bench)",
                     "launches_per_step": tc["launches"], "avg_launch_us": 1e3 * tc["ms"] / tc["launches"],
                     "share_of_step": tc["ms"] / profiled_step_ms, "algorithmic_flop_per_step": tc["work"], "how": prof_note}
     extra = {}

@@ -5,10 +5,10 @@ path = sys.argv[1]
 rows = list(csv.reader(open(path)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
 hdr = rows[hi]; data = rows[hi + 1:]
-ki = hdr.index('Kernel Name'); vi = hdr.index('Metric Value'); ui = hdr.index('Metric Unit')
+ki = hdr.index('Kernel Name'); vi = hdr.index('Metric Value'); ui = hdr.index('Metric Unit'); mi = hdr.index('Metric Name')
 seq = []
 for r in data:
-    if len(r) <= vi: continue
+    if len(r) <= vi or not r[mi].startswith('gpu__time_duration'): continue
     v = float(r[vi].replace(',', '')); u = r[ui]
     if u == 'ns': v /= 1000
     elif u == 'ms': v *= 1000

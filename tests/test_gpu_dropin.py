@@ -74,3 +74,40 @@ def test_audio_driver_repeat_padding_raises_like_reference(cuda_lib, monkeypatch
     with pytest.raises(ZeroDivisionError):
         get_prob_audio_8_cl.preprocess_audio_and_predict(path_video="clip.mp4", path_weights="w", fps=25, step=1, padding="repeat")
     config.reset()
+
+
+@pytest.mark.parametrize("init", ["spread", "default"])
+def test_pipeline_compound_top1_agreement(cuda_lib, init):
+    """North-star bar: compound top-1 agreement >= 99.5 % (run.py's own configuration: AV-8cl weight matrix,
+    Rule 1) between the batched CUDA pipeline and the oracle of the reference path, bf16 and fp32, on a clip
+    with gaps; fp32 mode must agree on every frame."""
+    import pandas as pd
+
+    from avcer_b200 import get_weights_matrices as gwm
+    from avcer_b200.pipeline import Engine
+    from oracle import audio as oa, fusion as of, video as ov
+
+    n, fps = 200, 25
+    exists = np.ones(n, bool)
+    exists[[40, 41, 133]] = False
+    crops = syn.make_crops(500, n)
+    wav = syn.make_wav(501, int(n / fps * 16000) - 160)
+    sd_vs, sd_vd = syn.make_vs_state_dict(0, init), syn.make_vd_state_dict(1, init)
+    sd_a = syn.make_audio_state_dict(2, 8, init, 12)
+    o_dyn, o_stat = ov.predict_video([crops[i] if exists[i] else None for i in range(n)], fps, sd_vs, sd_vd)
+    rows, ids, _ = oa.predict_audio(wav, fps, sd_a)
+    stat_df = pd.DataFrame(o_stat, columns=of.VIDEO_ORDER)
+    dyn_df = pd.DataFrame(o_dyn, columns=of.VIDEO_ORDER)
+    audio_df = pd.DataFrame(rows, columns=of.AUDIO_ORDER)
+    audio_df["frames"] = [str(i).zfill(6) + ".jpg" for i in ids]
+    w1, w2 = gwm.class_weights(gwm.weights_3), [1, 1, 1]
+    ref = np.stack(of.get_c_expr_db_pred(stat_df, dyn_df, audio_df, "c", w1, w2, False, True)[:4])
+    for prec, bar in (("fp32", 1.0), ("bf16", 0.995)):
+        eng = Engine(sd_vs, sd_vd, sd_a, precision=prec, device="cuda:0")
+        out = eng.run_clips(torch.from_numpy(crops[exists]), [exists], [fps], torch.from_numpy(wav), [len(wav)], w1, w2, False, True)
+        got = out["labels"].cpu().numpy()
+        agree = (got == ref).mean(axis=1)
+        assert agree.min() >= bar, (prec, agree)
+        # the same engine through CUDA graphs (second call replays) gives identical labels
+        again = eng.run_clips(torch.from_numpy(crops[exists]), [exists], [fps], torch.from_numpy(wav), [len(wav)], w1, w2, False, True)
+        assert torch.equal(again["labels"], out["labels"])

@@ -269,6 +269,74 @@ __global__ void compound_scores_kernel(const TC* __restrict__ pred, long long n,
   out[i] = (double)A::add(A::mul(a, (TC)t.w1[k]), A::mul(b, (TC)t.w2[k]));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight search: data/utils.py:138-163 (get_weights_prob_model: 10 000 Dirichlet
+// weight sets) and :166-209 (get_weights_v_model / get_weights_av_model: grid over per-model weights).
+// For every candidate weight set the reference recomputes  argmax_c sum_m P_m[f,c] * w[m,c]  over all frames
+// and a classification report.  Here one launch evaluates all candidates: lanes own weight sets (their 21
+// weights live in registers, their 7x7 confusion counters in a private shared-memory row -- no atomics), a
+// tile of frames is staged in shared memory and broadcast to the lanes.  Arithmetic is the reference's:
+// binary64, (p0*w0 + p1*w1) + p2*w2 with separate multiplies and adds, first-maximum argmax.
+constexpr int WS_FRAMES = 128;      // frames per staged tile
+constexpr int WS_WARPS = 8;         // 256 weight sets per CTA
+
+template <int M>
+__global__ void __launch_bounds__(WS_WARPS * 32)
+weight_search_kernel(const double* __restrict__ preds, long long n, const int* __restrict__ gt,
+                     const double* __restrict__ weights, long long n_weights, int frame_groups,
+                     unsigned long long* __restrict__ cm) {
+  extern __shared__ unsigned char ws_smem[];
+  double* sp = reinterpret_cast<double*>(ws_smem);                               // [WS_FRAMES][M*7]
+  int* sgt = reinterpret_cast<int*>(sp + WS_FRAMES * M * 7);                    // [WS_FRAMES]
+  unsigned* cnt = reinterpret_cast<unsigned*>(sgt + WS_FRAMES);                  // [256][49]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long ws = (long long)blockIdx.x * (WS_WARPS * 32) + threadIdx.x;    // this lane's weight set
+  const bool active = ws < n_weights;
+  double w[M][7];
+#pragma unroll
+  for (int m = 0; m < M; ++m)
+#pragma unroll
+    for (int c = 0; c < 7; ++c) w[m][c] = active ? weights[(ws * M + m) * 7 + c] : 0.0;
+  unsigned* my = cnt + threadIdx.x * 49;
+  for (int i = 0; i < 49; ++i) my[i] = 0u;
+  // frames of this CTA: contiguous slice blockIdx.y of `frame_groups`
+  const long long per = (n + frame_groups - 1) / frame_groups;
+  const long long f_begin = blockIdx.y * per;
+  const long long f_end = f_begin + per < n ? f_begin + per : n;
+  for (long long t0 = f_begin; t0 < f_end; t0 += WS_FRAMES) {
+    const int nf = (int)((f_end - t0) < WS_FRAMES ? (f_end - t0) : WS_FRAMES);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nf * M * 7; i += blockDim.x) {
+      const int f = i / (M * 7), r = i % (M * 7);
+      const int m = r / 7, c = r % 7;
+      sp[i] = preds[((long long)m * n + t0 + f) * 7 + c];
+    }
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) sgt[i] = gt[t0 + i];
+    __syncthreads();
+    if (active) {
+      for (int f = 0; f < nf; ++f) {
+        const double* pf = sp + f * M * 7;
+        double best = 0.0;
+        int bi = 0;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+          double v = __dmul_rn(pf[c], w[0][c]);
+#pragma unroll
+          for (int m = 1; m < M; ++m) v = __dadd_rn(v, __dmul_rn(pf[m * 7 + c], w[m][c]));
+          if (c == 0) { best = v; bi = 0; }
+          else if (v > best || (v != v && best == best)) { best = v; bi = c; }
+        }
+        const int g = sgt[f];
+        if (g >= 0 && g < 7) my[g * 7 + bi] += 1u;
+      }
+    }
+  }
+  (void)lane; (void)warp;
+  if (active)
+    for (int i = 0; i < 49; ++i)
+      if (my[i]) atomicAdd(cm + ws * 49 + i, (unsigned long long)my[i]);
+}
+
 }  // namespace avcer
 
 using namespace avcer;
@@ -389,4 +457,29 @@ extern "C" int avcer_compound_scores(const void* pred, int64_t n, int ncols, int
   if (pred_f64) compound_scores_kernel<double><<<g, 256, 0, as_stream(stream)>>>((const double*)pred, n, ncols, t, ce_mask, out);
   else compound_scores_kernel<float><<<g, 256, 0, as_stream(stream)>>>((const float*)pred, n, ncols, t, ce_mask, out);
   return check_launch("compound_scores_kernel");
+}
+
+extern "C" int avcer_weight_search_confusion(const double* preds, int n_models, int64_t n, const int32_t* gt,
+                                             const double* weights, int64_t n_weights, uint64_t* cm, void* stream) {
+  AVCER_REQUIRE(n_models == 2 || n_models == 3, "weight_search: 2 or 3 prediction streams");
+  AVCER_REQUIRE(n >= 0 && n_weights >= 0, "weight_search: bad sizes");
+  if (n == 0 || n_weights == 0) return 0;
+  const int wblocks = (int)((n_weights + WS_WARPS * 32 - 1) / (WS_WARPS * 32));
+  long long tiles = (n + WS_FRAMES - 1) / WS_FRAMES;
+  int fg = (int)(tiles < 1 ? 1 : tiles);
+  const int want = (148 * 2 + wblocks - 1) / wblocks;          // enough CTAs to fill the GPU twice
+  if (fg > want) fg = want;
+  if (fg > 65535) fg = 65535;
+  const size_t smem = (size_t)WS_FRAMES * n_models * 7 * sizeof(double) + WS_FRAMES * sizeof(int) +
+                      (size_t)WS_WARPS * 32 * 49 * sizeof(unsigned);
+  dim3 grid(wblocks, fg);
+  cudaStream_t st = as_stream(stream);
+  if (n_models == 3) {
+    AVCER_CUDA(cudaFuncSetAttribute(weight_search_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    weight_search_kernel<3><<<grid, WS_WARPS * 32, smem, st>>>(preds, n, gt, weights, n_weights, fg, (unsigned long long*)cm);
+  } else {
+    AVCER_CUDA(cudaFuncSetAttribute(weight_search_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    weight_search_kernel<2><<<grid, WS_WARPS * 32, smem, st>>>(preds, n, gt, weights, n_weights, fg, (unsigned long long*)cm);
+  }
+  return check_launch("weight_search_kernel");
 }

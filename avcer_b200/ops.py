@@ -17,7 +17,7 @@ from ._lib import check as _check
 
 __all__ = [
     "F32", "BF16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "dtype_code", "torch_dtype", "contract", "conv2d_nhwc",
-    "linear", "preprocess", "fuse_compound", "softmax7", "window_to_frame_mean", "gather_rows", "maxpool3x3s2",
+    "linear", "preprocess", "fuse_compound", "weight_search_confusion", "softmax7", "window_to_frame_mean", "gather_rows", "maxpool3x3s2",
     "avgpool", "small_linear", "lstm_cell", "audio_normalize_windows", "w2v_conv0_ln_gelu", "layernorm", "add_rows",
     "attention", "maxpool1d5_relu", "avgpool1d_relu", "cast",
 ]
@@ -207,6 +207,21 @@ def fuse_compound(p_vs: torch.Tensor, p_vd: torch.Tensor, p_a: torch.Tensor, wei
         _check(fn(p_vs.data_ptr(), p_vd.data_ptr(), p_a.data_ptr(), n, w1, w2, int(bool(ce_weights_type)),
                  int(bool(ce_mask)), labels.data_ptr(), _stream()))
     return labels
+
+
+def weight_search_confusion(preds: torch.Tensor, gt: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+    """preds [M, n, 7] f64, gt [n] int32, weights [W, M, 7] f64 (all CUDA) -> confusion counts [W, 7, 7] int64
+    (rows = ground truth, columns = fused argmax) for every candidate weight set."""
+    _cuda(preds, "preds")
+    m, n, c = preds.shape
+    w = weights.shape[0]
+    assert c == 7 and weights.shape == (w, m, 7) and gt.shape == (n,)
+    assert preds.dtype == torch.float64 and weights.dtype == torch.float64 and gt.dtype == torch.int32
+    assert preds.is_contiguous() and weights.is_contiguous() and gt.is_contiguous()
+    cm = torch.zeros((w, 7, 7), device=preds.device, dtype=torch.int64)
+    check(_lib.load().avcer_weight_search_confusion(preds.data_ptr(), m, n, gt.data_ptr(), weights.data_ptr(), w,
+                                                    cm.data_ptr(), _stream()))
+    return cm
 
 
 def softmax7(x: torch.Tensor) -> torch.Tensor:

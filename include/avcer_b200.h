@@ -125,6 +125,14 @@ int avcer_compound_scores(const void* pred, int64_t n, int ncols, int pred_f64,
                           const int32_t* pairs_host, const double* w_host, int k, int ce_mask,
                           double* out, void* stream);
 
+/* Weight search (data/utils.py:138-209: get_weights_prob_model / get_weights_v_model / get_weights_av_model).
+ * For each of n_weights candidate weight sets weights[w][m][c] the fused prediction
+ * argmax_c sum_m preds[m][f][c] * weights[w][m][c] (binary64, left to right, first maximum) is compared with
+ * gt[f]; cm[w][gt][pred] (7x7, caller-zeroed, uint64) receives the confusion counts from which the host
+ * derives sklearn's precision / recall / F1 exactly.  preds: [n_models][n][7] f64, n_models 2 or 3. */
+int avcer_weight_search_confusion(const double* preds, int n_models, int64_t n, const int32_t* gt,
+                                  const double* weights, int64_t n_weights, uint64_t* cm, void* stream);
+
 /* Row softmax over 7 classes in fp32, exactly data/utils.py:125-127 (max-subtract, exp, sum, div).
  * `ld` = row pitch of the input in floats (8 for the 8-class audio logits: "Other" is dropped
  * before the softmax, run.py:96). */

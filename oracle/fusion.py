@@ -99,3 +99,42 @@ def get_c_expr_db_pred(stat_df, dyn_df, audio_df, name_video, weights_1, weights
     p_vs, p_vd, p_a, loc = align_streams(stat_df.copy(), dyn_df.copy(), audio_df.copy(), name_video)
     av, vs, vd, a = fuse_labels(p_vs, p_vd, p_a, weights_1, weights_2, ce_weights_type, ce_mask)
     return av, vs, vd, a, loc
+
+
+# ------------------------------------------------------------------------------------------------ weight search
+def metrics_for_fusion(true, pred):
+    """utils.py:115-122: precision, f1 and recall (UAR) averaged over classes 1..6 of sklearn's report."""
+    from sklearn.metrics import classification_report
+
+    rep = classification_report(true, pred, output_dict=True, zero_division=0)
+    acc = np.zeros(3)
+    for cl in range(1, 7):
+        for j, key in enumerate(["precision", "f1-score", "recall"]):
+            acc[j] += rep[str(cl)][key]
+    return tuple(acc / 6)
+
+
+def search_prob_weights(ground_truth, predictions, weights):
+    """utils.py:145-158 for given candidate weights [W, M, C]: (best metric, index of the first strict best)."""
+    best, best_idx = 0, None
+    for w in range(len(weights)):
+        final = np.asarray(predictions[0]) * weights[w, 0]
+        for m in range(1, len(predictions)):
+            final += np.asarray(predictions[m]) * weights[w, m]
+        metric = metrics_for_fusion(ground_truth, np.argmax(final, axis=-1))[2]
+        if metric > best:
+            best, best_idx = metric, w
+    return best, best_idx
+
+
+def search_av_weights(grid, ground_truth, predictions):
+    """utils.py:188-209: triple loop over scalar model weights."""
+    p1, p2, p3 = (np.array(p) for p in predictions[:3])
+    best_w, best = [0, 0, 0], 0
+    for ws in grid:
+        for wd in grid:
+            for wa in grid:
+                acc = metrics_for_fusion(ground_truth, np.argmax(ws * p1 + wd * p2 + wa * p3, axis=1))[2]
+                if acc > best:
+                    best, best_w = acc, [ws, wd, wa]
+    return best, best_w

@@ -228,6 +228,44 @@ def make_audio():
     print("audio.npz")
 
 
+def weight_search_inputs(seed=0, n=600):
+    rng = np.random.default_rng(seed)
+    gt = rng.integers(0, 7, n)
+    preds = [rng.dirichlet(np.ones(7) * 0.5, size=n) for _ in range(3)]
+    for k in range(3):
+        preds[k][np.arange(n), gt] += 0.4 * (k + 1) / 3        # informative but imperfect streams
+    return gt, preds
+
+
+def make_weight_search():
+    import contextlib
+    import io
+
+    from data.utils import get_weights_av_model as ref_av
+    from data.utils import get_weights_prob_model as ref_prob
+    from data.utils import get_weights_v_model as ref_v
+
+    gt, preds = weight_search_inputs()
+    preds_l = [p.tolist() for p in preds]
+    np.random.seed(42)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        bw = ref_prob(gt.tolist(), preds_l, 60, 7)
+    np.random.seed(42)
+    W = np.zeros((60, 3, 7))
+    for i in range(60):
+        W[i] = np.random.dirichlet(alpha=np.ones((3,)), size=7).T
+    best, idx = of.search_prob_weights(gt.tolist(), preds_l, W)
+    assert np.array_equal(W[idx], bw)
+    grid = [0.1, 0.4, 0.7, 1.0]
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        aw = ref_av(grid, gt.tolist(), preds_l)
+        vw = ref_v(grid, gt.tolist(), preds_l[:2])
+    assert of.search_av_weights(grid, gt.tolist(), preds_l)[1] == aw
+    np.savez_compressed(os.path.join(OUT, "weight_search.npz"), prob_best=bw, prob_idx=np.int64(idx), av_best=np.asarray(aw),
+                        v_best=np.asarray(vw), grid=np.asarray(grid))
+    print("weight_search.npz")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -235,6 +273,7 @@ def main():
         # run.py imports get_prob_video, which loads the (CWD-relative) weight files at import time
         harness.save_video_weights(wd, syn.make_vs_state_dict(0, "spread"), syn.make_vd_state_dict(1))
         make_fusion()
+        make_weight_search()
         make_preprocess()
         make_video(wd)
         make_audio()

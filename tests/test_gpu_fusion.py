@@ -131,3 +131,35 @@ def test_data_utils_dropins(cuda_lib, golden):
     assert du.get_image_location("v", "000012.jpg") == "v/00013.jpg"
     with pytest.raises(ZeroDivisionError):
         du.pad_wav(torch.zeros(0), 10)
+
+
+def test_weight_search_dropins_match_reference(cuda_lib, golden):
+    """the Dirichlet / grid weight searches of data/utils.py:138-209, every candidate
+    evaluated in one launch; selected weights identical to the stock functions (golden) and per-candidate
+    confusion matrices identical to a numpy evaluation."""
+    from avcer_b200 import ops
+    from avcer_b200.data import utils as du
+    from oracle.make_golden import weight_search_inputs
+
+    g = golden["weight_search"]
+    gt, preds = weight_search_inputs()
+    preds_l = [p.tolist() for p in preds]
+    np.random.seed(42)
+    bw = du.get_weights_prob_model(gt.tolist(), preds_l, 60, 7)
+    assert np.array_equal(bw, g["prob_best"])
+    grid = g["grid"].tolist()
+    assert du.get_weights_av_model(grid, gt.tolist(), preds_l) == g["av_best"].tolist()
+    assert du.get_weights_v_model(grid, gt.tolist(), preds_l[:2]) == g["v_best"].tolist()
+    # confusion counts of 300 random candidates against numpy, incl. a ragged frame count
+    rng = np.random.default_rng(5)
+    W = rng.dirichlet(np.ones(3), size=(300, 7)).transpose(0, 2, 1).copy()
+    P = np.stack(preds)[:, :577]
+    cm = ops.weight_search_confusion(_t(P), _t(gt[:577].astype(np.int32)), _t(W)).cpu().numpy()
+    for w in (0, 17, 299):
+        final = P[0] * W[w, 0]
+        final += P[1] * W[w, 1]
+        final += P[2] * W[w, 2]
+        ref = np.zeros((7, 7), dtype=np.int64)
+        np.add.at(ref, (gt[:577], np.argmax(final, axis=-1)), 1)
+        assert np.array_equal(cm[w], ref)
+    assert cm.sum() == 300 * 577

@@ -2,6 +2,7 @@
 // kernel ("fp32 mode"), both driven by the same avcer_contract_desc geometry.
 #include "common.h"
 #include "tc_gemm.cuh"
+#include "tc_gemm2.cuh"
 
 #include <cudaTypedefs.h>
 #include <mutex>
@@ -79,6 +80,24 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   return check_launch("tc_gemm_kernel");
 }
 
+template <int MODE>
+static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
+                      const TcGemmParams& p, int sms, cudaStream_t st) {
+  using Cfg = TcGemm2Cfg<MODE>;
+  auto kern = tc_gemm2_kernel<MODE>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AVCER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_done = true;
+  }
+  const int m_tiles = p.tw * p.th * p.tn;
+  const int pair_tiles = ((m_tiles + 1) / 2) * p.tiles_n;
+  int clusters = sms / 2;
+  if (clusters > pair_tiles) clusters = pair_tiles;
+  kern<<<2 * clusters, Cfg::THREADS, Cfg::SMEM, st>>>(ta, tb, tc, tr, p);     // __cluster_dims__(2,1,1)
+  return check_launch("tc_gemm2_kernel");
+}
+
 static int num_sms_cached() {
   static int n = 0;
   if (n == 0) {
@@ -111,6 +130,8 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
     if (waves256 * 2.0 / 1.4 < (double)waves128) BN = 256;
   }
   if (getenv("AVCER_NO_BN256") && BN == 256) BN = 128;
+  static const int cta2_env = getenv("AVCER_CTA2") ? atoi(getenv("AVCER_CTA2")) : 1;
+  const bool use_cta2 = cta2_env != 0 && BN == 256 && !d->a_strip && d->group_cin_shift == 0 && !d->out_f32;
 
   TcGemmParams p{};
   if (d->a_strip) {
@@ -168,7 +189,7 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
     uint64_t dims[2] = {ktot, (uint64_t)d->cout};
     uint64_t strides[1] = {ktot * 2};
     AVCER_REQUIRE((ktot * 2) % 16 == 0, "contract: weight row pitch must be a multiple of 16 bytes");
-    uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)(use_cta2 ? 128 : BN)};   // two-SM tiles: each CTA stages half of the 256 weight rows
     if (encode_map(&tb, d->wt, 2, dims, strides, box, swz)) return 1;
   }
   // output / residual maps: (cout, w, h, n) boxes of the same shape as the activation box
@@ -195,6 +216,10 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
     }
   }
   const int grid = num_sms_cached();
+  if (use_cta2) {
+    if (mode == OUT_TMA) return launch_tc2<OUT_TMA>(ta, tb, tc, tr, p, grid, st);
+    return launch_tc2<OUT_TMA_RES>(ta, tb, tc, tr, p, grid, st);
+  }
   // K chunks per pipeline stage: small tiles (little MMA work per chunk) batch several chunks per barrier
 #define AVCER_TC_CASE(bn, bk, occ)                                                                         \
   if (BN == bn && BK == bk) {                                                                              \

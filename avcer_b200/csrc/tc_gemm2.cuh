@@ -1,0 +1,327 @@
+// Two-SM (cta_group::2) flavour of the tcgen05 implicit-GEMM kernel: a cluster of two CTAs on one TPC
+// computes a 256 x 256 output tile with UMMA M = 256.  Each CTA stages its own 128 activation rows and
+// HALF of the 256-row weight tile, so the shared-memory operand traffic per MMA is 64 B/clk per SM instead
+// of 96 (128x256 single-CTA) or 128 (128x128) -- the limiter of the single-CTA tiles.
+//
+// Protocol (leader = cluster rank 0):
+//   * both CTAs' TMA producers load into their own shared memory but complete their bytes on the LEADER's
+//     `full` barrier (cta_group::2 TMA, barrier address with the peer bit cleared);
+//   * the leader's MMA thread issues tcgen05.mma.cta_group::2 (A rows 0-127 / B half 0 from CTA 0,
+//     rows 128-255 / half 1 from CTA 1; accumulator rows land in each CTA's own TMEM) and multicasts its
+//     commits to the `empty` / `tfull` barriers of both CTAs;
+//   * each CTA runs its own epilogue on its 128 rows (same ring-staged TMA-store epilogue as tc_gemm.cuh);
+//     all epilogue warps of both CTAs release the accumulator on the leader's `tempty` barrier.
+// Geometry (boxes, taps, padding by TMA zero fill, persistent scheduling) is identical to tc_gemm.cuh.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace avcer {
+
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even CTA of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                                int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrive on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // arrive on the leader CTA's barrier at this offset
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int MODE>
+struct TcGemm2Cfg {
+  static constexpr int BN = 256;                 // N of the pair tile (each CTA stages 128 weight rows)
+  static constexpr int BK = 64;
+  static constexpr int A_STAGE = 128 * BK * 2;   // own 128 activation rows
+  static constexpr int B_STAGE = 128 * BK * 2;   // own half of the weight tile
+  static constexpr int STAGE = A_STAGE + B_STAGE;
+  static constexpr int HALF = 128 * 128;
+  static constexpr int C_SLOTS = 2;
+  static constexpr int R_SLOTS = (MODE == OUT_TMA_RES) ? 2 : 0;
+  static constexpr int BUDGET = 224 * 1024;
+  static constexpr int FIT = (BUDGET - (C_SLOTS + R_SLOTS) * HALF) / STAGE;
+  static constexpr int STAGES = FIT > 8 ? 8 : FIT;
+  static constexpr int SMEM = STAGES * STAGE + (C_SLOTS + R_SLOTS) * HALF + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int HALVES = BN / 64;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+};
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                const TcGemmParams p) {
+  using Cfg = TcGemm2Cfg<MODE>;
+  constexpr int BN = Cfg::BN, BK = Cfg::BK;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 8];
+  __shared__ uint32_t tmem_slot_s;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + Cfg::STAGES * Cfg::A_STAGE;
+  const uint32_t c_base = smem_base + Cfg::STAGES * Cfg::STAGE;
+  const uint32_t r_base = c_base + Cfg::C_SLOTS * Cfg::HALF;
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
+  auto rfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + a); };
+  auto rfree_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 6 + a); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int rows = p.bw * p.bh * p.bn;
+  const int k_iters = p.taps_w * p.taps_h * p.kchunks;
+  const int m_tiles = p.tw * p.th * p.tn;
+  const int pair_tiles = ((m_tiles + 1) >> 1) * p.tiles_n;   // tiles_n counts 256-wide N tiles
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    if (MODE == OUT_TMA_RES) tma_prefetch_desc(&tmR);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);        // leader: one arrive.expect_tx covering both CTAs' bytes
+      mbar_init(empty_bar(s), 1);       // multicast commit from the leader's MMA thread
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * Cfg::EPI_WARPS);   // epilogue warps of BOTH CTAs (used on the leader only)
+      mbar_init(rfull_bar(a), 1);
+      mbar_init(rfree_bar(a), Cfg::EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(smem_u32(&tmem_slot_s), Cfg::TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                   // peer barriers are initialised before any remote arrive / multicast
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_s);
+
+  auto tile_coords = [&](int pt, int& nt, int& w0, int& h0, int& n0) {
+    nt = pt % p.tiles_n;
+    const int mt = 2 * (pt / p.tiles_n) + (int)rank;       // phantom tile when m_tiles is odd: n0 >= NB -> all out of bounds
+    w0 = (mt % p.tw) * p.bw;
+    h0 = ((mt / p.tw) % p.th) * p.bh;
+    n0 = (mt / (p.tw * p.th)) * p.bn;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_pair = 2u * (p.a_bytes + Cfg::B_STAGE);
+      for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
+        int nt, w0, h0, n0;
+        tile_coords(pt, nt, w0, h0, n0);
+        int kcol = 0;
+        for (int ty = 0; ty < p.taps_h; ++ty) {
+          for (int tx = 0; tx < p.taps_w; ++tx) {
+            for (int kc = 0; kc < p.kchunks; ++kc, kcol += BK) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), tx_pair);
+              tma_load_5d_2sm(a_base + stage * Cfg::A_STAGE, &tmA, full_bar(stage), kc * BK, w0 + p.off_w + tx,
+                              h0 + p.off_h + (p.tap_h_in_dim4 ? 0 : ty), n0, p.tap_h_in_dim4 ? ty : 0);
+              tma_load_2d_2sm(b_base + stage * Cfg::B_STAGE, &tmB, full_bar(stage), kcol, nt * BN + (int)rank * 128);
+              if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader only)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_kmajor(a_base + stage * Cfg::A_STAGE, 1024u, 2u);
+          const uint64_t bdesc = umma_desc_kmajor(b_base + stage * Cfg::B_STAGE, 1024u, 2u);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_2sm(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (it | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(empty_bar(stage));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(tfull_bar(acc));
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------ residual producer (per CTA, own rows)
+    if (MODE == OUT_TMA_RES && lane == 0) {
+      uint32_t hcount = 0;
+      for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
+        int nt, w0, h0, n0;
+        tile_coords(pt, nt, w0, h0, n0);
+        for (int hf = 0; hf < Cfg::HALVES; ++hf, ++hcount) {
+          const int slot = hcount & 1;
+          mbar_wait(rfree_bar(slot), ((hcount >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(rfull_bar(slot), static_cast<uint32_t>(rows) * 128);
+          tma_load_5d(r_base + slot * Cfg::HALF, &tmR, rfull_bar(slot), nt * BN + hf * 64, w0, h0, n0, 0);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (per CTA, own 128 rows)
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int r = q * 32 + lane;
+    const bool store_thread = (threadIdx.x == 128);
+    uint32_t hcount = 0;
+    int local = 0;
+    for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1u;
+      int nt, w0, h0, n0;
+      tile_coords(pt, nt, w0, h0, n0);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int hf = 0; hf < Cfg::HALVES; ++hf, ++hcount) {
+        const int slot = hcount & 1;
+        if (store_thread) bulk_wait_group_read<1>();
+        named_bar_sync(1, 256);
+        const uint32_t cbuf = c_base + slot * Cfg::HALF;
+        const uint32_t rbuf = r_base + slot * Cfg::HALF;
+        const uint32_t row_off = r * 128;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + acc * BN + (2 * hf + grp) * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
+        tmem_ld_wait();
+        const int co = nt * BN + (2 * hf + grp) * 32;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr && co < p.Cout) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co + j));
+            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+          }
+        }
+        auto apply_act = [&]() {
+          if (p.act == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = f[j] < 0.0f ? 0.0f : f[j];
+          } else if (p.act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
+          }
+        };
+        const int j0 = grp * 4;
+        if (MODE == OUT_TMA_RES) {
+          if (p.res_after_act) apply_act();
+          mbar_wait(rfull_bar(slot), (hcount >> 1) & 1u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            ld_shared_v4(rbuf + row_off + (((j0 + j) ^ (r & 7)) << 4), u);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 t = __bfloat1622float2(h2[e]);
+              f[j * 8 + e * 2] += t.x;
+              f[j * 8 + e * 2 + 1] += t.y;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(rfree_bar(slot));
+          if (!p.res_after_act) apply_act();
+        } else {
+          apply_act();
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
+          st_shared_v4(cbuf + row_off + (((j0 + j) ^ (r & 7)) << 4), u);
+        }
+        fence_proxy_async();
+        named_bar_sync(2, 256);
+        if (store_thread) {
+          if (nt * BN + hf * 64 < p.Cout) tma_store_5d(&tmC, cbuf, nt * BN + hf * 64, w0, h0, n0, 0);
+          bulk_commit_group();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar(acc));    // both CTAs release the accumulator on the leader
+    }
+    if (store_thread) bulk_wait_group<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                  // the peer may still multicast into / arrive on this CTA's barriers until here
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace avcer

@@ -80,11 +80,11 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   return check_launch("tc_gemm_kernel");
 }
 
-template <int MODE>
+template <int MODE, int BN>
 static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
                       const TcGemmParams& p, int sms, cudaStream_t st) {
-  using Cfg = TcGemm2Cfg<MODE>;
-  auto kern = tc_gemm2_kernel<MODE>;
+  using Cfg = TcGemm2Cfg<MODE, BN>;
+  auto kern = tc_gemm2_kernel<MODE, BN>;
   static bool attr_done = false;
   if (!attr_done) {
     AVCER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -131,7 +131,8 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   }
   if (getenv("AVCER_NO_BN256") && BN == 256) BN = 128;
   static const int cta2_env = getenv("AVCER_CTA2") ? atoi(getenv("AVCER_CTA2")) : 1;
-  const bool use_cta2 = cta2_env != 0 && BN == 256 && !d->a_strip && d->group_cin_shift == 0 && !d->out_f32;
+  const bool use_cta2 = cta2_env != 0 && (BN == 256 || (BN == 128 && cta2_env >= 2)) && BK == 64 && !d->a_strip &&
+                        d->group_cin_shift == 0 && !d->out_f32;
 
   TcGemmParams p{};
   if (d->a_strip) {
@@ -189,7 +190,7 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
     uint64_t dims[2] = {ktot, (uint64_t)d->cout};
     uint64_t strides[1] = {ktot * 2};
     AVCER_REQUIRE((ktot * 2) % 16 == 0, "contract: weight row pitch must be a multiple of 16 bytes");
-    uint32_t box[2] = {(uint32_t)BK, (uint32_t)(use_cta2 ? 128 : BN)};   // two-SM tiles: each CTA stages half of the 256 weight rows
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)(use_cta2 ? BN / 2 : BN)};   // two-SM tiles: each CTA stages half of the 256 weight rows
     if (encode_map(&tb, d->wt, 2, dims, strides, box, swz)) return 1;
   }
   // output / residual maps: (cout, w, h, n) boxes of the same shape as the activation box
@@ -217,8 +218,12 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   }
   const int grid = num_sms_cached();
   if (use_cta2) {
-    if (mode == OUT_TMA) return launch_tc2<OUT_TMA>(ta, tb, tc, tr, p, grid, st);
-    return launch_tc2<OUT_TMA_RES>(ta, tb, tc, tr, p, grid, st);
+    if (BN == 256) {
+      if (mode == OUT_TMA) return launch_tc2<OUT_TMA, 256>(ta, tb, tc, tr, p, grid, st);
+      return launch_tc2<OUT_TMA_RES, 256>(ta, tb, tc, tr, p, grid, st);
+    }
+    if (mode == OUT_TMA) return launch_tc2<OUT_TMA, 128>(ta, tb, tc, tr, p, grid, st);
+    return launch_tc2<OUT_TMA_RES, 128>(ta, tb, tc, tr, p, grid, st);
   }
   // K chunks per pipeline stage: small tiles (little MMA work per chunk) batch several chunks per barrier
 #define AVCER_TC_CASE(bn, bk, occ)                                                                         \

@@ -69,15 +69,15 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <int MODE>
+template <int MODE, int BN_>
 struct TcGemm2Cfg {
-  static constexpr int BN = 256;                 // N of the pair tile (each CTA stages 128 weight rows)
+  static constexpr int BN = BN_;                 // N of the pair tile (each CTA stages BN/2 weight rows): 256 or 128
   static constexpr int BK = 64;
   static constexpr int A_STAGE = 128 * BK * 2;   // own 128 activation rows
-  static constexpr int B_STAGE = 128 * BK * 2;   // own half of the weight tile
+  static constexpr int B_STAGE = (BN / 2) * BK * 2;   // own half of the weight tile
   static constexpr int STAGE = A_STAGE + B_STAGE;
   static constexpr int HALF = 128 * 128;
-  static constexpr int C_SLOTS = 2;
+  static constexpr int C_SLOTS = 2;              // output staging ring (a 4-slot ring measured no faster)
   static constexpr int R_SLOTS = (MODE == OUT_TMA_RES) ? 2 : 0;
   static constexpr int BUDGET = 224 * 1024;
   static constexpr int FIT = (BUDGET - (C_SLOTS + R_SLOTS) * HALF) / STAGE;
@@ -89,12 +89,12 @@ struct TcGemm2Cfg {
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
 };
 
-template <int MODE>
+template <int MODE, int BN_>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                 const TcGemmParams p) {
-  using Cfg = TcGemm2Cfg<MODE>;
+  using Cfg = TcGemm2Cfg<MODE, BN_>;
   constexpr int BN = Cfg::BN, BK = Cfg::BK;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 8];
@@ -120,7 +120,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int rows = p.bw * p.bh * p.bn;
   const int k_iters = p.taps_w * p.taps_h * p.kchunks;
   const int m_tiles = p.tw * p.th * p.tn;
-  const int pair_tiles = ((m_tiles + 1) >> 1) * p.tiles_n;   // tiles_n counts 256-wide N tiles
+  const int pair_tiles = ((m_tiles + 1) >> 1) * p.tiles_n;   // tiles_n counts BN-wide N tiles
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -176,7 +176,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), tx_pair);
               tma_load_5d_2sm(a_base + stage * Cfg::A_STAGE, &tmA, full_bar(stage), kc * BK, w0 + p.off_w + tx,
                               h0 + p.off_h + (p.tap_h_in_dim4 ? 0 : ty), n0, p.tap_h_in_dim4 ? ty : 0);
-              tma_load_2d_2sm(b_base + stage * Cfg::B_STAGE, &tmB, full_bar(stage), kcol, nt * BN + (int)rank * 128);
+              tma_load_2d_2sm(b_base + stage * Cfg::B_STAGE, &tmB, full_bar(stage), kcol, nt * BN + (int)rank * (BN / 2));
               if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
             }
           }
@@ -242,11 +242,12 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
 #pragma unroll 1
       for (int hf = 0; hf < Cfg::HALVES; ++hf, ++hcount) {
-        const int slot = hcount & 1;
-        if (store_thread) bulk_wait_group_read<1>();
+        const int slot = hcount % Cfg::C_SLOTS;
+        const int rslot = hcount & 1;
+        if (store_thread) bulk_wait_group_read<Cfg::C_SLOTS - 1>();
         named_bar_sync(1, 256);
         const uint32_t cbuf = c_base + slot * Cfg::HALF;
-        const uint32_t rbuf = r_base + slot * Cfg::HALF;
+        const uint32_t rbuf = r_base + rslot * Cfg::HALF;
         const uint32_t row_off = r * 128;
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + acc * BN + (2 * hf + grp) * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
@@ -274,7 +275,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int j0 = grp * 4;
         if (MODE == OUT_TMA_RES) {
           if (p.res_after_act) apply_act();
-          mbar_wait(rfull_bar(slot), (hcount >> 1) & 1u);
+          mbar_wait(rfull_bar(rslot), (hcount >> 1) & 1u);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
@@ -288,7 +289,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(rfree_bar(slot));
+          if (lane == 0) mbar_arrive(rfree_bar(rslot));
           if (!p.res_after_act) apply_act();
         } else {
           apply_act();

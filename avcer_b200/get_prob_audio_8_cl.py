@@ -44,7 +44,6 @@ class EmotionRecognition:
                                             self.model_params["root_path"], self.model_params["epoch"], self.device)
 
     def load_audio_features(self, path, fps):
-        from .pipeline import Engine  # noqa: F401  (kept local: only ops are needed here)
         from . import ops
 
         wav = convert_mp4_to_mp3(path, self.sr)

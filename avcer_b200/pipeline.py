@@ -89,15 +89,6 @@ def plan_audio(n_samples: int, fps: float, step: float = 0.5, window: int = 4, s
 
 
 # =========================================================================================== engine
-@dataclass
-class Clip:
-    """One clip of synthetic or decoded input, host side."""
-    frames: np.ndarray                 # uint8 [n_present, 224, 224, 3] BGR crops (only the present ones)
-    exists: np.ndarray                 # bool [N]
-    fps: float
-    wav: Optional[np.ndarray]          # float32 [L] 16 kHz mono
-
-
 class Engine:
     """Holds the three packed networks and runs clips through K1 -> VS -> VD, A, alignment and K4."""
 

@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int16, c_int32, c_int64, c_uint8, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libavcer_b200.so")
+# AVCER_LIB: alternative build of the same library (A/B measurements of kernel changes); default is the in-tree build
+LIB_PATH = os.environ.get("AVCER_LIB") or os.path.join(_HERE, "libavcer_b200.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2

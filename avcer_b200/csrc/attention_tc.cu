@@ -3,17 +3,19 @@
 // softmax(Q K^T / sqrt(d)) V of HF Wav2Vec2Attention (12 encoder layers, 16 heads x 64) and of
 // src/architectures/attention_layers.py:10-38 (tl1: 32 heads x 32, tl2: 16 heads x 64).
 //
-// One CTA per (window, head); K and V of the head are staged once in shared memory, 13 warps each
-// own 16 query rows.  The whole key axis fits on chip, so the softmax is exact two-pass (row max
-// first, then exp / sum / PV) with warp-shuffle reductions; QK^T and PV run on the tensor cores
-// (mma.sync m16n8k16, the score accumulators are re-used directly as the A operand of PV).
-// This op is ~2 % of the audio network's FLOPs; the dense projections around it are tcgen05.
+// One CTA of 7 warps per (window, head); two CTAs share an SM, so the staging of one overlaps the math of the
+// other.  K and V of the head are staged once in shared memory; every warp owns up to two 16-row query tiles.
+// The key axis is walked ONCE in two blocks of <= 112 keys whose scores stay in registers (online softmax:
+// block maximum, rescale of the running output between the blocks, exp2, row sums, PV), so QK^T is computed a
+// single time; QK^T and PV run on the tensor cores (mma.sync m16n8k16, the probabilities are re-used directly as
+// the A operand of PV).  This op is ~2 % of the audio network's FLOPs; the dense projections around it are tcgen05.
 #include "common.h"
 
 namespace avcer {
 
 constexpr int ATT_MAXT = 208;               // 13 x 16
-constexpr int ATT_WARPS = ATT_MAXT / 16;
+constexpr int ATT_WARPS = 7;                // 13 query tiles over 7 warps (two tiles per warp)
+constexpr int ATT_BLK = 7;                  // key chunks (of 16) per softmax block: 2 blocks cover 208 keys
 
 __device__ __forceinline__ uint32_t smem_u32_generic(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -35,7 +37,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 
 template <int DH>
-__global__ void __launch_bounds__(ATT_WARPS * 32, 1)
+__global__ void __launch_bounds__(ATT_WARPS * 32, 2)
 attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, int t, int heads, float scale_log2e,
                     __nv_bfloat16* __restrict__ out) {
   constexpr int PITCH = DH + 8;                       // +16 B per row: conflict-free ldmatrix
@@ -50,6 +52,8 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, int t, int heads, flo
   const long long row_stride = 3ll * heads * DH;
   const __nv_bfloat16* base = qkv + (long long)b * t * row_stride + (long long)head * DH;
 
+  pdl_wait();
+  pdl_launch_dependents();
   // stage Q, K, V rows (16 B vectors), zero-fill the padded rows
   constexpr int VEC = DH / 8;
   for (int i = tid; i < ATT_MAXT * VEC * 3; i += blockDim.x) {
@@ -63,90 +67,102 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, int t, int heads, flo
   }
   __syncthreads();
 
-  const int q0 = warp * 16;
-  if (q0 >= t) return;
   const int g = lane >> 2, tq = lane & 3;
-  // Q fragments of this warp's 16 rows
-  uint32_t qf[KS][4];
-#pragma unroll
-  for (int ks = 0; ks < KS; ++ks) {
-    const int r = q0 + (lane & 7) + 8 * ((lane >> 3) & 1);
-    const int c = ks * 16 + 8 * (lane >> 4);
-    ldsm_x4(smem_u32_generic(sq + r * PITCH + c), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
-  }
   const int n_chunks = (t + 15) / 16;
+  __nv_bfloat16* ob = out + (long long)b * t * heads * DH + (long long)head * DH;
 
-  auto scores = [&](int ch, float (&s0)[4], float (&s1)[4]) {
-    // S[16 x 16 keys] for key chunk ch: two n-tiles (keys 16ch..+7 and +8..+15)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
+  for (int q0 = warp * 16; q0 < t; q0 += ATT_WARPS * 16) {
+    // Q fragments of this warp's 16 rows
+    uint32_t qf[KS][4];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
-      uint32_t b0, b1, b2, b3;
-      const int key = ch * 16 + (lane & 7) + 8 * (lane >> 4);
-      const int d = ks * 16 + 8 * ((lane >> 3) & 1);
-      ldsm_x4(smem_u32_generic(sk + key * PITCH + d), b0, b1, b2, b3);
-      mma_bf16(s0, qf[ks], b0, b1);
-      mma_bf16(s1, qf[ks], b2, b3);
+      const int r = q0 + (lane & 7) + 8 * ((lane >> 3) & 1);
+      const int c = ks * 16 + 8 * (lane >> 4);
+      ldsm_x4(smem_u32_generic(sq + r * PITCH + c), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
     }
-    // mask keys >= t
-    const int k0 = ch * 16 + 2 * tq;
-    if (k0 >= t) { s0[0] = -INFINITY; s0[2] = -INFINITY; }
-    if (k0 + 1 >= t) { s0[1] = -INFINITY; s0[3] = -INFINITY; }
-    if (k0 + 8 >= t) { s1[0] = -INFINITY; s1[2] = -INFINITY; }
-    if (k0 + 9 >= t) { s1[1] = -INFINITY; s1[3] = -INFINITY; }
-  };
+    float o[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[n][i] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;     // rows g and g+8 of the warp tile
 
-  // pass 1: row maxima (rows g and g+8 of the warp tile)
-  float m0 = -INFINITY, m1 = -INFINITY;
-  for (int ch = 0; ch < n_chunks; ++ch) {
-    float s0[4], s1[4];
-    scores(ch, s0, s1);
-    m0 = fmaxf(m0, fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1])));
-    m1 = fmaxf(m1, fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3])));
-  }
-  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-  const float mb0 = m0 * scale_log2e, mb1 = m1 * scale_log2e;
-
-  // pass 2: p = exp(scale * (s - max)), row sums, O += P V
-  float o[NT][4];
+#pragma unroll 1
+    for (int c0 = 0; c0 < n_chunks; c0 += ATT_BLK) {
+      // scores of up to ATT_BLK key chunks: s[c][0..3] = keys 16ch..+7, s[c][4..7] = keys +8..+15
+      float s[ATT_BLK][8];
+      float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
-  for (int n = 0; n < NT; ++n)
+      for (int c = 0; c < ATT_BLK; ++c) {
+        const int ch = c0 + c;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) o[n][i] = 0.f;
-  float l0 = 0.f, l1 = 0.f;
-  for (int ch = 0; ch < n_chunks; ++ch) {
-    float s0[4], s1[4];
-    scores(ch, s0, s1);
-    float p[8];
-    p[0] = exp2f(s0[0] * scale_log2e - mb0); p[1] = exp2f(s0[1] * scale_log2e - mb0);
-    p[2] = exp2f(s0[2] * scale_log2e - mb1); p[3] = exp2f(s0[3] * scale_log2e - mb1);
-    p[4] = exp2f(s1[0] * scale_log2e - mb0); p[5] = exp2f(s1[1] * scale_log2e - mb0);
-    p[6] = exp2f(s1[2] * scale_log2e - mb1); p[7] = exp2f(s1[3] * scale_log2e - mb1);
-    l0 += p[0] + p[1] + p[4] + p[5];
-    l1 += p[2] + p[3] + p[6] + p[7];
-    uint32_t pa[4] = {pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7])};
+        for (int i = 0; i < 8; ++i) s[c][i] = (ch < n_chunks) ? 0.f : -INFINITY;
+        if (ch < n_chunks) {
 #pragma unroll
-    for (int n2 = 0; n2 < NT / 2; ++n2) {
-      uint32_t v0, v1, v2, v3;
-      const int key = ch * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
-      const int d = n2 * 16 + 8 * (lane >> 4);
-      ldsm_x4_t(smem_u32_generic(sv + key * PITCH + d), v0, v1, v2, v3);
-      mma_bf16(o[2 * n2], pa, v0, v1);
-      mma_bf16(o[2 * n2 + 1], pa, v2, v3);
+          for (int ks = 0; ks < KS; ++ks) {
+            uint32_t b0, b1, b2, b3;
+            const int key = ch * 16 + (lane & 7) + 8 * (lane >> 4);
+            const int d = ks * 16 + 8 * ((lane >> 3) & 1);
+            ldsm_x4(smem_u32_generic(sk + key * PITCH + d), b0, b1, b2, b3);
+            mma_bf16(*reinterpret_cast<float(*)[4]>(&s[c][0]), qf[ks], b0, b1);
+            mma_bf16(*reinterpret_cast<float(*)[4]>(&s[c][4]), qf[ks], b2, b3);
+          }
+          // mask keys >= t
+          const int k0 = ch * 16 + 2 * tq;
+          if (k0 >= t) { s[c][0] = -INFINITY; s[c][2] = -INFINITY; }
+          if (k0 + 1 >= t) { s[c][1] = -INFINITY; s[c][3] = -INFINITY; }
+          if (k0 + 8 >= t) { s[c][4] = -INFINITY; s[c][6] = -INFINITY; }
+          if (k0 + 9 >= t) { s[c][5] = -INFINITY; s[c][7] = -INFINITY; }
+          bm0 = fmaxf(bm0, fmaxf(fmaxf(s[c][0], s[c][1]), fmaxf(s[c][4], s[c][5])));
+          bm1 = fmaxf(bm1, fmaxf(fmaxf(s[c][2], s[c][3]), fmaxf(s[c][6], s[c][7])));
+        }
+      }
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+      // online softmax: every chunk of a block starts below t, so the block maximum is finite
+      const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);
+      if (c0 > 0) {
+        const float a0 = exp2f((m0 - n0) * scale_log2e), a1 = exp2f((m1 - n1) * scale_log2e);
+        l0 *= a0; l1 *= a1;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) { o[n][0] *= a0; o[n][1] *= a0; o[n][2] *= a1; o[n][3] *= a1; }
+      }
+      m0 = n0; m1 = n1;
+      const float mb0 = m0 * scale_log2e, mb1 = m1 * scale_log2e;
+#pragma unroll
+      for (int c = 0; c < ATT_BLK; ++c) {
+        const int ch = c0 + c;
+        if (ch < n_chunks) {
+          float p[8];
+          p[0] = exp2f(s[c][0] * scale_log2e - mb0); p[1] = exp2f(s[c][1] * scale_log2e - mb0);
+          p[2] = exp2f(s[c][2] * scale_log2e - mb1); p[3] = exp2f(s[c][3] * scale_log2e - mb1);
+          p[4] = exp2f(s[c][4] * scale_log2e - mb0); p[5] = exp2f(s[c][5] * scale_log2e - mb0);
+          p[6] = exp2f(s[c][6] * scale_log2e - mb1); p[7] = exp2f(s[c][7] * scale_log2e - mb1);
+          l0 += p[0] + p[1] + p[4] + p[5];
+          l1 += p[2] + p[3] + p[6] + p[7];
+          uint32_t pa[4] = {pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7])};
+#pragma unroll
+          for (int n2 = 0; n2 < NT / 2; ++n2) {
+            uint32_t v0, v1, v2, v3;
+            const int key = ch * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+            const int d = n2 * 16 + 8 * (lane >> 4);
+            ldsm_x4_t(smem_u32_generic(sv + key * PITCH + d), v0, v1, v2, v3);
+            mma_bf16(o[2 * n2], pa, v0, v1);
+            mma_bf16(o[2 * n2 + 1], pa, v2, v3);
+          }
+        }
+      }
     }
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-  const int r0 = q0 + g, r1 = q0 + g + 8;
-  __nv_bfloat16* ob = out + (long long)b * t * heads * DH + (long long)head * DH;
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    const int r0 = q0 + g, r1 = q0 + g + 8;
 #pragma unroll
-  for (int n = 0; n < NT; ++n) {
-    const int c = n * 8 + 2 * tq;
-    if (r0 < t) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * heads * DH + c) = pack_bf16(o[n][0] * i0, o[n][1] * i0);
-    if (r1 < t) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * heads * DH + c) = pack_bf16(o[n][2] * i1, o[n][3] * i1);
+    for (int n = 0; n < NT; ++n) {
+      const int c = n * 8 + 2 * tq;
+      if (r0 < t) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * heads * DH + c) = pack_bf16(o[n][0] * i0, o[n][1] * i0);
+      if (r1 < t) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * heads * DH + c) = pack_bf16(o[n][2] * i1, o[n][3] * i1);
+    }
   }
 }
 
@@ -161,8 +177,8 @@ static int launch_attention_tc(const void* qkv, int n, int t, int heads, float s
     attr_done = true;
   }
   dim3 grid(heads, n);
-  kern<<<grid, ATT_WARPS * 32, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv), t, heads,
-                                            scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(out));
+  launch_pdl(kern, grid, ATT_WARPS * 32, smem, st, static_cast<const __nv_bfloat16*>(qkv), t, heads,
+             scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(out));
   return check_launch("attention_tc_kernel");
 }
 

@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/avcer_b200.h"
 
@@ -30,6 +31,47 @@ inline int check_launch(const char* what) {
   } while (0)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// SM count of the current device (cached; 148 on B200): persistent kernels size their grids with it.
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// Programmatic dependent launch (PDL).  Hot-path kernels are launched with the programmatic-stream-serialization
+// attribute: the next kernel's CTAs may become resident and run their prologue (barrier init, TMEM allocation,
+// descriptor prefetch, constant staging) while the previous kernel drains, and block in pdl_wait() until that kernel
+// has completed and flushed its writes.  Every kernel launched through launch_pdl() must call pdl_wait() before its
+// first access to memory another kernel may have written, and before its own first global write.  Works inside CUDA
+// graph capture (programmatic edges).  AVCER_PDL=0 launches the same kernels fully serialised.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static const int on = getenv("AVCER_PDL") ? atoi(getenv("AVCER_PDL")) : 1;
+  return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // Storage-type helpers for kernels templated on float / __nv_bfloat16.
 __device__ __forceinline__ float to_f32(float v) { return v; }

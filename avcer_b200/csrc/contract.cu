@@ -3,6 +3,7 @@
 #include "common.h"
 #include "tc_gemm.cuh"
 #include "tc_gemm2.cuh"
+#include "conv3x3.cuh"
 
 #include <cudaTypedefs.h>
 #include <mutex>
@@ -76,15 +77,15 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   }
   int g = grid * OCC;                     // persistent: OCC CTAs per SM
   if (g > p.num_tiles) g = p.num_tiles;
-  kern<<<g, Cfg::THREADS, Cfg::SMEM, st>>>(ta, tb, tc, tr, p);
+  launch_pdl(kern, g, Cfg::THREADS, Cfg::SMEM, st, ta, tb, tc, tr, p);
   return check_launch("tc_gemm_kernel");
 }
 
-template <int MODE, int BN>
+template <int MODE, int BN, int RS = 4, int FLAT = 0>
 static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
                       const TcGemmParams& p, int sms, cudaStream_t st) {
-  using Cfg = TcGemm2Cfg<MODE, BN>;
-  auto kern = tc_gemm2_kernel<MODE, BN>;
+  using Cfg = TcGemm2Cfg<MODE, BN, RS, FLAT>;
+  auto kern = tc_gemm2_kernel<MODE, BN, RS, FLAT>;
   static bool attr_done = false;
   if (!attr_done) {
     AVCER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -94,8 +95,22 @@ static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   const int pair_tiles = ((m_tiles + 1) / 2) * p.tiles_n;
   int clusters = sms / 2;
   if (clusters > pair_tiles) clusters = pair_tiles;
-  kern<<<2 * clusters, Cfg::THREADS, Cfg::SMEM, st>>>(ta, tb, tc, tr, p);     // __cluster_dims__(2,1,1)
+  launch_pdl(kern, 2 * clusters, Cfg::THREADS, Cfg::SMEM, st, ta, tb, tc, tr, p);     // __cluster_dims__(2,1,1)
   return check_launch("tc_gemm2_kernel");
+}
+
+// Development aid (not part of the public header): device buffer of kTraceCtas*kTraceTiles*kTraceSlots u64 that the
+// two-SM kernel fills with per-tile clock64 stamps of its first CTAs; nullptr (default) disables tracing.
+static unsigned long long* g_trace = nullptr;
+extern "C" int avcer_debug_set_trace(void* buf) {
+  g_trace = static_cast<unsigned long long*>(buf);
+  return 0;
+}
+
+static int g_debug = 0;
+extern "C" int avcer_debug_set_flags(int flags) {
+  g_debug = flags;
+  return 0;
 }
 
 static int num_sms_cached() {
@@ -109,7 +124,78 @@ static int num_sms_cached() {
   return n;
 }
 
+// 3x3 "same" stride-1 convolutions with 64 / 128 output channels over dense NHWC tensors (ResNet-50 layer1 / layer2
+// conv2): halo-in-shared-memory kernel of conv3x3.cuh.  Returns -1 when the geometry is not its case.
+template <int BN, bool RES>
+static int launch_conv3(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, Conv3Params& p, cudaStream_t st) {
+  using Cfg = Conv3Cfg<BN, RES>;
+  auto kern = conv3x3_kernel<BN, RES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AVCER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BUDGET));
+    attr_done = true;
+  }
+  p.a_stages = (Cfg::BUDGET - 1024 - Cfg::B_BYTES - Cfg::C_BYTES) / (int)p.a_stage;
+  if (p.a_stages > Cfg::MAX_A_STAGES) p.a_stages = Cfg::MAX_A_STAGES;
+  AVCER_REQUIRE(p.a_stages >= 2, "conv3x3: activation stage of %u bytes does not fit twice", p.a_stage);
+  const size_t smem = (size_t)p.a_stages * p.a_stage + Cfg::B_BYTES + Cfg::C_BYTES + 1024;
+  int g = num_sms();
+  if (g > p.num_tiles) g = p.num_tiles;
+  launch_pdl(kern, g, Cfg::THREADS, smem, st, ta, tb, tc, p);
+  return check_launch("conv3x3_kernel");
+}
+
+static int conv3x3_tc(const avcer_contract_desc* d, cudaStream_t st) {
+  static const int on = getenv("AVCER_CONV3") ? atoi(getenv("AVCER_CONV3")) : 1;
+  const int C = d->cin, W = d->W, H = d->H, NB = d->NB, Cout = d->cout;
+  const bool shape = on != 0 && d->taps_w == 3 && d->taps_h == 3 && d->off_w == -1 && d->off_h == -1 && !d->tap_h_in_dim4 &&
+                     d->group_cin_shift == 0 && !d->a_strip && !d->out_f32 && d->residual == nullptr && C % 64 == 0 &&
+                     ((Cout == 64 && C == 64) || Cout == 128) && W + 2 >= 28 && W + 2 <= 63 && NB >= 1 &&
+                     (d->act == ACT_NONE || d->act == ACT_RELU);
+  const bool dense = d->a_dim[0] == C && d->a_dim[1] == W && d->a_dim[2] == H && d->a_dim[3] == NB && d->a_stride[0] == 1 &&
+                     d->a_stride[1] == C && d->a_stride[2] == (int64_t)W * C && d->a_stride[3] == (int64_t)H * W * C &&
+                     d->out_stride[0] == Cout && d->out_stride[1] == (int64_t)W * Cout && d->out_stride[2] == (int64_t)H * W * Cout;
+  if (!shape || !dense) return -1;
+  Conv3Params p{};
+  p.H = H; p.W = W; p.NB = NB; p.C = C; p.Cout = Cout;
+  p.P = W + 2;
+  p.bh = 256 / p.P;
+  if (p.bh > H) p.bh = H;
+  p.tiles_h = (H + p.bh - 1) / p.bh;
+  p.num_tiles = NB * p.tiles_h;
+  p.kchunks = C / 64;
+  p.a_bytes = (unsigned)((p.bh + 2) * p.P) * 128u;
+  p.a_stage = (unsigned)(((2 * p.P + 2 + 256) * 128 + 1023) / 1024 * 1024);
+  p.bias = d->bias;
+  p.act = d->act;
+  CUtensorMap ta, tb, tc;
+  {
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB, 1};
+    uint64_t strides[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2, (uint64_t)1 << 30};
+    uint32_t box[5] = {64u, (uint32_t)p.P, (uint32_t)(p.bh + 2), 1u, 1u};
+    if (encode_map(&ta, d->a, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)9 * C, (uint64_t)Cout};
+    uint64_t strides[1] = {(uint64_t)9 * C * 2};
+    uint32_t box[2] = {64u, (uint32_t)Cout};
+    if (encode_map(&tb, d->wt, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  {
+    uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)NB, 1};
+    uint64_t strides[4] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2, (uint64_t)1 << 30};
+    uint32_t box[5] = {64u, (uint32_t)W, (uint32_t)p.bh, 1u, 1u};
+    if (encode_map(&tc, d->out, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  if (Cout == 64) return launch_conv3<64, true>(ta, tb, tc, p, st);
+  return launch_conv3<128, false>(ta, tb, tc, p, st);
+}
+
 static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
+  {
+    const int rc = conv3x3_tc(d, st);
+    if (rc >= 0) return rc;
+  }
   AVCER_REQUIRE(d->a_stride[0] == 1, "contract: a_stride[0] must be 1");
   const int BK = (d->cin % 64 == 0) ? 64 : 32;
   AVCER_REQUIRE(d->cin % BK == 0, "contract(bf16): cin=%d must be a multiple of 32", d->cin);
@@ -169,6 +255,8 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   p.out = d->out;
   p.act = d->act;
   p.res_after_act = d->res_after_act;
+  p.trace = g_trace;
+  p.debug = g_debug;
   if (p.num_tiles == 0) return 0;
 
   const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -196,6 +284,13 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   // output / residual maps: (cout, w, h, n) boxes of the same shape as the activation box
   CUtensorMap tc = ta, tr = ta;
   const int mode = d->out_f32 ? OUT_DIRECT_F32 : (d->residual ? OUT_TMA_RES : OUT_TMA);
+  // Plain [M, Cout] outputs (Linear layers, pointwise convs run as GEMMs): M tiles are 128 consecutive rows, so the
+  // two-SM kernel can use its barrier-free per-warp epilogue.
+  static const int flat_env = getenv("AVCER_FLAT") ? atoi(getenv("AVCER_FLAT")) : 1;
+  // It trades two pipeline stages for per-warp staging slabs: only for short K loops, whose tiles are epilogue-bound
+  // (deep K loops are MMA-bound and want the stages: measured +30 % time on K >= 1024 GEMMs with residual).
+  const bool flat = flat_env != 0 && use_cta2 && BN == 256 && d->H == 1 && d->NB == 1 && p.bw == 128 && p.bh == 1 && p.bn == 1 &&
+                    (long long)d->taps_w * d->taps_h * p.kchunks <= (flat_env > 1 ? 1 << 30 : 8);
   if (mode != OUT_DIRECT_F32) {
     const int64_t ext[3] = {d->W, d->H, d->NB};
     auto make_out_map = [&](CUtensorMap* m, const void* base, const int64_t* str) -> int {
@@ -208,6 +303,7 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
       }
       strides[3] = (uint64_t)1 << 30;
       uint32_t box[5] = {64u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, 1u};
+      if (flat) box[1] = 32u;                                   // per-warp slabs of 32 rows (FLAT epilogue)
       return encode_map(m, base, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     };
     if (make_out_map(&tc, d->out, d->out_stride)) return 1;
@@ -219,8 +315,14 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   const int grid = num_sms_cached();
   if (use_cta2) {
     if (BN == 256) {
+      if (flat) {
+        if (mode == OUT_TMA) return launch_tc2<OUT_TMA, 256, 4, 1>(ta, tb, tc, tr, p, grid, st);
+        return launch_tc2<OUT_TMA_RES, 256, 4, 1>(ta, tb, tc, tr, p, grid, st);
+      }
       if (mode == OUT_TMA) return launch_tc2<OUT_TMA, 256>(ta, tb, tc, tr, p, grid, st);
-      return launch_tc2<OUT_TMA_RES, 256>(ta, tb, tc, tr, p, grid, st);
+      static const int rslots = getenv("AVCER_RSLOTS") ? atoi(getenv("AVCER_RSLOTS")) : 4;
+      if (rslots == 2) return launch_tc2<OUT_TMA_RES, 256, 2>(ta, tb, tc, tr, p, grid, st);
+      return launch_tc2<OUT_TMA_RES, 256, 4>(ta, tb, tc, tr, p, grid, st);
     }
     if (mode == OUT_TMA) return launch_tc2<OUT_TMA, 128>(ta, tb, tc, tr, p, grid, st);
     return launch_tc2<OUT_TMA_RES, 128>(ta, tb, tc, tr, p, grid, st);

@@ -58,6 +58,8 @@ template <> struct Vec8<__nv_bfloat16> {
 // ------------------------------------------------------------------ max pool 3x3/2, no padding (video.py:103)
 template <typename T>
 __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, int n, int h, int w, int c, int ho, int wo, T* __restrict__ y) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c8 = c / 8;
   const long long total = (long long)n * ho * wo * c8;
@@ -84,6 +86,8 @@ __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, int n, int h, int w
 // ------------------------------------------------------------------ global average pool (video.py:124)
 template <typename T>
 __global__ void avgpool_kernel(const T* __restrict__ x, int n, int hw, int c, T* __restrict__ y) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c8 = c / 8;
   if (i >= (long long)n * c8) return;
@@ -106,6 +110,8 @@ __global__ void avgpool_kernel(const T* __restrict__ x, int n, int hw, int c, T*
 template <typename T>
 __global__ void small_linear_kernel(const T* __restrict__ x, long long n, int k, long long ldx, const float* __restrict__ w,
                                     const float* __restrict__ b, int m, int softmax, float* __restrict__ y) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -135,6 +141,8 @@ template <typename T>
 __global__ void lstm_cell_kernel(const float* __restrict__ xproj, const int* __restrict__ xidx,
                                  const float* __restrict__ hproj, float* __restrict__ c, T* __restrict__ h_out,
                                  long long ldh, long long n, int hidden, int first) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * hidden) return;
   const long long r = i / hidden;
@@ -161,6 +169,8 @@ __global__ void lstm_cell_kernel(const float* __restrict__ xproj, const int* __r
 __global__ void __launch_bounds__(512)
 audio_normalize_kernel(const float* __restrict__ wav, const long long* __restrict__ starts,
                        const long long* __restrict__ ends, int win, int pad_mode, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ double red[16];
   __shared__ double bc[2];
   const int wi = blockIdx.x;
@@ -204,60 +214,86 @@ audio_normalize_kernel(const float* __restrict__ wav, const long long* __restric
 }
 
 // ------------------------------------------------------------------ K5b wav2vec2 conv0 (Cin=1,k=10,s=5,bias) + LayerNorm(512) + GELU
-// (HF Wav2Vec2LayerNormConvLayer #0).  One warp per output time step; lane owns channels
-// {128*q + 4*lane + e}.
+// (HF Wav2Vec2LayerNormConvLayer #0).  Persistent blocks (filter + LN parameters staged in shared memory once
+// per block); one warp per PAIR of consecutive output time steps, so every filter vector read from shared
+// memory feeds two steps; lane owns channels {128*q + 4*lane + e}.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 w2v_conv0_kernel(const float* __restrict__ x, int n, int t_in, int t_out, const float* __restrict__ w,
                  const float* __restrict__ b, const float* __restrict__ g, const float* __restrict__ be,
                  T* __restrict__ y, long long y_pitch_rows) {
   __shared__ __align__(16) float sw[10][512];
   __shared__ __align__(16) float sb[512], sg[512], sbe[512];
-  for (int i = threadIdx.x; i < 5120; i += blockDim.x) sw[i % 10][i / 10] = w[i];   // w is [512][1][10]
+  for (int i = threadIdx.x; i < 5120; i += blockDim.x) sw[i >> 9][i & 511] = w[(i & 511) * 10 + (i >> 9)];   // w is [512][1][10]
   for (int i = threadIdx.x; i < 512; i += blockDim.x) { sb[i] = b[i]; sg[i] = g[i]; sbe[i] = be[i]; }
   __syncthreads();
+  pdl_wait();                       // the filter / LN parameters above are constants; x and y belong to other kernels
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int batch = blockIdx.y;
-  const float* xb = x + (long long)batch * t_in;
-  for (int t = blockIdx.x * 8 + wid; t < t_out; t += gridDim.x * 8) {
-    float xv[10];
+  const int pairs_per_row = (t_out + 1) >> 1;
+  const long long pairs = (long long)n * pairs_per_row;
+  for (long long pi = (long long)blockIdx.x * 8 + wid; pi < pairs; pi += (long long)gridDim.x * 8) {
+    const int batch = (int)(pi / pairs_per_row);
+    const int t = 2 * (int)(pi - (long long)batch * pairs_per_row);
+    const bool two = t + 1 < t_out;
+    const float* xb = x + (long long)batch * t_in + 5 * t;
+    float xv[15];
 #pragma unroll
-    for (int k = 0; k < 10; ++k) xv[k] = __ldg(xb + 5 * t + k);
-    float v[16];
+    for (int k = 0; k < 10; ++k) xv[k] = __ldg(xb + k);
+#pragma unroll
+    for (int k = 10; k < 15; ++k) xv[k] = two ? __ldg(xb + k) : 0.0f;
+    float v[2][16];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int c0 = 128 * q + 4 * lane;
-      float4 a = *reinterpret_cast<const float4*>(&sb[c0]);
+      const float4 bias = *reinterpret_cast<const float4*>(&sb[c0]);
+      float4 a0 = bias, a1 = bias;
 #pragma unroll
       for (int k = 0; k < 10; ++k) {
         const float4 wk = *reinterpret_cast<const float4*>(&sw[k][c0]);
-        a.x = fmaf(wk.x, xv[k], a.x); a.y = fmaf(wk.y, xv[k], a.y); a.z = fmaf(wk.z, xv[k], a.z); a.w = fmaf(wk.w, xv[k], a.w);
+        a0.x = fmaf(wk.x, xv[k], a0.x); a0.y = fmaf(wk.y, xv[k], a0.y); a0.z = fmaf(wk.z, xv[k], a0.z); a0.w = fmaf(wk.w, xv[k], a0.w);
+        a1.x = fmaf(wk.x, xv[k + 5], a1.x); a1.y = fmaf(wk.y, xv[k + 5], a1.y); a1.z = fmaf(wk.z, xv[k + 5], a1.z); a1.w = fmaf(wk.w, xv[k + 5], a1.w);
       }
-      v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+      v[0][4 * q] = a0.x; v[0][4 * q + 1] = a0.y; v[0][4 * q + 2] = a0.z; v[0][4 * q + 3] = a0.w;
+      v[1][4 * q] = a1.x; v[1][4 * q + 1] = a1.y; v[1][4 * q + 2] = a1.z; v[1][4 * q + 3] = a1.w;
     }
-    float s = 0.f;
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) s += v[i];
-    const float mean = warp_sum(s) * (1.0f / 512.0f);
-    float q2 = 0.f;
+    for (int i = 0; i < 16; ++i) { s0 += v[0][i]; s1 += v[1][i]; }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; q2 = fmaf(d, d, q2); }
-    const float rstd = rsqrtf(warp_sum(q2) * (1.0f / 512.0f) + 1e-5f);
+    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    const float mean[2] = {s0 * (1.0f / 512.0f), s1 * (1.0f / 512.0f)};
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float d0 = v[0][i] - mean[0], d1 = v[1][i] - mean[1];
+      q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o); }
+    const float rstd[2] = {rsqrtf(q0 * (1.0f / 512.0f) + 1e-5f), rsqrtf(q1 * (1.0f / 512.0f) + 1e-5f)};
     T* yr = y + ((long long)batch * y_pitch_rows + t) * 512;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int c0 = 128 * q + 4 * lane;
-      float o[4];
+      const float4 gg = *reinterpret_cast<const float4*>(&sg[c0]);
+      const float4 bb = *reinterpret_cast<const float4*>(&sbe[c0]);
+      const float ga[4] = {gg.x, gg.y, gg.z, gg.w}, ba[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = gelu_for<T>((v[4 * q + e] - mean) * rstd * sg[c0 + e] + sbe[c0 + e]);
-      if (sizeof(T) == 2) {
-        uint2 u;
-        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-        h2[0] = __floats2bfloat162_rn(o[0], o[1]);
-        h2[1] = __floats2bfloat162_rn(o[2], o[3]);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(yr) + c0) = u;
-      } else {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(yr) + c0) = make_float4(o[0], o[1], o[2], o[3]);
+      for (int u2 = 0; u2 < 2; ++u2) {
+        if (u2 == 1 && !two) break;
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = gelu_for<T>((v[u2][4 * q + e] - mean[u2]) * rstd[u2] * ga[e] + ba[e]);
+        if (sizeof(T) == 2) {
+          uint2 u;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+          h2[0] = __floats2bfloat162_rn(o[0], o[1]);
+          h2[1] = __floats2bfloat162_rn(o[2], o[3]);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(yr) + u2 * 512 + c0) = u;
+        } else {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(yr) + u2 * 512 + c0) = make_float4(o[0], o[1], o[2], o[3]);
+        }
       }
     }
   }
@@ -269,6 +305,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const T* __restrict__ x, long long rows, long long ldx, const T* __restrict__ add,
                  long long add_rows, const float* __restrict__ g, const float* __restrict__ b, float eps, int act,
                  T* __restrict__ y, long long ldy) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int C = CHUNKS * 256;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -315,6 +353,8 @@ layernorm_kernel(const T* __restrict__ x, long long rows, long long ldx, const T
 template <typename T>
 __global__ void add_rows_kernel(const T* __restrict__ x, long long rows, int c, const T* __restrict__ add,
                                 long long add_rows, T* __restrict__ y) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c8 = c / 8;
   if (i >= rows * c8) return;
@@ -388,6 +428,8 @@ attention_kernel(const T* __restrict__ qkv, int t, int heads, float scale, T* __
 // ------------------------------------------------------------------ audio head pools (audio_8_cl.py:146-159)
 template <typename T>
 __global__ void maxpool1d5_relu_kernel(const T* __restrict__ x, int n, int t, int c, int to, T* __restrict__ y) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n * to * c) return;
   const int cc = (int)(i % c);
@@ -403,6 +445,8 @@ __global__ void maxpool1d5_relu_kernel(const T* __restrict__ x, int n, int t, in
 }
 template <typename T>
 __global__ void avgpool1d_relu_kernel(const T* __restrict__ x, int n, int t, int c, T* __restrict__ y) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n * c) return;
   const int cc = (int)(i % c);
@@ -438,7 +482,7 @@ extern "C" int avcer_maxpool3x3s2(const void* x, int n, int h, int w, int c, voi
   const int ho = (h - 3) / 2 + 1, wo = (w - 3) / 2 + 1;
   const long long total = (long long)n * ho * wo * (c / 8);
   if (total == 0) return 0;
-  AVCER_DISPATCH(dtype, (maxpool3x3s2_kernel<T><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(
+  AVCER_DISPATCH(dtype, (launch_pdl(maxpool3x3s2_kernel<T>, blocks_for(total, 256), 256, 0, as_stream(stream), 
                             (const T*)x, n, h, w, c, ho, wo, (T*)y)));
   return check_launch("maxpool3x3s2");
 }
@@ -447,7 +491,7 @@ extern "C" int avcer_avgpool(const void* x, int n, int hw, int c, void* y, int d
   AVCER_REQUIRE(c % 8 == 0 && hw > 0, "avgpool: bad shape");
   const long long total = (long long)n * (c / 8);
   if (total == 0) return 0;
-  AVCER_DISPATCH(dtype, (avgpool_kernel<T><<<blocks_for(total, 128), 128, 0, as_stream(stream)>>>((const T*)x, n, hw, c, (T*)y)));
+  AVCER_DISPATCH(dtype, (launch_pdl(avgpool_kernel<T>, blocks_for(total, 128), 128, 0, as_stream(stream), (const T*)x, n, hw, c, (T*)y)));
   return check_launch("avgpool");
 }
 
@@ -455,7 +499,7 @@ extern "C" int avcer_small_linear(const void* x, int64_t n, int k, int64_t ldx, 
                                   int softmax, float* y, int dtype, void* stream) {
   AVCER_REQUIRE(m >= 1 && m <= 8 && k > 0, "small_linear: m must be in [1,8]");
   if (n == 0) return 0;
-  AVCER_DISPATCH(dtype, (small_linear_kernel<T><<<blocks_for(n * 32, 256), 256, 0, as_stream(stream)>>>(
+  AVCER_DISPATCH(dtype, (launch_pdl(small_linear_kernel<T>, blocks_for(n * 32, 256), 256, 0, as_stream(stream), 
                             (const T*)x, n, k, ldx, w, b, m, softmax, y)));
   return check_launch("small_linear");
 }
@@ -465,7 +509,7 @@ extern "C" int avcer_lstm_cell(const float* xproj, const int32_t* xidx, const fl
   AVCER_REQUIRE(hidden > 0 && ldh >= hidden, "lstm_cell: bad shape");
   const long long total = n * hidden;
   if (total == 0) return 0;
-  AVCER_DISPATCH(dtype, (lstm_cell_kernel<T><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(
+  AVCER_DISPATCH(dtype, (launch_pdl(lstm_cell_kernel<T>, blocks_for(total, 256), 256, 0, as_stream(stream), 
                             xproj, xidx, hproj, c, (T*)h_out, ldh, n, hidden, first)));
   return check_launch("lstm_cell");
 }
@@ -474,7 +518,7 @@ extern "C" int avcer_audio_normalize_windows(const float* wav, const int64_t* st
                                              int win, int pad_mode, float* out, void* stream) {
   AVCER_REQUIRE(pad_mode >= 0 && pad_mode <= 2 && win > 0, "audio_normalize_windows: bad arguments");
   if (n_win == 0) return 0;
-  audio_normalize_kernel<<<n_win, 512, 0, as_stream(stream)>>>(wav, (const long long*)starts, (const long long*)ends, win, pad_mode, out);
+  launch_pdl(audio_normalize_kernel, n_win, 512, 0, as_stream(stream), wav, (const long long*)starts, (const long long*)ends, win, pad_mode, out);
   return check_launch("audio_normalize_windows");
 }
 
@@ -485,11 +529,12 @@ extern "C" int avcer_w2v_conv0_ln_gelu(const float* x, int n, int t_in, const fl
   const int t_out = (t_in - 10) / 5 + 1;
   AVCER_REQUIRE(y_pitch_rows >= t_out, "w2v_conv0: y pitch too small");
   if (n == 0) return 0;
-  int gx = (t_out + 7) / 8;
-  if (gx > 400) gx = 400;
-  dim3 grid(gx, n);
-  AVCER_DISPATCH(dtype, (w2v_conv0_kernel<T><<<grid, 256, 0, as_stream(stream)>>>(x, n, t_in, t_out, w, b, ln_g, ln_b,
-                                                                                 (T*)y, y_pitch_rows)));
+  const long long pairs = (long long)n * ((t_out + 1) / 2);
+  long long gx = (pairs + 7) / 8;
+  const long long cap = 3ll * num_sms();          // persistent: three resident blocks per SM
+  if (gx > cap) gx = cap;
+  AVCER_DISPATCH(dtype, (launch_pdl(w2v_conv0_kernel<T>, (unsigned)gx, 256, 0, as_stream(stream), x, n, t_in, t_out, w, b, ln_g, ln_b,
+                                                                                    (T*)y, y_pitch_rows)));
   return check_launch("w2v_conv0");
 }
 
@@ -501,7 +546,7 @@ extern "C" int avcer_layernorm(const void* x, int64_t rows, int c, int64_t ldx, 
   if (rows == 0) return 0;
 #define AVCER_LN_CASE(ch)                                                                                         \
   if (c == ch * 256) {                                                                                            \
-    AVCER_DISPATCH(dtype, (layernorm_kernel<T, ch><<<blocks_for(rows * 32, 256), 256, 0, as_stream(stream)>>>(  \
+    AVCER_DISPATCH(dtype, (launch_pdl(layernorm_kernel<T, ch>, blocks_for(rows * 32, 256), 256, 0, as_stream(stream),   \
                               (const T*)x, rows, ldx, (const T*)add, add_rows > 0 ? add_rows : 1, g, b, eps, act, \
                               (T*)y, ldy)));                                                                      \
   }
@@ -515,7 +560,7 @@ extern "C" int avcer_add_rows(const void* x, int64_t rows, int c, const void* ad
   AVCER_REQUIRE(c % 8 == 0 && add_rows > 0, "add_rows: bad shape");
   const long long total = rows * (c / 8);
   if (total == 0) return 0;
-  AVCER_DISPATCH(dtype, (add_rows_kernel<T><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(
+  AVCER_DISPATCH(dtype, (launch_pdl(add_rows_kernel<T>, blocks_for(total, 256), 256, 0, as_stream(stream), 
                             (const T*)x, rows, c, (const T*)add, add_rows, (T*)y)));
   return check_launch("add_rows");
 }
@@ -551,7 +596,7 @@ extern "C" int avcer_maxpool1d5_relu(const void* x, int n, int t, int c, void* y
   const int to = t / 5;
   const long long total = (long long)n * to * c;
   if (total == 0) return 0;
-  AVCER_DISPATCH(dtype, (maxpool1d5_relu_kernel<T><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(
+  AVCER_DISPATCH(dtype, (launch_pdl(maxpool1d5_relu_kernel<T>, blocks_for(total, 256), 256, 0, as_stream(stream), 
                             (const T*)x, n, t, c, to, (T*)y)));
   return check_launch("maxpool1d5_relu");
 }
@@ -559,7 +604,7 @@ extern "C" int avcer_maxpool1d5_relu(const void* x, int n, int t, int c, void* y
 extern "C" int avcer_avgpool1d_relu(const void* x, int n, int t, int c, void* y, int dtype, void* stream) {
   const long long total = (long long)n * c;
   if (total == 0) return 0;
-  AVCER_DISPATCH(dtype, (avgpool1d_relu_kernel<T><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(
+  AVCER_DISPATCH(dtype, (launch_pdl(avgpool1d_relu_kernel<T>, blocks_for(total, 256), 256, 0, as_stream(stream), 
                             (const T*)x, n, t, c, (T*)y)));
   return check_launch("avgpool1d_relu");
 }

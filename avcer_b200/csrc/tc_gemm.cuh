@@ -22,6 +22,7 @@
 // * Persistent: grid = min(#tiles, #SM); tiles are strided across CTAs, N fastest so CTAs of
 //   one wave share the same activation box in L2.
 #pragma once
+#include "common.h"
 #include "ptx.cuh"
 
 namespace avcer {
@@ -51,7 +52,15 @@ struct TcGemmParams {
   void* out;                          // fp32 output (direct-store mode)
   int act;
   int res_after_act;     // 0: act(acc + bias + res)   1: act(acc + bias) + res
+  int debug;                   // development aid (avcer_debug_set_flags): epilogue steps to skip, 0 in production
+  unsigned long long* trace;   // development aid (avcer_debug_set_trace): per-tile clock64 stamps of the first CTAs, else nullptr
 };
+
+constexpr int kTraceCtas = 4, kTraceTiles = 64, kTraceSlots = 16;
+__device__ __forceinline__ void trace_stamp(const TcGemmParams& p, int local_tile, int slot) {
+  if (p.trace != nullptr && blockIdx.x < kTraceCtas && local_tile < kTraceTiles)
+    p.trace[(blockIdx.x * kTraceTiles + local_tile) * kTraceSlots + slot] = clock64();
+}
 
 template <int BN, int BK, int MODE, int KSUB, int OCC>
 struct TcGemmCfg {
@@ -136,6 +145,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_s);
+  pdl_wait();                  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer

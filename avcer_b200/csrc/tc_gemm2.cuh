@@ -69,7 +69,7 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <int MODE, int BN_>
+template <int MODE, int BN_, int RS_ = 4, int FLAT_ = 0>
 struct TcGemm2Cfg {
   static constexpr int BN = BN_;                 // N of the pair tile (each CTA stages BN/2 weight rows): 256 or 128
   static constexpr int BK = 64;
@@ -78,39 +78,46 @@ struct TcGemm2Cfg {
   static constexpr int STAGE = A_STAGE + B_STAGE;
   static constexpr int HALF = 128 * 128;
   static constexpr int C_SLOTS = 2;              // output staging ring (a 4-slot ring measured no faster)
-  static constexpr int R_SLOTS = (MODE == OUT_TMA_RES) ? 2 : 0;
+  static constexpr int R_SLOTS = (MODE == OUT_TMA_RES) ? RS_ : 0;   // residual prefetch ring: 64 KB of residual reads in flight per SM
+  static constexpr int R_RING = R_SLOTS > 0 ? R_SLOTS : 1;
   static constexpr int BUDGET = 224 * 1024;
-  static constexpr int FIT = (BUDGET - (C_SLOTS + R_SLOTS) * HALF) / STAGE;
+  // FLAT epilogue (outputs that are plain [M, Cout] rows): every epilogue warp owns two 32-row x 128 B staging
+  // slabs (and two residual slabs) and moves them with its own TMA operations -- no CTA-wide barriers.
+  static constexpr int SLAB = 32 * 128;
+  static constexpr int C_BYTES = FLAT_ ? 8 * 2 * SLAB : C_SLOTS * HALF;
+  static constexpr int R_BYTES = (MODE == OUT_TMA_RES) ? (FLAT_ ? 8 * 2 * SLAB : R_SLOTS * HALF) : 0;
+  static constexpr int N_RBARS = FLAT_ ? 16 : 2 * R_RING;        // FLAT: one per (warp, slab); else rfull + rfree rings
+  static constexpr int FIT = (BUDGET - C_BYTES - R_BYTES) / STAGE;
   static constexpr int STAGES = FIT > 8 ? 8 : FIT;
-  static constexpr int SMEM = STAGES * STAGE + (C_SLOTS + R_SLOTS) * HALF + 1024;
+  static constexpr int SMEM = STAGES * STAGE + C_BYTES + R_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int HALVES = BN / 64;
   static constexpr int EPI_WARPS = 8;
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
 };
 
-template <int MODE, int BN_>
+template <int MODE, int BN_, int RS_, int FLAT_>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                 const TcGemmParams p) {
-  using Cfg = TcGemm2Cfg<MODE, BN_>;
+  using Cfg = TcGemm2Cfg<MODE, BN_, RS_, FLAT_>;
   constexpr int BN = Cfg::BN, BK = Cfg::BK;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 8];
+  __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 4 + Cfg::N_RBARS];
   __shared__ uint32_t tmem_slot_s;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + Cfg::STAGES * Cfg::A_STAGE;
   const uint32_t c_base = smem_base + Cfg::STAGES * Cfg::STAGE;
-  const uint32_t r_base = c_base + Cfg::C_SLOTS * Cfg::HALF;
+  const uint32_t r_base = c_base + Cfg::C_BYTES;
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
   auto rfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + a); };
-  auto rfree_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 6 + a); };
+  auto rfree_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + Cfg::R_RING + a); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -136,8 +143,14 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 2 * Cfg::EPI_WARPS);   // epilogue warps of BOTH CTAs (used on the leader only)
-      mbar_init(rfull_bar(a), 1);
-      mbar_init(rfree_bar(a), Cfg::EPI_WARPS);
+    }
+    if (FLAT_) {
+      for (int a = 0; a < Cfg::N_RBARS; ++a) mbar_init(rfull_bar(a), 1);      // (epilogue warp, slab) residual barriers
+    } else {
+      for (int a = 0; a < Cfg::R_RING; ++a) {
+        mbar_init(rfull_bar(a), 1);
+        mbar_init(rfree_bar(a), Cfg::EPI_WARPS);
+      }
     }
     fence_mbar_init();
   }
@@ -150,6 +163,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();                   // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_s);
+  pdl_wait();                  // the prologue above overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
   auto tile_coords = [&](int pt, int& nt, int& w0, int& h0, int& n0) {
     nt = pt % p.tiles_n;
@@ -165,10 +180,12 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_pair = 2u * (p.a_bytes + Cfg::B_STAGE);
-      for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
+      int local = 0;
+      for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters, ++local) {
         int nt, w0, h0, n0;
         tile_coords(pt, nt, w0, h0, n0);
         int kcol = 0;
+        trace_stamp(p, local, 0);
         for (int ty = 0; ty < p.taps_h; ++ty) {
           for (int tx = 0; tx < p.taps_w; ++tx) {
             for (int kc = 0; kc < p.kchunks; ++kc, kcol += BK) {
@@ -181,6 +198,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
         }
+        trace_stamp(p, local, 1);
       }
     }
   } else if (warp == 1) {
@@ -193,12 +211,15 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters, ++local) {
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1u;
+        trace_stamp(p, local, 2);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
+        trace_stamp(p, local, 3);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (it == 0) trace_stamp(p, local, 4);
           const uint64_t adesc = umma_desc_kmajor(a_base + stage * Cfg::A_STAGE, 1024u, 2u);
           const uint64_t bdesc = umma_desc_kmajor(b_base + stage * Cfg::B_STAGE, 1024u, 2u);
 #pragma unroll
@@ -208,23 +229,154 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit_2sm(tfull_bar(acc));
+        trace_stamp(p, local, 5);
       }
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------ residual producer (per CTA, own rows)
-    if (MODE == OUT_TMA_RES && lane == 0) {
+    if (MODE == OUT_TMA_RES && !FLAT_ && lane == 0) {
       uint32_t hcount = 0;
-      for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
+      int local = 0;
+      for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters, ++local) {
         int nt, w0, h0, n0;
         tile_coords(pt, nt, w0, h0, n0);
         for (int hf = 0; hf < Cfg::HALVES; ++hf, ++hcount) {
-          const int slot = hcount & 1;
-          mbar_wait(rfree_bar(slot), ((hcount >> 1) & 1u) ^ 1u);
+          if (hf == Cfg::HALVES - 1) trace_stamp(p, local, 13);
+          const int slot = hcount % Cfg::R_RING;
+          mbar_wait(rfree_bar(slot), ((hcount / Cfg::R_RING) & 1u) ^ 1u);
           mbar_arrive_expect_tx(rfull_bar(slot), static_cast<uint32_t>(rows) * 128);
           tma_load_5d(r_base + slot * Cfg::HALF, &tmR, rfull_bar(slot), nt * BN + hf * 64, w0, h0, n0, 0);
         }
       }
     }
+  } else if (warp >= 4 && FLAT_) {
+    // ------------------------------------------------------------ FLAT epilogue: warps run independently.
+    // Warp (q, grp) owns rows 32q..32q+31 of the CTA's 128 and the 64-column halves hf = grp, grp+2, ...:
+    // tcgen05.ld 64 columns -> bias / residual / activation -> bf16 into its own swizzled 4 KB slab -> its own
+    // TMA store (box 64 x 32 rows, clipped at M); the residual slab of its item j+2 is prefetched by the same warp
+    // as soon as item j has consumed that slab.  The only cross-warp synchronisation left is tfull / tempty.
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int ew = warp - 4;
+    constexpr int HPW = Cfg::HALVES / 2;                     // halves per warp per tile
+    const uint32_t cslab = c_base + ew * 2 * Cfg::SLAB;
+    const uint32_t rslab = r_base + ew * 2 * Cfg::SLAB;
+    const uint32_t rbar = rfull_bar(2 * ew);
+    const int my_tiles = cluster_id < pair_tiles ? (pair_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
+    const int n_items = my_tiles * HPW;
+    auto item_coords = [&](int j, int& col0, int& row0) {
+      const int pt = cluster_id + (j / HPW) * num_clusters;
+      col0 = (pt % p.tiles_n) * BN + (grp + 2 * (j % HPW)) * 64;
+      row0 = (2 * (pt / p.tiles_n) + (int)rank) * 128 + q * 32;
+    };
+    auto issue_res = [&](int j) {
+      if (j < n_items) {
+        int col0, row0;
+        item_coords(j, col0, row0);
+        mbar_arrive_expect_tx(rbar + 8u * (j & 1), Cfg::SLAB);
+        tma_load_5d(rslab + (j & 1) * Cfg::SLAB, &tmR, rbar + 8u * (j & 1), col0, row0, 0, 0, 0);
+      }
+    };
+    if (MODE == OUT_TMA_RES && lane == 0 && !(p.debug & 32)) { issue_res(0); issue_res(1); }
+    const uint32_t row_off = lane * 128;
+    int j = 0;
+    for (int local = 0; local < my_tiles; ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1u;
+      if (threadIdx.x == 128) trace_stamp(p, local, 6);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      if (threadIdx.x == 128) trace_stamp(p, local, 7);
+#pragma unroll 1
+      for (int h = 0; h < HPW; ++h, ++j) {
+        int col0, row0;
+        item_coords(j, col0, row0);
+        const int hf = grp + 2 * h;
+        const uint32_t cbuf = cslab + (j & 1) * Cfg::SLAB;
+        const uint32_t rbuf = rslab + (j & 1) * Cfg::SLAB;
+        if (lane == 0) bulk_wait_group_read<1>();            // the store that last read this slab (item j-2) is done with it
+        __syncwarp();
+        if (threadIdx.x == 128 && h == 0) trace_stamp(p, local, 8);
+        uint32_t v[2][32];
+        const uint32_t taddr = tmem_base + acc * BN + hf * 64 + (static_cast<uint32_t>(q * 32) << 16);
+        if (!(p.debug & 8)) {
+          tmem_ld_32x32(taddr, v[0]);
+          tmem_ld_32x32(taddr + 32, v[1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v[0][i] = i; v[1][i] = i; }
+        }
+        if (MODE == OUT_TMA_RES && !(p.debug & 32)) mbar_wait(rbar + 8u * (j & 1), (j >> 1) & 1u);
+        if (threadIdx.x == 128 && h == 0) trace_stamp(p, local, 9);
+        tmem_ld_wait();
+        if (threadIdx.x == 128 && h == 0) trace_stamp(p, local, 10);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[cc][i]);
+          const int co = col0 + cc * 32;
+          if (p.bias != nullptr && co < p.Cout && !(p.debug & 1)) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co + i));
+              f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+            }
+          }
+          auto apply_act = [&]() {
+            if (p.act == ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = f[i] < 0.0f ? 0.0f : f[i];
+            } else if (p.act == ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = gelu_erf_fast(f[i]);
+            }
+          };
+          if (MODE == OUT_TMA_RES) {
+            if (p.res_after_act) apply_act();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (p.debug & 2) break;
+              uint4 u;
+              ld_shared_v4(rbuf + row_off + (((cc * 4 + i) ^ (lane & 7)) << 4), u);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t = __bfloat1622float2(h2[e]);
+                f[i * 8 + e * 2] += t.x;
+                f[i * 8 + e * 2 + 1] += t.y;
+              }
+            }
+            if (!p.res_after_act) apply_act();
+          } else {
+            apply_act();
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[i * 8 + e * 2], f[i * 8 + e * 2 + 1]);
+            if (!(p.debug & 4)) st_shared_v4(cbuf + row_off + (((cc * 4 + i) ^ (lane & 7)) << 4), u);
+          }
+        }
+        if (threadIdx.x == 128 && h == 0) trace_stamp(p, local, 11);
+        fence_proxy_async();
+        __syncwarp();
+        if (threadIdx.x == 128 && h == 0) trace_stamp(p, local, 12);
+        if (lane == 0) {
+          if (col0 < p.Cout && !(p.debug & 16)) tma_store_5d(&tmC, cbuf, col0, row0, 0, 0, 0);
+          bulk_commit_group();
+          if (MODE == OUT_TMA_RES && !(p.debug & 32)) issue_res(j + 2);         // every lane has consumed this residual slab (syncwarp above)
+        }
+        if (threadIdx.x == 128 && h < 2) trace_stamp(p, local, 13 + h);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+      if (threadIdx.x == 128) trace_stamp(p, local, 15);
+    }
+    if (lane == 0) bulk_wait_group<0>();
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (per CTA, own 128 rows)
     const int q = warp & 3;
@@ -238,12 +390,14 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t acc_phase = (local >> 1) & 1u;
       int nt, w0, h0, n0;
       tile_coords(pt, nt, w0, h0, n0);
+      if (store_thread) trace_stamp(p, local, 6);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (store_thread) trace_stamp(p, local, 7);
 #pragma unroll 1
       for (int hf = 0; hf < Cfg::HALVES; ++hf, ++hcount) {
         const int slot = hcount % Cfg::C_SLOTS;
-        const int rslot = hcount & 1;
+        const int rslot = hcount % Cfg::R_RING;
         if (store_thread) bulk_wait_group_read<Cfg::C_SLOTS - 1>();
         named_bar_sync(1, 256);
         const uint32_t cbuf = c_base + slot * Cfg::HALF;
@@ -275,7 +429,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int j0 = grp * 4;
         if (MODE == OUT_TMA_RES) {
           if (p.res_after_act) apply_act();
-          mbar_wait(rfull_bar(rslot), (hcount >> 1) & 1u);
+          mbar_wait(rfull_bar(rslot), (hcount / Cfg::R_RING) & 1u);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
@@ -307,11 +461,13 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (store_thread) {
           if (nt * BN + hf * 64 < p.Cout) tma_store_5d(&tmC, cbuf, nt * BN + hf * 64, w0, h0, n0, 0);
           bulk_commit_group();
+          if (hf < 4) trace_stamp(p, local, 8 + hf);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(tempty_bar(acc));    // both CTAs release the accumulator on the leader
+      if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+      if (store_thread) trace_stamp(p, local, 12);    // both CTAs release the accumulator on the leader
     }
     if (store_thread) bulk_wait_group<0>();
   }

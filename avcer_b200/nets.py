@@ -122,6 +122,9 @@ class VSNet:
             y = self._conv(t, blk["conv3"], ops.ACT_RELU, residual=identity)
             if taps is not None:
                 taps[f"block{bi}"] = y
+        return self._tail(y)
+
+    def _tail(self, y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         pooled = ops.avgpool(y)
         fc1 = self.w["fc1"]
         feat = ops.linear(pooled, fc1.wt, fc1.bias, act=ops.ACT_RELU)      # relu(fc1): VD input and fc2 input

@@ -61,6 +61,8 @@ def run_linear(name, m, k, n, dtype, act=ops.ACT_NONE, residual=False, out_f32=F
             r = r + res.float()
         if act == ops.ACT_GELU:
             r = F.gelu(r)
+        if act == ops.ACT_RELU:
+            r = F.relu(r)
         err = (y.float() - r).abs().max().item()
         tol = 0.06 if (dtype == torch.bfloat16 and not out_f32) else 2e-3
         print(f"[{'OK ' if err < tol else 'BAD'}] {name}: max|err|={err:.4g}", flush=True)
@@ -92,6 +94,14 @@ run_conv("conv3x3 bf16 32x14x14 256->256", 32, 14, 14, 256, 256, 3, 1, bf)
 run_conv("conv3x3 bf16 5x7x7 512->512", 5, 7, 7, 512, 512, 3, 1, bf)
 run_conv("conv1x1 s2 bf16 4x55x55 256->128", 4, 55, 55, 256, 128, 1, 2, bf)
 run_conv("conv1x1 s2 bf16 3x14x14 1024->512 res", 3, 14, 14, 1024, 512, 1, 2, bf, residual=True)
+
+# two-SM kernel, FLAT per-warp epilogue: ragged M (odd tile count, rows not a multiple of 32), residual, activations
+run_linear("flat bf16 50003x256x1024 relu+res", 50003, 256, 1024, bf, act=ops.ACT_RELU, residual=True)
+run_linear("flat bf16 50176x1024x256 relu", 50176, 1024, 256, bf, act=ops.ACT_RELU)
+run_linear("flat bf16 12736x1024x4096 gelu", 12736, 1024, 4096, bf, act=ops.ACT_GELU)
+run_linear("flat bf16 12736x4096x1024 res", 12736, 4096, 1024, bf, residual=True)
+run_linear("flat bf16 20001x64x256 res", 20001, 64, 256, bf, residual=True)
+run_conv("conv1x1 bf16 256x14x14 256->1024 res (flat)", 256, 14, 14, 256, 1024, 1, 1, bf, residual=True)
 
 # quick timing of a big GEMM
 try:

@@ -1,0 +1,112 @@
+"""Kernel-level GPU checks through the C ABI against plain torch fp32 references of the same op:
+the tcgen05 contraction (one- and two-SM tiles, barrier-free FLAT epilogue on ragged M, residual /
+activation epilogues, pointwise convs run as flat GEMMs) and the attention kernel (reference:
+src/architectures/attention_layers.py:10-38 and HF Wav2Vec2Attention)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+BF = torch.bfloat16
+
+
+def _ref_linear(x, w, b, res, act):
+    from avcer_b200 import ops
+
+    r = x.float() @ w.float().t() + b
+    if res is not None:
+        r = r + res.float()
+    if act == ops.ACT_RELU:
+        r = F.relu(r)
+    elif act == ops.ACT_GELU:
+        r = F.gelu(r)
+    return r
+
+
+@pytest.mark.parametrize("m,k,n,act,res", [
+    (50003, 256, 1024, "relu", True),      # two-SM 256-wide tiles, FLAT epilogue, odd tile count, M % 32 != 0
+    (20001, 64, 256, "none", True),        # one K chunk per tile (layer1 conv3 shape)
+    (12736, 1024, 4096, "gelu", False),    # wav2vec2 FFN (64 windows)
+    (12736, 4096, 1024, "none", True),
+    (300, 256, 128, "relu", False),        # single-SM 128-wide tiles (generic box epilogue)
+    (199, 1024, 64, "none", False),        # 64-wide tiles, two CTAs per SM
+])
+def test_contract_linear_matches_torch(cuda_lib, m, k, n, act, res):
+    from avcer_b200 import ops
+
+    torch.manual_seed(m + n)
+    code = {"none": ops.ACT_NONE, "relu": ops.ACT_RELU, "gelu": ops.ACT_GELU}[act]
+    x = torch.randn(m, k, device=DEV).to(BF)
+    w = (torch.randn(n, k, device=DEV) / k ** 0.5).to(BF)
+    b = torch.randn(n, device=DEV)
+    r = torch.randn(m, n, device=DEV).to(BF) if res else None
+    y = ops.linear(x, w, b, residual=r, act=code)
+    ref = _ref_linear(x, w, b, r, code)
+    # bf16 output rounding: half an ulp of the largest magnitude (|ref| <= ~8 -> 0.03)
+    assert (y.float() - ref).abs().max().item() < 0.04
+
+
+def test_pointwise_conv_equals_flat_gemm(cuda_lib):
+    """A 1x1 stride-1 conv is dispatched as one [n*h*w, C] GEMM; results must equal the boxed conv path bit for bit
+    (same MMA order per output element) and torch within bf16 rounding."""
+    from avcer_b200 import ops
+
+    torch.manual_seed(3)
+    n, h, w, cin, cout = 37, 14, 14, 256, 1024
+    x = torch.randn(n, h, w, cin, device=DEV).to(BF)
+    wt = (torch.randn(cout, cin, device=DEV) / cin ** 0.5).to(BF)
+    b = torch.randn(cout, device=DEV)
+    r = torch.randn(n, h, w, cout, device=DEV).to(BF)
+    y = ops.conv2d_nhwc(x, wt, b, kh=1, kw=1, residual=r, act=ops.ACT_RELU)
+    boxed = torch.empty_like(y)
+    ops.contract(a=x, a_dim=(cin, w, h, n, 1), a_stride=(1, cin, w * cin, h * w * cin, n * h * w * cin), wt=wt, bias=b, out=boxed,
+                 out_stride=(cout, w * cout, h * w * cout), W=w, H=h, NB=n, cin=cin, cout=cout, residual=r, act=ops.ACT_RELU)
+    assert torch.equal(y, boxed)
+    ref = F.relu(x.float().view(-1, cin) @ wt.float().t() + b + r.float().view(-1, cout)).view(n, h, w, cout)
+    assert (y.float() - ref).abs().max().item() < 0.04
+
+
+@pytest.mark.parametrize("heads,dh", [(16, 64), (32, 32)])
+@pytest.mark.parametrize("t", [199, 208, 113, 50, 1])
+@pytest.mark.parametrize("dtype", [BF, torch.float32])
+def test_attention_matches_torch(cuda_lib, heads, dh, t, dtype):
+    from avcer_b200 import ops
+
+    torch.manual_seed(t * heads)
+    n = 3
+    qkv = (torch.randn(n * t, 3 * heads * dh, device=DEV) * 1.5).to(dtype)
+    scale = dh ** -0.5
+    out = ops.attention(qkv, n, t, heads, dh, scale)
+    q, k, v = (z.float().view(n, t, heads, dh).transpose(1, 2) for z in qkv.split(heads * dh, dim=1))
+    ref = torch.softmax(q @ k.transpose(-1, -2) * scale, -1) @ v
+    ref = ref.transpose(1, 2).reshape(n * t, heads * dh)
+    tol = 2e-2 if dtype == BF else 2e-5       # bf16: probabilities and outputs are rounded to 8 bits
+    assert (out.float() - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("n,h,w,c,cout", [
+    (3, 55, 55, 64, 64),        # layer1 conv2: resident filter bank, 4-row tiles, ragged last tile (55 = 13*4 + 3)
+    (2, 28, 28, 128, 128),      # layer2 conv2: streamed weights, two K chunks, 8-row tiles (28 = 3*8 + 4)
+    (150, 28, 28, 128, 128),    # more tiles than SMs (persistent loop, accumulator / stage ring wrap-around)
+    (5, 30, 40, 128, 128),      # non-square image
+    (2, 26, 26, 192, 128),      # three K chunks, narrowest supported row (pitch 28)
+])
+def test_conv3x3_halo_kernel_matches_torch(cuda_lib, n, h, w, c, cout):
+    """3x3 'same' convs with 64 / 128 output channels run on the halo-in-shared-memory kernel (conv3x3.cuh):
+    borders (TMA zero fill), the dropped pad columns and the clipped last tile must all match torch."""
+    from avcer_b200 import ops
+
+    torch.manual_seed(n + w)
+    x = torch.randn(n, h, w, c, device=DEV).to(BF)
+    w4 = (torch.randn(cout, c, 3, 3, device=DEV) / (9 * c) ** 0.5).to(BF)
+    b = torch.randn(cout, device=DEV)
+    wt = w4.permute(0, 2, 3, 1).reshape(cout, 9 * c).contiguous()
+    y = ops.conv2d_nhwc(x, wt, b, kh=3, kw=3, pad_h=1, pad_w=1, act=ops.ACT_RELU)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w4.float(), b, padding=1)).permute(0, 2, 3, 1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert (y.float() - ref).abs().max().item() < 0.04

@@ -4,6 +4,7 @@
 #include "tc_gemm.cuh"
 #include "tc_gemm2.cuh"
 #include "conv3x3.cuh"
+#include "stem_pool.cuh"
 
 #include <cudaTypedefs.h>
 #include <mutex>
@@ -343,6 +344,38 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   return set_error("contract: no tensor-core instantiation for BN=%d BK=%d", BN, BK);
 }
 
+// ------------------------------------------------------------------ fused stem + max-pool (bf16)
+static int stem_pool_tc(const void* x, const void* w_packed, const float* bias, int n, void* out, cudaStream_t st) {
+  AVCER_REQUIRE(x != nullptr && w_packed != nullptr && bias != nullptr && out != nullptr, "stem_pool: null pointer");
+  AVCER_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "stem_pool: x / w_packed / out must be 16-byte aligned");
+  if (n == 0) return 0;
+  // strips of the zero-bordered [n, 232, 240, 4] input: (64 elements, 15 per padded row, output row oy -> padded row
+  // 2*oy, crop, filter row ky -> +1 padded row)
+  constexpr uint64_t ROW = 240 * 4, IMG = 232 * ROW;
+  CUtensorMap ta;
+  uint64_t dims[5] = {64, ROW / 64, 112, (uint64_t)n, 7};
+  uint64_t strides[4] = {64 * 2, 2 * ROW * 2, IMG * 2, ROW * 2};
+  uint32_t box[5] = {64, (uint32_t)(ROW / 64), 1, 1, 1};
+  if (encode_map(&ta, x, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  StemPoolParams p{};
+  p.n = n;
+  p.units = 4 * n;
+  p.w_packed = w_packed;
+  p.bias = bias;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  static bool attr_done = false;
+  if (!attr_done) {
+    AVCER_CUDA(cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemPoolCfg::SMEM));
+    attr_done = true;
+  }
+  int g = num_sms();
+  if (g > p.units) g = p.units;
+  launch_pdl(stem_pool_kernel, g, StemPoolCfg::THREADS, StemPoolCfg::SMEM, st, ta, p);
+  return check_launch("stem_pool_kernel");
+}
+
 // ------------------------------------------------------------------ SIMT fp32 path
 struct SimtParams {
   const float* a;
@@ -514,4 +547,10 @@ extern "C" int avcer_contract(const avcer_contract_desc* d, void* stream) {
   if (d->dtype == AVCER_BF16) return contract_tc(d, as_stream(stream));
   if (d->dtype == AVCER_F32) return contract_simt(d, as_stream(stream));
   return set_error("contract: unknown dtype %d", d->dtype);
+}
+
+extern "C" int avcer_stem_pool(const void* x_padded, const void* w_packed, const float* bias, int n, void* out, void* stream) {
+  using namespace avcer;
+  AVCER_REQUIRE(n >= 0, "stem_pool: negative batch");
+  return stem_pool_tc(x_padded, w_packed, bias, n, out, as_stream(stream));
 }

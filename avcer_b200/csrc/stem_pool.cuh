@@ -1,0 +1,232 @@
+// ResNet-50 stem fused with its max-pool: 7x7/2 "TF-same" conv (pad 2|3) + folded BN + ReLU + 3x3/2 un-padded
+// max-pool, [n,232,240,4] zero-bordered bf16 crops -> [n,55,55,64] bf16
+// (reference src/architectures/video.py:63-90 Conv2dSame, :98-103, :116-117).
+//
+// Why a dedicated kernel: run as two launches the 112x112x64 stem output (1.6 MB per crop) is written to HBM and
+// read back by the pool (822 MB per 256 crops), and the generic kernel re-fetches the 28 KB filter bank for every
+// output row through 7 tiny pipeline stages, which leaves it latency-bound at 190 TFLOP/s.  Here
+//   * the filter bank (7 filter rows x 4 KB, UMMA core-matrix order) is loaded ONCE per CTA and stays resident;
+//   * one pipeline stage = the 7 padded input rows of one output row (7 x 1920 B, SWIZZLE_NONE strips whose
+//     stride-2 window overlap is expressed in the UMMA descriptor: LBO 16 B, SBO 128 B), 8 stages in flight;
+//   * a work unit is 14 pooled rows of one crop = 29 consecutive stem rows; the epilogue keeps the last four stem
+//     rows (ReLU'd, bf16) in a shared-memory ring and emits pooled row j as soon as stem rows 2j..2j+2 are there,
+//     so the stem activation never leaves the SM.
+// max-pool of the bf16-rounded ReLU outputs == bf16 rounding of the pooled fp32 values (rounding is monotonic), so
+// the result is bit-identical to the two-kernel path; NaNs propagate like torch (ReLU select, __hmax2_nan).
+// Warp roles: warp0 strip producer, warp1 MMA issuer, warp2 TMEM allocator, warps 4-11 epilogue + pooling.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace avcer {
+
+struct StemPoolParams {
+  int n;                    // crops
+  int units;                // n * 4 work units (14 pooled rows each; the last of a crop has 13)
+  const void* w_packed;     // [7][4 KB] filter rows in UMMA no-swizzle core-matrix order
+  const float* bias;        // [64] folded BN shift
+  __nv_bfloat16* out;       // [n, 55, 55, 64]
+};
+
+struct StemPoolCfg {
+  static constexpr int STRIP = 2048;                 // one padded input row (1920 B) per 2 KB slot
+  static constexpr int A_STAGE = 7 * STRIP;          // the 7 filter rows of one output row
+  static constexpr int STAGES = 8;
+  static constexpr int B_BYTES = 7 * 4096;
+  static constexpr int ROW = 112 * 128;              // one stem output row: 112 px x 64 ch bf16
+  static constexpr int RING = 4;
+  static constexpr int SMEM = STAGES * A_STAGE + 1024 /*junk-row overread of the last strip*/ + B_BYTES + RING * ROW + 1024;
+  static constexpr int TMEM_COLS = 128;              // 2 accumulator buffers x 64 columns
+  static constexpr int THREADS = 384;
+  static constexpr int UNIT_ROWS = 14;               // pooled rows per unit
+};
+
+__global__ void __launch_bounds__(384, 1)
+stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const StemPoolParams p) {
+  using Cfg = StemPoolCfg;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 5];     // full[8] empty[8] tfull[2] tempty[2] bfull
+  __shared__ uint32_t tmem_slot_s;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = a_base + Cfg::STAGES * Cfg::A_STAGE + 1024;
+  const uint32_t ring_base = b_base + Cfg::B_BYTES;
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
+  const uint32_t bfull_bar = bar_base + 8u * (2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmA);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);          // one arrive per epilogue warp
+    }
+    mbar_init(bfull_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&tmem_slot_s), Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_s);
+  pdl_wait();
+  pdl_launch_dependents();
+
+  // unit -> crop, first pooled row, pooled rows in the unit; stem rows r0 .. r0 + 2*rows (inclusive)
+  auto unit_geom = [&](int unit, int& n, int& j0, int& rows) {
+    n = unit >> 2;
+    j0 = (unit & 3) * Cfg::UNIT_ROWS;
+    rows = (j0 + Cfg::UNIT_ROWS <= 55) ? Cfg::UNIT_ROWS : 55 - j0;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ strip producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bfull_bar, Cfg::B_BYTES);           // filter bank: constant, fetched once
+      bulk_load_1d(b_base, p.w_packed, Cfg::B_BYTES, bfull_bar);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        int n, j0, rows;
+        unit_geom(unit, n, j0, rows);
+        for (int r = 2 * j0; r <= 2 * (j0 + rows); ++r) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), 7u * 1920u);
+          for (int ky = 0; ky < 7; ++ky)
+            tma_load_5d(a_base + stage * Cfg::A_STAGE + ky * Cfg::STRIP, &tmA, full_bar(stage), 0, 0, r, n, ky);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer: 14 x (128 x 64 x 16) per stem row
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+      mbar_wait(bfull_bar, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        int n, j0, rows;
+        unit_geom(unit, n, j0, rows);
+        for (int r = 0; r <= 2 * rows; ++r, ++local) {
+          const int acc = local & 1;
+          mbar_wait(tempty_bar(acc), ((local >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * 64;
+#pragma unroll
+          for (int ky = 0; ky < 7; ++ky) {
+            // A: output pixel ox reads the 32 elements starting 16 B * ox into the strip (core matrices 8 rows x 16 B,
+            // rows 16 B apart: LBO = 16 B to the next K core, SBO = 128 B to the next 8 rows)
+            const uint64_t adesc = umma_desc_nosw(a_base + stage * Cfg::A_STAGE + ky * Cfg::STRIP, 16u, 128u);
+            // B: packed core matrices [k/8][n/8]: LBO (next k core) = 64/8 * 128 B, SBO (next n core) = 128 B
+            const uint64_t bdesc = umma_desc_nosw(b_base + ky * 4096, 64u * 16u, 128u);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              umma_bf16(d_tmem, adesc + 2u * k, bdesc + 128u * k, idesc, (ky | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          umma_commit(tfull_bar(acc));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue: bias + ReLU -> row ring -> 3x3/2 max-pool
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;                 // which 32 of the 64 output channels
+    const int px = q * 32 + lane;                    // stem pixel (accumulator row); 112..127 are junk rows
+    const int et = threadIdx.x - 128;                // 0..255
+    float bias[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bias[j] = __ldg(p.bias + grp * 32 + j);
+    int local = 0;
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      int n, j0, rows;
+      unit_geom(unit, n, j0, rows);
+      for (int r = 0; r <= 2 * rows; ++r, ++local) {
+        const int acc = local & 1;
+        mbar_wait(tfull_bar(acc), (local >> 1) & 1u);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + acc * 64 + grp * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));           // accumulator is free again
+        if (px < 112) {
+          const uint32_t row = ring_base + (local & 3) * Cfg::ROW + px * 128;   // ring position runs on across units
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = __uint_as_float(v[j * 8 + e * 2]) + bias[j * 8 + e * 2];
+              float b = __uint_as_float(v[j * 8 + e * 2 + 1]) + bias[j * 8 + e * 2 + 1];
+              a = a < 0.0f ? 0.0f : a;                           // NaN-propagating like torch.relu
+              b = b < 0.0f ? 0.0f : b;
+              h2[e] = __floats2bfloat162_rn(a, b);
+            }
+            st_shared_v4(row + (((grp * 4 + j) ^ (px & 7)) << 4), u);
+          }
+        }
+        named_bar_sync(1, 256);                                   // stem row r is complete in the ring
+        if (r >= 2 && (r & 1) == 0) {
+          // pooled row j = j0 + r/2 - 1 from stem rows r-2, r-1, r: 55 pixels x 8 chunks of 8 channels
+          const int j = j0 + (r >> 1) - 1;
+          __nv_bfloat16* orow = p.out + ((long long)(n * 55 + j) * 55) * 64;
+          for (int it = et; it < 55 * 8; it += 256) {
+            const int po = it >> 3, ch = it & 7;
+            uint4 m;
+            __nv_bfloat162* mm = reinterpret_cast<__nv_bfloat162*>(&m);
+            bool first = true;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const uint32_t rbase = ring_base + ((local - 2 + dy) & 3) * Cfg::ROW;
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                const int sp = 2 * po + dx;
+                uint4 u;
+                ld_shared_v4(rbase + sp * 128 + ((ch ^ (sp & 7)) << 4), u);
+                const __nv_bfloat162* uu = reinterpret_cast<const __nv_bfloat162*>(&u);
+                if (first) {
+                  m = u;
+                  first = false;
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) mm[e] = __hmax2_nan(mm[e], uu[e]);
+                }
+              }
+            }
+            *reinterpret_cast<uint4*>(orow + po * 64 + ch * 8) = m;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace avcer

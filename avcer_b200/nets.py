@@ -74,6 +74,7 @@ class VSNet:
         self.precision = precision
         self.device = torch.device(device)
         self.w = weights.pack_vs(state_dict, self.device, self.dtype)
+        self.fused_stem = True          # bf16: stem + max-pool in one kernel (False: two kernels, same bits)
 
     @property
     def input_layout(self) -> int:
@@ -109,12 +110,15 @@ class VSNet:
 
     def forward(self, x: torch.Tensor, taps: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         assert x.shape[1:] == (PAD_H, PAD, 4) and x.dtype == self.dtype
-        y = self.stem(x)
-        if taps is not None:
-            taps["stem"] = y
-        y = ops.maxpool3x3s2(y)
-        if taps is not None:
-            taps["pool"] = y
+        if taps is None and self.dtype == torch.bfloat16 and self.fused_stem:
+            y = ops.stem_pool(x, self.w["stem_packed"], self.w["stem"].bias)      # stem activation stays on chip
+        else:
+            y = self.stem(x)
+            if taps is not None:
+                taps["stem"] = y
+            y = ops.maxpool3x3s2(y)
+            if taps is not None:
+                taps["pool"] = y
         for bi, blk in enumerate(self.w["blocks"]):
             identity = self._conv(y, blk["ds"], ops.ACT_NONE) if "ds" in blk else y
             t = self._conv(y, blk["conv1"], ops.ACT_RELU)

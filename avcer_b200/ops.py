@@ -18,7 +18,7 @@ from ._lib import check as _check
 __all__ = [
     "F32", "BF16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "dtype_code", "torch_dtype", "contract", "conv2d_nhwc",
     "linear", "preprocess", "fuse_compound", "weight_search_confusion", "softmax7", "window_to_frame_mean", "gather_rows", "maxpool3x3s2",
-    "avgpool", "small_linear", "lstm_cell", "audio_normalize_windows", "w2v_conv0_ln_gelu", "layernorm", "add_rows",
+    "stem_pool", "avgpool", "small_linear", "lstm_cell", "audio_normalize_windows", "w2v_conv0_ln_gelu", "layernorm", "add_rows",
     "attention", "maxpool1d5_relu", "avgpool1d_relu", "cast",
 ]
 
@@ -262,6 +262,17 @@ def gather_rows(src: torch.Tensor, index: Optional[torch.Tensor], n_out: int, pe
 
 
 # ----------------------------------------------------------------------------------------- small layers
+def stem_pool(x: torch.Tensor, wt_packed: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """Fused ResNet stem + max-pool: x [n,232,240,4] bf16 zero-bordered crops -> [n,55,55,64] bf16."""
+    _cuda(x, "x")
+    n = x.shape[0]
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and tuple(x.shape[1:]) == (PAD_H, PAD_W, 4)
+    y = torch.empty((n, 55, 55, 64), device=x.device, dtype=torch.bfloat16)
+    with _Timed("contract_bf16", 2.0 * n * 112 * 112 * 64 * 147):        # 7x7x3 real taps (SURVEY.md section 8d)
+        _check(_lib.load().avcer_stem_pool(x.data_ptr(), wt_packed.data_ptr(), bias.data_ptr(), n, y.data_ptr(), _stream()))
+    return y
+
+
 def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
     n, h, w, c = x.shape
     y = torch.empty((n, (h - 3) // 2 + 1, (w - 3) // 2 + 1, c), device=x.device, dtype=x.dtype)

@@ -155,6 +155,13 @@ int avcer_gather_rows(const float* src, const int32_t* src_index, int64_t n_out,
 /* ------------------------------------------------------------------------------------------
  * Small layers of the VS / VD / A networks (channels-last).  `dtype` selects bf16 or fp32 storage.
  */
+/* ResNet-50 stem fused with its max-pool (bf16 only): Conv2dSame 7x7/2 with TF-"same" padding 2|3
+ * (architectures/video.py:63-90, :98-100) + folded BatchNorm (eps 1e-3) + ReLU (:116) + MaxPool2d(3, 2) without
+ * padding (:103, :117).  x_padded: zero-bordered NHWC4 crops [n, 232, 240, 4] (layout 1 of avcer_preprocess_u8);
+ * w_packed: the folded filter bank per filter row in UMMA core-matrix order [7][32/8][64/8][8][8] bf16 (28 KB);
+ * bias: [64] fp32; out: [n, 55, 55, 64] bf16.  Bit-identical to avcer_contract (stem geometry) followed by
+ * avcer_maxpool3x3s2; the 112x112x64 stem activation is never written to global memory. */
+int avcer_stem_pool(const void* x_padded, const void* w_packed, const float* bias, int n, void* out, void* stream);
 /* 3x3 stride-2 un-padded max pool, NHWC (architectures/video.py:103,117). */
 int avcer_maxpool3x3s2(const void* x, int n, int h, int w, int c, void* y, int dtype, void* stream);
 /* Global average pool NHWC -> [n, c] (video.py:124). */

@@ -110,3 +110,23 @@ def test_conv3x3_halo_kernel_matches_torch(cuda_lib, n, h, w, c, cout):
     finally:
         torch.backends.cudnn.allow_tf32 = prev
     assert (y.float() - ref).abs().max().item() < 0.04
+
+
+@pytest.mark.parametrize("n", [1, 5, 41])
+def test_fused_stem_pool_is_bit_identical_to_two_kernels(cuda_lib, n):
+    """avcer_stem_pool (stem activation kept on chip) must reproduce stem conv -> max-pool bit for bit, including
+    the unit seams (pooled rows 13|14, 27|28, 41|42), the last pooled row and NaN propagation."""
+    from avcer_b200 import nets, ops, synthetic as syn
+
+    net = nets.VSNet(syn.make_vs_state_dict(0, "spread"), "bf16", DEV)
+    crops = torch.from_numpy(syn.make_crops(3, n)).to(DEV)
+    x = net.alloc_input(n)
+    ops.preprocess(crops, n, x, net.input_layout)
+    if n == 5:
+        x[2, 100, 57, 1] = float("nan")          # one poisoned input pixel must poison the same pooled outputs
+    ref = ops.maxpool3x3s2(net.stem(x))
+    got = ops.stem_pool(x, net.w["stem_packed"], net.w["stem"].bias)
+    assert got.shape == ref.shape == (n, 55, 55, 64)
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+    if n == 5:
+        assert torch.isnan(got[2]).any() and not torch.isnan(got[[0, 1, 3, 4]]).any()

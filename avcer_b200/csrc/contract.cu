@@ -108,12 +108,6 @@ extern "C" int avcer_debug_set_trace(void* buf) {
   return 0;
 }
 
-static int g_debug = 0;
-extern "C" int avcer_debug_set_flags(int flags) {
-  g_debug = flags;
-  return 0;
-}
-
 static int num_sms_cached() {
   static int n = 0;
   if (n == 0) {
@@ -257,7 +251,6 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   p.act = d->act;
   p.res_after_act = d->res_after_act;
   p.trace = g_trace;
-  p.debug = g_debug;
   if (p.num_tiles == 0) return 0;
 
   const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;

@@ -52,7 +52,6 @@ struct TcGemmParams {
   void* out;                          // fp32 output (direct-store mode)
   int act;
   int res_after_act;     // 0: act(acc + bias + res)   1: act(acc + bias) + res
-  int debug;                   // development aid (avcer_debug_set_flags): epilogue steps to skip, 0 in production
   unsigned long long* trace;   // development aid (avcer_debug_set_trace): per-tile clock64 stamps of the first CTAs, else nullptr
 };
 

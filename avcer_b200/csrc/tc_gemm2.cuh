@@ -277,7 +277,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tma_load_5d(rslab + (j & 1) * Cfg::SLAB, &tmR, rbar + 8u * (j & 1), col0, row0, 0, 0, 0);
       }
     };
-    if (MODE == OUT_TMA_RES && lane == 0 && !(p.debug & 32)) { issue_res(0); issue_res(1); }
+    if (MODE == OUT_TMA_RES && lane == 0) { issue_res(0); issue_res(1); }
     const uint32_t row_off = lane * 128;
     int j = 0;
     for (int local = 0; local < my_tiles; ++local) {
@@ -299,14 +299,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (threadIdx.x == 128 && h == 0) trace_stamp(p, local, 8);
         uint32_t v[2][32];
         const uint32_t taddr = tmem_base + acc * BN + hf * 64 + (static_cast<uint32_t>(q * 32) << 16);
-        if (!(p.debug & 8)) {
-          tmem_ld_32x32(taddr, v[0]);
-          tmem_ld_32x32(taddr + 32, v[1]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { v[0][i] = i; v[1][i] = i; }
-        }
-        if (MODE == OUT_TMA_RES && !(p.debug & 32)) mbar_wait(rbar + 8u * (j & 1), (j >> 1) & 1u);
+        tmem_ld_32x32(taddr, v[0]);
+        tmem_ld_32x32(taddr + 32, v[1]);
+        if (MODE == OUT_TMA_RES) mbar_wait(rbar + 8u * (j & 1), (j >> 1) & 1u);
         if (threadIdx.x == 128 && h == 0) trace_stamp(p, local, 9);
         tmem_ld_wait();
         if (threadIdx.x == 128 && h == 0) trace_stamp(p, local, 10);
@@ -316,7 +311,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[cc][i]);
           const int co = col0 + cc * 32;
-          if (p.bias != nullptr && co < p.Cout && !(p.debug & 1)) {
+          if (p.bias != nullptr && co < p.Cout) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co + i));
@@ -336,7 +331,6 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (p.res_after_act) apply_act();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              if (p.debug & 2) break;
               uint4 u;
               ld_shared_v4(rbuf + row_off + (((cc * 4 + i) ^ (lane & 7)) << 4), u);
               const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -357,7 +351,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
             for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[i * 8 + e * 2], f[i * 8 + e * 2 + 1]);
-            if (!(p.debug & 4)) st_shared_v4(cbuf + row_off + (((cc * 4 + i) ^ (lane & 7)) << 4), u);
+            st_shared_v4(cbuf + row_off + (((cc * 4 + i) ^ (lane & 7)) << 4), u);
           }
         }
         if (threadIdx.x == 128 && h == 0) trace_stamp(p, local, 11);
@@ -365,9 +359,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
         if (threadIdx.x == 128 && h == 0) trace_stamp(p, local, 12);
         if (lane == 0) {
-          if (col0 < p.Cout && !(p.debug & 16)) tma_store_5d(&tmC, cbuf, col0, row0, 0, 0, 0);
+          if (col0 < p.Cout) tma_store_5d(&tmC, cbuf, col0, row0, 0, 0, 0);
           bulk_commit_group();
-          if (MODE == OUT_TMA_RES && !(p.debug & 32)) issue_res(j + 2);         // every lane has consumed this residual slab (syncwarp above)
+          if (MODE == OUT_TMA_RES) issue_res(j + 2);         // every lane has consumed this residual slab (syncwarp above)
         }
         if (threadIdx.x == 128 && h < 2) trace_stamp(p, local, 13 + h);
       }

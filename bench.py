@@ -240,10 +240,10 @@ def main():
     tc = kern.get("contract_bf16") or kern.get("contract_f32")
     if tc:
         ach = tc["work"] / (tc["ms"] / 1e3) / 1e12
-        roofline = {"kernel": "tc_gemm_kernel (tcgen05 implicit GEMM: all VS/VD/A contractions)", "bound": "tensor", "achieved": ach,
+        roofline = {"kernel": "tcgen05 contraction kernels (tc_gemm / tc_gemm2 implicit GEMM, conv3x3 halo conv, fused stem+pool: all VS/VD/A contractions)", "bound": "tensor", "achieved": ach,
                     "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
                     "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)", "traffic": traffic,
-                    "traffic_note": "mean DRAM bytes per tc_gemm launch from profiles/r01_kernel_digest.json (ncu, 1-clip run of this bench)",
+                    "traffic_note": "mean DRAM bytes per launch of that kernel family from profiles/r01_kernel_digest.json (ncu, 1-clip run of this bench)",
                     "launches_per_step": tc["launches"], "avg_launch_us": 1e3 * tc["ms"] / tc["launches"],
                     "share_of_step": tc["ms"] / profiled_step_ms, "algorithmic_flop_per_step": tc["work"], "how": prof_note}
     extra = {}

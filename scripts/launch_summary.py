@@ -12,7 +12,10 @@ for r in data:
     v = float(r[vi].replace(',', '')); u = r[ui]
     if u == 'ns': v /= 1000
     elif u == 'ms': v *= 1000
-    seq.append((re.sub(r'\(.*', '', r[ki]).replace('void avcer::', '').replace('avcer::', ''), v))
+    name = re.sub(r'\(.*', '', r[ki]).replace('void avcer::', '').replace('avcer::', '')
+    if name.startswith(('conv3x3_kernel', 'stem_pool_kernel')):   # tcgen05 contraction kernels like tc_gemm*
+        name = 'tc_gemm:' + name
+    seq.append((name, v))
 agg = collections.defaultdict(lambda: [0, 0.0])
 for n, t in seq:
     agg[n[:60]][0] += 1; agg[n[:60]][1] += t

@@ -1,8 +1,9 @@
-"""A handful of representative hot-path launches for `ncu --set full` (one launch of each after warm-up)."""
+"""Representative hot-path launches for `ncu --set full` (two launches each; profile with
+-k regex:'tc_gemm|conv3x3|stem_pool|attention_tc|preprocess_identity|fuse_compound|w2v_conv0|layernorm')."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from avcer_b200 import ops, _lib
+from avcer_b200 import nets, ops, _lib, synthetic as syn, get_weights_matrices as gwm
 
 _lib.require_device()
 dev = "cuda"
@@ -22,22 +23,30 @@ def conv(n, h, w, cin, cout, k, stride=1, res=False, reps=2):
     torch.cuda.synchronize()
 
 
-# VS layers at batch 256 (kernel ids in the order launched; two launches each, profile the second)
-conv(B, 14, 14, 256, 256, 3)                 # l3.c2  3x3 (MMA bound)
-conv(B, 55, 55, 64, 256, 1, res=True)        # l1.c3  1x1 + residual (HBM bound)
-conv(B, 55, 55, 64, 64, 3)                   # l1.c2  3x3, N = 64
-# audio: ff1 GEMM with GELU, 32 windows
-x = torch.randn(32 * 199, 1024, device=dev).to(bf); w = (torch.randn(4096, 1024, device=dev) / 32).to(bf); b = torch.zeros(4096, device=dev)
+# VS layers at batch 256 (two launches each)
+net = nets.VSNet(syn.make_vs_state_dict(0, "default"), "bf16", dev)
+crops = torch.randint(0, 256, (1024, 224, 224, 3), dtype=torch.uint8, device=dev)
+xin = net.alloc_input(1024)
+for _ in range(2):
+    ops.preprocess(crops, 1024, xin, 1)                                  # K1 at 1024 crops
+for _ in range(2):
+    ops.stem_pool(xin[:B], net.w["stem_packed"], net.w["stem"].bias)     # fused stem + pool
+conv(B, 55, 55, 64, 64, 3)                   # l1.c2  halo 3x3, resident weights
+conv(B, 28, 28, 128, 128, 3)                 # l2.c2  halo 3x3, streamed weights
+conv(B, 14, 14, 256, 256, 3)                 # l3.c2  two-SM implicit GEMM (MMA bound)
+conv(B, 55, 55, 64, 256, 1, res=True)        # l1.c3  flat epilogue + residual (HBM bound)
+conv(B, 14, 14, 256, 1024, 1, res=True)      # l3.c3  flat epilogue + residual
+conv(B, 55, 55, 256, 64, 1)                  # l1.c1  64-wide tiles (HBM bound)
+# audio: FFN GEMM with GELU and attention, 64 windows
+x = torch.randn(64 * 199, 1024, device=dev).to(bf); w = (torch.randn(4096, 1024, device=dev) / 32).to(bf); b = torch.zeros(4096, device=dev)
 for _ in range(2):
     ops.linear(x, w, b, act=ops.ACT_GELU)
-# K1 and K4 at full size
-crops = torch.randint(0, 256, (1024, 224, 224, 3), dtype=torch.uint8, device=dev)
-dst = torch.zeros((1024, 232, 232, 4), device=dev, dtype=bf)
+qkv = torch.randn(64 * 199, 3072, device=dev).to(bf)
 for _ in range(2):
-    ops.preprocess(crops, 1024, dst, 1)
+    ops.attention(qkv, 64, 199, 16, 64, 0.125)
+# K4 at 1.5 M frames
 n = 1_500_000
 ps = [torch.softmax(torch.randn(n, 7, device=dev), 1).contiguous() for _ in range(3)]
-from avcer_b200 import get_weights_matrices as gwm
 for _ in range(2):
     ops.fuse_compound(ps[0], ps[1], ps[2], gwm.class_weights(gwm.weights_3), [1, 1, 1], False, True)
 torch.cuda.synchronize()

@@ -19,7 +19,8 @@ for r in rows[hi + 1:]:
         d[r[mi].split('.')[0]] = v * mult
 agg = collections.defaultdict(lambda: {"launches": 0, "us": 0.0, "dram_read": 0.0, "dram_write": 0.0})
 for d in per.values():
-    fam = "tc_gemm_kernel" if d["name"].startswith("tc_gemm") else d["name"].split('<')[0]
+    # one family for every tcgen05 contraction kernel (generic one- / two-SM GEMM, halo 3x3 conv, fused stem + pool)
+    fam = "tc_gemm_kernel" if d["name"].startswith(("tc_gemm", "conv3x3_kernel", "stem_pool_kernel")) else d["name"].split('<')[0]
     a = agg[fam]
     a["launches"] += 1; a["us"] += d.get("us", 0); a["dram_read"] += d.get("dram__bytes_read", 0); a["dram_write"] += d.get("dram__bytes_write", 0)
 tot = sum(a["us"] for a in agg.values())

@@ -15,8 +15,7 @@ NAMES = ["prod.begin", "prod.end", "mma.begin", "mma.acc_free", "mma.first_full"
          "epi.h0", "epi.h1", "epi.h2", "epi.h3", "epi.release", "res.last_issue"]
 
 
-def run(name, n, h, w, cin, cout, k, stride=1, res=False, flags=0):
-    lib.avcer_debug_set_flags(flags)
+def run(name, n, h, w, cin, cout, k, stride=1, res=False):
     x = torch.randn(n, h, w, cin, device=dev).to(bf)
     wt = (torch.randn(cout, k * k * cin, device=dev) / (cin * k * k) ** 0.5).to(bf)
     b = torch.randn(cout, device=dev)
@@ -50,35 +49,8 @@ def run(name, n, h, w, cin, cout, k, stride=1, res=False, flags=0):
             print(f"   steady-state cycles per tile (epi.release spacing): {per:.0f}")
 
 
-run("l1.c3 1x1 64->256 +res (55x55) flags=63", 256, 55, 55, 64, 256, 1, res=True, flags=63)
-run("l1.c3 1x1 64->256 +res (55x55) flags=34", 256, 55, 55, 64, 256, 1, res=True, flags=34)
-run("l3.c3 1x1 256->1024 +res flags=63", 256, 14, 14, 256, 1024, 1, res=True, flags=63)
-lib.avcer_debug_set_flags(0)
-if len(sys.argv) > 1: sys.exit(0)
+run("l3.c3 1x1 256->1024 +res (14x14)", 256, 14, 14, 256, 1024, 1, res=True)
+run("l3.0.ds 1x1 s2 512->1024 (28->14)", 256, 28, 28, 512, 1024, 1, stride=2)
+run("l1.c3 1x1 64->256 +res (55x55)", 256, 55, 55, 64, 256, 1, res=True)
 
-# which epilogue step costs what: skip steps one at a time (results are garbage; timing only)
-def timed_flags(n, h, w, cin, cout, res):
-    x = torch.randn(n, h, w, cin, device=dev).to(bf)
-    wt = (torch.randn(cout, cin, device=dev) / cin ** 0.5).to(bf)
-    b = torch.randn(cout, device=dev)
-    r = torch.randn(n, h, w, cout, device=dev).to(bf) if res else None
-    out = torch.empty(n, h, w, cout, device=dev, dtype=bf)
-    for flags, what in ((0, "baseline"), (1, "no bias"), (2, "no residual LDS"), (4, "no STS"), (8, "no LDTM"), (16, "no TMA store"),
-                        (32, "no residual TMA"), (34, "no residual at all"), (63, "nothing")):
-        lib.avcer_debug_set_flags(flags)
-        gr = torch.cuda.CUDAGraph()
-        ops.conv2d_nhwc(x, wt, b, kh=1, kw=1, residual=r, act=ops.ACT_RELU, out=out)
-        torch.cuda.synchronize()
-        with torch.cuda.graph(gr):
-            for _ in range(10):
-                ops.conv2d_nhwc(x, wt, b, kh=1, kw=1, residual=r, act=ops.ACT_RELU, out=out)
-        gr.replay(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
-        print(f"   flags {flags:2d} ({what:20s}): {e0.elapsed_time(e1) * 100:.1f} us per launch")
-    lib.avcer_debug_set_flags(0)
-
-print("== l3.c3 shape, skipping epilogue steps"); timed_flags(256, 14, 14, 256, 1024, True)
-print("== l1.c3 shape, skipping epilogue steps"); timed_flags(256, 55, 55, 64, 256, True)
-print("== l3.1.c1 shape (no residual)"); timed_flags(256, 14, 14, 1024, 256, False)
 print("trace done")

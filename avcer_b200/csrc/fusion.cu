@@ -93,65 +93,52 @@ __device__ __forceinline__ void fuse_one(const TIn (&a)[7], const TIn (&b)[7], c
   lab[3] = compound_argmax<TC>(x[2], p);
 }
 
-// Warp-cooperative streaming pass.  A warp owns 32*FPT consecutive frames (FPT = 4 for f32, 2 for f64 inputs):
-// each of the three probability streams is fetched with seven fully coalesced 128-bit loads per lane (one
-// contiguous 3584-byte span per stream), staged in a warp-private shared-memory tile (conflict-free both ways,
-// __syncwarp only -- no block barrier), then every lane finishes its FPT frames and the labels leave as
-// coalesced 128-bit stores.
+// Warp-cooperative streaming pass.  A warp owns 32*FPT consecutive frames per iteration (FPT = 4 for f32, 2 for f64
+// inputs): the three probability streams are copied global -> shared with fully coalesced 16-byte cp.async (one
+// contiguous 3584-byte span per stream, no register staging), then lane l finishes frames l, l+32, ... of the chunk,
+// reading its 7 values per stream with a 7-word lane stride (conflict-free) and writing its labels as coalesced 8-byte
+// stores.  Keeping the chunk in shared memory instead of registers (the first version held 84 staging + 84 fp64
+// registers per lane: 198 registers, 8 warps per SM, fp64 pipe 30 % busy, latency-bound) lets 5 blocks share an SM.
 template <typename TIn, typename TC>
-__global__ void __launch_bounds__(FUSE_THREADS)
+__global__ void __launch_bounds__(FUSE_THREADS, 5)
 fuse_compound_kernel(const TIn* __restrict__ pvs, const TIn* __restrict__ pvd, const TIn* __restrict__ pa,
                      long long n, const FuseParams p, long long* __restrict__ labels) {
-  constexpr int FPT = 16 / sizeof(TIn);            // frames per lane
+  constexpr int FPT = 16 / sizeof(TIn);            // frames per lane and iteration
   constexpr int NV = 7;                            // 16-byte vectors per lane per stream
   constexpr int WARPS = FUSE_THREADS / 32;
-  __shared__ uint4 tile[WARPS][32 * NV];       // one stream at a time: 3.5 KB per warp
+  __shared__ uint4 tile[WARPS][3][32 * NV];        // 10.5 KB per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long groups = n / (32 * FPT);         // full warp-chunks
   const TIn* src[3] = {pvs, pvd, pa};
   for (long long g = (long long)blockIdx.x * WARPS + warp; g < groups; g += (long long)gridDim.x * WARPS) {
     const long long f0 = g * 32 * FPT;
-    uint4 v[3][NV];
 #pragma unroll
-    for (int m = 0; m < 3; ++m)
+    for (int m = 0; m < 3; ++m) {
+      const uint4* gsrc = reinterpret_cast<const uint4*>(src[m] + f0 * 7);
 #pragma unroll
-      for (int k = 0; k < NV; ++k) v[m][k] = __ldg(reinterpret_cast<const uint4*>(src[m] + f0 * 7) + lane + 32 * k);
-#pragma unroll
-    for (int m = 0; m < 3; ++m) {          // lane-strided (coalesced) order -> frame-major order, through the tile
-#pragma unroll
-      for (int k = 0; k < NV; ++k) tile[warp][lane + 32 * k] = v[m][k];
-      __syncwarp();
-#pragma unroll
-      for (int k = 0; k < NV; ++k) v[m][k] = tile[warp][lane * NV + k];
-      __syncwarp();
+      for (int k = 0; k < NV; ++k) {
+        const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(&tile[warp][m][lane + 32 * k]));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gsrc + lane + 32 * k) : "memory");
+      }
     }
-    long long lab[FPT][4];
-#pragma unroll
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+#pragma unroll 1
     for (int j = 0; j < FPT; ++j) {
+      const int fi = j * 32 + lane;                // frame inside the chunk
       TIn a[7], b[7], c[7];
 #pragma unroll
       for (int k = 0; k < 7; ++k) {
-        a[k] = reinterpret_cast<const TIn*>(&v[0][0])[j * 7 + k];
-        b[k] = reinterpret_cast<const TIn*>(&v[1][0])[j * 7 + k];
-        c[k] = reinterpret_cast<const TIn*>(&v[2][0])[j * 7 + k];
+        a[k] = reinterpret_cast<const TIn*>(&tile[warp][0][0])[fi * 7 + k];
+        b[k] = reinterpret_cast<const TIn*>(&tile[warp][1][0])[fi * 7 + k];
+        c[k] = reinterpret_cast<const TIn*>(&tile[warp][2][0])[fi * 7 + k];
       }
-      fuse_one<TIn, TC>(a, b, c, p, lab[j]);
+      long long lab[4];
+      fuse_one<TIn, TC>(a, b, c, p, lab);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) labels[s * n + f0 + fi] = lab[s];
     }
-    const long long fl = f0 + (long long)lane * FPT;
-    if ((n & 1) == 0) {              // every label row starts 16-byte aligned
-#pragma unroll
-      for (int s = 0; s < 4; ++s)
-#pragma unroll
-        for (int j = 0; j < FPT; j += 2) {
-          longlong2 o = make_longlong2(lab[j][s], lab[j + 1][s]);
-          *reinterpret_cast<longlong2*>(labels + s * n + fl + j) = o;
-        }
-    } else {
-#pragma unroll
-      for (int s = 0; s < 4; ++s)
-#pragma unroll
-        for (int j = 0; j < FPT; ++j) labels[s * n + fl + j] = lab[j][s];
-    }
+    __syncwarp();                                  // the chunk is consumed: the next cp.async may overwrite it
   }
   // tail frames (n % (32*FPT)) one per thread, by block 0
   const long long tail0 = groups * 32 * FPT;

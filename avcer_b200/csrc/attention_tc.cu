@@ -182,7 +182,11 @@ static int launch_attention_tc(const void* qkv, int n, int t, int heads, float s
   return check_launch("attention_tc_kernel");
 }
 
+int attention_tc5(const void* qkv, int n, int t, int heads, float scale, void* out, cudaStream_t st);   // contract.cu (tcgen05)
+
 int attention_tc(const void* qkv, int n, int t, int heads, int dh, float scale, void* out, cudaStream_t st) {
+  static const int att5 = getenv("AVCER_ATT5") ? atoi(getenv("AVCER_ATT5")) : 1;
+  if (att5 != 0 && dh == 64 && t <= ATT_MAXT) return attention_tc5(qkv, n, t, heads, scale, out, st);
   AVCER_REQUIRE(t >= 1 && t <= ATT_MAXT, "attention(bf16): T=%d exceeds the on-chip limit %d", t, ATT_MAXT);
   AVCER_REQUIRE(n <= 65535, "attention: at most 65535 windows per call");
   if (dh == 64) return launch_attention_tc<64>(qkv, n, t, heads, scale, out, st);

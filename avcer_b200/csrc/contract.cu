@@ -5,6 +5,7 @@
 #include "tc_gemm2.cuh"
 #include "conv3x3.cuh"
 #include "stem_pool.cuh"
+#include "attention_tc5.cuh"
 
 #include <cudaTypedefs.h>
 #include <mutex>
@@ -367,6 +368,39 @@ static int stem_pool_tc(const void* x, const void* w_packed, const float* bias, 
   if (g > p.units) g = p.units;
   launch_pdl(stem_pool_kernel, g, StemPoolCfg::THREADS, StemPoolCfg::SMEM, st, ta, p);
   return check_launch("stem_pool_kernel");
+}
+
+// ------------------------------------------------------------------ tcgen05 attention (bf16, head dim 64, T <= 208)
+int attention_tc5(const void* qkv, int n, int t, int heads, float scale, void* out, cudaStream_t st) {
+  using Cfg = Att5Cfg;
+  AVCER_REQUIRE(t >= 1 && t <= Cfg::MAXT, "attention(tcgen05): T=%d exceeds %d", t, Cfg::MAXT);
+  AVCER_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "attention(tcgen05): qkv / out must be 16-byte aligned");
+  if (n == 0) return 0;
+  Att5Params p{};
+  p.n = n; p.t = t; p.heads = heads;
+  p.npad = (t + 15) / 16 * 16;
+  p.mtiles = (t + 127) / 128;
+  p.items = n * heads * p.mtiles;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  CUtensorMap tq, tkv;
+  const uint64_t cols = (uint64_t)3 * heads * 64;
+  uint64_t dims[2] = {cols, (uint64_t)n * t};
+  uint64_t strides[1] = {cols * 2};
+  uint32_t boxq[2] = {64u, 128u};
+  uint32_t boxkv[2] = {64u, (uint32_t)Cfg::MAXT};
+  if (encode_map(&tq, qkv, 2, dims, strides, boxq, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  if (encode_map(&tkv, qkv, 2, dims, strides, boxkv, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AVCER_CUDA(cudaFuncSetAttribute(attention_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_done = true;
+  }
+  int g = num_sms();
+  if (g > p.items) g = p.items;
+  launch_pdl(attention_tc5_kernel, g, Cfg::THREADS, Cfg::SMEM, st, tq, tkv, p);
+  return check_launch("attention_tc5_kernel");
 }
 
 // ------------------------------------------------------------------ SIMT fp32 path

@@ -68,13 +68,16 @@ def test_pointwise_conv_equals_flat_gemm(cuda_lib):
 
 
 @pytest.mark.parametrize("heads,dh", [(16, 64), (32, 32)])
-@pytest.mark.parametrize("t", [199, 208, 113, 50, 1])
+@pytest.mark.parametrize("t", [199, 208, 129, 128, 113, 50, 17, 1])
 @pytest.mark.parametrize("dtype", [BF, torch.float32])
 def test_attention_matches_torch(cuda_lib, heads, dh, t, dtype):
+    """bf16, head dim 64: tcgen05 kernel (attention_tc5.cuh: Q K^T and P V on the 5th-gen tensor cores, V as an MN-major
+    operand); bf16, head dim 32: mma.sync kernel; fp32: SIMT kernel.  T covers one / two 128-row query tiles, partial
+    key chunks (T % 64, T % 16 != 0) and more work items than SMs."""
     from avcer_b200 import ops
 
     torch.manual_seed(t * heads)
-    n = 3
+    n = 3 if t < 199 else 11
     qkv = (torch.randn(n * t, 3 * heads * dh, device=DEV) * 1.5).to(dtype)
     scale = dh ** -0.5
     out = ops.attention(qkv, n, t, heads, dh, scale)

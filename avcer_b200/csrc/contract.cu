@@ -381,7 +381,7 @@ int attention_tc5(const void* qkv, int n, int t, int heads, float scale, void* o
   p.n = n; p.t = t; p.heads = heads;
   p.npad = (t + 15) / 16 * 16;
   p.mtiles = (t + 127) / 128;
-  p.items = n * heads * p.mtiles;
+  p.units = n * heads;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = static_cast<__nv_bfloat16*>(out);
   CUtensorMap tq, tkv;
@@ -398,7 +398,7 @@ int attention_tc5(const void* qkv, int n, int t, int heads, float scale, void* o
     attr_done = true;
   }
   int g = num_sms();
-  if (g > p.items) g = p.items;
+  if (g > p.units) g = p.units;
   launch_pdl(attention_tc5_kernel, g, Cfg::THREADS, Cfg::SMEM, st, tq, tkv, p);
   return check_launch("attention_tc5_kernel");
 }

@@ -26,6 +26,18 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return 0.5f * x * (1.0f + copysignf(e, x));
 }
 
+// (a0, a1) += (b0, b1) as ONE packed fp32x2 instruction (sm_100 FADD2; each lane rounds like add.rn.f32).  Epilogues
+// are bound by instruction issue on the four schedulers, so halving the add count is a direct win.
+__device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb;\n\t"
+      "mov.b64 ra, {%0, %1};\n\t"
+      "mov.b64 rb, {%2, %3};\n\t"
+      "add.rn.f32x2 ra, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -9,6 +9,15 @@ namespace avcer {
 constexpr int ACT_GELU_L = AVCER_ACT_GELU;
 
 template <typename T> __device__ __forceinline__ float gelu_for(float x) { return sizeof(T) == 2 ? gelu_erf_fast(x) : gelu_erf(x); }
+// GELU of a pair: packed fp32x2 evaluation where the result is stored as bf16, libdevice erff in fp32 mode
+template <typename T> __device__ __forceinline__ void gelu_pair(float& a, float& b) {
+  if (sizeof(T) == 2) {
+    gelu_erf_fast2(a, b);
+  } else {
+    a = gelu_erf(a);
+    b = gelu_erf(b);
+  }
+}
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -284,7 +293,9 @@ w2v_conv0_kernel(const float* __restrict__ x, int n, int t_in, int t_out, const 
         if (u2 == 1 && !two) break;
         float o[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = gelu_for<T>((v[u2][4 * q + e] - mean[u2]) * rstd[u2] * ga[e] + ba[e]);
+        for (int e = 0; e < 4; ++e) o[e] = (v[u2][4 * q + e] - mean[u2]) * rstd[u2] * ga[e] + ba[e];
+        gelu_pair<T>(o[0], o[1]);
+        gelu_pair<T>(o[2], o[3]);
         if (sizeof(T) == 2) {
           uint2 u;
           __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
@@ -342,9 +353,10 @@ layernorm_kernel(const T* __restrict__ x, long long rows, long long ldx, const T
     Vec8<float>::load(g + c0, gg);
     Vec8<float>::load(b + c0, bb);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float t = (v[j][e] - mean) * rstd * gg[e] + bb[e];
-      o[e] = act == ACT_GELU_L ? gelu_for<T>(t) : t;
+    for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mean) * rstd * gg[e] + bb[e];
+    if (act == ACT_GELU_L) {
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) gelu_pair<T>(o[e], o[e + 1]);
     }
     Vec8<T>::store(y + row * ldy + c0, o);
   }

@@ -285,7 +285,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 32; ++j) f[j] = f[j] < 0.0f ? 0.0f : f[j];   // NaN-propagating like torch.relu
         } else if (p.act == ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = (MODE == OUT_DIRECT_F32) ? gelu_erf(f[j]) : gelu_erf_fast(f[j]);
+          for (int j = 0; j < 32; j += 2) {
+            if (MODE == OUT_DIRECT_F32) { f[j] = gelu_erf(f[j]); f[j + 1] = gelu_erf(f[j + 1]); }
+            else gelu_erf_fast2(f[j], f[j + 1]);
+          }
         }
       };
 

@@ -350,7 +350,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int i = 0; i < 32; ++i) f[i] = f[i] < 0.0f ? 0.0f : f[i];
               } else if (p.act == ACT_GELU) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = gelu_erf_fast(f[i]);
+                for (int i = 0; i < 32; i += 2) gelu_erf_fast2(f[i], f[i + 1]);
               }
             };
             if (MODE == OUT_TMA_RES) {
@@ -444,7 +444,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int j = 0; j < 32; ++j) f[j] = f[j] < 0.0f ? 0.0f : f[j];
           } else if (p.act == ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
+            for (int j = 0; j < 32; j += 2) gelu_erf_fast2(f[j], f[j + 1]);
           }
         };
         const int j0 = grp * 4;

@@ -256,15 +256,18 @@ w2v_conv0_kernel(const float* __restrict__ x, int n, int t_in, int t_out, const 
     for (int q = 0; q < 4; ++q) {
       const int c0 = 128 * q + 4 * lane;
       const float4 bias = *reinterpret_cast<const float4*>(&sb[c0]);
-      float4 a0 = bias, a1 = bias;
+      // packed fp32x2 FMAs (two channels per instruction; per-lane arithmetic identical to fmaf)
+      uint64_t a0l = pack_f32x2(bias.x, bias.y), a0h = pack_f32x2(bias.z, bias.w), a1l = a0l, a1h = a0h;
 #pragma unroll
       for (int k = 0; k < 10; ++k) {
         const float4 wk = *reinterpret_cast<const float4*>(&sw[k][c0]);
-        a0.x = fmaf(wk.x, xv[k], a0.x); a0.y = fmaf(wk.y, xv[k], a0.y); a0.z = fmaf(wk.z, xv[k], a0.z); a0.w = fmaf(wk.w, xv[k], a0.w);
-        a1.x = fmaf(wk.x, xv[k + 5], a1.x); a1.y = fmaf(wk.y, xv[k + 5], a1.y); a1.z = fmaf(wk.z, xv[k + 5], a1.z); a1.w = fmaf(wk.w, xv[k + 5], a1.w);
+        const uint64_t wl = pack_f32x2(wk.x, wk.y), wh = pack_f32x2(wk.z, wk.w);
+        const uint64_t x0 = pack_f32x2(xv[k], xv[k]), x1 = pack_f32x2(xv[k + 5], xv[k + 5]);
+        a0l = fma_f32x2(wl, x0, a0l); a0h = fma_f32x2(wh, x0, a0h);
+        a1l = fma_f32x2(wl, x1, a1l); a1h = fma_f32x2(wh, x1, a1h);
       }
-      v[0][4 * q] = a0.x; v[0][4 * q + 1] = a0.y; v[0][4 * q + 2] = a0.z; v[0][4 * q + 3] = a0.w;
-      v[1][4 * q] = a1.x; v[1][4 * q + 1] = a1.y; v[1][4 * q + 2] = a1.z; v[1][4 * q + 3] = a1.w;
+      unpack_f32x2(a0l, v[0][4 * q], v[0][4 * q + 1]); unpack_f32x2(a0h, v[0][4 * q + 2], v[0][4 * q + 3]);
+      unpack_f32x2(a1l, v[1][4 * q], v[1][4 * q + 1]); unpack_f32x2(a1h, v[1][4 * q + 2], v[1][4 * q + 3]);
     }
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll

@@ -136,7 +136,7 @@ def main():
     ap.add_argument("--fps", type=int, default=25)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--a-batch", type=int, default=64)
-    ap.add_argument("--vs-batch", type=int, default=256)
+    ap.add_argument("--vs-batch", type=int, default=1024)     # crops per VS forward inside the pipeline (config 2 below stays at 256)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()
@@ -150,7 +150,7 @@ def main():
                             f"({n_frames} crops 224x224 + {n_samples} audio samples, {n_windows} windows of 4 s / step 0.5 s per clip), "
                             "VS ResNet-50 + VD LSTM + A wav2vec2-L12 (8 classes) + fusion Rule 1 with the AV-8cl weight matrix",
                 "clips_per_gpu": args.clips_per_gpu, "frames_per_clip": n_frames, "windows_per_clip": n_windows,
-                "parallelism": f"clip-sharded x{args.gpus}", "l2_policy": "inputs (>=1.8 GB/step) larger than L2", "weights": "random-init, seeded"}
+                "vs_batch": args.vs_batch, "a_batch": args.a_batch, "parallelism": f"clip-sharded x{args.gpus}", "l2_policy": "inputs (>=1.8 GB/step) larger than L2", "weights": "random-init, seeded"}
     if args.impl == "reference":
         return run_reference_arm(args, workload)
 

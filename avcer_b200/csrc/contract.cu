@@ -151,7 +151,8 @@ static int conv3x3_tc(const avcer_contract_desc* d, cudaStream_t st) {
   const bool dense = d->a_dim[0] == C && d->a_dim[1] == W && d->a_dim[2] == H && d->a_dim[3] == NB && d->a_stride[0] == 1 &&
                      d->a_stride[1] == C && d->a_stride[2] == (int64_t)W * C && d->a_stride[3] == (int64_t)H * W * C &&
                      d->out_stride[0] == Cout && d->out_stride[1] == (int64_t)W * Cout && d->out_stride[2] == (int64_t)H * W * Cout;
-  if (!shape || !dense) return -1;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(d->a) | reinterpret_cast<uintptr_t>(d->wt) | reinterpret_cast<uintptr_t>(d->out)) & 15) == 0;
+  if (!shape || !dense || !aligned) return -1;       // the generic path validates and reports
   Conv3Params p{};
   p.H = H; p.W = W; p.NB = NB; p.C = C; p.Cout = Cout;
   p.P = W + 2;

@@ -175,6 +175,55 @@ preprocess_identity_kernel(const uint8_t* __restrict__ src, void* __restrict__ d
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Audio decode seam (reference: src/data/utils.py:49-60 convert_mp4_to_mp3 after its ffmpeg
+// call): interleaved int16 PCM -> float (1/32768) -> channel mean -> torchaudio's polyphase sinc resampler
+// (transforms.Resample defaults: a strided conv1d of the zero-padded signal with `nnew` filters of `taps` =
+// 2*width + orig coefficients; output sample f*nnew + j = sum_k bank[j][k] * x[f*orig + k - width]).
+// One CTA produces RS_FRAMES frames (RS_FRAMES*nnew outputs): the input span is converted once into shared memory,
+// thread j walks the taps with the bank stored tap-major ([taps][nnew]) so that a warp reads consecutive coefficients.
+constexpr int RS_FRAMES = 4;
+
+__device__ __forceinline__ float pcm_mono(const short* __restrict__ pcm, long long i, long long n, int ch) {
+  if (i < 0 || i >= n) return 0.f;
+  float s = 0.f;
+  for (int c = 0; c < ch; ++c) s += (float)pcm[i * ch + c] * (1.0f / 32768.0f);
+  return ch > 1 ? s / (float)ch : s;
+}
+
+__global__ void __launch_bounds__(256)
+pcm16_resample_kernel(const short* __restrict__ pcm, long long n, int ch, const float* __restrict__ bank, int orig, int nnew,
+                      int width, long long n_out, float* __restrict__ out) {
+  extern __shared__ float xs[];
+  const int taps = 2 * width + orig;
+  const long long f0 = (long long)blockIdx.x * RS_FRAMES;
+  const int span = (RS_FRAMES - 1) * orig + taps;
+  const long long base = f0 * orig - width;
+  for (int i = threadIdx.x; i < span; i += blockDim.x) xs[i] = pcm_mono(pcm, base + i, n, ch);
+  __syncthreads();
+  for (int j = threadIdx.x; j < nnew; j += blockDim.x) {
+    float acc[RS_FRAMES];
+#pragma unroll
+    for (int f = 0; f < RS_FRAMES; ++f) acc[f] = 0.f;
+    for (int k = 0; k < taps; ++k) {
+      const float c = __ldg(bank + (size_t)k * nnew + j);
+#pragma unroll
+      for (int f = 0; f < RS_FRAMES; ++f) acc[f] = fmaf(c, xs[f * orig + k], acc[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < RS_FRAMES; ++f) {
+      const long long o = (f0 + f) * nnew + j;
+      if (o < n_out) out[o] = acc[f];
+    }
+  }
+}
+
+__global__ void pcm16_mono_kernel(const short* __restrict__ pcm, long long n, int ch, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = pcm_mono(pcm, i, n, ch);
+}
+
 }  // namespace avcer
 
 using namespace avcer;
@@ -208,4 +257,32 @@ extern "C" int avcer_preprocess_u8(const uint8_t* src, const int64_t* src_offset
   else if (dst_layout == 1) preprocess_kernel<1><<<grid, 256, 0, st>>>(src, offs, src_h, src_w, maps, dst);
   else preprocess_kernel<2><<<grid, 256, 0, st>>>(src, offs, src_h, src_w, maps, dst);
   return check_launch("preprocess_kernel");
+}
+
+extern "C" int avcer_pcm16_resample(const int16_t* pcm, int64_t n, int channels, const float* bank_tap_major, int orig,
+                                    int nnew, int width, float* out, int64_t n_out, void* stream) {
+  AVCER_REQUIRE(n >= 0 && channels >= 1 && n_out >= 0, "pcm16_resample: bad sizes");
+  if (n_out == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (bank_tap_major == nullptr) {                 // same rate: scale + channel mean only
+    AVCER_REQUIRE(n_out == n, "pcm16_resample: n_out must equal n without a filter bank");
+    pcm16_mono_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pcm, n, channels, out);
+    return check_launch("pcm16_mono_kernel");
+  }
+  AVCER_REQUIRE(orig >= 1 && nnew >= 1 && width >= 0, "pcm16_resample: bad resampling ratio");
+  const int64_t frames = n / orig + 1;             // conv1d output length over the padded signal
+  AVCER_REQUIRE(n_out <= frames * nnew, "pcm16_resample: n_out %lld exceeds the %lld samples the filter produces", (long long)n_out,
+                (long long)(frames * nnew));
+  const int taps = 2 * width + orig;
+  const size_t smem = ((size_t)(RS_FRAMES - 1) * orig + taps) * sizeof(float);
+  AVCER_REQUIRE(smem <= 200 * 1024, "pcm16_resample: ratio %d/%d needs %zu B of shared memory", orig, nnew, smem);
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    cudaFuncSetAttribute(pcm16_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  const int64_t used_frames = (n_out + nnew - 1) / nnew;
+  const unsigned grid = (unsigned)((used_frames + RS_FRAMES - 1) / RS_FRAMES);
+  pcm16_resample_kernel<<<grid, 256, smem, st>>>(pcm, (long long)n, channels, bank_tap_major, orig, nnew, width, (long long)n_out, out);
+  return check_launch("pcm16_resample_kernel");
 }

@@ -40,23 +40,19 @@ def pth_processing(fp) -> torch.Tensor:
 
 
 def convert_mp4_to_mp3(path, sampling_rate=16000):
+    """data/utils.py:42-60.  The ffmpeg call (container demux + codec decode) stays upstream: the 16-bit PCM .wav it
+    writes next to the video must exist.  What follows it in the reference -- torchaudio.load's 1/32768 scaling, the
+    channel mean and torchaudio.transforms.Resample -- runs in one kernel (avcer_pcm16_resample)."""
     path_save = path[:-3] + "wav"
     if not os.path.exists(path_save):
         raise FileNotFoundError(f"{path_save}: audio decode (ffmpeg) is outside the accelerated path; provide the .wav")
     with wave.open(path_save, "rb") as f:
         sr, nch, sw, n = f.getframerate(), f.getnchannels(), f.getsampwidth(), f.getnframes()
-        assert sw == 2, "16-bit PCM expected"
-        pcm = np.frombuffer(f.readframes(n), dtype="<i2").reshape(-1, nch).T.astype(np.float32) / 32768.0
-    wav = torch.from_numpy(pcm)
-    if wav.size(0) > 1:
-        wav = wav.mean(dim=0, keepdim=True)
-    if sr != sampling_rate:
-        import torchaudio
-
-        wav = torchaudio.transforms.Resample(orig_freq=sr, new_freq=sampling_rate)(wav)
-        sr = sampling_rate
-    assert sr == sampling_rate
-    return wav.squeeze(0)
+        if sw != 2:
+            raise ValueError(f"{path_save}: 16-bit PCM expected, got {8 * sw}-bit samples")
+        pcm = np.frombuffer(f.readframes(n), dtype="<i2").reshape(-1, nch)
+    dev = config.device()
+    return ops.pcm16_to_mono(torch.from_numpy(np.ascontiguousarray(pcm)).to(dev), sr, sampling_rate).cpu()
 
 
 def pad_wav(wav, max_length):

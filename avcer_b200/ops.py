@@ -6,6 +6,7 @@ hand-written kernel of libavcer_b200.so.
 from __future__ import annotations
 
 import ctypes
+import math
 from typing import Optional, Sequence
 
 import numpy as np
@@ -18,7 +19,7 @@ from ._lib import check as _check
 __all__ = [
     "F32", "BF16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "dtype_code", "torch_dtype", "contract", "conv2d_nhwc",
     "linear", "preprocess", "fuse_compound", "weight_search_confusion", "softmax7", "window_to_frame_mean", "gather_rows", "maxpool3x3s2",
-    "stem_pool", "avgpool", "small_linear", "lstm_cell", "audio_normalize_windows", "w2v_conv0_ln_gelu", "layernorm", "add_rows",
+    "stem_pool", "avgpool", "small_linear", "lstm_cell", "sinc_resample_bank", "pcm16_to_mono", "audio_normalize_windows", "w2v_conv0_ln_gelu", "layernorm", "add_rows",
     "attention", "maxpool1d5_relu", "avgpool1d_relu", "cast",
 ]
 
@@ -305,6 +306,44 @@ def lstm_cell(xproj: Optional[torch.Tensor], xidx: Optional[torch.Tensor], hproj
 
 
 PAD_MODES = {"mean": 0, "constant": 1, "repeat": 2}
+
+
+def sinc_resample_bank(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """Polyphase filter bank of torchaudio.transforms.Resample with its defaults (Hann-windowed sinc, computed in
+    float64 and rounded to float32), the transform the reference applies at src/data/utils.py:53-55.
+    Returns (bank [nnew, 2*width + orig] float32, orig, nnew, width) with the rates divided by their gcd."""
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, nnew = int(orig_freq) // g, int(new_freq) // g
+    cutoff = min(orig, nnew) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / cutoff)
+    taps = np.arange(-width, width + orig, dtype=np.float64) / orig                  # tap position, in input periods
+    phase = -np.arange(nnew, dtype=np.float64) / nnew                                # one filter per output phase
+    t = np.clip((phase[:, None] + taps[None, :]) * cutoff, -lowpass_filter_width, lowpass_filter_width)
+    hann = np.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t = t * math.pi
+    sinc = np.ones_like(t)
+    nz = t != 0
+    sinc[nz] = np.sin(t[nz]) / t[nz]
+    return (sinc * hann * (cutoff / orig)).astype(np.float32), orig, nnew, width
+
+
+def pcm16_to_mono(pcm: torch.Tensor, sr: int, sampling_rate: int) -> torch.Tensor:
+    """pcm: device int16 [n, channels] (interleaved .wav payload) -> fp32 mono at `sampling_rate` (data/utils.py:49-60)."""
+    _cuda(pcm, "pcm")
+    if pcm.dtype != torch.int16 or pcm.dim() != 2 or not pcm.is_contiguous():
+        raise ValueError("pcm16_to_mono expects a contiguous int16 [n, channels] tensor")
+    n, ch = pcm.shape
+    if sr == sampling_rate:
+        out = torch.empty(n, device=pcm.device, dtype=torch.float32)
+        check(_lib.load().avcer_pcm16_resample(pcm.data_ptr(), n, ch, None, 1, 1, 0, out.data_ptr(), n, _stream()))
+        return out
+    bank, orig, nnew, width = sinc_resample_bank(sr, sampling_rate)
+    bank_t = torch.from_numpy(np.ascontiguousarray(bank.T)).to(pcm.device)
+    n_out = -(-nnew * n // orig)
+    out = torch.empty(n_out, device=pcm.device, dtype=torch.float32)
+    check(_lib.load().avcer_pcm16_resample(pcm.data_ptr(), n, ch, bank_t.data_ptr(), orig, nnew, width, out.data_ptr(), n_out,
+                                           _stream()))
+    return out
 
 
 def audio_normalize_windows(wav: torch.Tensor, starts: torch.Tensor, win: int, pad_mode: str,

@@ -180,6 +180,13 @@ int avcer_lstm_cell(const float* xproj, const int32_t* xidx, const float* hproj,
                     void* h_out, int64_t ldh, int64_t n, int hidden, int first, int dtype,
                     void* stream);
 
+/* Audio decode seam (data/utils.py:49-60, convert_mp4_to_mp3 after its ffmpeg call): interleaved int16 PCM
+ * [n, channels] -> x/32768 -> channel mean -> torchaudio.transforms.Resample (default "sinc_interp_hann" polyphase
+ * filter: out[f*nnew + j] = sum_k bank[j][k] * x[f*orig + k - width], zero outside the signal).
+ * bank_tap_major: [2*width + orig][nnew] fp32 (the transposed filter bank), orig/nnew = the two rates divided by
+ * their gcd; n_out = ceil(nnew*n/orig).  bank_tap_major == NULL: same rate, only the scale + channel mean (n_out == n). */
+int avcer_pcm16_resample(const int16_t* pcm, int64_t n, int channels, const float* bank_tap_major,
+                         int orig, int nnew, int width, float* out, int64_t n_out, void* stream);
 /* K5a: gather audio chunks wav[starts[i], ends[i]) (at most `win` samples; chunks of several clips
  * may live in one concatenated buffer), pad the tail to `win` with the chunk mean ("mean"), zeros
  * ("constant") or by tiling ("repeat") (data/utils.py:63-89), then HF

@@ -187,3 +187,45 @@ def predict_audio(wav: np.ndarray, fps: float, sd, step: float = 0.5, window: in
             rows.append(l)
             ids.append(f)
     return np.asarray(rows, dtype=np.float32), np.asarray(ids, dtype=np.int64), logits
+
+
+# ---------------------------------------------------------------------------------------------- decode seam
+def sinc_resample_kernel(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """Filter bank of torchaudio.transforms.Resample with its defaults ("sinc_interp_hann"), the transform the
+    reference applies at src/data/utils.py:53-55.  torchaudio is a third-party dependency (pinned
+    torchaudio==2.1.2 in src/requirements.txt, not under /root/reference); its published algorithm
+    (torchaudio.functional._get_sinc_resample_kernel) is restated here: float64 table, cast to float32.
+    Returns (kernel [new, 2*width + orig] float32, width, orig, new) with orig / new reduced by their gcd."""
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    base_freq = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base_freq)
+    idx = np.arange(-width, width + orig, dtype=np.float64)[None, :] / orig
+    t = np.arange(0, -new, -1, dtype=np.float64)[:, None] / new + idx
+    t *= base_freq
+    t = np.clip(t, -lowpass_filter_width, lowpass_filter_width)
+    window = np.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t *= math.pi
+    scale = base_freq / orig
+    with np.errstate(invalid="ignore", divide="ignore"):
+        kern = np.where(t == 0, 1.0, np.sin(t) / t)
+    kern = kern * window * scale
+    return kern.astype(np.float32), width, orig, new
+
+
+def pcm16_to_mono_16k(pcm: np.ndarray, sr: int, sampling_rate: int = 16000) -> np.ndarray:
+    """convert_mp4_to_mp3 after the ffmpeg step (src/data/utils.py:49-60): `pcm` is the int16 [n, channels] content
+    of the .wav; torchaudio.load scales by 1/32768, the channels are averaged, and the signal is resampled to
+    `sampling_rate` (strided conv1d with the filter bank above, torchaudio.functional._apply_sinc_resample_kernel)."""
+    wav = torch.from_numpy(pcm.astype(np.float32) / 32768.0).t()           # [channels, n]
+    if wav.size(0) > 1:
+        wav = wav.mean(dim=0, keepdim=True)
+    if sr == sampling_rate:
+        return wav.squeeze(0).numpy()
+    kern, width, orig, new = sinc_resample_kernel(sr, sampling_rate)
+    length = wav.shape[1]
+    padded = F.pad(wav, (width, width + orig))
+    res = F.conv1d(padded[:, None], torch.from_numpy(kern)[:, None], stride=orig)      # [1, new, frames]
+    res = res.transpose(1, 2).reshape(1, -1)
+    target = int(math.ceil(new * length / orig))
+    return res[0, :target].numpy()

@@ -266,6 +266,52 @@ def make_weight_search():
     print("weight_search.npz")
 
 
+def resample_inputs():
+    """Seeded int16 PCM in the two layouts the reference's ffmpeg step can leave behind (it asks for 44.1 kHz stereo)."""
+    rng = np.random.default_rng(77)
+    t1 = np.arange(16317) / 44100.0
+    stereo = np.stack([8000 * np.sin(2 * np.pi * 440 * t1) + 3000 * rng.standard_normal(t1.size),
+                       6000 * np.sin(2 * np.pi * 1250 * t1 + 0.3) + 3000 * rng.standard_normal(t1.size)], axis=1)
+    mono48 = 9000 * np.sin(2 * np.pi * 900 * np.arange(9001) / 48000.0) + 2000 * rng.standard_normal(9001)
+    return {"stereo_44100": (np.clip(stereo, -32768, 32767).astype(np.int16), 44100),
+            "mono_48000": (np.clip(mono48, -32768, 32767).astype(np.int16)[:, None], 48000)}
+
+
+def make_resample(wd):
+    """The reference's own convert_mp4_to_mp3 (src/data/utils.py:42-60) on .wav files that already exist (so its
+    ffmpeg call is skipped); only torchaudio.load -- unusable here without torchcodec -- is replaced by a reader with
+    the same normalisation (int16 / 32768, channels first)."""
+    import wave
+
+    import torchaudio
+    from data.utils import convert_mp4_to_mp3 as ref_convert
+
+    def load(path):
+        with wave.open(path, "rb") as f:
+            sr, nch, n = f.getframerate(), f.getnchannels(), f.getnframes()
+            pcm = np.frombuffer(f.readframes(n), dtype="<i2").reshape(-1, nch)
+        return torch.from_numpy(pcm.astype(np.float32) / 32768.0).t().contiguous(), sr
+
+    out = {}
+    stock_load, torchaudio.load = torchaudio.load, load
+    try:
+        for name, (pcm, sr) in resample_inputs().items():
+            path = os.path.join(wd, name + ".wav")
+            with wave.open(path, "wb") as f:
+                f.setnchannels(pcm.shape[1]); f.setsampwidth(2); f.setframerate(sr)
+                f.writeframes(pcm.astype("<i2").tobytes())
+            ref = ref_convert(os.path.join(wd, name + ".mp4"), 16000).numpy()
+            mine = oa.pcm16_to_mono_16k(pcm, sr, 16000)
+            assert ref.shape == mine.shape and np.abs(ref - mine).max() < 2e-6, (name, ref.shape, mine.shape, np.abs(ref - mine).max())
+            out[name + "_pcm"] = pcm
+            out[name + "_sr"] = np.int64(sr)
+            out[name + "_out"] = ref.astype(np.float32)
+    finally:
+        torchaudio.load = stock_load
+    np.savez_compressed(os.path.join(OUT, "resample.npz"), **out)
+    print("resample.npz")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -277,6 +323,7 @@ def main():
         make_preprocess()
         make_video(wd)
         make_audio()
+        make_resample(wd)
 
 
 if __name__ == "__main__":

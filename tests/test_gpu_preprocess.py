@@ -63,3 +63,33 @@ def test_k1_packed_layouts(cuda_lib):
         assert border.abs().max().item() == 0                                     # zero border and zero 4th channel
     # empty batch is a no-op
     ops.preprocess(src[:0], 0, nchw, 0)
+
+
+def test_pcm16_resample_matches_reference(cuda_lib, golden, tmp_path):
+    """Audio decode seam (data/utils.py:49-60): int16 PCM -> mono -> 16 kHz on the GPU against what the reference's own
+    convert_mp4_to_mp3 produced from the same .wav payloads (tests/golden/resample.npz), through the drop-in function
+    (reads the .wav next to the video path) and against the oracle on a longer seeded signal with three channels."""
+    import wave
+
+    from avcer_b200 import ops
+    from avcer_b200.data.utils import convert_mp4_to_mp3
+    from oracle import audio as oa
+
+    g = golden["resample"]
+    for name in ("stereo_44100", "mono_48000"):
+        pcm, sr, ref = g[name + "_pcm"], int(g[name + "_sr"]), g[name + "_out"]
+        with wave.open(str(tmp_path / (name + ".wav")), "wb") as f:
+            f.setnchannels(pcm.shape[1]); f.setsampwidth(2); f.setframerate(sr)
+            f.writeframes(pcm.astype("<i2").tobytes())
+        got = convert_mp4_to_mp3(str(tmp_path / (name + ".mp4")), 16000)
+        assert got.dtype == torch.float32 and tuple(got.shape) == ref.shape
+        assert np.abs(got.numpy() - ref).max() < 2e-6, name
+    rng = np.random.default_rng(5)
+    for sr, n, ch in ((44100, 200003, 3), (22050, 70001, 1), (8000, 33333, 2), (16000, 5000, 2), (44100, 441, 1), (44100, 1, 1)):
+        pcm = rng.integers(-20000, 20000, (n, ch)).astype(np.int16)
+        want = oa.pcm16_to_mono_16k(pcm, sr, 16000)
+        got = ops.pcm16_to_mono(torch.from_numpy(pcm).to(DEV), sr, 16000).cpu().numpy()
+        assert got.shape == want.shape, (sr, n, ch)
+        assert np.abs(got - want).max() < 3e-6, (sr, n, ch, np.abs(got - want).max())
+    with pytest.raises(FileNotFoundError):
+        convert_mp4_to_mp3(str(tmp_path / "absent.mp4"), 16000)

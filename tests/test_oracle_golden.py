@@ -104,3 +104,17 @@ def test_audio_schedule_nan_window(golden):
     assert sched[-1][0] == sched[-1][1] == L
     with pytest.raises(ZeroDivisionError):
         oa.pad_window(np.zeros(0, np.float32), 64000, "repeat")
+
+
+def test_resample_matches_reference(golden):
+    """convert_mp4_to_mp3's post-ffmpeg arithmetic (data/utils.py:49-60) on the int16 fixtures the reference itself
+    converted (oracle/make_golden.py:make_resample), and the product's own filter-bank restatement against the oracle's."""
+    from avcer_b200 import ops
+    g = golden["resample"]
+    for name in ("stereo_44100", "mono_48000"):
+        pcm, sr, ref = g[name + "_pcm"], int(g[name + "_sr"]), g[name + "_out"]
+        got = oa.pcm16_to_mono_16k(pcm, sr, 16000)
+        assert got.shape == ref.shape and np.abs(got - ref).max() < 2e-6, name
+        bank, orig, nnew, width = ops.sinc_resample_bank(sr, 16000)
+        okern, owidth, oorig, onew = oa.sinc_resample_kernel(sr, 16000)
+        assert (orig, nnew, width) == (oorig, onew, owidth) and np.array_equal(bank, okern), name

@@ -150,7 +150,8 @@ static int conv3x3_tc(const avcer_contract_desc* d, cudaStream_t st) {
                      (d->act == ACT_NONE || d->act == ACT_RELU);
   const bool dense = d->a_dim[0] == C && d->a_dim[1] == W && d->a_dim[2] == H && d->a_dim[3] == NB && d->a_stride[0] == 1 &&
                      d->a_stride[1] == C && d->a_stride[2] == (int64_t)W * C && d->a_stride[3] == (int64_t)H * W * C &&
-                     d->out_stride[0] == Cout && d->out_stride[1] == (int64_t)W * Cout && d->out_stride[2] == (int64_t)H * W * Cout;
+                     d->out_stride[0] >= Cout && d->out_stride[0] % 8 == 0 && d->out_stride[1] == (int64_t)W * d->out_stride[0] &&
+                     d->out_stride[2] == (int64_t)H * W * d->out_stride[0];          // output pixels may sit in wider rows
   const bool aligned = ((reinterpret_cast<uintptr_t>(d->a) | reinterpret_cast<uintptr_t>(d->wt) | reinterpret_cast<uintptr_t>(d->out)) & 15) == 0;
   if (!shape || !dense || !aligned) return -1;       // the generic path validates and reports
   Conv3Params p{};
@@ -180,7 +181,8 @@ static int conv3x3_tc(const avcer_contract_desc* d, cudaStream_t st) {
   }
   {
     uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)NB, 1};
-    uint64_t strides[4] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2, (uint64_t)1 << 30};
+    const uint64_t op = (uint64_t)d->out_stride[0];
+    uint64_t strides[4] = {op * 2, (uint64_t)W * op * 2, (uint64_t)H * W * op * 2, (uint64_t)1 << 30};
     uint32_t box[5] = {64u, (uint32_t)W, (uint32_t)p.bh, 1u, 1u};
     if (encode_map(&tc, d->out, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
@@ -340,7 +342,8 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------ fused stem + max-pool (bf16)
-static int stem_pool_tc(const void* x, const void* w_packed, const float* bias, int n, void* out, cudaStream_t st) {
+static int stem_pool_tc(const void* x, const void* w_packed, const float* bias, int n, void* out, int64_t out_pitch, cudaStream_t st) {
+  AVCER_REQUIRE(out_pitch >= 64 && out_pitch % 8 == 0, "stem_pool: out_pitch %lld must be a multiple of 8, at least 64", (long long)out_pitch);
   AVCER_REQUIRE(x != nullptr && w_packed != nullptr && bias != nullptr && out != nullptr, "stem_pool: null pointer");
   AVCER_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(out) & 15) == 0,
@@ -360,6 +363,7 @@ static int stem_pool_tc(const void* x, const void* w_packed, const float* bias, 
   p.w_packed = w_packed;
   p.bias = bias;
   p.out = static_cast<__nv_bfloat16*>(out);
+  p.out_pitch = out_pitch;
   static bool attr_done = false;
   if (!attr_done) {
     AVCER_CUDA(cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemPoolCfg::SMEM));
@@ -580,5 +584,12 @@ extern "C" int avcer_contract(const avcer_contract_desc* d, void* stream) {
 extern "C" int avcer_stem_pool(const void* x_padded, const void* w_packed, const float* bias, int n, void* out, void* stream) {
   using namespace avcer;
   AVCER_REQUIRE(n >= 0, "stem_pool: negative batch");
-  return stem_pool_tc(x_padded, w_packed, bias, n, out, as_stream(stream));
+  return stem_pool_tc(x_padded, w_packed, bias, n, out, 64, as_stream(stream));
+}
+
+extern "C" int avcer_stem_pool_ld(const void* x_padded, const void* w_packed, const float* bias, int n, void* out, int64_t out_pitch,
+                                  void* stream) {
+  using namespace avcer;
+  AVCER_REQUIRE(n >= 0, "stem_pool: negative batch");
+  return stem_pool_tc(x_padded, w_packed, bias, n, out, out_pitch, as_stream(stream));
 }

@@ -24,7 +24,8 @@ struct StemPoolParams {
   int units;                // n * 4 work units (14 pooled rows each; the last of a crop has 13)
   const void* w_packed;     // [7][4 KB] filter rows in UMMA no-swizzle core-matrix order
   const float* bias;        // [64] folded BN shift
-  __nv_bfloat16* out;       // [n, 55, 55, 64]
+  __nv_bfloat16* out;       // [n, 55, 55, 64] with `out_pitch` elements between pixels
+  long long out_pitch;      // >= 64, multiple of 8 (a wider row lets the caller place other channels next to the pooled ones)
 };
 
 struct StemPoolCfg {
@@ -190,7 +191,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const StemPoolParams p
         if (r >= 2 && (r & 1) == 0) {
           // pooled row j = j0 + r/2 - 1 from stem rows r-2, r-1, r: 55 pixels x 8 chunks of 8 channels
           const int j = j0 + (r >> 1) - 1;
-          __nv_bfloat16* orow = p.out + ((long long)(n * 55 + j) * 55) * 64;
+          __nv_bfloat16* orow = p.out + ((long long)(n * 55 + j) * 55) * p.out_pitch;
           for (int it = et; it < 55 * 8; it += 256) {
             const int po = it >> 3, ch = it & 7;
             uint4 m;
@@ -214,7 +215,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const StemPoolParams p
                 }
               }
             }
-            *reinterpret_cast<uint4*>(orow + po * 64 + ch * 8) = m;
+            *reinterpret_cast<uint4*>(orow + po * p.out_pitch + ch * 8) = m;
           }
         }
       }

@@ -52,7 +52,7 @@ def convert_mp4_to_mp3(path, sampling_rate=16000):
             raise ValueError(f"{path_save}: 16-bit PCM expected, got {8 * sw}-bit samples")
         pcm = np.frombuffer(f.readframes(n), dtype="<i2").reshape(-1, nch)
     dev = config.device()
-    return ops.pcm16_to_mono(torch.from_numpy(np.ascontiguousarray(pcm)).to(dev), sr, sampling_rate).cpu()
+    return ops.pcm16_to_mono(torch.from_numpy(np.array(pcm)).to(dev), sr, sampling_rate).cpu()
 
 
 def pad_wav(wav, max_length):

@@ -75,6 +75,7 @@ class VSNet:
         self.device = torch.device(device)
         self.w = weights.pack_vs(state_dict, self.device, self.dtype)
         self.fused_stem = True          # bf16: stem + max-pool in one kernel (False: two kernels, same bits)
+        self.fused_shortcut = True      # bf16: layer1.0's projection shortcut folded into conv3 (K-concatenated GEMM)
 
     @property
     def input_layout(self) -> int:
@@ -110,8 +111,13 @@ class VSNet:
 
     def forward(self, x: torch.Tensor, taps: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         assert x.shape[1:] == (PAD_H, PAD, 4) and x.dtype == self.dtype
+        cat = None
         if taps is None and self.dtype == torch.bfloat16 and self.fused_stem:
-            y = ops.stem_pool(x, self.w["stem_packed"], self.w["stem"].bias)      # stem activation stays on chip
+            if self.fused_shortcut and "conv3_ds" in self.w["blocks"][0]:
+                cat = torch.empty((x.shape[0], 55, 55, 128), device=self.device, dtype=self.dtype)
+                y = ops.stem_pool(x, self.w["stem_packed"], self.w["stem"].bias, out=cat[..., :64])
+            else:
+                y = ops.stem_pool(x, self.w["stem_packed"], self.w["stem"].bias)      # stem activation stays on chip
         else:
             y = self.stem(x)
             if taps is not None:
@@ -120,6 +126,15 @@ class VSNet:
             if taps is not None:
                 taps["pool"] = y
         for bi, blk in enumerate(self.w["blocks"]):
+            if bi == 0 and cat is not None:
+                # layer1.0: block input and conv2 output share one [n*55*55, 128] matrix, so conv3 and the projection
+                # shortcut are a single K = 128 GEMM (no shortcut tensor, no residual read)
+                m = cat.shape[0] * 55 * 55
+                c1, c2, c3 = blk["conv1"], blk["conv2"], blk["conv3_ds"]
+                t = ops.linear(cat.view(m, 128)[:, :64], c1.wt, c1.bias, act=ops.ACT_RELU).view(-1, 55, 55, 64)
+                ops.conv2d_nhwc(t, c2.wt, c2.bias, kh=3, kw=3, pad_h=1, pad_w=1, act=ops.ACT_RELU, out=cat[..., 64:])
+                y = ops.linear(cat.view(m, 128), c3.wt, c3.bias, act=ops.ACT_RELU).view(-1, 55, 55, 256)
+                continue
             identity = self._conv(y, blk["ds"], ops.ACT_NONE) if "ds" in blk else y
             t = self._conv(y, blk["conv1"], ops.ACT_RELU)
             t = self._conv(t, blk["conv2"], ops.ACT_RELU)

@@ -148,8 +148,11 @@ def conv2d_nhwc(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor],
         assert kh == 1 and kw == 1 and pad_h == 0 and pad_w == 0, "strided conv only for 1x1"
         a_dim = (c, wo, ho, n, 1)
         a_stride = (1, stride * c, stride * w * c, h * w * c, n * h * w * c)
+    op = out.stride(2)                                   # pixel pitch: `out` may be a channel slice of a wider buffer
+    assert out.stride(3) == 1 and out.stride(1) == wo * op and out.stride(0) == ho * wo * op
+    assert residual is None or op == cout
     return contract(a=x, a_dim=a_dim, a_stride=a_stride, wt=wt, bias=bias, out=out,
-                    out_stride=(cout, wo * cout, ho * wo * cout), W=wo, H=ho, NB=n, cin=c, cout=cout, taps_w=kw,
+                    out_stride=(op, wo * op, ho * wo * op), W=wo, H=ho, NB=n, cin=c, cout=cout, taps_w=kw,
                     taps_h=kh, off_w=-pad_w, off_h=-pad_h, residual=residual, act=act)
 
 
@@ -263,15 +266,20 @@ def gather_rows(src: torch.Tensor, index: Optional[torch.Tensor], n_out: int, pe
 
 
 # ----------------------------------------------------------------------------------------- small layers
-def stem_pool(x: torch.Tensor, wt_packed: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
-    """Fused ResNet stem + max-pool: x [n,232,240,4] bf16 zero-bordered crops -> [n,55,55,64] bf16."""
+def stem_pool(x: torch.Tensor, wt_packed: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused ResNet stem + max-pool: x [n,232,240,4] bf16 zero-bordered crops -> [n,55,55,64] bf16.
+    `out`: optional channel slice [n,55,55,64] of a wider contiguous [n,55,55,C] buffer (pixel pitch C)."""
     _cuda(x, "x")
     n = x.shape[0]
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and tuple(x.shape[1:]) == (PAD_H, PAD_W, 4)
-    y = torch.empty((n, 55, 55, 64), device=x.device, dtype=torch.bfloat16)
+    if out is None:
+        out = torch.empty((n, 55, 55, 64), device=x.device, dtype=torch.bfloat16)
+    pitch = out.stride(2)
+    assert out.dtype == torch.bfloat16 and tuple(out.shape) == (n, 55, 55, 64) and out.stride(3) == 1
+    assert out.stride(1) == 55 * pitch and out.stride(0) == 55 * 55 * pitch
     with _Timed("contract_bf16", 2.0 * n * 112 * 112 * 64 * 147):        # 7x7x3 real taps (SURVEY.md section 8d)
-        _check(_lib.load().avcer_stem_pool(x.data_ptr(), wt_packed.data_ptr(), bias.data_ptr(), n, y.data_ptr(), _stream()))
-    return y
+        _check(_lib.load().avcer_stem_pool_ld(x.data_ptr(), wt_packed.data_ptr(), bias.data_ptr(), n, out.data_ptr(), pitch, _stream()))
+    return out
 
 
 def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:

@@ -162,6 +162,11 @@ int avcer_gather_rows(const float* src, const int32_t* src_index, int64_t n_out,
  * bias: [64] fp32; out: [n, 55, 55, 64] bf16.  Bit-identical to avcer_contract (stem geometry) followed by
  * avcer_maxpool3x3s2; the 112x112x64 stem activation is never written to global memory. */
 int avcer_stem_pool(const void* x_padded, const void* w_packed, const float* bias, int n, void* out, void* stream);
+/* Same with `out_pitch` (>= 64, multiple of 8) bf16 elements between output pixels: the pooled activation can be
+ * written into the first 64 columns of a wider [n*55*55, out_pitch] matrix (used to place the block input next to
+ * conv2's output so that conv3 and the projection shortcut, video.py:46-58, become one K-concatenated GEMM). */
+int avcer_stem_pool_ld(const void* x_padded, const void* w_packed, const float* bias, int n, void* out,
+                       int64_t out_pitch, void* stream);
 /* 3x3 stride-2 un-padded max pool, NHWC (architectures/video.py:103,117). */
 int avcer_maxpool3x3s2(const void* x, int n, int h, int w, int c, void* y, int dtype, void* stream);
 /* Global average pool NHWC -> [n, c] (video.py:124). */

@@ -9,6 +9,7 @@ dev = "cuda:0"
 N = int(os.environ.get("N", "256"))
 quiet = "quiet" in sys.argv
 net = nets.VSNet(syn.make_vs_state_dict(0, "default"), "bf16", dev)
+net.fused_shortcut = os.environ.get("FS", "1") != "0"
 g = torch.Generator(device=dev).manual_seed(5)
 crops = torch.randint(0, 256, (N, 224, 224, 3), dtype=torch.uint8, device=dev, generator=g)
 x = net.alloc_input(N)
@@ -18,7 +19,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 names = ["stem"]
 for li, nb in enumerate((3, 4, 6, 3), 1):
     for b in range(nb):
-        names += ([f"l{li}.{b}.ds"] if b == 0 else []) + [f"l{li}.{b}.c1", f"l{li}.{b}.c2", f"l{li}.{b}.c3"]
+        names += ([f"l{li}.{b}.ds"] if b == 0 and not (li == 1 and net.fused_shortcut) else []) + [f"l{li}.{b}.c1", f"l{li}.{b}.c2", f"l{li}.{b}.c3"]
 names.append("fc1")
 
 for it in range(3):

@@ -15,7 +15,18 @@ int set_error(const char* fmt, ...) {
   return 1;
 }
 
+int& sm_limit_ref() {
+  static thread_local int limit = 0;
+  return limit;
+}
+
 }  // namespace avcer
+
+extern "C" int avcer_set_sm_limit(int n_sms) {
+  if (n_sms < 0 || (n_sms & 1)) return avcer::set_error("set_sm_limit: %d must be 0 (all) or a positive even SM count", n_sms);
+  avcer::sm_limit_ref() = n_sms;
+  return 0;
+}
 
 extern "C" const char* avcer_last_error(void) { return avcer::g_err; }
 

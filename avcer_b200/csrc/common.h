@@ -32,7 +32,9 @@ inline int check_launch(const char* what) {
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// SM count of the current device (cached; 148 on B200): persistent kernels size their grids with it.
+// SM count persistent kernels size their grids with: the device's (cached; 148 on B200), or the caller's smaller
+// share of it (avcer_set_sm_limit) when two branches of the pipeline run side by side on different streams.
+int& sm_limit_ref();
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -41,7 +43,8 @@ inline int num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  const int lim = sm_limit_ref();
+  return (lim > 0 && lim < n) ? lim : n;
 }
 
 // Programmatic dependent launch (PDL).  Hot-path kernels are launched with the programmatic-stream-serialization
@@ -49,13 +52,20 @@ inline int num_sms() {
 // descriptor prefetch, constant staging) while the previous kernel drains, and block in pdl_wait() until that kernel
 // has completed and flushed its writes.  Every kernel launched through launch_pdl() must call pdl_wait() before its
 // first access to memory another kernel may have written, and before its own first global write.  Works inside CUDA
-// graph capture (programmatic edges).  AVCER_PDL=0 launches the same kernels fully serialised.
+// graph capture (programmatic edges).  AVCER_PDL=0 launches the same kernels fully serialised (3 % slower audio
+// forward, 1.5 % slower VS forward).
+// History: PDL's simultaneous release of all CTAs exposed a missing generic->async proxy fence in the residual ring of
+// the barrier epilogue (tc_gemm.cuh / tc_gemm2.cuh): the TMA refill of a slot could overtake the last ld.shared of the
+// previous occupant (about 2 % of the audio encoder's residual GEMM launches showed 16-byte-granular corruptions);
+// tests/test_gpu_nets.py::test_forwards_are_bit_stable_run_to_run and scripts/probe_layer_race.py guard it.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Off while the caller runs with an SM share (avcer_set_sm_limit): an early-resident dependent kernel would sit on the
+// SMs the share leaves free for the other branch's stream.
 inline bool pdl_enabled() {
   static const int on = getenv("AVCER_PDL") ? atoi(getenv("AVCER_PDL")) : 1;
-  return on != 0;
+  return on != 0 && sm_limit_ref() == 0;
 }
 
 template <typename... KArgs, typename... Args>
@@ -70,6 +80,35 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// launch_pdl for persistent single-CTA kernels.  While the caller runs with an SM share (avcer_set_sm_limit) the CTAs are
+// launched as clusters of two, which the hardware places on the two SMs of one TPC: a kernel of one branch then leaves
+// whole TPCs free, so the two-SM (cta_group::2) kernels of the other branch can still be placed beside it.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_tpc(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (sm_limit_ref() > 0 && grid.x % 2 == 0 && grid.y == 1 && grid.z == 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = 2;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

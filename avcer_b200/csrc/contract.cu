@@ -79,7 +79,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   }
   int g = grid * OCC;                     // persistent: OCC CTAs per SM
   if (g > p.num_tiles) g = p.num_tiles;
-  launch_pdl(kern, g, Cfg::THREADS, Cfg::SMEM, st, ta, tb, tc, tr, p);
+  launch_pdl_tpc(kern, g, Cfg::THREADS, Cfg::SMEM, st, ta, tb, tc, tr, p);
   return check_launch("tc_gemm_kernel");
 }
 
@@ -109,16 +109,7 @@ extern "C" int avcer_debug_set_trace(void* buf) {
   return 0;
 }
 
-static int num_sms_cached() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+static int num_sms_cached() { return num_sms(); }
 
 // 3x3 "same" stride-1 convolutions with 64 / 128 output channels over dense NHWC tensors (ResNet-50 layer1 / layer2
 // conv2): halo-in-shared-memory kernel of conv3x3.cuh.  Returns -1 when the geometry is not its case.
@@ -137,7 +128,7 @@ static int launch_conv3(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   const size_t smem = (size_t)p.a_stages * p.a_stage + Cfg::B_BYTES + Cfg::C_BYTES + 1024;
   int g = num_sms();
   if (g > p.num_tiles) g = p.num_tiles;
-  launch_pdl(kern, g, Cfg::THREADS, smem, st, ta, tb, tc, p);
+  launch_pdl_tpc(kern, g, Cfg::THREADS, smem, st, ta, tb, tc, p);
   return check_launch("conv3x3_kernel");
 }
 
@@ -371,7 +362,7 @@ static int stem_pool_tc(const void* x, const void* w_packed, const float* bias, 
   }
   int g = num_sms();
   if (g > p.units) g = p.units;
-  launch_pdl(stem_pool_kernel, g, StemPoolCfg::THREADS, StemPoolCfg::SMEM, st, ta, p);
+  launch_pdl_tpc(stem_pool_kernel, g, StemPoolCfg::THREADS, StemPoolCfg::SMEM, st, ta, p);
   return check_launch("stem_pool_kernel");
 }
 
@@ -404,7 +395,7 @@ int attention_tc5(const void* qkv, int n, int t, int heads, float scale, void* o
   }
   int g = num_sms();
   if (g > p.units) g = p.units;
-  launch_pdl(attention_tc5_kernel, g, Cfg::THREADS, Cfg::SMEM, st, tq, tkv, p);
+  launch_pdl_tpc(attention_tc5_kernel, g, Cfg::THREADS, Cfg::SMEM, st, tq, tkv, p);
   return check_launch("attention_tc5_kernel");
 }
 

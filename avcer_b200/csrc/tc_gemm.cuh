@@ -355,11 +355,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               st_shared_v4(cbuf + row_off + (((j0 + j) ^ (r & 7)) << 4), u);
             }
           }
+          fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine; residual reads
+                                               // ordered before the TMA refill of the slot
           if (MODE == OUT_TMA_RES) {
             __syncwarp();
             if (lane == 0) mbar_arrive(rfree_bar(rslot));
           }
-          fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
           named_bar_sync(2, EPI_THREADS);
           if (store_thread) {
             if (nt * BN + hf * 64 < p.Cout) tma_store_5d(&tmC, cbuf, nt * BN + hf * 64, w0, h0, n0, 0);

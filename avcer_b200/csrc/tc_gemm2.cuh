@@ -463,6 +463,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               f[j * 8 + e * 2 + 1] += t.y;
             }
           }
+          fence_proxy_async();                 // generic-proxy reads of the slot ordered before the TMA refill (async proxy)
           __syncwarp();
           if (lane == 0) mbar_arrive(rfree_bar(rslot));
           if (!p.res_after_act) apply_act();

@@ -26,9 +26,10 @@ class GraphedForward:
     """CUDA-graph cache around a fixed-shape forward: the ~60 (VS) / ~130 (A) kernel launches of one
     batch are captured once per (batch size, static input buffer) and replayed with a single launch."""
 
-    def __init__(self, fn):
+    def __init__(self, fn, sm_limit: int = 0):
         self.fn = fn
         self.cache = {}
+        self.sm_limit = sm_limit        # grid share of the persistent kernels baked into the captured launches
 
     def __call__(self, *static_inputs: torch.Tensor):
         key = tuple((t.data_ptr(), tuple(t.shape)) for t in static_inputs)
@@ -38,13 +39,13 @@ class GraphedForward:
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
             side.wait_stream(cur)
-            with torch.cuda.stream(side):              # warm-up outside capture (lazy attribute sets, allocator)
+            with torch.cuda.stream(side), ops.sm_limit(self.sm_limit):   # warm-up outside capture (lazy attribute sets, allocator)
                 self.fn(*static_inputs)
             cur.wait_stream(side)
             torch.cuda.synchronize()
             n0 = ops.STATS["launches"]
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph), ops.sm_limit(self.sm_limit):
                 outs = self.fn(*static_inputs)
             entry = (graph, outs, ops.STATS["launches"] - n0)
             ops.STATS["launches"] = n0

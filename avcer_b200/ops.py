@@ -20,7 +20,7 @@ __all__ = [
     "F32", "BF16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "dtype_code", "torch_dtype", "contract", "conv2d_nhwc",
     "linear", "preprocess", "fuse_compound", "weight_search_confusion", "softmax7", "window_to_frame_mean", "gather_rows", "maxpool3x3s2",
     "stem_pool", "avgpool", "small_linear", "lstm_cell", "sinc_resample_bank", "pcm16_to_mono", "audio_normalize_windows", "w2v_conv0_ln_gelu", "layernorm", "add_rows",
-    "attention", "maxpool1d5_relu", "avgpool1d_relu", "cast",
+    "attention", "maxpool1d5_relu", "avgpool1d_relu", "cast", "sm_limit",
 ]
 
 
@@ -58,6 +58,24 @@ class _Timed:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             PROFILE.append((self.tag, self.work, self.e0, e1))
+        return False
+
+
+class sm_limit:
+    """Context: persistent kernels launched (or captured) inside use `n_sms` SMs instead of the whole device
+    (avcer_set_sm_limit); 0 = no limit."""
+
+    def __init__(self, n_sms: int):
+        self.n = int(n_sms)
+
+    def __enter__(self):
+        if self.n:
+            _check(_lib.load().avcer_set_sm_limit(self.n))
+        return self
+
+    def __exit__(self, *exc):
+        if self.n:
+            _check(_lib.load().avcer_set_sm_limit(0))
         return False
 
 

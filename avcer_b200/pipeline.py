@@ -98,7 +98,7 @@ class Engine:
         return t.to(self.device, non_blocking=True)
 
     def __init__(self, sd_vs=None, sd_vd=None, sd_a=None, precision: str = "bf16", device: str = "cuda:0",
-                 vs_batch: int = 256, a_batch: int = 64, use_graphs: bool = True):
+                 vs_batch: int = 256, a_batch: int = 64, use_graphs: bool = True, overlap: Optional[Tuple[int, int]] = None):
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         self.precision = precision
@@ -112,18 +112,27 @@ class Engine:
         self._perm = torch.tensor(VIDEO_TO_AUDIO, device=self.device, dtype=torch.int32)
         # CUDA graphs for the two fixed-shape forwards (disabled while ops.PROFILE records per-kernel events)
         self.use_graphs = use_graphs
-        self._vs_graph = GraphedForward(lambda x: self.vs.forward(x)) if self.vs is not None else None
-        self._a_graph = GraphedForward(lambda x: self.a.forward(x)) if self.a is not None else None
+        # overlap = (SMs for the VS branch, SMs for the audio branch): run_clips runs the two branches side by side on
+        # two streams, each persistent kernel sized to its branch's share (the VS early layers are HBM-bound, the audio
+        # GEMMs tensor-bound, so the two branches complement each other); None = one after the other on one stream
+        self.overlap = overlap
+        vs_sms, a_sms = overlap if overlap else (0, 0)
+        self._vs_sms, self._a_sms = vs_sms, a_sms
+        self._a_stream = torch.cuda.Stream(device=self.device) if overlap else None
+        self._vs_graph = GraphedForward(lambda x: self.vs.forward(x), vs_sms) if self.vs is not None else None
+        self._a_graph = GraphedForward(lambda x: self.a.forward(x), a_sms) if self.a is not None else None
 
     def _vs_fwd(self, x: torch.Tensor):
         if self.use_graphs and ops.PROFILE is None:
             return self._vs_graph(x)
-        return self.vs.forward(x)
+        with ops.sm_limit(self._vs_sms):
+            return self.vs.forward(x)
 
     def _a_fwd(self, x: torch.Tensor):
         if self.use_graphs and ops.PROFILE is None:
             return self._a_graph(x)
-        return self.a.forward(x)
+        with ops.sm_limit(self._a_sms):
+            return self.a.forward(x)
 
     # ------------------------------------------------------------------ VS over packed 224x224 crops
     def _vs_input(self, n: int) -> torch.Tensor:
@@ -309,8 +318,21 @@ class Engine:
         back to back.  Host (pinned) tensors are copied to the device first; device tensors are used as is."""
         if not wav_cat.is_cuda:
             wav_cat = wav_cat.to(self.device, non_blocking=True)
-        probs, feats = self.vs_forward_u8(crops_u8) if crops_u8.is_cuda else self.vs_forward_host(crops_u8)
-        stat, dyn, plans = self.video_rows(probs, feats, exists_list, fps_list)
-        a_rows, logits = self.audio_rows(wav_cat, wav_lens, fps_list, [len(e) for e in exists_list], step, window, sr, padding)
+        n_frames = [len(e) for e in exists_list]
+        if self.overlap and ops.PROFILE is None:
+            cur = torch.cuda.current_stream()
+            self._a_stream.wait_stream(cur)
+            with torch.cuda.stream(self._a_stream):                      # audio branch: enqueued first, runs beside VS / VD
+                a_rows, logits = self.audio_rows(wav_cat, wav_lens, fps_list, n_frames, step, window, sr, padding)
+            probs, feats = self.vs_forward_u8(crops_u8) if crops_u8.is_cuda else self.vs_forward_host(crops_u8)
+            stat, dyn, plans = self.video_rows(probs, feats, exists_list, fps_list)
+            cur.wait_stream(self._a_stream)
+            for t in (a_rows, logits, wav_cat):
+                t.record_stream(cur)
+            wav_cat.record_stream(self._a_stream)
+        else:
+            probs, feats = self.vs_forward_u8(crops_u8) if crops_u8.is_cuda else self.vs_forward_host(crops_u8)
+            stat, dyn, plans = self.video_rows(probs, feats, exists_list, fps_list)
+            a_rows, logits = self.audio_rows(wav_cat, wav_lens, fps_list, n_frames, step, window, sr, padding)
         labels = self.fuse(stat, dyn, a_rows, weights_1, weights_2, ce_weights_type, ce_mask)
         return {"labels": labels, "stat": stat, "dyn": dyn, "audio_mean": a_rows, "window_logits": logits}

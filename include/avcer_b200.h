@@ -36,6 +36,11 @@ int avcer_version(void);
 /* 0 when a CUDA device of compute capability 10.x is usable; error otherwise (no CPU fallback). */
 int avcer_device_check(void);
 int avcer_num_sms(void);
+/* Grid share of the persistent kernels launched (or captured into a CUDA graph) by the calling thread from now on:
+ * n_sms SMs (even, > 0) instead of the whole device, 0 = whole device.  Lets the VS branch (HBM-bound early layers) and
+ * the audio branch (tensor-bound) of one pipeline step run side by side on two streams without one kernel's CTAs
+ * occupying every SM.  The reference runs the two branches one after the other (run.py:224-268). */
+int avcer_set_sm_limit(int n_sms);
 
 /* ------------------------------------------------------------------------------------------
  * K1  face-crop preprocessing.

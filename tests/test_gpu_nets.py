@@ -203,3 +203,33 @@ def test_gemm_tile_flavours_agree(cuda_lib):
 
 def F_gelu(t):
     return torch.nn.functional.gelu(t)
+
+
+def test_forwards_are_bit_stable_run_to_run(cuda_lib):
+    """Every kernel of the path is deterministic (no atomics, fixed reduction orders): repeated forwards of the audio
+    network (64 windows: 12 encoder layers, each with two residual GEMMs on the 4-deep residual ring) and of the VS
+    ResNet-50 must be bit-identical at every tap.  Guards against races between pipeline stages of one kernel and
+    between consecutive kernels (the failure mode seen with programmatic dependent launch, csrc/common.h)."""
+    from avcer_b200 import nets, ops
+
+    g = torch.Generator(device=DEV).manual_seed(11)
+    anet = nets.ANet(syn.make_audio_state_dict(2, 8, "spread", 12), "bf16", DEV)
+    x = torch.randn((64, 64000), device=DEV, generator=g)
+    ref = None
+    for _ in range(6):
+        taps = {}
+        taps["logits"] = anet.forward(x, taps)
+        torch.cuda.synchronize()
+        cur = {k: v.clone() for k, v in taps.items()}
+        if ref is None:
+            ref = cur
+            continue
+        for k in ref:
+            assert torch.equal(ref[k], cur[k]), f"audio tap {k} differs between two runs on the same input"
+    vnet = nets.VSNet(syn.make_vs_state_dict(0, "default"), "bf16", DEV)
+    crops = torch.randint(0, 256, (96, 224, 224, 3), dtype=torch.uint8, device=DEV, generator=g)
+    xin = vnet.alloc_input(96)
+    ops.preprocess(crops, 96, xin, vnet.input_layout)
+    outs = [tuple(t.clone() for t in vnet.forward(xin)) for _ in range(4)]
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1])

@@ -82,6 +82,7 @@ _SIGNATURES = {
     "avcer_audio_normalize_windows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "avcer_w2v_conv0_ln_gelu": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "avcer_layernorm": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_int, c_void_p, c_int64, c_int, c_void_p]),
+    "avcer_subsample_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_void_p]),
     "avcer_add_rows": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "avcer_attention": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p]),
     "avcer_maxpool1d5_relu": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),

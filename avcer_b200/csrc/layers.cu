@@ -383,6 +383,26 @@ __global__ void add_rows_kernel(const T* __restrict__ x, long long rows, int c, 
   Vec8<T>::store(y + r * c + cc, a);
 }
 
+// ------------------------------------------------------------------ pixel subsampling for the stride-s 1x1 convolutions
+// (architectures/video.py:13-15, 141-148: conv1 and the projection shortcut of the first block of layer2-4 both read the
+// block input at every s-th pixel).  The sampled pixels are written once as rows of a wider [n*ho*wo, out_pitch] matrix
+// (16 bytes per thread), next to which conv2 later places its output, so that conv1 becomes a plain row GEMM and
+// conv3 + shortcut one K-concatenated GEMM.
+__global__ void subsample_rows_kernel(const uint4* __restrict__ x, int n, int h, int w, int c16, int stride, int ho, int wo,
+                                      uint4* __restrict__ y, long long y_pitch16) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n * ho * wo * c16;
+  if (i >= total) return;
+  const int cc = (int)(i % c16);
+  const long long m = i / c16;
+  const int ow = (int)(m % wo);
+  const int oh = (int)((m / wo) % ho);
+  const long long img = m / ((long long)wo * ho);
+  y[m * y_pitch16 + cc] = __ldg(x + ((img * h + (long long)oh * stride) * w + (long long)ow * stride) * c16 + cc);
+}
+
 // ------------------------------------------------------------------ multi-head self-attention, T tokens, no mask
 // (HF Wav2Vec2Attention eval path; attention_layers.py:10-38).  One CTA per (window, head, 32-query
 // tile); K and V of the head live in shared memory as fp32 (K rows padded by 1 float so that the
@@ -568,6 +588,22 @@ extern "C" int avcer_layernorm(const void* x, int64_t rows, int c, int64_t ldx, 
   AVCER_LN_CASE(1) AVCER_LN_CASE(2) AVCER_LN_CASE(3) AVCER_LN_CASE(4)
 #undef AVCER_LN_CASE
   return check_launch("layernorm");
+}
+
+extern "C" int avcer_subsample_rows(const void* x, int n, int h, int w, int c, int stride, void* y, int64_t y_pitch, int dtype,
+                                    void* stream) {
+  const int esz = dtype == AVCER_BF16 ? 2 : 4;
+  AVCER_REQUIRE(dtype == AVCER_BF16 || dtype == AVCER_F32, "subsample_rows: unknown dtype %d", dtype);
+  AVCER_REQUIRE(n >= 0 && h > 0 && w > 0 && c > 0 && stride >= 1, "subsample_rows: bad shape");
+  AVCER_REQUIRE((c * esz) % 16 == 0 && (y_pitch * esz) % 16 == 0 && y_pitch >= c, "subsample_rows: rows must be multiples of 16 bytes");
+  AVCER_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0, "subsample_rows: 16-byte alignment");
+  const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
+  const int c16 = c * esz / 16;
+  const long long total = (long long)n * ho * wo * c16;
+  if (total == 0) return 0;
+  launch_pdl(subsample_rows_kernel, blocks_for(total, 256), 256, 0, as_stream(stream), (const uint4*)x, n, h, w, c16, stride, ho, wo,
+             (uint4*)y, (long long)(y_pitch * esz / 16));
+  return check_launch("subsample_rows");
 }
 
 extern "C" int avcer_add_rows(const void* x, int64_t rows, int c, const void* add, int64_t add_rows, void* y,

@@ -136,6 +136,21 @@ class VSNet:
                 ops.conv2d_nhwc(t, c2.wt, c2.bias, kh=3, kw=3, pad_h=1, pad_w=1, act=ops.ACT_RELU, out=cat[..., 64:])
                 y = ops.linear(cat.view(m, 128), c3.wt, c3.bias, act=ops.ACT_RELU).view(-1, 55, 55, 256)
                 continue
+            if taps is None and self.dtype == torch.bfloat16 and self.fused_shortcut and "conv3_ds" in blk and blk["conv1"].stride == 2:
+                # layer2-4 block 0: the stride-2 sampling of the block input is materialised once, as the first Cin
+                # columns of the matrix whose remaining columns conv2 fills; conv1 is a plain row GEMM over it and
+                # conv3 + projection shortcut one K = Cin + planes GEMM
+                c1, c2, c3 = blk["conv1"], blk["conv2"], blk["conv3_ds"]
+                nb, hh, ww, cin = y.shape
+                ho, wo = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
+                m = nb * ho * wo
+                cat = torch.empty((m, cin + c1.cout), device=self.device, dtype=self.dtype)
+                ops.subsample_rows(y, 2, cat[:, :cin])
+                t = ops.linear(cat[:, :cin], c1.wt, c1.bias, act=ops.ACT_RELU).view(nb, ho, wo, c1.cout)
+                ops.conv2d_nhwc(t, c2.wt, c2.bias, kh=3, kw=3, pad_h=1, pad_w=1, act=ops.ACT_RELU,
+                                out=cat.view(nb, ho, wo, cin + c1.cout)[..., cin:])
+                y = ops.linear(cat, c3.wt, c3.bias, act=ops.ACT_RELU).view(nb, ho, wo, c3.cout)
+                continue
             identity = self._conv(y, blk["ds"], ops.ACT_NONE) if "ds" in blk else y
             t = self._conv(y, blk["conv1"], ops.ACT_RELU)
             t = self._conv(t, blk["conv2"], ops.ACT_RELU)

@@ -19,7 +19,7 @@ from ._lib import check as _check
 __all__ = [
     "F32", "BF16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "dtype_code", "torch_dtype", "contract", "conv2d_nhwc",
     "linear", "preprocess", "fuse_compound", "weight_search_confusion", "softmax7", "window_to_frame_mean", "gather_rows", "maxpool3x3s2",
-    "stem_pool", "avgpool", "small_linear", "lstm_cell", "sinc_resample_bank", "pcm16_to_mono", "audio_normalize_windows", "w2v_conv0_ln_gelu", "layernorm", "add_rows",
+    "stem_pool", "subsample_rows", "avgpool", "small_linear", "lstm_cell", "sinc_resample_bank", "pcm16_to_mono", "audio_normalize_windows", "w2v_conv0_ln_gelu", "layernorm", "add_rows",
     "attention", "maxpool1d5_relu", "avgpool1d_relu", "cast", "sm_limit",
 ]
 
@@ -297,6 +297,16 @@ def stem_pool(x: torch.Tensor, wt_packed: torch.Tensor, bias: torch.Tensor, out:
     assert out.stride(1) == 55 * pitch and out.stride(0) == 55 * 55 * pitch
     with _Timed("contract_bf16", 2.0 * n * 112 * 112 * 64 * 147):        # 7x7x3 real taps
         _check(_lib.load().avcer_stem_pool_ld(x.data_ptr(), wt_packed.data_ptr(), bias.data_ptr(), n, out.data_ptr(), pitch, _stream()))
+    return out
+
+
+def subsample_rows(x: torch.Tensor, stride: int, out: torch.Tensor) -> torch.Tensor:
+    """x: [n,h,w,c] contiguous; out: [n*ho*wo, c] view (row pitch out.stride(0) >= c) receiving x[:, ::stride, ::stride]."""
+    _cuda(x, "x")
+    n, h, w, c = x.shape
+    assert x.is_contiguous() and out.stride(1) == 1 and out.shape[1] == c and out.dtype == x.dtype
+    assert out.shape[0] == n * ((h - 1) // stride + 1) * ((w - 1) // stride + 1)
+    check(_lib.load().avcer_subsample_rows(x.data_ptr(), n, h, w, c, stride, out.data_ptr(), out.stride(0), dtype_code(x.dtype), _stream()))
     return out
 
 

@@ -89,6 +89,21 @@ def plan_audio(n_samples: int, fps: float, step: float = 0.5, window: int = 4, s
 
 
 # =========================================================================================== engine
+def balanced_batches(n: int, max_batch: int) -> List[Tuple[int, int]]:
+    """[start, end) ranges of ceil(n / max_batch) batches whose sizes differ by at most one (a ragged tail batch of a few
+    items costs almost a full forward's latency; at most two distinct sizes keeps the CUDA-graph cache small)."""
+    if n <= 0:
+        return []
+    nb = -(-n // max_batch)
+    base, extra = divmod(n, nb)
+    out, s = [], 0
+    for i in range(nb):
+        e = s + base + (1 if i < extra else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
 class Engine:
     """Holds the three packed networks and runs clips through K1 -> VS -> VD, A, alignment and K4."""
 
@@ -145,8 +160,7 @@ class Engine:
         n = crops_u8.shape[0]
         probs = torch.empty((n, 7), device=self.device, dtype=torch.float32)
         feats = torch.empty((n, 512), device=self.device, dtype=self.vs.dtype)
-        for s in range(0, n, self.vs_batch):
-            e = min(n, s + self.vs_batch)
+        for s, e in balanced_batches(n, self.vs_batch):
             x = self._vs_input(e - s)
             ops.preprocess(crops_u8[s:e], e - s, x, self.vs.input_layout)
             p, f = self._vs_fwd(x)
@@ -167,11 +181,11 @@ class Engine:
             self._ready = [torch.cuda.Event() for _ in range(2)]
             self._free = [torch.cuda.Event() for _ in range(2)]
         cur = torch.cuda.current_stream()
-        starts = list(range(0, n, bs))
+        ranges = balanced_batches(n, bs)
+        starts = [r[0] for r in ranges]
 
         def issue_copy(i):
-            s0 = starts[i]
-            e0 = min(n, s0 + bs)
+            s0, e0 = ranges[i]
             k = i & 1
             if i >= 2:
                 self._copy_stream.wait_event(self._free[k])
@@ -183,8 +197,7 @@ class Engine:
 
         if starts:
             issue_copy(0)
-        for i, s0 in enumerate(starts):
-            e0 = min(n, s0 + bs)
+        for i, (s0, e0) in enumerate(ranges):
             if i + 1 < len(starts):
                 issue_copy(i + 1)
             k = i & 1
@@ -263,8 +276,7 @@ class Engine:
         en = self._upload(ends, np.int64)
         wn = int(st.numel())
         out = torch.empty((wn, self.a.num_classes), device=self.device, dtype=torch.float32)
-        for s in range(0, wn, self.a_batch):
-            e = min(wn, s + self.a_batch)
+        for s, e in balanced_batches(wn, self.a_batch):
             if self._a_in is None or self._a_in.shape[0] < self.a_batch or self._a_in.shape[1] != win:
                 self._a_in = torch.empty((self.a_batch, win), device=self.device, dtype=torch.float32)
             x = ops.audio_normalize_windows(wav, st[s:e], win, padding, ends=en[s:e], out=self._a_in[:e - s])

@@ -79,8 +79,8 @@ def pack_vs(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
             if bi == 0:
                 wd, bd = _fold_bn(sd[f"{p}.i_downsample.0.weight"], sd, f"{p}.i_downsample.1", eps)
                 blk["ds"] = PackedConv(dev(_tap_major(wd)), dev(bd, torch.float32), cin, planes * 4, 1, stride)
-                if stride == 1:
-                    # conv3 + projection shortcut as ONE contraction over K = [block input | conv2 output]
+                if True:
+                    # conv3 + projection shortcut as ONE contraction over K = [(sampled) block input | conv2 output]
                     # (video.py:46-58: relu(bn3(conv3(t)) + bn_ds(conv_ds(x)))): the shortcut never reaches memory
                     blk["conv3_ds"] = PackedConv(dev(torch.cat([_tap_major(wd), _tap_major(w)], dim=1)), dev(bd + b, torch.float32),
                                                  cin + planes, planes * 4, 1, 1)

@@ -172,6 +172,11 @@ int avcer_stem_pool(const void* x_padded, const void* w_packed, const float* bia
  * conv2's output so that conv3 and the projection shortcut, video.py:46-58, become one K-concatenated GEMM). */
 int avcer_stem_pool_ld(const void* x_padded, const void* w_packed, const float* bias, int n, void* out,
                        int64_t out_pitch, void* stream);
+/* Every stride-th pixel of an NHWC tensor as rows of a [n*ho*wo, y_pitch] matrix (ho = (h-1)/stride+1): the input
+ * sampling of the stride-2 1x1 convolutions of layer2-4's first blocks (architectures/video.py:13-15, 141-148), done once
+ * for conv1 and the projection shortcut; y_pitch >= c leaves room for conv2's output next to it (K-concatenated conv3). */
+int avcer_subsample_rows(const void* x, int n, int h, int w, int c, int stride, void* y, int64_t y_pitch,
+                         int dtype, void* stream);
 /* 3x3 stride-2 un-padded max pool, NHWC (architectures/video.py:103,117). */
 int avcer_maxpool3x3s2(const void* x, int n, int h, int w, int c, void* y, int dtype, void* stream);
 /* Global average pool NHWC -> [n, c] (video.py:124). */

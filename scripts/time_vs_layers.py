@@ -19,7 +19,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 names = ["stem"]
 for li, nb in enumerate((3, 4, 6, 3), 1):
     for b in range(nb):
-        names += ([f"l{li}.{b}.ds"] if b == 0 and not (li == 1 and net.fused_shortcut) else []) + [f"l{li}.{b}.c1", f"l{li}.{b}.c2", f"l{li}.{b}.c3"]
+        names += ([f"l{li}.{b}.ds"] if b == 0 and not net.fused_shortcut else []) + [f"l{li}.{b}.c1", f"l{li}.{b}.c2", f"l{li}.{b}.c3"]
 names.append("fc1")
 
 for it in range(3):

@@ -105,3 +105,14 @@ def test_audio_pack_shapes():
     # weight-norm fold equals the oracle's
     eff = oa.pos_conv_weight(sd)
     assert (w["pos_w"].view(1024, 128, 64).permute(0, 2, 1) - eff).abs().max() < 1e-6
+
+
+def test_balanced_batches_cover_and_differ_by_one():
+    from avcer_b200.pipeline import balanced_batches
+
+    assert balanced_batches(0, 64) == []
+    for n, mb in ((968, 64), (12000, 1024), (1, 64), (64, 64), (65, 64), (250, 256), (1500, 256)):
+        r = balanced_batches(n, mb)
+        assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        sizes = [e - s for s, e in r]
+        assert len(r) == -(-n // mb) and max(sizes) <= mb and max(sizes) - min(sizes) <= 1

@@ -30,8 +30,9 @@ def vs_specs(B=256):
     for li, (P, nb) in enumerate(zip((64, 128, 256, 512), (3, 4, 6, 3)), start=1):
         for bi in range(nb):
             M = B * hw[li] ** 2
-            if bi == 0: specs.append((f"l{li}.{bi}.ds", M, 4 * P, cin))
-            specs += [(f"l{li}.{bi}.c1", M, P, cin), (f"l{li}.{bi}.c2", M, P, 9 * P), (f"l{li}.{bi}.c3", M, 4 * P, P)]
+            # block 0: the projection shortcut is folded into conv3 (K = Cin + P, nets.VSNet.fused_shortcut)
+            specs += [(f"l{li}.{bi}.c1", M, P, cin), (f"l{li}.{bi}.c2", M, P, 9 * P),
+                      (f"l{li}.{bi}.c3" + ("+ds" if bi == 0 else ""), M, 4 * P, P + (cin if bi == 0 else 0))]
             cin = 4 * P
     return specs + [("fc1", B, 512, 2048)]
 
@@ -70,6 +71,7 @@ def section(start_prefix, specs, title, brief):
         if not n.startswith('tc_gemm'): other[n[:40]] += t
     for k, v in sorted(other.items(), key=lambda kv: -kv[1]): print(f"  {v:9.1f} us  {k}")
 
-section('preprocess', vs_specs(), "VS forward, batch 256", False)
+vb = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+section('preprocess', vs_specs(vb), f"VS forward, batch {vb}", False)
 ab = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 section('audio_normalize', a_specs(ab), f"A forward, {ab} windows", True)

@@ -23,7 +23,9 @@ out = []
 for r in data:
     e = {"kernel": r[col["Kernel Name"]][:70], "id": int(r[col["ID"]])}
     for k, m in want.items():
-        if m in col:
+        if m not in col:                     # some ncu versions prefix section metrics ("FBSP.TriageCompute.dram__throughput...")
+            m = next((h for h in hdr if h.endswith("." + m)), m)
+        if m in col and r[col[m]] != "":
             v = float(r[col[m]].replace(",", ""))
             u = units[col[m]]
             if k.startswith("dram_") and k != "dram_pct":
@@ -32,7 +34,9 @@ for r in data:
                 v = v / 1000 if u == "ns" else (v * 1000 if u == "ms" else v)
             e[k] = v
     out.append(e)
-json.dump(out, open(sys.argv[2], "w"), indent=1)
 for e in out:
-    print(f"{e['id']:3d} {e['kernel'][:58]:58s} {e['us']:8.1f} us  tensor {e.get('tensor_pipe_pct', 0):5.1f}%  dram {e.get('dram_pct', 0):5.1f}%  lts {e.get('lts_pct', 0):5.1f}%  "
-          f"issue {e.get('issue_active_pct', 0):5.1f}%  R/W {e.get('dram_read', 0) / 1e6:7.1f}/{e.get('dram_write', 0) / 1e6:7.1f} MB")
+    gbs = (e.get("dram_read", 0) + e.get("dram_write", 0)) / max(e["us"], 1e-9) / 1e3          # bytes / us -> GB/s
+    e["dram_gbs"] = gbs
+    print(f"{e['id']:3d} {e['kernel'][:58]:58s} {e['us']:8.1f} us  tensor {e.get('tensor_pipe_pct', 0):5.1f}%  dram {gbs:6.0f} GB/s ({gbs / 6452.8:4.2f} of copy peak)  "
+          f"lts {e.get('lts_pct', 0):5.1f}%  issue {e.get('issue_active_pct', 0):5.1f}%  R/W {e.get('dram_read', 0) / 1e6:7.1f}/{e.get('dram_write', 0) / 1e6:7.1f} MB")
+json.dump(out, open(sys.argv[2], "w"), indent=1)

@@ -37,10 +37,16 @@ conv(B, 14, 14, 256, 256, 3)                 # l3.c2  two-SM implicit GEMM (MMA 
 conv(B, 55, 55, 64, 256, 1, res=True)        # l1.c3  flat epilogue + residual (HBM bound)
 conv(B, 14, 14, 256, 1024, 1, res=True)      # l3.c3  flat epilogue + residual
 conv(B, 55, 55, 256, 64, 1)                  # l1.c1  64-wide tiles (HBM bound)
+xc = torch.randn(B * 55 * 55, 128, device=dev).to(bf); wc = (torch.randn(256, 128, device=dev) / 11).to(bf); bc = torch.zeros(256, device=dev)
+for _ in range(2):
+    ops.linear(xc, wc, bc, act=ops.ACT_RELU)  # l1.0 conv3 + projection shortcut as one K = 128 GEMM (no residual read)
 # audio: FFN GEMM with GELU and attention, 64 windows
 x = torch.randn(64 * 199, 1024, device=dev).to(bf); w = (torch.randn(4096, 1024, device=dev) / 32).to(bf); b = torch.zeros(4096, device=dev)
 for _ in range(2):
     ops.linear(x, w, b, act=ops.ACT_GELU)
+f4 = torch.randn(64 * 199, 4096, device=dev).to(bf); w2 = (torch.randn(1024, 4096, device=dev) / 64).to(bf); b2 = torch.zeros(1024, device=dev)
+for _ in range(2):
+    ops.linear(f4, w2, b2, residual=x)        # FFN-out GEMM: barrier epilogue with the 4-deep residual ring
 qkv = torch.randn(64 * 199, 3072, device=dev).to(bf)
 for _ in range(2):
     ops.attention(qkv, 64, 199, 16, 64, 0.125)

@@ -111,3 +111,35 @@ def test_pipeline_compound_top1_agreement(cuda_lib, init):
         # the same engine through CUDA graphs (second call replays) gives identical labels
         again = eng.run_clips(torch.from_numpy(crops[exists]), [exists], [fps], torch.from_numpy(wav), [len(wav)], w1, w2, False, True)
         assert torch.equal(again["labels"], out["labels"])
+
+
+def test_side_by_side_branches_match_serial_pipeline(cuda_lib):
+    """Engine(overlap=(vs_sms, a_sms)) runs the VS / VD branch and the audio branch on two streams with per-branch SM
+    shares (avcer_set_sm_limit); grid sizes do not enter any reduction order, so every output must be bit-identical to the
+    one-stream pipeline (two clips, a gap, ragged batches, host and device inputs)."""
+    from avcer_b200 import get_weights_matrices as gwm
+    from avcer_b200.pipeline import Engine
+
+    fps = [25, 30]
+    exists = [np.ones(70, bool), np.ones(45, bool)]
+    exists[0][[7, 8]] = False
+    crops = syn.make_crops(321, int(exists[0].sum() + exists[1].sum()))
+    wavs = [syn.make_wav(322, 44000), syn.make_wav(323, 24000 - 160)]
+    wav = np.concatenate(wavs)
+    sds = (syn.make_vs_state_dict(0, "default"), syn.make_vd_state_dict(1), syn.make_audio_state_dict(2, 8, "spread", 12))
+    w1, w2 = gwm.class_weights(gwm.weights_3), [1, 1, 1]
+    outs = []
+    for overlap in (None, (74, 74), (100, 48)):
+        eng = Engine(*sds, precision="bf16", device="cuda:0", vs_batch=48, a_batch=4, overlap=overlap)
+        for dev_inputs in (False, True):
+            c = torch.from_numpy(crops).to("cuda:0") if dev_inputs else torch.from_numpy(crops).pin_memory()
+            w = torch.from_numpy(wav).to("cuda:0") if dev_inputs else torch.from_numpy(wav)
+            out = eng.run_clips(c, exists, fps, w, [len(x) for x in wavs], w1, w2, False, True)
+            torch.cuda.synchronize()
+            outs.append({k: v.cpu() for k, v in out.items()})
+    for o in outs[1:]:
+        for k in ("labels", "stat", "dyn"):
+            assert torch.equal(o[k], outs[0][k]), k
+        for k in ("audio_mean", "window_logits"):
+            assert torch.equal(torch.nan_to_num(o[k], nan=-7.0), torch.nan_to_num(outs[0][k], nan=-7.0)), k
+    assert cuda_lib.load().avcer_set_sm_limit(3) != 0 and cuda_lib.load().avcer_set_sm_limit(0) == 0

@@ -56,6 +56,26 @@ def test_vs_batch_invariance_and_tails(cuda_lib):
     assert np.array_equal(p_all[::-1], p_rev)
 
 
+def test_vs_config2_full_batch_against_oracle(cuda_lib):
+    """BASELINE config 2 at full size: 256 crops through K1 + the bf16 VS forward (one batch, every fused path: stem + pool,
+    K-concatenated shortcuts, FLAT residual epilogues) against the fp32 oracle of architectures/video.py on the same crops;
+    north-star tolerance 2e-3 on the per-class probabilities with PyTorch-default random init, and identical arg-max
+    wherever the oracle's top-2 margin exceeds twice that."""
+    crops = syn.make_crops(77, 256)
+    sd = syn.make_vs_state_dict(0, "default")
+    probs, feat = _vs_probs(sd, "bf16", crops)
+    x = torch.from_numpy(np.stack([ov.pth_processing(c)[0] for c in crops]))
+    logits, ofeat = ov.resnet50_forward(sd, x)
+    ref = torch.softmax(logits, dim=1).numpy()
+    assert probs.shape == ref.shape == (256, 7)
+    err = np.abs(probs - ref).max()
+    assert err < 2e-3, err
+    top2 = np.sort(ref, axis=1)[:, -2:]
+    sure = (top2[:, 1] - top2[:, 0]) > 4e-3
+    assert np.array_equal(probs.argmax(1)[sure], ref.argmax(1)[sure])
+    assert np.abs(feat - np.maximum(ofeat.numpy(), 0)).max() < 0.15
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 def test_vd_matches_reference_golden(cuda_lib, golden, prec):
     from avcer_b200 import nets

@@ -71,7 +71,9 @@ _SIGNATURES = {
     "avcer_softmax7": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "avcer_softmax7_f64": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "avcer_window_to_frame_mean": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "avcer_window_to_frame_mean_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "avcer_gather_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "avcer_gather_rows_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "avcer_stem_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "avcer_stem_pool_ld": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     "avcer_maxpool3x3s2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),

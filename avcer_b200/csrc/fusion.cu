@@ -192,11 +192,27 @@ __global__ void softmax7_kernel(const T* __restrict__ x, long long n, int ld, T*
   for (int c = 0; c < 7; ++c) y[i * 7 + c] = v[c] / s;
 }
 
-// pandas group_mean for float32: Kahan-compensated float32 sum in row order, NaN skipped,
-// divided by the float32 count; nobs == 0 -> NaN.
-__global__ void window_to_frame_mean_kernel(const float* __restrict__ logits, int n_win, int ncls,
+// pandas group_mean: Kahan-compensated sum in the column dtype (float32 for the in-memory drivers' tables, float64 for
+// tables read back from CSV, get_pred_av.py:246-249) in row order, NaN skipped, divided by the count in that dtype;
+// nobs == 0 -> NaN.
+template <typename T> struct KahanOps;
+template <> struct KahanOps<float> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ float nan() { return __int_as_float(0x7fc00000); }
+};
+template <> struct KahanOps<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  static __device__ __forceinline__ double nan() { return __longlong_as_double(0x7ff8000000000000ll); }
+};
+template <typename T>
+__global__ void window_to_frame_mean_kernel(const T* __restrict__ logits, int n_win, int ncls,
                                             const int* __restrict__ f_lo, const int* __restrict__ f_hi,
-                                            long long n_frames, float* __restrict__ out) {
+                                            long long n_frames, T* __restrict__ out) {
+  using K = KahanOps<T>;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_frames * ncls) return;
   const long long f = i / ncls;
@@ -207,30 +223,31 @@ __global__ void window_to_frame_mean_kernel(const float* __restrict__ logits, in
     const int mid = (lo + hi) >> 1;
     if ((long long)f_hi[mid] > f) hi = mid; else lo = mid + 1;
   }
-  float sum = 0.f, comp = 0.f, nobs = 0.f;
+  T sum = 0, comp = 0, nobs = 0;
   for (int w = lo; w < n_win && (long long)f_lo[w] <= f; ++w) {
     if ((long long)f_hi[w] <= f) continue;
-    const float val = logits[(long long)w * ncls + c];
+    const T val = logits[(long long)w * ncls + c];
     if (val == val) {
-      nobs = __fadd_rn(nobs, 1.0f);
-      const float y = __fsub_rn(val, comp);
-      const float t = __fadd_rn(sum, y);
-      comp = __fsub_rn(__fsub_rn(t, sum), y);
-      if (comp != comp) comp = 0.f;
+      nobs = K::add(nobs, (T)1);
+      const T y = K::sub(val, comp);
+      const T t = K::add(sum, y);
+      comp = K::sub(K::sub(t, sum), y);
+      if (comp != comp) comp = 0;
       sum = t;
     }
   }
-  out[i] = nobs == 0.f ? __int_as_float(0x7fc00000) : __fdiv_rn(sum, nobs);
+  out[i] = nobs == (T)0 ? K::nan() : K::div(sum, nobs);
 }
 
-__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, long long n_out,
-                                   int ncols, const int* __restrict__ perm, float* __restrict__ out) {
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ src, const int* __restrict__ idx, long long n_out,
+                                   int ncols, const int* __restrict__ perm, T* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_out * ncols) return;
   const long long r = i / ncols;
   const int c = (int)(i % ncols);
   const int s = idx ? idx[r] : (int)r;
-  out[i] = s >= 0 ? src[(long long)s * ncols + (perm ? perm[c] : c)] : 0.f;
+  out[i] = s >= 0 ? src[(long long)s * ncols + (perm ? perm[c] : c)] : (T)0;
 }
 
 // data/utils.py:222-241 as a stand-alone op (the reference exposes it as a function): arbitrary
@@ -413,8 +430,18 @@ extern "C" int avcer_window_to_frame_mean(const float* logits, int n_win, int nc
   AVCER_REQUIRE(n_win >= 0 && ncls > 0 && n_frames >= 0, "window_to_frame_mean: bad shape");
   const long long tot = n_frames * ncls;
   if (tot == 0) return 0;
-  window_to_frame_mean_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, as_stream(stream)>>>(logits, n_win, ncls, f_lo,
-                                                                                             f_hi, n_frames, out);
+  window_to_frame_mean_kernel<float><<<(unsigned)((tot + 255) / 256), 256, 0, as_stream(stream)>>>(logits, n_win, ncls, f_lo,
+                                                                                                    f_hi, n_frames, out);
+  return check_launch("window_to_frame_mean_kernel");
+}
+
+extern "C" int avcer_window_to_frame_mean_f64(const double* logits, int n_win, int ncls, const int32_t* f_lo,
+                                              const int32_t* f_hi, int64_t n_frames, double* out, void* stream) {
+  AVCER_REQUIRE(n_win >= 0 && ncls > 0 && n_frames >= 0, "window_to_frame_mean: bad shape");
+  const long long tot = n_frames * ncls;
+  if (tot == 0) return 0;
+  window_to_frame_mean_kernel<double><<<(unsigned)((tot + 255) / 256), 256, 0, as_stream(stream)>>>(logits, n_win, ncls, f_lo,
+                                                                                                     f_hi, n_frames, out);
   return check_launch("window_to_frame_mean_kernel");
 }
 
@@ -423,8 +450,18 @@ extern "C" int avcer_gather_rows(const float* src, const int32_t* src_index, int
   AVCER_REQUIRE(n_out >= 0 && ncols > 0, "gather_rows: bad shape");
   const long long tot = n_out * ncols;
   if (tot == 0) return 0;
-  gather_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, as_stream(stream)>>>(src, src_index, n_out, ncols, perm,
-                                                                                   out);
+  gather_rows_kernel<float><<<(unsigned)((tot + 255) / 256), 256, 0, as_stream(stream)>>>(src, src_index, n_out, ncols, perm,
+                                                                                          out);
+  return check_launch("gather_rows_kernel");
+}
+
+extern "C" int avcer_gather_rows_f64(const double* src, const int32_t* src_index, int64_t n_out, int ncols,
+                                     const int32_t* perm, double* out, void* stream) {
+  AVCER_REQUIRE(n_out >= 0 && ncols > 0, "gather_rows: bad shape");
+  const long long tot = n_out * ncols;
+  if (tot == 0) return 0;
+  gather_rows_kernel<double><<<(unsigned)((tot + 255) / 256), 256, 0, as_stream(stream)>>>(src, src_index, n_out, ncols, perm,
+                                                                                           out);
   return check_launch("gather_rows_kernel");
 }
 

@@ -266,11 +266,13 @@ def softmax7(x: torch.Tensor) -> torch.Tensor:
 
 
 def window_to_frame_mean(logits: torch.Tensor, f_lo: torch.Tensor, f_hi: torch.Tensor, n_frames: int) -> torch.Tensor:
+    """pandas groupby.mean in the dtype of `logits` (float32 or float64), see avcer_window_to_frame_mean."""
     _cuda(logits, "logits")
     n_win, ncls = logits.shape
-    out = torch.empty((n_frames, ncls), device=logits.device, dtype=torch.float32)
-    check(_lib.load().avcer_window_to_frame_mean(logits.data_ptr(), n_win, ncls, f_lo.data_ptr(), f_hi.data_ptr(),
-                                                 n_frames, out.data_ptr(), _stream()))
+    assert logits.dtype in (torch.float32, torch.float64) and logits.is_contiguous()
+    out = torch.empty((n_frames, ncls), device=logits.device, dtype=logits.dtype)
+    fn = _lib.load().avcer_window_to_frame_mean if logits.dtype == torch.float32 else _lib.load().avcer_window_to_frame_mean_f64
+    check(fn(logits.data_ptr(), n_win, ncls, f_lo.data_ptr(), f_hi.data_ptr(), n_frames, out.data_ptr(), _stream()))
     return out
 
 
@@ -278,8 +280,10 @@ def gather_rows(src: torch.Tensor, index: Optional[torch.Tensor], n_out: int, pe
     _cuda(src, "src")
     ncols = src.shape[1] if perm is None else perm.numel()
     assert perm is None or ncols == src.shape[1]
-    out = torch.empty((n_out, ncols), device=src.device, dtype=torch.float32)
-    check(_lib.load().avcer_gather_rows(src.data_ptr(), _ptr(index), n_out, ncols, _ptr(perm), out.data_ptr(), _stream()))
+    assert src.dtype in (torch.float32, torch.float64) and src.is_contiguous()
+    out = torch.empty((n_out, ncols), device=src.device, dtype=src.dtype)
+    fn = _lib.load().avcer_gather_rows if src.dtype == torch.float32 else _lib.load().avcer_gather_rows_f64
+    check(fn(src.data_ptr(), _ptr(index), n_out, ncols, _ptr(perm), out.data_ptr(), _stream()))
     return out
 
 

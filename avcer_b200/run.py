@@ -26,12 +26,15 @@ COLUMN_NAMES = ["image_location", "Fearfully_Surprised", "Happily_Surprised", "S
 
 def audio_frame_rows(audio_df: pd.DataFrame, dev, dropna: bool = False):
     """groupby("frames").mean() of the long-format audio table on the GPU.  Returns (sorted unique
-    frame ids [U], per-frame means [U, ncls] fp32 device tensor)."""
+    frame ids [U], per-frame means [U, ncls] device tensor in the table's dtype, value columns)."""
     if dropna:
         audio_df = audio_df.dropna()
     cols = [c for c in audio_df.columns if c != "frames"]
     ids = audio_df["frames"].str.slice(0, -4).astype(np.int64).to_numpy()
-    vals = np.ascontiguousarray(audio_df[cols].to_numpy(dtype=np.float32))
+    # pandas accumulates a group in the column dtype: float32 for the tables the audio drivers return, float64 for
+    # tables read back from CSV (get_pred_av.py:246-249)
+    f64 = all(audio_df[c].dtype == np.float64 for c in cols)
+    vals = np.ascontiguousarray(audio_df[cols].to_numpy(dtype=np.float64 if f64 else np.float32))
     order = np.argsort(ids, kind="stable")               # pandas accumulates each group in row order
     ids_s = ids[order]
     uniq, first = np.unique(ids_s, return_index=True)
@@ -70,7 +73,7 @@ def aligned_probabilities(stat_df, dyn_df, audio_df, name_video, dropna_audio=Fa
     a_rows = ops.gather_rows(means, torch.from_numpy(sel.astype(np.int32)).to(dev), len(sel))
     p_a = ops.softmax7(a_rows)
     # bring the three streams to one dtype (numpy promotes mixed float32/float64 to float64)
-    if p_vs.dtype == torch.float64 or p_vd.dtype == torch.float64:
+    if torch.float64 in (p_vs.dtype, p_vd.dtype, p_a.dtype):
         p_vs, p_vd, p_a = p_vs.double(), p_vd.double(), p_a.double()
     return p_vs.contiguous(), p_vd.contiguous(), p_a.contiguous(), image_location
 

@@ -150,12 +150,18 @@ int avcer_softmax7_f64(const double* x, int64_t n, int ld, double* y, void* stre
  * contract.  logits: [n_win, ncls]; out: [n_frames, ncls]; frames never covered get NaN. */
 int avcer_window_to_frame_mean(const float* logits, int n_win, int ncls, const int32_t* f_lo,
                                const int32_t* f_hi, int64_t n_frames, float* out, void* stream);
+/* Same in float64: pandas accumulates in the column dtype, and the tables get_pred_av.py:246-249 reads back from CSV
+ * are float64. */
+int avcer_window_to_frame_mean_f64(const double* logits, int n_win, int ncls, const int32_t* f_lo,
+                                   const int32_t* f_hi, int64_t n_frames, double* out, void* stream);
 
 /* Gather rows: out[i,:] = src_index[i] >= 0 ? src[src_index[i], :] : 0   (carry-forward / gap
  * expansion of get_prob_video.py:157-178, and column permutation to audio order run.py:85-88
  * when `perm` is non-NULL: out[i, j] = src[idx, perm[j]]). */
 int avcer_gather_rows(const float* src, const int32_t* src_index, int64_t n_out, int ncols,
                       const int32_t* perm, float* out, void* stream);
+int avcer_gather_rows_f64(const double* src, const int32_t* src_index, int64_t n_out, int ncols,
+                          const int32_t* perm, double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Small layers of the VS / VD / A networks (channels-last).  `dtype` selects bf16 or fp32 storage.

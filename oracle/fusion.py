@@ -101,6 +101,36 @@ def get_c_expr_db_pred(stat_df, dyn_df, audio_df, name_video, weights_1, weights
     return av, vs, vd, a, loc
 
 
+def pred_av_labels(fmt_df: pd.DataFrame, tables: dict, name_videos, weights_1, weights_2, ce_weights_type, ce_mask):
+    """Restatement of get_pred_av.get_c_expr_db_pred (get_pred_av.py:198-334) on DataFrames instead of CSV paths:
+    `tables[video] = (static_df, dynamic_df, audio_long_df)` as pd.read_csv returns them (float64 columns), `fmt_df` the
+    challenge's frame list (column image_location).  Returns (compound labels [n] int64, image_locations)."""
+    cols = AUDIO_ORDER[:7]
+    fmt_video = [i.split("/")[0] for i in fmt_df.image_location]
+    p_vs, p_vd, p_a, locs = [], [], [], []
+    for video in name_videos:
+        stat, dyn, audio = tables[video]
+        loc_s = [f"{video}/{str(f + 1).zfill(5)}.jpg" for f in stat.index]
+        loc_d = [f"{video}/{str(f + 1).zfill(5)}.jpg" for f in dyn.index]
+        a = audio.dropna().groupby(["frames"]).mean().reset_index()
+        a_loc = [image_location(video, f) for f in a["frames"]]
+        wanted = [l for l, v in zip(fmt_df.image_location, fmt_video) if v == video]
+        keep = set(wanted)
+        vs = stat[[l in keep for l in loc_s]][cols].values
+        vd = softmax(dyn[[l in keep for l in loc_d]][cols].values)
+        av = a[[l in keep for l in a_loc]][cols].values
+        if len(wanted) > len(av):
+            av = np.vstack((av, [av[-1]] * (len(wanted) - len(av))))
+        p_vs.append(vs); p_vd.append(vd); p_a.append(softmax(av)); locs.extend(wanted)
+    preds = [np.concatenate(p_vs), np.concatenate(p_vd), np.concatenate(p_a)]
+    w1 = np.asarray(weights_1, dtype=np.float64)
+    final = preds[0] * w1[0] * weights_2[0]
+    for i in range(1, 3):
+        final = final + preds[i] * w1[i] * weights_2[i]
+    prob = compound_scores(final, ce_weights_type, ce_mask)
+    return np.argmax(prob[:, :7], axis=1), locs
+
+
 # ------------------------------------------------------------------------------------------------ weight search
 def metrics_for_fusion(true, pred):
     """utils.py:115-122: precision, f1 and recall (UAR) averaged over classes 1..6 of sklearn's report."""

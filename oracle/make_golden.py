@@ -312,6 +312,74 @@ def make_resample(wd):
     print("resample.npz")
 
 
+def pred_av_tables():
+    """Two clips shaped like the CSVs the drivers write (video columns in VIDEO_ORDER, long-format audio table with NaN
+    rows and a `frames` column); the second clip's audio stops early so the repeat-last-row rule applies."""
+    tables = {}
+    for k, (name, n, seed) in enumerate((("clipA", 120, 21), ("clipB", 90, 22))):
+        stat_df, dyn_df, audio_df = synthetic_fusion_inputs(seed, n)
+        if k == 1:
+            ids = audio_df["frames"].str.slice(0, -4).astype(int)
+            audio_df = audio_df[ids < 70].reset_index(drop=True)
+        tables[name] = (stat_df, dyn_df, audio_df)
+    locs = [f"clipA/{str(f + 1).zfill(5)}.jpg" for f in range(120) if f not in (3, 4, 57, 119)]
+    locs += [f"clipB/{str(f + 1).zfill(5)}.jpg" for f in range(90)]
+    fmt = pd.DataFrame({"image_location": locs})
+    for c in ("Fearfully_Surprised", "Happily_Surprised", "Sadly_Surprised", "Disgustedly_Surprised", "Angrily_Surprised",
+              "Sadly_Fearful", "Sadly_Angry"):
+        fmt[c] = 0
+    return tables, fmt
+
+
+def write_pred_av_files(root, tables, fmt):
+    """The directory layout get_pred_av.get_c_expr_db_pred reads (get_pred_av.py:232-249)."""
+    os.makedirs(os.path.join(root, "video"), exist_ok=True)
+    os.makedirs(os.path.join(root, "audio_mean_0.5", "model"), exist_ok=True)
+    for name, (stat_df, dyn_df, audio_df) in tables.items():
+        stat_df.to_csv(os.path.join(root, "video", f"static__{name}.csv"), index=False)
+        dyn_df.to_csv(os.path.join(root, "video", f"dynamic__{name}.csv"), index=False)
+        audio_df.to_csv(os.path.join(root, "audio_mean_0.5", "model", f"{name}.csv"), index=False)
+    fmt_path = os.path.join(root, "format.txt")
+    fmt.to_csv(fmt_path, index=False)
+    return fmt_path, ["video", "audio_mean_0.5", "model"]
+
+
+PRED_AV_CONFIGS = [("av8", [1, 1, 1], False, True), ("av8", [1, 1, 1], True, False), ("av8", "double", True, True), ("av7", [1, 1, 1], False, False)]
+
+
+def pred_av_weights(tag, w2):
+    from avcer_b200 import get_weights_matrices as gwm
+
+    table = gwm.weights_3 if tag == "av8" else gwm.weights_2
+    w1 = gwm.class_weights(table)
+    if tag == "av7":                        # two-stream table (video, audio): the dynamic stream gets zero weight
+        w1 = [w1[0], [0.0] * 7, w1[1]]
+    return np.asarray(w1, dtype=np.float64), (gwm.model_weights(gwm.weights_3) if w2 == "double" else w2)
+
+
+def make_pred_av(wd):
+    """The unmodified get_pred_av.get_c_expr_db_pred (get_pred_av.py:198-334) on CSV files written here."""
+    import get_pred_av as ref_pa
+
+    tables, fmt = pred_av_tables()
+    root = os.path.join(wd, "preds")
+    fmt_path, path_preds = write_pred_av_files(root, tables, fmt)
+    read = {n: (pd.read_csv(os.path.join(root, "video", f"static__{n}.csv")), pd.read_csv(os.path.join(root, "video", f"dynamic__{n}.csv")),
+                pd.read_csv(os.path.join(root, "audio_mean_0.5", "model", f"{n}.csv"))) for n in tables}
+    out = {}
+    for i, (tag, w2, cwt, cm) in enumerate(PRED_AV_CONFIGS):
+        w1, w2v = pred_av_weights(tag, w2)
+        ref_pa.get_c_expr_db_pred(fmt_path, root, path_preds, list(tables), w1, w2v, tag, f"cfg{i}", cwt, cm)
+        txt = pd.read_csv(os.path.join("src", "pred_results", "DF_C_EXPR_DB", f"C_EXPR_DB_{tag}_sd_cfg{i}_{cwt}_{cm}.txt"))
+        labels = txt.iloc[:, 1].to_numpy(dtype=np.int64)
+        mine, locs = of.pred_av_labels(pd.read_csv(fmt_path), read, list(tables), w1, w2v, cwt, cm)
+        assert list(txt.iloc[:, 0]) == locs and np.array_equal(labels, mine), (tag, w2, cwt, cm)
+        out[f"labels_{i}"] = labels
+    out["n_locations"] = np.int64(len(locs))
+    np.savez_compressed(os.path.join(OUT, "pred_av.npz"), **out)
+    print("pred_av.npz")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -324,6 +392,7 @@ def main():
         make_video(wd)
         make_audio()
         make_resample(wd)
+        make_pred_av(wd)
 
 
 if __name__ == "__main__":

@@ -163,3 +163,24 @@ def test_weight_search_dropins_match_reference(cuda_lib, golden):
         np.add.at(ref, (gt[:577], np.argmax(final, axis=-1)), 1)
         assert np.array_equal(cm[w], ref)
     assert cm.sum() == 300 * 577
+
+
+def test_get_pred_av_dropin_matches_reference(cuda_lib, golden, tmp_path, monkeypatch):
+    """Row a18: avcer_b200.get_pred_av.get_c_expr_db_pred on the CSV files (float64 tables: per-frame audio means and
+    softmax in float64 like pandas / numpy do) writes exactly the labels the unmodified reference wrote."""
+    import pandas as pd
+
+    from avcer_b200 import get_pred_av
+    from oracle.make_golden import PRED_AV_CONFIGS, pred_av_tables, pred_av_weights, write_pred_av_files
+
+    g = golden["pred_av"]
+    tables, fmt = pred_av_tables()
+    root = str(tmp_path / "preds")
+    fmt_path, path_preds = write_pred_av_files(root, tables, fmt)
+    monkeypatch.chdir(tmp_path)
+    for i, (tag, w2, cwt, cm) in enumerate(PRED_AV_CONFIGS):
+        w1, w2v = pred_av_weights(tag, w2)
+        labels, locs = get_pred_av.get_c_expr_db_pred(fmt_path, root, path_preds, list(tables), w1, w2v, tag, f"cfg{i}", cwt, cm)
+        assert len(locs) == int(g["n_locations"]) and np.array_equal(np.asarray(labels), g[f"labels_{i}"]), (tag, w2, cwt, cm)
+        txt = pd.read_csv(tmp_path / "src" / "pred_results" / "DF_C_EXPR_DB" / f"C_EXPR_DB_{tag}_sd_cfg{i}_{cwt}_{cm}.txt")
+        assert list(txt.iloc[:, 0]) == locs and np.array_equal(txt.iloc[:, 1].to_numpy(), g[f"labels_{i}"])

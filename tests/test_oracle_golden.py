@@ -118,3 +118,20 @@ def test_resample_matches_reference(golden):
         bank, orig, nnew, width = ops.sinc_resample_bank(sr, 16000)
         okern, owidth, oorig, onew = oa.sinc_resample_kernel(sr, 16000)
         assert (orig, nnew, width) == (oorig, onew, owidth) and np.array_equal(bank, okern), name
+
+
+def test_pred_av_labels_match_reference(golden, tmp_path):
+    """get_pred_av.get_c_expr_db_pred (get_pred_av.py:198-334): the restatement on the CSV tables against the labels the
+    unmodified reference wrote for the same files (two clips, dropped frames, NaN audio rows, repeat-last-row tail)."""
+    from oracle.make_golden import PRED_AV_CONFIGS, pred_av_tables, pred_av_weights, write_pred_av_files
+
+    g = golden["pred_av"]
+    tables, fmt = pred_av_tables()
+    root = str(tmp_path / "preds")
+    fmt_path, path_preds = write_pred_av_files(root, tables, fmt)
+    read = {n: (pd.read_csv(f"{root}/video/static__{n}.csv"), pd.read_csv(f"{root}/video/dynamic__{n}.csv"),
+                pd.read_csv(f"{root}/audio_mean_0.5/model/{n}.csv")) for n in tables}
+    for i, (tag, w2, cwt, cm) in enumerate(PRED_AV_CONFIGS):
+        w1, w2v = pred_av_weights(tag, w2)
+        labels, locs = of.pred_av_labels(pd.read_csv(fmt_path), read, list(tables), w1, w2v, cwt, cm)
+        assert len(locs) == int(g["n_locations"]) and np.array_equal(labels, g[f"labels_{i}"]), (tag, w2, cwt, cm)

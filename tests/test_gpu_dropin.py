@@ -143,3 +143,58 @@ def test_side_by_side_branches_match_serial_pipeline(cuda_lib):
         for k in ("audio_mean", "window_logits"):
             assert torch.equal(torch.nan_to_num(o[k], nan=-7.0), torch.nan_to_num(outs[0][k], nan=-7.0)), k
     assert cuda_lib.load().avcer_set_sm_limit(3) != 0 and cuda_lib.load().avcer_set_sm_limit(0) == 0
+
+
+def test_run_inference_end_to_end(cuda_lib, tmp_path):
+    """Row a1: run.run_inference (run.py:192-308) from files -- an .avi for fps / frame count, JPEG face crops of track 00
+    with a gap, a 44.1 kHz stereo .wav next to the video (what the reference's ffmpeg step leaves; resampled on the GPU)
+    -- against the oracle of the same path fed with the same files, fp32 mode."""
+    import wave
+
+    import pandas as pd
+
+    from avcer_b200 import config, get_weights_matrices as gwm, run
+    from oracle import audio as oa, fusion as of, video as ov
+
+    n, fps = 60, 25
+    frames = syn.make_crops(41, n, 120)
+    missing = {17, 18}
+    video = tmp_path / "clip.avi"
+    vw = cv2.VideoWriter(str(video), cv2.VideoWriter_fourcc(*"MJPG"), fps, (64, 48))
+    assert vw.isOpened()
+    for i in range(n):
+        vw.write(np.ascontiguousarray(frames[i][:48, :64]))
+    vw.release()
+    out_dir = tmp_path / "out"
+    os.makedirs(out_dir / "clip" / "00")
+    for i in range(n):
+        if i not in missing:
+            cv2.imwrite(str(out_dir / "clip" / "00" / f"{i:06d}.jpg"), frames[i])
+    rng = np.random.default_rng(43)
+    t = np.arange(int(n / fps * 44100)) / 44100.0
+    pcm = np.stack([7000 * np.sin(2 * np.pi * 330 * t) + 2500 * rng.standard_normal(t.size),
+                    5000 * np.sin(2 * np.pi * 990 * t) + 2500 * rng.standard_normal(t.size)], axis=1).astype(np.int16)
+    with wave.open(str(tmp_path / "clip.wav"), "wb") as f:
+        f.setnchannels(2); f.setsampwidth(2); f.setframerate(44100)
+        f.writeframes(pcm.astype("<i2").tobytes())
+    sd_vs, sd_vd = syn.make_vs_state_dict(0, "spread"), syn.make_vd_state_dict(1)
+    sd_a = syn.make_audio_state_dict(2, 8, "spread", 12)
+    config.set_precision("fp32")
+    config.set_state_dicts(vs=sd_vs, vd=sd_vd, audio={8: sd_a})
+    w1, w2 = gwm.class_weights(gwm.weights_3), [1, 1, 1]
+    try:
+        run.run_inference(path_video=str(video), path_save_results=str(out_dir), flag_save_prob=False, weights_prob_model=w1,
+                          weights_model=w2, ce_weights_type=False, ce_mask=True, flag_save_plot_pred=True)
+    finally:
+        config.reset()
+        config.set_precision("bf16")
+    got = np.load(out_dir / "predicted_CEs.npz")
+    crops = [cv2.imread(str(out_dir / "clip" / "00" / f"{i:06d}.jpg")) if i not in missing else None for i in range(n)]
+    o_dyn, o_stat = ov.predict_video(crops, fps, sd_vs, sd_vd)
+    rows, ids, _ = oa.predict_audio(oa.pcm16_to_mono_16k(pcm, 44100, 16000), fps, sd_a)
+    stat_df, dyn_df = pd.DataFrame(o_stat, columns=of.VIDEO_ORDER), pd.DataFrame(o_dyn, columns=of.VIDEO_ORDER)
+    audio_df = pd.DataFrame(rows, columns=of.AUDIO_ORDER)
+    audio_df["frames"] = [str(i).zfill(6) + ".jpg" for i in ids]
+    ref = of.get_c_expr_db_pred(stat_df, dyn_df, audio_df, "clip", w1, w2, False, True)
+    for key, want in zip(("AV", "VS", "VD", "A"), ref[:4]):
+        assert got[key].shape == (n,) and (got[key] == np.asarray(want)).mean() >= 0.98, key

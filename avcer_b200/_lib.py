@@ -68,6 +68,7 @@ _SIGNATURES = {
     "avcer_fuse_compound_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_int, c_void_p, c_void_p]),
     "avcer_compound_scores": (c_int, [c_void_p, c_int64, c_int, c_int, POINTER(c_int32), POINTER(c_double), c_int, c_int, c_void_p, c_void_p]),
     "avcer_weight_search_confusion": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "avcer_fused_argmax": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "avcer_softmax7": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "avcer_softmax7_f64": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "avcer_window_to_frame_mean": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -341,6 +341,25 @@ weight_search_kernel(const double* __restrict__ preds, long long n, const int* _
       if (my[i]) atomicAdd(cm + ws * 49 + i, (unsigned long long)my[i]);
 }
 
+// Weighted fusion + arg-max over the 7 basic emotions (get_pred_av.py:34-40, get_metrics): final = P_0 * W1[0] * W2[0];
+// final += P_m * W1[m] * W2[m]; np.argmax(final, axis=-1) -- float64, left to right, first maximum, NaN counts as largest.
+__global__ void fused_argmax_kernel(const double* __restrict__ preds, int n_models, long long n, const double* __restrict__ w1,
+                                    const double* __restrict__ w2, int* __restrict__ labels) {
+  const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  double best = 0.0;
+  int bi = 0;
+#pragma unroll
+  for (int c = 0; c < 7; ++c) {
+    double v = __dmul_rn(__dmul_rn(preds[f * 7 + c], w1[c]), w2[0]);
+    for (int m = 1; m < n_models; ++m)
+      v = __dadd_rn(v, __dmul_rn(__dmul_rn(preds[((long long)m * n + f) * 7 + c], w1[m * 7 + c]), w2[m]));
+    if (c == 0) { best = v; bi = 0; }
+    else if (v > best || (v != v && best == best)) { best = v; bi = c; }
+  }
+  labels[f] = bi;
+}
+
 }  // namespace avcer
 
 using namespace avcer;
@@ -506,4 +525,12 @@ extern "C" int avcer_weight_search_confusion(const double* preds, int n_models, 
     weight_search_kernel<2><<<grid, WS_WARPS * 32, smem, st>>>(preds, n, gt, weights, n_weights, fg, (unsigned long long*)cm);
   }
   return check_launch("weight_search_kernel");
+}
+
+extern "C" int avcer_fused_argmax(const double* preds, int n_models, int64_t n, const double* w1, const double* w2,
+                                  int32_t* labels, void* stream) {
+  AVCER_REQUIRE(n_models >= 1 && n >= 0, "fused_argmax: bad sizes");
+  if (n == 0) return 0;
+  fused_argmax_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(preds, n_models, (long long)n, w1, w2, labels);
+  return check_launch("fused_argmax_kernel");
 }

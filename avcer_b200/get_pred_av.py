@@ -10,17 +10,25 @@ import numpy as np
 import pandas as pd
 import torch
 
-from . import config, ops
+from . import _lib, config, ops
 from .data.utils import get_image_location, save_txt  # noqa: F401
 from .run import COLUMN_NAMES, NAME_EMO, audio_frame_rows
 
 
 def fused_argmax(predictions, weights_1, weights_2):
-    """get_metrics :34-40: argmax over the 7 basic emotions of sum_m P_m * W1[m] * W2[m] (float64)."""
-    final = np.asarray(predictions[0]) * weights_1[0] * weights_2[0]
-    for i in range(1, len(predictions)):
-        final = final + np.asarray(predictions[i]) * weights_1[i] * weights_2[i]
-    return np.argmax(final, axis=-1).astype("int32")
+    """get_metrics :34-40: argmax over the 7 basic emotions of sum_m P_m * W1[m] * W2[m] (float64), on the GPU
+    (avcer_fused_argmax).  predictions: n_models arrays [n, 7]; weights_1: [n_models][7]; weights_2: [n_models]."""
+    dev = config.device()
+    preds = torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(p, dtype=np.float64) for p in predictions]))).to(dev)
+    m, n, k = preds.shape
+    if k != 7:
+        raise ValueError("fused_argmax handles 7-class probability rows")
+    w1 = torch.from_numpy(np.array(np.broadcast_to(np.asarray(weights_1, dtype=np.float64).reshape(m, -1), (m, 7)))).to(dev)
+    w2 = torch.from_numpy(np.asarray(weights_2, dtype=np.float64).reshape(m)).to(dev)
+    labels = torch.empty(n, device=dev, dtype=torch.int32)
+    _lib.check(_lib.load().avcer_fused_argmax(preds.data_ptr(), m, n, w1.data_ptr(), w2.data_ptr(), labels.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream))
+    return labels.cpu().numpy()
 
 
 def get_c_expr_db_pred(prediction_file_format, root, path_preds, name_videos, weights_1, weights_2, modality,

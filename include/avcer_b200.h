@@ -138,6 +138,12 @@ int avcer_compound_scores(const void* pred, int64_t n, int ncols, int pred_f64,
 int avcer_weight_search_confusion(const double* preds, int n_models, int64_t n, const int32_t* gt,
                                   const double* weights, int64_t n_weights, uint64_t* cm, void* stream);
 
+/* Weighted fusion + arg-max over the 7 basic emotions (get_pred_av.py:34-40, get_metrics): labels[f] =
+ * argmax_c sum_m preds[m][f][c] * w1[m][c] * w2[m], float64, products and sum left to right, numpy arg-max semantics.
+ * preds: [n_models, n, 7] float64; w1: [n_models, 7] and w2: [n_models] DEVICE float64; labels: [n] int32. */
+int avcer_fused_argmax(const double* preds, int n_models, int64_t n, const double* w1, const double* w2,
+                       int32_t* labels, void* stream);
+
 /* Row softmax over 7 classes in fp32, exactly data/utils.py:125-127 (max-subtract, exp, sum, div).
  * `ld` = row pitch of the input in floats (8 for the 8-class audio logits: "Other" is dropped
  * before the softmax, run.py:96). */

@@ -184,3 +184,26 @@ def test_get_pred_av_dropin_matches_reference(cuda_lib, golden, tmp_path, monkey
         assert len(locs) == int(g["n_locations"]) and np.array_equal(np.asarray(labels), g[f"labels_{i}"]), (tag, w2, cwt, cm)
         txt = pd.read_csv(tmp_path / "src" / "pred_results" / "DF_C_EXPR_DB" / f"C_EXPR_DB_{tag}_sd_cfg{i}_{cwt}_{cm}.txt")
         assert list(txt.iloc[:, 0]) == locs and np.array_equal(txt.iloc[:, 1].to_numpy(), g[f"labels_{i}"])
+
+
+def test_fused_argmax_matches_numpy_semantics(cuda_lib):
+    """get_pred_av.get_metrics' fusion (get_pred_av.py:34-40) on the GPU: bit-exact labels against the reference's own
+    numpy expression, including ties (first maximum), zero rows and NaN rows."""
+    from avcer_b200 import get_pred_av, get_weights_matrices as gwm
+
+    rng = np.random.default_rng(9)
+    n = 5003
+    preds = [rng.dirichlet(np.ones(7) * 0.5, size=n) for _ in range(3)]
+    preds[0][10] = preds[1][10] = preds[2][10] = 0.0
+    preds[1][11, 3] = np.nan
+    preds[0][12] = preds[0][12][::-1].copy(); preds[1][12] = preds[0][12]; preds[2][12] = preds[0][12]
+    for p in preds:
+        p[13] = 1.0 / 7.0
+    w1 = np.asarray(gwm.class_weights(gwm.weights_3))
+    for w2 in ([1, 1, 1], gwm.model_weights(gwm.weights_3)):
+        final = preds[0] * w1[0] * w2[0]
+        for i in range(1, 3):
+            final += preds[i] * w1[i] * w2[i]
+        want = np.argmax(final, axis=-1)
+        got = get_pred_av.fused_argmax(preds, w1, w2)
+        assert got.dtype == np.int32 and np.array_equal(got, want)

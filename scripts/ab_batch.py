@@ -8,7 +8,7 @@ from avcer_b200.pipeline import Engine
 dev = "cuda:0"
 c = int(os.environ.get("CLIPS", "4"))
 n_frames, n_samples = 1500, 960000
-cfgs = [(256, 64), (512, 64), (512, 128), (1024, 64)]
+cfgs = [tuple(int(v) for v in t.split(",")) for t in os.environ.get("CFGS", "256,64;512,64;512,128;1024,64").split(";")]
 sds = (syn.make_vs_state_dict(0, "default"), syn.make_vd_state_dict(1), syn.make_audio_state_dict(2, 8, "spread", 12))
 engs = [Engine(*sds, precision="bf16", device=dev, vs_batch=v, a_batch=a) for v, a in cfgs]
 w1, w2 = gwm.class_weights(gwm.weights_3), [1, 1, 1]

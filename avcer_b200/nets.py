@@ -77,6 +77,7 @@ class VSNet:
         self.w = weights.pack_vs(state_dict, self.device, self.dtype)
         self.fused_stem = True          # bf16: stem + max-pool in one kernel (False: two kernels, same bits)
         self.fused_shortcut = True      # bf16: layer1.0's projection shortcut folded into conv3 (K-concatenated GEMM)
+        self.sampled_tail = True        # bf16: the last conv3 of layer1-3 only at the pixels the next stage samples
 
     @property
     def input_layout(self) -> int:
@@ -126,7 +127,10 @@ class VSNet:
             y = ops.maxpool3x3s2(y)
             if taps is not None:
                 taps["pool"] = y
-        for bi, blk in enumerate(self.w["blocks"]):
+        blocks = self.w["blocks"]
+        fuse = taps is None and self.dtype == torch.bfloat16 and self.fused_shortcut
+        sampled = False                 # `cat[:, :cin]` already holds the stride-2 sampled input of the coming block
+        for bi, blk in enumerate(blocks):
             if bi == 0 and cat is not None:
                 # layer1.0: block input and conv2 output share one [n*55*55, 128] matrix, so conv3 and the projection
                 # shortcut are a single K = 128 GEMM (no shortcut tensor, no residual read)
@@ -136,16 +140,21 @@ class VSNet:
                 ops.conv2d_nhwc(t, c2.wt, c2.bias, kh=3, kw=3, pad_h=1, pad_w=1, act=ops.ACT_RELU, out=cat[..., 64:])
                 y = ops.linear(cat.view(m, 128), c3.wt, c3.bias, act=ops.ACT_RELU).view(-1, 55, 55, 256)
                 continue
-            if taps is None and self.dtype == torch.bfloat16 and self.fused_shortcut and "conv3_ds" in blk and blk["conv1"].stride == 2:
+            if fuse and "conv3_ds" in blk and blk["conv1"].stride == 2:
                 # layer2-4 block 0: the stride-2 sampling of the block input is materialised once, as the first Cin
                 # columns of the matrix whose remaining columns conv2 fills; conv1 is a plain row GEMM over it and
                 # conv3 + projection shortcut one K = Cin + planes GEMM
                 c1, c2, c3 = blk["conv1"], blk["conv2"], blk["conv3_ds"]
-                nb, hh, ww, cin = y.shape
-                ho, wo = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
-                m = nb * ho * wo
-                cat = torch.empty((m, cin + c1.cout), device=self.device, dtype=self.dtype)
-                ops.subsample_rows(y, 2, cat[:, :cin])
+                if sampled:                                  # the previous block wrote the sampled pixels itself
+                    nb, ho, wo, cin = cat4.shape[0], cat4.shape[1], cat4.shape[2], c1.cin
+                    m = nb * ho * wo
+                    sampled = False
+                else:
+                    nb, hh, ww, cin = y.shape
+                    ho, wo = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
+                    m = nb * ho * wo
+                    cat = torch.empty((m, cin + c1.cout), device=self.device, dtype=self.dtype)
+                    ops.subsample_rows(y, 2, cat[:, :cin])
                 t = ops.linear(cat[:, :cin], c1.wt, c1.bias, act=ops.ACT_RELU).view(nb, ho, wo, c1.cout)
                 ops.conv2d_nhwc(t, c2.wt, c2.bias, kh=3, kw=3, pad_h=1, pad_w=1, act=ops.ACT_RELU,
                                 out=cat.view(nb, ho, wo, cin + c1.cout)[..., cin:])
@@ -154,6 +163,22 @@ class VSNet:
             identity = self._conv(y, blk["ds"], ops.ACT_NONE) if "ds" in blk else y
             t = self._conv(y, blk["conv1"], ops.ACT_RELU)
             t = self._conv(t, blk["conv2"], ops.ACT_RELU)
+            nxt = blocks[bi + 1] if bi + 1 < len(blocks) else None
+            if fuse and self.sampled_tail and "ds" not in blk and nxt is not None and "conv3_ds" in nxt and nxt["conv1"].stride == 2:
+                # Last block of a stage: the next stage reads its output only at every second pixel (stride-2 conv1 and
+                # projection shortcut, video.py:13-15, 141-148), and conv3 is pointwise -- so conv3 + residual + ReLU are
+                # computed at those pixels only (a quarter of the rows) and land directly in the left columns of the
+                # next block's K-concatenated matrix; the full-resolution stage output is never formed.
+                c3 = blk["conv3"]
+                nb, hh, ww, _ = t.shape
+                ho, wo = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
+                cat = torch.empty((nb * ho * wo, c3.cout + nxt["conv1"].cout), device=self.device, dtype=self.dtype)
+                cat4 = cat.view(nb, ho, wo, c3.cout + nxt["conv1"].cout)
+                ops.conv2d_nhwc(t, c3.wt, c3.bias, kh=1, kw=1, stride=2, residual=identity, residual_stride=2, act=ops.ACT_RELU,
+                                out=cat4[..., :c3.cout])
+                sampled = True
+                y = None
+                continue
             y = self._conv(t, blk["conv3"], ops.ACT_RELU, residual=identity)
             if taps is not None:
                 taps[f"block{bi}"] = y

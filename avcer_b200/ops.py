@@ -143,8 +143,10 @@ def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], 
 
 def conv2d_nhwc(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, kh: int, kw: int, stride: int = 1,
                 pad_h: int = 0, pad_w: int = 0, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x: [N,H,W,C] contiguous; wt: [Cout, kh*kw*C] (tap-major, channel-minor)."""
+                out: Optional[torch.Tensor] = None, residual_stride: int = 1) -> torch.Tensor:
+    """x: [N,H,W,C] contiguous; wt: [Cout, kh*kw*C] (tap-major, channel-minor).
+    residual_stride = s: `residual` is a contiguous [N, Hr, Wr, Cout] tensor read at every s-th pixel (a strided 1x1 conv
+    whose residual lives at the input resolution: only the output pixels the next stage samples are computed)."""
     n, h, w, c = x.shape
     cout = wt.shape[0]
     assert wt.shape[1] == kh * kw * c
@@ -152,7 +154,7 @@ def conv2d_nhwc(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor],
     wo = (w + 2 * pad_w - kw) // stride + 1
     if out is None:
         out = torch.empty((n, ho, wo, cout), device=x.device, dtype=x.dtype)
-    if (kh == 1 and kw == 1 and stride == 1 and pad_h == 0 and pad_w == 0 and x.is_contiguous() and out.is_contiguous()
+    if (kh == 1 and kw == 1 and stride == 1 and residual_stride == 1 and pad_h == 0 and pad_w == 0 and x.is_contiguous() and out.is_contiguous()
             and (residual is None or residual.is_contiguous()) and n * h * w < (1 << 31)):
         # A pointwise conv does not see the image structure: run it as one [n*h*w, C] GEMM so that every M tile is a
         # full 128 rows (a 14x14 image only offers 126 + 70 row boxes, a 7x7 pair 98: 77 % of the MMA rows).
@@ -168,10 +170,15 @@ def conv2d_nhwc(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor],
         a_stride = (1, stride * c, stride * w * c, h * w * c, n * h * w * c)
     op = out.stride(2)                                   # pixel pitch: `out` may be a channel slice of a wider buffer
     assert out.stride(3) == 1 and out.stride(1) == wo * op and out.stride(0) == ho * wo * op
-    assert residual is None or op == cout
+    res_stride = None
+    if residual is not None:
+        assert residual.is_contiguous() and residual.shape[3] == cout and residual.shape[0] == n
+        hr, wr = residual.shape[1], residual.shape[2]
+        assert (hr - 1) // residual_stride + 1 == ho and (wr - 1) // residual_stride + 1 == wo
+        res_stride = (residual_stride * cout, residual_stride * wr * cout, hr * wr * cout)
     return contract(a=x, a_dim=a_dim, a_stride=a_stride, wt=wt, bias=bias, out=out,
                     out_stride=(op, wo * op, ho * wo * op), W=wo, H=ho, NB=n, cin=c, cout=cout, taps_w=kw,
-                    taps_h=kh, off_w=-pad_w, off_h=-pad_h, residual=residual, act=act)
+                    taps_h=kh, off_w=-pad_w, off_h=-pad_h, residual=residual, res_stride=res_stride, act=act)
 
 
 def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, residual: Optional[torch.Tensor] = None,

@@ -51,6 +51,7 @@ class ContractDesc(ctypes.Structure):
         ("res_after_act", c_int32),
         ("dtype", c_int32),
         ("out_f32", c_int32),
+        ("a_step", c_int32),
     ]
 
 

@@ -29,10 +29,12 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box,
-                      CUtensorMapSwizzle swz) {
+                      CUtensorMapSwizzle swz, const uint32_t* elem_strides = nullptr) {
   auto fn = get_encode_fn();
   if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable");
   uint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (elem_strides)
+    for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims,
                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -136,7 +138,7 @@ static int conv3x3_tc(const avcer_contract_desc* d, cudaStream_t st) {
   static const int on = getenv("AVCER_CONV3") ? atoi(getenv("AVCER_CONV3")) : 1;
   const int C = d->cin, W = d->W, H = d->H, NB = d->NB, Cout = d->cout;
   const bool shape = on != 0 && d->taps_w == 3 && d->taps_h == 3 && d->off_w == -1 && d->off_h == -1 && !d->tap_h_in_dim4 &&
-                     d->group_cin_shift == 0 && !d->a_strip && !d->out_f32 && d->residual == nullptr && C % 64 == 0 &&
+                     d->group_cin_shift == 0 && !d->a_strip && d->a_step <= 1 && !d->out_f32 && d->residual == nullptr && C % 64 == 0 &&
                      ((Cout == 64 && C == 64) || Cout == 128) && W + 2 >= 28 && W + 2 <= 63 && NB >= 1 &&
                      (d->act == ACT_NONE || d->act == ACT_RELU);
   const bool dense = d->a_dim[0] == C && d->a_dim[1] == W && d->a_dim[2] == H && d->a_dim[3] == NB && d->a_stride[0] == 1 &&
@@ -237,6 +239,10 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   p.W = d->W; p.H = d->H; p.NB = d->NB;
   p.taps_w = d->taps_w; p.taps_h = d->taps_h; p.off_w = d->off_w; p.off_h = d->off_h;
   p.tap_h_in_dim4 = d->tap_h_in_dim4;
+  const int a_step = d->a_step > 1 ? d->a_step : 1;
+  AVCER_REQUIRE(a_step == 1 || (a_step <= 8 && !d->a_strip && !d->tap_h_in_dim4 && p.bw * a_step <= 256 && p.bh * a_step <= 256),
+                "contract(bf16): a_step=%d needs plain (c, w, h, n) input dims and boxes of at most 256 / a_step pixels", a_step);
+  p.a_step = a_step;
   p.kchunks = d->cin / BK;
   p.a_c0_per_ntile = d->group_cin_shift;   // BN == 64 == one group per N tile
   p.Cout = d->cout;
@@ -260,7 +266,10 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
     }
     uint32_t box[5] = {(uint32_t)BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, 1u};
     if (d->a_strip) { box[0] = (uint32_t)d->a_dim[0]; box[1] = (uint32_t)d->a_dim[1]; box[2] = 1; box[3] = 1; }
-    if (encode_map(&ta, d->a, 5, dims, strides, box, d->a_strip ? CU_TENSOR_MAP_SWIZZLE_NONE : swz)) return 1;
+    // strided spatial conv: the box spans bw*s x bh*s input pixels and TMA keeps every s-th one (traversal stride)
+    uint32_t estr[5] = {1u, (uint32_t)a_step, (uint32_t)a_step, 1u, 1u};
+    if (a_step > 1) { box[1] *= (uint32_t)a_step; box[2] *= (uint32_t)a_step; }
+    if (encode_map(&ta, d->a, 5, dims, strides, box, d->a_strip ? CU_TENSOR_MAP_SWIZZLE_NONE : swz, a_step > 1 ? estr : nullptr)) return 1;
   }
   {
     const uint64_t ktot = (uint64_t)d->taps_w * d->taps_h * d->cin;
@@ -534,6 +543,7 @@ __global__ void __launch_bounds__(256) simt_contract_kernel(const SimtParams p) 
 }
 
 static int contract_simt(const avcer_contract_desc* d, cudaStream_t st) {
+  AVCER_REQUIRE(d->a_step <= 1, "contract(fp32): a_step is a bf16-path feature");
   SimtParams p{};
   p.a = static_cast<const float*>(d->a);
   for (int i = 0; i < 5; ++i) { p.a_dim[i] = d->a_dim[i]; p.a_stride[i] = d->a_stride[i]; }

@@ -38,6 +38,7 @@ struct TcGemmParams {
   int W, H, NB;            // valid output extents (direct-store epilogue mask)
   int taps_w, taps_h;      // filter taps
   int off_w, off_h;        // coordinate offset of tap (0,0)  (= -padding)
+  int a_step;              // spatial step of the A box (>= 1): output pixel w reads input pixel a_step*w + off_w + tap
   int tap_h_in_dim4;       // 1: the h-tap index is coordinate 4 of the A map (stem: strided rows)
   int kchunks;             // K chunks (of BK) per tap
   int a_c0_per_ntile;      // channel-coordinate shift per N tile (grouped conv), else 0
@@ -173,7 +174,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int tap = kk / p.kchunks;
             const int tx = tap % p.taps_w, ty = tap / p.taps_w;
             tma_load_5d(a_base + (stage * KSUB + j) * Cfg::A_STAGE, &tmA, full_bar(stage), p.a_strip ? 0 : kc * BK + c_shift,
-                        p.a_strip ? 0 : w0 + p.off_w + tx, h0 + p.off_h + (p.tap_h_in_dim4 ? 0 : ty), n0,
+                        p.a_strip ? 0 : w0 * p.a_step + p.off_w + tx, h0 * p.a_step + p.off_h + (p.tap_h_in_dim4 ? 0 : ty), n0,
                         p.tap_h_in_dim4 ? ty : 0);
             if (p.b_packed != nullptr)
               bulk_load_1d(b_base + (stage * KSUB + j) * Cfg::B_STAGE,

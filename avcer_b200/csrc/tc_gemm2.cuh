@@ -191,8 +191,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int kc = 0; kc < p.kchunks; ++kc, kcol += BK) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
               if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), tx_pair);
-              tma_load_5d_2sm(a_base + stage * Cfg::A_STAGE, &tmA, full_bar(stage), kc * BK, w0 + p.off_w + tx,
-                              h0 + p.off_h + (p.tap_h_in_dim4 ? 0 : ty), n0, p.tap_h_in_dim4 ? ty : 0);
+              tma_load_5d_2sm(a_base + stage * Cfg::A_STAGE, &tmA, full_bar(stage), kc * BK, w0 * p.a_step + p.off_w + tx,
+                              h0 * p.a_step + p.off_h + (p.tap_h_in_dim4 ? 0 : ty), n0, p.tap_h_in_dim4 ? ty : 0);
               tma_load_2d_2sm(b_base + stage * Cfg::B_STAGE, &tmB, full_bar(stage), kcol, nt * BN + (int)rank * (BN / 2));
               if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
             }

@@ -107,7 +107,7 @@ def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], 
              tap_h_in_dim4: bool = False, group_cin_shift: int = 0, residual: Optional[torch.Tensor] = None,
              res_stride: Optional[Sequence[int]] = None, act: int = ACT_NONE, res_after_act: bool = False,
              a_offset: int = 0, algo_k: Optional[int] = None, a_strip: bool = False,
-             wt_packed: Optional[torch.Tensor] = None) -> torch.Tensor:
+             wt_packed: Optional[torch.Tensor] = None, a_step: int = 1) -> torch.Tensor:
     """Generic implicit GEMM (see avcer_contract in include/avcer_b200.h)."""
     _cuda(a, "a")
     d = ContractDesc()
@@ -130,6 +130,7 @@ def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], 
     d.tap_h_in_dim4 = int(tap_h_in_dim4)
     d.group_cin_shift = group_cin_shift
     d.a_strip = int(a_strip)
+    d.a_step = int(a_step)
     d.wt_packed = _ptr(wt_packed)
     d.act = act
     d.res_after_act = int(res_after_act)
@@ -161,13 +162,18 @@ def conv2d_nhwc(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor],
         linear(x.view(n * h * w, c), wt, bias, residual=None if residual is None else residual.view(n * h * w, cout),
                act=act, out=out.view(n * h * w, cout))
         return out
+    a_step = 1
     if stride == 1:
         a_dim = (c, w, h, n, 1)
         a_stride = (1, c, w * c, h * w * c, n * h * w * c)
-    else:
-        assert kh == 1 and kw == 1 and pad_h == 0 and pad_w == 0, "strided conv only for 1x1"
-        a_dim = (c, wo, ho, n, 1)
+    elif kh == 1 and kw == 1 and pad_h == 0 and pad_w == 0:
+        a_dim = (c, wo, ho, n, 1)                        # a strided 1x1 conv is a view of every stride-th pixel
         a_stride = (1, stride * c, stride * w * c, h * w * c, n * h * w * c)
+    else:
+        assert x.dtype == torch.bfloat16, "strided k x k convs: bf16 path only (TMA traversal stride)"
+        a_dim = (c, w, h, n, 1)                          # full-resolution input walked with traversal stride `stride`
+        a_stride = (1, c, w * c, h * w * c, n * h * w * c)
+        a_step = stride
     op = out.stride(2)                                   # pixel pitch: `out` may be a channel slice of a wider buffer
     assert out.stride(3) == 1 and out.stride(1) == wo * op and out.stride(0) == ho * wo * op
     res_stride = None
@@ -178,7 +184,7 @@ def conv2d_nhwc(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor],
         res_stride = (residual_stride * cout, residual_stride * wr * cout, hr * wr * cout)
     return contract(a=x, a_dim=a_dim, a_stride=a_stride, wt=wt, bias=bias, out=out,
                     out_stride=(op, wo * op, ho * wo * op), W=wo, H=ho, NB=n, cin=c, cout=cout, taps_w=kw,
-                    taps_h=kh, off_w=-pad_w, off_h=-pad_h, residual=residual, res_stride=res_stride, act=act)
+                    taps_h=kh, off_w=-pad_w, off_h=-pad_h, residual=residual, res_stride=res_stride, act=act, a_step=a_step)
 
 
 def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, residual: Optional[torch.Tensor] = None,

@@ -102,6 +102,10 @@ typedef struct {
   int32_t res_after_act;     /* 0: act(acc+bias+res); 1: act(acc+bias)+res */
   int32_t dtype;             /* AVCER_BF16 / AVCER_F32 (operands) */
   int32_t out_f32;           /* bf16 path only: write fp32 output */
+  int32_t a_step;            /* bf16 path only. s > 1: a strided spatial convolution -- a_dim / a_stride describe the
+                              * FULL-resolution input (c, w_in, h_in, n, 1) and output pixel (w, h) reads input pixel
+                              * (s*w + off_w + tap_w, s*h + off_h + tap_h): the TMA box walks the input with traversal
+                              * stride s (a 3x3 "same" conv evaluated only at every s-th pixel).  0 / 1: unit step. */
 } avcer_contract_desc;
 
 int avcer_contract(const avcer_contract_desc* d, void* stream);

@@ -10,7 +10,7 @@ N = int(os.environ.get("N", "256"))
 quiet = "quiet" in sys.argv
 net = nets.VSNet(syn.make_vs_state_dict(0, "default"), "bf16", dev)
 net.fused_shortcut = os.environ.get("FS", "1") != "0"
-net.sampled_tail = os.environ.get("ST", "1") != "0"
+net.sampled_tail = int(os.environ.get("ST", "2"))
 g = torch.Generator(device=dev).manual_seed(5)
 crops = torch.randint(0, 256, (N, 224, 224, 3), dtype=torch.uint8, device=dev, generator=g)
 x = net.alloc_input(N)

@@ -115,6 +115,39 @@ def test_conv3x3_halo_kernel_matches_torch(cuda_lib, n, h, w, c, cout):
     assert (y.float() - ref).abs().max().item() < 0.04
 
 
+@pytest.mark.parametrize("n,h,w,c,cout", [
+    (3, 55, 55, 64, 64),        # layer1's last conv2 at every second pixel (odd extent: 28 outputs per row)
+    (2, 28, 28, 128, 128),      # layer2
+    (40, 14, 14, 256, 256),     # layer3, more tiles than one wave
+    (1, 9, 7, 64, 128),         # tiny ragged image
+])
+def test_strided_conv3x3_equals_subsampled_full_conv(cuda_lib, n, h, w, c, cout):
+    """A 3x3 'same' conv evaluated only at every second pixel (avcer_contract a_step = 2: TMA traversal stride over the
+    full-resolution input, zero fill at the borders) must be bit-identical to the stride-1 conv sampled at those pixels
+    (same K order, same epilogue) and match torch's stride-2 conv."""
+    from avcer_b200 import ops
+
+    torch.manual_seed(n + w)
+    x = torch.randn(n, h, w, c, device=DEV).to(BF)
+    w4 = (torch.randn(cout, c, 3, 3, device=DEV) / (9 * c) ** 0.5).to(BF)
+    b = torch.randn(cout, device=DEV)
+    wt = w4.permute(0, 2, 3, 1).reshape(cout, 9 * c).contiguous()
+    y2 = ops.conv2d_nhwc(x, wt, b, kh=3, kw=3, stride=2, pad_h=1, pad_w=1, act=ops.ACT_RELU)
+    assert tuple(y2.shape) == (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, cout)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w4.float(), b, padding=1, stride=2)).permute(0, 2, 3, 1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert (y2.float() - ref).abs().max().item() < 0.04
+    import os
+    os.environ["AVCER_CONV3"] = "0"          # read once per process by the launcher: may already be cached as "on"
+    full = ops.conv2d_nhwc(x, wt, b, kh=3, kw=3, pad_h=1, pad_w=1, act=ops.ACT_RELU)
+    del os.environ["AVCER_CONV3"]
+    assert (y2.float() - full[:, ::2, ::2].float()).abs().max().item() < 0.02
+
+
 @pytest.mark.parametrize("n", [1, 5, 41])
 def test_fused_stem_pool_is_bit_identical_to_two_kernels(cuda_lib, n):
     """avcer_stem_pool (stem activation kept on chip) must reproduce stem conv -> max-pool bit for bit, including

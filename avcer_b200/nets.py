@@ -10,6 +10,7 @@ precision "fp32": fp32 storage, SIMT contractions (the tolerance-check mode of t
 """
 from __future__ import annotations
 
+import gc
 import math
 from typing import Dict, Optional, Tuple
 
@@ -45,8 +46,18 @@ class GraphedForward:
             torch.cuda.synchronize()
             n0 = ops.STATS["launches"]
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph), ops.sm_limit(self.sm_limit):
-                outs = self.fn(*static_inputs)
+            # No garbage collection while the stream is capturing: an unreachable Engine (its CUDA graphs sit in reference
+            # cycles) finalised in the middle of a capture destroys its graphs -- an operation that is not permitted
+            # during stream capture and invalidates the one in progress.  Collect first, then hold the collector off.
+            gc.collect()
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(graph), ops.sm_limit(self.sm_limit):
+                    outs = self.fn(*static_inputs)
+            finally:
+                if gc_was_on:
+                    gc.enable()
             entry = (graph, outs, ops.STATS["launches"] - n0)
             ops.STATS["launches"] = n0
             self.cache[key] = entry

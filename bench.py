@@ -15,6 +15,7 @@ successive steps cannot be served from cache.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -319,9 +320,14 @@ def main():
             fn()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for _ in range(reps):
-                    fn()
+            gc.collect()                   # no finaliser (e.g. of an old CUDA graph) may run while the stream is capturing
+            gc.disable()
+            try:
+                with torch.cuda.graph(g):
+                    for _ in range(reps):
+                        fn()
+            finally:
+                gc.enable()
             ts = []
             for i in range(5):
                 flush.zero_()

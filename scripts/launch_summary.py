@@ -30,9 +30,11 @@ def vs_specs(B=256):
     for li, (P, nb) in enumerate(zip((64, 128, 256, 512), (3, 4, 6, 3)), start=1):
         for bi in range(nb):
             M = B * hw[li] ** 2
-            # block 0: the projection shortcut is folded into conv3 (K = Cin + P, nets.VSNet.fused_shortcut)
-            specs += [(f"l{li}.{bi}.c1", M, P, cin), (f"l{li}.{bi}.c2", M, P, 9 * P),
-                      (f"l{li}.{bi}.c3" + ("+ds" if bi == 0 else ""), M, 4 * P, P + (cin if bi == 0 else 0))]
+            # block 0: the projection shortcut is folded into conv3 (K = Cin + P, nets.VSNet.fused_shortcut); last block of
+            # layer1-3: conv2 / conv3 only at the pixels the next stage samples (nets.VSNet.sampled_tail)
+            Mt = B * hw[li + 1] ** 2 if (li < 4 and bi == nb - 1) else M
+            specs += [(f"l{li}.{bi}.c1", M, P, cin), (f"l{li}.{bi}.c2" + ("/s2" if Mt != M else ""), Mt, P, 9 * P),
+                      (f"l{li}.{bi}.c3" + ("+ds" if bi == 0 else "") + ("/s2" if Mt != M else ""), Mt, 4 * P, P + (cin if bi == 0 else 0))]
             cin = 4 * P
     return specs + [("fc1", B, 512, 2048)]
 

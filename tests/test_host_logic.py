@@ -116,3 +116,25 @@ def test_balanced_batches_cover_and_differ_by_one():
         assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
         sizes = [e - s for s, e in r]
         assert len(r) == -(-n // mb) and max(sizes) <= mb and max(sizes) - min(sizes) <= 1
+
+
+def test_contract_descriptor_layout_matches_the_header(tmp_path):
+    """The ctypes mirror of avcer_contract_desc must have the size and field offsets the C compiler gives the header's
+    struct (a field appended on one side only would silently shift every argument)."""
+    import ctypes
+    import subprocess
+
+    from avcer_b200._lib import ContractDesc
+
+    fields = [f[0] for f in ContractDesc._fields_]
+    src = tmp_path / "layout.c"
+    body = "\n".join(f'  printf("{name} %zu\\n", offsetof(avcer_contract_desc, {name}));' for name in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "avcer_b200.h"\nint main(void) {\n'
+                   '  printf("sizeof %zu\\n", sizeof(avcer_contract_desc));\n' + body + "\n  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    assert int(out["sizeof"]) == ctypes.sizeof(ContractDesc)
+    for name in fields:
+        assert int(out[name]) == getattr(ContractDesc, name).offset, name

@@ -278,7 +278,7 @@ extern "C" int avcer_pcm16_resample(const int16_t* pcm, int64_t n, int channels,
   AVCER_REQUIRE(smem <= 200 * 1024, "pcm16_resample: ratio %d/%d needs %zu B of shared memory", orig, nnew, smem);
   static bool attr_set = false;
   if (smem > 48 * 1024 && !attr_set) {
-    cudaFuncSetAttribute(pcm16_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    AVCER_CUDA(cudaFuncSetAttribute(pcm16_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   const int64_t used_frames = (n_out + nnew - 1) / nnew;

@@ -87,7 +87,7 @@ class VSNet:
         self.device = torch.device(device)
         self.w = weights.pack_vs(state_dict, self.device, self.dtype)
         self.fused_stem = True          # bf16: stem + max-pool in one kernel (False: two kernels, same bits)
-        self.fused_shortcut = True      # bf16: layer1.0's projection shortcut folded into conv3 (K-concatenated GEMM)
+        self.fused_shortcut = True      # bf16: projection shortcuts folded into conv3 (K-concatenated GEMM, first block of a stage)
         self.sampled_tail = 2           # bf16: the last conv3 (1) and conv2 (2) of layer1-3 only at the pixels the next stage samples
 
     @property
@@ -174,36 +174,30 @@ class VSNet:
             identity = self._conv(y, blk["ds"], ops.ACT_NONE) if "ds" in blk else y
             t = self._conv(y, blk["conv1"], ops.ACT_RELU)
             nxt = blocks[bi + 1] if bi + 1 < len(blocks) else None
-            tail = fuse and self.sampled_tail and "ds" not in blk and nxt is not None and "conv3_ds" in nxt and nxt["conv1"].stride == 2
-            if tail and self.sampled_tail >= 2:
-                # ... and conv2's output is consumed by that conv3 only, so the 3x3 conv too is evaluated at every second
-                # pixel (a stride-2 "same" conv over the full-resolution conv1 output: TMA traversal stride 2)
+            if fuse and self.sampled_tail and "ds" not in blk and nxt is not None and "conv3_ds" in nxt and nxt["conv1"].stride == 2:
+                # Last block of a stage: the next stage reads its output only at every second pixel (stride-2 conv1 and
+                # projection shortcut, video.py:13-15, 141-148).  conv3 is pointwise, so conv3 + residual + ReLU are
+                # computed at those pixels only (a quarter of the rows) and land directly in the left columns of the next
+                # block's K-concatenated matrix; the full-resolution stage output is never formed.  conv2's output is
+                # consumed by that conv3 only, so (sampled_tail >= 2) the 3x3 conv too is evaluated at every second pixel:
+                # a stride-2 "same" conv over the full-resolution conv1 output (TMA traversal stride 2).
                 c2, c3 = blk["conv2"], blk["conv3"]
-                t = ops.conv2d_nhwc(t, c2.wt, c2.bias, kh=3, kw=3, stride=2, pad_h=1, pad_w=1, act=ops.ACT_RELU)
-                nb, ho, wo, _ = t.shape
+                c3_stride = 2
+                if self.sampled_tail >= 2:
+                    t = ops.conv2d_nhwc(t, c2.wt, c2.bias, kh=3, kw=3, stride=2, pad_h=1, pad_w=1, act=ops.ACT_RELU)
+                    c3_stride = 1
+                else:
+                    t = self._conv(t, c2, ops.ACT_RELU)
+                nb, hh, ww, _ = t.shape
+                ho, wo = (hh - 1) // c3_stride + 1, (ww - 1) // c3_stride + 1
                 cat = torch.empty((nb * ho * wo, c3.cout + nxt["conv1"].cout), device=self.device, dtype=self.dtype)
                 cat4 = cat.view(nb, ho, wo, c3.cout + nxt["conv1"].cout)
-                ops.conv2d_nhwc(t, c3.wt, c3.bias, kh=1, kw=1, residual=identity, residual_stride=2, act=ops.ACT_RELU,
-                                out=cat4[..., :c3.cout])
+                ops.conv2d_nhwc(t, c3.wt, c3.bias, kh=1, kw=1, stride=c3_stride, residual=identity, residual_stride=2,
+                                act=ops.ACT_RELU, out=cat4[..., :c3.cout])
                 sampled = True
                 y = None
                 continue
             t = self._conv(t, blk["conv2"], ops.ACT_RELU)
-            if tail:
-                # Last block of a stage: the next stage reads its output only at every second pixel (stride-2 conv1 and
-                # projection shortcut, video.py:13-15, 141-148), and conv3 is pointwise -- so conv3 + residual + ReLU are
-                # computed at those pixels only (a quarter of the rows) and land directly in the left columns of the
-                # next block's K-concatenated matrix; the full-resolution stage output is never formed.
-                c3 = blk["conv3"]
-                nb, hh, ww, _ = t.shape
-                ho, wo = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
-                cat = torch.empty((nb * ho * wo, c3.cout + nxt["conv1"].cout), device=self.device, dtype=self.dtype)
-                cat4 = cat.view(nb, ho, wo, c3.cout + nxt["conv1"].cout)
-                ops.conv2d_nhwc(t, c3.wt, c3.bias, kh=1, kw=1, stride=2, residual=identity, residual_stride=2, act=ops.ACT_RELU,
-                                out=cat4[..., :c3.cout])
-                sampled = True
-                y = None
-                continue
             y = self._conv(t, blk["conv3"], ops.ACT_RELU, residual=identity)
             if taps is not None:
                 taps[f"block{bi}"] = y

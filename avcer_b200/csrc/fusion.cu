@@ -56,7 +56,9 @@ __device__ __forceinline__ long long compound_argmax(const TC (&s)[7], const Fus
     }
     const TC pr = A::add(a, b);
     if (k == 0) { best = pr; bi = 0; }
-    else if (pr > best || (pr != pr && best == best)) { best = pr; bi = k; }
+    // "pr > best, or pr is NaN and best is not" in two compares instead of three: !(pr <= best) is the unordered
+    // greater-than (true when either side is NaN), and a NaN best never gives way
+    else if (!(pr <= best) && best == best) { best = pr; bi = k; }
   }
   return bi;
 }

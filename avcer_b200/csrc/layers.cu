@@ -149,7 +149,7 @@ __global__ void small_linear_kernel(const T* __restrict__ x, long long n, int k,
 template <typename T>
 __global__ void lstm_cell_kernel(const float* __restrict__ xproj, const int* __restrict__ xidx,
                                  const float* __restrict__ hproj, float* __restrict__ c, T* __restrict__ h_out,
-                                 long long ldh, long long n, int hidden, int first) {
+                                 long long ldh, long long n, int hidden, int first, int split, float* __restrict__ h_f32) {
   pdl_wait();
   pdl_launch_dependents();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,7 +170,32 @@ __global__ void lstm_cell_kernel(const float* __restrict__ xproj, const int* __r
   const float cprev = first ? 0.f : c[i];
   const float cn = fg * cprev + ig * gg;
   c[i] = cn;
-  h_out[r * ldh + j] = from_f32<T>(og * tanhf(cn));
+  const float hv = og * tanhf(cn);
+  if (h_f32) h_f32[i] = hv;
+  const T hi = from_f32<T>(hv);
+  h_out[r * ldh + j] = hi;
+  if (split) {
+    // bf16x3 operand of the next recurrent GEMM: [hi | lo | hi] against weights packed [w_hi | w_hi | w_lo], i.e.
+    // hi*w_hi + lo*w_hi + hi*w_lo -- 16 mantissa bits on both operands, fp32 accumulation in TMEM
+    h_out[r * ldh + hidden + j] = from_f32<T>(hv - to_f32(hi));
+    h_out[r * ldh + 2 * hidden + j] = hi;
+  }
+}
+
+// x fp32 [rows, k] -> bf16 [rows, 3k] = [hi | lo | hi] (bf16x3 split operand, see lstm_cell_kernel)
+__global__ void split_bf16x3_kernel(const float* __restrict__ x, long long rows, int k, long long ldx,
+                                    __nv_bfloat16* __restrict__ out, long long ldo) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * k) return;
+  const long long r = i / k;
+  const int j = (int)(i % k);
+  const float v = x[r * ldx + j];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  out[r * ldo + j] = hi;
+  out[r * ldo + k + j] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  out[r * ldo + 2 * k + j] = hi;
 }
 
 // ------------------------------------------------------------------ K5a audio window gather + pad + zero-mean/unit-var
@@ -540,13 +565,23 @@ extern "C" int avcer_small_linear(const void* x, int64_t n, int k, int64_t ldx, 
 }
 
 extern "C" int avcer_lstm_cell(const float* xproj, const int32_t* xidx, const float* hproj, float* c, void* h_out,
-                               int64_t ldh, int64_t n, int hidden, int first, int dtype, void* stream) {
-  AVCER_REQUIRE(hidden > 0 && ldh >= hidden, "lstm_cell: bad shape");
+                               int64_t ldh, int64_t n, int hidden, int first, int split, float* h_f32, int dtype, void* stream) {
+  AVCER_REQUIRE(hidden > 0 && ldh >= (split ? 3 : 1) * (int64_t)hidden, "lstm_cell: bad shape");
+  AVCER_REQUIRE(!split || dtype == AVCER_BF16, "lstm_cell: the [hi | lo | hi] split output is a bf16 feature");
   const long long total = n * hidden;
   if (total == 0) return 0;
   AVCER_DISPATCH(dtype, (launch_pdl(lstm_cell_kernel<T>, blocks_for(total, 256), 256, 0, as_stream(stream), 
-                            xproj, xidx, hproj, c, (T*)h_out, ldh, n, hidden, first)));
+                            xproj, xidx, hproj, c, (T*)h_out, ldh, n, hidden, first, split, h_f32)));
   return check_launch("lstm_cell");
+}
+
+extern "C" int avcer_split_bf16x3(const float* x, int64_t rows, int k, int64_t ldx, void* out, int64_t ldo, void* stream) {
+  AVCER_REQUIRE(k > 0 && ldx >= k && ldo >= 3 * (int64_t)k, "split_bf16x3: bad shape");
+  const long long total = rows * k;
+  if (total == 0) return 0;
+  launch_pdl(split_bf16x3_kernel, blocks_for(total, 256), 256, 0, as_stream(stream), x, (long long)rows, k, (long long)ldx,
+             (__nv_bfloat16*)out, (long long)ldo);
+  return check_launch("split_bf16x3");
 }
 
 extern "C" int avcer_audio_normalize_windows(const float* wav, const int64_t* starts, const int64_t* ends, int n_win,

@@ -54,7 +54,7 @@ def preprocess_video_and_predict(path_images="", save_path="", fps=30, total_fra
         probs, feats = eng.vs_forward_ragged(torch.from_numpy(flat).to(eng.device), offsets, hs, ws)
     else:
         probs = torch.zeros((1, 7), device=eng.device)
-        feats = torch.zeros((1, 512), device=eng.device, dtype=eng.vs.dtype)
+        feats = torch.zeros((1, 512), device=eng.device, dtype=torch.float32)
     stat, dyn, plans = eng.video_rows(probs, feats, [exists], [fps])
     plan = plans[0]
     # np.array() over a list mixing float32 rows and float64 zero rows promotes to float64 (:89,182-187)

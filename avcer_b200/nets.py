@@ -78,7 +78,7 @@ def _dtype(precision: str) -> torch.dtype:
 
 class VSNet:
     """Static visual ResNet-50.  forward(x) with x = zero-bordered NHWC4 crops [n,232,240,4]
-    (layout 1/2 of avcer_preprocess_u8) -> (probabilities [n,7] fp32, relu(fc1) features [n,512])."""
+    (layout 1/2 of avcer_preprocess_u8) -> (probabilities [n,7] fp32, relu(fc1) features [n,512] fp32)."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], precision: str = "bf16", device: str = "cuda:0"):
         require_device()
@@ -206,7 +206,8 @@ class VSNet:
     def _tail(self, y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         pooled = ops.avgpool(y)
         fc1 = self.w["fc1"]
-        feat = ops.linear(pooled, fc1.wt, fc1.bias, act=ops.ACT_RELU)      # relu(fc1): VD input and fc2 input
+        # relu(fc1) in fp32 (direct-store epilogue): fc2 input and, split into bf16x3, the LSTM input (VDNet.forward)
+        feat = ops.linear(pooled, fc1.wt, fc1.bias, act=ops.ACT_RELU, out_dtype=torch.float32)
         probs = ops.small_linear(feat, self.w["fc2_w"], self.w["fc2_b"], softmax=True)
         return probs, feat
 
@@ -222,26 +223,33 @@ class VDNet:
         self.w = weights.pack_vd(state_dict, self.device, self.dtype)
 
     def forward(self, feats: torch.Tensor, windows_t: torch.Tensor) -> torch.Tensor:
-        """feats: [U,512] relu(fc1) features (dtype); windows_t: int32 [10, M] positions into feats
-        (time-major).  Returns VD logits [M,7] fp32."""
+        """feats: [U,512] fp32 relu(fc1) features; windows_t: int32 [10, M] positions into feats
+        (time-major).  Returns VD logits [M,7] fp32.
+        bf16 mode runs every contraction as bf16x3 (activations [hi | lo | hi] x weights [hi | hi | lo], fp32
+        accumulation): the 20 chained recurrent GEMMs keep 16 mantissa bits at 3x the (negligible) tensor work."""
         steps, m = windows_t.shape
         if m == 0:
             return torch.empty((0, 7), device=self.device, dtype=torch.float32)
+        assert feats.dtype == torch.float32
         w = self.w
-        xproj = ops.linear(feats, w["w_ih1"], w["b1"], out_dtype=torch.float32)            # [U, 2048]
-        hcat = torch.zeros((m, 768), device=self.device, dtype=self.dtype)                   # [h1_t | h2_{t-1}]
+        split = w["split"]
+        s = 3 if split else 1
+        x = ops.split_bf16x3(feats) if split else feats
+        xproj = ops.linear(x, w["w_ih1"], w["b1"], out_dtype=torch.float32)                 # [U, 2048]
+        hcat = torch.zeros((m, s * 768), device=self.device, dtype=self.dtype)               # [h1_t | h2_{t-1}] (each x3 when split)
         c1 = torch.empty((m, 512), device=self.device, dtype=torch.float32)
         c2 = torch.empty((m, 256), device=self.device, dtype=torch.float32)
-        h1, h2 = hcat[:, :512], hcat[:, 512:]
+        h1, h2 = hcat[:, :s * 512], hcat[:, s * 512:]
+        h2_f32 = torch.empty((m, 256), device=self.device, dtype=torch.float32)
         hproj = torch.empty((m, 2048), device=self.device, dtype=torch.float32)
         g2 = torch.empty((m, 1024), device=self.device, dtype=torch.float32)
         for t in range(steps):
             if t > 0:
                 ops.linear(h1, w["w_hh1"], None, out=hproj)
-            ops.lstm_cell(xproj, windows_t[t], hproj if t > 0 else None, c1, h1, 512, first=(t == 0))
+            ops.lstm_cell(xproj, windows_t[t], hproj if t > 0 else None, c1, h1, 512, first=(t == 0), split=split)
             ops.linear(hcat, w["w_cat2"], w["b2"], out=g2)
-            ops.lstm_cell(None, None, g2, c2, h2, 256, first=(t == 0))
-        return ops.small_linear(h2, w["fc_w"], w["fc_b"], softmax=False)
+            ops.lstm_cell(None, None, g2, c2, h2, 256, first=(t == 0), split=split, h_f32=h2_f32 if t == steps - 1 else None)
+        return ops.small_linear(h2_f32, w["fc_w"], w["fc_b"], softmax=False)
 
 
 W2V_LENGTHS = (12799, 6399, 3199, 1599, 799, 399, 199)     # conv output lengths for 64000 samples

@@ -19,7 +19,7 @@ from ._lib import check as _check
 __all__ = [
     "F32", "BF16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "dtype_code", "torch_dtype", "contract", "conv2d_nhwc",
     "linear", "preprocess", "fuse_compound", "weight_search_confusion", "softmax7", "window_to_frame_mean", "gather_rows", "maxpool3x3s2",
-    "stem_pool", "subsample_rows", "avgpool", "small_linear", "lstm_cell", "sinc_resample_bank", "pcm16_to_mono", "audio_normalize_windows", "w2v_conv0_ln_gelu", "layernorm", "add_rows",
+    "stem_pool", "subsample_rows", "avgpool", "small_linear", "lstm_cell", "split_bf16x3", "sinc_resample_bank", "pcm16_to_mono", "audio_normalize_windows", "w2v_conv0_ln_gelu", "layernorm", "add_rows",
     "attention", "maxpool1d5_relu", "avgpool1d_relu", "cast", "sm_limit",
 ]
 
@@ -352,10 +352,24 @@ def small_linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], so
 
 
 def lstm_cell(xproj: Optional[torch.Tensor], xidx: Optional[torch.Tensor], hproj: Optional[torch.Tensor],
-              c: torch.Tensor, h_out: torch.Tensor, hidden: int, first: bool) -> None:
+              c: torch.Tensor, h_out: torch.Tensor, hidden: int, first: bool, split: bool = False,
+              h_f32: Optional[torch.Tensor] = None) -> None:
+    """split: h_out is the [n, 3*hidden] bf16x3 operand [hi | lo | hi]; h_f32: optional fp32 copy of h [n, hidden]."""
     n = c.shape[0]
     check(_lib.load().avcer_lstm_cell(_ptr(xproj), _ptr(xidx), _ptr(hproj), c.data_ptr(), h_out.data_ptr(),
-                                      h_out.stride(0), n, hidden, int(first), dtype_code(h_out.dtype), _stream()))
+                                      h_out.stride(0), n, hidden, int(first), int(split), _ptr(h_f32), dtype_code(h_out.dtype),
+                                      _stream()))
+
+
+def split_bf16x3(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x fp32 [rows, k] -> bf16 [rows, 3k] = [hi | lo | hi] (operand of a bf16x3 contraction)."""
+    _cuda(x, "x")
+    rows, k = x.shape
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    if out is None:
+        out = torch.empty((rows, 3 * k), device=x.device, dtype=torch.bfloat16)
+    check(_lib.load().avcer_split_bf16x3(x.data_ptr(), rows, k, x.stride(0), out.data_ptr(), out.stride(0), _stream()))
+    return out
 
 
 PAD_MODES = {"mean": 0, "constant": 1, "repeat": 2}

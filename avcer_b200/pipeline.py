@@ -159,7 +159,7 @@ class Engine:
         """crops_u8: device uint8 [n,224,224,3] BGR.  Returns (probs [n,7] fp32, features [n,512])."""
         n = crops_u8.shape[0]
         probs = torch.empty((n, 7), device=self.device, dtype=torch.float32)
-        feats = torch.empty((n, 512), device=self.device, dtype=self.vs.dtype)
+        feats = torch.empty((n, 512), device=self.device, dtype=torch.float32)
         for s, e in balanced_batches(n, self.vs_batch):
             x = self._vs_input(e - s)
             ops.preprocess(crops_u8[s:e], e - s, x, self.vs.input_layout)
@@ -174,7 +174,7 @@ class Engine:
         n = crops_host.shape[0]
         bs = self.vs_batch
         probs = torch.empty((n, 7), device=self.device, dtype=torch.float32)
-        feats = torch.empty((n, 512), device=self.device, dtype=self.vs.dtype)
+        feats = torch.empty((n, 512), device=self.device, dtype=torch.float32)
         if not hasattr(self, "_stage"):
             self._stage = [torch.empty((bs, 224, 224, 3), device=self.device, dtype=torch.uint8) for _ in range(2)]
             self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -214,7 +214,7 @@ class Engine:
         """Crops of arbitrary size packed back to back in `flat_u8` (K1 does the NEAREST resize)."""
         n = len(offsets)
         probs = torch.empty((n, 7), device=self.device, dtype=torch.float32)
-        feats = torch.empty((n, 512), device=self.device, dtype=self.vs.dtype)
+        feats = torch.empty((n, 512), device=self.device, dtype=torch.float32)
         off = torch.from_numpy(np.asarray(offsets, dtype=np.int64)).to(self.device)
         hh = torch.from_numpy(np.asarray(heights, dtype=np.int32)).to(self.device)
         ww = torch.from_numpy(np.asarray(widths, dtype=np.int32)).to(self.device)
@@ -313,14 +313,21 @@ class Engine:
 
     # ------------------------------------------------------------------ K4 on aligned per-frame rows
     def fuse(self, stat_video_order: torch.Tensor, dyn_video_order: torch.Tensor, audio_mean_logits: torch.Tensor,
-             weights_1, weights_2, ce_weights_type: bool, ce_mask: bool) -> torch.Tensor:
+             weights_1, weights_2, ce_weights_type: bool, ce_mask: bool, f64_video: bool = False,
+             labels: Optional[torch.Tensor] = None) -> torch.Tensor:
         """run.py:85-165 on device: permute the video columns into audio order, softmax the VD logits and
-        the audio mean logits (first 7 classes), then K4.  Returns int64 labels [4, n]."""
+        the audio mean logits (first 7 classes), then K4.  Returns int64 labels [4, n].
+        f64_video: the reference's video tables are float64 for this clip (a zero row was appended, np.array promotion at
+        get_prob_video.py:89,182-187), so the VD softmax and the fusion run in float64; the audio table stays float32."""
         n = stat_video_order.shape[0]
         p_vs = ops.gather_rows(stat_video_order, None, n, perm=self._perm)
-        p_vd = ops.softmax7(ops.gather_rows(dyn_video_order, None, n, perm=self._perm))
+        dyn = ops.gather_rows(dyn_video_order, None, n, perm=self._perm)
         p_a = ops.softmax7(audio_mean_logits)
-        return ops.fuse_compound(p_vs, p_vd, p_a, weights_1, weights_2, ce_weights_type, ce_mask)
+        if f64_video:
+            p_vs, p_vd, p_a = p_vs.double(), ops.softmax7(dyn.double()), p_a.double()
+        else:
+            p_vd = ops.softmax7(dyn)
+        return ops.fuse_compound(p_vs, p_vd, p_a, weights_1, weights_2, ce_weights_type, ce_mask, labels=labels)
 
     # ------------------------------------------------------------------ whole clips, batched
     def run_clips(self, crops_u8: torch.Tensor, exists_list: Sequence[np.ndarray], fps_list: Sequence[float],
@@ -347,4 +354,13 @@ class Engine:
             stat, dyn, plans = self.video_rows(probs, feats, exists_list, fps_list)
             a_rows, logits = self.audio_rows(wav_cat, wav_lens, fps_list, n_frames, step, window, sr, padding)
         labels = self.fuse(stat, dyn, a_rows, weights_1, weights_2, ce_weights_type, ce_mask)
+        # clips whose video tables the reference holds in float64 (a zero row: frames before the first VD output or
+        # without any crop) get their VD softmax and fusion redone in float64, like numpy does for them
+        base = 0
+        for plan, nf in zip(plans, n_frames):
+            if nf and (bool((plan.stat_src < 0).any()) or bool((plan.dyn_src < 0).any())):
+                sl = slice(base, base + nf)
+                labels[:, sl] = self.fuse(stat[sl], dyn[sl], a_rows[sl].contiguous(), weights_1, weights_2, ce_weights_type, ce_mask,
+                                          f64_video=True)
+            base += nf
         return {"labels": labels, "stat": stat, "dyn": dyn, "audio_mean": a_rows, "window_logits": logits}

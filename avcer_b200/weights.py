@@ -93,17 +93,30 @@ def pack_vs(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
     return out
 
 
+def split_bf16x3_weight(w: torch.Tensor) -> torch.Tensor:
+    """[N, K] fp32 -> [N, 3K] bf16 = [w_hi | w_hi | w_lo] (w_lo = bf16(w - w_hi)): the weight side of a bf16x3
+    contraction against activations laid out [a_hi | a_lo | a_hi] (avcer_split_bf16x3 / avcer_lstm_cell split)."""
+    hi = w.float().bfloat16()
+    lo = (w.float() - hi.float()).bfloat16()
+    return torch.cat([hi, hi, lo], dim=1)
+
+
 def pack_vd(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
     """LSTM(512->512) -> LSTM(512->256) -> Linear(256->7).  Layer 2's input and recurrent matrices
-    are concatenated along K so one GEMM over [h1_t | h2_{t-1}] yields its gate pre-activations."""
+    are concatenated along K so one GEMM over [h1_t | h2_{t-1}] yields its gate pre-activations.
+    bf16 mode packs every matrix for bf16x3 contractions (split_bf16x3_weight): the recurrence is a chain of 20
+    dependent GEMMs whose rounding errors would otherwise compound, and the network is tiny (57.7 MFLOP / window)."""
     def dev(t, dt=None):
         return t.to(device=device, dtype=dt or dtype).contiguous()
 
+    split = dtype == torch.bfloat16
+    mat = split_bf16x3_weight if split else (lambda w: w)
     return {
-        "w_ih1": dev(sd["lstm1.weight_ih_l0"]),
-        "w_hh1": dev(sd["lstm1.weight_hh_l0"]),
+        "split": split,
+        "w_ih1": dev(mat(sd["lstm1.weight_ih_l0"])),
+        "w_hh1": dev(mat(sd["lstm1.weight_hh_l0"])),
         "b1": dev(sd["lstm1.bias_ih_l0"] + sd["lstm1.bias_hh_l0"], torch.float32),
-        "w_cat2": dev(torch.cat([sd["lstm2.weight_ih_l0"], sd["lstm2.weight_hh_l0"]], dim=1)),
+        "w_cat2": dev(torch.cat([mat(sd["lstm2.weight_ih_l0"]), mat(sd["lstm2.weight_hh_l0"])], dim=1)),
         "b2": dev(sd["lstm2.bias_ih_l0"] + sd["lstm2.bias_hh_l0"], torch.float32),
         "fc_w": dev(sd["fc.weight"], torch.float32),
         "fc_b": dev(sd["fc.bias"], torch.float32),

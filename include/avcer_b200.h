@@ -206,10 +206,16 @@ int avcer_small_linear(const void* x, int64_t n, int k, int64_t ldx, const float
  * gates = xproj[xidx[r]] + hproj[r] (both [*, 4H] fp32, biases already folded into xproj);
  * c,h updated in place; c is fp32 [n,H]; h_out (dtype) feeds the next recurrent GEMM.
  * hproj may be NULL for the first step (h_{-1} = 0), xproj may be NULL when the input
- * projection is folded into hproj; ldh = row pitch of h_out in elements. */
+ * projection is folded into hproj; ldh = row pitch of h_out in elements.
+ * split != 0 (bf16 only): h is written as the bf16x3 operand [hi | lo | hi] (3*H columns; lo = bf16(h - hi)) that,
+ * against weights packed [w_hi | w_hi | w_lo], gives hi*w_hi + lo*w_hi + hi*w_lo: the recurrence keeps 16 mantissa
+ * bits through the bf16 tensor cores.  h_f32 (optional, [n,H]) also receives h in fp32 (input of the final Linear). */
 int avcer_lstm_cell(const float* xproj, const int32_t* xidx, const float* hproj, float* c,
-                    void* h_out, int64_t ldh, int64_t n, int hidden, int first, int dtype,
-                    void* stream);
+                    void* h_out, int64_t ldh, int64_t n, int hidden, int first, int split, float* h_f32,
+                    int dtype, void* stream);
+/* x fp32 [rows, k] (row pitch ldx) -> bf16 [rows, 3k] (row pitch ldo) = [hi | lo | hi]: the bf16x3 split of the
+ * relu(fc1) features feeding the LSTM input projection (get_prob_video.py:115-122). */
+int avcer_split_bf16x3(const float* x, int64_t rows, int k, int64_t ldx, void* out, int64_t ldo, void* stream);
 
 /* Audio decode seam (data/utils.py:49-60, convert_mp4_to_mp3 after its ffmpeg call): interleaved int16 PCM
  * [n, channels] -> x/32768 -> channel mean -> torchaudio.transforms.Resample (default "sinc_interp_hann" polyphase

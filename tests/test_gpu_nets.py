@@ -3,11 +3,20 @@ the oracle on identical seeded weights and inputs, and against the reference gol
 
 Tolerances (per-class probabilities, absolute):
   fp32 mode : 1e-5   (north star)
-  bf16 mode : 2e-3   (north star) with PyTorch-default random init -- the init the north star names
-              (measured 2.4e-4); 1e-2 with the deliberately wide "spread" init (logit range ~5, see
-              DESIGN.md), where bf16 storage of ~50 stacked layers is coarser than 2e-3 and the exact
-              value depends on the fp32 summation order inside the contractions: 2.9e-3 with per-tap
-              K loops, 6.1e-3 with the halo kernel's per-chunk loops, identical per-layer errors.
+  bf16 mode : 2e-3   (north star) on
+                * PyTorch-default random init (the init the north star names; measured 2.4e-4), and
+                * the "mid" init: He-normal convolutions, perturbed BN / LN statistics, heads scaled to a logit
+                  range of ~1 -- input-dependent outputs (asserted below: the reference's own probabilities
+                  vary across inputs by more than the tolerance);
+              VD (LSTM): 2e-3 on its widest init -- every contraction of the recurrence is bf16x3 (split
+              operands, fp32 accumulation), measured ~1e-5;
+              1e-2 on the deliberately wide "spread" init (logit range ~5) for VS / A: the probability error
+              is p(1-p) x the logit error, and the logit error of bf16 OPERANDS is ~0.65 % of the logit range
+              whatever is done about storage -- bf16 weights alone cost 1.1e-3 (VS) / 2.5e-3 (A) at this init,
+              an fp32 residual stream moves the total only from 4.8e-3 to 3.8e-3 (VS) and 6.8e-3 to 4.5e-3 (A)
+              (scripts/sim_bf16_budget.py, CPU emulation of every rounding point; profiles/r02_bf16_error_budget.txt).
+              What this init does assert in bf16: identical arg-max wherever the reference's top-2 margin
+              exceeds twice the measured error, and >= 99.5 % compound top-1 agreement (test_gpu_dropin.py).
 """
 import numpy as np
 import pytest
@@ -19,7 +28,8 @@ from oracle import video as ov
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-TOL = {("fp32", "spread"): 1e-5, ("fp32", "default"): 1e-5, ("bf16", "default"): 2e-3, ("bf16", "spread"): 1e-2}
+TOL = {("fp32", "spread"): 1e-5, ("fp32", "default"): 1e-5, ("fp32", "mid"): 1e-5,
+       ("bf16", "default"): 2e-3, ("bf16", "mid"): 2e-3, ("bf16", "spread"): 1e-2}
 
 
 def _vs_probs(sd, prec, crops):
@@ -33,13 +43,20 @@ def _vs_probs(sd, prec, crops):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
-@pytest.mark.parametrize("init", ["spread", "default"])
+@pytest.mark.parametrize("init", ["spread", "default", "mid"])
 def test_vs_matches_reference_golden(cuda_lib, golden, prec, init):
     g = golden["video"]
     crops = syn.make_crops(11, 6)
     probs, feat = _vs_probs(syn.make_vs_state_dict(0, init), prec, crops)
-    err = np.abs(probs - g[f"vs_{init}_probs"]).max()
+    ref = g[f"vs_{init}_probs"]
+    err = np.abs(probs - ref).max()
     assert err < TOL[(prec, init)], err
+    if init != "default":
+        # not a degenerate case: the reference's own probabilities move with the input by more than the tolerance
+        assert (ref.max(0) - ref.min(0)).max() > 2 * TOL[(prec, init)]
+        top2 = np.sort(ref, axis=1)[:, -2:]
+        sure = (top2[:, 1] - top2[:, 0]) > 2 * TOL[(prec, init)]
+        assert np.array_equal(probs.argmax(1)[sure], ref.argmax(1)[sure])
     ref_feat = np.maximum(g[f"vs_{init}_feat"], 0)
     assert np.abs(feat - ref_feat).max() < (2e-4 if prec == "fp32" else 0.15)
 
@@ -83,13 +100,14 @@ def test_vd_matches_reference_golden(cuda_lib, golden, prec):
     gen = torch.Generator().manual_seed(5)
     xw = torch.relu(torch.randn(12, 10, 512, generator=gen))
     net = nets.VDNet(syn.make_vd_state_dict(1), prec, DEV)
-    feats = xw.reshape(120, 512).to(DEV).to(net.dtype)
+    feats = xw.reshape(120, 512).to(DEV)                      # fp32 relu(fc1) features, as VSNet hands them over
     wins = torch.arange(120, dtype=torch.int32).view(12, 10).t().contiguous().to(DEV)
     out = net.forward(feats, wins).cpu()
     ref = torch.from_numpy(golden["video"]["vd_logits"])
     perr = (torch.softmax(out, 1) - torch.softmax(ref, 1)).abs().max().item()
-    assert perr < (1e-5 if prec == "fp32" else 4e-3), perr
-    assert (out - ref).abs().max().item() < (2e-5 if prec == "fp32" else 0.03)
+    # bf16 mode = bf16x3 contractions (split operands): the north-star 2e-3 holds with two orders of magnitude to spare
+    assert perr < (1e-5 if prec == "fp32" else 1e-4), perr
+    assert (out - ref).abs().max().item() < (2e-5 if prec == "fp32" else 1e-3)
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
@@ -108,25 +126,38 @@ def test_audio_matches_reference_golden(cuda_lib, golden, prec, ncls):
     assert out.shape == ref.shape
     p = torch.softmax(torch.from_numpy(out[:, :7]), 1).numpy()
     pr = torch.softmax(torch.from_numpy(ref[:, :7]), 1).numpy()
-    # "spread" init: logits of magnitude ~2 -> peaked probabilities; bf16 storage through the 12+2 layer
-    # stack is good to ~1e-2 here (numerics); the north-star 2e-3 is checked on default init below
+    # "spread" init (logit range ~5): the bf16 error budget of the module docstring (emulated 6.8e-3 on exactly these
+    # windows, measured 8e-3); the north-star 2e-3 is asserted on the default and "mid" inits below
     assert np.abs(p - pr).max() < (1e-5 if prec == "fp32" else 1.2e-2), np.abs(p - pr).max()
+    if prec == "bf16":
+        top2 = np.sort(pr, axis=1)[:, -2:]
+        sure = (top2[:, 1] - top2[:, 0]) > 2.4e-2
+        assert np.array_equal(p.argmax(1)[sure], pr.argmax(1)[sure])
     assert np.abs(out - ref).max() < (1e-4 if prec == "fp32" else 0.08)
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
-def test_audio_default_init_north_star_tolerance(cuda_lib, golden, prec):
+@pytest.mark.parametrize("init", ["default", "mid"])
+def test_audio_north_star_tolerance(cuda_lib, golden, prec, init):
+    """2e-3 (bf16) / 1e-5 (fp32) on the per-class probabilities against the unmodified reference: PyTorch-default init
+    and the input-dependent "mid" init (module docstring)."""
     from avcer_b200 import nets, ops, pipeline
 
     wav = syn.make_wav(31, 52800 + 123)
-    net = nets.ANet(syn.make_audio_state_dict(2, 8, "default", 12), prec, DEV)
+    net = nets.ANet(syn.make_audio_state_dict(2, 8, init, 12), prec, DEV)
     ap = pipeline.plan_audio(len(wav), 25, 0.5)
     x = ops.audio_normalize_windows(torch.from_numpy(wav).to(DEV), torch.from_numpy(ap.starts).to(DEV), 64000, "mean")
     out = net.forward(x).cpu().numpy()
-    ref = golden["audio"]["a8_default_window_logits"]
+    ref = golden["audio"][f"a8_{init}_window_logits"]
     p = torch.softmax(torch.from_numpy(out[:, :7]), 1).numpy()
     pr = torch.softmax(torch.from_numpy(ref[:, :7]), 1).numpy()
-    assert np.abs(p - pr).max() < (1e-5 if prec == "fp32" else 2e-3), np.abs(p - pr).max()
+    tol = 1e-5 if prec == "fp32" else 2e-3
+    assert np.abs(p - pr).max() < tol, np.abs(p - pr).max()
+    if init == "mid":
+        assert (pr.max(0) - pr.min(0)).max() > 10 * tol          # outputs depend on the input window
+        top2 = np.sort(pr, axis=1)[:, -2:]
+        sure = (top2[:, 1] - top2[:, 0]) > 2 * tol
+        assert sure.any() and np.array_equal(p.argmax(1)[sure], pr.argmax(1)[sure])
 
 
 def test_audio_padding_modes_and_nan_window(cuda_lib, golden):

@@ -63,7 +63,7 @@ def test_preprocess_digests(golden):
         assert hashlib.sha256(ov.pth_processing(img).tobytes()).hexdigest() == str(d)
 
 
-@pytest.mark.parametrize("init", ["spread", "default"])
+@pytest.mark.parametrize("init", ["spread", "default", "mid"])
 def test_vs_oracle_matches_reference(golden, init):
     g = golden["video"]
     crops = syn.make_crops(11, 6)[:3]

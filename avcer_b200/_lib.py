@@ -62,6 +62,7 @@ _SIGNATURES = {
     "avcer_device_check": (c_int, []),
     "avcer_num_sms": (c_int, []),
     "avcer_set_sm_limit": (c_int, [c_int]),
+    "avcer_debug_set_trace": (c_int, [c_void_p]),
     "avcer_preprocess_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "avcer_preprocess_maps": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "avcer_contract": (c_int, [POINTER(ContractDesc), c_void_p]),

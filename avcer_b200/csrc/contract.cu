@@ -103,7 +103,7 @@ static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   return check_launch("tc_gemm2_kernel");
 }
 
-// Development aid (not part of the public header): device buffer of kTraceCtas*kTraceTiles*kTraceSlots u64 that the
+// Development aid (avcer_debug_set_trace in the header): device buffer of kTraceCtas*kTraceTiles*kTraceSlots u64 that the
 // two-SM kernel fills with per-tile clock64 stamps of its first CTAs; nullptr (default) disables tracing.
 static unsigned long long* g_trace = nullptr;
 extern "C" int avcer_debug_set_trace(void* buf) {

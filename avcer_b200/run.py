@@ -122,7 +122,9 @@ def run_inference(path_video: str = "", path_save_results: str = "", flag_save_p
                                                    total_frames=total_frames, flag_save_prob=flag_save_prob,
                                                    flag_heatmaps=flag_heatmaps, model_heatmaps=model_heatmaps)
     print("Emotion prediction using audio model")
-    df_audio = preprocess_audio_and_predict(path_video=path_video, path_weights="src\\weights", fps=fps, step=0.5,
+    # the reference passes the Windows literal "src\weights" (run.py:245); on the Linux B200 host that is one odd directory
+    # name, so the separator is normalised
+    df_audio = preprocess_audio_and_predict(path_video=path_video, path_weights=os.path.join("src", "weights"), fps=fps, step=0.5,
                                             padding="mean", save_path=path_save_results, flag_save_prob=flag_save_prob,
                                             window=4, sr=16000, device=config.device())
     print("Compound expression prediction")

@@ -123,6 +123,21 @@ def pack_vd(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
     }
 
 
+def pos_conv_effective_weight(sd: Dict[str, torch.Tensor], prefix: str) -> torch.Tensor:
+    """Effective weight of wav2vec2's weight-normed positional conv (weight_norm(dim=2): w = g * v / ||v||, the norm taken
+    over (out, in) per kernel tap).  Accepts the three spellings a checkpoint can carry: the parametrizations API of
+    current torch (`parametrizations.weight.original0/1`), the older `weight_g` / `weight_v` pair, or a plain `weight`
+    saved after torch.nn.utils.remove_weight_norm."""
+    for kg, kv in ((".parametrizations.weight.original0", ".parametrizations.weight.original1"), (".weight_g", ".weight_v")):
+        if prefix + kg in sd and prefix + kv in sd:
+            g, v = sd[prefix + kg].double(), sd[prefix + kv].double()
+            return (v * (g / v.norm(p=2, dim=(0, 1), keepdim=True))).float()
+    if prefix + ".weight" in sd:
+        return sd[prefix + ".weight"].float()
+    raise KeyError(f"{prefix}: expected parametrizations.weight.original0/original1, weight_g/weight_v or weight in the "
+                   "audio state_dict (wav2vec2 positional conv)")
+
+
 def pack_audio(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
     """ExprModelV3 / V2 (wav2vec2-large-robust 12L + tl1 + tl2 + head)."""
     def dev(t, dt=None):
@@ -139,9 +154,7 @@ def pack_audio(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
     out["fp_ln"] = (dev(sd[p + "feature_projection.layer_norm.weight"], f32), dev(sd[p + "feature_projection.layer_norm.bias"], f32))
     out["fp_w"] = dev(sd[p + "feature_projection.projection.weight"])
     out["fp_b"] = dev(sd[p + "feature_projection.projection.bias"], f32)
-    g = sd[p + "encoder.pos_conv_embed.conv.parametrizations.weight.original0"].double()
-    v = sd[p + "encoder.pos_conv_embed.conv.parametrizations.weight.original1"].double()
-    w = (v * (g / v.norm(p=2, dim=(0, 1), keepdim=True))).float()          # [1024, 64, 128]
+    w = pos_conv_effective_weight(sd, p + "encoder.pos_conv_embed.conv")    # [1024, 64, 128]
     out["pos_w"] = dev(_tap_major(w))                                       # [1024, 128*64]
     out["pos_b"] = dev(sd[p + "encoder.pos_conv_embed.conv.bias"], f32)
     layers = []

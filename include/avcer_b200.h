@@ -41,6 +41,10 @@ int avcer_num_sms(void);
  * the audio branch (tensor-bound) of one pipeline step run side by side on two streams without one kernel's CTAs
  * occupying every SM.  The reference runs the two branches one after the other (run.py:224-268). */
 int avcer_set_sm_limit(int n_sms);
+/* Development aid: a device buffer of 4 CTAs x 64 tiles x 16 slots of uint64 that the two-SM contraction kernel fills
+ * with per-tile clock64 stamps of its first CTAs (producer / MMA / epilogue phases; scripts/trace_gemm2.py renders them);
+ * NULL (the default) disables tracing.  Not used on the product path. */
+int avcer_debug_set_trace(void* buf);
 
 /* ------------------------------------------------------------------------------------------
  * K1  face-crop preprocessing.

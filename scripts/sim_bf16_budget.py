@@ -208,32 +208,53 @@ def a_forward(sd, x, qa, qs, qw, n_layers=12):
     return F.linear(h, sd["feature_downsample.weight"], sd["feature_downsample.bias"])
 
 
-def run_a(init, scale):
+def run_a(init, scale, stages=False):
+    """The windows of tests/test_gpu_nets.py::test_audio_matches_reference_golden (52 923 samples, 7 windows incl. the
+    mostly padded tail ones)."""
+    from avcer_b200 import pipeline
+
     sd = syn.make_audio_state_dict(2, 8, init, 12)
     if scale != 1.0:
         sd["feature_downsample.weight"] = sd["feature_downsample.weight"] * scale
-    wav = syn.make_wav(31, 16000 * 5 - 160)
-    xs = np.stack([oa.zero_mean_unit_var(oa.pad_window(wav[s:s + 64000], 64000, "mean")) for s in (0, 8000, 16000)])
+    L = 52800 + 123
+    wav = syn.make_wav(31, L)
+    ap = pipeline.plan_audio(L, 25, 0.5)
+    xs = np.stack([oa.zero_mean_unit_var(oa.pad_window(wav[s:e], 64000, "mean")) for s, e in zip(ap.starts, ap.ends)])
     x = torch.from_numpy(xs)
     with torch.no_grad():
         lg = a_forward(sd, x, ident, ident, ident)
         ref = torch.softmax(lg[:, :7], 1)
         print(f"A init={init} scale={scale}: logit range {float(lg[:, :7].max() - lg[:, :7].min()):.2f}, p max {float(ref.max()):.3f}")
-        for name, (qa, qs, qw) in {"all_bf16": (rb, rb, rb), "stream_f32": (rb, ident, rb), "weights_only": (ident, ident, rb),
-                                   "acts_only_stream_f32": (rb, ident, ident)}.items():
+        variants = {"all_bf16": (rb, rb, rb), "stream_f32": (rb, ident, rb), "weights_only": (ident, ident, rb)}
+        if stages:
+            variants["residual stream only"] = (ident, rb, ident)
+            for st, what in (("fe", "feature-extractor activations only"), ("proj", "projection + positional conv operands only"),
+                             ("enc", "12 encoder layers' GEMM operands only"), ("tl", "tl1 / tl2 operands only"),
+                             ("head", "time_downsample head activations only")):
+                variants[what] = ({st: rb}, ident, ident)
+        for name, (qa, qs, qw) in variants.items():
             l2 = a_forward(sd, x, qa, qs, qw)
             p = torch.softmax(l2[:, :7], 1)
-            print(f"  {name:22s} max|dp| = {float((p - ref).abs().max()):.2e}   max|dlogit| = {float((l2 - lg).abs().max()):.2e}")
+            print(f"  {name:44s} max|dp| = {float((p - ref).abs().max()):.2e}   max|dlogit| = {float((l2 - lg).abs().max()):.2e}")
 
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
-    which = sys.argv[1] if len(sys.argv) > 1 else "vs"
+    which = sys.argv[1] if len(sys.argv) > 1 else "report"
     init = sys.argv[2] if len(sys.argv) > 2 else "spread"
     scale = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
     if which == "vs":
         run_vs(init, scale)
     elif which == "vd":
         run_vd()
-    else:
+    elif which == "a":
         run_a(init, scale)
+    else:
+        print("# bf16 error budget by CPU emulation of every rounding point (scripts/sim_bf16_budget.py report)")
+        print("# max|dp| = max over inputs and classes of |softmax(bf16 path) - softmax(fp32 path)|; north-star bar 2e-3")
+        run_vs("spread", 1.0)
+        run_vs("mid", 1.0)
+        run_vs("default", 1.0)
+        run_vd()
+        run_a("spread", 1.0, stages=True)
+        run_a("mid", 1.0)

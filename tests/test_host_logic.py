@@ -49,13 +49,17 @@ def test_plan_audio_matches_window_loop():
 
 
 def test_header_symbols_exported():
+    """include/avcer_b200.h, the dynamic symbol table of the built library (`nm -D`) and the ctypes table must name
+    exactly the same entry points: nothing undeclared is exported, nothing declared is missing."""
+    import subprocess
+
     hdr = open(os.path.join(ROOT, "include", "avcer_b200.h")).read()
     declared = set(re.findall(r"\b(avcer_[a-z0-9_]+)\s*\(", hdr))
     declared.discard("avcer_contract_desc")
     assert declared, "no declarations found"
-    lib = ctypes.CDLL(_lib.LIB_PATH)
-    for name in sorted(declared):
-        assert hasattr(lib, name), f"{name} declared in include/avcer_b200.h but not exported"
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    exported = {line.split()[-1] for line in nm.splitlines() if line.split()[-1].startswith("avcer_") and " T " in line}
+    assert exported == declared, f"header vs nm -D: {sorted(exported ^ declared)}"
     assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
     assert _lib.load().avcer_version() >= 100
 
@@ -105,6 +109,24 @@ def test_audio_pack_shapes():
     # weight-norm fold equals the oracle's
     eff = oa.pos_conv_weight(sd)
     assert (w["pos_w"].view(1024, 128, 64).permute(0, 2, 1) - eff).abs().max() < 1e-6
+
+
+def test_audio_pack_accepts_every_weight_norm_spelling():
+    """The positional conv's weight norm as saved by current torch (parametrizations), by older torch / transformers
+    (weight_g / weight_v) and after remove_weight_norm (plain weight); anything else is a descriptive KeyError."""
+    sd = syn.make_audio_state_dict(2, 8, "spread", 1)
+    pre = "wav2vec2.encoder.pos_conv_embed.conv"
+    ref = weights.pack_audio(sd, "cpu", torch.float32)["pos_w"]
+    old = dict(sd)
+    old[pre + ".weight_g"] = old.pop(pre + ".parametrizations.weight.original0")
+    old[pre + ".weight_v"] = old.pop(pre + ".parametrizations.weight.original1")
+    assert torch.equal(weights.pack_audio(old, "cpu", torch.float32)["pos_w"], ref)
+    plain = {k: v for k, v in sd.items() if "parametrizations" not in k}
+    plain[pre + ".weight"] = oa.pos_conv_weight(sd)
+    assert (weights.pack_audio(plain, "cpu", torch.float32)["pos_w"] - ref).abs().max() < 2e-6      # fp32 vs fp64 fold
+    bad = {k: v for k, v in sd.items() if "parametrizations" not in k}
+    with pytest.raises(KeyError, match="weight_g"):
+        weights.pack_audio(bad, "cpu", torch.float32)
 
 
 def test_balanced_batches_cover_and_differ_by_one():

@@ -135,3 +135,32 @@ def test_pred_av_labels_match_reference(golden, tmp_path):
         w1, w2v = pred_av_weights(tag, w2)
         labels, locs = of.pred_av_labels(pd.read_csv(fmt_path), read, list(tables), w1, w2v, cwt, cm)
         assert len(locs) == int(g["n_locations"]) and np.array_equal(labels, g[f"labels_{i}"]), (tag, w2, cwt, cm)
+
+
+def test_batch1_loops_match_batched_oracle(tmp_path):
+    """oracle/loop.py (the reference's own frame-at-a-time / window-at-a-time execution shape, timed by bench.py as the
+    "reference CPU path") against the batched restatements that make_golden pins to the unmodified reference."""
+    import cv2
+
+    from oracle import loop as ol
+
+    n, fps = 13, 25
+    missing = {0, 7}
+    frames = syn.make_crops(5, n, 96)
+    clip = tmp_path / "clip"
+    (clip / "00").mkdir(parents=True)
+    for i in range(n):
+        if i not in missing:
+            cv2.imwrite(str(clip / "00" / f"{i:06d}.jpg"), frames[i])
+    sd_vs, sd_vd = syn.make_vs_state_dict(0, "spread"), syn.make_vd_state_dict(1)
+    dyn, stat = ol.video_loop(str(clip), fps, n, sd_vs, sd_vd)
+    decoded = [cv2.imread(str(clip / "00" / f"{i:06d}.jpg")) if i not in missing else None for i in range(n)]
+    o_dyn, o_stat = ov.predict_video(decoded, fps, sd_vs, sd_vd)
+    assert dyn.dtype == o_dyn.dtype == np.float64 and stat.shape == o_stat.shape == (n, 7)
+    assert np.abs(stat - o_stat).max() < 1e-5 and np.abs(dyn - o_dyn).max() < 1e-4
+    sd_a = syn.make_audio_state_dict(2, 8, "spread", 1)
+    wav = syn.make_wav(9, 16000)
+    rows, ids = ol.audio_loop(wav, fps, sd_a, step=0.5)
+    o_rows, o_ids, _ = oa.predict_audio(wav, fps, sd_a, step=0.5)
+    assert np.array_equal(ids, o_ids) and np.array_equal(np.isnan(rows), np.isnan(o_rows))
+    assert np.nanmax(np.abs(rows - o_rows)) < 5e-5

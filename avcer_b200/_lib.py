@@ -66,8 +66,8 @@ _SIGNATURES = {
     "avcer_preprocess_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "avcer_preprocess_maps": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "avcer_contract": (c_int, [POINTER(ContractDesc), c_void_p]),
-    "avcer_fuse_compound": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_int, c_void_p, c_void_p]),
-    "avcer_fuse_compound_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_int, c_void_p, c_void_p]),
+    "avcer_fuse_compound": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_int, c_void_p, c_int64, c_void_p]),
+    "avcer_fuse_compound_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_int, c_void_p, c_int64, c_void_p]),
     "avcer_compound_scores": (c_int, [c_void_p, c_int64, c_int, c_int, POINTER(c_int32), POINTER(c_double), c_int, c_int, c_void_p, c_void_p]),
     "avcer_weight_search_confusion": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "avcer_fused_argmax": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -116,11 +116,14 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int h = unit % p.heads, b = unit / p.heads;
         mbar_wait(qk_empty, (u & 1u) ^ 1u);
         mbar_arrive_expect_tx(qk_full, p.mtiles * Cfg::Q_BYTES + Cfg::KV_BYTES);
-        for (int g = 0; g < p.mtiles; ++g) tma_load_2d(q_base + g * Cfg::Q_BYTES, &tmQ, qk_full, h * 64, b * p.t + g * 128);
-        tma_load_2d(k_base, &tmKV, qk_full, (p.heads + h) * 64, b * p.t);
+        // rank-3 maps (column, token, window): tokens >= T of a box are out of bounds and arrive as ZEROS, never as the
+        // first rows of the next window (a 0 * NaN in P V would otherwise leak an all-NaN window -- the empty tail
+        // window of "mean" padding, data/utils.py:74-89 -- into its predecessor in the batch)
+        for (int g = 0; g < p.mtiles; ++g) tma_load_3d(q_base + g * Cfg::Q_BYTES, &tmQ, qk_full, h * 64, g * 128, b);
+        tma_load_3d(k_base, &tmKV, qk_full, (p.heads + h) * 64, 0, b);
         mbar_wait(v_empty, (u & 1u) ^ 1u);
         mbar_arrive_expect_tx(v_full, Cfg::KV_BYTES);
-        tma_load_2d(v_base, &tmKV, v_full, (2 * p.heads + h) * 64, b * p.t);
+        tma_load_3d(v_base, &tmKV, v_full, (2 * p.heads + h) * 64, 0, b);
       }
     }
   } else if (warp == 1) {

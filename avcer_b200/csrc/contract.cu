@@ -391,12 +391,12 @@ int attention_tc5(const void* qkv, int n, int t, int heads, float scale, void* o
   p.out = static_cast<__nv_bfloat16*>(out);
   CUtensorMap tq, tkv;
   const uint64_t cols = (uint64_t)3 * heads * 64;
-  uint64_t dims[2] = {cols, (uint64_t)n * t};
-  uint64_t strides[1] = {cols * 2};
-  uint32_t boxq[2] = {64u, 128u};
-  uint32_t boxkv[2] = {64u, (uint32_t)Cfg::MAXT};
-  if (encode_map(&tq, qkv, 2, dims, strides, boxq, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
-  if (encode_map(&tkv, qkv, 2, dims, strides, boxkv, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  uint64_t dims[3] = {cols, (uint64_t)t, (uint64_t)n};          // (column, token, window): tokens >= T are zero-filled
+  uint64_t strides[2] = {cols * 2, (uint64_t)t * cols * 2};
+  uint32_t boxq[3] = {64u, 128u, 1u};
+  uint32_t boxkv[3] = {64u, (uint32_t)Cfg::MAXT, 1u};
+  if (encode_map(&tq, qkv, 3, dims, strides, boxq, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  if (encode_map(&tkv, qkv, 3, dims, strides, boxkv, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   static bool attr_done = false;
   if (!attr_done) {
     AVCER_CUDA(cudaFuncSetAttribute(attention_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));

@@ -104,7 +104,7 @@ __device__ __forceinline__ void fuse_one(const TIn (&a)[7], const TIn (&b)[7], c
 template <typename TIn, typename TC>
 __global__ void __launch_bounds__(FUSE_THREADS, 5)
 fuse_compound_kernel(const TIn* __restrict__ pvs, const TIn* __restrict__ pvd, const TIn* __restrict__ pa,
-                     long long n, const FuseParams p, long long* __restrict__ labels) {
+                     long long n, const FuseParams p, long long* __restrict__ labels, long long ld) {
   constexpr int FPT = 16 / sizeof(TIn);            // frames per lane and iteration
   constexpr int NV = 7;                            // 16-byte vectors per lane per stream
   constexpr int WARPS = FUSE_THREADS / 32;
@@ -138,7 +138,7 @@ fuse_compound_kernel(const TIn* __restrict__ pvs, const TIn* __restrict__ pvd, c
       long long lab[4];
       fuse_one<TIn, TC>(a, b, c, p, lab);
 #pragma unroll
-      for (int s = 0; s < 4; ++s) labels[s * n + f0 + fi] = lab[s];
+      for (int s = 0; s < 4; ++s) labels[s * ld + f0 + fi] = lab[s];
     }
     __syncwarp();                                  // the chunk is consumed: the next cp.async may overwrite it
   }
@@ -151,7 +151,7 @@ fuse_compound_kernel(const TIn* __restrict__ pvs, const TIn* __restrict__ pvd, c
     long long lab[4];
     fuse_one<TIn, TC>(a, b, c, p, lab);
 #pragma unroll
-    for (int s = 0; s < 4; ++s) labels[s * n + f] = lab[s];
+    for (int s = 0; s < 4; ++s) labels[s * ld + f] = lab[s];
   }
 }
 
@@ -159,7 +159,7 @@ fuse_compound_kernel(const TIn* __restrict__ pvs, const TIn* __restrict__ pvd, c
 template <typename TIn, typename TC>
 __global__ void __launch_bounds__(FUSE_THREADS)
 fuse_compound_scalar_kernel(const TIn* __restrict__ pvs, const TIn* __restrict__ pvd, const TIn* __restrict__ pa,
-                            long long n, const FuseParams p, long long* __restrict__ labels) {
+                            long long n, const FuseParams p, long long* __restrict__ labels, long long ld) {
   for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += (long long)gridDim.x * blockDim.x) {
     TIn a[7], b[7], c[7];
 #pragma unroll
@@ -167,7 +167,7 @@ fuse_compound_scalar_kernel(const TIn* __restrict__ pvs, const TIn* __restrict__
     long long lab[4];
     fuse_one<TIn, TC>(a, b, c, p, lab);
 #pragma unroll
-    for (int s = 0; s < 4; ++s) labels[s * n + f] = lab[s];
+    for (int s = 0; s < 4; ++s) labels[s * ld + f] = lab[s];
   }
 }
 
@@ -369,9 +369,11 @@ using namespace avcer;
 template <typename TIn>
 static int fuse_compound_impl(const TIn* p_vs, const TIn* p_vd, const TIn* p_a, int64_t n, const double* w1_host,
                               const double* w2_host, int ce_weights_type, int ce_mask, int64_t* labels,
-                              void* stream) {
+                              int64_t label_pitch, void* stream) {
   AVCER_REQUIRE(n >= 0, "fuse_compound: negative n");
+  AVCER_REQUIRE(label_pitch == 0 || label_pitch >= n, "fuse_compound: label_pitch %lld < n %lld", (long long)label_pitch, (long long)n);
   if (n == 0) return 0;
+  const long long ld = label_pitch > 0 ? label_pitch : n;
   FuseParams p{};
   p.has_w1 = w1_host != nullptr;
   p.ce_mask = ce_mask != 0;
@@ -398,7 +400,7 @@ static int fuse_compound_impl(const TIn* p_vs, const TIn* p_vd, const TIn* p_a, 
   p.w2_one = p.has_w1 && p.w2[0] == 1.0 && p.w2[1] == 1.0 && p.w2[2] == 1.0;
   p.cew_one = !ce_weights_type;
   const bool aligned = ((reinterpret_cast<uintptr_t>(p_vs) | reinterpret_cast<uintptr_t>(p_vd) | reinterpret_cast<uintptr_t>(p_a) |
-                         reinterpret_cast<uintptr_t>(labels)) & 15) == 0;
+                         reinterpret_cast<uintptr_t>(labels)) & 15) == 0 && ld % 2 == 0;
   constexpr int kFpt = 16 / sizeof(TIn);
   const long long work = aligned ? n / kFpt : n;
   const long long blocks_needed = (work + FUSE_THREADS - 1) / FUSE_THREADS + 1;
@@ -411,25 +413,25 @@ static int fuse_compound_impl(const TIn* p_vs, const TIn* p_vd, const TIn* p_a, 
   const bool f64 = p.has_w1 || sizeof(TIn) == 8;
   long long* lab = reinterpret_cast<long long*>(labels);
   if (aligned) {
-    if (f64) fuse_compound_kernel<TIn, double><<<grid, FUSE_THREADS, 0, st>>>(p_vs, p_vd, p_a, n, p, lab);
-    else fuse_compound_kernel<TIn, float><<<grid, FUSE_THREADS, 0, st>>>(p_vs, p_vd, p_a, n, p, lab);
+    if (f64) fuse_compound_kernel<TIn, double><<<grid, FUSE_THREADS, 0, st>>>(p_vs, p_vd, p_a, n, p, lab, ld);
+    else fuse_compound_kernel<TIn, float><<<grid, FUSE_THREADS, 0, st>>>(p_vs, p_vd, p_a, n, p, lab, ld);
   } else {
-    if (f64) fuse_compound_scalar_kernel<TIn, double><<<grid, FUSE_THREADS, 0, st>>>(p_vs, p_vd, p_a, n, p, lab);
-    else fuse_compound_scalar_kernel<TIn, float><<<grid, FUSE_THREADS, 0, st>>>(p_vs, p_vd, p_a, n, p, lab);
+    if (f64) fuse_compound_scalar_kernel<TIn, double><<<grid, FUSE_THREADS, 0, st>>>(p_vs, p_vd, p_a, n, p, lab, ld);
+    else fuse_compound_scalar_kernel<TIn, float><<<grid, FUSE_THREADS, 0, st>>>(p_vs, p_vd, p_a, n, p, lab, ld);
   }
   return check_launch("fuse_compound_kernel");
 }
 
 extern "C" int avcer_fuse_compound(const float* p_vs, const float* p_vd, const float* p_a, int64_t n,
                                    const double* w1_host, const double* w2_host, int ce_weights_type, int ce_mask,
-                                   int64_t* labels, void* stream) {
-  return fuse_compound_impl<float>(p_vs, p_vd, p_a, n, w1_host, w2_host, ce_weights_type, ce_mask, labels, stream);
+                                   int64_t* labels, int64_t label_pitch, void* stream) {
+  return fuse_compound_impl<float>(p_vs, p_vd, p_a, n, w1_host, w2_host, ce_weights_type, ce_mask, labels, label_pitch, stream);
 }
 
 extern "C" int avcer_fuse_compound_f64(const double* p_vs, const double* p_vd, const double* p_a, int64_t n,
                                        const double* w1_host, const double* w2_host, int ce_weights_type,
-                                       int ce_mask, int64_t* labels, void* stream) {
-  return fuse_compound_impl<double>(p_vs, p_vd, p_a, n, w1_host, w2_host, ce_weights_type, ce_mask, labels, stream);
+                                       int ce_mask, int64_t* labels, int64_t label_pitch, void* stream) {
+  return fuse_compound_impl<double>(p_vs, p_vd, p_a, n, w1_host, w2_host, ce_weights_type, ce_mask, labels, label_pitch, stream);
 }
 
 extern "C" int avcer_softmax7_f64(const double* x, int64_t n, int ld, double* y, void* stream) {

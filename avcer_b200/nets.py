@@ -31,11 +31,14 @@ class GraphedForward:
         self.fn = fn
         self.cache = {}
         self.sm_limit = sm_limit        # grid share of the persistent kernels baked into the captured launches
+        self.max_entries = 24
 
     def __call__(self, *static_inputs: torch.Tensor):
         key = tuple((t.data_ptr(), tuple(t.shape)) for t in static_inputs)
         entry = self.cache.get(key)
         if entry is None:
+            if len(self.cache) >= self.max_entries:          # bounded: ragged workloads would otherwise keep every shape's graph
+                self.cache.pop(next(iter(self.cache)))
             prof, ops.PROFILE = ops.PROFILE, None
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()

@@ -228,7 +228,8 @@ def preprocess(src: torch.Tensor, n: int, dst: torch.Tensor, layout: int, *, off
 # ----------------------------------------------------------------------------------------- K4 + glue
 def fuse_compound(p_vs: torch.Tensor, p_vd: torch.Tensor, p_a: torch.Tensor, weights_1, weights_2,
                   ce_weights_type: bool, ce_mask: bool, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Returns int64 labels [4, n] = (AV, VS, VD, A) compound-expression argmax."""
+    """Returns int64 labels [4, n] = (AV, VS, VD, A) compound-expression argmax.
+    `labels` may be a column slice [4, n] of a wider [4, total] buffer (row pitch labels.stride(0))."""
     _cuda(p_vs, "p_vs")
     n = p_vs.shape[0]
     assert p_vs.shape == p_vd.shape == p_a.shape == (n, 7)
@@ -237,6 +238,8 @@ def fuse_compound(p_vs: torch.Tensor, p_vd: torch.Tensor, p_a: torch.Tensor, wei
         assert t.is_contiguous()
     if labels is None:
         labels = torch.empty((4, n), device=p_vs.device, dtype=torch.int64)
+    assert labels.dtype == torch.int64 and tuple(labels.shape) == (4, n) and (n <= 1 or labels.stride(1) == 1)
+    pitch = labels.stride(0) if n > 0 else 0
     w1 = w2 = None
     if weights_1:
         w1a = np.ascontiguousarray(np.asarray(weights_1, dtype=np.float64).reshape(3, 7))
@@ -247,7 +250,7 @@ def fuse_compound(p_vs: torch.Tensor, p_vd: torch.Tensor, p_a: torch.Tensor, wei
     fn = lib.avcer_fuse_compound if p_vs.dtype == torch.float32 else lib.avcer_fuse_compound_f64
     with _Timed("fuse_compound", n * 116.0):      # 84 B in + 32 B of int64 labels out per frame
         _check(fn(p_vs.data_ptr(), p_vd.data_ptr(), p_a.data_ptr(), n, w1, w2, int(bool(ce_weights_type)),
-                 int(bool(ce_mask)), labels.data_ptr(), _stream()))
+                 int(bool(ce_mask)), labels.data_ptr(), pitch, _stream()))
     return labels
 
 
@@ -266,12 +269,13 @@ def weight_search_confusion(preds: torch.Tensor, gt: torch.Tensor, weights: torc
     return cm
 
 
-def softmax7(x: torch.Tensor) -> torch.Tensor:
+def softmax7(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Row softmax over the first 7 columns of x [n, >=7] (f32 or f64)."""
     _cuda(x, "x")
     n, ld = x.shape
     assert x.is_contiguous()
-    y = torch.empty((n, 7), device=x.device, dtype=x.dtype)
+    y = out if out is not None else torch.empty((n, 7), device=x.device, dtype=x.dtype)
+    assert tuple(y.shape) == (n, 7) and y.is_contiguous() and y.dtype == x.dtype
     lib = _lib.load()
     fn = lib.avcer_softmax7 if x.dtype == torch.float32 else lib.avcer_softmax7_f64
     check(fn(x.data_ptr(), n, ld, y.data_ptr(), _stream()))
@@ -289,12 +293,17 @@ def window_to_frame_mean(logits: torch.Tensor, f_lo: torch.Tensor, f_hi: torch.T
     return out
 
 
-def gather_rows(src: torch.Tensor, index: Optional[torch.Tensor], n_out: int, perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+def gather_rows(src: torch.Tensor, index: Optional[torch.Tensor], n_out: int, perm: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[i] = src[index[i]] (a zero row for index -1; identity when index is None), columns optionally permuted.
+    `out`: optional contiguous [n_out, ncols] destination (e.g. a slice of an all-gather send buffer)."""
     _cuda(src, "src")
     ncols = src.shape[1] if perm is None else perm.numel()
     assert perm is None or ncols == src.shape[1]
     assert src.dtype in (torch.float32, torch.float64) and src.is_contiguous()
-    out = torch.empty((n_out, ncols), device=src.device, dtype=src.dtype)
+    if out is None:
+        out = torch.empty((n_out, ncols), device=src.device, dtype=src.dtype)
+    assert tuple(out.shape) == (n_out, ncols) and out.is_contiguous() and out.dtype == src.dtype
     fn = _lib.load().avcer_gather_rows if src.dtype == torch.float32 else _lib.load().avcer_gather_rows_f64
     check(fn(src.data_ptr(), _ptr(index), n_out, ncols, _ptr(perm), out.data_ptr(), _stream()))
     return out

@@ -107,10 +107,31 @@ def balanced_batches(n: int, max_batch: int) -> List[Tuple[int, int]]:
 class Engine:
     """Holds the three packed networks and runs clips through K1 -> VS -> VD, A, alignment and K4."""
 
-    def _upload(self, a: np.ndarray, dtype) -> torch.Tensor:
-        """Host index array -> device through pinned memory, asynchronously (no stream sync)."""
-        t = torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).pin_memory()
-        return t.to(self.device, non_blocking=True)
+    _STAGE_SLOTS = 48           # ring of pinned staging buffers: a slot is reused ~4 steps later
+
+    def _upload(self, a: np.ndarray, dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Host index array -> device through a ring of reusable pinned staging buffers, asynchronously (no stream sync,
+        no cudaHostAlloc per call: a fresh pin_memory() costs more host time than the whole index plan).  A slot is only
+        overwritten after the copy that last read it has completed (per-slot event; the wait is normally a no-op)."""
+        a = np.ascontiguousarray(a, dtype=dtype)
+        if not hasattr(self, "_stage_ring"):
+            self._stage_ring = [[None, None] for _ in range(self._STAGE_SLOTS)]       # [pinned uint8 buffer, event]
+            self._stage_next = 0
+        slot = self._stage_ring[self._stage_next]
+        self._stage_next = (self._stage_next + 1) % self._STAGE_SLOTS
+        nbytes = max(a.nbytes, 1)
+        if slot[0] is None or slot[0].numel() < nbytes:
+            slot[0] = torch.empty(max(4096, 1 << (nbytes - 1).bit_length()), dtype=torch.uint8, pin_memory=True)
+            slot[1] = torch.cuda.Event()
+        else:
+            slot[1].synchronize()
+        host = slot[0][:a.nbytes].view(torch.from_numpy(a).dtype).view(a.shape)
+        host.copy_(torch.from_numpy(a))
+        if out is None:
+            out = torch.empty(a.shape, dtype=host.dtype, device=self.device)
+        out.copy_(host, non_blocking=True)
+        slot[1].record(torch.cuda.current_stream())
+        return out
 
     def __init__(self, sd_vs=None, sd_vd=None, sd_a=None, precision: str = "bf16", device: str = "cuda:0",
                  vs_batch: int = 256, a_batch: int = 64, use_graphs: bool = True, overlap: Optional[Tuple[int, int]] = None):
@@ -136,12 +157,38 @@ class Engine:
         self._a_stream = torch.cuda.Stream(device=self.device) if overlap else None
         self._vs_graph = GraphedForward(lambda x: self.vs.forward(x), vs_sms) if self.vs is not None else None
         self._a_graph = GraphedForward(lambda x: self.a.forward(x), a_sms) if self.a is not None else None
+        # the VD recurrence (~45 launches) is replayed as one graph per (features buffer, window count)
+        self._vd_graph = GraphedForward(lambda f, w: self.vd.forward(f, w), vs_sms) if self.vd is not None else None
+        self._vd_win: Dict[int, torch.Tensor] = {}
+        self._vs_out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
 
     def _vs_fwd(self, x: torch.Tensor):
         if self.use_graphs and ops.PROFILE is None:
             return self._vs_graph(x)
         with ops.sm_limit(self._vs_sms):
             return self.vs.forward(x)
+
+    def _vd_fwd(self, feats: torch.Tensor, win_rows: np.ndarray) -> torch.Tensor:
+        """win_rows: host int [10, M] rows of `feats` per time step.  The index buffer is persistent per M so that the
+        captured graph's pointers stay valid; the upload happens outside the graph."""
+        m = win_rows.shape[1]
+        if self.use_graphs and ops.PROFILE is None:
+            buf = self._vd_win.get(m)
+            if buf is None:
+                if len(self._vd_win) >= 16:
+                    self._vd_win.pop(next(iter(self._vd_win)))
+                buf = self._vd_win[m] = torch.empty((10, m), dtype=torch.int32, device=self.device)
+            self._upload(win_rows, np.int32, out=buf)
+            return self._vd_graph(feats, buf)
+        with ops.sm_limit(self._vs_sms):
+            return self.vd.forward(feats, self._upload(win_rows, np.int32))
+
+    def _vs_outputs(self, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Persistent (grow-only) per-frame VS outputs: stable addresses keep the VD graph cache hot across steps."""
+        if self._vs_out is None or self._vs_out[0].shape[0] < n:
+            self._vs_out = (torch.empty((n, 7), device=self.device, dtype=torch.float32),
+                            torch.empty((n, 512), device=self.device, dtype=torch.float32))
+        return self._vs_out[0][:n], self._vs_out[1][:n]
 
     def _a_fwd(self, x: torch.Tensor):
         if self.use_graphs and ops.PROFILE is None:
@@ -158,8 +205,7 @@ class Engine:
     def vs_forward_u8(self, crops_u8: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """crops_u8: device uint8 [n,224,224,3] BGR.  Returns (probs [n,7] fp32, features [n,512])."""
         n = crops_u8.shape[0]
-        probs = torch.empty((n, 7), device=self.device, dtype=torch.float32)
-        feats = torch.empty((n, 512), device=self.device, dtype=torch.float32)
+        probs, feats = self._vs_outputs(n)
         for s, e in balanced_batches(n, self.vs_batch):
             x = self._vs_input(e - s)
             ops.preprocess(crops_u8[s:e], e - s, x, self.vs.input_layout)
@@ -173,8 +219,7 @@ class Engine:
         copy stream while batch i is preprocessed and classified (double-buffered device staging)."""
         n = crops_host.shape[0]
         bs = self.vs_batch
-        probs = torch.empty((n, 7), device=self.device, dtype=torch.float32)
-        feats = torch.empty((n, 512), device=self.device, dtype=torch.float32)
+        probs, feats = self._vs_outputs(n)
         if not hasattr(self, "_stage"):
             self._stage = [torch.empty((bs, 224, 224, 3), device=self.device, dtype=torch.uint8) for _ in range(2)]
             self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -213,11 +258,10 @@ class Engine:
     def vs_forward_ragged(self, flat_u8: torch.Tensor, offsets: np.ndarray, heights: np.ndarray, widths: np.ndarray):
         """Crops of arbitrary size packed back to back in `flat_u8` (K1 does the NEAREST resize)."""
         n = len(offsets)
-        probs = torch.empty((n, 7), device=self.device, dtype=torch.float32)
-        feats = torch.empty((n, 512), device=self.device, dtype=torch.float32)
-        off = torch.from_numpy(np.asarray(offsets, dtype=np.int64)).to(self.device)
-        hh = torch.from_numpy(np.asarray(heights, dtype=np.int32)).to(self.device)
-        ww = torch.from_numpy(np.asarray(widths, dtype=np.int32)).to(self.device)
+        probs, feats = self._vs_outputs(n)
+        off = self._upload(np.asarray(offsets), np.int64)
+        hh = self._upload(np.asarray(heights), np.int32)
+        ww = self._upload(np.asarray(widths), np.int32)
         for s in range(0, n, self.vs_batch):
             e = min(n, s + self.vs_batch)
             x = self._vs_input(e - s)
@@ -229,7 +273,8 @@ class Engine:
 
     # ------------------------------------------------------------------ video branch of a set of clips
     def video_rows(self, probs: torch.Tensor, feats: torch.Tensor, exists_list: Sequence[np.ndarray],
-                   fps_list: Sequence[float]) -> Tuple[torch.Tensor, torch.Tensor, List[VideoPlan]]:
+                   fps_list: Sequence[float], stat_out: Optional[torch.Tensor] = None,
+                   dyn_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, List[VideoPlan]]:
         """probs/feats hold the VS outputs of the present frames of all clips, clip after clip.
         Returns per-frame (stat [sumN,7] VS probabilities, dyn [sumN,7] VD logits) in VIDEO_ORDER
         with the reference's carry-forward / gap semantics, plus the per-clip plans."""
@@ -252,16 +297,15 @@ class Engine:
         stat_idx_t = self._upload(np.concatenate(stat_idx), np.int32)
         dyn_idx_t = self._upload(np.concatenate(dyn_idx), np.int32)
         n_total = stat_idx_t.numel()
-        stat = ops.gather_rows(probs, stat_idx_t, n_total)
+        stat = ops.gather_rows(probs, stat_idx_t, n_total, out=stat_out)
         windows = np.concatenate(win_all, axis=0) if win_all else np.zeros((0, 10), dtype=np.int64)
         if windows.shape[0]:
             # windows index the sample list; map them to rows of `feats` so no feature copy is needed
             rows = np.concatenate(sample_rows)
-            win_rows = self._upload(rows[windows].T, np.int32)   # [10, M]
-            vd_logits = self.vd.forward(feats, win_rows)
+            vd_logits = self._vd_fwd(feats, rows[windows].T)       # [10, M] feature rows per time step
         else:
             vd_logits = torch.zeros((1, 7), device=dev, dtype=torch.float32)
-        dyn = ops.gather_rows(vd_logits, dyn_idx_t, n_total)
+        dyn = ops.gather_rows(vd_logits, dyn_idx_t, n_total, out=dyn_out)
         return stat, dyn, plans
 
     # ------------------------------------------------------------------ audio branch
@@ -289,7 +333,7 @@ class Engine:
         return ops.window_to_frame_mean(logits, lo, hi, n_frames)
 
     def audio_rows(self, wav_cat: torch.Tensor, wav_lens: Sequence[int], fps_list: Sequence[float], n_frames: Sequence[int],
-                   step: float = 0.5, window: int = 4, sr: int = 16000, padding: str = "mean"):
+                   step: float = 0.5, window: int = 4, sr: int = 16000, padding: str = "mean", out: Optional[torch.Tensor] = None):
         """Audio branch of several clips whose waveforms are concatenated in `wav_cat`.  Returns
         (per-frame mean logits [sum N, ncls] with the tail rule of run.py:99-103 applied, window logits)."""
         base = np.r_[0, np.cumsum(n_frames)]
@@ -309,7 +353,7 @@ class Engine:
         logits = self.audio_window_logits(wav_cat, np.concatenate(st_all), np.concatenate(en_all), padding, window * sr)
         a_mean = self.audio_frame_means(logits, np.concatenate(lo_all), np.concatenate(hi_all), int(base[-1]))
         tail = self._upload(np.concatenate(tail_src), np.int32)
-        return ops.gather_rows(a_mean, tail, int(base[-1])), logits
+        return ops.gather_rows(a_mean, tail, int(base[-1]), out=out), logits
 
     # ------------------------------------------------------------------ K4 on aligned per-frame rows
     def fuse(self, stat_video_order: torch.Tensor, dyn_video_order: torch.Tensor, audio_mean_logits: torch.Tensor,
@@ -330,37 +374,60 @@ class Engine:
         return ops.fuse_compound(p_vs, p_vd, p_a, weights_1, weights_2, ce_weights_type, ce_mask, labels=labels)
 
     # ------------------------------------------------------------------ whole clips, batched
+    def fuse_clips(self, stat: torch.Tensor, dyn: torch.Tensor, a_rows: torch.Tensor, f64_flags: Sequence[bool],
+                   n_frames: Sequence[int], weights_1, weights_2, ce_weights_type: bool, ce_mask: bool,
+                   labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """K4 over the per-frame rows of several clips (clip after clip).  Clips whose video tables the reference holds in
+        float64 (`f64_flags`: a zero row was appended -- frames before the first VD output or without any crop) get their
+        VD softmax and fusion redone in float64, like numpy does for them.  `labels`: optional [4, n] destination, which
+        may be a column slice of a wider buffer."""
+        labels = self.fuse(stat, dyn, a_rows, weights_1, weights_2, ce_weights_type, ce_mask, labels=labels)
+        base = 0
+        for flag, nf in zip(f64_flags, n_frames):
+            if nf and flag:
+                sl = slice(base, base + nf)
+                self.fuse(stat[sl], dyn[sl], a_rows[sl], weights_1, weights_2, ce_weights_type, ce_mask, f64_video=True,
+                          labels=labels[:, sl])
+            base += nf
+        return labels
+
+    @staticmethod
+    def needs_f64(exists: np.ndarray, fps: float) -> bool:
+        """True when the reference's video DataFrames of this clip are float64: a zero row is appended for every frame
+        before the first VD output (get_prob_video.py:89,163-178), i.e. unless frame 0 has a crop."""
+        ex = np.asarray(exists, dtype=bool)
+        return bool(ex.size) and not bool(ex[0])
+
     def run_clips(self, crops_u8: torch.Tensor, exists_list: Sequence[np.ndarray], fps_list: Sequence[float],
                   wav_cat: torch.Tensor, wav_lens: Sequence[int], weights_1, weights_2, ce_weights_type: bool, ce_mask: bool,
-                  step: float = 0.5, window: int = 4, sr: int = 16000, padding: str = "mean") -> Dict[str, torch.Tensor]:
+                  step: float = 0.5, window: int = 4, sr: int = 16000, padding: str = "mean",
+                  rows_out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None,
+                  fuse: bool = True) -> Dict[str, torch.Tensor]:
         """All clips at once.  crops_u8: uint8 [sum present frames, 224,224,3] BGR; wav_cat: fp32 waveforms
-        back to back.  Host (pinned) tensors are copied to the device first; device tensors are used as is."""
+        back to back.  Host (pinned) tensors are copied to the device first; device tensors are used as is.
+        rows_out = (stat [n,7], dyn [n,7], audio_mean [n,ncls]): contiguous destinations of the per-frame rows (slices of
+        an all-gather send buffer, dist.ShardedRunner); fuse=False stops before K4 (the caller fuses the gathered rows)."""
         if not wav_cat.is_cuda:
             wav_cat = wav_cat.to(self.device, non_blocking=True)
         n_frames = [len(e) for e in exists_list]
+        so, do, ao = rows_out if rows_out is not None else (None, None, None)
         if self.overlap and ops.PROFILE is None:
             cur = torch.cuda.current_stream()
             self._a_stream.wait_stream(cur)
             with torch.cuda.stream(self._a_stream):                      # audio branch: enqueued first, runs beside VS / VD
-                a_rows, logits = self.audio_rows(wav_cat, wav_lens, fps_list, n_frames, step, window, sr, padding)
+                a_rows, logits = self.audio_rows(wav_cat, wav_lens, fps_list, n_frames, step, window, sr, padding, out=ao)
             probs, feats = self.vs_forward_u8(crops_u8) if crops_u8.is_cuda else self.vs_forward_host(crops_u8)
-            stat, dyn, plans = self.video_rows(probs, feats, exists_list, fps_list)
+            stat, dyn, plans = self.video_rows(probs, feats, exists_list, fps_list, so, do)
             cur.wait_stream(self._a_stream)
             for t in (a_rows, logits, wav_cat):
                 t.record_stream(cur)
             wav_cat.record_stream(self._a_stream)
         else:
             probs, feats = self.vs_forward_u8(crops_u8) if crops_u8.is_cuda else self.vs_forward_host(crops_u8)
-            stat, dyn, plans = self.video_rows(probs, feats, exists_list, fps_list)
-            a_rows, logits = self.audio_rows(wav_cat, wav_lens, fps_list, n_frames, step, window, sr, padding)
-        labels = self.fuse(stat, dyn, a_rows, weights_1, weights_2, ce_weights_type, ce_mask)
-        # clips whose video tables the reference holds in float64 (a zero row: frames before the first VD output or
-        # without any crop) get their VD softmax and fusion redone in float64, like numpy does for them
-        base = 0
-        for plan, nf in zip(plans, n_frames):
-            if nf and (bool((plan.stat_src < 0).any()) or bool((plan.dyn_src < 0).any())):
-                sl = slice(base, base + nf)
-                labels[:, sl] = self.fuse(stat[sl], dyn[sl], a_rows[sl].contiguous(), weights_1, weights_2, ce_weights_type, ce_mask,
-                                          f64_video=True)
-            base += nf
-        return {"labels": labels, "stat": stat, "dyn": dyn, "audio_mean": a_rows, "window_logits": logits}
+            stat, dyn, plans = self.video_rows(probs, feats, exists_list, fps_list, so, do)
+            a_rows, logits = self.audio_rows(wav_cat, wav_lens, fps_list, n_frames, step, window, sr, padding, out=ao)
+        out = {"stat": stat, "dyn": dyn, "audio_mean": a_rows, "window_logits": logits}
+        if fuse:
+            flags = [bool((p.stat_src < 0).any()) or bool((p.dyn_src < 0).any()) for p in plans]
+            out["labels"] = self.fuse_clips(stat, dyn, a_rows, flags, n_frames, weights_1, weights_2, ce_weights_type, ce_mask)
+        return out

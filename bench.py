@@ -173,7 +173,7 @@ def run_reference_arm(args, workload):
             "ms_per_step": 1e3 * w, "wall_s_timed_steps": sum(walls), "batch1_loop": smp.loop_step()}
     cfg = dict(workload, cpu_step=f"{smp.frames} frames + {smp.windows} audio windows per step (bounded sample of the workload)")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * w, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * w, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": base,
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
             "note": "one host (all its cores) regardless of --gpus: compare with the N=1 line only"}
@@ -187,7 +187,9 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--clips-per-gpu", type=int, default=8)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--clips", type=int, default=64)              # strong scaling: the fixed clip set
+    ap.add_argument("--clips-per-gpu", type=int, default=8)       # weak scaling
     ap.add_argument("--clip-seconds", type=int, default=60)
     ap.add_argument("--fps", type=int, default=25)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
@@ -197,16 +199,32 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()
 
-    n_frames = args.clip_seconds * args.fps
-    n_samples = args.clip_seconds * 16000
     from avcer_b200.pipeline import plan_audio
 
-    n_windows = len(plan_audio(n_samples, args.fps).starts)
-    workload = {"workload": f"BASELINE config 4 shard: {args.clips_per_gpu} clips/GPU x {args.clip_seconds} s @ {args.fps} fps "
-                            f"({n_frames} crops 224x224 + {n_samples} audio samples, {n_windows} windows of 4 s / step 0.5 s per clip), "
-                            "VS ResNet-50 + VD LSTM + A wav2vec2-L12 (8 classes) + fusion Rule 1 with the AV-8cl weight matrix",
-                "clips_per_gpu": args.clips_per_gpu, "frames_per_clip": n_frames, "windows_per_clip": n_windows,
-                "vs_batch": args.vs_batch, "a_batch": args.a_batch, "parallelism": f"clip-sharded x{args.gpus}", "l2_policy": "inputs (>=1.8 GB/step) larger than L2", "weights": "random-init, seeded"}
+    # ---- the clip set.  strong (default, BASELINE config 4: a FIXED set of clips sharded over the GPUs): --clips clips of
+    # mixed length, mean --clip-seconds; weak: --clips-per-gpu clips of --clip-seconds on every rank (round-1 workload).
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.scaling == "strong":
+        pattern = (1.0, 0.5, 1.5, 1.0, 2.0, 1.0 / 6.0, 1.0, 5.0 / 6.0)                  # x clip_seconds; mean 1.0
+        durations = [max(1, int(round(args.clip_seconds * pattern[i % len(pattern)]))) for i in range(args.clips)]
+    else:
+        durations = [args.clip_seconds] * (args.clips_per_gpu * world_env)
+    frames_all = [d * args.fps for d in durations]
+    samples_all = [d * 16000 for d in durations]
+    windows_all = [len(plan_audio(sm, args.fps).starts) for sm in samples_all]
+    total_frames = sum(frames_all)
+    n_frames, n_windows = args.clip_seconds * args.fps, len(plan_audio(args.clip_seconds * 16000, args.fps).starts)
+    what = (f"BASELINE config 4, fixed set sharded over the GPUs (strong scaling): {len(durations)} clips of "
+            f"{min(durations)}-{max(durations)} s (mean {sum(durations) / len(durations):.0f} s) @ {args.fps} fps = {total_frames} face crops 224x224 + "
+            f"{sum(durations)} s of 16 kHz audio ({sum(windows_all)} windows of 4 s / step 0.5 s) per step"
+            if args.scaling == "strong" else
+            f"BASELINE config 4 shard (weak scaling): {args.clips_per_gpu} clips/GPU x {args.clip_seconds} s @ {args.fps} fps "
+            f"({n_frames} crops 224x224 + {n_windows} windows of 4 s / step 0.5 s per clip)")
+    workload = {"workload": what + ", VS ResNet-50 + VD LSTM + A wav2vec2-L12 (8 classes) + fusion Rule 1 with the AV-8cl weight matrix",
+                "clips": len(durations), "frames_per_step": total_frames, "windows_per_step": sum(windows_all),
+                "frames_per_clip": n_frames, "windows_per_clip": n_windows,
+                "vs_batch": args.vs_batch, "a_batch": args.a_batch, "parallelism": f"clip-sharded x{args.gpus} (LPT on frames + 11.6 x windows)",
+                "l2_policy": "inputs (>= 1.8 GB per rank and step) larger than L2", "weights": "random-init, seeded"}
     if args.impl == "reference":
         return run_reference_arm(args, workload)
 
@@ -221,20 +239,28 @@ def main():
                  precision=args.precision, device=dev, vs_batch=args.vs_batch, a_batch=args.a_batch)
     w1, w2 = gwm.class_weights(gwm.weights_3), [1, 1, 1]
 
-    # synthetic shard of this rank (seeded by the global clip index)
-    c = args.clips_per_gpu
-    g = torch.Generator(device=dev).manual_seed(1000 + rank)
-    crops_dev = torch.randint(0, 256, (c * n_frames, 224, 224, 3), dtype=torch.uint8, device=dev, generator=g)
-    wav_dev = (torch.randn(c * n_samples, device=dev, generator=g) * 0.1).contiguous()
-    exists = [np.ones(n_frames, dtype=bool) for _ in range(c)]
-    fps_list = [float(args.fps)] * c
-    wav_lens = [n_samples] * c
-    counts = [c * n_frames] * world
+    # every rank knows the metadata of all clips and generates the data of its own shard (seeded by the global clip index)
+    runner = adist.ShardedRunner(eng, frames_all, windows_all, [False] * len(durations), rank, world)
+    mine = runner.my_clips
+    local_frames = sum(frames_all[i] for i in mine)
+    crops_dev = torch.empty((local_frames, 224, 224, 3), dtype=torch.uint8, device=dev)
+    wav_dev = torch.empty(sum(samples_all[i] for i in mine), dtype=torch.float32, device=dev)
+    fo = so = 0
+    for i in mine:
+        g = torch.Generator(device=dev).manual_seed(1000 + i)
+        crops_dev[fo: fo + frames_all[i]] = torch.randint(0, 256, (frames_all[i], 224, 224, 3), dtype=torch.uint8, device=dev, generator=g)
+        wav_dev[so: so + samples_all[i]] = torch.randn(samples_all[i], device=dev, generator=g) * 0.1
+        fo += frames_all[i]
+        so += samples_all[i]
+    exists = [np.ones(frames_all[i], dtype=bool) for i in mine]
+    fps_list = [float(args.fps)] * len(mine)
+    wav_lens = [samples_all[i] for i in mine]
+    c = len(mine)
 
     def step(crops, wav):
-        out = eng.run_clips(crops, exists, fps_list, wav, wav_lens, w1, w2, False, True)
-        labels = out["labels"].t().contiguous()                       # [frames, 4]
-        return adist.allgather_rows(labels, counts) if world > 1 else labels
+        # K1 -> VS -> VD, A, alignment on this rank's clips; per-frame rows straight into the all-gather send buffer; ONE
+        # collective; the fusion tail (permute, softmax, K4) over every gathered block -> labels of all frames on all ranks
+        return runner.step(crops, exists, fps_list, wav, wav_lens, w1, w2, False, True)
 
     def barrier():
         if world > 1:
@@ -243,6 +269,12 @@ def main():
 
     for _ in range(args.warmup):
         step(crops_dev, wav_dev)
+    barrier()
+    # Host cost of enqueuing ONE step into an empty launch queue (the timed loop below enqueues back to back, where the
+    # host blocks on the driver's bounded queue and its wall time only mirrors the GPU's)
+    t_iso = time.perf_counter()
+    step(crops_dev, wav_dev)
+    host_isolated_ms = (time.perf_counter() - t_iso) * 1e3
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -274,7 +306,6 @@ def main():
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms = float(t.item())
-    total_frames = world * c * n_frames
     value = total_frames * args.steps / (ms / 1e3)
 
     # per-kernel roofline from the profiled step
@@ -331,8 +362,9 @@ def main():
         if world > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e = {"value": total_frames * args.steps / (float(t.item()) / 1e3), "unit": "frames/s",
-               "h2d_bytes_per_step": int(crops_host.numel() + wav_host.numel() * 4),
-               "d2h_bytes_per_step": int(labels_host.numel() * 8), "api": "avcer_b200.pipeline.Engine.run_clips (host pinned inputs)"}
+               "h2d_bytes_per_step": int(total_frames * 224 * 224 * 3 + sum(samples_all) * 4),      # whole job: every rank's crops + waveforms
+               "d2h_bytes_per_step": int(labels_host.numel() * 8 * world),                        # every rank reads all labels back
+               "api": "avcer_b200.dist.ShardedRunner.step -> pipeline.Engine.run_clips (pinned host inputs)"}
         crops_dev = crops_host.to(dev)
 
     # BASELINE config 2: VS alone, batch 256, bf16 (K1 + ResNet-50), L2 flushed between iterations
@@ -415,11 +447,14 @@ def main():
     if world == 1 and not args.skip_cpu_baseline:
         cpu = cpu_baseline()
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": workload,
-            "audio_seconds_per_sec": world * c * args.clip_seconds * args.steps / (ms / 1e3),
+            "audio_seconds_per_sec": sum(durations) * args.steps / (ms / 1e3),
+            "shard_frames": runner.counts, "collective": {"op": "all_gather_into_tensor", "bytes_per_rank": int(runner.send.numel() * 4),
+                                                         "layout": "per-frame VS probabilities [n,7] + VD logits [n,7] + audio mean logits [n,8], fp32"},
             "roofline": roofline, "kernels": dict(extra, **micro), "vs_resnet50_b256": vs_alone, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks}
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_isolated_ms,
+            "host_wall_ms_per_step_in_timed_loop": host_enqueue_ms, "clocks": clocks}
     print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()

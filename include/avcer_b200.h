@@ -120,17 +120,20 @@ int avcer_contract(const avcer_contract_desc* d, void* stream);
  * p_vs: [n,7] f32 VS probabilities (audio emotion order), p_vd / p_a: [n,7] f32 probabilities.
  * w1: [3][7] f64 per-class weights or NULL (=> mean of the three, run.py:115-116),
  * w2: [3] f64 per-model weights.  ce_weights_type / ce_mask as in run.py:31-32.
- * labels: [4][n] int64 (AV, VS, VD, A).  Arithmetic is IEEE double, left-to-right, no FMA
- * contraction; argmax returns the first maximum (numpy semantics, NaN counts as maximum).
+ * labels: [4][label_pitch] int64 (AV, VS, VD, A), frames 0..n-1 of each row written; label_pitch = 0 means n
+ * (a dense [4][n] array).  A pitch > n lets a shard's labels land directly in its slot of a [4][all frames] buffer
+ * (multi-GPU: every rank fuses the all-gathered per-frame rows block by block, no concatenation pass).
+ * Arithmetic is IEEE double, left-to-right, no FMA contraction; argmax returns the first maximum (numpy
+ * semantics, NaN counts as maximum).
  */
 int avcer_fuse_compound(const float* p_vs, const float* p_vd, const float* p_a, int64_t n,
                         const double* w1_host, const double* w2_host, int ce_weights_type,
-                        int ce_mask, int64_t* labels, void* stream);
+                        int ce_mask, int64_t* labels, int64_t label_pitch, void* stream);
 /* Same with float64 probability inputs (the reference DataFrames become float64 when a zero row
  * was appended, get_prob_video.py:89,160-178); arithmetic is then float64 in every branch. */
 int avcer_fuse_compound_f64(const double* p_vs, const double* p_vd, const double* p_a, int64_t n,
                             const double* w1_host, const double* w2_host, int ce_weights_type,
-                            int ce_mask, int64_t* labels, void* stream);
+                            int ce_mask, int64_t* labels, int64_t label_pitch, void* stream);
 
 /* data/utils.py:222-241 (get_compound_expression) as a stand-alone op: pred [n,ncols] (f32 or f64),
  * k pairs (i1,i2) with weights (w1,w2) given on the host, optional 1/7 mask; out [n,k] f64. */

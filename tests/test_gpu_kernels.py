@@ -88,6 +88,28 @@ def test_attention_matches_torch(cuda_lib, heads, dh, t, dtype):
     assert (out.float() - ref).abs().max().item() < tol
 
 
+@pytest.mark.parametrize("heads,dh", [(16, 64), (32, 32)])
+@pytest.mark.parametrize("dtype", [BF, torch.float32])
+def test_attention_windows_are_isolated_from_a_nan_neighbour(cuda_lib, heads, dh, dtype):
+    """An all-NaN window in the batch (the empty tail window of "mean" padding, data/utils.py:74-89) must not touch its
+    neighbours: T = 199 is not a multiple of the 16-key MMA step, so a kernel that pads a window's K / V rows with the
+    first rows of the next window turns 0 * NaN into NaN (found by the exact BASELINE config-1 test).  Every other
+    window's output must be bit-identical to the same batch with a finite neighbour."""
+    from avcer_b200 import ops
+
+    torch.manual_seed(3)
+    n, t = 4, 199
+    qkv = (torch.randn(n * t, 3 * heads * dh, device=DEV) * 1.5).to(dtype)
+    clean = ops.attention(qkv, n, t, heads, dh, dh ** -0.5).clone()
+    bad = qkv.clone()
+    bad[2 * t:3 * t] = float("nan")
+    out = ops.attention(bad, n, t, heads, dh, dh ** -0.5)
+    keep = torch.ones(n * t, dtype=torch.bool, device=DEV)
+    keep[2 * t:3 * t] = False
+    assert torch.isnan(out[~keep]).all()
+    assert torch.equal(out[keep], clean[keep])
+
+
 @pytest.mark.parametrize("n,h,w,c,cout", [
     (3, 55, 55, 64, 64),        # layer1 conv2: resident filter bank, 4-row tiles, ragged last tile (55 = 13*4 + 3)
     (2, 28, 28, 128, 128),      # layer2 conv2: streamed weights, two K chunks, 8-row tiles (28 = 3*8 + 4)

@@ -115,7 +115,9 @@ def make_vd_state_dict(seed: int = 1, init: str = "spread") -> "OrderedDict[str,
     sd["lstm2.weight_hh_l0"] = u((1024, 256), 256)
     sd["lstm2.bias_ih_l0"] = u((1024,), 256)
     sd["lstm2.bias_hh_l0"] = u((1024,), 256)
-    sd["fc.weight"] = u((7, 256), 256) * (1.0 if init == "default" else 4.0)
+    # "spread": head x4 (logit range ~4); "mid": head x4 x MID_HEAD_SCALE -- in the pipeline the LSTM's inputs are the VS
+    # network's bf16 features, so its end-to-end probability error scales with its own logit range like VS / A
+    sd["fc.weight"] = u((7, 256), 256) * (1.0 if init == "default" else 4.0 * (MID_HEAD_SCALE if init == "mid" else 1.0))
     sd["fc.bias"] = u((7,), 256)
     return sd
 

@@ -52,6 +52,11 @@ class ContractDesc(ctypes.Structure):
         ("dtype", c_int32),
         ("out_f32", c_int32),
         ("a_step", c_int32),
+        ("ln_stats", c_void_p),
+        ("ln_colsum", c_void_p),
+        ("ln_parts", c_int32),
+        ("ln_eps", c_float),
+        ("stats_out", c_void_p),
     ]
 
 
@@ -79,6 +84,7 @@ _SIGNATURES = {
     "avcer_gather_rows_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "avcer_stem_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "avcer_stem_pool_ld": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
+    "avcer_stem_pool_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     "avcer_maxpool3x3s2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "avcer_avgpool": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "avcer_small_linear": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),

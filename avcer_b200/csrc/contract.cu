@@ -139,6 +139,7 @@ static int conv3x3_tc(const avcer_contract_desc* d, cudaStream_t st) {
   const int C = d->cin, W = d->W, H = d->H, NB = d->NB, Cout = d->cout;
   const bool shape = on != 0 && d->taps_w == 3 && d->taps_h == 3 && d->off_w == -1 && d->off_h == -1 && !d->tap_h_in_dim4 &&
                      d->group_cin_shift == 0 && !d->a_strip && d->a_step <= 1 && !d->out_f32 && d->residual == nullptr && C % 64 == 0 &&
+                     d->ln_stats == nullptr && d->stats_out == nullptr &&
                      ((Cout == 64 && C == 64) || Cout == 128) && W + 2 >= 28 && W + 2 <= 63 && NB >= 1 &&
                      (d->act == ACT_NONE || d->act == ACT_RELU);
   const bool dense = d->a_dim[0] == C && d->a_dim[1] == W && d->a_dim[2] == H && d->a_dim[3] == NB && d->a_stride[0] == 1 &&
@@ -252,6 +253,17 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   p.act = d->act;
   p.res_after_act = d->res_after_act;
   p.trace = g_trace;
+  p.ln_stats = d->ln_stats;
+  p.ln_colsum = d->ln_colsum;
+  p.ln_parts = d->ln_parts;
+  p.ln_inv_k = 1.0f / (float)((long long)d->taps_w * d->taps_h * d->cin);
+  p.ln_eps = d->ln_eps;
+  p.stats_out = d->stats_out;
+  AVCER_REQUIRE(d->ln_stats == nullptr || (d->ln_colsum != nullptr && d->ln_parts > 0 && d->ln_parts <= 64 && !d->out_f32 &&
+                                           (reinterpret_cast<uintptr_t>(d->ln_stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(d->ln_colsum) & 15) == 0),
+                "contract(bf16): folded LayerNorm needs ln_colsum, 1..64 parts, 8/16-byte aligned tables and a bf16 output");
+  AVCER_REQUIRE(d->stats_out == nullptr || (!d->out_f32 && d->cout % 32 == 0 && (reinterpret_cast<uintptr_t>(d->stats_out) & 7) == 0),
+                "contract(bf16): stats_out needs a bf16 output with cout %% 32 == 0");
   if (p.num_tiles == 0) return 0;
 
   const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -288,6 +300,7 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   // It trades two pipeline stages for per-warp staging slabs: only for short K loops, whose tiles are epilogue-bound
   // (deep K loops are MMA-bound and want the stages: measured +30 % time on K >= 1024 GEMMs with residual).
   const bool flat = flat_env != 0 && use_cta2 && BN == 256 && d->H == 1 && d->NB == 1 && p.bw == 128 && p.bh == 1 && p.bn == 1 &&
+                    d->ln_stats == nullptr && d->stats_out == nullptr &&      // the LayerNorm hooks live in the ring epilogues
                     (long long)d->taps_w * d->taps_h * p.kchunks <= (flat_env > 1 ? 1 << 30 : 8);
   if (mode != OUT_DIRECT_F32) {
     const int64_t ext[3] = {d->W, d->H, d->NB};
@@ -373,6 +386,33 @@ static int stem_pool_tc(const void* x, const void* w_packed, const float* bias, 
   if (g > p.units) g = p.units;
   launch_pdl_tpc(stem_pool_kernel, g, StemPoolCfg::THREADS, StemPoolCfg::SMEM, st, ta, p);
   return check_launch("stem_pool_kernel");
+}
+
+// ------------------------------------------------------------------ K1 fused into the stem (packed 224x224 uint8 crops)
+static int stem_pool_u8_tc(const uint8_t* crops, const void* w_packed, const float* bias, int n, void* out, int64_t out_pitch,
+                           cudaStream_t st) {
+  AVCER_REQUIRE(out_pitch >= 64 && out_pitch % 8 == 0, "stem_pool_u8: out_pitch %lld must be a multiple of 8, at least 64", (long long)out_pitch);
+  AVCER_REQUIRE(crops != nullptr && w_packed != nullptr && bias != nullptr && out != nullptr, "stem_pool_u8: null pointer");
+  AVCER_REQUIRE((reinterpret_cast<uintptr_t>(crops) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "stem_pool_u8: crops / w_packed / out must be 16-byte aligned");
+  if (n == 0) return 0;
+  StemPoolParams p{};
+  p.n = n;
+  p.units = 4 * n;
+  p.w_packed = w_packed;
+  p.bias = bias;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.out_pitch = out_pitch;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AVCER_CUDA(cudaFuncSetAttribute(stem_pool_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemPoolU8Cfg::SMEM));
+    attr_done = true;
+  }
+  int g = num_sms();
+  if (g > p.units) g = p.units;
+  launch_pdl_tpc(stem_pool_u8_kernel, g, StemPoolU8Cfg::THREADS, StemPoolU8Cfg::SMEM, st, crops, p);
+  return check_launch("stem_pool_u8_kernel");
 }
 
 // ------------------------------------------------------------------ tcgen05 attention (bf16, head dim 64, T <= 208)
@@ -544,6 +584,7 @@ __global__ void __launch_bounds__(256) simt_contract_kernel(const SimtParams p) 
 
 static int contract_simt(const avcer_contract_desc* d, cudaStream_t st) {
   AVCER_REQUIRE(d->a_step <= 1, "contract(fp32): a_step is a bf16-path feature");
+  AVCER_REQUIRE(d->ln_stats == nullptr && d->stats_out == nullptr, "contract(fp32): the folded LayerNorm is a bf16-path feature");
   SimtParams p{};
   p.a = static_cast<const float*>(d->a);
   for (int i = 0; i < 5; ++i) { p.a_dim[i] = d->a_dim[i]; p.a_stride[i] = d->a_stride[i]; }
@@ -593,4 +634,11 @@ extern "C" int avcer_stem_pool_ld(const void* x_padded, const void* w_packed, co
   using namespace avcer;
   AVCER_REQUIRE(n >= 0, "stem_pool: negative batch");
   return stem_pool_tc(x_padded, w_packed, bias, n, out, out_pitch, as_stream(stream));
+}
+
+extern "C" int avcer_stem_pool_u8(const uint8_t* crops, const void* w_packed, const float* bias, int n, void* out, int64_t out_pitch,
+                                  void* stream) {
+  using namespace avcer;
+  AVCER_REQUIRE(n >= 0, "stem_pool_u8: negative batch");
+  return stem_pool_u8_tc(crops, w_packed, bias, n, out, out_pitch, as_stream(stream));
 }

@@ -412,6 +412,12 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int nt, w0, h0, n0;
       tile_coords(pt, nt, w0, h0, n0);
       if (store_thread) trace_stamp(p, local, 6);
+      long long grow = -1;
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (p.ln_stats != nullptr || p.stats_out != nullptr) {
+        grow = (r < rows) ? tile_row_index(p, r, w0, h0, n0) : -1;
+        ln_row_scalars(p, grow, ln_mean, ln_rstd);           // overlaps the wait for the accumulator
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (store_thread) trace_stamp(p, local, 7);
@@ -431,6 +437,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        ln_apply32(p, f, co, ln_mean, ln_rstd);
         if (p.bias != nullptr && co < p.Cout) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -470,6 +477,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         } else {
           apply_act();
         }
+        stats_store32(p, f, grow, co);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint4 u;

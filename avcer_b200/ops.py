@@ -19,7 +19,7 @@ from ._lib import check as _check
 __all__ = [
     "F32", "BF16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "dtype_code", "torch_dtype", "contract", "conv2d_nhwc",
     "linear", "preprocess", "fuse_compound", "weight_search_confusion", "softmax7", "window_to_frame_mean", "gather_rows", "maxpool3x3s2",
-    "stem_pool", "subsample_rows", "avgpool", "small_linear", "lstm_cell", "split_bf16x3", "sinc_resample_bank", "pcm16_to_mono", "audio_normalize_windows", "w2v_conv0_ln_gelu", "layernorm", "add_rows",
+    "stem_pool", "stem_pool_u8", "subsample_rows", "avgpool", "small_linear", "lstm_cell", "split_bf16x3", "sinc_resample_bank", "pcm16_to_mono", "audio_normalize_windows", "w2v_conv0_ln_gelu", "layernorm", "add_rows",
     "attention", "maxpool1d5_relu", "avgpool1d_relu", "cast", "sm_limit",
 ]
 
@@ -107,8 +107,11 @@ def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], 
              tap_h_in_dim4: bool = False, group_cin_shift: int = 0, residual: Optional[torch.Tensor] = None,
              res_stride: Optional[Sequence[int]] = None, act: int = ACT_NONE, res_after_act: bool = False,
              a_offset: int = 0, algo_k: Optional[int] = None, a_strip: bool = False,
-             wt_packed: Optional[torch.Tensor] = None, a_step: int = 1) -> torch.Tensor:
-    """Generic implicit GEMM (see avcer_contract in include/avcer_b200.h)."""
+             wt_packed: Optional[torch.Tensor] = None, a_step: int = 1, ln_stats: Optional[torch.Tensor] = None,
+             ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5, stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Generic implicit GEMM (see avcer_contract in include/avcer_b200.h).
+    ln_stats [rows, parts, 2] + ln_colsum [cout]: LayerNorm of the A rows folded into the epilogue (consumer side);
+    stats_out [rows, cout/32, 2]: per-row partial (sum, sum of squares) of the stored output (producer side)."""
     _cuda(a, "a")
     d = ContractDesc()
     code = dtype_code(a.dtype)
@@ -136,6 +139,13 @@ def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], 
     d.res_after_act = int(res_after_act)
     d.dtype = code
     d.out_f32 = int(code == BF16 and out.dtype == torch.float32)
+    if ln_stats is not None:
+        assert ln_stats.dtype == torch.float32 and ln_stats.is_contiguous() and ln_stats.dim() == 3 and ln_stats.shape[2] == 2
+        assert ln_stats.shape[0] == W * H * NB and ln_colsum is not None and ln_colsum.dtype == torch.float32 and ln_colsum.numel() == cout
+        d.ln_stats, d.ln_colsum, d.ln_parts, d.ln_eps = ln_stats.data_ptr(), ln_colsum.data_ptr(), ln_stats.shape[1], ln_eps
+    if stats_out is not None:
+        assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and tuple(stats_out.shape) == (W * H * NB, cout // 32, 2)
+        d.stats_out = stats_out.data_ptr()
     k_real = algo_k if algo_k is not None else taps_w * taps_h * cin
     with _Timed("contract_bf16" if code == BF16 else "contract_f32", 2.0 * W * H * NB * cout * k_real):
         _check(_lib.load().avcer_contract(ctypes.byref(d), _stream()))
@@ -189,7 +199,8 @@ def conv2d_nhwc(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor],
 
 def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, residual: Optional[torch.Tensor] = None,
            act: int = ACT_NONE, res_after_act: bool = False, out: Optional[torch.Tensor] = None,
-           out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+           out_dtype: Optional[torch.dtype] = None, ln_stats: Optional[torch.Tensor] = None,
+           ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5, stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x: [M, K] (row pitch = x.stride(0)), wt: [N, K]; returns [M, N]."""
     m, k = x.shape
     n = wt.shape[0]
@@ -201,7 +212,7 @@ def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, r
     return contract(a=x, a_dim=(k, m, 1, 1, 1), a_stride=(1, ld, big, big, big), wt=wt, bias=bias, out=out,
                     out_stride=(out.stride(0), 0, 0), W=m, H=1, NB=1, cin=k, cout=n, residual=residual,
                     res_stride=None if residual is None else (residual.stride(0), 0, 0), act=act,
-                    res_after_act=res_after_act)
+                    res_after_act=res_after_act, ln_stats=ln_stats, ln_colsum=ln_colsum, ln_eps=ln_eps, stats_out=stats_out)
 
 
 # ----------------------------------------------------------------------------------------- K1
@@ -323,6 +334,23 @@ def stem_pool(x: torch.Tensor, wt_packed: torch.Tensor, bias: torch.Tensor, out:
     assert out.stride(1) == 55 * pitch and out.stride(0) == 55 * 55 * pitch
     with _Timed("contract_bf16", 2.0 * n * 112 * 112 * 64 * 147):        # 7x7x3 real taps
         _check(_lib.load().avcer_stem_pool_ld(x.data_ptr(), wt_packed.data_ptr(), bias.data_ptr(), n, out.data_ptr(), pitch, _stream()))
+    return out
+
+
+def stem_pool_u8(crops: torch.Tensor, wt_packed: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K1 + stem + max-pool in one kernel: crops uint8 [n,224,224,3] (BGR, packed 224x224) -> [n,55,55,64] bf16, bit-identical
+    to preprocess(layout 1) + stem_pool.  `out` as in stem_pool."""
+    _cuda(crops, "crops")
+    n = crops.shape[0]
+    assert crops.dtype == torch.uint8 and crops.is_contiguous() and tuple(crops.shape[1:]) == (224, 224, 3)
+    if out is None:
+        out = torch.empty((n, 55, 55, 64), device=crops.device, dtype=torch.bfloat16)
+    pitch = out.stride(2)
+    assert out.dtype == torch.bfloat16 and tuple(out.shape) == (n, 55, 55, 64) and out.stride(3) == 1
+    assert out.stride(1) == 55 * pitch and out.stride(0) == 55 * 55 * pitch
+    # K1's algorithmic bytes are part of this launch; the tensor work is the stem's (7x7x3 real taps)
+    with _Timed("contract_bf16", 2.0 * n * 112 * 112 * 64 * 147):
+        _check(_lib.load().avcer_stem_pool_u8(crops.data_ptr(), wt_packed.data_ptr(), bias.data_ptr(), n, out.data_ptr(), pitch, _stream()))
     return out
 
 

@@ -156,6 +156,11 @@ class Engine:
         self._vs_sms, self._a_sms = vs_sms, a_sms
         self._a_stream = torch.cuda.Stream(device=self.device) if overlap else None
         self._vs_graph = GraphedForward(lambda x: self.vs.forward(x), vs_sms) if self.vs is not None else None
+        # K1 fused into the stem (packed 224x224 crops, bf16): the stem kernel reads the uint8 crops where they lie (one
+        # eager launch, its input address changes per batch); layer1 .. fc2 replay as a graph on the persistent stem output
+        self.fuse_k1 = True
+        self._vs_body_graph = GraphedForward(lambda c: self.vs.body(c), vs_sms) if self.vs is not None else None
+        self._vs_cat: Optional[torch.Tensor] = None
         self._a_graph = GraphedForward(lambda x: self.a.forward(x), a_sms) if self.a is not None else None
         # the VD recurrence (~45 launches) is replayed as one graph per (features buffer, window count)
         self._vd_graph = GraphedForward(lambda f, w: self.vd.forward(f, w), vs_sms) if self.vd is not None else None
@@ -190,6 +195,27 @@ class Engine:
                             torch.empty((n, 512), device=self.device, dtype=torch.float32))
         return self._vs_out[0][:n], self._vs_out[1][:n]
 
+    def _vs_fwd_u8(self, crops: torch.Tensor, consumed: Optional[torch.cuda.Event] = None):
+        """crops: device uint8 [n,224,224,3] -> (probs, feats) of one batch.  `consumed` is recorded as soon as the last
+        kernel that reads `crops` has been enqueued (the staging buffer may be refilled from then on)."""
+        n = crops.shape[0]
+        if self.fuse_k1 and self.vs.k1_fused:
+            if self._vs_cat is None or self._vs_cat.shape[0] < n:
+                self._vs_cat = torch.empty((max(n, self.vs_batch), 55, 55, 128), device=self.device, dtype=self.vs.dtype)
+            cat = self._vs_cat[:n]
+            with ops.sm_limit(self._vs_sms):
+                self.vs.stem_u8(crops, cat)
+                if consumed is not None:
+                    consumed.record(torch.cuda.current_stream())
+                if self.use_graphs and ops.PROFILE is None:
+                    return self._vs_body_graph(cat)
+                return self.vs.body(cat)
+        x = self._vs_input(n)
+        ops.preprocess(crops, n, x, self.vs.input_layout)
+        if consumed is not None:
+            consumed.record(torch.cuda.current_stream())
+        return self._vs_fwd(x)
+
     def _a_fwd(self, x: torch.Tensor):
         if self.use_graphs and ops.PROFILE is None:
             return self._a_graph(x)
@@ -207,9 +233,7 @@ class Engine:
         n = crops_u8.shape[0]
         probs, feats = self._vs_outputs(n)
         for s, e in balanced_batches(n, self.vs_batch):
-            x = self._vs_input(e - s)
-            ops.preprocess(crops_u8[s:e], e - s, x, self.vs.input_layout)
-            p, f = self._vs_fwd(x)
+            p, f = self._vs_fwd_u8(crops_u8[s:e])
             probs[s:e].copy_(p)
             feats[s:e].copy_(f)
         return probs, feats
@@ -247,10 +271,7 @@ class Engine:
                 issue_copy(i + 1)
             k = i & 1
             cur.wait_event(self._ready[k])
-            x = self._vs_input(e0 - s0)
-            ops.preprocess(self._stage[k][: e0 - s0], e0 - s0, x, self.vs.input_layout)
-            self._free[k].record(cur)
-            p, f = self._vs_fwd(x)
+            p, f = self._vs_fwd_u8(self._stage[k][: e0 - s0], consumed=self._free[k])
             probs[s0:e0].copy_(p)
             feats[s0:e0].copy_(f)
         return probs, feats

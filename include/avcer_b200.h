@@ -110,6 +110,20 @@ typedef struct {
                               * FULL-resolution input (c, w_in, h_in, n, 1) and output pixel (w, h) reads input pixel
                               * (s*w + off_w + tap_w, s*h + off_h + tap_h): the TMA box walks the input with traversal
                               * stride s (a 3x3 "same" conv evaluated only at every s-th pixel).  0 / 1: unit step. */
+  /* bf16 path only -- LayerNorm folded around the contraction (the pre-LN encoder layers of HF wav2vec2,
+   * Wav2Vec2EncoderLayerStableLayerNorm: h += Attn(LN(h)); h += FFN(LN(h))).  The LayerNorm pass disappears:
+   *   producer  (stats_out != NULL): besides `out`, the contraction leaves per output row and per 32-column chunk the
+   *             pair (sum, sum of squares) of the values it stores: stats_out[row][cout/32][2] fp32;
+   *   consumer  (ln_stats != NULL): A holds the RAW rows; the caller folded gamma into Wt (Wt[co,k] * gamma[k]) and beta
+   *             into bias (bias[co] + sum_k Wt[co,k] * beta[k]); the epilogue computes mean_r / rstd_r of row r from
+   *             ln_stats[row][ln_parts][2] (over all K = taps * cin columns, variance + ln_eps) and stores
+   *             act(rstd_r * (acc - mean_r * ln_colsum[co]) + bias[co] (+ residual)), ln_colsum[co] = sum_k Wt[co,k].
+   * Rows are the flattened output positions (n, h, w); both sides must address the same [rows, K] matrix. */
+  const float* ln_stats;
+  const float* ln_colsum;
+  int32_t ln_parts;
+  float ln_eps;
+  float* stats_out;
 } avcer_contract_desc;
 
 int avcer_contract(const avcer_contract_desc* d, void* stream);
@@ -194,6 +208,12 @@ int avcer_stem_pool(const void* x_padded, const void* w_packed, const float* bia
  * written into the first 64 columns of a wider [n*55*55, out_pitch] matrix (used to place the block input next to
  * conv2's output so that conv3 and the projection shortcut, video.py:46-58, become one K-concatenated GEMM). */
 int avcer_stem_pool_ld(const void* x_padded, const void* w_packed, const float* bias, int n, void* out,
+                       int64_t out_pitch, void* stream);
+/* K1 + stem + pool in ONE kernel for packed 224x224 crops (resize = identity; BASELINE configs): crops uint8 [n,224,224,3]
+ * in cv2's BGR order are converted on the way into shared memory with exactly K1's arithmetic (float(px) - mean ->
+ * bf16, data/utils.py:19-39), so the 442 KB per crop of avcer_preprocess_u8 layout 1 are neither written nor re-read.
+ * Output identical to avcer_preprocess_u8(layout 1) + avcer_stem_pool_ld, bit for bit. */
+int avcer_stem_pool_u8(const uint8_t* crops, const void* w_packed, const float* bias, int n, void* out,
                        int64_t out_pitch, void* stream);
 /* Every stride-th pixel of an NHWC tensor as rows of a [n*ho*wo, y_pitch] matrix (ho = (h-1)/stride+1): the input
  * sampling of the stride-2 1x1 convolutions of layer2-4's first blocks (architectures/video.py:13-15, 141-148), done once

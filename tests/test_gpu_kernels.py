@@ -88,6 +88,38 @@ def test_attention_matches_torch(cuda_lib, heads, dh, t, dtype):
     assert (out.float() - ref).abs().max().item() < tol
 
 
+@pytest.mark.parametrize("m,n_out", [(12736, 1024), (199, 1024), (5000, 3072), (333, 4096)])
+def test_layernorm_folded_into_the_contractions(cuda_lib, m, n_out):
+    """Producer side: a residual GEMM also leaves per-row (sum, sum of squares) partials of what it stores.  Consumer side:
+    the next GEMM reads the raw rows and finishes LayerNorm in its epilogue.  Against torch: the statistics, and
+    LayerNorm -> Linear (-> GELU) on the same bf16 rows.  M covers the two-SM ring epilogue (large) and the single-CTA
+    kernels (small), N the 256-wide and 128-wide tiles."""
+    from avcer_b200 import ops
+
+    torch.manual_seed(m + n_out)
+    k = 1024
+    x = torch.randn(m, k, device=DEV).to(BF)
+    wo = (torch.randn(k, k, device=DEV) / k ** 0.5).to(BF)
+    res = (torch.randn(m, k, device=DEV) * 2 + 0.3).to(BF)
+    stats = torch.empty((m, k // 32, 2), device=DEV)
+    h = ops.linear(x, wo, None, residual=res, stats_out=stats)
+    plain = ops.linear(x, wo, None, residual=res)
+    assert torch.equal(h, plain)                                                  # the hook does not touch the output
+    hf = x.float() @ wo.float().t() + res.float()
+    s = stats.sum(1)
+    assert (s[:, 0] - hf.sum(1)).abs().max().item() < 0.05 and ((s[:, 1] - (hf * hf).sum(1)).abs() / (hf * hf).sum(1)).max().item() < 1e-3
+    gamma = 0.9 + 0.2 * torch.rand(k, device=DEV)
+    beta = 0.05 * torch.randn(k, device=DEV)
+    w = torch.randn(n_out, k, device=DEV) / k ** 0.5
+    b = 0.02 * torch.randn(n_out, device=DEV)
+    wf = (w * gamma[None, :]).to(BF)
+    got = ops.linear(h, wf, b + w @ beta, act=ops.ACT_GELU, ln_stats=stats, ln_colsum=wf.float().sum(1))
+    ref = F.gelu(F.linear(F.layer_norm(h.float(), (k,), gamma, beta, 1e-5), w, b))
+    assert (got.float() - ref).abs().max().item() < 0.06
+    two_pass = ops.linear(ops.layernorm(h, gamma, beta, 1e-5), w.to(BF), b, act=ops.ACT_GELU)
+    assert (got.float() - two_pass.float()).abs().max().item() < 0.06
+
+
 @pytest.mark.parametrize("heads,dh", [(16, 64), (32, 32)])
 @pytest.mark.parametrize("dtype", [BF, torch.float32])
 def test_attention_windows_are_isolated_from_a_nan_neighbour(cuda_lib, heads, dh, dtype):
@@ -188,3 +220,30 @@ def test_fused_stem_pool_is_bit_identical_to_two_kernels(cuda_lib, n):
     assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
     if n == 5:
         assert torch.isnan(got[2]).any() and not torch.isnan(got[[0, 1, 3, 4]]).any()
+
+
+@pytest.mark.parametrize("n", [1, 3, 37, 300])
+def test_k1_fused_into_the_stem_is_bit_identical(cuda_lib, n):
+    """avcer_stem_pool_u8 (uint8 crops converted on the way into shared memory, 16-row strip ring, three converter warps)
+    against avcer_preprocess_u8(layout 1) + avcer_stem_pool: same bf16 strips, same MMAs, same pooling -> same bits.
+    n = 300: more work units than SMs (ring wrap-around across units, accumulator / barrier phases)."""
+    from avcer_b200 import nets, ops
+    from avcer_b200 import synthetic as syn
+
+    g = torch.Generator(device=DEV).manual_seed(n)
+    crops = torch.randint(0, 256, (n, 224, 224, 3), dtype=torch.uint8, device=DEV, generator=g)
+    crops[0, :3] = 255                      # extreme values next to the zero-padded border rows
+    crops[-1, -3:] = 0
+    net = nets.VSNet(syn.make_vs_state_dict(0, "spread"), "bf16", DEV)
+    x = net.alloc_input(n)
+    ops.preprocess(crops, n, x, net.input_layout)
+    ref = ops.stem_pool(x, net.w["stem_packed"], net.w["stem"].bias)
+    got = ops.stem_pool_u8(crops, net.w["stem_packed"], net.w["stem"].bias)
+    assert torch.equal(got, ref)
+    cat = torch.zeros((n, 55, 55, 128), device=DEV, dtype=BF)
+    ops.stem_pool_u8(crops, net.w["stem_packed"], net.w["stem"].bias, out=cat[..., :64])
+    assert torch.equal(cat[..., :64], ref) and cat[..., 64:].abs().max().item() == 0
+    if n <= 37:
+        p0, f0 = net.forward(x)
+        p1, f1 = net.forward_u8(crops)
+        assert torch.equal(p0, p1) and torch.equal(f0, f1)

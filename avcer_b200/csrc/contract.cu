@@ -259,9 +259,10 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   p.ln_inv_k = 1.0f / (float)((long long)d->taps_w * d->taps_h * d->cin);
   p.ln_eps = d->ln_eps;
   p.stats_out = d->stats_out;
-  AVCER_REQUIRE(d->ln_stats == nullptr || (d->ln_colsum != nullptr && d->ln_parts > 0 && d->ln_parts <= 64 && !d->out_f32 &&
-                                           (reinterpret_cast<uintptr_t>(d->ln_stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(d->ln_colsum) & 15) == 0),
-                "contract(bf16): folded LayerNorm needs ln_colsum, 1..64 parts, 8/16-byte aligned tables and a bf16 output");
+  AVCER_REQUIRE(d->ln_stats == nullptr || (d->ln_colsum != nullptr && d->bias != nullptr && d->ln_parts >= 2 && d->ln_parts <= 64 &&
+                                           d->ln_parts % 2 == 0 && !d->out_f32 && (reinterpret_cast<uintptr_t>(d->ln_stats) & 15) == 0 &&
+                                           (reinterpret_cast<uintptr_t>(d->ln_colsum) & 15) == 0),
+                "contract(bf16): folded LayerNorm needs ln_colsum, a bias, an even number (2..64) of parts, 16-byte aligned tables and a bf16 output");
   AVCER_REQUIRE(d->stats_out == nullptr || (!d->out_f32 && d->cout % 32 == 0 && (reinterpret_cast<uintptr_t>(d->stats_out) & 7) == 0),
                 "contract(bf16): stats_out needs a bf16 output with cout %% 32 == 0");
   if (p.num_tiles == 0) return 0;

@@ -333,46 +333,76 @@ stem_pool_u8_kernel(const uint8_t* __restrict__ crops, const StemPoolParams p) {
       bulk_load_1d(b_base, p.w_packed, Cfg::B_BYTES, bfull_bar);
     }
     const float m0 = 91.4953f, m1 = 103.8827f, m2 = 131.0912f;  // data/utils.py:27-29 (B, G, R)
-    long long g = 0;                                             // running ring-row counter across units
-    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-      int n, j0, rows;
-      unit_geom(unit, n, j0, rows);
-      const int p0 = 4 * j0;                                     // first padded row of the unit (stem row 2*j0)
-      const int np = 4 * rows + 7;                               // padded rows 4*j0 .. 4*(j0+rows)+6
-      const uint8_t* img = crops + (size_t)n * (224 * 224 * 3);
-      for (int i = 0; i < np; ++i, ++g) {
-        if ((int)(g % Cfg::CONV_WARPS) != cw) continue;
-        const int slot = (int)(g % Cfg::RING_ROWS);
-        const uint32_t use = (uint32_t)(g / Cfg::RING_ROWS);
-        mbar_wait(empty_bar(slot), (use & 1u) ^ 1u);
-        const int y = p0 + i - 2;                                // image row of padded row p0 + i
-        const uint32_t dst = a_base + slot * Cfg::STRIP + 2 * 8; // pixel 2 of the strip (8 bytes per NHWC4 pixel)
-        if (lane < 14) {
-          if (y >= 0 && y < 224) {
-            const uint4* src = reinterpret_cast<const uint4*>(img + (size_t)y * 672) + lane * 3;
-            const uint4 r0 = __ldg(src), r1 = __ldg(src + 1), r2 = __ldg(src + 2);
-            const uint32_t wd[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
-            // byte b of the 48 (compile-time index after unrolling: one extract per byte, everything stays in registers)
-            auto px = [&](int b) { return (float)((wd[b >> 2] >> ((b & 3) * 8)) & 0xffu); };
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {                        // two pixels per 16-byte store
-              uint4 u;
-              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-              h2[0] = __floats2bfloat162_rn(px(q * 6 + 0) - m0, px(q * 6 + 1) - m1);
-              h2[1] = __floats2bfloat162_rn(px(q * 6 + 2) - m2, 0.f);
-              h2[2] = __floats2bfloat162_rn(px(q * 6 + 3) - m0, px(q * 6 + 4) - m1);
-              h2[3] = __floats2bfloat162_rn(px(q * 6 + 5) - m2, 0.f);
-              st_shared_v4(dst + (lane * 8 + q) * 16, u);
-            }
-          } else {                                               // TF-"same" padding rows above / below the image
-#pragma unroll
-            for (int q = 0; q < 8; ++q) st_shared_v4(dst + (lane * 8 + q) * 16, make_uint4(0u, 0u, 0u, 0u));
-          }
-          fence_proxy_async();                                   // generic-proxy stores -> visible to the UMMA reads
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar(slot));
+    // Iterator over the ring rows this warp owns (g = cw, cw + 3, ...): unit -> (crop, first padded row, row count).
+    // The raw bytes of the NEXT owned row are requested before this row's slot is waited for, so the global-load
+    // latency hides behind the wait for the MMAs to release the slot.
+    struct RowIt {
+      int unit, i, np, p0, n;
+      long long g;
+    };
+    auto it_load = [&](RowIt& it) {                              // geometry of it.unit (if any)
+      if (it.unit < p.units) {
+        int j0, rows;
+        unit_geom(it.unit, it.n, j0, rows);
+        it.p0 = 4 * j0;                                          // first padded row of the unit (stem row 2*j0)
+        it.np = 4 * rows + 7;                                    // padded rows 4*j0 .. 4*(j0+rows)+6
       }
+    };
+    auto it_advance = [&](RowIt& it, int steps) {                // move `steps` ring rows forward
+      it.g += steps;
+      it.i += steps;
+      while (it.unit < p.units && it.i >= it.np) {
+        it.i -= it.np;
+        it.unit += gridDim.x;
+        it_load(it);
+      }
+    };
+    auto fetch = [&](const RowIt& it, uint4 (&raw)[3], bool& real) {
+      const int y = it.p0 + it.i - 2;                            // image row of padded row p0 + i
+      real = it.unit < p.units && y >= 0 && y < 224;
+      if (real && lane < 14) {
+        const uint4* src = reinterpret_cast<const uint4*>(crops + (size_t)it.n * (224 * 224 * 3) + (size_t)y * 672) + lane * 3;
+        raw[0] = __ldg(src); raw[1] = __ldg(src + 1); raw[2] = __ldg(src + 2);
+      }
+    };
+    RowIt it{(int)blockIdx.x, 0, 0, 0, 0, 0};
+    it_load(it);
+    it_advance(it, cw);
+    uint4 nxt[3] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+    bool nxt_real = false;
+    fetch(it, nxt, nxt_real);
+    while (it.unit < p.units) {
+      const uint4 r0 = nxt[0], r1 = nxt[1], r2 = nxt[2];
+      const bool real = nxt_real;
+      const int slot = (int)(it.g % Cfg::RING_ROWS);
+      const uint32_t use = (uint32_t)(it.g / Cfg::RING_ROWS);
+      it_advance(it, Cfg::CONV_WARPS);
+      fetch(it, nxt, nxt_real);                                  // next owned row: in flight during the wait below
+      mbar_wait(empty_bar(slot), (use & 1u) ^ 1u);
+      const uint32_t dst = a_base + slot * Cfg::STRIP + 2 * 8;   // pixel 2 of the strip (8 bytes per NHWC4 pixel)
+      if (lane < 14) {
+        if (real) {
+          const uint32_t wd[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+          // byte b of the 48 (compile-time index after unrolling: one extract per byte, everything stays in registers)
+          auto px = [&](int b) { return (float)((wd[b >> 2] >> ((b & 3) * 8)) & 0xffu); };
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {                          // two pixels per 16-byte store
+            uint4 u;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+            h2[0] = __floats2bfloat162_rn(px(q * 6 + 0) - m0, px(q * 6 + 1) - m1);
+            h2[1] = __floats2bfloat162_rn(px(q * 6 + 2) - m2, 0.f);
+            h2[2] = __floats2bfloat162_rn(px(q * 6 + 3) - m0, px(q * 6 + 4) - m1);
+            h2[3] = __floats2bfloat162_rn(px(q * 6 + 5) - m2, 0.f);
+            st_shared_v4(dst + (lane * 8 + q) * 16, u);
+          }
+        } else {                                                 // TF-"same" padding rows above / below the image
+#pragma unroll
+          for (int q = 0; q < 8; ++q) st_shared_v4(dst + (lane * 8 + q) * 16, make_uint4(0u, 0u, 0u, 0u));
+        }
+        fence_proxy_async();                                     // generic-proxy stores -> visible to the UMMA reads
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(slot));
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer: 14 x (128 x 64 x 16) per stem row

@@ -235,23 +235,29 @@ def test_run_clips_baseline_config1_exact(cuda_lib):
     exists = np.ones(n, bool)
     crops = syn.make_crops(700, n)
     wav = syn.make_wav(701, L)
-    sds = (syn.make_vs_state_dict(0, "mid"), syn.make_vd_state_dict(1, "mid"), syn.make_audio_state_dict(2, 8, "mid", 12))
     w1, w2 = gwm.class_weights(gwm.weights_3), [1, 1, 1]
-    ref, o_stat, o_dyn, o_wl = _oracle_labels(crops, exists, fps, wav, sds, w1, w2, False, True, 0.5, "mean", 8)
-    assert np.isnan(o_wl[-1]).all() and not np.isnan(o_wl[:-1]).any()
-    for prec, bar, tol in (("fp32", 1.0, 1e-5), ("bf16", 0.995, 2e-3)):
-        eng = Engine(*sds, precision=prec, device="cuda:0")
-        out = eng.run_clips(torch.from_numpy(crops), [exists], [fps], torch.from_numpy(wav), [L], w1, w2, False, True)
-        got = out["labels"].cpu().numpy()
-        assert got.shape == (4, n)
-        agree = (got == ref).mean(axis=1)
-        assert agree.min() >= bar, (prec, agree)
-        wl = out["window_logits"].cpu().numpy()
-        assert wl.shape == (21, 8) and np.isnan(wl[-1]).all() and not np.isnan(wl[:-1]).any()
-        assert not torch.isnan(out["audio_mean"]).any()
-        assert np.abs(out["stat"].cpu().numpy() - o_stat).max() < tol
-        assert np.abs(of.softmax(out["dyn"].cpu().numpy()) - of.softmax(o_dyn.astype(np.float32))).max() < tol
-        assert np.abs(of.softmax(wl[:-1, :7]) - of.softmax(o_wl[:-1, :7])).max() < tol
+    # "mid" init: the per-frame tables against the north-star tolerances (2e-3 bf16 / 1e-5 fp32).  "spread" init: the
+    # compound labels -- Rule 1 masks at 1/7, and the "mid" probabilities (1/7 +- 0.07) sit on that threshold by
+    # construction, which makes their arg-max a coin toss for any two implementations that differ in the last bits.
+    for init, check_tables in (("mid", True), ("spread", False)):
+        sds = (syn.make_vs_state_dict(0, init), syn.make_vd_state_dict(1, init), syn.make_audio_state_dict(2, 8, init, 12))
+        ref, o_stat, o_dyn, o_wl = _oracle_labels(crops, exists, fps, wav, sds, w1, w2, False, True, 0.5, "mean", 8)
+        assert np.isnan(o_wl[-1]).all() and not np.isnan(o_wl[:-1]).any()
+        for prec, bar, tol in (("fp32", 1.0, 1e-5), ("bf16", 0.995, 2e-3)):
+            eng = Engine(*sds, precision=prec, device="cuda:0")
+            out = eng.run_clips(torch.from_numpy(crops), [exists], [fps], torch.from_numpy(wav), [L], w1, w2, False, True)
+            got = out["labels"].cpu().numpy()
+            assert got.shape == (4, n)
+            wl = out["window_logits"].cpu().numpy()
+            assert wl.shape == (21, 8) and np.isnan(wl[-1]).all() and not np.isnan(wl[:-1]).any()
+            assert not torch.isnan(out["audio_mean"]).any()
+            if check_tables:
+                assert np.abs(out["stat"].cpu().numpy() - o_stat).max() < tol
+                assert np.abs(of.softmax(out["dyn"].cpu().numpy()) - of.softmax(o_dyn.astype(np.float32))).max() < tol
+                assert np.abs(of.softmax(wl[:-1, :7]) - of.softmax(o_wl[:-1, :7])).max() < tol
+            if not check_tables or prec == "fp32":
+                agree = (got == ref).mean(axis=1)
+                assert agree.min() >= bar, (init, prec, agree)
 
 
 def test_run_clips_config4_seven_class_repeat_variant(cuda_lib):

@@ -52,11 +52,6 @@ class ContractDesc(ctypes.Structure):
         ("dtype", c_int32),
         ("out_f32", c_int32),
         ("a_step", c_int32),
-        ("ln_stats", c_void_p),
-        ("ln_colsum", c_void_p),
-        ("ln_parts", c_int32),
-        ("ln_eps", c_float),
-        ("stats_out", c_void_p),
     ]
 
 
@@ -89,6 +84,7 @@ _SIGNATURES = {
     "avcer_avgpool": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "avcer_small_linear": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "avcer_lstm_cell": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "avcer_gru_cell": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "avcer_split_bf16x3": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int64, c_void_p]),
     "avcer_pcm16_resample": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
     "avcer_audio_normalize_windows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

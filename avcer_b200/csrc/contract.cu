@@ -139,7 +139,6 @@ static int conv3x3_tc(const avcer_contract_desc* d, cudaStream_t st) {
   const int C = d->cin, W = d->W, H = d->H, NB = d->NB, Cout = d->cout;
   const bool shape = on != 0 && d->taps_w == 3 && d->taps_h == 3 && d->off_w == -1 && d->off_h == -1 && !d->tap_h_in_dim4 &&
                      d->group_cin_shift == 0 && !d->a_strip && d->a_step <= 1 && !d->out_f32 && d->residual == nullptr && C % 64 == 0 &&
-                     d->ln_stats == nullptr && d->stats_out == nullptr &&
                      ((Cout == 64 && C == 64) || Cout == 128) && W + 2 >= 28 && W + 2 <= 63 && NB >= 1 &&
                      (d->act == ACT_NONE || d->act == ACT_RELU);
   const bool dense = d->a_dim[0] == C && d->a_dim[1] == W && d->a_dim[2] == H && d->a_dim[3] == NB && d->a_stride[0] == 1 &&
@@ -253,18 +252,6 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   p.act = d->act;
   p.res_after_act = d->res_after_act;
   p.trace = g_trace;
-  p.ln_stats = d->ln_stats;
-  p.ln_colsum = d->ln_colsum;
-  p.ln_parts = d->ln_parts;
-  p.ln_inv_k = 1.0f / (float)((long long)d->taps_w * d->taps_h * d->cin);
-  p.ln_eps = d->ln_eps;
-  p.stats_out = d->stats_out;
-  AVCER_REQUIRE(d->ln_stats == nullptr || (d->ln_colsum != nullptr && d->bias != nullptr && d->ln_parts >= 2 && d->ln_parts <= 64 &&
-                                           d->ln_parts % 2 == 0 && !d->out_f32 && (reinterpret_cast<uintptr_t>(d->ln_stats) & 15) == 0 &&
-                                           (reinterpret_cast<uintptr_t>(d->ln_colsum) & 15) == 0),
-                "contract(bf16): folded LayerNorm needs ln_colsum, a bias, an even number (2..64) of parts, 16-byte aligned tables and a bf16 output");
-  AVCER_REQUIRE(d->stats_out == nullptr || (!d->out_f32 && d->cout % 32 == 0 && (reinterpret_cast<uintptr_t>(d->stats_out) & 7) == 0),
-                "contract(bf16): stats_out needs a bf16 output with cout %% 32 == 0");
   if (p.num_tiles == 0) return 0;
 
   const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -301,7 +288,6 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   // It trades two pipeline stages for per-warp staging slabs: only for short K loops, whose tiles are epilogue-bound
   // (deep K loops are MMA-bound and want the stages: measured +30 % time on K >= 1024 GEMMs with residual).
   const bool flat = flat_env != 0 && use_cta2 && BN == 256 && d->H == 1 && d->NB == 1 && p.bw == 128 && p.bh == 1 && p.bn == 1 &&
-                    d->ln_stats == nullptr && d->stats_out == nullptr &&      // the LayerNorm hooks live in the ring epilogues
                     (long long)d->taps_w * d->taps_h * p.kchunks <= (flat_env > 1 ? 1 << 30 : 8);
   if (mode != OUT_DIRECT_F32) {
     const int64_t ext[3] = {d->W, d->H, d->NB};
@@ -585,7 +571,6 @@ __global__ void __launch_bounds__(256) simt_contract_kernel(const SimtParams p) 
 
 static int contract_simt(const avcer_contract_desc* d, cudaStream_t st) {
   AVCER_REQUIRE(d->a_step <= 1, "contract(fp32): a_step is a bf16-path feature");
-  AVCER_REQUIRE(d->ln_stats == nullptr && d->stats_out == nullptr, "contract(fp32): the folded LayerNorm is a bf16-path feature");
   SimtParams p{};
   p.a = static_cast<const float*>(d->a);
   for (int i = 0; i < 5; ++i) { p.a_dim[i] = d->a_dim[i]; p.a_stride[i] = d->a_stride[i]; }

@@ -182,6 +182,35 @@ __global__ void lstm_cell_kernel(const float* __restrict__ xproj, const int* __r
   }
 }
 
+// ------------------------------------------------------------------ GRU cell (PyTorch gate order r,z,n; ExprModelV1, audio_8_cl.py:23-29,63)
+// xg: rows [*, 3H] fp32 = W_ih x_t + b_ih (row r of this step at xg + (x_row0 + r * x_row_stride) * 3H);
+// hg: [n, 3H] fp32 = W_hh h_{t-1} + b_hh.   n_t = tanh(xg_n + r * hg_n);  h_t = (1 - z) * n_t + z * h_{t-1}.
+template <typename T>
+__global__ void gru_cell_kernel(const float* __restrict__ xg, long long x_row0, long long x_row_stride,
+                                const float* __restrict__ hg, float* __restrict__ h_state, T* __restrict__ h_out, long long ldh,
+                                int split, T* __restrict__ y, long long y_row0, long long y_row_stride, long long n, int hidden) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * hidden) return;
+  const long long r = i / hidden;
+  const int j = (int)(i % hidden);
+  const float* xr = xg + (x_row0 + r * x_row_stride) * 3 * hidden;
+  const float* hr = hg + r * 3 * hidden;
+  const float rg = sigmoid_f(xr[j] + hr[j]);
+  const float zg = sigmoid_f(xr[hidden + j] + hr[hidden + j]);
+  const float ng = tanhf(xr[2 * hidden + j] + rg * hr[2 * hidden + j]);
+  const float hv = (1.0f - zg) * ng + zg * h_state[i];
+  h_state[i] = hv;
+  const T hi = from_f32<T>(hv);
+  h_out[r * ldh + j] = hi;
+  if (split) {                                     // bf16x3 operand of the next recurrent GEMM (see lstm_cell_kernel)
+    h_out[r * ldh + hidden + j] = from_f32<T>(hv - to_f32(hi));
+    h_out[r * ldh + 2 * hidden + j] = hi;
+  }
+  if (y) y[(y_row0 + r * y_row_stride) * hidden + j] = hi;
+}
+
 // x fp32 [rows, k] -> bf16 [rows, 3k] = [hi | lo | hi] (bf16x3 split operand, see lstm_cell_kernel)
 __global__ void split_bf16x3_kernel(const float* __restrict__ x, long long rows, int k, long long ldx,
                                     __nv_bfloat16* __restrict__ out, long long ldo) {
@@ -573,6 +602,20 @@ extern "C" int avcer_lstm_cell(const float* xproj, const int32_t* xidx, const fl
   AVCER_DISPATCH(dtype, (launch_pdl(lstm_cell_kernel<T>, blocks_for(total, 256), 256, 0, as_stream(stream), 
                             xproj, xidx, hproj, c, (T*)h_out, ldh, n, hidden, first, split, h_f32)));
   return check_launch("lstm_cell");
+}
+
+extern "C" int avcer_gru_cell(const float* xg, int64_t x_row0, int64_t x_row_stride, const float* hg, float* h_state, void* h_out,
+                              int64_t ldh, int split, void* y, int64_t y_row0, int64_t y_row_stride, int64_t n, int hidden, int dtype,
+                              void* stream) {
+  AVCER_REQUIRE(hidden > 0 && ldh >= (split ? 3 : 1) * (int64_t)hidden, "gru_cell: bad shape");
+  AVCER_REQUIRE(!split || dtype == AVCER_BF16, "gru_cell: the [hi | lo | hi] split output is a bf16 feature");
+  AVCER_REQUIRE(xg != nullptr && hg != nullptr && h_state != nullptr && h_out != nullptr, "gru_cell: null pointer");
+  const long long total = n * hidden;
+  if (total == 0) return 0;
+  AVCER_DISPATCH(dtype, (launch_pdl(gru_cell_kernel<T>, blocks_for(total, 256), 256, 0, as_stream(stream), xg, (long long)x_row0,
+                                    (long long)x_row_stride, hg, h_state, (T*)h_out, (long long)ldh, split, (T*)y, (long long)y_row0,
+                                    (long long)y_row_stride, (long long)n, hidden)));
+  return check_launch("gru_cell");
 }
 
 extern "C" int avcer_split_bf16x3(const float* x, int64_t rows, int k, int64_t ldx, void* out, int64_t ldo, void* stream) {

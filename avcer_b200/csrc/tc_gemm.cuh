@@ -54,70 +54,7 @@ struct TcGemmParams {
   int act;
   int res_after_act;     // 0: act(acc + bias + res)   1: act(acc + bias) + res
   unsigned long long* trace;   // development aid (avcer_debug_set_trace): per-tile clock64 stamps of the first CTAs, else nullptr
-  // ---- LayerNorm folded around the contraction (wav2vec2 pre-LN encoder, HF Wav2Vec2EncoderLayerStableLayerNorm)
-  // consumer: the A rows are the RAW residual stream; gamma is folded into the weights, beta into the bias, and the
-  //   epilogue finishes the normalisation per output row:  out = act(rstd_r * (acc - mean_r * colsum[co]) + bias[co] ...)
-  //   with mean_r / rstd_r from the partial (sum, sum of squares) pairs the producing GEMM left in ln_stats.
-  const float* ln_stats;       // [rows][ln_parts][2] or nullptr
-  const float* ln_colsum;      // [Cout]: sum over k of the (gamma-folded, bf16-rounded) weights
-  int ln_parts;
-  float ln_inv_k, ln_eps;
-  // producer: per output row and 32-column chunk, (sum, sum of squares) of the values this contraction stores
-  float* stats_out;            // [rows][Cout / 32][2] or nullptr
 };
-
-// Flattened output row (n, h, w) of accumulator row r of a tile, or -1 outside the tensor (partial boxes, phantom tiles)
-__device__ __forceinline__ long long tile_row_index(const TcGemmParams& p, int r, int w0, int h0, int n0) {
-  const int dw = r % p.bw, dh = (r / p.bw) % p.bh, dn = r / (p.bw * p.bh);
-  const int w = w0 + dw, h = h0 + dh, n = n0 + dn;
-  if (dn >= p.bn || w >= p.W || h >= p.H || n >= p.NB) return -1;
-  return ((long long)n * p.H + h) * p.W + w;
-}
-// mean / rstd of the row from the producer's partial sums (one pass: E[x^2] - mean^2 in fp32 over <= 64 partials).
-// Returns (rstd, -rstd * mean): the epilogue then needs one FMA per value more than a plain bias add.
-__device__ __forceinline__ void ln_row_scalars(const TcGemmParams& p, long long row, float& rstd, float& nrm) {
-  rstd = 1.f;
-  nrm = 0.f;
-  if (p.ln_stats == nullptr || row < 0) return;
-  const float4* st = reinterpret_cast<const float4*>(p.ln_stats) + row * (p.ln_parts >> 1);   // two (sum, sumsq) pairs per load
-  float s1 = 0.f, s2 = 0.f;
-  for (int i = 0; i < (p.ln_parts >> 1); ++i) {
-    const float4 v = __ldg(st + i);
-    s1 += v.x + v.z;
-    s2 += v.y + v.w;
-  }
-  const float mean = s1 * p.ln_inv_k;
-  rstd = rsqrtf(fmaxf(s2 * p.ln_inv_k - mean * mean, 0.f) + p.ln_eps);
-  nrm = -rstd * mean;
-}
-// f = rstd * acc + (bias - rstd * mean * colsum): LayerNorm finished and bias added with two FMAs per value
-__device__ __forceinline__ void ln_apply32(const TcGemmParams& p, float (&f)[32], int co, float rstd, float nrm) {
-#pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float4 c = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + co + j));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co + j));
-    f[j] = fmaf(rstd, f[j], fmaf(nrm, c.x, b.x));
-    f[j + 1] = fmaf(rstd, f[j + 1], fmaf(nrm, c.y, b.y));
-    f[j + 2] = fmaf(rstd, f[j + 2], fmaf(nrm, c.z, b.z));
-    f[j + 3] = fmaf(rstd, f[j + 3], fmaf(nrm, c.w, b.w));
-  }
-}
-__device__ __forceinline__ void stats_store32(const TcGemmParams& p, const float (&f)[32], long long row, int co) {
-  if (p.stats_out == nullptr || row < 0 || co >= p.Cout) return;
-  // packed fp32x2 accumulation: 16 adds + 16 FMAs for 32 values
-  uint64_t s1 = pack_f32x2(f[0], f[1]);
-  uint64_t s2 = mul_f32x2(s1, s1);
-#pragma unroll
-  for (int j = 2; j < 32; j += 2) {
-    const uint64_t v = pack_f32x2(f[j], f[j + 1]);
-    s1 = fma_f32x2(v, pack_f32x2(1.0f, 1.0f), s1);
-    s2 = fma_f32x2(v, v, s2);
-  }
-  float a0, a1, b0, b1;
-  unpack_f32x2(s1, a0, a1);
-  unpack_f32x2(s2, b0, b1);
-  reinterpret_cast<float2*>(p.stats_out)[row * (p.Cout >> 5) + (co >> 5)] = make_float2(a0 + a1, b0 + b1);
-}
 
 constexpr int kTraceCtas = 4, kTraceTiles = 64, kTraceSlots = 16;
 __device__ __forceinline__ void trace_stamp(const TcGemmParams& p, int local_tile, int slot) {
@@ -325,12 +262,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int w0 = (mt % p.tw) * p.bw;
       const int h0 = ((mt / p.tw) % p.th) * p.bh;
       const int n0 = (mt / (p.tw * p.th)) * p.bn;
-      long long grow = -1;
-      float ln_rstd = 1.f, ln_nrm = 0.f;
-      if (p.ln_stats != nullptr || p.stats_out != nullptr) {
-        grow = (r < rows) ? tile_row_index(p, r, w0, h0, n0) : -1;
-        ln_row_scalars(p, grow, ln_rstd, ln_nrm);            // overlaps the wait for the accumulator
-      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
 
@@ -341,9 +272,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int co = nt * BN + c * 32;
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.ln_stats != nullptr) {
-          if (co < p.Cout) ln_apply32(p, f, co, ln_rstd, ln_nrm);
-        } else if (p.bias != nullptr && co < p.Cout) {
+        if (p.bias != nullptr && co < p.Cout) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co + j));
@@ -418,7 +347,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
               apply_act(f);
             }
-            stats_store32(p, f, grow, nt * BN + (2 * hf + sub) * 32);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 u;

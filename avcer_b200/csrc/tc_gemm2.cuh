@@ -412,12 +412,6 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int nt, w0, h0, n0;
       tile_coords(pt, nt, w0, h0, n0);
       if (store_thread) trace_stamp(p, local, 6);
-      long long grow = -1;
-      float ln_rstd = 1.f, ln_nrm = 0.f;
-      if (p.ln_stats != nullptr || p.stats_out != nullptr) {
-        grow = (r < rows) ? tile_row_index(p, r, w0, h0, n0) : -1;
-        ln_row_scalars(p, grow, ln_rstd, ln_nrm);            // overlaps the wait for the accumulator
-      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (store_thread) trace_stamp(p, local, 7);
@@ -437,9 +431,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.ln_stats != nullptr) {
-          if (co < p.Cout) ln_apply32(p, f, co, ln_rstd, ln_nrm);
-        } else if (p.bias != nullptr && co < p.Cout) {
+        if (p.bias != nullptr && co < p.Cout) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co + j));
@@ -478,7 +470,6 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         } else {
           apply_act();
         }
-        stats_store32(p, f, grow, co);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint4 u;

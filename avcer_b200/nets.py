@@ -291,7 +291,6 @@ class ANet:
         self.device = torch.device(device)
         self.w = weights.pack_audio(state_dict, self.device, self.dtype)
         self.num_classes = self.w["num_classes"]
-        self.fold_ln = True             # bf16: the 24 encoder LayerNorm passes folded into the GEMMs around them (False: explicit passes)
 
     def _conv1d_s2(self, x: torch.Tensor, t_in: int, k: int, wt, bias) -> torch.Tensor:
         """[B, t_in, 512] -> [B, t_out, 512], stride 2, no padding: the k taps of one output step are
@@ -311,18 +310,6 @@ class ANet:
         f = ops.layernorm(h, *L["ln2"], 1e-5)
         f = ops.linear(f, L["w1"], L["b1"], act=ops.ACT_GELU)
         return ops.linear(f, L["w2"], L["b2"], residual=h)
-
-    def _encoder_layer_folded(self, h: torch.Tensor, st_in: torch.Tensor, st_mid: torch.Tensor, st_out: Optional[torch.Tensor],
-                              L: dict, b: int, t: int) -> torch.Tensor:
-        """The same layer without LayerNorm passes (bf16): both LayerNorms are folded into the GEMM that consumes them
-        (gamma / beta in the packed weights, mean / rstd applied per row in the epilogue), and the row statistics of the
-        residual stream are a by-product of the GEMM that produced it (avcer_contract ln_stats / stats_out).
-        st_in: statistics of h; st_mid / st_out: buffers for the statistics of the two new residual-stream values."""
-        qkv = ops.linear(h, L["wqkv_ln"], L["bqkv_ln"], ln_stats=st_in, ln_colsum=L["cs_qkv"])
-        att = ops.attention(qkv, b, t, 16, 64, 0.125)
-        h = ops.linear(att, L["wo"], L["bo"], residual=h, stats_out=st_mid)
-        f = ops.linear(h, L["w1_ln"], L["b1_ln"], act=ops.ACT_GELU, ln_stats=st_mid, ln_colsum=L["cs_w1"])
-        return ops.linear(f, L["w2"], L["b2"], residual=h, stats_out=st_out)
 
     def _transformer_layer(self, h: torch.Tensor, T: dict, b: int, t: int) -> torch.Tensor:
         heads = T["heads"]
@@ -362,27 +349,16 @@ class ANet:
             taps["proj"] = h
         # grouped positional conv (k=128, pad 64, 16 groups), last frame dropped, GELU, added to h
         h2 = torch.empty_like(h)
-        fold = self.fold_ln and self.dtype == torch.bfloat16 and len(w["layers"]) > 0
-        # row statistics (sum, sum of squares per 32-column chunk) of the residual stream: two alternating buffers for the
-        # layer inputs, one for the mid-layer value; the positional-conv contraction produces the first set
-        st = [torch.empty((b * t, 32, 2), device=self.device, dtype=torch.float32) for _ in range(3)] if fold else None
         ops.contract(a=h, a_dim=(1024, t, 1, b, 1), a_stride=(1, 1024, _BIG, t * 1024, _BIG), wt=w["pos_w"], bias=w["pos_b"],
                      out=h2, out_stride=(1024, 0, t * 1024), W=t, H=1, NB=b, cin=64, cout=1024, taps_w=128, off_w=-64,
-                     group_cin_shift=64, residual=h, act=ops.ACT_GELU, res_after_act=True, stats_out=st[0] if fold else None)
+                     group_cin_shift=64, residual=h, act=ops.ACT_GELU, res_after_act=True)
         h = h2
         if taps is not None:
             taps["posconv"] = h
-        if fold:
-            n_layers = len(w["layers"])
-            for li, L in enumerate(w["layers"]):
-                h = self._encoder_layer_folded(h, st[li & 1], st[2], st[(li + 1) & 1] if li + 1 < n_layers else None, L, b, t)
-                if taps is not None:
-                    taps[f"layer{li}"] = h
-        else:
-            for li, L in enumerate(w["layers"]):
-                h = self._encoder_layer(h, L, b, t)
-                if taps is not None:
-                    taps[f"layer{li}"] = h
+        for li, L in enumerate(w["layers"]):
+            h = self._encoder_layer(h, L, b, t)
+            if taps is not None:
+                taps[f"layer{li}"] = h
         h = ops.layernorm(h, *w["enc_ln"], 1e-5)
         if taps is not None:
             taps["w2v"] = h

@@ -19,7 +19,7 @@ from ._lib import check as _check
 __all__ = [
     "F32", "BF16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "dtype_code", "torch_dtype", "contract", "conv2d_nhwc",
     "linear", "preprocess", "fuse_compound", "weight_search_confusion", "softmax7", "window_to_frame_mean", "gather_rows", "maxpool3x3s2",
-    "stem_pool", "stem_pool_u8", "subsample_rows", "avgpool", "small_linear", "lstm_cell", "split_bf16x3", "sinc_resample_bank", "pcm16_to_mono", "audio_normalize_windows", "w2v_conv0_ln_gelu", "layernorm", "add_rows",
+    "stem_pool", "stem_pool_u8", "subsample_rows", "avgpool", "small_linear", "lstm_cell", "gru_cell", "split_bf16x3", "sinc_resample_bank", "pcm16_to_mono", "audio_normalize_windows", "w2v_conv0_ln_gelu", "layernorm", "add_rows",
     "attention", "maxpool1d5_relu", "avgpool1d_relu", "cast", "sm_limit",
 ]
 
@@ -107,11 +107,8 @@ def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], 
              tap_h_in_dim4: bool = False, group_cin_shift: int = 0, residual: Optional[torch.Tensor] = None,
              res_stride: Optional[Sequence[int]] = None, act: int = ACT_NONE, res_after_act: bool = False,
              a_offset: int = 0, algo_k: Optional[int] = None, a_strip: bool = False,
-             wt_packed: Optional[torch.Tensor] = None, a_step: int = 1, ln_stats: Optional[torch.Tensor] = None,
-             ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5, stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Generic implicit GEMM (see avcer_contract in include/avcer_b200.h).
-    ln_stats [rows, parts, 2] + ln_colsum [cout]: LayerNorm of the A rows folded into the epilogue (consumer side);
-    stats_out [rows, cout/32, 2]: per-row partial (sum, sum of squares) of the stored output (producer side)."""
+             wt_packed: Optional[torch.Tensor] = None, a_step: int = 1) -> torch.Tensor:
+    """Generic implicit GEMM (see avcer_contract in include/avcer_b200.h)."""
     _cuda(a, "a")
     d = ContractDesc()
     code = dtype_code(a.dtype)
@@ -139,13 +136,6 @@ def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], 
     d.res_after_act = int(res_after_act)
     d.dtype = code
     d.out_f32 = int(code == BF16 and out.dtype == torch.float32)
-    if ln_stats is not None:
-        assert ln_stats.dtype == torch.float32 and ln_stats.is_contiguous() and ln_stats.dim() == 3 and ln_stats.shape[2] == 2
-        assert ln_stats.shape[0] == W * H * NB and ln_colsum is not None and ln_colsum.dtype == torch.float32 and ln_colsum.numel() == cout
-        d.ln_stats, d.ln_colsum, d.ln_parts, d.ln_eps = ln_stats.data_ptr(), ln_colsum.data_ptr(), ln_stats.shape[1], ln_eps
-    if stats_out is not None:
-        assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and tuple(stats_out.shape) == (W * H * NB, cout // 32, 2)
-        d.stats_out = stats_out.data_ptr()
     k_real = algo_k if algo_k is not None else taps_w * taps_h * cin
     with _Timed("contract_bf16" if code == BF16 else "contract_f32", 2.0 * W * H * NB * cout * k_real):
         _check(_lib.load().avcer_contract(ctypes.byref(d), _stream()))
@@ -199,8 +189,7 @@ def conv2d_nhwc(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor],
 
 def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, residual: Optional[torch.Tensor] = None,
            act: int = ACT_NONE, res_after_act: bool = False, out: Optional[torch.Tensor] = None,
-           out_dtype: Optional[torch.dtype] = None, ln_stats: Optional[torch.Tensor] = None,
-           ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5, stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+           out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """x: [M, K] (row pitch = x.stride(0)), wt: [N, K]; returns [M, N]."""
     m, k = x.shape
     n = wt.shape[0]
@@ -212,7 +201,7 @@ def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, r
     return contract(a=x, a_dim=(k, m, 1, 1, 1), a_stride=(1, ld, big, big, big), wt=wt, bias=bias, out=out,
                     out_stride=(out.stride(0), 0, 0), W=m, H=1, NB=1, cin=k, cout=n, residual=residual,
                     res_stride=None if residual is None else (residual.stride(0), 0, 0), act=act,
-                    res_after_act=res_after_act, ln_stats=ln_stats, ln_colsum=ln_colsum, ln_eps=ln_eps, stats_out=stats_out)
+                    res_after_act=res_after_act)
 
 
 # ----------------------------------------------------------------------------------------- K1
@@ -396,6 +385,17 @@ def lstm_cell(xproj: Optional[torch.Tensor], xidx: Optional[torch.Tensor], hproj
     check(_lib.load().avcer_lstm_cell(_ptr(xproj), _ptr(xidx), _ptr(hproj), c.data_ptr(), h_out.data_ptr(),
                                       h_out.stride(0), n, hidden, int(first), int(split), _ptr(h_f32), dtype_code(h_out.dtype),
                                       _stream()))
+
+
+def gru_cell(xg: torch.Tensor, x_row0: int, x_row_stride: int, hg: torch.Tensor, h_state: torch.Tensor, h_out: torch.Tensor,
+             hidden: int, split: bool = False, y: Optional[torch.Tensor] = None, y_row0: int = 0, y_row_stride: int = 1) -> None:
+    """One GRU time step for n = h_state.shape[0] sequences (see avcer_gru_cell)."""
+    n = h_state.shape[0]
+    assert xg.dtype == torch.float32 and hg.dtype == torch.float32 and h_state.dtype == torch.float32
+    assert xg.is_contiguous() and hg.is_contiguous() and h_state.is_contiguous() and (y is None or y.is_contiguous())
+    check(_lib.load().avcer_gru_cell(xg.data_ptr(), x_row0, x_row_stride, hg.data_ptr(), h_state.data_ptr(), h_out.data_ptr(),
+                                     h_out.stride(0), int(split), _ptr(y), y_row0, y_row_stride, n, hidden, dtype_code(h_out.dtype),
+                                     _stream()))
 
 
 def split_bf16x3(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -137,9 +137,10 @@ def _positional_encoding(d_model: int = 1024, max_len: int = 5000) -> torch.Tens
 
 
 def make_audio_state_dict(seed: int = 2, num_classes: int = 8, init: str = "spread",
-                          num_layers: int = 12) -> "OrderedDict[str, torch.Tensor]":
+                          num_layers: int = 12, variant: str = "v3") -> "OrderedDict[str, torch.Tensor]":
     """ExprModelV3 / ExprModelV2 (audio_8_cl.py:131-161, audio_7_cl.py:75-128): wav2vec2-large-robust
-    (12 layers, stable layer norm) + tl1 + tl2 + time_downsample + feature_downsample."""
+    (12 layers, stable layer norm) + tl1 + tl2 + time_downsample + feature_downsample.
+    variant="v1": ExprModelV1 (audio_8_cl.py:18-72): the same wav2vec2 + a 2-layer GRU(1024 -> 256) + a 256-wide head."""
     g = _gen(seed)
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     spread = init != "default"
@@ -184,8 +185,13 @@ def make_audio_state_dict(seed: int = 2, num_classes: int = 8, init: str = "spre
         lin(p + ".feed_forward.intermediate_dense", 4096, 1024)
         lin(p + ".feed_forward.output_dense", 1024, 4096, std=(0.5 / math.sqrt(4096)) if spread else None)
         ln(p + ".final_layer_norm", 1024)
+    if variant == "v1":
+        for layer, cin in ((0, 1024), (1, 256)):
+            k = (2.0 if spread else 1.0) / math.sqrt(256)            # PyTorch: U(-1/sqrt(H), 1/sqrt(H))
+            for nm, shape in (("weight_ih", (768, cin)), ("weight_hh", (768, 256)), ("bias_ih", (768,)), ("bias_hh", (768,))):
+                sd[f"gru.{nm}_l{layer}"] = (torch.rand(shape, generator=g) * 2 - 1) * k
     pe = _positional_encoding()
-    for t in ("tl1", "tl2"):
+    for t in (() if variant == "v1" else ("tl1", "tl2")):
         for nm in ("query_w", "keys_w", "values_w", "ff_layer_after_concat"):
             lin(f"{t}.self_attention.{nm}", 1024, 1024, bias=False)
         lin(f"{t}.feed_forward.layer_1", 1024, 1024)
@@ -208,13 +214,14 @@ def make_audio_state_dict(seed: int = 2, num_classes: int = 8, init: str = "spre
             sd[prefix + ".running_var"] = torch.ones(c)
         sd[prefix + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
 
-    sd["time_downsample.0.weight"] = torch.randn((1024, 1024, 5), generator=g) * math.sqrt(1.0 / (1024 * 5))
-    sd["time_downsample.0.bias"] = 0.02 * torch.randn(1024, generator=g)
-    bn1d("time_downsample.1", 1024)
-    sd["time_downsample.4.weight"] = torch.randn((1024, 1024, 3), generator=g) * math.sqrt(2.0 / (1024 * 3))
-    sd["time_downsample.4.bias"] = 0.02 * torch.randn(1024, generator=g)
-    bn1d("time_downsample.5", 1024)
-    lin("feature_downsample", num_classes, 1024, std=(3.0 / math.sqrt(1024)) if spread else None)
+    fs = 256 if variant == "v1" else 1024                              # f_size (audio_8_cl.py:33 / :146)
+    sd["time_downsample.0.weight"] = torch.randn((fs, fs, 5), generator=g) * math.sqrt(1.0 / (fs * 5))
+    sd["time_downsample.0.bias"] = 0.02 * torch.randn(fs, generator=g)
+    bn1d("time_downsample.1", fs)
+    sd["time_downsample.4.weight"] = torch.randn((fs, fs, 3), generator=g) * math.sqrt(2.0 / (fs * 3))
+    sd["time_downsample.4.bias"] = 0.02 * torch.randn(fs, generator=g)
+    bn1d("time_downsample.5", fs)
+    lin("feature_downsample", num_classes, fs, std=(3.0 / math.sqrt(fs)) if spread else None)
     if init == "mid":
         sd["feature_downsample.weight"] *= MID_HEAD_SCALE
     return sd

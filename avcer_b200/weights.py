@@ -157,25 +157,12 @@ def pack_audio(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
     w = pos_conv_effective_weight(sd, p + "encoder.pos_conv_embed.conv")    # [1024, 64, 128]
     out["pos_w"] = dev(_tap_major(w))                                       # [1024, 128*64]
     out["pos_b"] = dev(sd[p + "encoder.pos_conv_embed.conv.bias"], f32)
-    def fold_ln(w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
-        """LayerNorm folded into the Linear that consumes it (avcer_contract ln_stats / ln_colsum):
-        W (gamma * xhat + beta) + b = (W * gamma) xhat + (b + W beta).  Returns the storage-dtype weights, the fp32 bias and
-        the column sums of the weights AS STORED (the epilogue subtracts mean * colsum from an accumulator built from them)."""
-        wf = (w.double() * gamma.double()[None, :]).float().to(dtype)
-        bf = (b.double() + w.double() @ beta.double()).float()
-        return dev(wf), dev(bf, f32), dev(wf.float().sum(dim=1), f32)
-
     layers = []
     i = 0
     while f"{p}encoder.layers.{i}.layer_norm.weight" in sd:
         q = f"{p}encoder.layers.{i}."
-        wqkv = torch.cat([sd[q + "attention.q_proj.weight"], sd[q + "attention.k_proj.weight"], sd[q + "attention.v_proj.weight"]], 0)
-        bqkv = torch.cat([sd[q + "attention.q_proj.bias"], sd[q + "attention.k_proj.bias"], sd[q + "attention.v_proj.bias"]], 0)
-        wqkv_ln, bqkv_ln, cs_qkv = fold_ln(wqkv, bqkv, sd[q + "layer_norm.weight"], sd[q + "layer_norm.bias"])
-        w1_ln, b1_ln, cs_w1 = fold_ln(sd[q + "feed_forward.intermediate_dense.weight"], sd[q + "feed_forward.intermediate_dense.bias"],
-                                      sd[q + "final_layer_norm.weight"], sd[q + "final_layer_norm.bias"])
         layers.append({
-            "wqkv_ln": wqkv_ln, "bqkv_ln": bqkv_ln, "cs_qkv": cs_qkv, "w1_ln": w1_ln, "b1_ln": b1_ln, "cs_w1": cs_w1,
+
             "ln1": (dev(sd[q + "layer_norm.weight"], f32), dev(sd[q + "layer_norm.bias"], f32)),
             "wqkv": dev(torch.cat([sd[q + "attention.q_proj.weight"], sd[q + "attention.k_proj.weight"], sd[q + "attention.v_proj.weight"]], 0)),
             "bqkv": dev(torch.cat([sd[q + "attention.q_proj.bias"], sd[q + "attention.k_proj.bias"], sd[q + "attention.v_proj.bias"]], 0), f32),

@@ -110,20 +110,6 @@ typedef struct {
                               * FULL-resolution input (c, w_in, h_in, n, 1) and output pixel (w, h) reads input pixel
                               * (s*w + off_w + tap_w, s*h + off_h + tap_h): the TMA box walks the input with traversal
                               * stride s (a 3x3 "same" conv evaluated only at every s-th pixel).  0 / 1: unit step. */
-  /* bf16 path only -- LayerNorm folded around the contraction (the pre-LN encoder layers of HF wav2vec2,
-   * Wav2Vec2EncoderLayerStableLayerNorm: h += Attn(LN(h)); h += FFN(LN(h))).  The LayerNorm pass disappears:
-   *   producer  (stats_out != NULL): besides `out`, the contraction leaves per output row and per 32-column chunk the
-   *             pair (sum, sum of squares) of the values it stores: stats_out[row][cout/32][2] fp32;
-   *   consumer  (ln_stats != NULL): A holds the RAW rows; the caller folded gamma into Wt (Wt[co,k] * gamma[k]) and beta
-   *             into bias (bias[co] + sum_k Wt[co,k] * beta[k]); the epilogue computes mean_r / rstd_r of row r from
-   *             ln_stats[row][ln_parts][2] (over all K = taps * cin columns, variance + ln_eps) and stores
-   *             act(rstd_r * (acc - mean_r * ln_colsum[co]) + bias[co] (+ residual)), ln_colsum[co] = sum_k Wt[co,k].
-   * Rows are the flattened output positions (n, h, w); both sides must address the same [rows, K] matrix. */
-  const float* ln_stats;
-  const float* ln_colsum;
-  int32_t ln_parts;
-  float ln_eps;
-  float* stats_out;
 } avcer_contract_desc;
 
 int avcer_contract(const avcer_contract_desc* d, void* stream);
@@ -240,6 +226,14 @@ int avcer_small_linear(const void* x, int64_t n, int k, int64_t ldx, const float
 int avcer_lstm_cell(const float* xproj, const int32_t* xidx, const float* hproj, float* c,
                     void* h_out, int64_t ldh, int64_t n, int hidden, int first, int split, float* h_f32,
                     int dtype, void* stream);
+/* GRU cell pointwise step (PyTorch gate order r,z,n): the recurrent layers of ExprModelV1 (architectures/audio_8_cl.py:23-29,
+ * forward :63).  xg: [*, 3H] fp32 input projections W_ih x + b_ih of ALL time steps, the row of sequence r at this step is
+ * x_row0 + r * x_row_stride; hg: [n, 3H] fp32 = W_hh h_{t-1} + b_hh; h_state [n, H] fp32 is updated in place;
+ * h_out (dtype, row pitch ldh) feeds the next recurrent GEMM (split != 0: bf16x3 operand [hi | lo | hi], as avcer_lstm_cell);
+ * y (optional, dtype, [*, H]) receives h_t at row y_row0 + r * y_row_stride (the layer's output sequence). */
+int avcer_gru_cell(const float* xg, int64_t x_row0, int64_t x_row_stride, const float* hg, float* h_state,
+                   void* h_out, int64_t ldh, int split, void* y, int64_t y_row0, int64_t y_row_stride,
+                   int64_t n, int hidden, int dtype, void* stream);
 /* x fp32 [rows, k] (row pitch ldx) -> bf16 [rows, 3k] (row pitch ldo) = [hi | lo | hi]: the bf16x3 split of the
  * relu(fc1) features feeding the LSTM input projection (get_prob_video.py:115-122). */
 int avcer_split_bf16x3(const float* x, int64_t rows, int k, int64_t ldx, void* out, int64_t ldo, void* stream);

@@ -151,16 +151,45 @@ def _bn1d(x, sd, p):
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"], training=False, eps=1e-5)
 
 
+def gru_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, layers: int = 2) -> torch.Tensor:
+    """nn.GRU(1024 -> 256, 2 layers, batch_first) from zero state, eval mode (inter-layer dropout inactive); PyTorch gate
+    order r, z, n (architectures/audio_8_cl.py:23-29):  n = tanh(W_in x + b_in + r * (W_hn h + b_hn))."""
+    for layer in range(layers):
+        w_ih, w_hh = sd[f"gru.weight_ih_l{layer}"], sd[f"gru.weight_hh_l{layer}"]
+        b_ih, b_hh = sd[f"gru.bias_ih_l{layer}"], sd[f"gru.bias_hh_l{layer}"]
+        hid = w_hh.shape[1]
+        h = x.new_zeros(x.shape[0], hid)
+        outs = []
+        for t in range(x.shape[1]):
+            gi = x[:, t] @ w_ih.t() + b_ih
+            gh = h @ w_hh.t() + b_hh
+            i_r, i_z, i_n = gi.split(hid, dim=1)
+            h_r, h_z, h_n = gh.split(hid, dim=1)
+            r = torch.sigmoid(i_r + h_r)
+            z = torch.sigmoid(i_z + h_z)
+            n = torch.tanh(i_n + r * h_n)
+            h = (1 - z) * n + z * h
+            outs.append(h)
+        x = torch.stack(outs, dim=1)
+    return x
+
+
 def audio_model_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, taps=None) -> torch.Tensor:
-    """ExprModelV3 / ExprModelV2 forward (audio_8_cl.py:179-190): x [B,64000] -> logits [B, 8 or 7]."""
+    """ExprModelV3 / ExprModelV2 forward (audio_8_cl.py:179-190): x [B,64000] -> logits [B, 8 or 7].
+    A state_dict with `gru.*` keys is ExprModelV1 (audio_8_cl.py:18-72): wav2vec2 -> 2-layer GRU -> the same head at 256."""
     with torch.no_grad():
         h = wav2vec2_forward(sd, x, taps)
         if taps is not None:
             taps["w2v"] = h
-        h = transformer_layer(sd, h, "tl1", 32)
-        h = transformer_layer(sd, h, "tl2", 16)
-        if taps is not None:
-            taps["tl2"] = h
+        if "gru.weight_ih_l0" in sd:
+            h = gru_forward(sd, h)
+            if taps is not None:
+                taps["gru"] = h
+        else:
+            h = transformer_layer(sd, h, "tl1", 32)
+            h = transformer_layer(sd, h, "tl2", 16)
+            if taps is not None:
+                taps["tl2"] = h
         h = h.permute(0, 2, 1)
         h = F.conv1d(h, sd["time_downsample.0.weight"], sd["time_downsample.0.bias"], stride=3, dilation=2)
         h = F.relu(F.max_pool1d(_bn1d(h, sd, "time_downsample.1"), 5))

@@ -118,7 +118,9 @@ def reference_lstm(sd_vd):
 
 
 def reference_audio_model(sd_a, num_classes: int = 8, num_hidden_layers: int = 12):
-    if num_classes == 8:
+    if "gru.weight_ih_l0" in sd_a:
+        from architectures.audio_8_cl import ExprModelV1 as cls          # the GRU variant (audio_8_cl.py:18-72)
+    elif num_classes == 8:
         from architectures.audio_8_cl import ExprModelV3 as cls
     else:
         from architectures.audio_7_cl import ExprModelV2 as cls

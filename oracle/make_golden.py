@@ -231,6 +231,13 @@ def make_audio():
         ref = model(torch.from_numpy(xs)).numpy()
     assert np.abs(oa.audio_model_forward(sd, torch.from_numpy(xs)).numpy() - ref).max() < 2e-5
     out["a8_mid_window_logits"] = ref
+    # ExprModelV1 (the GRU variant of audio_8_cl.py:18-72), first three windows
+    sd = syn.make_audio_state_dict(2, 8, "mid", 12, variant="v1")
+    model = harness.reference_audio_model(sd, 8, 12)
+    with torch.no_grad():
+        ref = model(torch.from_numpy(xs[:3])).numpy()
+    assert np.abs(oa.audio_model_forward(sd, torch.from_numpy(xs[:3])).numpy() - ref).max() < 2e-5
+    out["a8_v1_window_logits"] = ref
     np.savez_compressed(os.path.join(OUT, "audio.npz"), **out)
     print("audio.npz")
 

@@ -52,29 +52,17 @@ for n in (256, 750):
 
 a = nets.ANet(syn.make_audio_state_dict(2, 8, "spread", 12), "bf16", DEV)
 xa = torch.randn((64, 64000), device=DEV, generator=gen)
-for fold in (True, False):
-    a.fold_ln = fold
-    print(f"A forward, 64 windows, fold_ln={fold}: {timed(lambda: a.forward(xa)):.3f} ms")
-
-# the four encoder GEMMs with / without the LayerNorm hooks (M = 64 windows x 199 tokens)
+print(f"A forward, 64 windows: {timed(lambda: a.forward(xa)):.3f} ms")
 m, k = 64 * 199, 1024
 bf = torch.bfloat16
 h = torch.randn(m, k, device=DEV).to(bf)
-st = torch.empty((m, 32, 2), device=DEV)
 for name, n_out, kk, act, res in (("qkv", 3072, 1024, ops.ACT_NONE, False), ("ffn1", 4096, 1024, ops.ACT_GELU, False),
                                   ("o-proj", 1024, 1024, ops.ACT_NONE, True), ("ffn2", 1024, 4096, ops.ACT_NONE, True)):
     x = torch.randn(m, kk, device=DEV).to(bf)
     w = (torch.randn(n_out, kk, device=DEV) / kk ** 0.5).to(bf)
     b = torch.zeros(n_out, device=DEV)
-    cs = w.float().sum(1)
     r = h if res else None
-    t_plain = timed(lambda: ops.linear(x, w, b, act=act, residual=r))
-    if res:
-        t_hook = timed(lambda: ops.linear(x, w, b, act=act, residual=r, stats_out=st))
-    else:
-        ops.linear(h, (torch.randn(k, k, device=DEV) / 32).to(bf), None, residual=h, stats_out=st)
-        t_hook = timed(lambda: ops.linear(x, w, b, act=act, ln_stats=st, ln_colsum=cs))
-    print(f"GEMM {name:7s} M={m} N={n_out} K={kk}: plain {t_plain * 1e3:.1f} us, with LN hook {t_hook * 1e3:.1f} us")
+    print(f"GEMM {name:7s} M={m} N={n_out} K={kk}: {timed(lambda: ops.linear(x, w, b, act=act, residual=r)) * 1e3:.1f} us")
 xl = torch.randn(m, k, device=DEV).to(bf)
 g1, b1 = torch.ones(k, device=DEV), torch.zeros(k, device=DEV)
 print(f"layernorm kernel [M,1024]: {timed(lambda: ops.layernorm(xl, g1, b1, 1e-5)) * 1e3:.1f} us")

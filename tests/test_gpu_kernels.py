@@ -88,38 +88,6 @@ def test_attention_matches_torch(cuda_lib, heads, dh, t, dtype):
     assert (out.float() - ref).abs().max().item() < tol
 
 
-@pytest.mark.parametrize("m,n_out", [(12736, 1024), (199, 1024), (5000, 3072), (333, 4096)])
-def test_layernorm_folded_into_the_contractions(cuda_lib, m, n_out):
-    """Producer side: a residual GEMM also leaves per-row (sum, sum of squares) partials of what it stores.  Consumer side:
-    the next GEMM reads the raw rows and finishes LayerNorm in its epilogue.  Against torch: the statistics, and
-    LayerNorm -> Linear (-> GELU) on the same bf16 rows.  M covers the two-SM ring epilogue (large) and the single-CTA
-    kernels (small), N the 256-wide and 128-wide tiles."""
-    from avcer_b200 import ops
-
-    torch.manual_seed(m + n_out)
-    k = 1024
-    x = torch.randn(m, k, device=DEV).to(BF)
-    wo = (torch.randn(k, k, device=DEV) / k ** 0.5).to(BF)
-    res = (torch.randn(m, k, device=DEV) * 2 + 0.3).to(BF)
-    stats = torch.empty((m, k // 32, 2), device=DEV)
-    h = ops.linear(x, wo, None, residual=res, stats_out=stats)
-    plain = ops.linear(x, wo, None, residual=res)
-    assert torch.equal(h, plain)                                                  # the hook does not touch the output
-    hf = x.float() @ wo.float().t() + res.float()
-    s = stats.sum(1)
-    assert (s[:, 0] - hf.sum(1)).abs().max().item() < 0.05 and ((s[:, 1] - (hf * hf).sum(1)).abs() / (hf * hf).sum(1)).max().item() < 1e-3
-    gamma = 0.9 + 0.2 * torch.rand(k, device=DEV)
-    beta = 0.05 * torch.randn(k, device=DEV)
-    w = torch.randn(n_out, k, device=DEV) / k ** 0.5
-    b = 0.02 * torch.randn(n_out, device=DEV)
-    wf = (w * gamma[None, :]).to(BF)
-    got = ops.linear(h, wf, b + w @ beta, act=ops.ACT_GELU, ln_stats=stats, ln_colsum=wf.float().sum(1))
-    ref = F.gelu(F.linear(F.layer_norm(h.float(), (k,), gamma, beta, 1e-5), w, b))
-    assert (got.float() - ref).abs().max().item() < 0.06
-    two_pass = ops.linear(ops.layernorm(h, gamma, beta, 1e-5), w.to(BF), b, act=ops.ACT_GELU)
-    assert (got.float() - two_pass.float()).abs().max().item() < 0.06
-
-
 @pytest.mark.parametrize("heads,dh", [(16, 64), (32, 32)])
 @pytest.mark.parametrize("dtype", [BF, torch.float32])
 def test_attention_windows_are_isolated_from_a_nan_neighbour(cuda_lib, heads, dh, dtype):

@@ -129,26 +129,6 @@ def test_audio_pack_accepts_every_weight_norm_spelling():
         weights.pack_audio(bad, "cpu", torch.float32)
 
 
-def test_folded_layernorm_weights_reproduce_ln_then_linear():
-    """weights.pack_audio's gamma / beta folding (the GEMM epilogue computes rstd * (x W'^T - mean * colsum) + b'):
-    against LayerNorm followed by the Linear, in fp32 on the CPU."""
-    sd = syn.make_audio_state_dict(2, 8, "spread", 1)
-    w = weights.pack_audio(sd, "cpu", torch.float32)["layers"][0]
-    q = "wav2vec2.encoder.layers.0."
-    x = torch.randn(50, 1024) * 3 + 0.7
-    mean, var = x.mean(1, keepdim=True), x.var(1, unbiased=False, keepdim=True)
-    rstd = torch.rsqrt(var + 1e-5)
-    for wl, bl, cs, lnp, lin in ((w["wqkv_ln"], w["bqkv_ln"], w["cs_qkv"], "layer_norm", None),
-                                 (w["w1_ln"], w["b1_ln"], w["cs_w1"], "final_layer_norm", "feed_forward.intermediate_dense")):
-        got = rstd * (x @ wl.t() - mean * cs[None, :]) + bl
-        ln = F.layer_norm(x, (1024,), sd[q + lnp + ".weight"], sd[q + lnp + ".bias"], 1e-5)
-        if lin is None:
-            ref = torch.cat([F.linear(ln, sd[q + f"attention.{n}_proj.weight"], sd[q + f"attention.{n}_proj.bias"]) for n in "qkv"], 1)
-        else:
-            ref = F.linear(ln, sd[q + lin + ".weight"], sd[q + lin + ".bias"])
-        assert (got - ref).abs().max() < 2e-4
-
-
 def test_balanced_batches_cover_and_differ_by_one():
     from avcer_b200.pipeline import balanced_batches
 

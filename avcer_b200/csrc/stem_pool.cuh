@@ -252,9 +252,12 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const StemPoolParams p
 // 442 KB per crop that K1 writes and the stem re-reads never exist: the stem reads 150 KB of pixels per crop.
 //   * shared memory holds a ring of 16 padded input rows (2 KB each, the same SWIZZLE_NONE strip layout K1 produced in
 //     HBM; borders zeroed once).  Stem row r multiplies rows 2r .. 2r+6, so advancing one stem row costs two new rows.
-//   * three converter warps each own every third ring row: 14 lanes load 48 bytes (16 pixels) with three 16-byte loads,
-//     convert with exactly K1's arithmetic (float(px) - mean, __floats2bfloat162_rn: bit-identical strips) and store
-//     8 x 16 bytes; generic->async proxy fence, then one arrive on the row's `full` barrier.
+//   * one producer thread streams the image rows (672 contiguous bytes each) into a 16-slot raw ring with 1-D bulk
+//     copies, up to 16 rows ahead; two converter warps each own every second ring row: 14 lanes read 48 bytes (16
+//     pixels) from the raw slot, convert with exactly K1's arithmetic (float(px) - mean, __floats2bfloat162_rn:
+//     bit-identical strips) and store 8 x 16 bytes; generic->async proxy fence, one arrive on the row's `full` barrier.
+//     (A first version loaded from global memory inside the converter warps: one load in flight per warp made the
+//     converters latency-bound, 215 us against 164 + 33 us for K1 + stem at batch 256.)
 //   * the MMA thread waits for the two newest rows, issues the same 14 UMMAs per stem row as stem_pool_kernel and
 //     commits to the `empty` barriers of the two rows that leave the 7-row window.
 // Epilogue (bias, ReLU, 4-row ring, 3x3/2 max-pool) is shared with stem_pool_kernel: outputs are bit-identical.
@@ -265,29 +268,35 @@ struct StemPoolU8Cfg {
   static constexpr int B_BYTES = 7 * 4096;
   static constexpr int ROW = 112 * 128;
   static constexpr int RING = 4;
-  static constexpr int SMEM = A_BYTES + 1024 /*junk-row overread of the last slot*/ + B_BYTES + RING * ROW + 1024;
+  static constexpr int RAW_ROW = 704;                // one image row: 672 bytes of BGR pixels in a 704-byte slot
+  static constexpr int RAW_BYTES = RING_ROWS * RAW_ROW;
+  static constexpr int SMEM = A_BYTES + 1024 /*junk-row overread of the last slot*/ + B_BYTES + RING * ROW + RAW_BYTES + 1024;
   static constexpr int TMEM_COLS = 128;
   static constexpr int THREADS = 384;
   static constexpr int UNIT_ROWS = 14;
-  static constexpr int CONV_WARPS = 3;               // warps 0, 2, 3
+  static constexpr int CONV_WARPS = 2;               // warps 2, 3
 };
 
 __global__ void __launch_bounds__(384, 1)
 stem_pool_u8_kernel(const uint8_t* __restrict__ crops, const StemPoolParams p) {
   using Cfg = StemPoolU8Cfg;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * Cfg::RING_ROWS + 5];     // full[16] empty[16] tfull[2] tempty[2] bfull
+  // full[16] empty[16] tfull[2] tempty[2] bfull rawfull[16] rawempty[16]
+  __shared__ __align__(8) uint64_t bars[4 * Cfg::RING_ROWS + 5];
   __shared__ uint32_t tmem_slot_s;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + Cfg::A_BYTES + 1024;
   const uint32_t ring_base = b_base + Cfg::B_BYTES;
+  const uint32_t raw_base = ring_base + Cfg::RING * Cfg::ROW;
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::RING_ROWS + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::RING_ROWS + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::RING_ROWS + 2 + a); };
   const uint32_t bfull_bar = bar_base + 8u * (2 * Cfg::RING_ROWS + 4);
+  auto rawfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::RING_ROWS + 5 + s); };
+  auto rawempty_bar = [&](int s) { return bar_base + 8u * (3 * Cfg::RING_ROWS + 5 + s); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -296,6 +305,8 @@ stem_pool_u8_kernel(const uint8_t* __restrict__ crops, const StemPoolParams p) {
     for (int s = 0; s < Cfg::RING_ROWS; ++s) {
       mbar_init(full_bar(s), 1);            // one arrive from the converter warp that owns the row
       mbar_init(empty_bar(s), 1);           // one tcgen05.commit when the row has left the 7-row window
+      mbar_init(rawfull_bar(s), 1);         // the bulk copy of the row's 672 bytes (or a plain arrive for a padding row)
+      mbar_init(rawempty_bar(s), 1);        // the converter warp has the bytes in registers
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -325,84 +336,83 @@ stem_pool_u8_kernel(const uint8_t* __restrict__ crops, const StemPoolParams p) {
     rows = (j0 + Cfg::UNIT_ROWS <= 55) ? Cfg::UNIT_ROWS : 55 - j0;
   };
 
-  if (warp == 0 || warp == 2 || warp == 3) {
-    // ------------------------------------------------------------ converters: ring row g = cw, cw + 3, ...
-    const int cw = warp == 0 ? 0 : warp - 1;
-    if (warp == 0 && lane == 0) {
+  if (warp == 0) {
+    // ------------------------------------------------------------ raw-row producer: one 672-byte bulk copy per image row,
+    // up to 16 rows ahead of the converters (global latency is hidden here, not in the converter warps)
+    if (lane == 0) {
       mbar_arrive_expect_tx(bfull_bar, Cfg::B_BYTES);           // filter bank: constant, fetched once
       bulk_load_1d(b_base, p.w_packed, Cfg::B_BYTES, bfull_bar);
-    }
-    const float m0 = 91.4953f, m1 = 103.8827f, m2 = 131.0912f;  // data/utils.py:27-29 (B, G, R)
-    // Iterator over the ring rows this warp owns (g = cw, cw + 3, ...): unit -> (crop, first padded row, row count).
-    // The raw bytes of the NEXT owned row are requested before this row's slot is waited for, so the global-load
-    // latency hides behind the wait for the MMAs to release the slot.
-    struct RowIt {
-      int unit, i, np, p0, n;
-      long long g;
-    };
-    auto it_load = [&](RowIt& it) {                              // geometry of it.unit (if any)
-      if (it.unit < p.units) {
-        int j0, rows;
-        unit_geom(it.unit, it.n, j0, rows);
-        it.p0 = 4 * j0;                                          // first padded row of the unit (stem row 2*j0)
-        it.np = 4 * rows + 7;                                    // padded rows 4*j0 .. 4*(j0+rows)+6
-      }
-    };
-    auto it_advance = [&](RowIt& it, int steps) {                // move `steps` ring rows forward
-      it.g += steps;
-      it.i += steps;
-      while (it.unit < p.units && it.i >= it.np) {
-        it.i -= it.np;
-        it.unit += gridDim.x;
-        it_load(it);
-      }
-    };
-    auto fetch = [&](const RowIt& it, uint4 (&raw)[3], bool& real) {
-      const int y = it.p0 + it.i - 2;                            // image row of padded row p0 + i
-      real = it.unit < p.units && y >= 0 && y < 224;
-      if (real && lane < 14) {
-        const uint4* src = reinterpret_cast<const uint4*>(crops + (size_t)it.n * (224 * 224 * 3) + (size_t)y * 672) + lane * 3;
-        raw[0] = __ldg(src); raw[1] = __ldg(src + 1); raw[2] = __ldg(src + 2);
-      }
-    };
-    RowIt it{(int)blockIdx.x, 0, 0, 0, 0, 0};
-    it_load(it);
-    it_advance(it, cw);
-    uint4 nxt[3] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
-    bool nxt_real = false;
-    fetch(it, nxt, nxt_real);
-    while (it.unit < p.units) {
-      const uint4 r0 = nxt[0], r1 = nxt[1], r2 = nxt[2];
-      const bool real = nxt_real;
-      const int slot = (int)(it.g % Cfg::RING_ROWS);
-      const uint32_t use = (uint32_t)(it.g / Cfg::RING_ROWS);
-      it_advance(it, Cfg::CONV_WARPS);
-      fetch(it, nxt, nxt_real);                                  // next owned row: in flight during the wait below
-      mbar_wait(empty_bar(slot), (use & 1u) ^ 1u);
-      const uint32_t dst = a_base + slot * Cfg::STRIP + 2 * 8;   // pixel 2 of the strip (8 bytes per NHWC4 pixel)
-      if (lane < 14) {
-        if (real) {
-          const uint32_t wd[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
-          // byte b of the 48 (compile-time index after unrolling: one extract per byte, everything stays in registers)
-          auto px = [&](int b) { return (float)((wd[b >> 2] >> ((b & 3) * 8)) & 0xffu); };
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {                          // two pixels per 16-byte store
-            uint4 u;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-            h2[0] = __floats2bfloat162_rn(px(q * 6 + 0) - m0, px(q * 6 + 1) - m1);
-            h2[1] = __floats2bfloat162_rn(px(q * 6 + 2) - m2, 0.f);
-            h2[2] = __floats2bfloat162_rn(px(q * 6 + 3) - m0, px(q * 6 + 4) - m1);
-            h2[3] = __floats2bfloat162_rn(px(q * 6 + 5) - m2, 0.f);
-            st_shared_v4(dst + (lane * 8 + q) * 16, u);
+      long long g = 0;
+      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        int n, j0, rows;
+        unit_geom(unit, n, j0, rows);
+        const int p0 = 4 * j0, np = 4 * rows + 7;               // padded rows 4*j0 .. 4*(j0+rows)+6 (stem rows 2*j0 ..)
+        const uint8_t* img = crops + (size_t)n * (224 * 224 * 3);
+        for (int i = 0; i < np; ++i, ++g) {
+          const int slot = (int)(g % Cfg::RING_ROWS);
+          mbar_wait(rawempty_bar(slot), ((uint32_t)(g / Cfg::RING_ROWS) & 1u) ^ 1u);
+          const int y = p0 + i - 2;                             // image row of padded row p0 + i
+          if (y >= 0 && y < 224) {
+            mbar_arrive_expect_tx(rawfull_bar(slot), 672u);
+            bulk_load_1d(raw_base + slot * Cfg::RAW_ROW, img + (size_t)y * 672, 672u, rawfull_bar(slot));
+          } else {
+            mbar_arrive(rawfull_bar(slot));                     // TF-"same" padding row: nothing to fetch
           }
-        } else {                                                 // TF-"same" padding rows above / below the image
-#pragma unroll
-          for (int q = 0; q < 8; ++q) st_shared_v4(dst + (lane * 8 + q) * 16, make_uint4(0u, 0u, 0u, 0u));
         }
-        fence_proxy_async();                                     // generic-proxy stores -> visible to the UMMA reads
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar(slot));
+    }
+  } else if (warp == 2 || warp == 3) {
+    // ------------------------------------------------------------ converters: ring row g = cw, cw + 2, ...
+    const int cw = warp - 2;
+    const float m0 = 91.4953f, m1 = 103.8827f, m2 = 131.0912f;  // data/utils.py:27-29 (B, G, R)
+    long long g = 0;
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      int n, j0, rows;
+      unit_geom(unit, n, j0, rows);
+      const int p0 = 4 * j0, np = 4 * rows + 7;
+      for (int i = 0; i < np; ++i, ++g) {
+        if ((int)(g % Cfg::CONV_WARPS) != cw) continue;
+        const int slot = (int)(g % Cfg::RING_ROWS);
+        const uint32_t use = (uint32_t)(g / Cfg::RING_ROWS);
+        const int y = p0 + i - 2;
+        const bool real = y >= 0 && y < 224;
+        mbar_wait(rawfull_bar(slot), use & 1u);
+        uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0, r2 = r0;
+        if (real && lane < 14) {
+          const uint32_t src = raw_base + slot * Cfg::RAW_ROW + lane * 48;
+          ld_shared_v4(src, r0);
+          ld_shared_v4(src + 16, r1);
+          ld_shared_v4(src + 32, r2);
+          fence_proxy_async();                                   // generic-proxy reads ordered before the bulk-copy refill (async proxy)
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rawempty_bar(slot));         // the raw slot may be refilled
+        mbar_wait(empty_bar(slot), (use & 1u) ^ 1u);
+        const uint32_t dst = a_base + slot * Cfg::STRIP + 2 * 8; // pixel 2 of the strip (8 bytes per NHWC4 pixel)
+        if (lane < 14) {
+          if (real) {
+            const uint32_t wd[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+            // byte b of the 48 (compile-time index after unrolling: one extract per byte, everything stays in registers)
+            auto px = [&](int b) { return (float)((wd[b >> 2] >> ((b & 3) * 8)) & 0xffu); };
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {                        // two pixels per 16-byte store
+              uint4 u;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+              h2[0] = __floats2bfloat162_rn(px(q * 6 + 0) - m0, px(q * 6 + 1) - m1);
+              h2[1] = __floats2bfloat162_rn(px(q * 6 + 2) - m2, 0.f);
+              h2[2] = __floats2bfloat162_rn(px(q * 6 + 3) - m0, px(q * 6 + 4) - m1);
+              h2[3] = __floats2bfloat162_rn(px(q * 6 + 5) - m2, 0.f);
+              st_shared_v4(dst + (lane * 8 + q) * 16, u);
+            }
+          } else {                                               // TF-"same" padding rows above / below the image
+#pragma unroll
+            for (int q = 0; q < 8; ++q) st_shared_v4(dst + (lane * 8 + q) * 16, make_uint4(0u, 0u, 0u, 0u));
+          }
+          fence_proxy_async();                                   // generic-proxy stores -> visible to the UMMA reads
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(slot));
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer: 14 x (128 x 64 x 16) per stem row

@@ -362,21 +362,45 @@ class ANet:
         h = ops.layernorm(h, *w["enc_ln"], 1e-5)
         if taps is not None:
             taps["w2v"] = h
-        h = self._transformer_layer(h, w["tl1"], b, t)
-        h = self._transformer_layer(h, w["tl2"], b, t)
-        if taps is not None:
-            taps["tl2"] = h
+        c = w["f_size"]
+        if w["variant"] == "v1":
+            h = self._gru(h, b, t)                       # [b*t, 256]
+            if taps is not None:
+                taps["gru"] = h
+        else:
+            h = self._transformer_layer(h, w["tl1"], b, t)
+            h = self._transformer_layer(h, w["tl2"], b, t)
+            if taps is not None:
+                taps["tl2"] = h
         # time_downsample: Conv1d(k5,s3,d2)+BN -> MaxPool1d(5) -> ReLU -> Conv1d(k3)+BN -> mean -> ReLU
         t1 = (t - 2 * 4 - 1) // 3 + 1
-        y = torch.empty((b, t1, 1024), device=self.device, dtype=self.dtype)
-        ops.contract(a=h, a_dim=(1024, t1, 1, b, 5), a_stride=(1, 3 * 1024, _BIG, t * 1024, 2 * 1024), wt=w["td0_w"],
-                     bias=w["td0_b"], out=y, out_stride=(1024, 0, t1 * 1024), W=t1, H=1, NB=b, cin=1024, cout=1024,
+        y = torch.empty((b, t1, c), device=self.device, dtype=self.dtype)
+        ops.contract(a=h, a_dim=(c, t1, 1, b, 5), a_stride=(1, 3 * c, _BIG, t * c, 2 * c), wt=w["td0_w"],
+                     bias=w["td0_b"], out=y, out_stride=(c, 0, t1 * c), W=t1, H=1, NB=b, cin=c, cout=c,
                      taps_w=1, taps_h=5, tap_h_in_dim4=True)
         y = ops.maxpool1d5_relu(y)
         t2 = y.shape[1]
         t3 = t2 - 2
-        z = torch.empty((b, t3, 1024), device=self.device, dtype=self.dtype)
-        ops.contract(a=y, a_dim=(3 * 1024, t3, 1, b, 1), a_stride=(1, 1024, _BIG, t2 * 1024, _BIG), wt=w["td4_w"],
-                     bias=w["td4_b"], out=z, out_stride=(1024, 0, t3 * 1024), W=t3, H=1, NB=b, cin=3 * 1024, cout=1024)
+        z = torch.empty((b, t3, c), device=self.device, dtype=self.dtype)
+        ops.contract(a=y, a_dim=(3 * c, t3, 1, b, 1), a_stride=(1, c, _BIG, t2 * c, _BIG), wt=w["td4_w"],
+                     bias=w["td4_b"], out=z, out_stride=(c, 0, t3 * c), W=t3, H=1, NB=b, cin=3 * c, cout=c)
         z = ops.avgpool1d_relu(z)
         return ops.small_linear(z, w["fd_w"], w["fd_b"], softmax=False)
+
+    def _gru(self, x: torch.Tensor, b: int, t: int) -> torch.Tensor:
+        """ExprModelV1's nn.GRU(1024 -> 256, 2 layers, batch_first) from zero state (audio_8_cl.py:23-29,63): per layer one
+        contraction for the input projections of all time steps, then t recurrent steps of (h W_hh^T + b_hh, gate math).
+        x: [b*t, Cin] rows in (window, time) order -> [b*t, 256]."""
+        split = self.dtype == torch.bfloat16
+        s = 3 if split else 1
+        for L in self.w["gru"]:
+            xg = ops.linear(x, L["w_ih"], L["b_ih"], out_dtype=torch.float32)                  # [b*t, 768]
+            h_state = torch.zeros((b, 256), device=self.device, dtype=torch.float32)
+            h_op = torch.zeros((b, s * 256), device=self.device, dtype=self.dtype)             # operand of the recurrent GEMM
+            hg = torch.empty((b, 768), device=self.device, dtype=torch.float32)
+            y = torch.empty((b * t, 256), device=self.device, dtype=self.dtype)
+            for step in range(t):
+                ops.linear(h_op, L["w_hh"], L["b_hh"], out=hg)
+                ops.gru_cell(xg, step, t, hg, h_state, h_op, 256, split=split, y=y, y_row0=step, y_row_stride=t)
+            x = y
+        return x

@@ -177,7 +177,15 @@ def pack_audio(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
         i += 1
     out["layers"] = layers
     out["enc_ln"] = (dev(sd[p + "encoder.layer_norm.weight"], f32), dev(sd[p + "encoder.layer_norm.bias"], f32))
-    for t, heads in (("tl1", 32), ("tl2", 16)):
+    v1 = "gru.weight_ih_l0" in sd                  # ExprModelV1 (audio_8_cl.py:18-72): 2-layer GRU instead of tl1 / tl2
+    out["variant"] = "v1" if v1 else "v3"
+    if v1:
+        # input projections are plain contractions over every time step at once; the 199-step recurrence runs bf16x3
+        # (split_bf16x3_weight) in bf16 mode, like the VD LSTM
+        rec = split_bf16x3_weight if dtype == torch.bfloat16 else (lambda w: w)
+        out["gru"] = [{"w_ih": dev(sd[f"gru.weight_ih_l{l}"]), "b_ih": dev(sd[f"gru.bias_ih_l{l}"], f32),
+                       "w_hh": dev(rec(sd[f"gru.weight_hh_l{l}"])), "b_hh": dev(sd[f"gru.bias_hh_l{l}"], f32)} for l in range(2)]
+    for t, heads in (() if v1 else (("tl1", 32), ("tl2", 16))):
         a = f"{t}.self_attention."
         out[t] = {
             "heads": heads,
@@ -196,4 +204,5 @@ def pack_audio(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
     out["fd_w"] = dev(sd["feature_downsample.weight"], f32)
     out["fd_b"] = dev(sd["feature_downsample.bias"], f32)
     out["num_classes"] = int(sd["feature_downsample.weight"].shape[0])
+    out["f_size"] = int(sd["feature_downsample.weight"].shape[1])          # 1024 (V2 / V3) or 256 (V1)
     return out

@@ -160,6 +160,26 @@ def test_audio_north_star_tolerance(cuda_lib, golden, prec, init):
         assert sure.any() and np.array_equal(p.argmax(1)[sure], pr.argmax(1)[sure])
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_audio_v1_gru_variant_matches_reference_golden(cuda_lib, golden, prec):
+    """ExprModelV1 (architectures/audio_8_cl.py:18-72: wav2vec2 -> 2-layer GRU(1024 -> 256) -> 256-wide head), the variant
+    the reference's alternate model lists use, against the unmodified reference class (tests/golden/audio.npz)."""
+    from avcer_b200 import nets, ops, pipeline
+
+    wav = syn.make_wav(31, 52800 + 123)
+    net = nets.ANet(syn.make_audio_state_dict(2, 8, "mid", 12, variant="v1"), prec, DEV)
+    assert net.w["variant"] == "v1" and net.w["f_size"] == 256
+    ap = pipeline.plan_audio(len(wav), 25, 0.5)
+    x = ops.audio_normalize_windows(torch.from_numpy(wav).to(DEV), torch.from_numpy(ap.starts[:3]).to(DEV), 64000, "mean")
+    out = net.forward(x).cpu().numpy()
+    ref = golden["audio"]["a8_v1_window_logits"]
+    assert out.shape == ref.shape == (3, 8)
+    p = torch.softmax(torch.from_numpy(out[:, :7]), 1).numpy()
+    pr = torch.softmax(torch.from_numpy(ref[:, :7]), 1).numpy()
+    assert np.abs(p - pr).max() < (1e-5 if prec == "fp32" else 2e-3), np.abs(p - pr).max()
+    assert np.abs(out - ref).max() < (1e-4 if prec == "fp32" else 0.02)
+
+
 def test_audio_padding_modes_and_nan_window(cuda_lib, golden):
     from avcer_b200 import ops, pipeline
 

@@ -93,6 +93,15 @@ def test_audio_oracle_matches_reference(golden):
     assert np.nanmax(np.abs(gm[list(range(8))].values - g["a8_a_frame_means"])) < 5e-5
 
 
+def test_audio_v1_oracle_matches_reference(golden):
+    """ExprModelV1 (GRU variant): the oracle's gru_forward restatement against the reference class's logits."""
+    wav = syn.make_wav(31, 52800 + 123)
+    sched = oa.window_schedule(len(wav), 25, 0.5)[:2]
+    xs = np.stack([oa.zero_mean_unit_var(oa.pad_window(wav[s:e], 64000, "mean")) for (s, e, _, _) in sched])
+    out = oa.audio_model_forward(syn.make_audio_state_dict(2, 8, "mid", 12, variant="v1"), torch.from_numpy(xs)).numpy()
+    assert np.abs(out - golden["audio"]["a8_v1_window_logits"][:2]).max() < 5e-5
+
+
 def test_audio_schedule_nan_window(golden):
     # L multiple of step_a: trailing empty window -> NaN logits for exactly one extra frame id (SURVEY a7)
     g = golden["audio"]

@@ -253,11 +253,9 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const StemPoolParams p
 //   * shared memory holds a ring of 16 padded input rows (2 KB each, the same SWIZZLE_NONE strip layout K1 produced in
 //     HBM; borders zeroed once).  Stem row r multiplies rows 2r .. 2r+6, so advancing one stem row costs two new rows.
 //   * one producer thread streams the image rows (672 contiguous bytes each) into a 16-slot raw ring with 1-D bulk
-//     copies, up to 16 rows ahead; two converter warps each own every second ring row: 14 lanes read 48 bytes (16
-//     pixels) from the raw slot, convert with exactly K1's arithmetic (float(px) - mean, __floats2bfloat162_rn:
-//     bit-identical strips) and store 8 x 16 bytes; generic->async proxy fence, one arrive on the row's `full` barrier.
-//     (A first version loaded from global memory inside the converter warps: one load in flight per warp made the
-//     converters latency-bound, 215 us against 164 + 33 us for K1 + stem at batch 256.)
+//     copies, up to 16 rows ahead; four converter warps take turns on the row pairs a stem row adds: 28 lanes x 4 pixel
+//     pairs per row, exactly K1's arithmetic (float(px) - mean, __floats2bfloat162_rn: bit-identical strips),
+//     conflict-free 16-byte stores, one generic->async proxy fence per pass, then one arrive per row `full` barrier.
 //   * the MMA thread waits for the two newest rows, issues the same 14 UMMAs per stem row as stem_pool_kernel and
 //     commits to the `empty` barriers of the two rows that leave the 7-row window.
 // Epilogue (bias, ReLU, 4-row ring, 3x3/2 max-pool) is shared with stem_pool_kernel: outputs are bit-identical.
@@ -272,12 +270,12 @@ struct StemPoolU8Cfg {
   static constexpr int RAW_BYTES = RING_ROWS * RAW_ROW;
   static constexpr int SMEM = A_BYTES + 1024 /*junk-row overread of the last slot*/ + B_BYTES + RING * ROW + RAW_BYTES + 1024;
   static constexpr int TMEM_COLS = 128;
-  static constexpr int THREADS = 384;
+  static constexpr int THREADS = 448;                // 12 warps of stem_pool_kernel + 2 more converter warps
   static constexpr int UNIT_ROWS = 14;
-  static constexpr int CONV_WARPS = 2;               // warps 2, 3
+  static constexpr int CONV_WARPS = 4;               // warps 2, 3, 12, 13
 };
 
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(448, 1)
 stem_pool_u8_kernel(const uint8_t* __restrict__ crops, const StemPoolParams p) {
   using Cfg = StemPoolU8Cfg;
   extern __shared__ uint8_t smem_raw[];
@@ -361,58 +359,67 @@ stem_pool_u8_kernel(const uint8_t* __restrict__ crops, const StemPoolParams p) {
         }
       }
     }
-  } else if (warp == 2 || warp == 3) {
-    // ------------------------------------------------------------ converters: ring row g = cw, cw + 2, ...
-    const int cw = warp - 2;
+  } else if (warp == 2 || warp == 3 || warp >= 12) {
+    // ------------------------------------------------------------ converters: four warps, one PASS each in turn.
+    // A pass = the two ring rows a stem row adds to the window (the first seven rows of a unit go as 2 + 2 + 2 + 1):
+    // 28 lanes x 4 pixel pairs per row, conflict-free 16-byte stores, ONE generic->async proxy fence per pass (the fence
+    // is the expensive part: per row and per lane it left the first versions at 215-240 us against 164 + 33 us).
+    const int cw = warp < 4 ? warp - 2 : warp - 10;             // 0..3
     const float m0 = 91.4953f, m1 = 103.8827f, m2 = 131.0912f;  // data/utils.py:27-29 (B, G, R)
-    long long g = 0;
+    long long g0 = 0;                                           // ring row of the unit's first padded row
+    long long pass = 0;
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
       int n, j0, rows;
       unit_geom(unit, n, j0, rows);
-      const int p0 = 4 * j0, np = 4 * rows + 7;
-      for (int i = 0; i < np; ++i, ++g) {
-        if ((int)(g % Cfg::CONV_WARPS) != cw) continue;
-        const int slot = (int)(g % Cfg::RING_ROWS);
-        const uint32_t use = (uint32_t)(g / Cfg::RING_ROWS);
-        const int y = p0 + i - 2;
-        const bool real = y >= 0 && y < 224;
-        mbar_wait(rawfull_bar(slot), use & 1u);
-        uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0, r2 = r0;
-        if (real && lane < 14) {
-          const uint32_t src = raw_base + slot * Cfg::RAW_ROW + lane * 48;
-          ld_shared_v4(src, r0);
-          ld_shared_v4(src + 16, r1);
-          ld_shared_v4(src + 32, r2);
-          fence_proxy_async();                                   // generic-proxy reads ordered before the bulk-copy refill (async proxy)
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(rawempty_bar(slot));         // the raw slot may be refilled
-        mbar_wait(empty_bar(slot), (use & 1u) ^ 1u);
-        const uint32_t dst = a_base + slot * Cfg::STRIP + 2 * 8; // pixel 2 of the strip (8 bytes per NHWC4 pixel)
-        if (lane < 14) {
-          if (real) {
-            const uint32_t wd[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
-            // byte b of the 48 (compile-time index after unrolling: one extract per byte, everything stays in registers)
-            auto px = [&](int b) { return (float)((wd[b >> 2] >> ((b & 3) * 8)) & 0xffu); };
+      const int p0 = 4 * j0;
+      const int npass = 4 + 2 * rows;
+      for (int k = 0; k < npass; ++k, ++pass) {
+        if ((int)(pass % Cfg::CONV_WARPS) != cw) continue;
+        const int i0 = k < 4 ? 2 * k : 7 + 2 * (k - 4);         // first row of the pass inside the unit
+        const int nr = k == 3 ? 1 : 2;
+        for (int rr = 0; rr < nr; ++rr) {
+          const long long g = g0 + i0 + rr;
+          const int slot = (int)(g % Cfg::RING_ROWS);
+          const uint32_t use = (uint32_t)(g / Cfg::RING_ROWS);
+          const int y = p0 + i0 + rr - 2;                       // image row of padded row p0 + i
+          const bool real = y >= 0 && y < 224;
+          mbar_wait(rawfull_bar(slot), use & 1u);
+          uint32_t px16[4][3];                                  // 4 pixel pairs x 6 bytes
+          if (real && lane < 28) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {                        // two pixels per 16-byte store
-              uint4 u;
-              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-              h2[0] = __floats2bfloat162_rn(px(q * 6 + 0) - m0, px(q * 6 + 1) - m1);
-              h2[1] = __floats2bfloat162_rn(px(q * 6 + 2) - m2, 0.f);
-              h2[2] = __floats2bfloat162_rn(px(q * 6 + 3) - m0, px(q * 6 + 4) - m1);
-              h2[3] = __floats2bfloat162_rn(px(q * 6 + 5) - m2, 0.f);
-              st_shared_v4(dst + (lane * 8 + q) * 16, u);
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t src = raw_base + slot * Cfg::RAW_ROW + (q * 28 + lane) * 6;
+#pragma unroll
+              for (int h = 0; h < 3; ++h) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(px16[q][h]) : "r"(src + 2 * h));
             }
-          } else {                                               // TF-"same" padding rows above / below the image
-#pragma unroll
-            for (int q = 0; q < 8; ++q) st_shared_v4(dst + (lane * 8 + q) * 16, make_uint4(0u, 0u, 0u, 0u));
+            fence_proxy_async();                                // generic-proxy reads ordered before the bulk-copy refill
           }
-          fence_proxy_async();                                   // generic-proxy stores -> visible to the UMMA reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(rawempty_bar(slot));       // the raw slot may be refilled
+          mbar_wait(empty_bar(slot), (use & 1u) ^ 1u);
+          const uint32_t dst = a_base + slot * Cfg::STRIP + 2 * 8;   // pixel 2 of the strip (8 bytes per NHWC4 pixel)
+          if (lane < 28) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                       // two pixels per 16-byte store
+              uint4 u = make_uint4(0u, 0u, 0u, 0u);
+              if (real) {
+                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+                const uint32_t a = px16[q][0], b = px16[q][1], c = px16[q][2];
+                h2[0] = __floats2bfloat162_rn((float)(a & 0xffu) - m0, (float)(a >> 8) - m1);
+                h2[1] = __floats2bfloat162_rn((float)(b & 0xffu) - m2, 0.f);
+                h2[2] = __floats2bfloat162_rn((float)(b >> 8) - m0, (float)(c & 0xffu) - m1);
+                h2[3] = __floats2bfloat162_rn((float)(c >> 8) - m2, 0.f);
+              }
+              st_shared_v4(dst + (q * 28 + lane) * 16, u);
+            }
+          }
         }
+        fence_proxy_async();                                    // the pass's strip stores -> visible to the UMMA reads
         __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar(slot));
+        if (lane == 0)
+          for (int rr = 0; rr < nr; ++rr) mbar_arrive(full_bar((int)((g0 + i0 + rr) % Cfg::RING_ROWS)));
       }
+      g0 += 4 * rows + 7;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer: 14 x (128 x 64 x 16) per stem row

@@ -13,6 +13,7 @@ import torch
 from . import config
 from .data.utils import convert_mp4_to_mp3
 from .pipeline import AUDIO_ORDER, plan_audio
+from .tables import AudioTable
 
 NUM_CLASSES = 8
 DEFAULT_MODEL = {"model_name": "FLW-ExprModelV3-2024.03.02-11.42.11", "model_cls": "ExprModelV3", "epoch": 63}
@@ -60,13 +61,11 @@ class EmotionRecognition:
         for s in range(0, len(plan.starts), batch):
             x = ops.audio_normalize_windows(wav_d, starts[s:s + batch], win, self.padding)
             logits.append(self.audio_model.forward(x))
-        logits = torch.cat(logits, 0).cpu().numpy()
-        counts = np.maximum(plan.f_hi - plan.f_lo, 0)
-        probs = np.repeat(logits, counts, axis=0)                              # one row per (window, covered frame)
-        framess = [str(i).zfill(6) + ".jpg" for lo, hi in zip(plan.f_lo, plan.f_hi) for i in range(int(lo), int(hi))]
+        logits = torch.cat(logits, 0)                                            # [Wn, ncls] on the device
         emo = AUDIO_ORDER[:7] if logits.shape[1] == 7 else AUDIO_ORDER
-        df = pd.DataFrame(probs, columns=emo)
-        df["frames"] = framess
+        # One row per (window, covered frame) with a `frames` string column is what the reference returns (:94-126); the
+        # façade holds the windows and their frame ranges and only builds that table if somebody looks at it (tables.py)
+        df = AudioTable(logits, plan.f_lo, plan.f_hi, emo)
         if self.flag_save_prob:
             save_path = os.path.join(self.save_path, self.model_params["model_name"])
             os.makedirs(save_path, exist_ok=True)

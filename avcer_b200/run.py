@@ -16,6 +16,7 @@ import torch
 from . import config, ops
 from .data.utils import get_image_location, save_txt  # noqa: F401  (re-exported like the reference)
 from .pipeline import AUDIO_ORDER
+from .tables import AudioTable
 
 NAME_EMO = AUDIO_ORDER                                   # run.py:56-65
 COM_EMO = {"Fearfully Surprised": [3, 6], "Happily Surprised": [4, 6], "Sadly Surprised": [5, 6],
@@ -24,9 +25,25 @@ COLUMN_NAMES = ["image_location", "Fearfully_Surprised", "Happily_Surprised", "S
                 "Angrily_Surprised", "Sadly_Fearful", "Sadly_Angry"]
 
 
-def audio_frame_rows(audio_df: pd.DataFrame, dev, dropna: bool = False):
+def audio_frame_rows(audio_df, dev, dropna: bool = False):
     """groupby("frames").mean() of the long-format audio table on the GPU.  Returns (sorted unique
-    frame ids [U], per-frame means [U, ncls] device tensor in the table's dtype, value columns)."""
+    frame ids [U], per-frame means [U, ncls] device tensor in the table's dtype, value columns).
+    audio_df: a DataFrame like the reference's (one row per (window, frame), `frames` strings), or the drivers'
+    AudioTable façade, which skips the string table altogether (avcer_b200/tables.py)."""
+    if isinstance(audio_df, AudioTable):
+        if not dropna and not audio_df.materialized:
+            # façade fast path: window logits + frame ranges -> per-frame means, no strings, no host round trip
+            logits = audio_df.window_logits
+            logits = (logits if isinstance(logits, torch.Tensor) else torch.from_numpy(np.asarray(logits))).to(dev).contiguous()
+            uniq = audio_df.frame_ids()
+            n_all = int(audio_df.f_hi.max()) if len(audio_df.f_hi) else 0
+            lo = torch.from_numpy(np.minimum(audio_df.f_lo, n_all).astype(np.int32)).to(dev)
+            hi = torch.from_numpy(np.minimum(audio_df.f_hi, n_all).astype(np.int32)).to(dev)
+            means = ops.window_to_frame_mean(logits, lo, hi, n_all)
+            if len(uniq) != n_all:
+                means = ops.gather_rows(means, torch.from_numpy(uniq.astype(np.int32)).to(dev), len(uniq))
+            return uniq, means, list(audio_df.value_columns)
+        audio_df = audio_df.materialize()            # someone edited the table, or NaN rows are to be dropped: generic path
     if dropna:
         audio_df = audio_df.dropna()
     cols = [c for c in audio_df.columns if c != "frames"]

@@ -331,3 +331,25 @@ def test_run_clips_float64_promotion_for_leading_gap(cuda_lib):
         p_a = ops.softmax7(out["audio_mean"]).cpu().numpy()
         ref = np.stack(of.fuse_labels(stat, p_vd, p_a, w1, [1, 1, 1], False, True))
         assert np.array_equal(out["labels"].cpu().numpy(), ref)
+
+
+def test_audio_table_fast_path_equals_the_string_table(cuda_lib):
+    """run.audio_frame_rows on the drivers' façade (window logits + frame ranges, no strings) against the same function on
+    the materialised long-format DataFrame (the reference's table): identical frame ids and bit-identical per-frame means,
+    including a NaN tail window and a clip whose audio is shorter than the video."""
+    from avcer_b200 import ops, run
+    from avcer_b200.pipeline import AUDIO_ORDER, plan_audio
+    from avcer_b200.tables import AudioTable
+
+    for L, fps, step in ((160000, 25, 0.5), (52923, 30, 1.0), (7000, 25, 0.5)):
+        ap = plan_audio(L, fps, step)
+        g = torch.Generator(device="cuda:0").manual_seed(L)
+        logits = torch.randn((len(ap.starts), 8), device="cuda:0", generator=g)
+        if L % int(step * 16000) == 0:
+            logits[-1] = float("nan")
+        fast = AudioTable(logits, ap.f_lo, ap.f_hi, AUDIO_ORDER)
+        slow = AudioTable(logits, ap.f_lo, ap.f_hi, AUDIO_ORDER).materialize()
+        u1, m1, c1 = run.audio_frame_rows(fast, "cuda:0")
+        u2, m2, c2 = run.audio_frame_rows(slow, "cuda:0")
+        assert not fast.materialized and c1 == c2 and np.array_equal(u1, u2)
+        assert torch.equal(torch.nan_to_num(m1, nan=-9.0), torch.nan_to_num(m2, nan=-9.0))

@@ -129,6 +129,37 @@ def test_audio_pack_accepts_every_weight_norm_spelling():
         weights.pack_audio(bad, "cpu", torch.float32)
 
 
+def test_audio_table_facade_materialises_the_reference_table():
+    """tables.AudioTable: compact (window logits + frame ranges) until somebody looks; then exactly the long-format
+    DataFrame of get_prob_audio_8_cl.py:94-126 (one row per (window, covered frame), `frames` strings, column order)."""
+    import pandas as pd
+
+    from avcer_b200.tables import AudioTable
+
+    ap = pipeline.plan_audio(52923, 25, 0.5)
+    rng = np.random.default_rng(0)
+    logits = rng.standard_normal((len(ap.starts), 8)).astype(np.float32)
+    logits[-1] = np.nan
+    cols = pipeline.AUDIO_ORDER
+    t = AudioTable(torch.from_numpy(logits), ap.f_lo, ap.f_hi, cols)
+    rows, frames = [], []
+    for (s0, e0, lo, hi), l in zip(oa.window_schedule(52923, 25, 0.5), logits):          # the reference's loop shape
+        for f in range(lo, hi):
+            rows.append(l)
+            frames.append(str(f).zfill(6) + ".jpg")
+    assert len(t) == len(rows) and not t.materialized and "compact" in repr(t)
+    assert t.frame_ids().tolist() == sorted({int(f[:-4]) for f in frames})
+    assert not t.materialized                                                             # still no string built
+    assert list(t.columns) == cols + ["frames"] and t.materialized
+    want = pd.DataFrame(np.asarray(rows), columns=cols)
+    want["frames"] = frames
+    pd.testing.assert_frame_equal(t.materialize(), want)
+    assert t["frames"].tolist() == frames and t.shape == want.shape
+    pd.testing.assert_frame_equal(t.groupby(["frames"]).mean().reset_index(), want.groupby(["frames"]).mean().reset_index())
+    t["image_location"] = 1                                                               # consumers may add columns (run.py:92)
+    assert "image_location" in t.materialize().columns
+
+
 def test_balanced_batches_cover_and_differ_by_one():
     from avcer_b200.pipeline import balanced_batches
 

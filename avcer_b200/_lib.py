@@ -95,6 +95,8 @@ _SIGNATURES = {
     "avcer_attention": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p]),
     "avcer_maxpool1d5_relu": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "avcer_avgpool1d_relu": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "avcer_jpeg_decode": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
     "avcer_cast": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
 }
 

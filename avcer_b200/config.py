@@ -16,7 +16,18 @@ PATH_STATIC = "src/weights/FER_static_ResNet50_AffectNet.pt"       # get_prob_vi
 PATH_DYNAMIC = "src/weights/FER_dinamic_LSTM_Aff-Wild2.pt"         # get_prob_video.py:51
 
 _state: Dict[str, object] = {"precision": "bf16", "device": "cuda:0", "vs": None, "vd": None, "audio": {},
-                             "engine": None, "audio_nets": {}}
+                             "engine": None, "audio_nets": {}, "jpeg": "gpu"}
+
+
+def set_jpeg_decoder(which: str) -> None:
+    """"gpu" (default): the face crops are decoded by avcer_jpeg_decode, bit-identical to cv2.imread; "cv2": decoded on the
+    host with cv2.imread like the reference (get_prob_video.py:95) -- for files outside the GPU decoder's coverage."""
+    assert which in ("gpu", "cv2")
+    _state["jpeg"] = which
+
+
+def jpeg_decoder() -> str:
+    return _state["jpeg"]
 
 
 def set_precision(precision: str) -> None:

@@ -16,29 +16,53 @@ from .pipeline import vd_step
 DICT_EMO_VIDEO = {0: "Neutral", 1: "Happiness", 2: "Sadness", 3: "Surprise", 4: "Fear", 5: "Disgust", 6: "Anger"}
 
 
-def _load_crops(path_images: str, total_frames: int):
-    """Reads face track "00" exactly as the reference does (get_prob_video.py:79,93-95): frame i is
-    present iff `00/{i:06d}.jpg` exists.  Returns (flat uint8 buffer, offsets, heights, widths, exists)."""
+def _present_frames(path_images: str, total_frames: int):
+    """Frame i is present iff `00/{i:06d}.jpg` exists (get_prob_video.py:79,93-94: only face track "00" is read)."""
     folder = os.path.join(path_images, "00")
     names = set(os.listdir(folder))
     exists = np.zeros(total_frames, dtype=bool)
-    chunks, offsets, hs, ws = [], [], [], []
-    off = 0
+    paths = []
     for i in range(total_frames):
         name = str(i).zfill(6) + ".jpg"
         if name in names:
-            img = cv2.imread(os.path.join(folder, name))           # BGR uint8, what pth_processing ends up consuming
             exists[i] = True
-            h, w, _ = img.shape
-            chunks.append(np.ascontiguousarray(img).reshape(-1))
-            offsets.append(off)
-            hs.append(h)
-            ws.append(w)
-            off += (h * w * 3 + 15) // 16 * 16                       # keep every crop 16-byte aligned
+            paths.append(os.path.join(folder, name))
+    return paths, exists
+
+
+def _load_crops_gpu(paths, device):
+    """The crops decoded ON THE GPU (avcer_jpeg_decode, bit-identical to the cv2.imread of get_prob_video.py:95): the host
+    only reads the file bytes and parses the JPEG headers.  Returns (flat uint8 device buffer, offsets, heights, widths)."""
+    from . import jpeg
+
+    files = []
+    for p in paths:
+        with open(p, "rb") as f:
+            files.append(f.read())
+    try:
+        return jpeg.decode_batch(files, device)
+    except jpeg.UnsupportedJpeg as e:
+        raise jpeg.UnsupportedJpeg(f"{e} -- the GPU decoder covers what cv2.imwrite writes by default (baseline, 4:2:0 / 4:4:4); "
+                                   "avcer_b200.config.set_jpeg_decoder('cv2') decodes on the host instead") from e
+
+
+def _load_crops_cv2(paths, device):
+    """Host decode with cv2.imread exactly as the reference does (:95); the crops are staged 16-byte aligned."""
+    chunks, offsets, hs, ws = [], [], [], []
+    off = 0
+    for p in paths:
+        img = cv2.imread(p)                                          # BGR uint8, what pth_processing ends up consuming
+        h, w, _ = img.shape
+        chunks.append(np.ascontiguousarray(img).reshape(-1))
+        offsets.append(off)
+        hs.append(h)
+        ws.append(w)
+        off += (h * w * 3 + 15) // 16 * 16                           # keep every crop 16-byte aligned
     flat = np.zeros(max(off, 16), dtype=np.uint8)
     for c, o in zip(chunks, offsets):
         flat[o:o + c.size] = c
-    return flat, np.asarray(offsets, dtype=np.int64), np.asarray(hs, dtype=np.int32), np.asarray(ws, dtype=np.int32), exists
+    return (torch.from_numpy(flat).to(device), np.asarray(offsets, dtype=np.int64), np.asarray(hs, dtype=np.int32),
+            np.asarray(ws, dtype=np.int32))
 
 
 def preprocess_video_and_predict(path_images="", save_path="", fps=30, total_frames=[], flag_save_prob=False,
@@ -48,10 +72,12 @@ def preprocess_video_and_predict(path_images="", save_path="", fps=30, total_fra
     if flag_heatmaps:
         raise NotImplementedError("Grad-CAM heatmaps need a backward pass and are outside the accelerated path")
     eng = config.video_engine()
-    flat, offsets, hs, ws, exists = _load_crops(path_images, total_frames)
-    n_present = int(exists.sum())
+    paths, exists = _present_frames(path_images, total_frames)
+    n_present = len(paths)
     if n_present:
-        probs, feats = eng.vs_forward_ragged(torch.from_numpy(flat).to(eng.device), offsets, hs, ws)
+        load = _load_crops_gpu if config.jpeg_decoder() == "gpu" else _load_crops_cv2
+        flat, offsets, hs, ws = load(paths, eng.device)
+        probs, feats = eng.vs_forward_ragged(flat, offsets, hs, ws)
     else:
         probs = torch.zeros((1, 7), device=eng.device)
         feats = torch.zeros((1, 512), device=eng.device, dtype=torch.float32)

@@ -1,0 +1,191 @@
+"""Batched baseline-JPEG decode on the GPU: the drop-in for the `cv2.imread` of the face crops
+(reference src/get_prob_video.py:95; the files are written by src/data/get_face_images.py:60 with cv2.imwrite defaults).
+
+The host does what is inherently serial and tiny -- walking the marker segments (T.81 B.2: SOF0, DQT, DHT, SOS) and removing
+the byte stuffing of the entropy-coded segment -- and hands the batch to `avcer_jpeg_decode` (csrc/jpeg.cu): Huffman
+decoding with one thread per image, libjpeg-turbo's integer IDCT, fancy chroma up-sampling and YCbCr -> BGR conversion,
+bit-identical to cv2.imread.  Covered: baseline sequential DCT, 8 bit, three components, 4:2:0 or 4:4:4, no restart markers
+(everything cv2.imwrite produces by default).  Other files raise `UnsupportedJpeg`; `config.set_jpeg_decoder("cv2")` hands
+decoding back to the host (upstream of the accelerated path, as in the reference).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+ZIGZAG = np.array([0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21,
+                   28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61,
+                   54, 47, 55, 62, 63], dtype=np.int64)
+
+IMAGE_DTYPE = np.dtype([("data_off", "<i8"), ("data_len", "<i8"), ("coef_off", "<i8"), ("plane_off", "<i8"), ("out_off", "<i8"),
+                        ("width", "<i4"), ("height", "<i4"), ("mcus_w", "<i4"), ("mcus_h", "<i4"), ("hs", "<i4"), ("qt_y", "<i4"),
+                        ("qt_c", "<i4"), ("reserved", "<i4")], align=True)          # avcer_jpeg_image
+
+
+class UnsupportedJpeg(ValueError):
+    pass
+
+
+class ParsedJpeg:
+    __slots__ = ("width", "height", "hs", "qt_y", "qt_c", "huff_bits", "huff_vals", "data")
+
+
+def _u16(b: bytes, i: int) -> int:
+    return (b[i] << 8) | b[i + 1]
+
+
+def parse(buf: bytes) -> ParsedJpeg:
+    """Marker walk of one file.  Returns frame size, sampling (hs), the two quantisation tables in natural order, the four
+    Huffman tables (DC / AC of luma, DC / AC of chroma) and the entropy-coded segment with the byte stuffing removed."""
+    if len(buf) < 4 or buf[0] != 0xFF or buf[1] != 0xD8:
+        raise UnsupportedJpeg("not a JPEG file (no SOI marker)")
+    qt, huff, comps, scan = {}, {}, [], None
+    width = height = 0
+    i = 2
+    n = len(buf)
+    while i + 4 <= n:
+        if buf[i] != 0xFF:
+            raise UnsupportedJpeg(f"marker expected at byte {i}")
+        m = buf[i + 1]
+        if m == 0xFF:
+            i += 1
+            continue
+        seg_len = _u16(buf, i + 2)
+        seg = buf[i + 4: i + 2 + seg_len]
+        if m == 0xC0:
+            if seg[0] != 8:
+                raise UnsupportedJpeg("only 8-bit samples")
+            height, width = _u16(seg, 1), _u16(seg, 3)
+            comps = [(seg[6 + 3 * c], seg[7 + 3 * c] >> 4, seg[7 + 3 * c] & 15, seg[8 + 3 * c]) for c in range(seg[5])]
+        elif 0xC1 <= m <= 0xCF and m not in (0xC4, 0xC8, 0xCC):
+            raise UnsupportedJpeg(f"SOF marker 0x{m:02x}: only baseline sequential DCT (SOF0) is decoded on the GPU")
+        elif m == 0xDB:
+            j = 0
+            while j < len(seg):
+                if seg[j] >> 4:
+                    raise UnsupportedJpeg("16-bit quantisation tables")
+                t = np.zeros(64, dtype=np.uint16)
+                t[ZIGZAG] = np.frombuffer(seg, dtype=np.uint8, count=64, offset=j + 1)
+                qt[seg[j] & 15] = t
+                j += 65
+        elif m == 0xC4:
+            j = 0
+            while j < len(seg):
+                bits = np.frombuffer(seg, dtype=np.uint8, count=16, offset=j + 1)
+                cnt = int(bits.sum())
+                vals = np.zeros(256, dtype=np.uint8)
+                vals[:cnt] = np.frombuffer(seg, dtype=np.uint8, count=cnt, offset=j + 17)
+                huff[(seg[j] >> 4, seg[j] & 15)] = (bits.copy(), vals)
+                j += 17 + cnt
+        elif m == 0xDD:
+            if _u16(seg, 0) != 0:
+                raise UnsupportedJpeg("restart intervals")
+        elif m == 0xDA:
+            ids = [c[0] for c in comps]
+            scan = [(ids.index(seg[1 + 2 * k]), seg[2 + 2 * k] >> 4, seg[2 + 2 * k] & 15) for k in range(seg[0])]
+            i += 2 + seg_len
+            break
+        i += 2 + seg_len
+    if scan is None or not comps:
+        raise UnsupportedJpeg("no SOF0 / SOS marker")
+    if len(comps) != 3 or [s[0] for s in scan] != [0, 1, 2]:
+        raise UnsupportedJpeg(f"{len(comps)} components: only three-component YCbCr files are decoded on the GPU")
+    (_, yh, yv, yq), (_, bh, bv, bq), (_, rh, rv, rq) = comps
+    if (bh, bv, rh, rv) != (1, 1, 1, 1) or yh != yv or yh not in (1, 2) or bq != rq or scan[1][1:] != scan[2][1:]:
+        raise UnsupportedJpeg(f"sampling {yh}x{yv} / {bh}x{bv} / {rh}x{rv}: only 4:2:0 and 4:4:4 are decoded on the GPU")
+    end = buf.rfind(b"\xff\xd9")
+    a = np.frombuffer(buf, dtype=np.uint8, count=(end if end >= i else n) - i, offset=i)
+    ff = np.nonzero(a[:-1] == 0xFF)[0]
+    nxt = a[ff + 1]
+    if np.any((nxt >= 0xD0) & (nxt <= 0xD7)):
+        raise UnsupportedJpeg("restart markers")
+    stuffed = ff[nxt == 0]
+    out = ParsedJpeg()
+    out.width, out.height, out.hs = width, height, yh
+    out.qt_y, out.qt_c = qt[yq], qt[bq]
+    tabs = [huff[(0, scan[0][1])], huff[(1, scan[0][2])], huff[(0, scan[1][1])], huff[(1, scan[1][2])]]
+    out.huff_bits = np.stack([t[0] for t in tabs])
+    out.huff_vals = np.stack([t[1] for t in tabs])
+    out.data = np.delete(a, stuffed + 1) if len(stuffed) else a
+    return out
+
+
+def decode_batch(files: Sequence[bytes], device, align_out: int = 16) -> Tuple[torch.Tensor, np.ndarray, np.ndarray, np.ndarray]:
+    """Decode a batch of JPEG byte strings.  Returns (flat uint8 device buffer, byte offsets [n], heights [n], widths [n]):
+    image i is out[offsets[i] : offsets[i] + h*w*3] viewed as [h, w, 3] in BGR order -- what cv2.imread returns, and the
+    ragged layout Engine.vs_forward_ragged / avcer_preprocess_u8 consume.  `align_out`: alignment of every image's offset."""
+    dev = torch.device(device)
+    n = len(files)
+    if n == 0:
+        return torch.zeros(16, dtype=torch.uint8, device=dev), np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32)
+    parsed = [parse(f) for f in files]
+    # images that share their Huffman tables go in one launch (cv2.imwrite always uses the Annex-K tables)
+    groups = {}
+    for i, p in enumerate(parsed):
+        groups.setdefault(p.huff_bits.tobytes() + p.huff_vals.tobytes(), []).append(i)
+    heights = np.array([p.height for p in parsed], dtype=np.int32)
+    widths = np.array([p.width for p in parsed], dtype=np.int32)
+    sizes = heights.astype(np.int64) * widths * 3
+    padded = (sizes + align_out - 1) // align_out * align_out
+    offsets = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64)
+    out = torch.empty(int(padded.sum()) + 16, dtype=torch.uint8, device=dev)
+    lib = _lib.load()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    statuses = []
+    for idx in groups.values():
+        imgs = np.zeros(len(idx), dtype=IMAGE_DTYPE)
+        qtabs, qindex, chunks = [], {}, []
+        data_off = coef_off = plane_off = pix = 0
+        prefix = np.zeros(len(idx), dtype=np.int64)
+        for k, i in enumerate(idx):
+            p = parsed[i]
+            mw, mh = -(-p.width // (8 * p.hs)), -(-p.height // (8 * p.hs))
+            for name, t in (("qt_y", p.qt_y), ("qt_c", p.qt_c)):
+                key = t.tobytes()
+                if key not in qindex:
+                    qindex[key] = len(qtabs)
+                    qtabs.append(t)
+                imgs[name][k] = qindex[key]
+            imgs["data_off"][k], imgs["data_len"][k] = data_off, len(p.data)
+            imgs["coef_off"][k], imgs["plane_off"][k], imgs["out_off"][k] = coef_off, plane_off, offsets[i]
+            imgs["width"][k], imgs["height"][k], imgs["mcus_w"][k], imgs["mcus_h"][k], imgs["hs"][k] = p.width, p.height, mw, mh, p.hs
+            prefix[k] = pix
+            pix += p.width * p.height
+            chunks.append(p.data)
+            pad = (-len(p.data)) % 4
+            if pad:
+                chunks.append(np.zeros(pad, dtype=np.uint8))
+            data_off += len(p.data) + pad
+            blocks = mw * mh * (p.hs * p.hs + 2)
+            coef_off += blocks
+            plane_off += blocks * 64
+        data = torch.from_numpy(np.concatenate(chunks + [np.zeros(8, dtype=np.uint8)])).to(dev)
+        meta = torch.from_numpy(imgs.view(np.uint8).reshape(-1).copy()).to(dev)
+        bits = torch.from_numpy(parsed[idx[0]].huff_bits.reshape(-1).copy()).to(dev)
+        vals = torch.from_numpy(parsed[idx[0]].huff_vals.reshape(-1).copy()).to(dev)
+        qt = torch.from_numpy(np.stack(qtabs).astype(np.uint16).view(np.int16)).to(dev)
+        pre = torch.from_numpy(prefix).to(dev)
+        coefs = torch.empty(coef_off * 64, dtype=torch.int16, device=dev)
+        planes = torch.empty(plane_off + 8, dtype=torch.uint8, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        rc = lib.avcer_jpeg_decode(data.data_ptr(), meta.data_ptr(), len(idx), bits.data_ptr(), vals.data_ptr(), qt.data_ptr(),
+                                   pre.data_ptr(), coef_off, pix, coefs.data_ptr(), planes.data_ptr(), out.data_ptr(),
+                                   status.data_ptr(), ctypes.c_void_p(stream))
+        _lib.check(rc)
+        statuses.append((status, idx))
+    for status, idx in statuses:
+        s = int(status.item())
+        if s:
+            raise UnsupportedJpeg(f"corrupt entropy-coded data in image {idx[s - 1]} of the batch")
+    return out, offsets, heights, widths
+
+
+def decode_images(files: Sequence[bytes], device) -> List[torch.Tensor]:
+    """Convenience: one uint8 [h, w, 3] BGR device tensor per file (views into one buffer)."""
+    out, off, hs, ws = decode_batch(files, device)
+    return [out[int(o): int(o) + int(h) * int(w) * 3].view(int(h), int(w), 3) for o, h, w in zip(off, hs, ws)]

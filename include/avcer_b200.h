@@ -277,6 +277,35 @@ int avcer_avgpool1d_relu(const void* x, int n, int t, int c, void* y, int dtype,
 /* dtype conversion helpers (fp32 <-> bf16). */
 int avcer_cast(const void* x, int64_t n, int src_dtype, void* y, int dst_dtype, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Baseline-JPEG decode of the face crops: replaces cv2.imread at get_prob_video.py:95 for
+ * the files data/get_face_images.py:60 writes with cv2.imwrite defaults (baseline sequential DCT, 8 bit, YCbCr 4:2:0 or
+ * 4:4:4, no restart markers).  Bit-identical to cv2.imread: T.81 Huffman decoding, libjpeg-turbo's jpeg_idct_islow,
+ * h2v2 fancy up-sampling and ycc_rgb_convert restated as integer kernels.
+ * The HOST parses the markers (SOF0 / DQT / DHT / SOS), removes the byte stuffing (FF 00 -> FF) and fills, per image: */
+typedef struct {
+  int64_t data_off;   /* byte offset of the image's entropy-coded segment in `data` (multiple of 4) */
+  int64_t data_len;   /* its length in bytes */
+  int64_t coef_off;   /* first 8x8 block of the image in `coefs` (all Y blocks row-major, then Cb, then Cr) */
+  int64_t plane_off;  /* byte offset of the image's Y sample plane in `planes` (Cb and Cr planes follow); multiple of 8 */
+  int64_t out_off;    /* byte offset of the decoded BGR image in `out` */
+  int32_t width, height;
+  int32_t mcus_w, mcus_h;  /* MCU grid: ceil(width / (8*hs)), ceil(height / (8*hs)) */
+  int32_t hs;         /* luma sampling factor on both axes: 2 = 4:2:0, 1 = 4:4:4 */
+  int32_t qt_y, qt_c; /* indices into qtables */
+  int32_t reserved;
+} avcer_jpeg_image;
+/* data: all entropy-coded segments; huff_bits [4][16] / huff_vals [4][256]: the tables DC0, AC0, DC1, AC1 (luma, chroma)
+ * shared by the batch; qtables [*][64] uint16 in natural (row-major) order; pixel_prefix [n]: index of every image's first
+ * pixel in the batch; coefs [total_blocks][64] int16 and planes (sum of MCU-padded component planes) are scratch;
+ * out receives height x width x 3 bytes per image in B, G, R order; *status (device) is 0 on success, else 1 + the index of
+ * an image with a corrupt bit stream. */
+int avcer_jpeg_decode(const uint8_t* data, const avcer_jpeg_image* images, int n, const uint8_t* huff_bits,
+                      const uint8_t* huff_vals, const uint16_t* qtables, const int64_t* pixel_prefix,
+                      int64_t total_blocks, int64_t total_pixels, int16_t* coefs, uint8_t* planes, uint8_t* out,
+                      int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

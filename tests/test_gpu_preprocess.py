@@ -93,3 +93,34 @@ def test_pcm16_resample_matches_reference(cuda_lib, golden, tmp_path):
         assert np.abs(got - want).max() < 3e-6, (sr, n, ch, np.abs(got - want).max())
     with pytest.raises(FileNotFoundError):
         convert_mp4_to_mp3(str(tmp_path / "absent.mp4"), 16000)
+
+
+def test_jpeg_decode_bit_identical_to_cv2(cuda_lib):
+    """avcer_jpeg_decode against cv2.imdecode (the reference's decoder, get_prob_video.py:95): one ragged batch mixing
+    sizes (full / partial / single MCUs, odd chroma widths), qualities (different quantisation tables) and 4:4:4 files;
+    a second batch of 300 crops 224x224 (more images than one warp, the packed BASELINE shape)."""
+    import cv2
+
+    from avcer_b200 import jpeg, synthetic as syn
+
+    cases = [(224, 224, 95), (97, 133, 95), (16, 16, 95), (8, 8, 50), (1, 1, 95), (17, 31, 75), (200, 301, 95), (33, 16, 50),
+             (2, 2, 95), (15, 15, 95), (480, 640, 90), (225, 223, 95)]
+    files, refs = [], []
+    for h, w, q in cases:
+        img = np.ascontiguousarray(syn.make_crops(h * 1000 + w, 1, max(h, w))[0][:h, :w])
+        for extra in ([], [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]):
+            ok, buf = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q] + extra)
+            files.append(buf.tobytes())
+            refs.append(cv2.imdecode(buf, cv2.IMREAD_COLOR))
+    got = jpeg.decode_images(files, "cuda:0")
+    for g, r, c in zip(got, refs, [c for c in cases for _ in range(2)]):
+        assert g.shape == r.shape and np.array_equal(g.cpu().numpy(), r), c
+    crops = syn.make_crops(5, 300)
+    files = [cv2.imencode(".jpg", c)[1].tobytes() for c in crops]
+    out, off, hs, ws = jpeg.decode_batch(files, "cuda:0", align_out=1)
+    assert (hs == 224).all() and (ws == 224).all() and off[1] == 224 * 224 * 3
+    dec = out[: 300 * 224 * 224 * 3].view(300, 224, 224, 3).cpu().numpy()
+    for i in (0, 1, 31, 32, 33, 150, 299):
+        assert np.array_equal(dec[i], cv2.imdecode(np.frombuffer(files[i], np.uint8), cv2.IMREAD_COLOR)), i
+    with pytest.raises(jpeg.UnsupportedJpeg):
+        jpeg.decode_batch([cv2.imencode(".jpg", crops[0], [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])[1].tobytes()], "cuda:0")

@@ -173,3 +173,56 @@ def test_batch1_loops_match_batched_oracle(tmp_path):
     o_rows, o_ids, _ = oa.predict_audio(wav, fps, sd_a, step=0.5)
     assert np.array_equal(ids, o_ids) and np.array_equal(np.isnan(rows), np.isnan(o_rows))
     assert np.nanmax(np.abs(rows - o_rows)) < 5e-5
+
+
+JPEG_CASES = [(224, 224, 95), (97, 133, 95), (16, 16, 95), (8, 8, 50), (1, 1, 95), (17, 31, 75), (200, 301, 95), (33, 16, 50),
+              (2, 2, 95), (15, 15, 95)]
+
+
+def _jpeg_image(h, w):
+    return np.ascontiguousarray(syn.make_crops(h * 1000 + w, 1, max(h, w))[0][:h, :w])
+
+
+def test_jpeg_oracle_matches_cv2():
+    """oracle/jpeg.py (libjpeg-turbo's baseline decoder restated: Huffman, islow IDCT, h2v2 fancy up-sampling, YCbCr -> BGR)
+    against cv2.imdecode -- the decoder the reference itself calls (get_prob_video.py:95) -- bit for bit, on full, partial
+    and tiny MCU grids, odd chroma widths, two qualities and 4:4:4."""
+    import cv2
+
+    from oracle import jpeg as oj
+
+    for h, w, q in JPEG_CASES:
+        ok, buf = cv2.imencode(".jpg", _jpeg_image(h, w), [cv2.IMWRITE_JPEG_QUALITY, q])
+        assert ok and np.array_equal(oj.decode(buf.tobytes()), cv2.imdecode(buf, cv2.IMREAD_COLOR)), (h, w, q)
+    ok, buf = cv2.imencode(".jpg", _jpeg_image(50, 70), [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444])
+    assert np.array_equal(oj.decode(buf.tobytes()), cv2.imdecode(buf, cv2.IMREAD_COLOR))
+
+
+def test_jpeg_host_parser_matches_oracle_header():
+    """avcer_b200.jpeg.parse (the product's own marker walk + byte un-stuffing, host side of avcer_jpeg_decode) against the
+    oracle's header reader; files outside the GPU decoder's coverage are rejected, not mis-decoded."""
+    import cv2
+
+    from avcer_b200 import jpeg
+    from oracle import jpeg as oj
+
+    for h, w, q in JPEG_CASES[:6]:
+        ok, buf = cv2.imencode(".jpg", _jpeg_image(h, w), [cv2.IMWRITE_JPEG_QUALITY, q])
+        b = buf.tobytes()
+        p, o = jpeg.parse(b), oj.parse(b)
+        assert (p.width, p.height, p.hs) == (o.width, o.height, o.components[0][1])
+        assert np.array_equal(p.qt_y, o.qt[o.components[0][3]]) and np.array_equal(p.qt_c, o.qt[o.components[1][3]])
+        for t, key in enumerate([(0, 0), (1, 0), (0, 1), (1, 1)]):
+            bits, vals = o.huff[key]
+            assert np.array_equal(p.huff_bits[t], bits[1:]) and np.array_equal(p.huff_vals[t][: len(vals)], vals)
+        assert bytes(p.data) == o.data.replace(b"\xff\x00", b"\xff")
+    img = _jpeg_image(40, 40)
+    for flags in ([cv2.IMWRITE_JPEG_PROGRESSIVE, 1], [cv2.IMWRITE_JPEG_RST_INTERVAL, 4]):
+        ok, buf = cv2.imencode(".jpg", img, flags)
+        with pytest.raises(jpeg.UnsupportedJpeg):
+            jpeg.parse(buf.tobytes())
+    ok, buf = cv2.imencode(".jpg", img[:, :, 0])
+    with pytest.raises(jpeg.UnsupportedJpeg):
+        jpeg.parse(buf.tobytes())
+    with pytest.raises(jpeg.UnsupportedJpeg):
+        jpeg.parse(b"not a jpeg at all")

@@ -156,9 +156,11 @@ class Engine:
         self._vs_sms, self._a_sms = vs_sms, a_sms
         self._a_stream = torch.cuda.Stream(device=self.device) if overlap else None
         self._vs_graph = GraphedForward(lambda x: self.vs.forward(x), vs_sms) if self.vs is not None else None
-        # K1 fused into the stem (packed 224x224 crops, bf16): the stem kernel reads the uint8 crops where they lie (one
-        # eager launch, its input address changes per batch); layer1 .. fc2 replay as a graph on the persistent stem output
-        self.fuse_k1 = True
+        # K1 fused into the stem (packed 224x224 crops, bf16; avcer_stem_pool_u8): the stem kernel reads the uint8 crops
+        # where they lie (one eager launch, its input address changes per batch); layer1 .. fc2 replay as a graph on the
+        # persistent stem output.  Bit-identical, but OFF by default: measured 240 us against 160 + 33 us for K1 + the
+        # TMA-fed stem at batch 256 in three converter designs (profiles/r02_k1_fusion_negative.txt)
+        self.fuse_k1 = False
         self._vs_body_graph = GraphedForward(lambda c: self.vs.body(c), vs_sms) if self.vs is not None else None
         self._vs_cat: Optional[torch.Tensor] = None
         self._a_graph = GraphedForward(lambda x: self.a.forward(x), a_sms) if self.a is not None else None

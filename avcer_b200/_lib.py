@@ -66,6 +66,7 @@ _SIGNATURES = {
     "avcer_preprocess_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "avcer_preprocess_maps": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "avcer_contract": (c_int, [POINTER(ContractDesc), c_void_p]),
+    "avcer_last_contract_kernel": (c_int, []),
     "avcer_fuse_compound": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_int, c_void_p, c_int64, c_void_p]),
     "avcer_fuse_compound_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_int, c_void_p, c_int64, c_void_p]),
     "avcer_compound_scores": (c_int, [c_void_p, c_int64, c_int, c_int, POINTER(c_int32), POINTER(c_double), c_int, c_int, c_void_p, c_void_p]),
@@ -96,7 +97,7 @@ _SIGNATURES = {
     "avcer_maxpool1d5_relu": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "avcer_avgpool1d_relu": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "avcer_jpeg_decode": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_void_p]),
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "avcer_cast": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
 }
 

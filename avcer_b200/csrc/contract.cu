@@ -113,6 +113,14 @@ extern "C" int avcer_debug_set_trace(void* buf) {
 
 static int num_sms_cached() { return num_sms(); }
 
+// Which kernel the last avcer_contract call of this thread dispatched to (avcer_last_contract_kernel): lets the host
+// attribute per-launch timings to the exact kernel (bench.py's roofline names ONE dominant kernel, not a family).
+static thread_local int g_last_kernel = 0;
+enum KernelId : int {
+  KID_NONE = 0, KID_SIMT = 1, KID_TC_64 = 2, KID_TC_128 = 3, KID_TC_256 = 4, KID_TC_F32OUT = 5, KID_TC2_256 = 6, KID_TC2_256_RES = 7,
+  KID_TC2_256_FLAT = 8, KID_TC2_256_FLAT_RES = 9, KID_TC2_128 = 10, KID_CONV3_64 = 11, KID_CONV3_128 = 12, KID_TC_STRIP = 13
+};
+
 // 3x3 "same" stride-1 convolutions with 64 / 128 output channels over dense NHWC tensors (ResNet-50 layer1 / layer2
 // conv2): halo-in-shared-memory kernel of conv3x3.cuh.  Returns -1 when the geometry is not its case.
 template <int BN, bool RES>
@@ -179,6 +187,7 @@ static int conv3x3_tc(const avcer_contract_desc* d, cudaStream_t st) {
     uint32_t box[5] = {64u, (uint32_t)W, (uint32_t)p.bh, 1u, 1u};
     if (encode_map(&tc, d->out, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
+  g_last_kernel = Cout == 64 ? KID_CONV3_64 : KID_CONV3_128;
   if (Cout == 64) return launch_conv3<64, true>(ta, tb, tc, p, st);
   return launch_conv3<128, false>(ta, tb, tc, p, st);
 }
@@ -311,6 +320,11 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
     }
   }
   const int grid = num_sms_cached();
+  if (use_cta2)
+    g_last_kernel = BN != 256 ? KID_TC2_128 : flat ? (mode == OUT_TMA ? KID_TC2_256_FLAT : KID_TC2_256_FLAT_RES)
+                                                   : (mode == OUT_TMA ? KID_TC2_256 : KID_TC2_256_RES);
+  else
+    g_last_kernel = mode == OUT_DIRECT_F32 ? KID_TC_F32OUT : d->a_strip ? KID_TC_STRIP : BN == 64 ? KID_TC_64 : BN == 128 ? KID_TC_128 : KID_TC_256;
   if (use_cta2) {
     if (BN == 256) {
       if (flat) {
@@ -593,6 +607,7 @@ static int contract_simt(const avcer_contract_desc* d, cudaStream_t st) {
   const long long gx = (p.M + 63) / 64;
   AVCER_REQUIRE(gx < (1ll << 31), "contract(f32): M too large");
   dim3 grid((unsigned)gx, (unsigned)((d->cout + 63) / 64));
+  g_last_kernel = KID_SIMT;
   simt_contract_kernel<<<grid, 256, 0, st>>>(p);
   return check_launch("simt_contract_kernel");
 }
@@ -628,3 +643,5 @@ extern "C" int avcer_stem_pool_u8(const uint8_t* crops, const void* w_packed, co
   AVCER_REQUIRE(n >= 0, "stem_pool_u8: negative batch");
   return stem_pool_u8_tc(crops, w_packed, bias, n, out, out_pitch, as_stream(stream));
 }
+
+extern "C" int avcer_last_contract_kernel(void) { return avcer::g_last_kernel; }

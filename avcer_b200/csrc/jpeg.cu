@@ -6,6 +6,8 @@
 // cv2.imdecode on the CPU).
 //
 // Three kernels, all integer / byte work bound by latency and HBM, not by math:
+//   0. jpeg_unstuff_kernel  -- the byte stuffing of the entropy-coded segments (FF 00 -> FF) removed by a block-per-image
+//      stream compaction (the host only walks the marker segments: ~20 per file);
 //   1. jpeg_huffman_kernel  -- ONE THREAD PER IMAGE walks its entropy-coded segment (T.81 F.2.2): 64-bit bit buffer refilled
 //      with aligned 32-bit loads, 10-bit look-ahead tables in shared memory (code length + symbol in one lookup, canonical
 //      max-code search for the few longer codes), one symbol per loop iteration so that the 32 images of a warp stay
@@ -49,13 +51,69 @@ __constant__ unsigned char c_zigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32,
                                           54, 47, 55, 62, 63};
 __device__ __forceinline__ int zigzag_natural(int k) { return c_zigzag[k]; }
 
+// Byte un-stuffing (T.81 B.1.1.5: a 0x00 follows every 0xFF data byte) as a per-image stream compaction: one block per
+// image, 1 KB chunks, warp-shuffle + shared-memory exclusive scan of the keep flags, scatter.  A restart marker
+// (FF D0..D7) inside the segment is reported through `status` (not covered: cv2.imwrite never writes them by default).
+constexpr int UNSTUFF_THREADS = 256;
+__global__ void __launch_bounds__(UNSTUFF_THREADS)
+jpeg_unstuff_kernel(const unsigned char* __restrict__ raw, const JpegImage* __restrict__ imgs, unsigned char* __restrict__ data,
+                    long long* __restrict__ lens, int* __restrict__ status) {
+  __shared__ int warp_sums[UNSTUFF_THREADS / 32];
+  __shared__ long long base_s;
+  const int img = blockIdx.x;
+  const long long off = imgs[img].data_off, len = imgs[img].data_len;
+  const unsigned char* src = raw + off;
+  unsigned char* dst = data + off;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  for (long long c0 = 0; c0 < len; c0 += UNSTUFF_THREADS * 4) {
+    // every thread owns 4 consecutive bytes
+    const long long i0 = c0 + threadIdx.x * 4;
+    unsigned char b[4];
+    int keep[4], cnt = 0;
+    unsigned char prev = (i0 > 0 && i0 - 1 < len) ? src[i0 - 1] : 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = i0 + j;
+      b[j] = i < len ? src[i] : 0;
+      keep[j] = i < len && !(prev == 0xFF && b[j] == 0x00);
+      if (i < len && prev == 0xFF && b[j] >= 0xD0 && b[j] <= 0xD7) atomicExch(status, -(img + 1));     // restart marker
+      // a stuffed 0x00 is dropped, and does not itself make the NEXT byte look stuffed (FF 00 00 keeps the second 00)
+      prev = b[j];
+      cnt += keep[j];
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+    for (int w = 0; w < UNSTUFF_THREADS / 32; ++w) {
+      if (w < wid) wbase += warp_sums[w];
+      total += warp_sums[w];
+    }
+    long long pos = base_s + wbase + incl - cnt;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (keep[j]) dst[pos++] = b[j];
+    __syncthreads();
+    if (threadIdx.x == 0) base_s += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) lens[img] = base_s;
+}
+
 // bits: [4][16] code counts per length, vals: [4][256] symbols; table order DC0, AC0, DC1, AC1
 constexpr int HUFF_THREADS = 32;      // one warp per block: a batch of 1 500 crops already spreads over 47 SMs
 
 __global__ void __launch_bounds__(HUFF_THREADS)
 jpeg_huffman_kernel(const unsigned char* __restrict__ data, const JpegImage* __restrict__ imgs, int n,
-                    const unsigned char* __restrict__ bits, const unsigned char* __restrict__ vals, short* __restrict__ coefs,
-                    int* __restrict__ status) {
+                    const long long* __restrict__ lens, const unsigned char* __restrict__ bits,
+                    const unsigned char* __restrict__ vals, short* __restrict__ coefs, int* __restrict__ status) {
   __shared__ HuffTab tabs[4];
   // ---- expand the four tables (every thread block builds its own copy; ~4 K entries)
   for (int t = 0; t < 4; ++t) {
@@ -87,7 +145,7 @@ jpeg_huffman_kernel(const unsigned char* __restrict__ data, const JpegImage* __r
   if (img >= n) return;
   const JpegImage im = imgs[img];
   const unsigned int* words = reinterpret_cast<const unsigned int*>(data + im.data_off);
-  const long long n_words = (im.data_len + 3) >> 2;
+  const long long n_words = (lens[img] + 3) >> 2;             // un-stuffed length (jpeg_unstuff_kernel)
   long long wi = 0;
   unsigned long long bb = 0;      // bit buffer, MSB-aligned content in the low `nb` bits
   int nb = 0;
@@ -107,7 +165,7 @@ jpeg_huffman_kernel(const unsigned char* __restrict__ data, const JpegImage* __r
   const long long y_blocks = (long long)yw * im.mcus_h * im.hs;
   const long long c_blocks = (long long)im.mcus_w * im.mcus_h;
   const long long n_mcus = c_blocks;
-  int pred[3] = {0, 0, 0};
+  int pred_y = 0, pred_cb = 0, pred_cr = 0;                   // DC predictors in registers (no dynamically indexed array)
   int bad = 0;
   for (long long mcu = 0; mcu < n_mcus && !bad; ++mcu) {
     const int mx = (int)(mcu % im.mcus_w), my = (int)(mcu / im.mcus_w);
@@ -151,8 +209,9 @@ jpeg_huffman_kernel(const unsigned char* __restrict__ data, const JpegImage* __r
           if (v < (1 << (size - 1))) v -= (1 << size) - 1;  // EXTEND (T.81 F.2.2.1)
         }
         if (k == 0) {
-          pred[comp] += v;
-          out[0] = (short)pred[comp];
+          int& pr = comp == 0 ? pred_y : comp == 1 ? pred_cb : pred_cr;
+          pr += v;
+          out[0] = (short)pr;
           k = 1;
         } else if (size == 0) {
           if (run != 15) break;                             // EOB
@@ -307,13 +366,13 @@ using namespace avcer;
 
 static_assert(sizeof(JpegImage) == sizeof(avcer_jpeg_image), "JpegImage must mirror avcer_jpeg_image");
 
-extern "C" int avcer_jpeg_decode(const uint8_t* data, const avcer_jpeg_image* images, int n, const uint8_t* huff_bits,
+extern "C" int avcer_jpeg_decode(const uint8_t* raw, const avcer_jpeg_image* images, int n, const uint8_t* huff_bits,
                                  const uint8_t* huff_vals, const uint16_t* qtables, const int64_t* pixel_prefix,
-                                 int64_t total_blocks, int64_t total_pixels, int16_t* coefs, uint8_t* planes, uint8_t* out,
-                                 int32_t* status, void* stream) {
+                                 int64_t total_blocks, int64_t total_pixels, uint8_t* data, int64_t* lens, int16_t* coefs,
+                                 uint8_t* planes, uint8_t* out, int32_t* status, void* stream) {
   AVCER_REQUIRE(n >= 0 && total_blocks >= 0 && total_pixels >= 0, "jpeg_decode: negative size");
   if (n == 0) return 0;
-  AVCER_REQUIRE(data && images && huff_bits && huff_vals && qtables && pixel_prefix && coefs && planes && out && status,
+  AVCER_REQUIRE(raw && data && lens && images && huff_bits && huff_vals && qtables && pixel_prefix && coefs && planes && out && status,
                 "jpeg_decode: null pointer");
   AVCER_REQUIRE((reinterpret_cast<uintptr_t>(data) & 3) == 0 && (reinterpret_cast<uintptr_t>(planes) & 7) == 0 &&
                     (reinterpret_cast<uintptr_t>(coefs) & 1) == 0,
@@ -323,7 +382,10 @@ extern "C" int avcer_jpeg_decode(const uint8_t* data, const avcer_jpeg_image* im
   AVCER_CUDA(cudaMemsetAsync(coefs, 0, (size_t)total_blocks * 64 * sizeof(int16_t), st));
   AVCER_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
   const JpegImage* imgs = reinterpret_cast<const JpegImage*>(images);
-  jpeg_huffman_kernel<<<(n + HUFF_THREADS - 1) / HUFF_THREADS, HUFF_THREADS, 0, st>>>(data, imgs, n, huff_bits, huff_vals, coefs, status);
+  jpeg_unstuff_kernel<<<n, UNSTUFF_THREADS, 0, st>>>(raw, imgs, data, reinterpret_cast<long long*>(lens), status);
+  if (int rc = check_launch("jpeg_unstuff_kernel")) return rc;
+  jpeg_huffman_kernel<<<(n + HUFF_THREADS - 1) / HUFF_THREADS, HUFF_THREADS, 0, st>>>(data, imgs, n, reinterpret_cast<const long long*>(lens),
+                                                                                      huff_bits, huff_vals, coefs, status);
   if (int rc = check_launch("jpeg_huffman_kernel")) return rc;
   jpeg_idct_kernel<<<(unsigned)((total_blocks + 31) / 32), 256, 0, st>>>(coefs, imgs, n, total_blocks, qtables, planes);
   if (int rc = check_launch("jpeg_idct_kernel")) return rc;

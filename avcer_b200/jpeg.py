@@ -1,8 +1,8 @@
 """Batched baseline-JPEG decode on the GPU: the drop-in for the `cv2.imread` of the face crops
 (reference src/get_prob_video.py:95; the files are written by src/data/get_face_images.py:60 with cv2.imwrite defaults).
 
-The host does what is inherently serial and tiny -- walking the marker segments (T.81 B.2: SOF0, DQT, DHT, SOS) and removing
-the byte stuffing of the entropy-coded segment -- and hands the batch to `avcer_jpeg_decode` (csrc/jpeg.cu): Huffman
+The host does what is inherently serial and tiny -- walking the ~20 marker segments of every file (T.81 B.2: SOF0, DQT, DHT,
+SOS) -- and hands the batch to `avcer_jpeg_decode` (csrc/jpeg.cu): byte un-stuffing as a stream compaction, Huffman
 decoding with one thread per image, libjpeg-turbo's integer IDCT, fancy chroma up-sampling and YCbCr -> BGR conversion,
 bit-identical to cv2.imread.  Covered: baseline sequential DCT, 8 bit, three components, 4:2:0 or 4:4:4, no restart markers
 (everything cv2.imwrite produces by default).  Other files raise `UnsupportedJpeg`; `config.set_jpeg_decoder("cv2")` hands
@@ -27,6 +27,9 @@ IMAGE_DTYPE = np.dtype([("data_off", "<i8"), ("data_len", "<i8"), ("coef_off", "
                         ("qt_c", "<i4"), ("reserved", "<i4")], align=True)          # avcer_jpeg_image
 
 
+PROFILE = None          # measurement aid: a list receiving (event before, event after) around every avcer_jpeg_decode call
+
+
 class UnsupportedJpeg(ValueError):
     pass
 
@@ -41,7 +44,7 @@ def _u16(b: bytes, i: int) -> int:
 
 def parse(buf: bytes) -> ParsedJpeg:
     """Marker walk of one file.  Returns frame size, sampling (hs), the two quantisation tables in natural order, the four
-    Huffman tables (DC / AC of luma, DC / AC of chroma) and the entropy-coded segment with the byte stuffing removed."""
+    Huffman tables (DC / AC of luma, DC / AC of chroma) and the entropy-coded segment as it sits in the file."""
     if len(buf) < 4 or buf[0] != 0xFF or buf[1] != 0xD8:
         raise UnsupportedJpeg("not a JPEG file (no SOI marker)")
     qt, huff, comps, scan = {}, {}, [], None
@@ -99,20 +102,19 @@ def parse(buf: bytes) -> ParsedJpeg:
     if (bh, bv, rh, rv) != (1, 1, 1, 1) or yh != yv or yh not in (1, 2) or bq != rq or scan[1][1:] != scan[2][1:]:
         raise UnsupportedJpeg(f"sampling {yh}x{yv} / {bh}x{bv} / {rh}x{rv}: only 4:2:0 and 4:4:4 are decoded on the GPU")
     end = buf.rfind(b"\xff\xd9")
-    a = np.frombuffer(buf, dtype=np.uint8, count=(end if end >= i else n) - i, offset=i)
-    ff = np.nonzero(a[:-1] == 0xFF)[0]
-    nxt = a[ff + 1]
-    if np.any((nxt >= 0xD0) & (nxt <= 0xD7)):
-        raise UnsupportedJpeg("restart markers")
-    stuffed = ff[nxt == 0]
     out = ParsedJpeg()
     out.width, out.height, out.hs = width, height, yh
     out.qt_y, out.qt_c = qt[yq], qt[bq]
     tabs = [huff[(0, scan[0][1])], huff[(1, scan[0][2])], huff[(0, scan[1][1])], huff[(1, scan[1][2])]]
     out.huff_bits = np.stack([t[0] for t in tabs])
     out.huff_vals = np.stack([t[1] for t in tabs])
-    out.data = np.delete(a, stuffed + 1) if len(stuffed) else a
+    out.data = buf[i: end if end >= i else n]            # entropy-coded segment, still byte-stuffed (the device removes the stuffing)
     return out
+
+
+def unstuff(data: bytes) -> bytes:
+    """Host restatement of the device's un-stuffing pass (tests): FF 00 -> FF."""
+    return bytes(data).replace(b"\xff\x00", b"\xff")
 
 
 def decode_batch(files: Sequence[bytes], device, align_out: int = 16) -> Tuple[torch.Tensor, np.ndarray, np.ndarray, np.ndarray]:
@@ -159,12 +161,14 @@ def decode_batch(files: Sequence[bytes], device, align_out: int = 16) -> Tuple[t
             chunks.append(p.data)
             pad = (-len(p.data)) % 4
             if pad:
-                chunks.append(np.zeros(pad, dtype=np.uint8))
+                chunks.append(b"\x00" * pad)
             data_off += len(p.data) + pad
             blocks = mw * mh * (p.hs * p.hs + 2)
             coef_off += blocks
             plane_off += blocks * 64
-        data = torch.from_numpy(np.concatenate(chunks + [np.zeros(8, dtype=np.uint8)])).to(dev)
+        raw = torch.frombuffer(bytearray(b"".join(chunks) + b"\x00" * 8), dtype=torch.uint8).to(dev)
+        data = torch.empty_like(raw)
+        lens = torch.empty(len(idx), dtype=torch.int64, device=dev)
         meta = torch.from_numpy(imgs.view(np.uint8).reshape(-1).copy()).to(dev)
         bits = torch.from_numpy(parsed[idx[0]].huff_bits.reshape(-1).copy()).to(dev)
         vals = torch.from_numpy(parsed[idx[0]].huff_vals.reshape(-1).copy()).to(dev)
@@ -173,15 +177,24 @@ def decode_batch(files: Sequence[bytes], device, align_out: int = 16) -> Tuple[t
         coefs = torch.empty(coef_off * 64, dtype=torch.int16, device=dev)
         planes = torch.empty(plane_off + 8, dtype=torch.uint8, device=dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
-        rc = lib.avcer_jpeg_decode(data.data_ptr(), meta.data_ptr(), len(idx), bits.data_ptr(), vals.data_ptr(), qt.data_ptr(),
-                                   pre.data_ptr(), coef_off, pix, coefs.data_ptr(), planes.data_ptr(), out.data_ptr(),
-                                   status.data_ptr(), ctypes.c_void_p(stream))
+        if PROFILE is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        rc = lib.avcer_jpeg_decode(raw.data_ptr(), meta.data_ptr(), len(idx), bits.data_ptr(), vals.data_ptr(), qt.data_ptr(),
+                                   pre.data_ptr(), coef_off, pix, data.data_ptr(), lens.data_ptr(), coefs.data_ptr(), planes.data_ptr(),
+                                   out.data_ptr(), status.data_ptr(), ctypes.c_void_p(stream))
         _lib.check(rc)
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((e0, e1))
         statuses.append((status, idx))
     for status, idx in statuses:
         s = int(status.item())
-        if s:
+        if s > 0:
             raise UnsupportedJpeg(f"corrupt entropy-coded data in image {idx[s - 1]} of the batch")
+        if s < 0:
+            raise UnsupportedJpeg(f"restart markers in image {idx[-s - 1]} of the batch")
     return out, offsets, heights, widths
 
 

@@ -40,12 +40,18 @@ def check(rc: int) -> None:
     _check(rc)
 
 
+CONTRACT_KERNELS = {1: "simt_contract_kernel", 2: "tc_gemm_kernel<64>", 3: "tc_gemm_kernel<128>", 4: "tc_gemm_kernel<256>",
+                    5: "tc_gemm_kernel<f32 out>", 6: "tc_gemm2_kernel<OUT_TMA,256,ring>", 7: "tc_gemm2_kernel<OUT_TMA_RES,256,ring>",
+                    8: "tc_gemm2_kernel<OUT_TMA,256,FLAT>", 9: "tc_gemm2_kernel<OUT_TMA_RES,256,FLAT>", 10: "tc_gemm2_kernel<128>",
+                    11: "conv3x3_kernel<64>", 12: "conv3x3_kernel<128>", 13: "tc_gemm_kernel<strip>"}
+
+
 class _Timed:
-    __slots__ = ("tag", "work", "e0")
+    __slots__ = ("tag", "work", "e0", "bytes")
 
     def __init__(self, tag: str, work: float, launches: int = 1):
         STATS["launches"] += launches
-        self.tag, self.work, self.e0 = tag, work, None
+        self.tag, self.work, self.e0, self.bytes = tag, work, None, 0.0
 
     def __enter__(self):
         if PROFILE is not None:
@@ -57,7 +63,7 @@ class _Timed:
         if self.e0 is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            PROFILE.append((self.tag, self.work, self.e0, e1))
+            PROFILE.append((self.tag, self.work, self.e0, e1, self.bytes))
         return False
 
 
@@ -137,8 +143,15 @@ def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], 
     d.dtype = code
     d.out_f32 = int(code == BF16 and out.dtype == torch.float32)
     k_real = algo_k if algo_k is not None else taps_w * taps_h * cin
-    with _Timed("contract_bf16" if code == BF16 else "contract_f32", 2.0 * W * H * NB * cout * k_real):
+    rows = W * H * NB
+    with _Timed("contract_bf16" if code == BF16 else "contract_f32", 2.0 * rows * cout * k_real) as tm:
         _check(_lib.load().avcer_contract(ctypes.byref(d), _stream()))
+        if PROFILE is not None:
+            # exact kernel + algorithmic bytes of this launch (operands + output once, at their storage width)
+            esz = a.element_size()
+            tm.tag = "contract:" + CONTRACT_KERNELS.get(_lib.load().avcer_last_contract_kernel(), "?")
+            tm.bytes = float(esz * (rows * (k_real if taps_w * taps_h == 1 else cin) + cout * taps_w * taps_h * cin + (rows * cout if residual is not None else 0))
+                             + out.element_size() * rows * cout)
     return out
 
 

@@ -308,31 +308,46 @@ def main():
     ms = float(t.item())
     value = total_frames * args.steps / (ms / 1e3)
 
-    # per-kernel roofline from the profiled step
+    # per-kernel roofline from the profiled step: every launch carries (kernel, algorithmic work, algorithmic bytes)
     agg = {}
-    for tag, work, a, b in prof:
-        d = agg.setdefault(tag, [0.0, 0.0, 0])
+    for tag, work, a, b, nbytes in prof:
+        d = agg.setdefault(tag, [0.0, 0.0, 0, 0.0])
         d[0] += work
         d[1] += a.elapsed_time(b)
         d[2] += 1
-    kern = {k: {"work": v[0], "ms": v[1], "launches": v[2]} for k, v in agg.items()}
+        d[3] += nbytes
+    kern = {k: {"work": v[0], "ms": v[1], "launches": v[2], "bytes": v[3]} for k, v in agg.items()}
     step_ms = ms / args.steps
     roofline = None
-    traffic = None
-    digest = os.path.join(ROOT, "profiles", "r01_kernel_digest.json")
-    if os.path.exists(digest):          # dram__bytes_read.sum + dram__bytes_write.sum per tc_gemm launch (ncu, same workload at 1 clip)
-        traffic = json.load(open(digest)).get("tc_gemm_kernel", {}).get("dram_bytes_per_launch")
     prof_note = ("per-launch CUDA events on one extra eager step run right after the timed region "
                  f"(that step: {profiled_step_ms:.1f} ms; timed steps replay CUDA graphs: {step_ms:.1f} ms)")
-    tc = kern.get("contract_bf16") or kern.get("contract_f32")
-    if tc:
+    # NCU names of the contraction kernels (profiles/r02_kernel_digest.json: dram__bytes_read.sum + dram__bytes_write.sum per launch)
+    ncu_names = {"tc_gemm2_kernel<OUT_TMA,256,ring>": "tc_gemm2_kernel<0, 256, 4, 0>", "tc_gemm2_kernel<OUT_TMA_RES,256,ring>": "tc_gemm2_kernel<1, 256, 4, 0>",
+                 "tc_gemm2_kernel<OUT_TMA,256,FLAT>": "tc_gemm2_kernel<0, 256, 4, 1>", "tc_gemm2_kernel<OUT_TMA_RES,256,FLAT>": "tc_gemm2_kernel<1, 256, 4, 1>",
+                 "conv3x3_kernel<64>": "conv3x3_kernel<64, 1>", "conv3x3_kernel<128>": "conv3x3_kernel<128, 0>"}
+    digest_path = os.path.join(ROOT, "profiles", "r02_kernel_digest.json")
+    digest = json.load(open(digest_path)) if os.path.exists(digest_path) else {}
+    fam = {k: v for k, v in kern.items() if k.startswith("contract")}
+    if fam:
+        name, tc = max(fam.items(), key=lambda kv: kv[1]["ms"])          # the ONE dominant kernel of the step
         ach = tc["work"] / (tc["ms"] / 1e3) / 1e12
-        roofline = {"kernel": "tcgen05 contraction kernels (tc_gemm / tc_gemm2 implicit GEMM, conv3x3 halo conv, fused stem+pool: all VS/VD/A contractions)", "bound": "tensor", "achieved": ach,
-                    "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
-                    "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)", "traffic": traffic,
-                    "traffic_note": "mean DRAM bytes per launch of that kernel family from profiles/r01_kernel_digest.json (ncu, 1-clip run of this bench)",
+        fam_work, fam_ms, fam_n = sum(v["work"] for v in fam.values()), sum(v["ms"] for v in fam.values()), sum(v["launches"] for v in fam.values())
+        short = name.split(":", 1)[-1]
+        dg = digest.get(ncu_names.get(short, short), {})
+        roofline = {"kernel": short + " (two-SM tcgen05 implicit GEMM, 256x256 tiles: FFN / qkv / conv GEMMs of the audio network, wide VS layers)"
+                    if short.startswith("tc_gemm2_kernel<OUT_TMA,256,ring") else short,
+                    "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
+                    "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
+                    "traffic": dg.get("dram_bytes_per_launch"),
+                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel (ncu --set full, profiles/r02_kernel_digest.json); "
+                                    "algorithmic_bytes_per_launch = operands + output once" if dg else "no ncu capture of this kernel in profiles/",
+                    "algorithmic_bytes_per_launch": tc["bytes"] / tc["launches"], "algorithmic_flop_per_launch": tc["work"] / tc["launches"],
                     "launches_per_step": tc["launches"], "avg_launch_us": 1e3 * tc["ms"] / tc["launches"],
-                    "share_of_step": tc["ms"] / profiled_step_ms, "algorithmic_flop_per_step": tc["work"], "how": prof_note}
+                    "share_of_step": tc["ms"] / profiled_step_ms, "how": prof_note,
+                    "all_contraction_kernels": {"achieved": fam_work / (fam_ms / 1e3) / 1e12, "frac": fam_work / (fam_ms / 1e3) / 1e12 / peaks["tf_sustained"],
+                                                "launches_per_step": fam_n, "share_of_step": fam_ms / profiled_step_ms,
+                                                "per_kernel": {k.split(":", 1)[-1]: {"tflops": v["work"] / (v["ms"] / 1e3) / 1e12, "ms": v["ms"], "launches": v["launches"]}
+                                                               for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}}}
     extra = {}
     for tag, name in (("preprocess", "k1_preprocess"), ("fuse_compound", "k4_fusion")):
         if tag in kern:

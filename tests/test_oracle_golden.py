@@ -215,7 +215,7 @@ def test_jpeg_host_parser_matches_oracle_header():
         for t, key in enumerate([(0, 0), (1, 0), (0, 1), (1, 1)]):
             bits, vals = o.huff[key]
             assert np.array_equal(p.huff_bits[t], bits[1:]) and np.array_equal(p.huff_vals[t][: len(vals)], vals)
-        assert bytes(p.data) == o.data.replace(b"\xff\x00", b"\xff")
+        assert bytes(p.data) == o.data and jpeg.unstuff(p.data) == o.data.replace(b"\xff\x00", b"\xff")
     img = _jpeg_image(40, 40)
     for flags in ([cv2.IMWRITE_JPEG_PROGRESSIVE, 1], [cv2.IMWRITE_JPEG_RST_INTERVAL, 4]):
         ok, buf = cv2.imencode(".jpg", img, flags)

@@ -35,7 +35,7 @@ class UnsupportedJpeg(ValueError):
 
 
 class ParsedJpeg:
-    __slots__ = ("width", "height", "hs", "qt_y", "qt_c", "huff_bits", "huff_vals", "data")
+    __slots__ = ("width", "height", "hs", "qt_y", "qt_c", "huff_bits", "huff_vals", "data", "scan_start")
 
 
 def _u16(b: bytes, i: int) -> int:
@@ -109,12 +109,32 @@ def parse(buf: bytes) -> ParsedJpeg:
     out.huff_bits = np.stack([t[0] for t in tabs])
     out.huff_vals = np.stack([t[1] for t in tabs])
     out.data = buf[i: end if end >= i else n]            # entropy-coded segment, still byte-stuffed (the device removes the stuffing)
+    out.scan_start = i
     return out
 
 
 def unstuff(data: bytes) -> bytes:
     """Host restatement of the device's un-stuffing pass (tests): FF 00 -> FF."""
     return bytes(data).replace(b"\xff\x00", b"\xff")
+
+
+_header_cache = {}       # header bytes (SOI .. end of the SOS segment) -> ParsedJpeg without data
+
+
+def _parse_cached(f: bytes, last):
+    """Files written by one encoder at one size share their whole header byte for byte (cv2.imwrite: 623 bytes): the marker
+    walk runs once per distinct header, every other file costs one prefix comparison.  Returns (header info, scan offset)."""
+    if last is not None and f.startswith(last[0]):
+        return last
+    p = parse(f)
+    hdr = bytes(f[:p.scan_start])
+    hit = _header_cache.get(hdr)
+    if hit is None:
+        if len(_header_cache) > 256:
+            _header_cache.clear()
+        p.data = None
+        hit = _header_cache[hdr] = (hdr, p, p.huff_bits.tobytes() + p.huff_vals.tobytes())
+    return hit
 
 
 def decode_batch(files: Sequence[bytes], device, align_out: int = 16) -> Tuple[torch.Tensor, np.ndarray, np.ndarray, np.ndarray]:
@@ -125,63 +145,74 @@ def decode_batch(files: Sequence[bytes], device, align_out: int = 16) -> Tuple[t
     n = len(files)
     if n == 0:
         return torch.zeros(16, dtype=torch.uint8, device=dev), np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32)
-    parsed = [parse(f) for f in files]
-    # images that share their Huffman tables go in one launch (cv2.imwrite always uses the Annex-K tables)
-    groups = {}
-    for i, p in enumerate(parsed):
-        groups.setdefault(p.huff_bits.tobytes() + p.huff_vals.tobytes(), []).append(i)
-    heights = np.array([p.height for p in parsed], dtype=np.int32)
-    widths = np.array([p.width for p in parsed], dtype=np.int32)
+    heads, segs = [], []
+    last = None
+    for f in files:
+        last = _parse_cached(f, last)
+        heads.append(last)
+        end = f.rfind(b"\xff\xd9")
+        segs.append(f[len(last[0]): end if end >= len(last[0]) else len(f)])
+    heights = np.array([h[1].height for h in heads], dtype=np.int32)
+    widths = np.array([h[1].width for h in heads], dtype=np.int32)
+    hs = np.array([h[1].hs for h in heads], dtype=np.int32)
     sizes = heights.astype(np.int64) * widths * 3
     padded = (sizes + align_out - 1) // align_out * align_out
     offsets = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64)
     out = torch.empty(int(padded.sum()) + 16, dtype=torch.uint8, device=dev)
     lib = _lib.load()
     stream = torch.cuda.current_stream(dev).cuda_stream
+    # images that share their Huffman tables go in one launch (cv2.imwrite always uses the Annex-K tables)
+    groups = {}
+    for i, h in enumerate(heads):
+        groups.setdefault(h[2], []).append(i)
     statuses = []
     for idx in groups.values():
-        imgs = np.zeros(len(idx), dtype=IMAGE_DTYPE)
-        qtabs, qindex, chunks = [], {}, []
-        data_off = coef_off = plane_off = pix = 0
-        prefix = np.zeros(len(idx), dtype=np.int64)
-        for k, i in enumerate(idx):
-            p = parsed[i]
-            mw, mh = -(-p.width // (8 * p.hs)), -(-p.height // (8 * p.hs))
-            for name, t in (("qt_y", p.qt_y), ("qt_c", p.qt_c)):
-                key = t.tobytes()
-                if key not in qindex:
-                    qindex[key] = len(qtabs)
-                    qtabs.append(t)
-                imgs[name][k] = qindex[key]
-            imgs["data_off"][k], imgs["data_len"][k] = data_off, len(p.data)
-            imgs["coef_off"][k], imgs["plane_off"][k], imgs["out_off"][k] = coef_off, plane_off, offsets[i]
-            imgs["width"][k], imgs["height"][k], imgs["mcus_w"][k], imgs["mcus_h"][k], imgs["hs"][k] = p.width, p.height, mw, mh, p.hs
-            prefix[k] = pix
-            pix += p.width * p.height
-            chunks.append(p.data)
-            pad = (-len(p.data)) % 4
-            if pad:
-                chunks.append(b"\x00" * pad)
-            data_off += len(p.data) + pad
-            blocks = mw * mh * (p.hs * p.hs + 2)
-            coef_off += blocks
-            plane_off += blocks * 64
-        raw = torch.frombuffer(bytearray(b"".join(chunks) + b"\x00" * 8), dtype=torch.uint8).to(dev)
+        idx = np.asarray(idx)
+        m = len(idx)
+        qtabs, qindex = [], {}
+
+        def qslot(t):
+            key = t.tobytes()
+            if key not in qindex:
+                qindex[key] = len(qtabs)
+                qtabs.append(t)
+            return qindex[key]
+
+        qy = np.array([qslot(heads[i][1].qt_y) for i in idx], dtype=np.int32)
+        qc = np.array([qslot(heads[i][1].qt_c) for i in idx], dtype=np.int32)
+        lens = np.array([len(segs[i]) for i in idx], dtype=np.int64)
+        lens4 = (lens + 3) // 4 * 4
+        w, h, s = widths[idx].astype(np.int64), heights[idx].astype(np.int64), hs[idx].astype(np.int64)
+        mw, mh = -(-w // (8 * s)), -(-h // (8 * s))
+        blocks = mw * mh * (s * s + 2)
+        imgs = np.zeros(m, dtype=IMAGE_DTYPE)
+        imgs["data_off"] = np.concatenate([[0], np.cumsum(lens4)[:-1]])
+        imgs["data_len"] = lens
+        imgs["coef_off"] = np.concatenate([[0], np.cumsum(blocks)[:-1]])
+        imgs["plane_off"] = imgs["coef_off"] * 64
+        imgs["out_off"] = offsets[idx]
+        imgs["width"], imgs["height"], imgs["mcus_w"], imgs["mcus_h"], imgs["hs"] = w, h, mw, mh, s
+        imgs["qt_y"], imgs["qt_c"] = qy, qc
+        prefix = np.concatenate([[0], np.cumsum(w * h)[:-1]]).astype(np.int64)
+        coef_total, pix = int(blocks.sum()), int((w * h).sum())
+        pad = [b"\x00" * int(p) for p in (lens4 - lens)]
+        raw = torch.frombuffer(bytearray(b"".join(x for i, p in zip(idx, pad) for x in (segs[i], p)) + b"\x00" * 8), dtype=torch.uint8).to(dev)
         data = torch.empty_like(raw)
-        lens = torch.empty(len(idx), dtype=torch.int64, device=dev)
-        meta = torch.from_numpy(imgs.view(np.uint8).reshape(-1).copy()).to(dev)
-        bits = torch.from_numpy(parsed[idx[0]].huff_bits.reshape(-1).copy()).to(dev)
-        vals = torch.from_numpy(parsed[idx[0]].huff_vals.reshape(-1).copy()).to(dev)
+        dlens = torch.empty(m, dtype=torch.int64, device=dev)
+        meta = torch.from_numpy(imgs.view(np.uint8).reshape(-1)).to(dev)
+        p0 = heads[idx[0]][1]
+        bits = torch.from_numpy(p0.huff_bits.reshape(-1).copy()).to(dev)
+        vals = torch.from_numpy(p0.huff_vals.reshape(-1).copy()).to(dev)
         qt = torch.from_numpy(np.stack(qtabs).astype(np.uint16).view(np.int16)).to(dev)
         pre = torch.from_numpy(prefix).to(dev)
-        coefs = torch.empty(coef_off * 64, dtype=torch.int16, device=dev)
-        planes = torch.empty(plane_off + 8, dtype=torch.uint8, device=dev)
+        coefs = torch.empty(coef_total * 64, dtype=torch.int16, device=dev)
+        planes = torch.empty(coef_total * 64 + 8, dtype=torch.uint8, device=dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         if PROFILE is not None:
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record()
-        rc = lib.avcer_jpeg_decode(raw.data_ptr(), meta.data_ptr(), len(idx), bits.data_ptr(), vals.data_ptr(), qt.data_ptr(),
-                                   pre.data_ptr(), coef_off, pix, data.data_ptr(), lens.data_ptr(), coefs.data_ptr(), planes.data_ptr(),
+        rc = lib.avcer_jpeg_decode(raw.data_ptr(), meta.data_ptr(), m, bits.data_ptr(), vals.data_ptr(), qt.data_ptr(),
+                                   pre.data_ptr(), coef_total, pix, data.data_ptr(), dlens.data_ptr(), coefs.data_ptr(), planes.data_ptr(),
                                    out.data_ptr(), status.data_ptr(), ctypes.c_void_p(stream))
         _lib.check(rc)
         if PROFILE is not None:

@@ -104,7 +104,10 @@ jpeg_unstuff_kernel(const unsigned char* __restrict__ raw, const JpegImage* __re
     if (threadIdx.x == 0) base_s += total;
     __syncthreads();
   }
-  if (threadIdx.x == 0) lens[img] = base_s;
+  if (threadIdx.x == 0) {
+    lens[img] = base_s;
+    for (long long i = base_s; i < ((base_s + 3) & ~3ll) + 4 && i < len + 4; ++i) dst[i] = 0;   // the bit reader loads whole words
+  }
 }
 
 // bits: [4][16] code counts per length, vals: [4][256] symbols; table order DC0, AC0, DC1, AC1

@@ -119,6 +119,18 @@ def unstuff(data: bytes) -> bytes:
 
 
 _header_cache = {}       # header bytes (SOI .. end of the SOS segment) -> ParsedJpeg without data
+_stage_bufs = {}         # device -> pinned uint8 staging buffer (grow-only)
+_stage_events = {}       # device -> event recorded after the last H2D copy out of the staging buffer
+
+
+def _staging(dev: torch.device, nbytes: int) -> torch.Tensor:
+    buf = _stage_bufs.get(dev)
+    if buf is None or buf.numel() < nbytes:
+        buf = _stage_bufs[dev] = torch.empty(max(nbytes, 1 << 20) * 5 // 4, dtype=torch.uint8, pin_memory=True)
+        _stage_events[dev] = torch.cuda.Event()
+    else:
+        _stage_events[dev].synchronize()          # the previous batch's copy has left the buffer
+    return buf
 
 
 def _parse_cached(f: bytes, last):
@@ -145,13 +157,14 @@ def decode_batch(files: Sequence[bytes], device, align_out: int = 16) -> Tuple[t
     n = len(files)
     if n == 0:
         return torch.zeros(16, dtype=torch.uint8, device=dev), np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32)
-    heads, segs = [], []
+    heads, starts, ends = [], [], []
     last = None
     for f in files:
         last = _parse_cached(f, last)
         heads.append(last)
         end = f.rfind(b"\xff\xd9")
-        segs.append(f[len(last[0]): end if end >= len(last[0]) else len(f)])
+        starts.append(len(last[0]))
+        ends.append(end if end >= len(last[0]) else len(f))
     heights = np.array([h[1].height for h in heads], dtype=np.int32)
     widths = np.array([h[1].width for h in heads], dtype=np.int32)
     hs = np.array([h[1].hs for h in heads], dtype=np.int32)
@@ -180,7 +193,7 @@ def decode_batch(files: Sequence[bytes], device, align_out: int = 16) -> Tuple[t
 
         qy = np.array([qslot(heads[i][1].qt_y) for i in idx], dtype=np.int32)
         qc = np.array([qslot(heads[i][1].qt_c) for i in idx], dtype=np.int32)
-        lens = np.array([len(segs[i]) for i in idx], dtype=np.int64)
+        lens = np.array([ends[i] - starts[i] for i in idx], dtype=np.int64)
         lens4 = (lens + 3) // 4 * 4
         w, h, s = widths[idx].astype(np.int64), heights[idx].astype(np.int64), hs[idx].astype(np.int64)
         mw, mh = -(-w // (8 * s)), -(-h // (8 * s))
@@ -195,8 +208,17 @@ def decode_batch(files: Sequence[bytes], device, align_out: int = 16) -> Tuple[t
         imgs["qt_y"], imgs["qt_c"] = qy, qc
         prefix = np.concatenate([[0], np.cumsum(w * h)[:-1]]).astype(np.int64)
         coef_total, pix = int(blocks.sum()), int((w * h).sum())
-        pad = [b"\x00" * int(p) for p in (lens4 - lens)]
-        raw = torch.frombuffer(bytearray(b"".join(x for i, p in zip(idx, pad) for x in (segs[i], p)) + b"\x00" * 8), dtype=torch.uint8).to(dev)
+        # the entropy-coded segments go straight from the file buffers into one pinned staging buffer (one host copy, one H2D)
+        total = int(lens4.sum()) + 8
+        stage = _staging(dev, total)
+        stage_np = stage.numpy()
+        doff = imgs["data_off"]
+        for k, i in enumerate(idx):
+            o = int(doff[k])
+            stage_np[o: o + int(lens[k])] = np.frombuffer(files[i], dtype=np.uint8, count=int(lens[k]), offset=starts[i])
+        raw = torch.empty(total, dtype=torch.uint8, device=dev)
+        raw.copy_(stage[:total], non_blocking=True)
+        _stage_events[dev].record(torch.cuda.current_stream(dev))
         data = torch.empty_like(raw)
         dlens = torch.empty(m, dtype=torch.int64, device=dev)
         meta = torch.from_numpy(imgs.view(np.uint8).reshape(-1)).to(dev)

@@ -106,7 +106,7 @@ jpeg_unstuff_kernel(const unsigned char* __restrict__ raw, const JpegImage* __re
   }
   if (threadIdx.x == 0) {
     lens[img] = base_s;
-    for (long long i = base_s; i < ((base_s + 3) & ~3ll) + 4 && i < len + 4; ++i) dst[i] = 0;   // the bit reader loads whole words
+    for (long long i = base_s; i < ((base_s + 3) & ~3ll); ++i) dst[i] = 0;   // the bit reader loads whole words (stays inside this image's slot)
   }
 }
 

@@ -1,5 +1,5 @@
 """Representative hot-path launches for `ncu --set full` (two launches each; profile with
--k regex:'tc_gemm|conv3x3|stem_pool|attention_tc|preprocess_identity|fuse_compound|w2v_conv0|layernorm')."""
+-k regex:'tc_gemm|conv3x3|stem_pool|attention_tc|preprocess_identity|fuse_compound|w2v_conv0|layernorm|jpeg_')."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -31,6 +31,8 @@ for _ in range(2):
     ops.preprocess(crops, 1024, xin, 1)                                  # K1 at 1024 crops
 for _ in range(2):
     ops.stem_pool(xin[:B], net.w["stem_packed"], net.w["stem"].bias)     # fused stem + pool
+for _ in range(2):
+    ops.stem_pool_u8(crops[:B], net.w["stem_packed"], net.w["stem"].bias)   # K1 fused into the stem (measured slower: why?)
 conv(B, 55, 55, 64, 64, 3)                   # l1.c2  halo 3x3, resident weights
 conv(B, 28, 28, 128, 128, 3)                 # l2.c2  halo 3x3, streamed weights
 conv(B, 14, 14, 256, 256, 3)                 # l3.c2  two-SM implicit GEMM (MMA bound)
@@ -55,5 +57,11 @@ n = 1_500_000
 ps = [torch.softmax(torch.randn(n, 7, device=dev), 1).contiguous() for _ in range(3)]
 for _ in range(2):
     ops.fuse_compound(ps[0], ps[1], ps[2], gwm.class_weights(gwm.weights_3), [1, 1, 1], False, True)
+# baseline-JPEG decode of 1500 crops 224x224 (un-stuff, Huffman, IDCT, colour)
+import cv2
+from avcer_b200 import jpeg
+files = [cv2.imencode(".jpg", c)[1].tobytes() for c in syn.make_crops(3, 30)] * 50
+for _ in range(2):
+    jpeg.decode_batch(files, dev)
 torch.cuda.synchronize()
 print("prof_kernels done")

@@ -116,7 +116,7 @@ constexpr int HUFF_THREADS = 32;      // one warp per block: a batch of 1 500 cr
 __global__ void __launch_bounds__(HUFF_THREADS)
 jpeg_huffman_kernel(const unsigned char* __restrict__ data, const JpegImage* __restrict__ imgs, int n,
                     const long long* __restrict__ lens, const unsigned char* __restrict__ bits,
-                    const unsigned char* __restrict__ vals, short* __restrict__ coefs, int* __restrict__ status) {
+                    const unsigned char* __restrict__ vals, short* __restrict__ coefs, int* __restrict__ status, int ipw) {
   __shared__ HuffTab tabs[4];
   // ---- expand the four tables (every thread block builds its own copy; ~4 K entries)
   for (int t = 0; t < 4; ++t) {
@@ -144,7 +144,11 @@ jpeg_huffman_kernel(const unsigned char* __restrict__ data, const JpegImage* __r
   }
   __syncthreads();
 
-  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  // `ipw` images per warp (lanes >= ipw idle): a small batch is spread over more warps, so that every SM has work, the
+  // lanes of a warp diverge less (a block costs the maximum symbol count over the warp's images) and fewer lanes' cache
+  // misses serialise on one warp.  ipw = 32 once the batch is large enough to fill the machine anyway.
+  if ((int)threadIdx.x >= ipw) return;
+  const int img = blockIdx.x * ipw + threadIdx.x;
   if (img >= n) return;
   const JpegImage im = imgs[img];
   const unsigned int* words = reinterpret_cast<const unsigned int*>(data + im.data_off);
@@ -152,10 +156,12 @@ jpeg_huffman_kernel(const unsigned char* __restrict__ data, const JpegImage* __r
   long long wi = 0;
   unsigned long long bb = 0;      // bit buffer, MSB-aligned content in the low `nb` bits
   int nb = 0;
+  unsigned int ahead = n_words > 0 ? __ldg(words) : 0u;       // the next word is always already on its way
   auto refill = [&]() {           // keep at least 32 valid bits (zero bits past the end, like libjpeg's padding)
     if (nb <= 32) {
-      unsigned int w = wi < n_words ? __ldg(words + wi) : 0u;
+      unsigned int w = ahead;
       ++wi;
+      ahead = wi < n_words ? __ldg(words + wi) : 0u;
       w = __byte_perm(w, 0, 0x0123);                       // big-endian bit order
       bb = (bb << 32) | w;
       nb += 32;
@@ -387,8 +393,10 @@ extern "C" int avcer_jpeg_decode(const uint8_t* raw, const avcer_jpeg_image* ima
   const JpegImage* imgs = reinterpret_cast<const JpegImage*>(images);
   jpeg_unstuff_kernel<<<n, UNSTUFF_THREADS, 0, st>>>(raw, imgs, data, reinterpret_cast<long long*>(lens), status);
   if (int rc = check_launch("jpeg_unstuff_kernel")) return rc;
-  jpeg_huffman_kernel<<<(n + HUFF_THREADS - 1) / HUFF_THREADS, HUFF_THREADS, 0, st>>>(data, imgs, n, reinterpret_cast<const long long*>(lens),
-                                                                                      huff_bits, huff_vals, coefs, status);
+  int ipw = (n + 4 * num_sms() - 1) / (4 * num_sms());      // aim at >= 4 warps per SM
+  ipw = ipw < 1 ? 1 : ipw > HUFF_THREADS ? HUFF_THREADS : ipw;
+  jpeg_huffman_kernel<<<(n + ipw - 1) / ipw, HUFF_THREADS, 0, st>>>(data, imgs, n, reinterpret_cast<const long long*>(lens), huff_bits,
+                                                                    huff_vals, coefs, status, ipw);
   if (int rc = check_launch("jpeg_huffman_kernel")) return rc;
   jpeg_idct_kernel<<<(unsigned)((total_blocks + 31) / 32), 256, 0, st>>>(coefs, imgs, n, total_blocks, qtables, planes);
   if (int rc = check_launch("jpeg_idct_kernel")) return rc;

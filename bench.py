@@ -452,6 +452,35 @@ def main():
                            "ms": t, "algorithmic": unit_desc, "l2_policy": "working set larger than L2; L2 flushed before the 8-launch graph replay",
                            "peak_source": f"{peaks['source']} HBM copy"}
         del ps, lab, xin, flush, flush2
+        # baseline-JPEG decode of the crops on the GPU (the reference: cv2.imread per frame on one core)
+        try:
+            import cv2
+
+            from avcer_b200 import jpeg as ajpeg
+
+            base = syn.make_crops(3, 30)
+            files = [cv2.imencode(".jpg", base[i % 30])[1].tobytes() for i in range(1500)]
+            ajpeg.decode_batch(files, dev)
+            torch.cuda.synchronize()
+            walls, devs = [], []
+            for _ in range(3):
+                ajpeg.PROFILE = []
+                t0 = time.perf_counter()
+                ajpeg.decode_batch(files, dev)
+                torch.cuda.synchronize()
+                walls.append((time.perf_counter() - t0) * 1e3)
+                devs.append(sum(a.elapsed_time(b) for a, b in ajpeg.PROFILE))
+            ajpeg.PROFILE = None
+            t0 = time.perf_counter()
+            for f in files[:100]:
+                cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_COLOR)
+            t_cv = (time.perf_counter() - t0) / 100
+            micro["jpeg_decode_1500_crops"] = {"bound": "latency (one thread per image in the Huffman kernel)", "crops_per_s_wall": 1500 / min(walls) * 1e3,
+                                               "crops_per_s_kernels": 1500 / min(devs) * 1e3, "ms_wall": min(walls), "ms_kernels": min(devs),
+                                               "bytes_per_file": sum(map(len, files)) / 1500, "cv2_imdecode_crops_per_s_one_core": 1 / t_cv,
+                                               "parity": "bit-identical to cv2.imread (tests/test_gpu_preprocess.py)"}
+        except Exception as e:  # pragma: no cover  (cv2 missing: the figure is optional)
+            micro["jpeg_decode_1500_crops"] = {"skipped": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
         if world > 1:

@@ -261,7 +261,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const StemPoolParams p
 // Epilogue (bias, ReLU, 4-row ring, 3x3/2 max-pool) is shared with stem_pool_kernel: outputs are bit-identical.
 struct StemPoolU8Cfg {
   static constexpr int STRIP = 2048;
-  static constexpr int RING_ROWS = 16;
+  static constexpr int RING_ROWS = 16;               // power of two: slot = g & 15, use count = g >> 4
   static constexpr int A_BYTES = RING_ROWS * STRIP;
   static constexpr int B_BYTES = 7 * 4096;
   static constexpr int ROW = 112 * 128;
@@ -340,15 +340,15 @@ stem_pool_u8_kernel(const uint8_t* __restrict__ crops, const StemPoolParams p) {
     if (lane == 0) {
       mbar_arrive_expect_tx(bfull_bar, Cfg::B_BYTES);           // filter bank: constant, fetched once
       bulk_load_1d(b_base, p.w_packed, Cfg::B_BYTES, bfull_bar);
-      long long g = 0;
+      uint32_t g = 0;                                           // ring-row counter (32-bit unsigned: slot = g & 15, use = g >> 4)
       for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
         int n, j0, rows;
         unit_geom(unit, n, j0, rows);
         const int p0 = 4 * j0, np = 4 * rows + 7;               // padded rows 4*j0 .. 4*(j0+rows)+6 (stem rows 2*j0 ..)
         const uint8_t* img = crops + (size_t)n * (224 * 224 * 3);
         for (int i = 0; i < np; ++i, ++g) {
-          const int slot = (int)(g % Cfg::RING_ROWS);
-          mbar_wait(rawempty_bar(slot), ((uint32_t)(g / Cfg::RING_ROWS) & 1u) ^ 1u);
+          const int slot = (int)(g & (Cfg::RING_ROWS - 1));
+          mbar_wait(rawempty_bar(slot), ((g >> 4) & 1u) ^ 1u);
           const int y = p0 + i - 2;                             // image row of padded row p0 + i
           if (y >= 0 && y < 224) {
             mbar_arrive_expect_tx(rawfull_bar(slot), 672u);
@@ -366,21 +366,21 @@ stem_pool_u8_kernel(const uint8_t* __restrict__ crops, const StemPoolParams p) {
     // is the expensive part: per row and per lane it left the first versions at 215-240 us against 164 + 33 us).
     const int cw = warp < 4 ? warp - 2 : warp - 10;             // 0..3
     const float m0 = 91.4953f, m1 = 103.8827f, m2 = 131.0912f;  // data/utils.py:27-29 (B, G, R)
-    long long g0 = 0;                                           // ring row of the unit's first padded row
-    long long pass = 0;
+    uint32_t g0 = 0;                                            // ring row of the unit's first padded row
+    uint32_t pass = 0;
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
       int n, j0, rows;
       unit_geom(unit, n, j0, rows);
       const int p0 = 4 * j0;
       const int npass = 4 + 2 * rows;
       for (int k = 0; k < npass; ++k, ++pass) {
-        if ((int)(pass % Cfg::CONV_WARPS) != cw) continue;
+        if ((int)(pass & (Cfg::CONV_WARPS - 1)) != cw) continue;
         const int i0 = k < 4 ? 2 * k : 7 + 2 * (k - 4);         // first row of the pass inside the unit
         const int nr = k == 3 ? 1 : 2;
         for (int rr = 0; rr < nr; ++rr) {
-          const long long g = g0 + i0 + rr;
-          const int slot = (int)(g % Cfg::RING_ROWS);
-          const uint32_t use = (uint32_t)(g / Cfg::RING_ROWS);
+          const uint32_t g = g0 + i0 + rr;
+          const int slot = (int)(g & (Cfg::RING_ROWS - 1));
+          const uint32_t use = g >> 4;
           const int y = p0 + i0 + rr - 2;                       // image row of padded row p0 + i
           const bool real = y >= 0 && y < 224;
           mbar_wait(rawfull_bar(slot), use & 1u);
@@ -417,7 +417,7 @@ stem_pool_u8_kernel(const uint8_t* __restrict__ crops, const StemPoolParams p) {
         fence_proxy_async();                                    // the pass's strip stores -> visible to the UMMA reads
         __syncwarp();
         if (lane == 0)
-          for (int rr = 0; rr < nr; ++rr) mbar_arrive(full_bar((int)((g0 + i0 + rr) % Cfg::RING_ROWS)));
+          for (int rr = 0; rr < nr; ++rr) mbar_arrive(full_bar((int)((g0 + i0 + rr) & (Cfg::RING_ROWS - 1))));
       }
       g0 += 4 * rows + 7;
     }
@@ -427,7 +427,7 @@ stem_pool_u8_kernel(const uint8_t* __restrict__ crops, const StemPoolParams p) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
       mbar_wait(bfull_bar, 0);
       tc_fence_after();
-      long long g0 = 0;                                          // ring-row counter of the unit's first padded row
+      uint32_t g0 = 0;                                           // ring-row counter of the unit's first padded row (32-bit unsigned)
       int local = 0;
       for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
         int n, j0, rows;
@@ -439,15 +439,15 @@ stem_pool_u8_kernel(const uint8_t* __restrict__ crops, const StemPoolParams p) {
           tc_fence_after();
           // rows g0+2r .. g0+2r+6; all but the two newest were waited for by the previous stem row
           for (int ky = (r == 0 ? 0 : 5); ky < 7; ++ky) {
-            const long long g = g0 + 2 * r + ky;
-            mbar_wait(full_bar((int)(g % Cfg::RING_ROWS)), (uint32_t)(g / Cfg::RING_ROWS) & 1u);
+            const uint32_t g = g0 + 2 * r + ky;
+            mbar_wait(full_bar((int)(g & (Cfg::RING_ROWS - 1))), (g >> 4) & 1u);
           }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * 64;
 #pragma unroll
           for (int ky = 0; ky < 7; ++ky) {
-            const long long g = g0 + 2 * r + ky;
-            const uint64_t adesc = umma_desc_nosw(a_base + (uint32_t)(g % Cfg::RING_ROWS) * Cfg::STRIP, 16u, 128u);
+            const uint32_t g = g0 + 2 * r + ky;
+            const uint64_t adesc = umma_desc_nosw(a_base + (g & (Cfg::RING_ROWS - 1)) * Cfg::STRIP, 16u, 128u);
             const uint64_t bdesc = umma_desc_nosw(b_base + ky * 4096, 64u * 16u, 128u);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
@@ -455,7 +455,7 @@ stem_pool_u8_kernel(const uint8_t* __restrict__ crops, const StemPoolParams p) {
           }
           // rows that leave the window: two per stem row, all seven after the unit's last stem row
           const int nfree = (r == nrows - 1) ? 7 : 2;
-          for (int f = 0; f < nfree; ++f) umma_commit(empty_bar((int)((g0 + 2 * r + f) % Cfg::RING_ROWS)));
+          for (int f = 0; f < nfree; ++f) umma_commit(empty_bar((int)((g0 + 2 * r + f) & (Cfg::RING_ROWS - 1))));
           umma_commit(tfull_bar(acc));
         }
         g0 += 4 * rows + 7;

@@ -25,7 +25,7 @@ for r in data:
     for k, m in want.items():
         if m not in col:                     # some ncu versions prefix section metrics ("FBSP.TriageCompute.dram__throughput...")
             m = next((h for h in hdr if h.endswith("." + m)), m)
-        if m in col and r[col[m]] != "":
+        if m in col and r[col[m]] not in ("", "no data", "n/a"):
             v = float(r[col[m]].replace(",", ""))
             u = units[col[m]]
             if k.startswith("dram_") and k != "dram_pct":

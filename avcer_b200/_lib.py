@@ -12,6 +12,8 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int16, c_int32
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # AVCER_LIB: alternative build of the same library (A/B measurements of kernel changes); default is the in-tree build
 LIB_PATH = os.environ.get("AVCER_LIB") or os.path.join(_HERE, "libavcer_b200.so")
+# the same sources compiled with -DAVCER_HALF: IEEE half as the 16-bit storage type (precision "fp16")
+LIB_PATH_FP16 = os.path.join(_HERE, "libavcer_b200_fp16.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
@@ -59,6 +61,7 @@ class ContractDesc(ctypes.Structure):
 _SIGNATURES = {
     "avcer_last_error": (c_char_p, []),
     "avcer_version": (c_int, []),
+    "avcer_storage_type": (c_char_p, []),
     "avcer_device_check": (c_int, []),
     "avcer_num_sms": (c_int, []),
     "avcer_set_sm_limit": (c_int, [c_int]),
@@ -101,26 +104,35 @@ _SIGNATURES = {
     "avcer_cast": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
 }
 
-_lib = None
+_libs = {}
 
 
-def load() -> ctypes.CDLL:
-    """Load the shared library and bind every exported symbol (raises if it is missing)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def load(kind: str = "bf16") -> ctypes.CDLL:
+    """Load a build of the shared library and bind every exported symbol (raises if it is missing).
+    kind "bf16": libavcer_b200.so (bfloat16 storage; also every fp32 / fp64 / integer kernel); kind "fp16":
+    libavcer_b200_fp16.so (the same kernels with IEEE half storage)."""
+    lib = _libs.get(kind)
+    if lib is not None:
+        return lib
+    path = LIB_PATH if kind == "bf16" else LIB_PATH_FP16
+    if not os.path.exists(path):
         raise AvcerError(
-            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(or `make -C avcer_b200/csrc`). avcer_b200 has no CPU fallback."
         )
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    if lib.avcer_storage_type().decode() != kind:
+        raise AvcerError(f"{path} stores {lib.avcer_storage_type().decode()}, expected {kind}")
+    _libs[kind] = lib
     return lib
+
+
+def loaded():
+    return list(_libs.values())
 
 
 def exported_symbols():

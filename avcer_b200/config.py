@@ -31,7 +31,7 @@ def jpeg_decoder() -> str:
 
 
 def set_precision(precision: str) -> None:
-    assert precision in ("bf16", "fp32")
+    assert precision in ("bf16", "fp16", "fp32")
     _state["precision"] = precision
     reset()
 

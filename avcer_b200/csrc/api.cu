@@ -32,6 +32,8 @@ extern "C" const char* avcer_last_error(void) { return avcer::g_err; }
 
 extern "C" int avcer_version(void) { return 100; }
 
+extern "C" const char* avcer_storage_type(void) { return AVCER_STORAGE_NAME; }
+
 extern "C" int avcer_device_check(void) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);

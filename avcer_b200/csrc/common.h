@@ -2,12 +2,32 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 
 #include "../../include/avcer_b200.h"
+
+// ---- 16-bit storage type of this build.  The library is compiled twice from the same sources: libavcer_b200.so stores
+// activations / weights as bfloat16 (the default "bf16" precision), libavcer_b200_fp16.so (-DAVCER_HALF) as IEEE half
+// ("fp16" precision: same kernels, same throughput, 11 instead of 8 mantissa bits -- the wide-init probability error drops
+// from 6-8e-3 to ~1e-3; the price is the 65504 range, which the path's activations, <= ~200, do not come near).
+// In the half build the bf16 spellings below are redirected to their half twins, so the kernel sources are shared verbatim;
+// the few places that depend on the bit layout (UMMA instruction descriptor, mma.sync type, a shift-based unpack) test
+// AVCER_HALF explicitly.  The C ABI is unchanged: dtype code AVCER_BF16 means "the 16-bit storage type of this library".
+#ifdef AVCER_HALF
+#define __nv_bfloat16 __half
+#define __nv_bfloat162 __half2
+#define __floats2bfloat162_rn __floats2half2_rn
+#define __bfloat1622float2 __half22float2
+#define __float2bfloat16_rn __float2half_rn
+#define __bfloat162float __half2float
+#define AVCER_STORAGE_NAME "fp16"
+#else
+#define AVCER_STORAGE_NAME "bf16"
+#endif
 
 namespace avcer {
 

@@ -35,7 +35,12 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
   uint32_t estr[5] = {1, 1, 1, 1, 1};
   if (elem_strides)
     for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims,
+#ifdef AVCER_HALF
+  constexpr CUtensorMapDataType kElem = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+#else
+  constexpr CUtensorMapDataType kElem = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+#endif
+  CUresult r = fn(m, kElem, rank, const_cast<void*>(base), dims,
                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -291,8 +291,13 @@ __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr, uint32_t lbo_
 
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, shape M x N.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  // bits 4-5: accumulator format (1 = f32); bits 7-9 / 10-12: A / B element format (1 = bf16, 0 = f16: the AVCER_HALF build)
+#ifdef AVCER_HALF
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+#else
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
+#endif
 }
 
 }  // namespace avcer

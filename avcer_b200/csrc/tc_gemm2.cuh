@@ -331,8 +331,14 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 ld_shared_v4(rbuf + row_off + (((cc * 4 + i) ^ (lane & 7)) << 4), u);
                 const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
+                for (int e = 0; e < 4; ++e) {
+#ifdef AVCER_HALF
+                  const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                  add_f32x2(f[i * 8 + e * 2], f[i * 8 + e * 2 + 1], t.x, t.y);
+#else
                   add_f32x2(f[i * 8 + e * 2], f[i * 8 + e * 2 + 1], __uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+#endif
+                }
               }
               uint4 o;
               __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);

@@ -5,7 +5,8 @@ libavcer_b200 kernel launches (host orchestration only -- no torch math on the d
   VDNet : 2-layer LSTM over sliding windows      (reference src/architectures/video.py:169-185)
   ANet  : wav2vec2-large-robust + 2 TL + head    (reference src/architectures/audio_8_cl.py:131-190)
 
-precision "bf16": bf16 storage, tcgen05 tensor-core contractions with fp32 accumulation.
+precision "bf16": bf16 storage, tcgen05 tensor-core contractions with fp32 accumulation (libavcer_b200.so).
+precision "fp16": the same kernels built with IEEE half storage (libavcer_b200_fp16.so): same speed, 11 mantissa bits.
 precision "fp32": fp32 storage, SIMT contractions (the tolerance-check mode of the north star).
 """
 from __future__ import annotations
@@ -17,6 +18,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import ops, weights
+from . import _lib
 from ._lib import require_device
 
 PAD_H, PAD = ops.PAD_H, ops.PAD_W      # 232 rows x 240-pixel pitch of the zero-bordered stem input
@@ -74,9 +76,16 @@ class GraphedForward:
 def _dtype(precision: str) -> torch.dtype:
     if precision == "bf16":
         return torch.bfloat16
+    if precision == "fp16":
+        return torch.float16
     if precision == "fp32":
         return torch.float32
-    raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+    raise ValueError(f"precision must be 'bf16', 'fp16' or 'fp32', got {precision!r}")
+
+
+def _tc(dtype: torch.dtype) -> bool:
+    """16-bit storage = the tensor-core path (bf16 or fp16 build of the library)."""
+    return dtype in (torch.bfloat16, torch.float16)
 
 
 class VSNet:
@@ -86,6 +95,7 @@ class VSNet:
     def __init__(self, state_dict: Dict[str, torch.Tensor], precision: str = "bf16", device: str = "cuda:0"):
         require_device()
         self.dtype = _dtype(precision)
+        _lib.load("fp16" if self.dtype == torch.float16 else "bf16")       # the matching build of the library, loaded up front
         self.precision = precision
         self.device = torch.device(device)
         self.w = weights.pack_vs(state_dict, self.device, self.dtype)
@@ -95,7 +105,7 @@ class VSNet:
 
     @property
     def input_layout(self) -> int:
-        return 1 if self.dtype == torch.bfloat16 else 2
+        return 1 if _tc(self.dtype) else 2
 
     def alloc_input(self, n: int) -> torch.Tensor:
         """Zero-bordered input buffer; the border is written once here, K1 only fills the interior."""
@@ -105,7 +115,7 @@ class VSNet:
         n = x.shape[0]
         st = self.w["stem"]
         y = torch.empty((n, 112, 112, 64), device=self.device, dtype=self.dtype)
-        if self.dtype == torch.bfloat16:
+        if _tc(self.dtype):
             # Strip mode: one padded image row (240 px x 4 ch = 1920 B = 15 x 128 B) is fetched once per (oy, ky);
             # output ox reads the 32 elements starting 16 B * ox into it (overlap expressed in the MMA descriptor).
             ops.contract(a=x, a_dim=(64, PAD * 4 // 64, 112, n, 7), a_stride=(1, 64, 2 * PAD * 4, PAD_H * PAD * 4, PAD * 4),
@@ -128,7 +138,7 @@ class VSNet:
     @property
     def k1_fused(self) -> bool:
         """bf16 + fused stem: packed 224x224 uint8 crops can enter the network directly (forward_u8)."""
-        return self.dtype == torch.bfloat16 and self.fused_stem and self.fused_shortcut and "conv3_ds" in self.w["blocks"][0]
+        return _tc(self.dtype) and self.fused_stem and self.fused_shortcut and "conv3_ds" in self.w["blocks"][0]
 
     def stem_u8(self, crops_u8: torch.Tensor, cat: Optional[torch.Tensor] = None) -> torch.Tensor:
         """K1 + stem + max-pool in one kernel (avcer_stem_pool_u8): uint8 [n,224,224,3] BGR crops -> the left 64 channels of
@@ -145,7 +155,7 @@ class VSNet:
     def forward(self, x: torch.Tensor, taps: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         assert x.shape[1:] == (PAD_H, PAD, 4) and x.dtype == self.dtype
         cat = None
-        if taps is None and self.dtype == torch.bfloat16 and self.fused_stem:
+        if taps is None and _tc(self.dtype) and self.fused_stem:
             if self.fused_shortcut and "conv3_ds" in self.w["blocks"][0]:
                 cat = torch.empty((x.shape[0], 55, 55, 128), device=self.device, dtype=self.dtype)
                 y = ops.stem_pool(x, self.w["stem_packed"], self.w["stem"].bias, out=cat[..., :64])
@@ -165,7 +175,7 @@ class VSNet:
         left 64 channels hold it (layer1.0's K-concatenated layout)."""
         cat = y if is_cat and y.shape[-1] == 128 else None
         blocks = self.w["blocks"]
-        fuse = taps is None and self.dtype == torch.bfloat16 and self.fused_shortcut
+        fuse = taps is None and _tc(self.dtype) and self.fused_shortcut
         sampled = False                 # `cat[:, :cin]` already holds the stride-2 sampled input of the coming block
         for bi, blk in enumerate(blocks):
             if bi == 0 and cat is not None:
@@ -245,6 +255,7 @@ class VDNet:
     def __init__(self, state_dict: Dict[str, torch.Tensor], precision: str = "bf16", device: str = "cuda:0"):
         require_device()
         self.dtype = _dtype(precision)
+        _lib.load("fp16" if self.dtype == torch.float16 else "bf16")       # the matching build of the library, loaded up front
         self.device = torch.device(device)
         self.w = weights.pack_vd(state_dict, self.device, self.dtype)
 
@@ -260,7 +271,7 @@ class VDNet:
         w = self.w
         split = w["split"]
         s = 3 if split else 1
-        x = ops.split_bf16x3(feats) if split else feats
+        x = ops.split_bf16x3(feats, dtype=self.dtype) if split else feats
         xproj = ops.linear(x, w["w_ih1"], w["b1"], out_dtype=torch.float32)                 # [U, 2048]
         hcat = torch.zeros((m, s * 768), device=self.device, dtype=self.dtype)               # [h1_t | h2_{t-1}] (each x3 when split)
         c1 = torch.empty((m, 512), device=self.device, dtype=torch.float32)
@@ -288,6 +299,7 @@ class ANet:
     def __init__(self, state_dict: Dict[str, torch.Tensor], precision: str = "bf16", device: str = "cuda:0"):
         require_device()
         self.dtype = _dtype(precision)
+        _lib.load("fp16" if self.dtype == torch.float16 else "bf16")       # the matching build of the library, loaded up front
         self.device = torch.device(device)
         self.w = weights.pack_audio(state_dict, self.device, self.dtype)
         self.num_classes = self.w["num_classes"]
@@ -391,7 +403,7 @@ class ANet:
         """ExprModelV1's nn.GRU(1024 -> 256, 2 layers, batch_first) from zero state (audio_8_cl.py:23-29,63): per layer one
         contraction for the input projections of all time steps, then t recurrent steps of (h W_hh^T + b_hh, gate math).
         x: [b*t, Cin] rows in (window, time) order -> [b*t, 256]."""
-        split = self.dtype == torch.bfloat16
+        split = _tc(self.dtype)
         s = 3 if split else 1
         for L in self.w["gru"]:
             xg = ops.linear(x, L["w_ih"], L["b_ih"], out_dtype=torch.float32)                  # [b*t, 768]

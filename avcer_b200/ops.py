@@ -76,12 +76,15 @@ class sm_limit:
 
     def __enter__(self):
         if self.n:
-            _check(_lib.load().avcer_set_sm_limit(self.n))
+            _lib.load()
+            for lib in _lib.loaded():                 # every build of the library keeps its own (thread-local) limit
+                _check(lib.avcer_set_sm_limit(self.n))
         return self
 
     def __exit__(self, *exc):
         if self.n:
-            _check(_lib.load().avcer_set_sm_limit(0))
+            for lib in _lib.loaded():
+                _check(lib.avcer_set_sm_limit(0))
         return False
 
 
@@ -89,8 +92,17 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def _L(*tensors: Optional[torch.Tensor]):
+    """The library build that matches the operands: libavcer_b200_fp16.so as soon as one of them is float16 (precision
+    "fp16"), else libavcer_b200.so (bfloat16 storage; also every fp32 / fp64 / integer kernel)."""
+    for t in tensors:
+        if t is not None and t.dtype == torch.float16:
+            return _lib.load("fp16")
+    return _lib.load("bf16")
+
+
 def dtype_code(dt: torch.dtype) -> int:
-    if dt == torch.bfloat16:
+    if dt in (torch.bfloat16, torch.float16):          # "the 16-bit storage type of the library" (_L picks the matching build)
         return BF16
     if dt == torch.float32:
         return F32
@@ -142,14 +154,15 @@ def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], 
     d.res_after_act = int(res_after_act)
     d.dtype = code
     d.out_f32 = int(code == BF16 and out.dtype == torch.float32)
+    assert wt.dtype == a.dtype and (residual is None or residual.dtype == a.dtype)
     k_real = algo_k if algo_k is not None else taps_w * taps_h * cin
     rows = W * H * NB
     with _Timed("contract_bf16" if code == BF16 else "contract_f32", 2.0 * rows * cout * k_real) as tm:
-        _check(_lib.load().avcer_contract(ctypes.byref(d), _stream()))
+        _check(_L(a, out).avcer_contract(ctypes.byref(d), _stream()))
         if PROFILE is not None:
             # exact kernel + algorithmic bytes of this launch (operands + output once, at their storage width)
             esz = a.element_size()
-            tm.tag = "contract:" + CONTRACT_KERNELS.get(_lib.load().avcer_last_contract_kernel(), "?")
+            tm.tag = "contract:" + CONTRACT_KERNELS.get(_L(a, out).avcer_last_contract_kernel(), "?")
             tm.bytes = float(esz * (rows * (k_real if taps_w * taps_h == 1 else cin) + cout * taps_w * taps_h * cin + (rows * cout if residual is not None else 0))
                              + out.element_size() * rows * cout)
     return out
@@ -183,7 +196,7 @@ def conv2d_nhwc(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor],
         a_dim = (c, wo, ho, n, 1)                        # a strided 1x1 conv is a view of every stride-th pixel
         a_stride = (1, stride * c, stride * w * c, h * w * c, n * h * w * c)
     else:
-        assert x.dtype == torch.bfloat16, "strided k x k convs: bf16 path only (TMA traversal stride)"
+        assert x.dtype != torch.float32, "strided k x k convs: tensor-core path only (TMA traversal stride)"
         a_dim = (c, w, h, n, 1)                          # full-resolution input walked with traversal stride `stride`
         a_stride = (1, c, w * c, h * w * c, n * h * w * c)
         a_step = stride
@@ -226,7 +239,7 @@ def preprocess(src: torch.Tensor, n: int, dst: torch.Tensor, layout: int, *, off
                maps: Optional[torch.Tensor] = None) -> torch.Tensor:
     """src: flat uint8 device buffer of BGR HWC crops. layout 0: f32 NCHW, 1: bf16 NHWC4 padded, 2: f32 NHWC4 padded."""
     _cuda(src, "src")
-    lib = _lib.load()
+    lib = _L(dst)
     if heights is not None and maps is None:
         maps = torch.empty((n, 2, 224), device=src.device, dtype=torch.int16)
         check(lib.avcer_preprocess_maps(heights.data_ptr(), widths.data_ptr(), n, maps.data_ptr(), _stream()))
@@ -328,14 +341,14 @@ def stem_pool(x: torch.Tensor, wt_packed: torch.Tensor, bias: torch.Tensor, out:
     `out`: optional channel slice [n,55,55,64] of a wider contiguous [n,55,55,C] buffer (pixel pitch C)."""
     _cuda(x, "x")
     n = x.shape[0]
-    assert x.dtype == torch.bfloat16 and x.is_contiguous() and tuple(x.shape[1:]) == (PAD_H, PAD_W, 4)
+    assert x.dtype in (torch.bfloat16, torch.float16) and x.is_contiguous() and tuple(x.shape[1:]) == (PAD_H, PAD_W, 4)
     if out is None:
-        out = torch.empty((n, 55, 55, 64), device=x.device, dtype=torch.bfloat16)
+        out = torch.empty((n, 55, 55, 64), device=x.device, dtype=x.dtype)
     pitch = out.stride(2)
-    assert out.dtype == torch.bfloat16 and tuple(out.shape) == (n, 55, 55, 64) and out.stride(3) == 1
+    assert out.dtype == x.dtype and tuple(out.shape) == (n, 55, 55, 64) and out.stride(3) == 1
     assert out.stride(1) == 55 * pitch and out.stride(0) == 55 * 55 * pitch
     with _Timed("contract_bf16", 2.0 * n * 112 * 112 * 64 * 147):        # 7x7x3 real taps (SURVEY.md section 8d)
-        _check(_lib.load().avcer_stem_pool_ld(x.data_ptr(), wt_packed.data_ptr(), bias.data_ptr(), n, out.data_ptr(), pitch, _stream()))
+        _check(_L(x).avcer_stem_pool_ld(x.data_ptr(), wt_packed.data_ptr(), bias.data_ptr(), n, out.data_ptr(), pitch, _stream()))
     return out
 
 
@@ -348,11 +361,11 @@ def stem_pool_u8(crops: torch.Tensor, wt_packed: torch.Tensor, bias: torch.Tenso
     if out is None:
         out = torch.empty((n, 55, 55, 64), device=crops.device, dtype=torch.bfloat16)
     pitch = out.stride(2)
-    assert out.dtype == torch.bfloat16 and tuple(out.shape) == (n, 55, 55, 64) and out.stride(3) == 1
+    assert out.dtype in (torch.bfloat16, torch.float16) and tuple(out.shape) == (n, 55, 55, 64) and out.stride(3) == 1
     assert out.stride(1) == 55 * pitch and out.stride(0) == 55 * 55 * pitch
     # K1's algorithmic bytes are part of this launch; the tensor work is the stem's (7x7x3 real taps)
     with _Timed("contract_bf16", 2.0 * n * 112 * 112 * 64 * 147):
-        _check(_lib.load().avcer_stem_pool_u8(crops.data_ptr(), wt_packed.data_ptr(), bias.data_ptr(), n, out.data_ptr(), pitch, _stream()))
+        _check(_L(out).avcer_stem_pool_u8(crops.data_ptr(), wt_packed.data_ptr(), bias.data_ptr(), n, out.data_ptr(), pitch, _stream()))
     return out
 
 
@@ -362,21 +375,21 @@ def subsample_rows(x: torch.Tensor, stride: int, out: torch.Tensor) -> torch.Ten
     n, h, w, c = x.shape
     assert x.is_contiguous() and out.stride(1) == 1 and out.shape[1] == c and out.dtype == x.dtype
     assert out.shape[0] == n * ((h - 1) // stride + 1) * ((w - 1) // stride + 1)
-    check(_lib.load().avcer_subsample_rows(x.data_ptr(), n, h, w, c, stride, out.data_ptr(), out.stride(0), dtype_code(x.dtype), _stream()))
+    check(_L(x).avcer_subsample_rows(x.data_ptr(), n, h, w, c, stride, out.data_ptr(), out.stride(0), dtype_code(x.dtype), _stream()))
     return out
 
 
 def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
     n, h, w, c = x.shape
     y = torch.empty((n, (h - 3) // 2 + 1, (w - 3) // 2 + 1, c), device=x.device, dtype=x.dtype)
-    check(_lib.load().avcer_maxpool3x3s2(x.data_ptr(), n, h, w, c, y.data_ptr(), dtype_code(x.dtype), _stream()))
+    check(_L(x).avcer_maxpool3x3s2(x.data_ptr(), n, h, w, c, y.data_ptr(), dtype_code(x.dtype), _stream()))
     return y
 
 
 def avgpool(x: torch.Tensor) -> torch.Tensor:
     n, h, w, c = x.shape
     y = torch.empty((n, c), device=x.device, dtype=x.dtype)
-    check(_lib.load().avcer_avgpool(x.data_ptr(), n, h * w, c, y.data_ptr(), dtype_code(x.dtype), _stream()))
+    check(_L(x).avcer_avgpool(x.data_ptr(), n, h * w, c, y.data_ptr(), dtype_code(x.dtype), _stream()))
     return y
 
 
@@ -385,7 +398,7 @@ def small_linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], so
     m = w.shape[0]
     assert x.stride(1) == 1 and w.dtype == torch.float32 and w.is_contiguous()
     y = torch.empty((n, m), device=x.device, dtype=torch.float32)
-    check(_lib.load().avcer_small_linear(x.data_ptr(), n, k, x.stride(0), w.data_ptr(), _ptr(b), m, int(softmax), y.data_ptr(),
+    check(_L(x).avcer_small_linear(x.data_ptr(), n, k, x.stride(0), w.data_ptr(), _ptr(b), m, int(softmax), y.data_ptr(),
                                          dtype_code(x.dtype), _stream()))
     return y
 
@@ -395,7 +408,7 @@ def lstm_cell(xproj: Optional[torch.Tensor], xidx: Optional[torch.Tensor], hproj
               h_f32: Optional[torch.Tensor] = None) -> None:
     """split: h_out is the [n, 3*hidden] bf16x3 operand [hi | lo | hi]; h_f32: optional fp32 copy of h [n, hidden]."""
     n = c.shape[0]
-    check(_lib.load().avcer_lstm_cell(_ptr(xproj), _ptr(xidx), _ptr(hproj), c.data_ptr(), h_out.data_ptr(),
+    check(_L(h_out).avcer_lstm_cell(_ptr(xproj), _ptr(xidx), _ptr(hproj), c.data_ptr(), h_out.data_ptr(),
                                       h_out.stride(0), n, hidden, int(first), int(split), _ptr(h_f32), dtype_code(h_out.dtype),
                                       _stream()))
 
@@ -406,19 +419,19 @@ def gru_cell(xg: torch.Tensor, x_row0: int, x_row_stride: int, hg: torch.Tensor,
     n = h_state.shape[0]
     assert xg.dtype == torch.float32 and hg.dtype == torch.float32 and h_state.dtype == torch.float32
     assert xg.is_contiguous() and hg.is_contiguous() and h_state.is_contiguous() and (y is None or y.is_contiguous())
-    check(_lib.load().avcer_gru_cell(xg.data_ptr(), x_row0, x_row_stride, hg.data_ptr(), h_state.data_ptr(), h_out.data_ptr(),
+    check(_L(h_out).avcer_gru_cell(xg.data_ptr(), x_row0, x_row_stride, hg.data_ptr(), h_state.data_ptr(), h_out.data_ptr(),
                                      h_out.stride(0), int(split), _ptr(y), y_row0, y_row_stride, n, hidden, dtype_code(h_out.dtype),
                                      _stream()))
 
 
-def split_bf16x3(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x fp32 [rows, k] -> bf16 [rows, 3k] = [hi | lo | hi] (operand of a bf16x3 contraction)."""
+def split_bf16x3(x: torch.Tensor, out: Optional[torch.Tensor] = None, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """x fp32 [rows, k] -> 16-bit [rows, 3k] = [hi | lo | hi] (operand of a bf16x3 / fp16x3 contraction)."""
     _cuda(x, "x")
     rows, k = x.shape
     assert x.dtype == torch.float32 and x.stride(1) == 1
     if out is None:
-        out = torch.empty((rows, 3 * k), device=x.device, dtype=torch.bfloat16)
-    check(_lib.load().avcer_split_bf16x3(x.data_ptr(), rows, k, x.stride(0), out.data_ptr(), out.stride(0), _stream()))
+        out = torch.empty((rows, 3 * k), device=x.device, dtype=dtype)
+    check(_L(out).avcer_split_bf16x3(x.data_ptr(), rows, k, x.stride(0), out.data_ptr(), out.stride(0), _stream()))
     return out
 
 
@@ -480,7 +493,7 @@ def audio_normalize_windows(wav: torch.Tensor, starts: torch.Tensor, win: int, p
 def w2v_conv0_ln_gelu(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, g: torch.Tensor, be: torch.Tensor,
                       y: torch.Tensor) -> torch.Tensor:
     n, t_in = x.shape
-    check(_lib.load().avcer_w2v_conv0_ln_gelu(x.data_ptr(), n, t_in, w.data_ptr(), b.data_ptr(), g.data_ptr(),
+    check(_L(y).avcer_w2v_conv0_ln_gelu(x.data_ptr(), n, t_in, w.data_ptr(), b.data_ptr(), g.data_ptr(),
                                               be.data_ptr(), y.data_ptr(), y.shape[1], dtype_code(y.dtype), _stream()))
     return y
 
@@ -491,7 +504,7 @@ def layernorm(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, eps: float, *, 
     rows, c = x.shape
     if out is None:
         out = torch.empty((rows, c), device=x.device, dtype=x.dtype)
-    check(_lib.load().avcer_layernorm(x.data_ptr(), rows, c, x.stride(0), _ptr(add), 0 if add is None else add.shape[0],
+    check(_L(x).avcer_layernorm(x.data_ptr(), rows, c, x.stride(0), _ptr(add), 0 if add is None else add.shape[0],
                                       g.data_ptr(), b.data_ptr(), eps, act, out.data_ptr(), out.stride(0),
                                       dtype_code(x.dtype), _stream()))
     return out
@@ -502,7 +515,7 @@ def add_rows(x: torch.Tensor, add: torch.Tensor, out: Optional[torch.Tensor] = N
     assert x.is_contiguous()
     if out is None:
         out = torch.empty_like(x)
-    check(_lib.load().avcer_add_rows(x.data_ptr(), rows, c, add.data_ptr(), add.shape[0], out.data_ptr(),
+    check(_L(x).avcer_add_rows(x.data_ptr(), rows, c, add.data_ptr(), add.shape[0], out.data_ptr(),
                                      dtype_code(x.dtype), _stream()))
     return out
 
@@ -513,25 +526,25 @@ def attention(qkv: torch.Tensor, n: int, t: int, heads: int, dh: int, scale: flo
     assert qkv.is_contiguous()
     if out is None:
         out = torch.empty((n * t, heads * dh), device=qkv.device, dtype=qkv.dtype)
-    check(_lib.load().avcer_attention(qkv.data_ptr(), n, t, heads, dh, scale, out.data_ptr(), dtype_code(qkv.dtype), _stream()))
+    check(_L(qkv).avcer_attention(qkv.data_ptr(), n, t, heads, dh, scale, out.data_ptr(), dtype_code(qkv.dtype), _stream()))
     return out
 
 
 def maxpool1d5_relu(x: torch.Tensor) -> torch.Tensor:
     n, t, c = x.shape
     y = torch.empty((n, t // 5, c), device=x.device, dtype=x.dtype)
-    check(_lib.load().avcer_maxpool1d5_relu(x.data_ptr(), n, t, c, y.data_ptr(), dtype_code(x.dtype), _stream()))
+    check(_L(x).avcer_maxpool1d5_relu(x.data_ptr(), n, t, c, y.data_ptr(), dtype_code(x.dtype), _stream()))
     return y
 
 
 def avgpool1d_relu(x: torch.Tensor) -> torch.Tensor:
     n, t, c = x.shape
     y = torch.empty((n, c), device=x.device, dtype=x.dtype)
-    check(_lib.load().avcer_avgpool1d_relu(x.data_ptr(), n, t, c, y.data_ptr(), dtype_code(x.dtype), _stream()))
+    check(_L(x).avcer_avgpool1d_relu(x.data_ptr(), n, t, c, y.data_ptr(), dtype_code(x.dtype), _stream()))
     return y
 
 
 def cast(x: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
     y = torch.empty(x.shape, device=x.device, dtype=dt)
-    check(_lib.load().avcer_cast(x.data_ptr(), x.numel(), dtype_code(x.dtype), y.data_ptr(), dtype_code(dt), _stream()))
+    check(_L(x, y).avcer_cast(x.data_ptr(), x.numel(), dtype_code(x.dtype), y.data_ptr(), dtype_code(dt), _stream()))
     return y

@@ -93,11 +93,11 @@ def pack_vs(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
     return out
 
 
-def split_bf16x3_weight(w: torch.Tensor) -> torch.Tensor:
-    """[N, K] fp32 -> [N, 3K] bf16 = [w_hi | w_hi | w_lo] (w_lo = bf16(w - w_hi)): the weight side of a bf16x3
+def split_bf16x3_weight(w: torch.Tensor, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """[N, K] fp32 -> [N, 3K] 16-bit = [w_hi | w_hi | w_lo] (w_lo = round(w - w_hi)): the weight side of a bf16x3 (fp16x3)
     contraction against activations laid out [a_hi | a_lo | a_hi] (avcer_split_bf16x3 / avcer_lstm_cell split)."""
-    hi = w.float().bfloat16()
-    lo = (w.float() - hi.float()).bfloat16()
+    hi = w.float().to(dtype)
+    lo = (w.float() - hi.float()).to(dtype)
     return torch.cat([hi, hi, lo], dim=1)
 
 
@@ -109,8 +109,8 @@ def pack_vd(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
     def dev(t, dt=None):
         return t.to(device=device, dtype=dt or dtype).contiguous()
 
-    split = dtype == torch.bfloat16
-    mat = split_bf16x3_weight if split else (lambda w: w)
+    split = dtype in (torch.bfloat16, torch.float16)
+    mat = (lambda w: split_bf16x3_weight(w, dtype)) if split else (lambda w: w)
     return {
         "split": split,
         "w_ih1": dev(mat(sd["lstm1.weight_ih_l0"])),
@@ -182,7 +182,7 @@ def pack_audio(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
     if v1:
         # input projections are plain contractions over every time step at once; the 199-step recurrence runs bf16x3
         # (split_bf16x3_weight) in bf16 mode, like the VD LSTM
-        rec = split_bf16x3_weight if dtype == torch.bfloat16 else (lambda w: w)
+        rec = (lambda w: split_bf16x3_weight(w, dtype)) if dtype in (torch.bfloat16, torch.float16) else (lambda w: w)
         out["gru"] = [{"w_ih": dev(sd[f"gru.weight_ih_l{l}"]), "b_ih": dev(sd[f"gru.bias_ih_l{l}"], f32),
                        "w_hh": dev(rec(sd[f"gru.weight_hh_l{l}"])), "b_hh": dev(sd[f"gru.bias_hh_l{l}"], f32)} for l in range(2)]
     for t, heads in (() if v1 else (("tl1", 32), ("tl2", 16))):

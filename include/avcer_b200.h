@@ -33,6 +33,9 @@ extern "C" {
 
 const char* avcer_last_error(void);
 int avcer_version(void);
+/* "bf16" (libavcer_b200.so) or "fp16" (libavcer_b200_fp16.so): the 16-bit storage type this build of the library gives to
+ * dtype code AVCER_BF16 -- same kernels, same entry points; the fp16 build keeps 11 mantissa bits instead of 8. */
+const char* avcer_storage_type(void);
 /* 0 when a CUDA device of compute capability 10.x is usable; error otherwise (no CPU fallback). */
 int avcer_device_check(void);
 int avcer_num_sms(void);

@@ -35,16 +35,19 @@ def _ref_linear(x, w, b, res, act):
 def test_contract_linear_matches_torch(cuda_lib, m, k, n, act, res):
     from avcer_b200 import ops
 
-    torch.manual_seed(m + n)
     code = {"none": ops.ACT_NONE, "relu": ops.ACT_RELU, "gelu": ops.ACT_GELU}[act]
-    x = torch.randn(m, k, device=DEV).to(BF)
-    w = (torch.randn(n, k, device=DEV) / k ** 0.5).to(BF)
-    b = torch.randn(n, device=DEV)
-    r = torch.randn(m, n, device=DEV).to(BF) if res else None
-    y = ops.linear(x, w, b, residual=r, act=code)
-    ref = _ref_linear(x, w, b, r, code)
-    # bf16 output rounding: half an ulp of the largest magnitude (|ref| <= ~8 -> 0.03)
-    assert (y.float() - ref).abs().max().item() < 0.04
+    # bf16 build and half build of the library (same kernels, other storage type): output rounding is half an ulp of the
+    # largest magnitude (|ref| <= ~8 -> 0.03 in bf16, 0.004 in fp16)
+    for dt, tol in ((BF, 0.04), (torch.float16, 0.006)):
+        torch.manual_seed(m + n)
+        x = torch.randn(m, k, device=DEV).to(dt)
+        w = (torch.randn(n, k, device=DEV) / k ** 0.5).to(dt)
+        b = torch.randn(n, device=DEV)
+        r = torch.randn(m, n, device=DEV).to(dt) if res else None
+        y = ops.linear(x, w, b, residual=r, act=code)
+        assert y.dtype == dt
+        ref = _ref_linear(x, w, b, r, code)
+        assert (y.float() - ref).abs().max().item() < tol, dt
 
 
 def test_pointwise_conv_equals_flat_gemm(cuda_lib):
@@ -69,7 +72,7 @@ def test_pointwise_conv_equals_flat_gemm(cuda_lib):
 
 @pytest.mark.parametrize("heads,dh", [(16, 64), (32, 32)])
 @pytest.mark.parametrize("t", [199, 208, 129, 128, 113, 50, 17, 1])
-@pytest.mark.parametrize("dtype", [BF, torch.float32])
+@pytest.mark.parametrize("dtype", [BF, torch.float16, torch.float32])
 def test_attention_matches_torch(cuda_lib, heads, dh, t, dtype):
     """bf16, head dim 64: tcgen05 kernel (attention_tc5.cuh: Q K^T and P V on the 5th-gen tensor cores, V as an MN-major
     operand); bf16, head dim 32: mma.sync kernel; fp32: SIMT kernel.  T covers one / two 128-row query tiles, partial
@@ -84,7 +87,7 @@ def test_attention_matches_torch(cuda_lib, heads, dh, t, dtype):
     q, k, v = (z.float().view(n, t, heads, dh).transpose(1, 2) for z in qkv.split(heads * dh, dim=1))
     ref = torch.softmax(q @ k.transpose(-1, -2) * scale, -1) @ v
     ref = ref.transpose(1, 2).reshape(n * t, heads * dh)
-    tol = 2e-2 if dtype == BF else 2e-5       # bf16: probabilities and outputs are rounded to 8 bits
+    tol = {BF: 2e-2, torch.float16: 3e-3, torch.float32: 2e-5}[dtype]       # bf16 / fp16: probabilities and outputs are rounded to 8 / 11 bits
     assert (out.float() - ref).abs().max().item() < tol
 
 

@@ -29,7 +29,9 @@ from oracle import video as ov
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 TOL = {("fp32", "spread"): 1e-5, ("fp32", "default"): 1e-5, ("fp32", "mid"): 1e-5,
-       ("bf16", "default"): 2e-3, ("bf16", "mid"): 2e-3, ("bf16", "spread"): 1e-2}
+       ("bf16", "default"): 2e-3, ("bf16", "mid"): 2e-3, ("bf16", "spread"): 1e-2,
+       # precision "fp16": the same kernels built with IEEE half storage (11 mantissa bits): the north-star 2e-3 on EVERY init
+       ("fp16", "default"): 2e-3, ("fp16", "mid"): 2e-3, ("fp16", "spread"): 2e-3}
 
 
 def _vs_probs(sd, prec, crops):
@@ -42,7 +44,7 @@ def _vs_probs(sd, prec, crops):
     return probs.cpu().numpy(), feat.float().cpu().numpy()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
 @pytest.mark.parametrize("init", ["spread", "default", "mid"])
 def test_vs_matches_reference_golden(cuda_lib, golden, prec, init):
     g = golden["video"]
@@ -58,7 +60,7 @@ def test_vs_matches_reference_golden(cuda_lib, golden, prec, init):
         sure = (top2[:, 1] - top2[:, 0]) > 2 * TOL[(prec, init)]
         assert np.array_equal(probs.argmax(1)[sure], ref.argmax(1)[sure])
     ref_feat = np.maximum(g[f"vs_{init}_feat"], 0)
-    assert np.abs(feat - ref_feat).max() < (2e-4 if prec == "fp32" else 0.15)
+    assert np.abs(feat - ref_feat).max() < {"fp32": 2e-4, "bf16": 0.15, "fp16": 0.02}[prec]
 
 
 def test_vs_batch_invariance_and_tails(cuda_lib):
@@ -93,7 +95,7 @@ def test_vs_config2_full_batch_against_oracle(cuda_lib):
     assert np.abs(feat - np.maximum(ofeat.numpy(), 0)).max() < 0.15
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
 def test_vd_matches_reference_golden(cuda_lib, golden, prec):
     from avcer_b200 import nets
 
@@ -110,7 +112,7 @@ def test_vd_matches_reference_golden(cuda_lib, golden, prec):
     assert (out - ref).abs().max().item() < (2e-5 if prec == "fp32" else 1e-3)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
 @pytest.mark.parametrize("ncls", [8, 7])
 def test_audio_matches_reference_golden(cuda_lib, golden, prec, ncls):
     from avcer_b200 import nets, ops, pipeline
@@ -128,15 +130,16 @@ def test_audio_matches_reference_golden(cuda_lib, golden, prec, ncls):
     pr = torch.softmax(torch.from_numpy(ref[:, :7]), 1).numpy()
     # "spread" init (logit range ~5): the bf16 error budget of the module docstring (emulated 6.8e-3 on exactly these
     # windows, measured 8e-3); the north-star 2e-3 is asserted on the default and "mid" inits below
-    assert np.abs(p - pr).max() < (1e-5 if prec == "fp32" else 1.2e-2), np.abs(p - pr).max()
+    # fp16 storage: the same wide init within the north-star 2e-3 (emulated 1.2e-3)
+    assert np.abs(p - pr).max() < {"fp32": 1e-5, "bf16": 1.2e-2, "fp16": 2e-3}[prec], np.abs(p - pr).max()
     if prec == "bf16":
         top2 = np.sort(pr, axis=1)[:, -2:]
         sure = (top2[:, 1] - top2[:, 0]) > 2.4e-2
         assert np.array_equal(p.argmax(1)[sure], pr.argmax(1)[sure])
-    assert np.abs(out - ref).max() < (1e-4 if prec == "fp32" else 0.08)
+    assert np.abs(out - ref).max() < {"fp32": 1e-4, "bf16": 0.08, "fp16": 0.02}[prec]
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
 @pytest.mark.parametrize("init", ["default", "mid"])
 def test_audio_north_star_tolerance(cuda_lib, golden, prec, init):
     """2e-3 (bf16) / 1e-5 (fp32) on the per-class probabilities against the unmodified reference: PyTorch-default init
@@ -160,7 +163,7 @@ def test_audio_north_star_tolerance(cuda_lib, golden, prec, init):
         assert sure.any() and np.array_equal(p.argmax(1)[sure], pr.argmax(1)[sure])
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
 def test_audio_v1_gru_variant_matches_reference_golden(cuda_lib, golden, prec):
     """ExprModelV1 (architectures/audio_8_cl.py:18-72: wav2vec2 -> 2-layer GRU(1024 -> 256) -> 256-wide head), the variant
     the reference's alternate model lists use, against the unmodified reference class (tests/golden/audio.npz)."""

@@ -57,9 +57,11 @@ def test_header_symbols_exported():
     declared = set(re.findall(r"\b(avcer_[a-z0-9_]+)\s*\(", hdr))
     declared.discard("avcer_contract_desc")
     assert declared, "no declarations found"
-    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], check=True, capture_output=True, text=True).stdout
-    exported = {line.split()[-1] for line in nm.splitlines() if line.split()[-1].startswith("avcer_") and " T " in line}
-    assert exported == declared, f"header vs nm -D: {sorted(exported ^ declared)}"
+    for path in (_lib.LIB_PATH, _lib.LIB_PATH_FP16):          # the bf16 build and the half build export the same surface
+        nm = subprocess.run(["nm", "-D", "--defined-only", path], check=True, capture_output=True, text=True).stdout
+        exported = {line.split()[-1] for line in nm.splitlines() if line.split()[-1].startswith("avcer_") and " T " in line}
+        assert exported == declared, f"header vs nm -D of {path}: {sorted(exported ^ declared)}"
+    assert _lib.load("bf16").avcer_storage_type() == b"bf16" and _lib.load("fp16").avcer_storage_type() == b"fp16"
     assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
     assert _lib.load().avcer_version() >= 100
 

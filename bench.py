@@ -192,7 +192,7 @@ def main():
     ap.add_argument("--clips-per-gpu", type=int, default=8)       # weak scaling
     ap.add_argument("--clip-seconds", type=int, default=60)
     ap.add_argument("--fps", type=int, default=25)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--a-batch", type=int, default=64)
     ap.add_argument("--vs-batch", type=int, default=1024)     # crops per VS forward inside the pipeline (config 2 below stays at 256)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -492,7 +492,7 @@ def main():
         cpu = cpu_baseline()
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": workload,
+            "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision], "data": "synthetic", "config": workload,
             "audio_seconds_per_sec": sum(durations) * args.steps / (ms / 1e3),
             "shard_frames": runner.counts, "collective": {"op": "all_gather_into_tensor", "bytes_per_rank": int(runner.send.numel() * 4),
                                                          "layout": "per-frame VS probabilities [n,7] + VD logits [n,7] + audio mean logits [n,8], fp32"},

@@ -10,13 +10,15 @@ Tolerances (per-class probabilities, absolute):
                   vary across inputs by more than the tolerance);
               VD (LSTM): 2e-3 on its widest init -- every contraction of the recurrence is bf16x3 (split
               operands, fp32 accumulation), measured ~1e-5;
-              1e-2 on the deliberately wide "spread" init (logit range ~5) for VS / A: the probability error
-              is p(1-p) x the logit error, and the logit error of bf16 OPERANDS is ~0.65 % of the logit range
-              whatever is done about storage -- bf16 weights alone cost 1.1e-3 (VS) / 2.5e-3 (A) at this init,
-              an fp32 residual stream moves the total only from 4.8e-3 to 3.8e-3 (VS) and 6.8e-3 to 4.5e-3 (A)
-              (scripts/sim_bf16_budget.py, CPU emulation of every rounding point; profiles/r02_bf16_error_budget.txt).
-              What this init does assert in bf16: identical arg-max wherever the reference's top-2 margin
-              exceeds twice the measured error, and >= 99.5 % compound top-1 agreement (test_gpu_dropin.py).
+              the deliberately wide "spread" init (logit range ~5): VS 2e-3 (measured 1.6e-3 on the golden crops, since relu(fc1)
+              leaves the network in fp32), A 1.2e-2 (measured 6.4e-3): the probability error is p(1-p) x the logit error, and the
+              logit error of bf16 OPERANDS is ~0.65 % of the logit range whatever is done about storage -- bf16 weights alone
+              cost 1.1e-3 (VS) / 2.5e-3 (A) at this init, an fp32 residual stream moves the audio total only from 6.8e-3 to
+              4.5e-3 (scripts/sim_bf16_budget.py, CPU emulation of every rounding point; profiles/r02_bf16_error_budget.txt).
+              What the audio network does assert on this init in bf16: identical arg-max wherever the reference's top-2 margin
+              exceeds twice the bound, and >= 99.5 % compound top-1 agreement (test_gpu_dropin.py).
+  fp16 mode : 2e-3 on EVERY init, the wide one included (measured VS 9.0e-4, A 1.0e-3): the same kernels built with IEEE half
+              storage (libavcer_b200_fp16.so, -DAVCER_HALF) -- 11 mantissa bits instead of 8 at the same tensor-core rate.
 """
 import numpy as np
 import pytest
@@ -29,7 +31,9 @@ from oracle import video as ov
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 TOL = {("fp32", "spread"): 1e-5, ("fp32", "default"): 1e-5, ("fp32", "mid"): 1e-5,
-       ("bf16", "default"): 2e-3, ("bf16", "mid"): 2e-3, ("bf16", "spread"): 1e-2,
+       # VS in bf16 on the wide init: 1.6e-3 measured on these crops since relu(fc1) leaves the network in fp32 (6.1e-3 with
+       # bf16 features in round 1); deterministic kernels make the figure reproducible, so the north-star bar is asserted
+       ("bf16", "default"): 2e-3, ("bf16", "mid"): 2e-3, ("bf16", "spread"): 2e-3,
        # precision "fp16": the same kernels built with IEEE half storage (11 mantissa bits): the north-star 2e-3 on EVERY init
        ("fp16", "default"): 2e-3, ("fp16", "mid"): 2e-3, ("fp16", "spread"): 2e-3}
 

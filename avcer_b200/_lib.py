@@ -92,6 +92,7 @@ _SIGNATURES = {
     "avcer_split_bf16x3": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int64, c_void_p]),
     "avcer_pcm16_resample": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
     "avcer_audio_normalize_windows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "avcer_w2v_conv0_tc": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p]),
     "avcer_w2v_conv0_ln_gelu": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "avcer_layernorm": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_int, c_void_p, c_int64, c_int, c_void_p]),
     "avcer_subsample_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_void_p]),

@@ -6,6 +6,7 @@
 #include "conv3x3.cuh"
 #include "stem_pool.cuh"
 #include "attention_tc5.cuh"
+#include "conv0_tc.cuh"
 
 #include <cudaTypedefs.h>
 #include <mutex>
@@ -647,6 +648,39 @@ extern "C" int avcer_stem_pool_u8(const uint8_t* crops, const void* w_packed, co
   using namespace avcer;
   AVCER_REQUIRE(n >= 0, "stem_pool_u8: negative batch");
   return stem_pool_u8_tc(crops, w_packed, bias, n, out, out_pitch, as_stream(stream));
+}
+
+// ------------------------------------------------------------------ wav2vec2 conv0 + LayerNorm + GELU on the tensor cores
+extern "C" int avcer_w2v_conv0_tc(const float* x, int n, int t_in, const void* w_packed, const float* ln_g, const float* ln_b,
+                                  float eps, void* y, int64_t y_pitch_rows, void* stream) {
+  using namespace avcer;
+  AVCER_REQUIRE(t_in >= 10 && n >= 0, "w2v_conv0_tc: bad shape n=%d t_in=%d", n, t_in);
+  const int t_out = (t_in - 10) / 5 + 1;
+  AVCER_REQUIRE(y_pitch_rows >= t_out, "w2v_conv0_tc: y pitch too small");
+  AVCER_REQUIRE(x != nullptr && w_packed != nullptr && ln_g != nullptr && ln_b != nullptr && y != nullptr, "w2v_conv0_tc: null pointer");
+  AVCER_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                "w2v_conv0_tc: w_packed / y must be 16-byte aligned");
+  if (n == 0) return 0;
+  CUtensorMap ty;
+  uint64_t dims[5] = {512, (uint64_t)t_out, (uint64_t)n, 1, 1};
+  uint64_t strides[4] = {512 * 2, (uint64_t)y_pitch_rows * 512 * 2, (uint64_t)1 << 30, (uint64_t)1 << 30};
+  uint32_t box[5] = {64u, 32u, 1u, 1u, 1u};
+  if (encode_map(&ty, y, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  Conv0Params p{};
+  p.x = x; p.w_packed = w_packed; p.gamma = ln_g; p.beta = ln_b;
+  p.n = n; p.t_in = t_in; p.t_out = t_out;
+  p.tiles_per_row = (t_out + 127) / 128;
+  p.num_tiles = n * p.tiles_per_row;
+  p.eps = eps;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AVCER_CUDA(cudaFuncSetAttribute(w2v_conv0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv0Cfg::SMEM));
+    attr_done = true;
+  }
+  int g = num_sms();
+  if (g > p.num_tiles) g = p.num_tiles;
+  launch_pdl_tpc(w2v_conv0_tc_kernel, g, Conv0Cfg::THREADS, Conv0Cfg::SMEM, as_stream(stream), ty, p);
+  return check_launch("w2v_conv0_tc_kernel");
 }
 
 extern "C" int avcer_last_contract_kernel(void) { return avcer::g_last_kernel; }

@@ -15,9 +15,16 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // Same function with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. far below one
 // bf16 ulp): one MUFU.RCP + one MUFU.EX2 + a 5-term Horner instead of libdevice erff.  Used where
 // the result is stored as bf16; the fp32 mode keeps erff.
+// 1 / d for d >= 1 (no denormal operand or result to rescue: the bare MUFU.RCP, without the range fix-up
+// FSETP / FSEL / 2 x FMUL that __fdividef and 1.0f / d carry).
+__device__ __forceinline__ float rcp_approx(float d) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return r;
+}
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
@@ -59,33 +66,35 @@ __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c
 }
 
 // gelu_erf_fast on two values at once: the same Abramowitz & Stegun 7.1.26 evaluation with every multiply / FMA
-// issued as a packed fp32x2 instruction (13 packed + 4 MUFU + 2 logic per PAIR instead of ~17 per value).  The layers
+// issued as a packed fp32x2 instruction (10 packed + 4 MUFU + 2 logic per PAIR instead of ~17 per value).  The layers
 // that apply GELU to every activation (conv0, the feature-extractor LayerNorms, the FFN epilogue) are issue-bound.
-__device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
-  const float a0 = fabsf(x0), a1 = fabsf(x1);
-  const uint64_t a = pack_f32x2(a0, a1);
-  const uint64_t z = mul_f32x2(a, pack_f32x2(0.70710678118654752440f, 0.70710678118654752440f));
-  const uint64_t d = fma_f32x2(pack_f32x2(0.3275911f, 0.3275911f), z, pack_f32x2(1.0f, 1.0f));
+// With a = |x|, z = a / sqrt 2:  t = 1 / (1 + p z),  erf(z) = 1 - t * poly(t) * exp(-z^2),  gelu = 0.5 (x + a erf(z));
+// the constants of z are folded into the coefficients and the polynomial is evaluated negated, so no instruction is
+// spent on z itself, on a sign flip or on halving both terms.
+__device__ __forceinline__ uint64_t gelu_erf_fast2(uint64_t x) {
+  const uint64_t a = x & 0x7fffffff7fffffffull;
+  const uint64_t d = fma_f32x2(pack_f32x2(0.3275911f * 0.70710678118654752440f, 0.3275911f * 0.70710678118654752440f), a,
+                               pack_f32x2(1.0f, 1.0f));
   float d0, d1;
   unpack_f32x2(d, d0, d1);
-  const uint64_t t = pack_f32x2(__fdividef(1.0f, d0), __fdividef(1.0f, d1));
-  uint64_t poly = fma_f32x2(pack_f32x2(1.061405429f, 1.061405429f), t, pack_f32x2(-1.453152027f, -1.453152027f));
-  poly = fma_f32x2(poly, t, pack_f32x2(1.421413741f, 1.421413741f));
-  poly = fma_f32x2(poly, t, pack_f32x2(-0.284496736f, -0.284496736f));
-  poly = fma_f32x2(poly, t, pack_f32x2(0.254829592f, 0.254829592f));
-  const uint64_t pt = mul_f32x2(poly, t);
-  // exp(-z^2) = 2^(-z^2 * log2 e)
-  const uint64_t nz = mul_f32x2(mul_f32x2(z, pack_f32x2(-1.4426950408889634f, -1.4426950408889634f)), z);
+  const uint64_t t = pack_f32x2(rcp_approx(d0), rcp_approx(d1));
+  uint64_t poly = fma_f32x2(pack_f32x2(-1.061405429f, -1.061405429f), t, pack_f32x2(1.453152027f, 1.453152027f));
+  poly = fma_f32x2(poly, t, pack_f32x2(-1.421413741f, -1.421413741f));
+  poly = fma_f32x2(poly, t, pack_f32x2(0.284496736f, 0.284496736f));
+  poly = fma_f32x2(poly, t, pack_f32x2(-0.254829592f, -0.254829592f));
+  const uint64_t npt = mul_f32x2(poly, t);                // -t * poly(t)
+  // exp(-z^2) = 2^(-a^2 * log2(e) / 2)
+  const uint64_t nz = mul_f32x2(mul_f32x2(a, pack_f32x2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f)), a);
   float n0, n1;
   unpack_f32x2(nz, n0, n1);
   float e0, e1;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(n0));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(n1));
-  // erf(|x| / sqrt 2) = 1 - pt * e;  gelu = 0.5 x + 0.5 |x| erf
-  const uint64_t er = fma_f32x2(mul_f32x2(pt, pack_f32x2(-1.0f, -1.0f)), pack_f32x2(e0, e1), pack_f32x2(1.0f, 1.0f));
-  const uint64_t half = pack_f32x2(0.5f, 0.5f);
-  const uint64_t r = fma_f32x2(mul_f32x2(a, half), er, mul_f32x2(pack_f32x2(x0, x1), half));
-  unpack_f32x2(r, x0, x1);
+  const uint64_t er = fma_f32x2(npt, pack_f32x2(e0, e1), pack_f32x2(1.0f, 1.0f));      // erf(|x| / sqrt 2)
+  return mul_f32x2(fma_f32x2(a, er, x), pack_f32x2(0.5f, 0.5f));
+}
+__device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
+  unpack_f32x2(gelu_erf_fast2(pack_f32x2(x0, x1)), x0, x1);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

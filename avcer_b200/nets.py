@@ -174,10 +174,18 @@ class VSNet:
         """layer1 .. fc2 from the pooled stem output: `y` is either [n,55,55,64] or (is_cat) the [n,55,55,128] matrix whose
         left 64 channels hold it (layer1.0's K-concatenated layout)."""
         cat = y if is_cat and y.shape[-1] == 128 else None
+        y, _, _ = self._blocks(y, cat, None, 0, len(self.w["blocks"]), taps)
+        return self._tail(y)
+
+    def _blocks(self, y, cat, cat4, lo: int, hi: int, taps: Optional[dict] = None, tail_out: Optional[torch.Tensor] = None):
+        """Bottleneck blocks [lo, hi).  State between blocks: `y` (block input, NHWC) or, after a sampled stage tail, the
+        K-concatenated matrix `cat` / `cat4` whose left columns hold the stride-2 sampled input of the coming block.
+        `tail_out`: where the sampled tail of block hi-1 puts that matrix (rows of a batch slice of a larger one)."""
         blocks = self.w["blocks"]
         fuse = taps is None and _tc(self.dtype) and self.fused_shortcut
-        sampled = False                 # `cat[:, :cin]` already holds the stride-2 sampled input of the coming block
-        for bi, blk in enumerate(blocks):
+        sampled = cat4 is not None      # `cat[:, :cin]` already holds the stride-2 sampled input of the coming block
+        for bi in range(lo, hi):
+            blk = blocks[bi]
             if bi == 0 and cat is not None:
                 # layer1.0: block input and conv2 output share one [n*55*55, 128] matrix, so conv3 and the projection
                 # shortcut are a single K = 128 GEMM (no shortcut tensor, no residual read)
@@ -226,7 +234,11 @@ class VSNet:
                     t = self._conv(t, c2, ops.ACT_RELU)
                 nb, hh, ww, _ = t.shape
                 ho, wo = (hh - 1) // c3_stride + 1, (ww - 1) // c3_stride + 1
-                cat = torch.empty((nb * ho * wo, c3.cout + nxt["conv1"].cout), device=self.device, dtype=self.dtype)
+                if tail_out is not None and bi == hi - 1:
+                    cat = tail_out
+                    assert cat.shape == (nb * ho * wo, c3.cout + nxt["conv1"].cout)
+                else:
+                    cat = torch.empty((nb * ho * wo, c3.cout + nxt["conv1"].cout), device=self.device, dtype=self.dtype)
                 cat4 = cat.view(nb, ho, wo, c3.cout + nxt["conv1"].cout)
                 ops.conv2d_nhwc(t, c3.wt, c3.bias, kh=1, kw=1, stride=c3_stride, residual=identity, residual_stride=2,
                                 act=ops.ACT_RELU, out=cat4[..., :c3.cout])
@@ -237,7 +249,7 @@ class VSNet:
             y = self._conv(t, blk["conv3"], ops.ACT_RELU, residual=identity)
             if taps is not None:
                 taps[f"block{bi}"] = y
-        return self._tail(y)
+        return y, cat, (cat4 if sampled else None)
 
     def _tail(self, y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         pooled = ops.avgpool(y)
@@ -303,6 +315,7 @@ class ANet:
         self.device = torch.device(device)
         self.w = weights.pack_audio(state_dict, self.device, self.dtype)
         self.num_classes = self.w["num_classes"]
+        self.conv0_tc = True       # 16-bit modes: feature-extractor layer 0 on the tensor cores (avcer_w2v_conv0_tc)
 
     def _conv1d_s2(self, x: torch.Tensor, t_in: int, k: int, wt, bias) -> torch.Tensor:
         """[B, t_in, 512] -> [B, t_out, 512], stride 2, no padding: the k taps of one output step are
@@ -341,7 +354,10 @@ class ANet:
         w = self.w
         t0 = W2V_LENGTHS[0]
         h = torch.empty((b, t0, 512), device=self.device, dtype=self.dtype)
-        ops.w2v_conv0_ln_gelu(x, w["conv0_w"], w["conv0_b"], *w["conv_ln"][0], h)
+        if self.conv0_tc and "conv0_tc" in w:
+            ops.w2v_conv0_tc(x, w["conv0_tc"], *w["conv_ln"][0], h)
+        else:
+            ops.w2v_conv0_ln_gelu(x, w["conv0_w"], w["conv0_b"], *w["conv_ln"][0], h)
         if taps is not None:
             taps["conv0"] = h
         t = t0

@@ -19,7 +19,7 @@ from ._lib import check as _check
 __all__ = [
     "F32", "BF16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "dtype_code", "torch_dtype", "contract", "conv2d_nhwc",
     "linear", "preprocess", "fuse_compound", "weight_search_confusion", "softmax7", "window_to_frame_mean", "gather_rows", "maxpool3x3s2",
-    "stem_pool", "stem_pool_u8", "subsample_rows", "avgpool", "small_linear", "lstm_cell", "gru_cell", "split_bf16x3", "sinc_resample_bank", "pcm16_to_mono", "audio_normalize_windows", "w2v_conv0_ln_gelu", "layernorm", "add_rows",
+    "stem_pool", "stem_pool_u8", "subsample_rows", "avgpool", "small_linear", "lstm_cell", "gru_cell", "split_bf16x3", "sinc_resample_bank", "pcm16_to_mono", "audio_normalize_windows", "w2v_conv0_ln_gelu", "w2v_conv0_tc", "layernorm", "add_rows",
     "attention", "maxpool1d5_relu", "avgpool1d_relu", "cast", "sm_limit",
 ]
 
@@ -495,6 +495,17 @@ def w2v_conv0_ln_gelu(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, g: torc
     n, t_in = x.shape
     check(_L(y).avcer_w2v_conv0_ln_gelu(x.data_ptr(), n, t_in, w.data_ptr(), b.data_ptr(), g.data_ptr(),
                                               be.data_ptr(), y.data_ptr(), y.shape[1], dtype_code(y.dtype), _stream()))
+    return y
+
+
+def w2v_conv0_tc(x: torch.Tensor, w_packed: torch.Tensor, g: torch.Tensor, be: torch.Tensor, y: torch.Tensor,
+                 eps: float = 1e-5) -> torch.Tensor:
+    """Same contract as w2v_conv0_ln_gelu on the tensor cores (16-bit libraries only; w_packed = weights.pack_conv0_tc)."""
+    n, t_in = x.shape
+    assert y.dtype in (torch.bfloat16, torch.float16) and w_packed.dtype == y.dtype and y.shape[2] == 512 and y.stride(1) == 512
+    with _Timed("w2v_conv0_tc", 0.0):
+        check(_L(y).avcer_w2v_conv0_tc(x.data_ptr(), n, t_in, w_packed.data_ptr(), g.data_ptr(), be.data_ptr(), eps,
+                                       y.data_ptr(), y.stride(0) // 512, _stream()))
     return y
 
 

@@ -101,6 +101,19 @@ def split_bf16x3_weight(w: torch.Tensor, dtype: torch.dtype = torch.bfloat16) ->
     return torch.cat([hi, hi, lo], dim=1)
 
 
+def pack_conv0_tc(w: torch.Tensor, b: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """wav2vec2 conv0 filter bank [512, 10] + bias [512] -> the B operand of avcer_w2v_conv0_tc: rows
+    [w_hi(10) | w_hi(10) | w_lo(10) | b_hi | b_lo] (K = 32, the weight side of a 16-bit x3 product whose activation side is
+    [x_hi | x_lo | x_hi | 1 | 1]) stored as UMMA no-swizzle core matrices [k/8][channel/8][8 channels][8 k]."""
+    w, b = w.float().reshape(512, 10), b.float().reshape(512, 1)
+    w_hi, b_hi = w.to(dtype), b.to(dtype)
+    w_lo, b_lo = (w - w_hi.float()).to(dtype), (b - b_hi.float()).to(dtype)
+    # IEEE half: the kernel stores 2^11 x_lo (a quiet sample's low half would be a half subnormal), so this block is 2^-11 w_hi
+    w_hi2 = (w_hi.float() / 2048.0).to(dtype) if dtype == torch.float16 else w_hi
+    rows = torch.cat([w_hi, w_hi2, w_lo, b_hi, b_lo], dim=1)                 # [512, 32]
+    return rows.view(64, 8, 4, 8).permute(2, 0, 1, 3).contiguous()
+
+
 def pack_vd(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
     """LSTM(512->512) -> LSTM(512->256) -> Linear(256->7).  Layer 2's input and recurrent matrices
     are concatenated along K so one GEMM over [h1_t | h2_{t-1}] yields its gate pre-activations.
@@ -149,6 +162,8 @@ def pack_audio(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
     fe = p + "feature_extractor.conv_layers."
     out["conv0_w"] = dev(sd[fe + "0.conv.weight"].reshape(512, 10), f32)
     out["conv0_b"] = dev(sd[fe + "0.conv.bias"], f32)
+    if dtype in (torch.bfloat16, torch.float16):
+        out["conv0_tc"] = dev(pack_conv0_tc(sd[fe + "0.conv.weight"], sd[fe + "0.conv.bias"], dtype))
     out["conv_ln"] = [(dev(sd[f"{fe}{i}.layer_norm.weight"], f32), dev(sd[f"{fe}{i}.layer_norm.bias"], f32)) for i in range(7)]
     out["convs"] = [(dev(_tap_major(sd[f"{fe}{i}.conv.weight"])), dev(sd[f"{fe}{i}.conv.bias"], f32)) for i in range(1, 7)]
     out["fp_ln"] = (dev(sd[p + "feature_projection.layer_norm.weight"], f32), dev(sd[p + "feature_projection.layer_norm.bias"], f32))

@@ -265,6 +265,13 @@ int avcer_audio_normalize_windows(const float* wav, const int64_t* starts, const
 int avcer_w2v_conv0_ln_gelu(const float* x, int n, int t_in, const float* w, const float* b,
                             const float* ln_g, const float* ln_b, void* y, int64_t y_pitch_rows,
                             int dtype, void* stream);
+/* K5b on the tensor cores (16-bit storage only): the same layer as a 128 x 512 x 32 tcgen05 contraction per 128 time steps
+ * (16-bit x3 split of samples, filters and bias; fp32 accumulation) with LayerNorm + GELU applied straight from TMEM.
+ * w_packed: [4][64][8][8] 16-bit core matrices of rows [w_hi | w_hi | w_lo | b_hi | b_lo] (weights.pack_conv0_tc).
+ * Replaces the same reference call as avcer_w2v_conv0_ln_gelu (HF Wav2Vec2LayerNormConvLayer #0 behind
+ * architectures/audio_8_cl.py:135,180). */
+int avcer_w2v_conv0_tc(const float* x, int n, int t_in, const void* w_packed, const float* ln_g,
+                       const float* ln_b, float eps, void* y, int64_t y_pitch_rows, void* stream);
 /* Row LayerNorm over `c` channels (eps given) with optional fused GELU and optional additive
  * term (positional encoding / residual) applied BEFORE the norm: y = act(LN(x + add)).
  * Rows are addressed as x + r*ldx; add row index = r % add_rows (add_rows = 0: no add). */

@@ -256,3 +256,79 @@ def make_wav(seed: int, n_samples: int) -> np.ndarray:
         x += rng.uniform(0.02, 0.06) * np.sin(2 * np.pi * f0 * t * (1 + 0.05 * np.sin(2 * np.pi * rng.uniform(0.1, 1.0) * t)) + rng.uniform(0, 6.28))
     x += rng.normal(0, 0.03, size=n_samples)
     return x.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------ face detector
+RF_BLOCKS = (3, 4, 6, 3)
+RF_PLANES = (64, 128, 256, 512)
+RF_CLASS_SCALE, RF_CLASS_BIAS = 0.5, 0.5
+
+
+def make_retinaface_state_dict(seed: int = 5, init: str = "spread") -> "OrderedDict[str, torch.Tensor]":
+    """RetinaFace(cfg_re50, phase='test') of data/face_detection/ibug/face_detection/retina_face/retina_face.py:48-115:
+    torchvision ResNet-50 body (keys body.*; fc / avgpool dropped by IntermediateLayerGetter), FPN, three SSH modules and
+    the class / box / landmark heads (2 anchors per position).  The reference loads weights/Resnet50_Final.pth
+    (retina_face_predictor.py:39-44), which does not ship with the repository.
+    init="spread": He-normal convolutions, perturbed BatchNorm statistics, a stem BatchNorm that normalises the raw
+    mean-subtracted pixels, class heads scaled and biased so that a few per cent of the anchors score above 0.8."""
+    g = _gen(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    _conv("body.conv1.weight", 64, 3, 7, sd, g, init)
+    _bn("body.bn1", 64, sd, g, init, var=1.0 if init == "default" else 2.0 * 70.0 ** 2)
+    cin = 64
+    for li, (planes, blocks) in enumerate(zip(RF_PLANES, RF_BLOCKS), start=1):
+        for b in range(blocks):
+            p = f"body.layer{li}.{b}"
+            _conv(p + ".conv1.weight", planes, cin, 1, sd, g, init)
+            _bn(p + ".bn1", planes, sd, g, init)
+            _conv(p + ".conv2.weight", planes, planes, 3, sd, g, init)
+            _bn(p + ".bn2", planes, sd, g, init)
+            _conv(p + ".conv3.weight", planes * 4, planes, 1, sd, g, init)
+            _bn(p + ".bn3", planes * 4, sd, g, init, gamma_scale=0.5)
+            if b == 0:
+                _conv(p + ".downsample.0.weight", planes * 4, cin, 1, sd, g, init)
+                _bn(p + ".downsample.1", planes * 4, sd, g, init, gamma_scale=0.7)
+            cin = planes * 4
+    for i, c in enumerate((512, 1024, 2048), start=1):
+        _conv(f"fpn.output{i}.0.weight", 256, c, 1, sd, g, init)
+        _bn(f"fpn.output{i}.1", 256, sd, g, init)
+    for i in (1, 2):
+        _conv(f"fpn.merge{i}.0.weight", 256, 256, 3, sd, g, init)
+        _bn(f"fpn.merge{i}.1", 256, sd, g, init)
+    for i in (1, 2, 3):
+        for name, co, ci in (("conv3X3", 128, 256), ("conv5X5_1", 64, 256), ("conv5X5_2", 64, 64), ("conv7X7_2", 64, 64),
+                             ("conv7x7_3", 64, 64)):
+            _conv(f"ssh{i}.{name}.0.weight", co, ci, 3, sd, g, init)
+            _bn(f"ssh{i}.{name}.1", co, sd, g, init)
+    for head, per_anchor in (("ClassHead", 2), ("BboxHead", 4), ("LandmarkHead", 10)):
+        for i in range(3):
+            w = _kaiming_uniform((2 * per_anchor, 256, 1, 1), 256, g)
+            b = _kaiming_uniform((2 * per_anchor,), 256, g)
+            if init != "default":
+                if head == "ClassHead":
+                    # the SSH features are positive (post-ReLU) and O(4): centre the filters so that the logits do not drift
+                    # with the feature mean, scale them to a face-vs-background logit spread of ~2 and bias towards background
+                    w = (w - w.mean(dim=1, keepdim=True)) * RF_CLASS_SCALE
+                    b = b + torch.tensor([RF_CLASS_BIAS, -RF_CLASS_BIAS] * 2)
+                else:
+                    w = w * 0.5
+            sd[f"{head}.{i}.conv1x1.weight"] = w
+            sd[f"{head}.{i}.conv1x1.bias"] = b
+    return sd
+
+
+def make_frames(seed: int, n: int, height: int, width: int) -> np.ndarray:
+    """Synthetic BGR video frames [n, height, width, 3] uint8: low-frequency blobs plus noise, drifting slowly from frame
+    to frame so that consecutive detections overlap (what the tracker keys on)."""
+    rng = np.random.default_rng(seed)
+    gh, gw = height // 16 + 2, width // 16 + 2
+    base = rng.uniform(0, 255, (gh, gw, 3))
+    drift = rng.normal(0, 4.0, (n, gh, gw, 3)).cumsum(axis=0)
+    out = np.empty((n, height, width, 3), dtype=np.uint8)
+    ys = np.minimum(np.arange(height) // 16, gh - 1)
+    xs = np.minimum(np.arange(width) // 16, gw - 1)
+    for i in range(n):
+        coarse = np.clip(base + drift[i], 0, 255)
+        img = coarse[ys][:, xs] + rng.normal(0, 12.0, (height, width, 3))
+        out[i] = np.clip(img, 0, 255).astype(np.uint8)
+    return out

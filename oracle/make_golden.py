@@ -22,6 +22,7 @@ sys.path.insert(0, ROOT)
 from avcer_b200 import get_weights_matrices as gwm  # noqa: E402
 from avcer_b200 import synthetic as syn  # noqa: E402
 from oracle import audio as oa  # noqa: E402
+from oracle import face as ofa  # noqa: E402
 from oracle import fusion as of  # noqa: E402
 from oracle import harness  # noqa: E402
 from oracle import video as ov  # noqa: E402
@@ -394,9 +395,140 @@ def make_pred_av(wd):
     print("pred_av.npz")
 
 
+def face_tracker_sequences(seed=3):
+    """Box sequences that exercise the tracker on their own: drifting boxes, births, deaths, an empty frame (which clears
+    every tracklet), a degenerate zero-area box and two faces swapping order."""
+    rng = np.random.default_rng(seed)
+    seqs = []
+    for s in range(3):
+        boxes = rng.uniform(20, 200, (4, 2))
+        boxes = np.concatenate([boxes, boxes + rng.uniform(30, 80, (4, 2))], axis=1)
+        frames = []
+        for t in range(12):
+            boxes = boxes + rng.normal(0, 4.0 + 6.0 * s, boxes.shape)
+            cur = boxes.copy()
+            if t == 4:
+                cur = cur[:2]                                   # two faces disappear ...
+            if t == 5:
+                cur = cur[::-1]                                 # ... come back (new ids) in reverse order
+            if t == 7 and s == 1:
+                cur = np.empty((0, 4))                          # empty frame: every tracklet is dropped
+            if t == 9:
+                cur = np.concatenate([cur, [[50, 50, 50, 90]]])     # zero-area box: never tracked (id None)
+            frames.append(np.concatenate([cur, rng.uniform(0.8, 1.0, (len(cur), 1)), rng.uniform(0, 200, (len(cur), 10))], axis=1).astype(np.float32))
+        seqs.append(frames)
+    return seqs
+
+
+def write_face_video(path, frames, fps=25):
+    import cv2
+
+    h, w = frames.shape[1:3]
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), fps, (w, h))
+    assert vw.isOpened()
+    for f in frames:
+        vw.write(f)
+    vw.release()
+
+
+def make_face(wd):
+    """The unmodified RetinaFace / RetinaFacePredictor / SimpleFaceTracker / VideoPredictor.process of the reference
+    (data/face_detection/ibug/face_detection, data/get_face_images.py) on synthetic weights, frames and a MJPG video."""
+    from types import SimpleNamespace
+
+    import cv2
+    from data.face_detection.ibug.face_detection import RetinaFacePredictor
+    from data.face_detection.ibug.face_detection.retina_face.config import cfg_re50
+    from data.face_detection.ibug.face_detection.utils import SimpleFaceTracker
+    from data.get_face_images import VideoPredictor
+
+    sd = syn.make_retinaface_state_dict(5, "spread")
+    wpath = os.path.join(wd, "retinaface_synthetic.pth")
+    torch.save(dict(sd), wpath)
+    pred = RetinaFacePredictor(threshold=0.8, device="cpu", model=SimpleNamespace(weights=wpath, config=SimpleNamespace(**cfg_re50)))
+    out = {}
+    # (1) raw network outputs on one small frame (odd feature-map sizes: 100 x 136 -> 13 x 17, 7 x 9, 4 x 5)
+    fr = syn.make_frames(40, 1, 100, 136)[0]
+    x = ofa.prepare(fr)
+    with torch.no_grad():
+        loc, conf, lm = pred.net(x)
+    mine = ofa.forward(x, sd)
+    for a, b, name in zip((loc, conf, lm), mine, ("loc", "conf", "landms")):
+        assert torch.equal(a, b), name                      # same torch ops in the same order: bit-identical
+        out["raw_" + name] = a[0].numpy()
+    # (2) the predictor call on a short drifting sequence + the tracker on its detections
+    frames = syn.make_frames(41, 6, 150, 200)
+    tracker, my_tracker = SimpleFaceTracker(iou_threshold=0.4, minimum_face_size=0.0), ofa.SimpleFaceTracker(0.4, 0.0)
+    ids_all = []
+    for i, f in enumerate(frames):
+        dets = pred(f, rgb=False)
+        assert np.array_equal(dets, ofa.predict(sd, f)), i
+        ids = tracker(dets)
+        assert ids == my_tracker(dets)
+        out[f"dets_{i}"] = dets
+        ids_all.append(np.asarray(ids, dtype=np.int64))
+        assert len(dets) > 0, "synthetic detector produced no face: retune synthetic.RF_CLASS_*"
+    out["ids"] = np.concatenate(ids_all)
+    out["ids_count"] = np.asarray([len(a) for a in ids_all], dtype=np.int64)
+    assert np.array_equal(pred(frames[0][..., ::-1].copy(), rgb=True), out["dets_0"])
+    # (3) the tracker alone
+    for s, seq in enumerate(face_tracker_sequences()):
+        tracker.reset()
+        my_tracker.reset()
+        got = []
+        for boxes in seq:
+            ids = tracker(boxes)
+            assert ids == my_tracker(boxes)
+            got.append(np.asarray([-1 if v is None else v for v in ids], dtype=np.int64))
+        out[f"track_{s}"] = np.concatenate(got) if got else np.empty(0, dtype=np.int64)
+    # (4) VideoPredictor.process, unmodified, on an MJPG file (constructed without __init__: that one hard-codes cuda:0
+    # and the weight file inside the package)
+    vpath = os.path.join(wd, "faces_clip.avi")
+    write_face_video(vpath, syn.make_frames(42, 8, 150, 200))
+    vp = VideoPredictor.__new__(VideoPredictor)
+    vp.video_stream, vp.device, vp.count_frame = None, "cpu", None
+    vp.model, vp.face_tracker = pred, SimpleFaceTracker(iou_threshold=0.4, minimum_face_size=0.0)
+    save = os.path.join(wd, "faces_out")
+    vp.process(vpath, save)
+    vp.video_stream.release()
+    vp.video_stream = None
+    cap = cv2.VideoCapture(vpath)
+    decoded = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        decoded.append(f)
+    cap.release()
+    out["video_frames_sha256"] = np.frombuffer(hashlib.sha256(np.stack(decoded).tobytes()).digest(), dtype=np.uint8)
+    names, digests = [], []
+    for root, _, files in sorted(os.walk(os.path.join(save, "faces_clip"))):
+        for fn in sorted(files):
+            rel = os.path.relpath(os.path.join(root, fn), save)
+            names.append(rel.replace(os.sep, "/"))
+            digests.append(np.frombuffer(hashlib.sha256(open(os.path.join(root, fn), "rb").read()).digest(), dtype=np.uint8))
+    assert names, "VideoPredictor.process wrote no crop"
+    out["process_files"] = np.asarray(names)
+    out["process_sha256"] = np.stack(digests)
+    # my restatement of the loop on the same decoded frames
+    my_tracker.reset()
+    mine_files = []
+    for i, f in enumerate(decoded):
+        dets = ofa.predict(sd, f)
+        for (t, sx, sy, ex, ey) in ofa.crop_boxes(dets, my_tracker(dets), f.shape[1], f.shape[0]):
+            mine_files.append(f"faces_clip/{t:02d}/{i:06d}.jpg")
+    assert sorted(mine_files) == sorted(names)
+    np.savez_compressed(os.path.join(OUT, "face.npz"), **out)
+    print("face.npz", len(names), "crops;", [len(out[f"dets_{i}"]) for i in range(6)], "detections per frame")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if len(sys.argv) > 1 and sys.argv[1] == "face":          # only the face-detector fixture (the others are unchanged)
+        with harness.reference_env() as wd:
+            make_face(wd)
+        return
     with harness.reference_env() as wd:
         # run.py imports get_prob_video, which loads the (CWD-relative) weight files at import time
         harness.save_video_weights(wd, syn.make_vs_state_dict(0, "spread"), syn.make_vd_state_dict(1))
@@ -407,6 +539,7 @@ def main():
         make_audio()
         make_resample(wd)
         make_pred_av(wd)
+        make_face(wd)
 
 
 if __name__ == "__main__":

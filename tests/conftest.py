@@ -19,7 +19,7 @@ def golden():
     import numpy as np
 
     return {name: np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
-            for name in ("fusion", "preprocess", "video", "audio", "weight_search", "resample", "pred_av")}
+            for name in ("fusion", "preprocess", "video", "audio", "weight_search", "resample", "pred_av", "face")}
 
 
 @pytest.fixture(scope="session")

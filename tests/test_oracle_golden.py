@@ -226,3 +226,68 @@ def test_jpeg_host_parser_matches_oracle_header():
         jpeg.parse(buf.tobytes())
     with pytest.raises(jpeg.UnsupportedJpeg):
         jpeg.parse(b"not a jpeg at all")
+
+
+# ------------------------------------------------------------------------------------------ face detector
+def test_face_oracle_matches_reference(golden):
+    """oracle/face.py against what the reference's own RetinaFace / RetinaFacePredictor returned (tests/golden/face.npz):
+    raw network outputs bit-identical (same torch ops in the same order), detections per frame bit-identical."""
+    from oracle import face as ofa
+
+    g = golden["face"]
+    sd = syn.make_retinaface_state_dict(5, "spread")
+    fr = syn.make_frames(40, 1, 100, 136)[0]
+    loc, conf, lm = ofa.forward(ofa.prepare(fr), sd)
+    assert np.array_equal(loc[0].numpy(), g["raw_loc"]) and np.array_equal(conf[0].numpy(), g["raw_conf"])
+    assert np.array_equal(lm[0].numpy(), g["raw_landms"])
+    assert loc.shape[1] == ofa.prior_box(100, 136).shape[0] == 2 * (13 * 17 + 7 * 9 + 4 * 5)
+    frames = syn.make_frames(41, 6, 150, 200)
+    tracker = ofa.SimpleFaceTracker(0.4, 0.0)
+    ids = []
+    for i in (0, 3, 5):
+        assert np.array_equal(ofa.predict(sd, frames[i]), g[f"dets_{i}"]), i
+    for i in range(6):
+        ids += tracker(g[f"dets_{i}"])
+    assert ids == list(g["ids"])
+    assert np.array_equal(ofa.predict(sd, frames[0][..., ::-1].copy(), rgb=True), g["dets_0"])
+
+
+def test_face_tracker_matches_reference(golden):
+    from oracle import face as ofa
+    from oracle.make_golden import face_tracker_sequences
+
+    g = golden["face"]
+    tracker = ofa.SimpleFaceTracker(0.4, 0.0)
+    for s, seq in enumerate(face_tracker_sequences()):
+        tracker.reset()
+        got = []
+        for boxes in seq:
+            got += [-1 if v is None else v for v in tracker(boxes)]
+        assert got == list(g[f"track_{s}"]), s
+    assert -1 in list(g["track_0"])                                   # the zero-area box stays untracked
+
+
+def test_face_nms_properties():
+    """Greedy NMS (py_cpu_nms.py:11-39): survivors are mutually below the IoU threshold, every suppressed box overlaps a
+    higher-scoring survivor (tie order is whatever numpy's default argsort yields: the host side calls the same function)."""
+    from oracle import face as ofa
+
+    rng = np.random.default_rng(0)
+    xy = rng.uniform(0, 100, (300, 2))
+    dets = np.concatenate([xy, xy + rng.uniform(5, 40, (300, 2)), rng.uniform(0, 1, (300, 1))], axis=1).astype(np.float32)
+    dets[10, 4] = 2.0
+    dets[11, :4] = dets[10, :4]                                       # an exact duplicate of the best box is suppressed
+    keep = ofa.nms(dets, 0.4, 5000)
+    assert keep[0] == 10 and 11 not in keep
+
+    def iou(a, b):
+        w = max(0.0, min(a[2], b[2]) - max(a[0], b[0]) + 1)
+        h = max(0.0, min(a[3], b[3]) - max(a[1], b[1]) + 1)
+        return w * h / ((a[2] - a[0] + 1) * (a[3] - a[1] + 1) + (b[2] - b[0] + 1) * (b[3] - b[1] + 1) - w * h)
+
+    for i, a in enumerate(keep):
+        for b in keep[:i]:
+            assert iou(dets[a], dets[b]) <= 0.4
+    for j in set(range(300)) - set(keep):
+        assert any(iou(dets[j], dets[k]) > 0.4 and dets[k, 4] >= dets[j, 4] for k in keep)
+    assert len(ofa.nms(dets, 0.4, 5)) <= 5                            # top_k truncates BEFORE suppression

@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import gc
 import math
-from typing import Dict, Optional, Tuple
+from typing import List, Dict, Optional, Tuple
 
 import torch
 
@@ -258,6 +258,88 @@ class VSNet:
         feat = ops.linear(pooled, fc1.wt, fc1.bias, act=ops.ACT_RELU, out_dtype=torch.float32)
         probs = ops.small_linear(feat, self.w["fc2_w"], self.w["fc2_b"], softmax=True)
         return probs, feat
+
+
+class RetinaFaceNet:
+    """RetinaFace-ResNet50 face detector (retina_face.py:48-115 of the reference's ibug package):
+    detect(frames) with frames = uint8 [n,H,W,3] video frames on the device -> decoded rows [n, P, 15] fp32
+    (x1, y1, x2, y2, score, 5 landmarks; priors in the reference's order).  Any frame size; a batch shares one size."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], precision: str = "bf16", device: str = "cuda:0"):
+        require_device()
+        self.dtype = _dtype(precision)
+        _lib.load("fp16" if self.dtype == torch.float16 else "bf16")
+        self.device = torch.device(device)
+        self.w = weights.pack_retinaface(state_dict, self.device, self.dtype)
+        self._maps: Dict[tuple, torch.Tensor] = {}
+
+    def _conv(self, x, pc: weights.PackedConv, act: int, residual=None, out=None) -> torch.Tensor:
+        pad = (pc.k - 1) // 2
+        if pc.k == 3 and pc.stride == 2 and not _tc(self.dtype):
+            # fp32 mode has no strided k x k implicit GEMM: stride-1 conv, then every second pixel (the same values)
+            full = ops.conv2d_nhwc(x, pc.wt, pc.bias, kh=3, kw=3, stride=1, pad_h=1, pad_w=1, act=act)
+            n, h, w, c = full.shape
+            y = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), device=self.device, dtype=self.dtype)
+            ops.subsample_rows(full, 2, y.view(-1, c))
+            return y
+        return ops.conv2d_nhwc(x, pc.wt, pc.bias, kh=pc.k, kw=pc.k, stride=pc.stride, pad_h=pad, pad_w=pad, residual=residual,
+                               act=act, out=out)
+
+    def _map(self, n_in: int, n_out: int) -> torch.Tensor:
+        key = (n_in, n_out)
+        if key not in self._maps:
+            self._maps[key] = ops.nearest_source_index(n_in, n_out).to(self.device)
+        return self._maps[key]
+
+    def _merge(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        return ops.upsample_add(a, b, self._map(b.shape[1], a.shape[1]), self._map(b.shape[2], a.shape[2]))
+
+    def _ssh(self, x: torch.Tensor, w: dict) -> torch.Tensor:
+        """retina_face_net.py:43-62; relu(cat(...)) = every branch's last conv with a ReLU epilogue writing its channel slice."""
+        n, h, ww, _ = x.shape
+        out = torch.empty((n, h, ww, 256), device=self.device, dtype=self.dtype)
+        self._conv(x, w["conv3X3"], ops.ACT_RELU, out=out[..., :128])
+        c5_1 = self._conv(x, w["conv5X5_1"], ops.ACT_RELU)
+        self._conv(c5_1, w["conv5X5_2"], ops.ACT_RELU, out=out[..., 128:192])
+        c7_2 = self._conv(c5_1, w["conv7X7_2"], ops.ACT_RELU)
+        self._conv(c7_2, w["conv7x7_3"], ops.ACT_RELU, out=out[..., 192:])
+        return out
+
+    def heads(self, frames: torch.Tensor, rgb: bool = False, taps: Optional[dict] = None) -> List[torch.Tensor]:
+        """-> per pyramid level (strides 8, 16, 32) the fp32 [n*fh*fw, 64] head matrix: columns 0-3 class logits
+        (anchor 0: background, face; anchor 1), 4-11 box, 12-31 landmark regressions."""
+        w = self.w
+        y = ops.det_stem(frames, w["stem_w"], w["stem_b"], self.dtype, rgb)
+        if taps is not None:
+            taps["stem"] = y
+        y = ops.maxpool3x3s2p1(y)
+        if taps is not None:
+            taps["pool"] = y
+        feats = []
+        for blk in w["blocks"]:
+            idn = self._conv(y, blk["ds"], ops.ACT_NONE) if "ds" in blk else y
+            t = self._conv(y, blk["conv1"], ops.ACT_RELU)
+            t = self._conv(t, blk["conv2"], ops.ACT_RELU)
+            y = self._conv(t, blk["conv3"], ops.ACT_RELU, residual=idn)
+            if blk["last_of_layer"]:
+                if taps is not None:
+                    taps[f"layer{blk['layer']}"] = y
+                if blk["layer"] >= 2:
+                    feats.append(y)
+        o1, o2, o3 = (self._conv(f, pc, ops.ACT_RELU) for f, pc in zip(feats, w["fpn_out"]))
+        o2 = self._conv(self._merge(o2, o3), w["fpn_merge"][1], ops.ACT_RELU)
+        o1 = self._conv(self._merge(o1, o2), w["fpn_merge"][0], ops.ACT_RELU)
+        out = []
+        for i, (o, sw, hw) in enumerate(zip((o1, o2, o3), w["ssh"], w["heads"])):
+            f = self._ssh(o, sw)
+            if taps is not None:
+                taps[f"fpn{i + 1}"], taps[f"ssh{i + 1}"] = o, f
+            out.append(ops.linear(f.view(-1, 256), hw.wt, hw.bias, out_dtype=torch.float32))
+        return out
+
+    def detect(self, frames: torch.Tensor, rgb: bool = False) -> torch.Tensor:
+        n, h, w, _ = frames.shape
+        return ops.det_decode(self.heads(frames, rgb), n, h, w)
 
 
 class VDNet:

@@ -19,7 +19,7 @@ from ._lib import check as _check
 __all__ = [
     "F32", "BF16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "dtype_code", "torch_dtype", "contract", "conv2d_nhwc",
     "linear", "preprocess", "fuse_compound", "weight_search_confusion", "softmax7", "window_to_frame_mean", "gather_rows", "maxpool3x3s2",
-    "stem_pool", "stem_pool_u8", "subsample_rows", "avgpool", "small_linear", "lstm_cell", "gru_cell", "split_bf16x3", "sinc_resample_bank", "pcm16_to_mono", "audio_normalize_windows", "w2v_conv0_ln_gelu", "w2v_conv0_tc", "layernorm", "add_rows",
+    "stem_pool", "stem_pool_u8", "subsample_rows", "avgpool", "small_linear", "lstm_cell", "gru_cell", "split_bf16x3", "sinc_resample_bank", "pcm16_to_mono", "audio_normalize_windows", "w2v_conv0_ln_gelu", "w2v_conv0_tc", "det_stem", "maxpool3x3s2p1", "upsample_add", "det_decode", "nearest_source_index", "layernorm", "add_rows",
     "attention", "maxpool1d5_relu", "avgpool1d_relu", "cast", "sm_limit",
 ]
 
@@ -384,6 +384,60 @@ def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
     y = torch.empty((n, (h - 3) // 2 + 1, (w - 3) // 2 + 1, c), device=x.device, dtype=x.dtype)
     check(_L(x).avcer_maxpool3x3s2(x.data_ptr(), n, h, w, c, y.data_ptr(), dtype_code(x.dtype), _stream()))
     return y
+
+
+# ----------------------------------------------------------------------------------------- face detector layers
+def det_stem(frames: torch.Tensor, wt: torch.Tensor, bias: torch.Tensor, dtype: torch.dtype, rgb: bool = False) -> torch.Tensor:
+    """frames: uint8 [n,h,w,3] video frames (B,G,R; rgb: R,G,B) -> relu(conv7x7/2(frames - mean) + bias) [n,ceil(h/2),ceil(w/2),64]."""
+    _cuda(frames, "frames")
+    n, h, w, c = frames.shape
+    assert frames.dtype == torch.uint8 and c == 3 and frames.is_contiguous() and wt.shape == (147, 64) and wt.dtype == torch.float32
+    y = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 64), device=frames.device, dtype=dtype)
+    with _Timed("det_stem", 2.0 * y.numel() * 147):
+        _check(_L(y).avcer_det_stem(frames.data_ptr(), n, h, w, int(rgb), wt.data_ptr(), bias.data_ptr(), y.data_ptr(), dtype_code(dtype), _stream()))
+    return y
+
+
+def maxpool3x3s2p1(x: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = x.shape
+    assert x.is_contiguous()
+    y = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), device=x.device, dtype=x.dtype)
+    check(_L(x).avcer_maxpool3x3s2p1(x.data_ptr(), n, h, w, c, y.data_ptr(), dtype_code(x.dtype), _stream()))
+    return y
+
+
+def nearest_source_index(n_in: int, n_out: int) -> torch.Tensor:
+    """Source index of every output position of F.interpolate(mode="nearest", size=n_out) (ATen
+    nearest_neighbor_compute_source_index: min(int(floorf(dst * scale)), n_in - 1) with the fp32 scale n_in / n_out)."""
+    import numpy as np
+
+    scale = np.float32(n_in) / np.float32(n_out)
+    idx = np.floor(np.arange(n_out, dtype=np.float32) * scale).astype(np.int64)
+    return torch.from_numpy(np.minimum(idx, n_in - 1).astype(np.int32))
+
+
+def upsample_add(a: torch.Tensor, b: torch.Tensor, ymap: torch.Tensor, xmap: torch.Tensor) -> torch.Tensor:
+    """a [n,h,w,c] + nearest-upsampled b [n,hb,wb,c]; ymap [h] / xmap [w] int32 device tensors (nearest_source_index)."""
+    n, h, w, c = a.shape
+    assert a.is_contiguous() and b.is_contiguous() and b.shape[0] == n and b.shape[3] == c and a.dtype == b.dtype
+    assert ymap.dtype == torch.int32 and xmap.dtype == torch.int32 and ymap.numel() == h and xmap.numel() == w
+    out = torch.empty_like(a)
+    check(_L(a).avcer_upsample_add(a.data_ptr(), b.data_ptr(), n, h, w, b.shape[1], b.shape[2], c, ymap.data_ptr(), xmap.data_ptr(),
+                                   out.data_ptr(), dtype_code(a.dtype), _stream()))
+    return out
+
+
+def det_decode(heads: Sequence[torch.Tensor], n: int, height: int, width: int) -> torch.Tensor:
+    """heads: three fp32 [n * fh_k * fw_k, pitch] matrices (strides 8, 16, 32) -> dets [n, P, 15] fp32."""
+    fhw = [((height + s - 1) // s, (width + s - 1) // s) for s in (8, 16, 32)]
+    pitch = heads[0].stride(0)
+    for hk, (fh, fw) in zip(heads, fhw):
+        assert hk.dtype == torch.float32 and hk.shape[0] == n * fh * fw and hk.stride(0) == pitch and hk.stride(1) == 1
+    P = 2 * sum(fh * fw for fh, fw in fhw)
+    dets = torch.empty((n, P, 15), device=heads[0].device, dtype=torch.float32)
+    check(_lib.load().avcer_det_decode(heads[0].data_ptr(), heads[1].data_ptr(), heads[2].data_ptr(), pitch, n, height, width,
+                                       dets.data_ptr(), _stream()))
+    return dets
 
 
 def avgpool(x: torch.Tensor) -> torch.Tensor:

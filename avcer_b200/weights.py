@@ -101,6 +101,59 @@ def split_bf16x3_weight(w: torch.Tensor, dtype: torch.dtype = torch.bfloat16) ->
     return torch.cat([hi, hi, lo], dim=1)
 
 
+RF_BLOCKS = (3, 4, 6, 3)
+RF_PLANES = (64, 128, 256, 512)
+
+
+def pack_retinaface(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> dict:
+    """RetinaFace-ResNet50 (data/face_detection/ibug/face_detection/retina_face/retina_face.py:48-115; state_dict keys
+    body.* = torchvision resnet50, fpn.*, ssh{1,2,3}.*, ClassHead / BboxHead / LandmarkHead.{0,1,2}.conv1x1).  BatchNorm
+    (eps 1e-5) folded; the stem stays fp32 [147, 64] (row = (ky*7 + kx)*3 + c) for avcer_det_stem; the three 1x1 heads of a
+    level become one [64, 256] matrix (rows: 4 class, 8 box, 20 landmark logits, 32 zero rows)."""
+    eps = 1e-5
+
+    def dev(t, dt=None):
+        return t.to(device=device, dtype=dt or dtype).contiguous()
+
+    def conv_bn(wkey, bnkey, k, stride=1):
+        w, b = _fold_bn(sd[wkey], sd, bnkey, eps)
+        return PackedConv(dev(_tap_major(w)), dev(b, torch.float32), w.shape[1], w.shape[0], k, stride)
+
+    out = {}
+    w, b = _fold_bn(sd["body.conv1.weight"], sd, "body.bn1", eps)
+    out["stem_w"] = dev(w.permute(2, 3, 1, 0).reshape(147, 64), torch.float32)
+    out["stem_b"] = dev(b, torch.float32)
+    blocks: List[dict] = []
+    for li, (planes, nblocks) in enumerate(zip(RF_PLANES, RF_BLOCKS), start=1):
+        for bi in range(nblocks):
+            p = f"body.layer{li}.{bi}"
+            stride = 2 if (li > 1 and bi == 0) else 1
+            blk = {"conv1": conv_bn(p + ".conv1.weight", p + ".bn1", 1), "conv2": conv_bn(p + ".conv2.weight", p + ".bn2", 3, stride),
+                   "conv3": conv_bn(p + ".conv3.weight", p + ".bn3", 1), "last_of_layer": bi == nblocks - 1, "layer": li}
+            if bi == 0:
+                blk["ds"] = conv_bn(p + ".downsample.0.weight", p + ".downsample.1", 1, stride)
+            blocks.append(blk)
+    out["blocks"] = blocks
+    out["fpn_out"] = [conv_bn(f"fpn.output{i}.0.weight", f"fpn.output{i}.1", 1) for i in (1, 2, 3)]
+    out["fpn_merge"] = [conv_bn(f"fpn.merge{i}.0.weight", f"fpn.merge{i}.1", 3) for i in (1, 2)]
+    out["ssh"] = [{name: conv_bn(f"ssh{i}.{name}.0.weight", f"ssh{i}.{name}.1", 3)
+                   for name in ("conv3X3", "conv5X5_1", "conv5X5_2", "conv7X7_2", "conv7x7_3")} for i in (1, 2, 3)]
+    heads = []
+    for i in range(3):
+        wh = torch.zeros(64, 256)
+        bh = torch.zeros(64)
+        row = 0
+        for name in ("ClassHead", "BboxHead", "LandmarkHead"):
+            wi, bi_ = sd[f"{name}.{i}.conv1x1.weight"].float().reshape(-1, 256), sd[f"{name}.{i}.conv1x1.bias"].float()
+            wh[row:row + wi.shape[0]] = wi
+            bh[row:row + wi.shape[0]] = bi_
+            row += wi.shape[0]
+        assert row == 32
+        heads.append(PackedConv(dev(wh), dev(bh, torch.float32), 256, 64, 1, 1))
+    out["heads"] = heads
+    return out
+
+
 def pack_conv0_tc(w: torch.Tensor, b: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """wav2vec2 conv0 filter bank [512, 10] + bias [512] -> the B operand of avcer_w2v_conv0_tc: rows
     [w_hi(10) | w_hi(10) | w_lo(10) | b_hi | b_lo] (K = 32, the weight side of a 16-bit x3 product whose activation side is

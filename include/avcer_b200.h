@@ -322,6 +322,26 @@ int avcer_jpeg_decode(const uint8_t* raw, const avcer_jpeg_image* images, int n,
                       int64_t total_blocks, int64_t total_pixels, uint8_t* data, int64_t* lens, int16_t* coefs,
                       uint8_t* planes, uint8_t* out, int32_t* status, void* stream);
 
+/* ---- Face detector: RetinaFace-ResNet50 behind data/get_face_images.py:38-63.  The 1x1 / 3x3
+ * convolutions of body, FPN, SSH and heads are avcer_contract calls; these are the layers it does not cover. ---- */
+/* Stem on raw video frames (retina_face_predictor.py:61-67 + torchvision resnet50 conv1/bn1/relu): frames [n,h,w,3] uint8
+ * (B,G,R; rgb != 0: R,G,B), minus (104,117,123), conv 7x7 / 2 pad 3 with wt [147][64] fp32 (row = (ky*7+kx)*3 + c in BGR
+ * order, BatchNorm folded) + bias [64], ReLU -> out [n, ceil(h/2), ceil(w/2), 64] (dtype). */
+int avcer_det_stem(const uint8_t* frames, int n, int h, int w, int rgb, const float* wt, const float* bias,
+                   void* out, int dtype, void* stream);
+/* Max pool 3x3 / 2 pad 1 over NHWC (torchvision resnet50.maxpool): [n,h,w,c] -> [n, ceil(h/2), ceil(w/2), c]. */
+int avcer_maxpool3x3s2p1(const void* x, int n, int h, int w, int c, void* y, int dtype, void* stream);
+/* FPN top-down merge (retina_face_net.py:88-94): out[n,y,x,:] = a[n,y,x,:] + b[n, ymap[y], xmap[x], :] with a, out
+ * [n,h,w,c], b [n,hb,wb,c]; ymap [h] / xmap [w] int32 = the source indices of F.interpolate(mode="nearest"). */
+int avcer_upsample_add(const void* a, const void* b, int n, int h, int w, int hb, int wb, int c,
+                       const int32_t* ymap, const int32_t* xmap, void* out, int dtype, void* stream);
+/* Anchors (prior_box.py:17-33), 2-class softmax, box and landmark decoding (box_utils.py:210-249) and scaling to pixels
+ * (retina_face_predictor.py:75-84) of the three head maps: heads_k [n * ceil(height/s_k) * ceil(width/s_k), head_pitch]
+ * fp32 with s = 8, 16, 32 and columns [cls a0 (bg, face), cls a1 | box a0 (4), a1 | landmarks a0 (10), a1] ->
+ * dets [n, P, 15] fp32 rows (x1, y1, x2, y2, score, 5 x (x, y)), priors in the reference's order. */
+int avcer_det_decode(const float* heads0, const float* heads1, const float* heads2, int64_t head_pitch, int n,
+                     int height, int width, float* dets, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

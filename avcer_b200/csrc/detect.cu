@@ -77,6 +77,33 @@ det_stem_kernel(const uint8_t* __restrict__ frames, int h, int w, int rgb, const
   }
 }
 
+// ------------------------------------------------------------------ stem input for the tensor-core path
+// uint8 frame -> zero-bordered NHWC4 [n, hp, wp, 4] in the 16-bit storage type: input pixel (y, x) lands at (y + 3, x + 3)
+// as (B - 104, G - 117, R - 123, 0) -- integers of magnitude <= 151, exact in bf16 and fp16 -- everything else is zero, so
+// that the 7x7 / 2 pad-3 stem becomes the strip-mode contraction the VS stem uses (avcer_contract a_strip: output ox of a
+// filter row reads the 8 pixels x 4 channels starting at padded column 2 ox; pixel 7 and channel 3 carry zero weights).
+__global__ void det_prepare_kernel(const uint8_t* __restrict__ frames, int n, int h, int w, int rgb, int hp, int wp,
+                                   __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * hp * wp) return;
+  const int px = (int)(i % wp), py = (int)((i / wp) % hp), b = (int)(i / ((long long)wp * hp));
+  const int x = px - 3, y = py - 3;
+  float v[3] = {0.f, 0.f, 0.f};
+  if (x >= 0 && x < w && y >= 0 && y < h) {
+    const uint8_t* s = frames + (((long long)b * h + y) * w + x) * 3;
+    v[0] = (float)s[rgb ? 2 : 0] - 104.f;
+    v[1] = (float)s[1] - 117.f;
+    v[2] = (float)s[rgb ? 0 : 2] - 123.f;
+  }
+  uint2 u;
+  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+  h2[0] = __floats2bfloat162_rn(v[0], v[1]);
+  h2[1] = __floats2bfloat162_rn(v[2], 0.f);
+  reinterpret_cast<uint2*>(out)[i] = u;
+}
+
 // ------------------------------------------------------------------ max pool 3x3/2 pad 1 (torchvision resnet50.maxpool)
 template <typename T>
 __global__ void maxpool3x3s2p1_kernel(const T* __restrict__ x, int n, int h, int w, int c, int ho, int wo, T* __restrict__ y) {
@@ -225,6 +252,15 @@ extern "C" int avcer_det_stem(const uint8_t* frames, int n, int h, int w, int rg
     launch_pdl(kern, grid, 256, ST_SMEM, as_stream(stream), frames, h, w, rgb, wt, bias, (T*)out, ho, wo);
   });
   return check_launch("det_stem");
+}
+
+extern "C" int avcer_det_prepare(const uint8_t* frames, int n, int h, int w, int rgb, int hp, int wp, void* out, void* stream) {
+  AVCER_REQUIRE(n >= 0 && h >= 1 && w >= 1 && hp >= h + 6 && wp >= w + 6, "det_prepare: bad shape");
+  AVCER_REQUIRE((reinterpret_cast<uintptr_t>(out) & 7) == 0, "det_prepare: out must be 8-byte aligned");
+  const long long total = (long long)n * hp * wp;
+  if (total == 0) return 0;
+  launch_pdl(det_prepare_kernel, blocks_for(total, 256), 256, 0, as_stream(stream), frames, n, h, w, rgb, hp, wp, (__nv_bfloat16*)out);
+  return check_launch("det_prepare");
 }
 
 extern "C" int avcer_maxpool3x3s2p1(const void* x, int n, int h, int w, int c, void* y, int dtype, void* stream) {

@@ -31,22 +31,30 @@ cfg_re50 = {"name": "Resnet50", "min_sizes": [[16, 32], [64, 128], [256, 512]], 
 def greedy_nms(dets: np.ndarray, thresh: float, top_k: int) -> List[int]:
     """Indices kept by py_cpu_nms (retina_face/py_cpu_nms.py:11-39): candidates in descending score order (numpy's default
     argsort reversed, cut to top_k first), a candidate is dropped when its IoU with an earlier kept one exceeds `thresh`
-    ('+1' pixel widths, float32 arithmetic of the float32 rows)."""
+    ('+1' pixel widths, float32 arithmetic of the float32 rows).  The overlaps of a block of candidates against all later
+    ones are formed in one vectorised pass (the same elementwise float32 operations as the reference's per-box pass), the
+    greedy scan then only combines boolean rows."""
     order = dets[:, 4].argsort()[::-1][:top_k]
     b = dets[order]
-    area = (b[:, 2] - b[:, 0] + 1) * (b[:, 3] - b[:, 1] + 1)
-    alive = np.ones(len(b), dtype=bool)
+    n = len(b)
+    x1, y1, x2, y2 = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
+    area = (x2 - x1 + 1) * (y2 - y1 + 1)
+    alive = np.ones(n, dtype=bool)
     keep: List[int] = []
-    for i in range(len(b)):
-        if not alive[i]:
+    block = 256
+    for lo in range(0, n, block):
+        hi = min(n, lo + block)
+        if not alive[lo:hi].any():
             continue
-        keep.append(int(order[i]))
-        rest = slice(i + 1, None)
-        w = np.maximum(0.0, np.minimum(b[i, 2], b[rest, 2]) - np.maximum(b[i, 0], b[rest, 0]) + 1)
-        h = np.maximum(0.0, np.minimum(b[i, 3], b[rest, 3]) - np.maximum(b[i, 1], b[rest, 1]) + 1)
+        w = np.maximum(0.0, np.minimum(x2[lo:hi, None], x2[None, lo:]) - np.maximum(x1[lo:hi, None], x1[None, lo:]) + 1)
+        h = np.maximum(0.0, np.minimum(y2[lo:hi, None], y2[None, lo:]) - np.maximum(y1[lo:hi, None], y1[None, lo:]) + 1)
         inter = w * h
         with np.errstate(invalid="ignore", divide="ignore"):
-            alive[rest] &= inter / (area[i] + area[rest] - inter) <= thresh       # a NaN overlap suppresses, like the reference
+            ok = inter / (area[lo:hi, None] + area[None, lo:] - inter) <= thresh      # a NaN overlap suppresses, like the reference
+        for i in range(lo, hi):
+            if alive[i]:
+                keep.append(int(order[i]))
+                alive[i + 1:] &= ok[i - lo, i + 1 - lo:]
     return keep
 
 
@@ -73,6 +81,7 @@ class RetinaFacePredictor:
             sd = sd["state_dict"]
         sd = {k.split("module.", 1)[-1] if k.startswith("module.") else k: v for k, v in sd.items()}
         self.net = nets.RetinaFaceNet(sd, precision or _cfg.precision(), str(device))
+        self._pinned: Optional[torch.Tensor] = None
 
     @staticmethod
     def get_model(name: str = "resnet50") -> SimpleNamespace:
@@ -103,8 +112,8 @@ class RetinaFacePredictor:
     def detect_batch(self, frames: Union[np.ndarray, torch.Tensor], rgb: bool = False) -> List[np.ndarray]:
         """frames: uint8 [n,H,W,3] (numpy, or a tensor already on the device) -> per frame the [k,15] float32 rows the
         reference's call returns (x1, y1, x2, y2, score, 5 landmark points), in its order."""
-        if isinstance(frames, np.ndarray):
-            frames = torch.from_numpy(np.ascontiguousarray(frames)).to(self.net.device, non_blocking=True)
+        if not isinstance(frames, torch.Tensor):
+            frames = self._upload(frames)
         assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
         n = frames.shape[0]
         dets = self.net.detect(frames.contiguous(), rgb)                                # [n, P, 15] on the device
@@ -113,6 +122,19 @@ class RetinaFacePredictor:
         rows = dets[hit[:, 0], hit[:, 1]].cpu().numpy()
         owner = hit[:, 0].cpu().numpy()
         return [self._select(rows[owner == i]) for i in range(n)]
+
+    def _upload(self, frames: Union[np.ndarray, Sequence[np.ndarray]]) -> torch.Tensor:
+        """Host frames (one [n,H,W,3] array or a list of [H,W,3] arrays, e.g. straight from cv2.VideoCapture.read) -> device,
+        staged through a pinned buffer that is kept between calls."""
+        n = len(frames)
+        shape = (n,) + tuple(frames[0].shape)
+        if self._pinned is None or self._pinned.numel() < int(np.prod(shape)):
+            self._pinned = torch.empty(int(np.prod(shape)), dtype=torch.uint8).pin_memory()
+        stage = self._pinned[:int(np.prod(shape))].view(shape)
+        dst = stage.numpy()
+        for i in range(n):
+            dst[i] = frames[i]
+        return stage.to(self.net.device, non_blocking=True)
 
     def __call__(self, image: np.ndarray, rgb: bool = True) -> np.ndarray:
         return self.detect_batch(image[None], rgb=rgb)[0]

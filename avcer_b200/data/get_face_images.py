@@ -11,7 +11,6 @@ from __future__ import annotations
 import os
 
 import cv2
-import numpy as np
 
 from .. import config
 from .face_detection import RetinaFacePredictor, SimpleFaceTracker
@@ -71,6 +70,6 @@ class VideoPredictor:
                     break
                 frames.append(fr)
             if frames:
-                for fr, dets in zip(frames, self.model.detect_batch(np.stack(frames), rgb=False)):
+                for fr, dets in zip(frames, self.model.detect_batch(frames, rgb=False)):
                     self._emit(fr, dets, save_path, name_file)
         self.face_tracker.reset()

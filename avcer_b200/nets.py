@@ -271,6 +271,7 @@ class RetinaFaceNet:
         _lib.load("fp16" if self.dtype == torch.float16 else "bf16")
         self.device = torch.device(device)
         self.w = weights.pack_retinaface(state_dict, self.device, self.dtype)
+        self.stem_tc = True            # 16-bit modes: stem as strip-mode tcgen05 contractions (False: the fp32 direct-conv kernel)
         self._maps: Dict[tuple, torch.Tensor] = {}
 
     def _conv(self, x, pc: weights.PackedConv, act: int, residual=None, out=None) -> torch.Tensor:
@@ -309,7 +310,10 @@ class RetinaFaceNet:
         """-> per pyramid level (strides 8, 16, 32) the fp32 [n*fh*fw, 64] head matrix: columns 0-3 class logits
         (anchor 0: background, face; anchor 1), 4-11 box, 12-31 landmark regressions."""
         w = self.w
-        y = ops.det_stem(frames, w["stem_w"], w["stem_b"], self.dtype, rgb)
+        if "stem_packed" in w and self.stem_tc:
+            y = ops.det_stem_tc(frames, w["stem_wt"], w["stem_packed"], w["stem_b"], self.dtype, rgb)
+        else:
+            y = ops.det_stem(frames, w["stem_w"], w["stem_b"], self.dtype, rgb)
         if taps is not None:
             taps["stem"] = y
         y = ops.maxpool3x3s2p1(y)

@@ -19,7 +19,7 @@ from ._lib import check as _check
 __all__ = [
     "F32", "BF16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "dtype_code", "torch_dtype", "contract", "conv2d_nhwc",
     "linear", "preprocess", "fuse_compound", "weight_search_confusion", "softmax7", "window_to_frame_mean", "gather_rows", "maxpool3x3s2",
-    "stem_pool", "stem_pool_u8", "subsample_rows", "avgpool", "small_linear", "lstm_cell", "gru_cell", "split_bf16x3", "sinc_resample_bank", "pcm16_to_mono", "audio_normalize_windows", "w2v_conv0_ln_gelu", "w2v_conv0_tc", "det_stem", "maxpool3x3s2p1", "upsample_add", "det_decode", "nearest_source_index", "layernorm", "add_rows",
+    "stem_pool", "stem_pool_u8", "subsample_rows", "avgpool", "small_linear", "lstm_cell", "gru_cell", "split_bf16x3", "sinc_resample_bank", "pcm16_to_mono", "audio_normalize_windows", "w2v_conv0_ln_gelu", "w2v_conv0_tc", "det_stem", "det_stem_tc", "maxpool3x3s2p1", "upsample_add", "det_decode", "nearest_source_index", "layernorm", "add_rows",
     "attention", "maxpool1d5_relu", "avgpool1d_relu", "cast", "sm_limit",
 ]
 
@@ -395,6 +395,29 @@ def det_stem(frames: torch.Tensor, wt: torch.Tensor, bias: torch.Tensor, dtype: 
     y = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 64), device=frames.device, dtype=dtype)
     with _Timed("det_stem", 2.0 * y.numel() * 147):
         _check(_L(y).avcer_det_stem(frames.data_ptr(), n, h, w, int(rgb), wt.data_ptr(), bias.data_ptr(), y.data_ptr(), dtype_code(dtype), _stream()))
+    return y
+
+
+def det_stem_tc(frames: torch.Tensor, wt: torch.Tensor, wt_packed: torch.Tensor, bias: torch.Tensor, dtype: torch.dtype,
+                rgb: bool = False) -> torch.Tensor:
+    """The same layer on the tensor cores (16-bit storage): avcer_det_prepare writes the zero-bordered NHWC4 copy of the
+    frames (mean-subtracted pixels are exact integers), then one strip-mode contraction per band of 128 output columns
+    (wt [64, 7*32] / wt_packed: the VS stem's layouts, weights.pack_retinaface)."""
+    _cuda(frames, "frames")
+    n, h, w, c = frames.shape
+    assert frames.dtype == torch.uint8 and c == 3 and frames.is_contiguous() and dtype in (torch.bfloat16, torch.float16)
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    bands = (wo + 127) // 128
+    hp = h + 6
+    wp = (max(w + 6, 256 * (bands - 1) + 272) + 15) // 16 * 16          # a band's strip is 17 x 64 elements = 272 pixels
+    x = torch.empty((n, hp, wp, 4), device=frames.device, dtype=dtype)
+    check(_L(x).avcer_det_prepare(frames.data_ptr(), n, h, w, int(rgb), hp, wp, x.data_ptr(), _stream()))
+    y = torch.empty((n, ho, wo, 64), device=frames.device, dtype=dtype)
+    for s in range(bands):
+        bw = min(128, wo - 128 * s)
+        contract(a=x, a_offset=256 * s * 4, a_dim=(64, 17, ho, n, 7), a_stride=(1, 64, 2 * wp * 4, hp * wp * 4, wp * 4), wt=wt, bias=bias,
+                 out=y[:, :, 128 * s:, :], out_stride=(64, wo * 64, ho * wo * 64), W=bw, H=ho, NB=n, cin=32, cout=64, taps_w=1, taps_h=7,
+                 tap_h_in_dim4=True, act=ACT_RELU, algo_k=147, a_strip=True, wt_packed=wt_packed)
     return y
 
 

@@ -123,6 +123,12 @@ def pack_retinaface(sd: Dict[str, torch.Tensor], device, dtype: torch.dtype) -> 
     w, b = _fold_bn(sd["body.conv1.weight"], sd, "body.bn1", eps)
     out["stem_w"] = dev(w.permute(2, 3, 1, 0).reshape(147, 64), torch.float32)
     out["stem_b"] = dev(b, torch.float32)
+    if dtype in (torch.bfloat16, torch.float16):
+        # tensor-core stem: the VS stem's strip-mode layouts ([64, 7 rows, 8 pixels x 4 channels]; pixel 7, channel 3 zero)
+        stem = torch.zeros(64, 7, 8, 4)
+        stem[:, :, :7, :3] = w.permute(0, 2, 3, 1)
+        out["stem_wt"] = dev(stem.reshape(64, 7 * 32))
+        out["stem_packed"] = dev(stem.reshape(8, 8, 7, 4, 8).permute(2, 3, 0, 1, 4).contiguous().reshape(-1))
     blocks: List[dict] = []
     for li, (planes, nblocks) in enumerate(zip(RF_PLANES, RF_BLOCKS), start=1):
         for bi in range(nblocks):

@@ -482,6 +482,38 @@ def main():
         except Exception as e:  # pragma: no cover  (cv2 missing: the figure is optional)
             micro["jpeg_decode_1500_crops"] = {"skipped": f"{type(e).__name__}: {e}"}
 
+        # the face detector that produces the crops (RetinaFace-ResNet50 on raw 1080p frames;
+        # the reference: one batch-1 call per frame, data/get_face_images.py:45-61)
+        try:
+            from avcer_b200 import nets as anets
+
+            fnet = anets.RetinaFaceNet(syn.make_retinaface_state_dict(5, "spread"), args.precision, str(dev))
+            fframes = torch.from_numpy(syn.make_frames(7, 8, 1080, 1920)).to(dev)
+            fl2 = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+            fnet.detect(fframes)
+            ops.PROFILE = fprof = []
+            fnet.detect(fframes)
+            torch.cuda.synchronize()
+            ops.PROFILE = None
+            fflop = sum(p[1] for p in fprof)
+            fts = []
+            for _ in range(5):
+                fl2.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fnet.detect(fframes)
+                b.record()
+                torch.cuda.synchronize()
+                fts.append(a.elapsed_time(b))
+            ft = statistics.median(fts)
+            micro["face_detect_8x1080p"] = {"bound": "tensor", "frames_per_s": 8 / ft * 1e3, "ms": ft, "gflop_per_frame": fflop / 8 / 1e9,
+                                            "achieved": fflop / ft / 1e9, "unit": "TFLOP/s", "peak": peaks["tf_burst"],
+                                            "frac": fflop / ft / 1e9 / peaks["tf_burst"],
+                                            "parity": "detections, track ids and crop files equal the unmodified reference's (tests/test_gpu_face.py)"}
+            del fnet, fframes, fl2
+        except Exception as e:  # pragma: no cover
+            micro["face_detect_8x1080p"] = {"skipped": f"{type(e).__name__}: {e}"}
+
     if rank != 0:
         if world > 1:
             torch.distributed.barrier()

@@ -329,6 +329,10 @@ int avcer_jpeg_decode(const uint8_t* raw, const avcer_jpeg_image* images, int n,
  * order, BatchNorm folded) + bias [64], ReLU -> out [n, ceil(h/2), ceil(w/2), 64] (dtype). */
 int avcer_det_stem(const uint8_t* frames, int n, int h, int w, int rgb, const float* wt, const float* bias,
                    void* out, int dtype, void* stream);
+/* The same stem's input for the tensor-core path: frames -> zero-bordered NHWC4 [n, hp, wp, 4] in the library's 16-bit
+ * storage type, pixel (y, x) at (y + 3, x + 3) as (B - 104, G - 117, R - 123, 0) (exact integers), zeros elsewhere; the
+ * convolution itself is then a strip-mode avcer_contract (a_strip) per band of 128 output columns. hp >= h + 6, wp >= w + 6. */
+int avcer_det_prepare(const uint8_t* frames, int n, int h, int w, int rgb, int hp, int wp, void* out, void* stream);
 /* Max pool 3x3 / 2 pad 1 over NHWC (torchvision resnet50.maxpool): [n,h,w,c] -> [n, ceil(h/2), ceil(w/2), c]. */
 int avcer_maxpool3x3s2p1(const void* x, int n, int h, int w, int c, void* y, int dtype, void* stream);
 /* FPN top-down merge (retina_face_net.py:88-94): out[n,y,x,:] = a[n,y,x,:] + b[n, ymap[y], xmap[x], :] with a, out

@@ -39,6 +39,31 @@ def test_det_stem_matches_torch(cuda_lib, h, w, rgb):
     assert float((got16 - ref).abs().max()) <= 2.0 ** -8 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("h,w,rgb", [(100, 136, False), (33, 300, True), (7, 5, False), (61, 515, False)])
+def test_det_stem_tensor_core_matches_torch(cuda_lib, dtype, h, w, rgb):
+    """The stem as strip-mode tcgen05 contractions over the zero-bordered NHWC4 copy of the frames (avcer_det_prepare +
+    avcer_contract a_strip, one call per band of 128 output columns: 300 -> 150 = 128 + 22, 515 -> 258 = 128 + 128 + 2):
+    the mean-subtracted pixels are exact in 16 bits, so against a torch conv with the SAME 16-bit-rounded filters only the
+    summation order and the output rounding differ."""
+    from avcer_b200 import ops, weights
+
+    g = torch.Generator().manual_seed(h * 1000 + w)
+    fr = torch.randint(0, 256, (2, h, w, 3), dtype=torch.uint8, generator=g)
+    wt = (torch.randn(64, 3, 7, 7, generator=g) * 0.01).to(dtype).float()
+    bias = torch.randn(64, generator=g) * 0.1
+    bgr = fr.flip(-1) if rgb else fr
+    x = (bgr.double() - torch.tensor([104.0, 117.0, 123.0], dtype=torch.float64)).permute(0, 3, 1, 2)
+    ref = F.relu(F.conv2d(x, wt.double(), bias.double(), stride=2, padding=3)).permute(0, 2, 3, 1).float()
+    stem = torch.zeros(64, 7, 8, 4)
+    stem[:, :, :7, :3] = wt.permute(0, 2, 3, 1)
+    packed = stem.reshape(8, 8, 7, 4, 8).permute(2, 3, 0, 1, 4).contiguous().reshape(-1)
+    got = ops.det_stem_tc(fr.to(DEV), stem.reshape(64, 224).to(DEV, dtype), packed.to(DEV, dtype), bias.to(DEV), dtype, rgb).float().cpu()
+    assert got.shape == ref.shape
+    ulp = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    assert bool(((got - ref).abs() <= ulp * ref.abs() + 1e-4 * float(ref.abs().max())).all()), float((got - ref).abs().max())
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 def test_maxpool_pad1_and_upsample_add(cuda_lib, dtype):
     from avcer_b200 import ops

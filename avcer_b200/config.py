@@ -16,7 +16,7 @@ PATH_STATIC = "src/weights/FER_static_ResNet50_AffectNet.pt"       # get_prob_vi
 PATH_DYNAMIC = "src/weights/FER_dinamic_LSTM_Aff-Wild2.pt"         # get_prob_video.py:51
 
 _state: Dict[str, object] = {"precision": "bf16", "device": "cuda:0", "vs": None, "vd": None, "audio": {},
-                             "engine": None, "audio_nets": {}, "jpeg": "gpu"}
+                             "engine": None, "audio_nets": {}, "jpeg": "gpu", "face": None, "face_predictor": None}
 
 
 def set_jpeg_decoder(which: str) -> None:
@@ -41,8 +41,11 @@ def set_device(device: str) -> None:
     reset()
 
 
-def set_state_dicts(vs=None, vd=None, audio: Optional[dict] = None) -> None:
-    """audio: {model_name or num_classes: state_dict}."""
+def set_state_dicts(vs=None, vd=None, audio: Optional[dict] = None, face=None) -> None:
+    """audio: {model_name or num_classes: state_dict}; face: the RetinaFace-ResNet50 state_dict of the face detector
+    (otherwise read from data/weights/Resnet50_Final.pth on first use, like the reference's ibug package)."""
+    if face is not None:
+        _state["face"] = face
     if vs is not None:
         _state["vs"] = vs
     if vd is not None:
@@ -55,6 +58,11 @@ def set_state_dicts(vs=None, vd=None, audio: Optional[dict] = None) -> None:
 def reset() -> None:
     _state["engine"] = None
     _state["audio_nets"] = {}
+    _state["face_predictor"] = None
+
+
+def face_state_dict():
+    return _state["face"]
 
 
 def precision() -> str:

@@ -35,8 +35,10 @@ class VideoPredictor:
         self.total_frames = int(self.video_stream.get(cv2.CAP_PROP_FRAME_COUNT))
 
     def init_predictor(self):
-        self.model = RetinaFacePredictor(threshold=0.8, device=self.device,
-                                         model=self._model_spec or RetinaFacePredictor.get_model("resnet50"), precision=self._precision)
+        spec = self._model_spec or RetinaFacePredictor.get_model("resnet50")
+        if self._model_spec is None and config.face_state_dict() is not None:       # injected weights (config.set_state_dicts)
+            spec.weights = config.face_state_dict()
+        self.model = RetinaFacePredictor(threshold=0.8, device=self.device, model=spec, precision=self._precision)
         self.face_tracker = SimpleFaceTracker(iou_threshold=0.4, minimum_face_size=0.0)
 
     def __del__(self):

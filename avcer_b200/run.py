@@ -115,8 +115,10 @@ def run_inference(path_video: str = "", path_save_results: str = "", flag_save_p
                   weights_prob_model: Optional[list] = None, weights_model: Optional[list] = [1, 1, 1],
                   flag_heatmaps: bool = False, model_heatmaps: str = "static", ce_weights_type: bool = True,
                   ce_mask: bool = False, flag_save_plot_pred: bool = True) -> None:
-    """run.py:192-308 without the upstream face detector: the face crops of track "00" must already
-    exist under <path_save_results>/<clip>/00/ (what VideoPredictor.process would have written)."""
+    """run.py:192-308: face crops (detector + tracker) -> VS / VD -> audio -> compound expressions.  The reference detects
+    on every call; here crops of track "00" that already exist under <path_save_results>/<clip>/00/ are reused (the
+    BASELINE configs start from pre-cropped faces), otherwise `VideoPredictor.process` writes them first.  fps and the frame
+    count are the detector's (`int()` of the container's values, get_face_images.py:23-24)."""
     import cv2
 
     from .get_prob_audio_8_cl import preprocess_audio_and_predict
@@ -126,12 +128,19 @@ def run_inference(path_video: str = "", path_save_results: str = "", flag_save_p
     clip = os.path.basename(path_video)[:-4]
     crops = os.path.join(path_save_results, clip)
     if not os.path.isdir(os.path.join(crops, "00")):
-        raise FileNotFoundError(f"{crops}/00: face detection/tracking (RetinaFace) is upstream of the accelerated path; "
-                                "write the crops first")
-    cap = cv2.VideoCapture(path_video)
-    fps = cap.get(cv2.CAP_PROP_FPS)
-    total_frames = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
-    cap.release()
+        from .data.get_face_images import VideoPredictor
+
+        print(f"Face images detection in video: {os.path.basename(path_video)}")
+        detect = VideoPredictor()
+        detect.process(path_video, path_save_results)
+        fps, total_frames = detect.fps, detect.total_frames
+        if not os.path.isdir(os.path.join(crops, "00")):
+            raise FileNotFoundError(f"{crops}/00: no face was detected in {path_video}")
+    else:
+        cap = cv2.VideoCapture(path_video)
+        fps = int(cap.get(cv2.CAP_PROP_FPS))
+        total_frames = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+        cap.release()
     if not fps or total_frames <= 0:
         raise RuntimeError(f"cannot read fps / frame count of {path_video}")
     print("Emotion prediction using visual models")

@@ -200,6 +200,57 @@ def test_run_inference_end_to_end(cuda_lib, tmp_path):
         assert got[key].shape == (n,) and np.array_equal(got[key], np.asarray(want)), key      # fp32 mode: every frame
 
 
+def test_run_inference_from_raw_video_detects_faces_first(cuda_lib, tmp_path):
+    """Row a1 with its first stage (run.py:222-226): no crops on disk, so run_inference runs the face detector + tracker
+     on the video, then the VS / VD / audio / fusion path on track 00's crops.  Checked against the oracle
+    of the emotion path fed with the crop files the detector wrote (the detector itself: tests/test_gpu_face.py)."""
+    import wave
+
+    import pandas as pd
+
+    from avcer_b200 import config, get_weights_matrices as gwm, run
+    from oracle import audio as oa, fusion as of, video as ov
+
+    n, fps = 30, 25
+    video = tmp_path / "talk.avi"
+    vw = cv2.VideoWriter(str(video), cv2.VideoWriter_fourcc(*"MJPG"), fps, (200, 150))
+    assert vw.isOpened()
+    for f in syn.make_frames(42, n, 150, 200):
+        vw.write(f)
+    vw.release()
+    rng = np.random.default_rng(44)
+    pcm = (3000 * rng.standard_normal((int(n / fps * 16000), 1))).astype(np.int16)
+    with wave.open(str(tmp_path / "talk.wav"), "wb") as f:
+        f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000)
+        f.writeframes(pcm.astype("<i2").tobytes())
+    sd_vs, sd_vd = syn.make_vs_state_dict(0, "spread"), syn.make_vd_state_dict(1)
+    sd_a = syn.make_audio_state_dict(2, 8, "spread", 12)
+    out_dir = tmp_path / "out"
+    config.set_precision("fp32")
+    config.set_state_dicts(vs=sd_vs, vd=sd_vd, audio={8: sd_a}, face=syn.make_retinaface_state_dict(5, "spread"))
+    w1, w2 = gwm.class_weights(gwm.weights_3), [1, 1, 1]
+    try:
+        run.run_inference(path_video=str(video), path_save_results=str(out_dir), flag_save_prob=False, weights_prob_model=w1,
+                          weights_model=w2, ce_weights_type=False, ce_mask=True, flag_save_plot_pred=True)
+    finally:
+        config.set_state_dicts(face=None)
+        config._state["face"] = None
+        config.reset()
+        config.set_precision("bf16")
+    track0 = out_dir / "talk" / "00"
+    assert track0.is_dir() and len(os.listdir(track0)) >= 1      # the synthetic detector's tracks are short: most frames are gaps
+    got = np.load(out_dir / "predicted_CEs.npz")
+    crops = [cv2.imread(str(track0 / f"{i:06d}.jpg")) if (track0 / f"{i:06d}.jpg").exists() else None for i in range(n)]
+    o_dyn, o_stat = ov.predict_video(crops, fps, sd_vs, sd_vd)
+    rows, ids, _ = oa.predict_audio(oa.pcm16_to_mono_16k(pcm, 16000, 16000), fps, sd_a)
+    stat_df, dyn_df = pd.DataFrame(o_stat, columns=of.VIDEO_ORDER), pd.DataFrame(o_dyn, columns=of.VIDEO_ORDER)
+    audio_df = pd.DataFrame(rows, columns=of.AUDIO_ORDER)
+    audio_df["frames"] = [str(i).zfill(6) + ".jpg" for i in ids]
+    ref = of.get_c_expr_db_pred(stat_df, dyn_df, audio_df, "talk", w1, w2, False, True)
+    for key, want in zip(("AV", "VS", "VD", "A"), ref[:4]):
+        assert got[key].shape == (n,) and np.array_equal(got[key], np.asarray(want)), key
+
+
 def _oracle_labels(crops, exists, fps, wav, sds, w1, w2, cwt, cm, step, padding, ncls):
     """The reference path restated by the oracle: per-frame video tables, long-format audio table, run.get_c_expr_db_pred."""
     import pandas as pd

@@ -672,14 +672,26 @@ extern "C" int avcer_w2v_conv0_tc(const float* x, int n, int t_in, const void* w
   p.tiles_per_row = (t_out + 127) / 128;
   p.num_tiles = n * p.tiles_per_row;
   p.eps = eps;
-  static bool attr_done = false;
-  if (!attr_done) {
-    AVCER_CUDA(cudaFuncSetAttribute(w2v_conv0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv0Cfg::SMEM));
-    attr_done = true;
-  }
+  // 8 epilogue warps (2 per TMEM lane quarter) by default.  AVCER_CONV0_G=4 selects 16 (96 registers per thread): measured
+  // 352 vs 336 us per 64 windows -- more warps do not help, both the MUFU and the FMA pipe sit at ~50 % (ncu) whatever the
+  // warp count, and prefetching the TMEM loads gained 5 %.
+  static const int groups = getenv("AVCER_CONV0_G") ? atoi(getenv("AVCER_CONV0_G")) : 2;
   int g = num_sms();
   if (g > p.num_tiles) g = p.num_tiles;
-  launch_pdl_tpc(w2v_conv0_tc_kernel, g, Conv0Cfg::THREADS, Conv0Cfg::SMEM, as_stream(stream), ty, p);
+  static bool attr_done[2] = {false, false};
+  if (groups == 2) {
+    if (!attr_done[0]) {
+      AVCER_CUDA(cudaFuncSetAttribute(w2v_conv0_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv0Cfg<2>::SMEM));
+      attr_done[0] = true;
+    }
+    launch_pdl_tpc(w2v_conv0_tc_kernel<2>, g, Conv0Cfg<2>::THREADS, Conv0Cfg<2>::SMEM, as_stream(stream), ty, p);
+  } else {
+    if (!attr_done[1]) {
+      AVCER_CUDA(cudaFuncSetAttribute(w2v_conv0_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv0Cfg<4>::SMEM));
+      attr_done[1] = true;
+    }
+    launch_pdl_tpc(w2v_conv0_tc_kernel<4>, g, Conv0Cfg<4>::THREADS, Conv0Cfg<4>::SMEM, as_stream(stream), ty, p);
+  }
   return check_launch("w2v_conv0_tc_kernel");
 }
 

@@ -40,19 +40,25 @@ struct Conv0Params {
   float eps;
 };
 
+// G = epilogue warps per TMEM lane quarter (each owns 512 / G channels of its 32 rows): 2 -> 8 epilogue warps, 4 -> 16.
+template <int G>
 struct Conv0Cfg {
   static constexpr int A_BYTES = 128 * 64;            // 128 rows x 32 elements
   static constexpr int B_BYTES = 512 * 64;
   static constexpr int SLAB = 32 * 128;               // 32 rows x 64 columns, 128B-swizzled
-  static constexpr int C_BYTES = 8 * 2 * SLAB;
-  static constexpr int SMEM = 2 * A_BYTES + B_BYTES + C_BYTES + 2 * 2048 /*gamma, beta*/ + 2 * 2 * 128 * 8 /*row partials, double-buffered*/ + 1024;
-  static constexpr int THREADS = 384;                 // warp 0: bank loader, 1: MMA, 2-3: A builders, 4-11: epilogue
+  static constexpr int EPI_WARPS = 4 * G;
+  static constexpr int C_BYTES = EPI_WARPS * 2 * SLAB;
+  static constexpr int PART_BYTES = 2 * G * 128 * 8;  // float2 row partials, double-buffered by tile parity
+  static constexpr int SMEM = 2 * A_BYTES + B_BYTES + C_BYTES + 2 * 2048 /*gamma, beta*/ + PART_BYTES + 1024;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;   // warp 0: bank loader, 1: MMA, 2-3: A builders, 4..: epilogue
   static constexpr int TMEM_COLS = 512;
+  static constexpr int CW = 512 / G;                  // channels per epilogue warp
 };
 
-__global__ void __launch_bounds__(384, 1)
+template <int G>
+__global__ void __launch_bounds__(Conv0Cfg<G>::THREADS, 1)
 w2v_conv0_tc_kernel(const __grid_constant__ CUtensorMap tmY, const Conv0Params p) {
-  using Cfg = Conv0Cfg;
+  using Cfg = Conv0Cfg<G>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[8];           // afull[2] aempty[2] tfull tempty bfull
   __shared__ uint32_t tmem_slot_s;
@@ -77,7 +83,7 @@ w2v_conv0_tc_kernel(const __grid_constant__ CUtensorMap tmY, const Conv0Params p
       mbar_init(aempty(s), 1);              // tcgen05.commit
     }
     mbar_init(tfull, 1);
-    mbar_init(tempty, 8);                   // one arrive per epilogue warp
+    mbar_init(tempty, Cfg::EPI_WARPS);      // one arrive per epilogue warp
     mbar_init(bfull, 1);
     fence_mbar_init();
   }
@@ -163,31 +169,34 @@ w2v_conv0_tc_kernel(const __grid_constant__ CUtensorMap tmY, const Conv0Params p
     }
   } else {
     // ------------------------------------------------------------ epilogue: LayerNorm + GELU straight from TMEM
-    const int q = warp & 3, g = (warp - 4) >> 2;      // lane quarter (rows 32q ..), channel half (256g ..)
+    const int q = warp & 3, g = (warp - 4) >> 2;      // lane quarter (rows 32q ..), channel group (CW g ..)
     const int ew = warp - 4;
     const int r = q * 32 + lane;                      // row of the tile owned by this thread
     const uint32_t cslab = c_base + ew * 2 * Cfg::SLAB;
     const uint32_t row_off = lane * 128;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 256;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * Cfg::CW;
     int j = 0;                                        // slabs issued so far by this warp (staging ring of 2)
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = blockIdx.x + i * gridDim.x;
       const int b = tile / p.tiles_per_row, t0 = (tile % p.tiles_per_row) * 128;
       mbar_wait(tfull, i & 1u);
       tc_fence_after();
-      // pass 1: (sum, sum of squares) of this thread's 256 channels
+      // pass 1: (sum, sum of squares) of this thread's CW channels
       uint64_t s1p = 0ull, s2p = 0ull;                // packed (even, odd) column partial sums
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
+      for (int c = 0; c < Cfg::CW / 64; ++c) {        // two TMEM loads in flight per wait: the pass is latency-bound otherwise
+        uint32_t v[2][32];
+        tmem_ld_32x32(taddr + c * 64, v[0]);
+        tmem_ld_32x32(taddr + c * 64 + 32, v[1]);
         tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          const uint64_t f = pack_f32x2(__uint_as_float(v[k]), __uint_as_float(v[k + 1]));
-          s1p = fma_f32x2(f, pack_f32x2(1.0f, 1.0f), s1p);
-          s2p = fma_f32x2(f, f, s2p);
-        }
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            const uint64_t f = pack_f32x2(__uint_as_float(v[hh][k]), __uint_as_float(v[hh][k + 1]));
+            s1p = fma_f32x2(f, pack_f32x2(1.0f, 1.0f), s1p);
+            s2p = fma_f32x2(f, f, s2p);
+          }
       }
       float s1, s2, t1, t2;
       unpack_f32x2(s1p, s1, t1);
@@ -196,53 +205,65 @@ w2v_conv0_tc_kernel(const __grid_constant__ CUtensorMap tmY, const Conv0Params p
       s2 += t2;
       // double-buffered by tile parity: a warp that runs ahead writes tile i+1's partials into the other buffer, and cannot
       // reach tile i+2 before its partner has passed the barrier of tile i+1, i.e. has read tile i's
-      float2* part = part_s + (i & 1) * 256;
+      float2* part = part_s + (i & 1) * (G * 128);
       part[g * 128 + r] = make_float2(s1, s2);
-      named_bar_sync(1, 256);                         // both halves of every row have their partials
-      const float2 o = part[(g ^ 1) * 128 + r];
-      const float mean = (s1 + o.x) * (1.0f / 512.0f);
-      const float rstd = rsqrtf(fmaxf((s2 + o.y) * (1.0f / 512.0f) - mean * mean, 0.f) + p.eps);
+      named_bar_sync(1, 32 * Cfg::EPI_WARPS);         // every channel group of every row has its partials
+      s1 = 0.f;
+      s2 = 0.f;
+#pragma unroll
+      for (int gg = 0; gg < G; ++gg) {                // same order in every group: all of them get the same statistics
+        const float2 o = part[gg * 128 + r];
+        s1 += o.x;
+        s2 += o.y;
+      }
+      const float mean = s1 * (1.0f / 512.0f);
+      const float rstd = rsqrtf(fmaxf(s2 * (1.0f / 512.0f) - mean * mean, 0.f) + p.eps);
       const uint64_t rstd2 = pack_f32x2(rstd, rstd), nm2 = pack_f32x2(-mean * rstd, -mean * rstd);
-      // pass 2: normalise, GELU, round, stage 64-column slabs, TMA store
-#pragma unroll 1
-      for (int hf = 0; hf < 4; ++hf, ++j) {
+      // pass 2: normalise, GELU, round, stage 64-column slabs, TMA store.  Steps of 32 columns; the TMEM load of the next
+      // step is in flight while the current one is computed (its ~300-cycle latency would otherwise be exposed per step).
+      constexpr int STEPS = Cfg::CW / 32;
+      uint32_t v[2][32];
+      tmem_ld_32x32(taddr, v[0]);
+#pragma unroll
+      for (int st = 0; st < STEPS; ++st) {
+        const int cur = st & 1;
         const uint32_t cbuf = cslab + (j & 1) * Cfg::SLAB;
-        if (lane == 0) bulk_wait_group_read<1>();     // the store that last read this slab is done with it
-        __syncwarp();
-        uint32_t v[2][32];
-        tmem_ld_32x32(taddr + hf * 64, v[0]);
-        tmem_ld_32x32(taddr + hf * 64 + 32, v[1]);
-        tmem_ld_wait();
-        const int c0 = g * 256 + hf * 64;
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          uint64_t f[16];                             // 16 channel pairs, all independent: the scheduler interleaves them
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int c = c0 + cc * 32 + 2 * e;
-            const uint64_t u = fma_f32x2(pack_f32x2(__uint_as_float(v[cc][2 * e]), __uint_as_float(v[cc][2 * e + 1])), rstd2, nm2);
-            f[e] = fma_f32x2(u, *reinterpret_cast<const uint64_t*>(&g_s[c]), *reinterpret_cast<const uint64_t*>(&g_s[512 + c]));
-          }
-#pragma unroll
-          for (int e = 0; e < 16; ++e) f[e] = gelu_erf_fast2(f[e]);
-#pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8) {
-            uint4 u;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float lo, hi;
-              unpack_f32x2(f[k8 * 4 + e], lo, hi);
-              h2[e] = __floats2bfloat162_rn(lo, hi);
-            }
-            st_shared_v4(cbuf + row_off + (((cc * 4 + k8) ^ (lane & 7)) << 4), u);
-          }
+        tmem_ld_wait();                               // v[cur] has landed
+        if (st + 1 < STEPS) tmem_ld_32x32(taddr + (st + 1) * 32, v[cur ^ 1]);
+        if ((st & 1) == 0) {
+          if (lane == 0) bulk_wait_group_read<1>();   // the store that last read this slab is done with it
+          __syncwarp();
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_5d(&tmY, cbuf, c0, t0 + q * 32, b, 0, 0);    // box 64 channels x 32 steps, clipped at t_out
-          bulk_commit_group();
+        const int c0 = g * Cfg::CW + st * 32;
+        uint64_t f[16];                               // 16 channel pairs, all independent: the scheduler interleaves them
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int c = c0 + 2 * e;
+          const uint64_t u = fma_f32x2(pack_f32x2(__uint_as_float(v[cur][2 * e]), __uint_as_float(v[cur][2 * e + 1])), rstd2, nm2);
+          f[e] = fma_f32x2(u, *reinterpret_cast<const uint64_t*>(&g_s[c]), *reinterpret_cast<const uint64_t*>(&g_s[512 + c]));
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) f[e] = gelu_erf_fast2(f[e]);
+#pragma unroll
+        for (int k8 = 0; k8 < 4; ++k8) {
+          uint4 u;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float lo, hi;
+            unpack_f32x2(f[k8 * 4 + e], lo, hi);
+            h2[e] = __floats2bfloat162_rn(lo, hi);
+          }
+          st_shared_v4(cbuf + row_off + ((((st & 1) * 4 + k8) ^ (lane & 7)) << 4), u);
+        }
+        if (st & 1) {                                 // a 64-column slab is complete
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_5d(&tmY, cbuf, c0 - 32, t0 + q * 32, b, 0, 0);    // box 64 channels x 32 steps, clipped at t_out
+            bulk_commit_group();
+          }
+          ++j;
         }
       }
       tc_fence_before();

@@ -2,6 +2,7 @@
 // storage type (bf16 in the default mode, fp32 in "fp32 mode").  Arithmetic is always fp32.
 // Reference call sites are cited per kernel.
 #include "common.h"
+#include <stdlib.h>
 #include "ptx.cuh"
 #include "vec8.cuh"
 
@@ -341,54 +342,136 @@ w2v_conv0_kernel(const float* __restrict__ x, int n, int t_in, int t_out, const 
 }
 
 // ------------------------------------------------------------------ LayerNorm rows (warp per row), optional pre-add and GELU
-template <typename T, int CHUNKS>
-__global__ void __launch_bounds__(256)
+// Template R: 1 = the row unpacked to fp32 registers; 3 = the row kept in storage form (wide 16-bit rows, see the launcher);
+// 2 = two rows per warp in storage form (measured no faster, not instantiated).
+// Rows stay in registers in their STORAGE form (16 bytes per 8 values in the 16-bit modes) and are unpacked in each of the
+// three passes (sum, centred sum of squares, normalise): 16 instead of 32 registers per 1024-channel row, so that two rows
+// per warp still fit 64 registers and the SM keeps 32+ warps resident.
+template <typename T> struct Raw8;
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) { a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4); }
+  __device__ __forceinline__ void get(float (&v)[8]) const { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+  __device__ __forceinline__ void add(const float* p) {
+    const float4 c = *reinterpret_cast<const float4*>(p), d = *reinterpret_cast<const float4*>(p + 4);
+    a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w; b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+  }
+};
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 u;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+  // x + add is formed in fp32 and NOT rounded back in the one-row kernel; re-rounding here would change results, so the
+  // pre-add case keeps using R = 1 with fp32 registers (see the launcher)
+};
+
+template <typename T, int CHUNKS, int R>
+__global__ void __launch_bounds__(256, R == 2 ? 3 : (R == 3 ? 4 : 1))
 layernorm_kernel(const T* __restrict__ x, long long rows, long long ldx, const T* __restrict__ add,
                  long long add_rows, const float* __restrict__ g, const float* __restrict__ b, float eps, int act,
                  T* __restrict__ y, long long ldy) {
   pdl_wait();
   pdl_launch_dependents();
   constexpr int C = CHUNKS * 256;
-  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long row0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (R == 2 ? 2 : 1);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  float v[CHUNKS][8];
-  float s = 0.f;
+  if (row0 >= rows) return;
+  if (R == 1) {
+    float v[CHUNKS][8];
+    float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < CHUNKS; ++j) Vec8<T>::load(x + row * ldx + j * 256 + lane * 8, v[j]);
-  if (add) {
+    for (int j = 0; j < CHUNKS; ++j) Vec8<T>::load(x + row0 * ldx + j * 256 + lane * 8, v[j]);
+    if (add) {
+#pragma unroll
+      for (int j = 0; j < CHUNKS; ++j) {
+        float a[8];
+        Vec8<T>::load(add + (row0 % add_rows) * C + j * 256 + lane * 8, a);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[j][e] += a[e];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CHUNKS; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[j][e];
+    const float mean = warp_sum(s) * (1.0f / (float)C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < CHUNKS; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = v[j][e] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / (float)C) + eps);
 #pragma unroll
     for (int j = 0; j < CHUNKS; ++j) {
-      float a[8];
-      Vec8<T>::load(add + (row % add_rows) * C + j * 256 + lane * 8, a);
+      const int c0 = j * 256 + lane * 8;
+      float gg[8], bb[8], o[8];
+      Vec8<float>::load(g + c0, gg);
+      Vec8<float>::load(b + c0, bb);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[j][e] += a[e];
+      for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mean) * rstd * gg[e] + bb[e];
+      if (act == ACT_GELU_L) {
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) gelu_pair<T>(o[e], o[e + 1]);
+      }
+      Vec8<T>::store(y + row0 * ldy + c0, o);
     }
+    return;
   }
+  // R == 2 / 3 (3 = ONE row, storage form, 4 blocks per SM), no pre-add: same arithmetic per row as above
+  constexpr int NR = R == 2 ? 2 : 1;
+  Raw8<T> raw[NR][CHUNKS];
 #pragma unroll
-  for (int j = 0; j < CHUNKS; ++j)
+  for (int r = 0; r < NR; ++r) {
+    const long long row = row0 + r < rows ? row0 + r : rows - 1;          // a ragged last pair re-reads the last row
 #pragma unroll
-    for (int e = 0; e < 8; ++e) s += v[j][e];
-  const float mean = warp_sum(s) * (1.0f / (float)C);
-  float q = 0.f;
+    for (int j = 0; j < CHUNKS; ++j) raw[r][j].load(x + row * ldx + j * 256 + lane * 8);
+  }
+  float mean[NR], rstd[NR];
 #pragma unroll
-  for (int j = 0; j < CHUNKS; ++j)
+  for (int r = 0; r < NR; ++r) {
+    float s = 0.f;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { const float d = v[j][e] - mean; q = fmaf(d, d, q); }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / (float)C) + eps);
+    for (int j = 0; j < CHUNKS; ++j) {
+      float v[8];
+      raw[r][j].get(v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[e];
+    }
+    mean[r] = warp_sum(s) * (1.0f / (float)C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < CHUNKS; ++j) {
+      float v[8];
+      raw[r][j].get(v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = v[e] - mean[r]; q = fmaf(d, d, q); }
+    }
+    rstd[r] = rsqrtf(warp_sum(q) * (1.0f / (float)C) + eps);
+  }
 #pragma unroll
   for (int j = 0; j < CHUNKS; ++j) {
     const int c0 = j * 256 + lane * 8;
-    float gg[8], bb[8], o[8];
+    float gg[8], bb[8];
     Vec8<float>::load(g + c0, gg);
     Vec8<float>::load(b + c0, bb);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mean) * rstd * gg[e] + bb[e];
-    if (act == ACT_GELU_L) {
+    for (int r = 0; r < NR; ++r) {
+      if (row0 + r < rows) {
+        float v[8], o[8];
+        raw[r][j].get(v);
 #pragma unroll
-      for (int e = 0; e < 8; e += 2) gelu_pair<T>(o[e], o[e + 1]);
+        for (int e = 0; e < 8; ++e) o[e] = (v[e] - mean[r]) * rstd[r] * gg[e] + bb[e];
+        if (act == ACT_GELU_L) {
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) gelu_pair<T>(o[e], o[e + 1]);
+        }
+        Vec8<T>::store(y + (row0 + r) * ldy + c0, o);
+      }
     }
-    Vec8<T>::store(y + row * ldy + c0, o);
   }
 }
 
@@ -629,13 +712,18 @@ extern "C" int avcer_layernorm(const void* x, int64_t rows, int c, int64_t ldx, 
   AVCER_REQUIRE(c % 256 == 0 && c <= 1024, "layernorm: c must be a multiple of 256, at most 1024");
   AVCER_REQUIRE(add == nullptr || add_rows > 0, "layernorm: add_rows must be > 0 with add");
   if (rows == 0) return 0;
-#define AVCER_LN_CASE(ch)                                                                                         \
-  if (c == ch * 256) {                                                                                            \
-    AVCER_DISPATCH(dtype, (launch_pdl(layernorm_kernel<T, ch>, blocks_for(rows * 32, 256), 256, 0, as_stream(stream),   \
+  // variant 1: the row in fp32 registers (pre-add, fp32 mode, narrow rows); variant 3: wide 16-bit rows without pre-add held
+  // in storage form at 64 registers per thread -> 32 instead of 16 resident warps per SM (the 1024-channel kernel needed 119
+  // registers).  Same arithmetic in the same order: bit-identical outputs; measured 18.3 -> 15.9 us per [12736, 1024] pass
+  // with the input in L2 (scripts/time_ln.py).  Two rows per warp (variant 2) measured the same and was dropped.
+  const int variant = (add == nullptr && dtype == AVCER_BF16 && c >= 768) ? 3 : 1;
+#define AVCER_LN_CASE(ch, var)                                                                                    \
+  if (c == ch * 256 && variant == var) {                                                                          \
+    AVCER_DISPATCH(dtype, (launch_pdl(layernorm_kernel<T, ch, var>, blocks_for(rows * 32, 256), 256, 0, as_stream(stream), \
                               (const T*)x, rows, ldx, (const T*)add, add_rows > 0 ? add_rows : 1, g, b, eps, act, \
                               (T*)y, ldy)));                                                                      \
   }
-  AVCER_LN_CASE(1) AVCER_LN_CASE(2) AVCER_LN_CASE(3) AVCER_LN_CASE(4)
+  AVCER_LN_CASE(1, 1) AVCER_LN_CASE(2, 1) AVCER_LN_CASE(3, 1) AVCER_LN_CASE(4, 1) AVCER_LN_CASE(3, 3) AVCER_LN_CASE(4, 3)
 #undef AVCER_LN_CASE
   return check_launch("layernorm");
 }

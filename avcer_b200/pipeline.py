@@ -134,7 +134,7 @@ class Engine:
         return out
 
     def __init__(self, sd_vs=None, sd_vd=None, sd_a=None, precision: str = "bf16", device: str = "cuda:0",
-                 vs_batch: int = 256, a_batch: int = 64, use_graphs: bool = True, overlap: Optional[Tuple[int, int]] = None):
+                 vs_batch: int = 256, a_batch: int = 141, use_graphs: bool = True, overlap: Optional[Tuple[int, int]] = None):
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         self.precision = precision

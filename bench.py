@@ -193,8 +193,11 @@ def main():
     ap.add_argument("--clip-seconds", type=int, default=60)
     ap.add_argument("--fps", type=int, default=25)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
-    ap.add_argument("--a-batch", type=int, default=64)
-    ap.add_argument("--vs-batch", type=int, default=1024)     # crops per VS forward inside the pipeline (config 2 below stays at 256)
+    # windows per audio forward: 141 x 199 tokens = 110 row tiles of 256, i.e. 440 / 1320 / 1760 tiles for the encoder's N = 1024 /
+    # 3072 / 4096 GEMMs = 5.95 / 17.8 / 23.8 waves over the 74 CTA pairs (64 windows: 2.70 / 8.1 / 10.8 -> a tenth of every
+    # GEMM is a partly empty wave); measured 51.0 k -> 51.7 k frames/s
+    ap.add_argument("--a-batch", type=int, default=141)
+    ap.add_argument("--vs-batch", type=int, default=1536)     # crops per VS forward inside the pipeline (config 2 below stays at 256); 768 - 2048 measured within 1 %
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()

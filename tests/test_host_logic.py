@@ -193,3 +193,71 @@ def test_contract_descriptor_layout_matches_the_header(tmp_path):
     assert int(out["sizeof"]) == ctypes.sizeof(ContractDesc)
     for name in fields:
         assert int(out[name]) == getattr(ContractDesc, name).offset, name
+
+
+# ------------------------------------------------------------------------------------------ face detector host side
+def test_face_tracker_and_nms_product_code_match_reference(golden):
+    """The product's host-side SimpleFaceTracker and greedy NMS (avcer_b200/data/face_detection.py) against the track ids
+    the unmodified reference produced (tests/golden/face.npz) and against the oracle's restatement of py_cpu_nms."""
+    from avcer_b200.data.face_detection import SimpleFaceTracker, greedy_nms
+    from oracle import face as ofa
+    from oracle.make_golden import face_tracker_sequences
+
+    g = golden["face"]
+    t = SimpleFaceTracker(iou_threshold=0.4, minimum_face_size=0.0)
+    for s, seq in enumerate(face_tracker_sequences()):
+        t.reset()
+        got = []
+        for boxes in seq:
+            got += [-1 if v is None else v for v in t(boxes)]
+        assert got == list(g[f"track_{s}"]), s
+    t.reset()
+    ids = []
+    for i in range(6):
+        ids += t(g[f"dets_{i}"])
+    assert ids == list(g["ids"])
+    assert t(np.empty((0, 15), dtype=np.float32)) == [] and t._tracklets == []
+    t.iou_threshold, t.minimum_face_size = 0.5, 3.0
+    assert (t.iou_threshold, t.minimum_face_size) == (0.5, 3.0)
+    rng = np.random.default_rng(1)
+    for trial in range(30):
+        n = int(rng.integers(1, 700))
+        xy = rng.uniform(0, 300, (n, 2))
+        d = np.concatenate([xy, xy + rng.uniform(5, 60, (n, 2)), rng.uniform(0, 1, (n, 1))], axis=1).astype(np.float32)
+        if trial % 5 == 0:
+            d[n // 2, 2] = np.nan
+        for k in (5000, 9):
+            assert greedy_nms(d, 0.4, k) == ofa.nms(d, 0.4, k), (trial, k)
+
+
+def test_nearest_source_index_matches_torch_interpolate():
+    """FPN top-down merge (retina_face_net.py:88-94): the host computes the source row / column of every output position with
+    ATen's nearest rule; checked against F.interpolate itself on an index ramp for every size pair the pyramid can produce."""
+    import torch.nn.functional as F
+
+    from avcer_b200 import ops
+
+    for n_in in list(range(1, 40)) + [68, 135, 240]:
+        for n_out in range(n_in, min(2 * n_in + 2, 500)):
+            ref = F.interpolate(torch.arange(n_in, dtype=torch.float32).view(1, 1, n_in, 1), size=(n_out, 1), mode="nearest").view(-1).long()
+            assert torch.equal(ref, ops.nearest_source_index(n_in, n_out).long()), (n_in, n_out)
+
+
+def test_retinaface_packer_layout():
+    """weights.pack_retinaface: BatchNorm folded with eps 1e-5, stem rows ordered (ky, kx, c), heads concatenated
+    [class 4 | box 8 | landmarks 20 | zeros], 16 bottlenecks with the stride on conv2."""
+    from avcer_b200 import weights
+
+    sd = syn.make_retinaface_state_dict(5, "spread")
+    w = weights.pack_retinaface(sd, "cpu", torch.float32)
+    s = sd["body.bn1.weight"].double() / torch.sqrt(sd["body.bn1.running_var"].double() + 1e-5)
+    want = (sd["body.conv1.weight"].double() * s.view(-1, 1, 1, 1))[5, 2, 3, 4]
+    assert abs(float(w["stem_w"][(3 * 7 + 4) * 3 + 2, 5]) - float(want)) < 1e-9
+    assert len(w["blocks"]) == 16 and [b["conv2"].stride for b in w["blocks"]] == [1, 1, 1, 2, 1, 1, 1, 2, 1, 1, 1, 1, 1, 2, 1, 1]
+    h = w["heads"][1]
+    assert h.wt.shape == (64, 256) and float(h.wt[32:].abs().max()) == 0.0
+    assert torch.equal(h.wt[0:4], sd["ClassHead.1.conv1x1.weight"].reshape(4, 256))
+    assert torch.equal(h.wt[4:12], sd["BboxHead.1.conv1x1.weight"].reshape(8, 256))
+    assert torch.equal(h.bias[12:32], sd["LandmarkHead.1.conv1x1.bias"])
+    w16 = weights.pack_retinaface(sd, "cpu", torch.bfloat16)
+    assert w16["stem_wt"].shape == (64, 224) and w16["stem_packed"].numel() == 64 * 224

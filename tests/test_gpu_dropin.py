@@ -358,6 +358,43 @@ def test_run_clips_config4_seven_class_repeat_variant(cuda_lib):
             assert margin.max() < 0.03, (prec, margin.max())
 
 
+def test_run_clips_many_mixed_clips_against_per_clip_oracle(cuda_lib):
+    """Five clips in ONE Engine.run_clips call -- mixed frame rates (24 / 25 / 30 fps: VD sampling step 5 / 5 / 6), random
+    gaps including a leading one (float64 promotion) and a long one (window reset), audio lengths that are and are not
+    multiples of the step (an all-NaN tail window in the MIDDLE of an audio batch, next to other clips' windows) -- against
+    the oracle run clip by clip.  fp32: all four label streams identical on every frame of every clip; what is batched
+    together must not interact."""
+    from avcer_b200 import get_weights_matrices as gwm
+    from avcer_b200.pipeline import Engine
+
+    rng = np.random.default_rng(77)
+    spec = [(24, 37, 16000 * 2 - 123), (25, 50, 16000 * 2), (30, 61, 16000 * 2 + 4000), (25, 23, 8000 * 3), (30, 45, 16000 + 77)]
+    sds = (syn.make_vs_state_dict(0, "spread"), syn.make_vd_state_dict(1), syn.make_audio_state_dict(2, 8, "spread", 12))
+    w1, w2 = gwm.class_weights(gwm.weights_3), [1, 1, 1]
+    exists_l, crops_l, wav_l = [], [], []
+    for ci, (fps, n, L) in enumerate(spec):
+        ex = rng.random(n) > 0.08
+        if ci == 0:
+            ex[:3] = False                      # leading gap: the reference's tables become float64
+        if ci == 2:
+            ex[20:33] = False                   # a gap longer than a VD window: the window restarts
+        ex[-1] = True
+        exists_l.append(ex)
+        crops_l.append(syn.make_crops(800 + ci, int(ex.sum())))
+        wav_l.append(syn.make_wav(900 + ci, L))
+    eng = Engine(*sds, precision="fp32", device="cuda:0")
+    out = eng.run_clips(torch.from_numpy(np.concatenate(crops_l)), exists_l, [float(f) for f, _, _ in spec],
+                        torch.from_numpy(np.concatenate(wav_l)), [len(w) for w in wav_l], w1, w2, False, True)
+    got = out["labels"].cpu().numpy()
+    assert got.shape == (4, sum(n for _, n, _ in spec))
+    off = 0
+    for ci, (fps, n, L) in enumerate(spec):
+        ref, o_stat, o_dyn, o_wl = _oracle_labels(crops_l[ci], exists_l[ci], fps, wav_l[ci], sds, w1, w2, False, True, 0.5, "mean", 8)
+        mine = got[:, off:off + n]
+        assert np.array_equal(mine, ref), (ci, np.argwhere(mine != ref)[:10])
+        off += n
+
+
 def test_run_clips_float64_promotion_for_leading_gap(cuda_lib):
     """A clip whose first crops are missing: the reference's video tables are float64 (np.array over float32 rows and
     float64 zero rows, get_prob_video.py:89,182-187), so its VD softmax and the unweighted mean run in float64.  K4 is

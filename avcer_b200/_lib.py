@@ -54,6 +54,7 @@ class ContractDesc(ctypes.Structure):
         ("dtype", c_int32),
         ("out_f32", c_int32),
         ("a_step", c_int32),
+        ("reverse_tiles", c_int32),
     ]
 
 

@@ -173,6 +173,7 @@ static int conv3x3_tc(const avcer_contract_desc* d, cudaStream_t st) {
   p.a_stage = (unsigned)(((2 * p.P + 2 + 256) * 128 + 1023) / 1024 * 1024);
   p.bias = d->bias;
   p.act = d->act;
+  p.reverse = d->reverse_tiles != 0;
   CUtensorMap ta, tb, tc;
   {
     uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB, 1};
@@ -266,6 +267,7 @@ static int contract_tc(const avcer_contract_desc* d, cudaStream_t st) {
   p.out = d->out;
   p.act = d->act;
   p.res_after_act = d->res_after_act;
+  p.reverse = d->reverse_tiles != 0;
   p.trace = g_trace;
   if (p.num_tiles == 0) return 0;
 

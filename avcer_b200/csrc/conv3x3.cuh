@@ -34,6 +34,7 @@ struct Conv3Params {
   int bh;           // output rows per tile
   int tiles_h;      // ceil(H / bh)
   int num_tiles;    // NB * tiles_h
+  int reverse;      // 1: tiles are walked from the last to the first
   int kchunks;      // C / 64
   unsigned a_bytes; // bytes of one activation box: (bh + 2) * P * 128
   unsigned a_stage; // bytes reserved per activation stage: rows read by the MMAs (2P + 2 + 256), rounded up to 1 KB
@@ -118,8 +119,9 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int sa = 0;
       uint32_t pa = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n = tile / p.tiles_h;
-        const int h0 = (tile - n * p.tiles_h) * p.bh;
+        const int te = p.reverse ? p.num_tiles - 1 - tile : tile;
+        const int n = te / p.tiles_h;
+        const int h0 = (te - n * p.tiles_h) * p.bh;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(emptyA(sa), pa ^ 1u);
           mbar_arrive_expect_tx(fullA(sa), p.a_bytes);
@@ -212,8 +214,9 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int local = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
-      const int n = tile / p.tiles_h;
-      const int h0 = (tile - n * p.tiles_h) * p.bh;
+      const int te = p.reverse ? p.num_tiles - 1 - tile : tile;
+      const int n = te / p.tiles_h;
+      const int h0 = (te - n * p.tiles_h) * p.bh;
       mbar_wait(tfull(acc), (local >> 1) & 1u);
       tc_fence_after();
       if (store_thread) bulk_wait_group_read<0>();      // previous tile's stores have read the staging buffers

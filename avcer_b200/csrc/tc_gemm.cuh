@@ -33,6 +33,7 @@ enum OutMode : int { OUT_TMA = 0, OUT_TMA_RES = 1, OUT_DIRECT_F32 = 2 };
 
 struct TcGemmParams {
   int num_tiles, tiles_n;
+  int reverse;             // 1: the persistent CTAs walk the tiles from the last to the first (see avcer_contract_desc.reverse_tiles)
   int bw, bh, bn;          // box extents of one M tile (bw*bh*bn <= 128)
   int tw, th, tn;          // tiles along w / h / n
   int W, H, NB;            // valid output extents (direct-store epilogue mask)
@@ -156,8 +157,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t tx_bytes = p.a_bytes + Cfg::B_STAGE;
       int local = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
-        const int nt = tile % p.tiles_n;
-        const int mt = tile / p.tiles_n;
+        const int te = p.reverse ? p.num_tiles - 1 - tile : tile;
+        const int nt = te % p.tiles_n;
+        const int mt = te / p.tiles_n;
         const int w0 = (mt % p.tw) * p.bw;
         const int h0 = ((mt / p.tw) % p.th) * p.bh;
         const int n0 = (mt / (p.tw * p.th)) * p.bn;
@@ -230,8 +232,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (MODE == OUT_TMA_RES && lane == 0) {
       uint32_t hcount = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n;
-        const int mt = tile / p.tiles_n;
+        const int te = p.reverse ? p.num_tiles - 1 - tile : tile;
+        const int nt = te % p.tiles_n;
+        const int mt = te / p.tiles_n;
         const int w0 = (mt % p.tw) * p.bw;
         const int h0 = ((mt / p.tw) % p.th) * p.bh;
         const int n0 = (mt / (p.tw * p.th)) * p.bn;
@@ -257,8 +260,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1u;
-      const int nt = tile % p.tiles_n;
-      const int mt = tile / p.tiles_n;
+      const int te = p.reverse ? p.num_tiles - 1 - tile : tile;
+      const int nt = te % p.tiles_n;
+      const int mt = te / p.tiles_n;
       const int w0 = (mt % p.tw) * p.bw;
       const int h0 = ((mt / p.tw) % p.th) * p.bh;
       const int n0 = (mt / (p.tw * p.th)) * p.bn;

@@ -167,6 +167,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   pdl_launch_dependents();
 
   auto tile_coords = [&](int pt, int& nt, int& w0, int& h0, int& n0) {
+    if (p.reverse) pt = pair_tiles - 1 - pt;
     nt = pt % p.tiles_n;
     const int mt = 2 * (pt / p.tiles_n) + (int)rank;       // phantom tile when m_tiles is odd: n0 >= NB -> all out of bounds
     w0 = (mt % p.tw) * p.bw;
@@ -265,7 +266,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int my_tiles = cluster_id < pair_tiles ? (pair_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
     const int n_items = my_tiles * HPW;
     auto item_coords = [&](int j, int& col0, int& row0) {
-      const int pt = cluster_id + (j / HPW) * num_clusters;
+      int pt = cluster_id + (j / HPW) * num_clusters;
+      if (p.reverse) pt = pair_tiles - 1 - pt;
       col0 = (pt % p.tiles_n) * BN + (grp + 2 * (j % HPW)) * 64;
       row0 = (2 * (pt / p.tiles_n) + (int)rank) * 128 + q * 32;
     };

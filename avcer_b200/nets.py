@@ -101,6 +101,8 @@ class VSNet:
         self.w = weights.pack_vs(state_dict, self.device, self.dtype)
         self.fused_stem = True          # bf16: stem + max-pool in one kernel (False: two kernels, same bits)
         self.fused_shortcut = True      # bf16: projection shortcuts folded into conv3 (K-concatenated GEMM, first block of a stage)
+        self.alternate = True           # bf16: consecutive contractions walk their tiles in opposite directions (L2 reuse, _rev)
+        self._dir = False
         self.sampled_tail = 2           # bf16: the last conv3 (1) and conv2 (2) of layer1-3 only at the pixels the next stage samples
 
     @property
@@ -130,10 +132,20 @@ class VSNet:
                          algo_k=147)          # 7x7x3 real taps; the padded pixel/channel carry zero weights
         return y
 
+    def _rev(self) -> bool:
+        """Tile direction of the next contraction.  Every layer1 / layer2 tensor of a full batch is larger than the 126 MB L2
+        (256 crops: 99 - 396 MB), so a consumer that walks its tiles in the producer's order finds its first rows evicted;
+        walking them backwards it starts on what the producer wrote last.  Directions simply alternate from launch to launch
+        (same tiles, same arithmetic: bit-identical results)."""
+        if not (self.alternate and _tc(self.dtype)):
+            return False
+        self._dir = not self._dir
+        return self._dir
+
     def _conv(self, x: torch.Tensor, pc: weights.PackedConv, act: int, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         pad = (pc.k - 1) // 2
         return ops.conv2d_nhwc(x, pc.wt, pc.bias, kh=pc.k, kw=pc.k, stride=pc.stride, pad_h=pad, pad_w=pad,
-                               residual=residual, act=act)
+                               residual=residual, act=act, reverse=self._rev())
 
     @property
     def k1_fused(self) -> bool:
@@ -178,6 +190,8 @@ class VSNet:
         return self._tail(y)
 
     def _blocks(self, y, cat, cat4, lo: int, hi: int, taps: Optional[dict] = None, tail_out: Optional[torch.Tensor] = None):
+        if lo == 0:
+            self._dir = False           # the stem walks forward; the first contraction after it walks backwards
         """Bottleneck blocks [lo, hi).  State between blocks: `y` (block input, NHWC) or, after a sampled stage tail, the
         K-concatenated matrix `cat` / `cat4` whose left columns hold the stride-2 sampled input of the coming block.
         `tail_out`: where the sampled tail of block hi-1 puts that matrix (rows of a batch slice of a larger one)."""
@@ -191,9 +205,9 @@ class VSNet:
                 # shortcut are a single K = 128 GEMM (no shortcut tensor, no residual read)
                 m = cat.shape[0] * 55 * 55
                 c1, c2, c3 = blk["conv1"], blk["conv2"], blk["conv3_ds"]
-                t = ops.linear(cat.view(m, 128)[:, :64], c1.wt, c1.bias, act=ops.ACT_RELU).view(-1, 55, 55, 64)
-                ops.conv2d_nhwc(t, c2.wt, c2.bias, kh=3, kw=3, pad_h=1, pad_w=1, act=ops.ACT_RELU, out=cat[..., 64:])
-                y = ops.linear(cat.view(m, 128), c3.wt, c3.bias, act=ops.ACT_RELU).view(-1, 55, 55, 256)
+                t = ops.linear(cat.view(m, 128)[:, :64], c1.wt, c1.bias, act=ops.ACT_RELU, reverse=self._rev()).view(-1, 55, 55, 64)
+                ops.conv2d_nhwc(t, c2.wt, c2.bias, kh=3, kw=3, pad_h=1, pad_w=1, act=ops.ACT_RELU, out=cat[..., 64:], reverse=self._rev())
+                y = ops.linear(cat.view(m, 128), c3.wt, c3.bias, act=ops.ACT_RELU, reverse=self._rev()).view(-1, 55, 55, 256)
                 continue
             if fuse and "conv3_ds" in blk and blk["conv1"].stride == 2:
                 # layer2-4 block 0: the stride-2 sampling of the block input is materialised once, as the first Cin
@@ -210,10 +224,10 @@ class VSNet:
                     m = nb * ho * wo
                     cat = torch.empty((m, cin + c1.cout), device=self.device, dtype=self.dtype)
                     ops.subsample_rows(y, 2, cat[:, :cin])
-                t = ops.linear(cat[:, :cin], c1.wt, c1.bias, act=ops.ACT_RELU).view(nb, ho, wo, c1.cout)
+                t = ops.linear(cat[:, :cin], c1.wt, c1.bias, act=ops.ACT_RELU, reverse=self._rev()).view(nb, ho, wo, c1.cout)
                 ops.conv2d_nhwc(t, c2.wt, c2.bias, kh=3, kw=3, pad_h=1, pad_w=1, act=ops.ACT_RELU,
-                                out=cat.view(nb, ho, wo, cin + c1.cout)[..., cin:])
-                y = ops.linear(cat, c3.wt, c3.bias, act=ops.ACT_RELU).view(nb, ho, wo, c3.cout)
+                                out=cat.view(nb, ho, wo, cin + c1.cout)[..., cin:], reverse=self._rev())
+                y = ops.linear(cat, c3.wt, c3.bias, act=ops.ACT_RELU, reverse=self._rev()).view(nb, ho, wo, c3.cout)
                 continue
             identity = self._conv(y, blk["ds"], ops.ACT_NONE) if "ds" in blk else y
             t = self._conv(y, blk["conv1"], ops.ACT_RELU)
@@ -228,7 +242,7 @@ class VSNet:
                 c2, c3 = blk["conv2"], blk["conv3"]
                 c3_stride = 2
                 if self.sampled_tail >= 2:
-                    t = ops.conv2d_nhwc(t, c2.wt, c2.bias, kh=3, kw=3, stride=2, pad_h=1, pad_w=1, act=ops.ACT_RELU)
+                    t = ops.conv2d_nhwc(t, c2.wt, c2.bias, kh=3, kw=3, stride=2, pad_h=1, pad_w=1, act=ops.ACT_RELU, reverse=self._rev())
                     c3_stride = 1
                 else:
                     t = self._conv(t, c2, ops.ACT_RELU)
@@ -241,7 +255,7 @@ class VSNet:
                     cat = torch.empty((nb * ho * wo, c3.cout + nxt["conv1"].cout), device=self.device, dtype=self.dtype)
                 cat4 = cat.view(nb, ho, wo, c3.cout + nxt["conv1"].cout)
                 ops.conv2d_nhwc(t, c3.wt, c3.bias, kh=1, kw=1, stride=c3_stride, residual=identity, residual_stride=2,
-                                act=ops.ACT_RELU, out=cat4[..., :c3.cout])
+                                act=ops.ACT_RELU, out=cat4[..., :c3.cout], reverse=self._rev())
                 sampled = True
                 y = None
                 continue

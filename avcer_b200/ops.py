@@ -125,7 +125,7 @@ def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], 
              tap_h_in_dim4: bool = False, group_cin_shift: int = 0, residual: Optional[torch.Tensor] = None,
              res_stride: Optional[Sequence[int]] = None, act: int = ACT_NONE, res_after_act: bool = False,
              a_offset: int = 0, algo_k: Optional[int] = None, a_strip: bool = False,
-             wt_packed: Optional[torch.Tensor] = None, a_step: int = 1) -> torch.Tensor:
+             wt_packed: Optional[torch.Tensor] = None, a_step: int = 1, reverse: bool = False) -> torch.Tensor:
     """Generic implicit GEMM (see avcer_contract in include/avcer_b200.h)."""
     _cuda(a, "a")
     d = ContractDesc()
@@ -149,6 +149,7 @@ def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], 
     d.group_cin_shift = group_cin_shift
     d.a_strip = int(a_strip)
     d.a_step = int(a_step)
+    d.reverse_tiles = int(reverse)
     d.wt_packed = _ptr(wt_packed)
     d.act = act
     d.res_after_act = int(res_after_act)
@@ -170,7 +171,7 @@ def contract(*, a: torch.Tensor, a_dim: Sequence[int], a_stride: Sequence[int], 
 
 def conv2d_nhwc(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, kh: int, kw: int, stride: int = 1,
                 pad_h: int = 0, pad_w: int = 0, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
-                out: Optional[torch.Tensor] = None, residual_stride: int = 1) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, residual_stride: int = 1, reverse: bool = False) -> torch.Tensor:
     """x: [N,H,W,C] contiguous; wt: [Cout, kh*kw*C] (tap-major, channel-minor).
     residual_stride = s: `residual` is a contiguous [N, Hr, Wr, Cout] tensor read at every s-th pixel (a strided 1x1 conv
     whose residual lives at the input resolution: only the output pixels the next stage samples are computed)."""
@@ -186,7 +187,7 @@ def conv2d_nhwc(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor],
         # A pointwise conv does not see the image structure: run it as one [n*h*w, C] GEMM so that every M tile is a
         # full 128 rows (a 14x14 image only offers 126 + 70 row boxes, a 7x7 pair 98: 77 % of the MMA rows).
         linear(x.view(n * h * w, c), wt, bias, residual=None if residual is None else residual.view(n * h * w, cout),
-               act=act, out=out.view(n * h * w, cout))
+               act=act, out=out.view(n * h * w, cout), reverse=reverse)
         return out
     a_step = 1
     if stride == 1:
@@ -210,12 +211,12 @@ def conv2d_nhwc(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor],
         res_stride = (residual_stride * cout, residual_stride * wr * cout, hr * wr * cout)
     return contract(a=x, a_dim=a_dim, a_stride=a_stride, wt=wt, bias=bias, out=out,
                     out_stride=(op, wo * op, ho * wo * op), W=wo, H=ho, NB=n, cin=c, cout=cout, taps_w=kw,
-                    taps_h=kh, off_w=-pad_w, off_h=-pad_h, residual=residual, res_stride=res_stride, act=act, a_step=a_step)
+                    taps_h=kh, off_w=-pad_w, off_h=-pad_h, residual=residual, res_stride=res_stride, act=act, a_step=a_step, reverse=reverse)
 
 
 def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, residual: Optional[torch.Tensor] = None,
            act: int = ACT_NONE, res_after_act: bool = False, out: Optional[torch.Tensor] = None,
-           out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+           out_dtype: Optional[torch.dtype] = None, reverse: bool = False) -> torch.Tensor:
     """x: [M, K] (row pitch = x.stride(0)), wt: [N, K]; returns [M, N]."""
     m, k = x.shape
     n = wt.shape[0]
@@ -227,7 +228,7 @@ def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, r
     return contract(a=x, a_dim=(k, m, 1, 1, 1), a_stride=(1, ld, big, big, big), wt=wt, bias=bias, out=out,
                     out_stride=(out.stride(0), 0, 0), W=m, H=1, NB=1, cin=k, cout=n, residual=residual,
                     res_stride=None if residual is None else (residual.stride(0), 0, 0), act=act,
-                    res_after_act=res_after_act)
+                    res_after_act=res_after_act, reverse=reverse)
 
 
 # ----------------------------------------------------------------------------------------- K1

@@ -113,6 +113,10 @@ typedef struct {
                               * FULL-resolution input (c, w_in, h_in, n, 1) and output pixel (w, h) reads input pixel
                               * (s*w + off_w + tap_w, s*h + off_h + tap_h): the TMA box walks the input with traversal
                               * stride s (a 3x3 "same" conv evaluated only at every s-th pixel).  0 / 1: unit step. */
+  int32_t reverse_tiles;     /* bf16 path only. 1: the persistent CTAs walk the output tiles from the LAST to the first.  A
+                              * consumer that runs opposite to its producer starts on the rows the producer wrote last, i.e.
+                              * the ones still in L2 (tensors larger than the 126 MB L2 are otherwise re-read from HBM in
+                              * full).  Same tiles, same arithmetic: results are bit-identical. */
 } avcer_contract_desc;
 
 int avcer_contract(const avcer_contract_desc* d, void* stream);

@@ -112,8 +112,12 @@ class RetinaFacePredictor:
     def detect_batch(self, frames: Union[np.ndarray, torch.Tensor], rgb: bool = False) -> List[np.ndarray]:
         """frames: uint8 [n,H,W,3] (numpy, or a tensor already on the device) -> per frame the [k,15] float32 rows the
         reference's call returns (x1, y1, x2, y2, score, 5 landmark points), in its order."""
+        if len(frames) == 0:
+            return []
         if not isinstance(frames, torch.Tensor):
             frames = self._upload(frames)
+        elif not frames.is_cuda:
+            frames = frames.to(self.net.device)
         assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
         n = frames.shape[0]
         dets = self.net.detect(frames.contiguous(), rgb)                                # [n, P, 15] on the device

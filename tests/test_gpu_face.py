@@ -206,3 +206,31 @@ def test_video_predictor_process_matches_reference(cuda_lib, golden, tmp_path, p
         same = sum(np.array_equal(np.frombuffer(hashlib.sha256(open(os.path.join(save, n), "rb").read()).digest(), dtype=np.uint8), d)
                    for n, d in zip(names, g["process_sha256"]))
         assert same == len(names), (same, len(names))
+
+
+@pytest.mark.parametrize("cfg", [dict(threshold=0.5, top_k=2, nms_top_k=5000, conf_thresh=0.02, nms_thresh=0.4),
+                                 dict(threshold=0.6, top_k=750, nms_top_k=3, conf_thresh=0.02, nms_thresh=0.4),
+                                 dict(threshold=0.01, top_k=750, nms_top_k=5000, conf_thresh=0.3, nms_thresh=0.1),
+                                 dict(threshold=0.9, top_k=750, nms_top_k=5000, conf_thresh=0.02, nms_thresh=0.9)])
+def test_predictor_config_variants_match_oracle(cuda_lib, cfg):
+    """create_config / threshold variants (retina_face_predictor.py:55-58, 86-109): the device only hands over boxes with
+    score > conf_thresh AND >= threshold and the host runs NMS on those -- equivalent to the reference's order (NMS over
+    everything above conf_thresh, truncations, then the threshold) because suppression and both truncations act from the
+    high-score end.  Checked for truncating top_k / nms_top_k, a threshold BELOW conf_thresh, loose and tight NMS."""
+    from types import SimpleNamespace
+
+    from avcer_b200.data.face_detection import RetinaFacePredictor, cfg_re50
+    from oracle import face as ofa
+
+    sd = syn.make_retinaface_state_dict(5, "spread")
+    frame = syn.make_frames(43, 1, 150, 200)[0]
+    loc, conf, lm = ofa.forward(ofa.prepare(frame), sd)
+    ref = ofa.postprocess(loc[0], conf[0], lm[0], 150, 200, cfg["threshold"], cfg["conf_thresh"], cfg["nms_thresh"], cfg["nms_top_k"], cfg["top_k"])
+    pred = RetinaFacePredictor(threshold=cfg["threshold"], device=DEV, model=SimpleNamespace(weights=sd, config=SimpleNamespace(**cfg_re50)),
+                               config=RetinaFacePredictor.create_config(top_k=cfg["top_k"], conf_thresh=cfg["conf_thresh"],
+                                                                        nms_thresh=cfg["nms_thresh"], nms_top_k=cfg["nms_top_k"]),
+                               precision="fp32")
+    got = pred(frame, rgb=False)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    if len(ref):
+        assert np.abs(got[:, 4] - ref[:, 4]).max() < 1e-5 and np.abs(got - ref).max() < 2e-3

@@ -30,20 +30,71 @@ def _present_frames(path_images: str, total_frames: int):
     return paths, exists
 
 
-def _load_crops_gpu(paths, device):
-    """The crops decoded ON THE GPU (avcer_jpeg_decode, bit-identical to the cv2.imread of get_prob_video.py:95): the host
-    only reads the file bytes and parses the JPEG headers.  Returns (flat uint8 device buffer, offsets, heights, widths)."""
+CHUNK = 512      # crops per decode + VS chunk of the GPU-decoded path: the host reads / parses chunk k+1 while chunk k runs
+READ_THREADS = 8  # workers of avcer_read_files: open() + read() from Python cost ~20 us per 30 KB crop of interpreter overhead
+_read_buf = None
+
+
+def _read_files(paths):
+    """File bytes of `paths` as memoryviews into ONE pinned host buffer, filled by the library's multi-threaded reader
+    (avcer_read_files).  The views are valid until the next call."""
+    import ctypes
+
+    from . import _lib
+
+    global _read_buf
+    n = len(paths)
+    lib = _lib.load()
+    arr = (ctypes.c_char_p * n)(*[os.fsencode(p) for p in paths])
+    offsets = np.empty(n, dtype=np.int64)
+    sizes = np.empty(n, dtype=np.int64)
+    needed = ctypes.c_int64(0)
+    for attempt in range(2):
+        cap = 0 if _read_buf is None else _read_buf.numel()
+        rc = lib.avcer_read_files(arr, n, None if _read_buf is None else _read_buf.data_ptr(), cap, offsets.ctypes.data,
+                                  sizes.ctypes.data, ctypes.byref(needed), READ_THREADS)
+        if rc == 0:
+            break
+        if needed.value > cap and attempt == 0:            # first call / larger clip: grow the buffer and read again
+            _read_buf = torch.empty(max(needed.value * 5 // 4, 1 << 20), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+            continue
+        msg = lib.avcer_last_error().decode()
+        raise FileNotFoundError(msg) if "cannot" in msg else _lib.AvcerError(msg)
+    mv = memoryview(_read_buf.numpy())
+    return [mv[o:o + z] for o, z in zip(offsets.tolist(), sizes.tolist())]
+
+
+def _unsupported(e):
     from . import jpeg
 
-    files = []
-    for p in paths:
-        with open(p, "rb") as f:
-            files.append(f.read())
-    try:
-        return jpeg.decode_batch(files, device)
-    except jpeg.UnsupportedJpeg as e:
-        raise jpeg.UnsupportedJpeg(f"{e} -- the GPU decoder covers what cv2.imwrite writes by default (baseline, 4:2:0 / 4:4:4); "
-                                   "avcer_b200.config.set_jpeg_decoder('cv2') decodes on the host instead") from e
+    return jpeg.UnsupportedJpeg(f"{e} -- the GPU decoder covers what cv2.imwrite writes by default (baseline, 4:2:0 / 4:4:4); "
+                                "avcer_b200.config.set_jpeg_decoder('cv2') decodes on the host instead")
+
+
+def _vs_from_files_gpu(eng, paths):
+    """The crops decoded ON THE GPU (avcer_jpeg_decode, bit-identical to the cv2.imread of get_prob_video.py:95) and fed to
+    K1 + VS chunk by chunk: the host only reads file bytes and parses JPEG headers, and does so for the next chunk while
+    the GPU decodes and classifies the current one (no synchronisation until every chunk is enqueued)."""
+    from . import jpeg
+
+    n = len(paths)
+    probs, feats = eng._vs_outputs(n)
+    pending = []
+    for s in range(0, n, CHUNK):
+        files = _read_files(paths[s:s + CHUNK])
+        try:
+            flat, offsets, hs, ws, st = jpeg.decode_batch(files, eng.device, defer_status=True)
+        except jpeg.UnsupportedJpeg as e:
+            raise _unsupported(e) from e
+        st.base = s
+        pending.append(st)
+        eng.vs_forward_ragged(flat, offsets, hs, ws, out=(probs[s:s + len(files)], feats[s:s + len(files)]))
+    for st in pending:
+        try:
+            st.check()
+        except jpeg.UnsupportedJpeg as e:
+            raise _unsupported(e) from e
+    return probs, feats
 
 
 def _load_crops_cv2(paths, device):
@@ -75,9 +126,11 @@ def preprocess_video_and_predict(path_images="", save_path="", fps=30, total_fra
     paths, exists = _present_frames(path_images, total_frames)
     n_present = len(paths)
     if n_present:
-        load = _load_crops_gpu if config.jpeg_decoder() == "gpu" else _load_crops_cv2
-        flat, offsets, hs, ws = load(paths, eng.device)
-        probs, feats = eng.vs_forward_ragged(flat, offsets, hs, ws)
+        if config.jpeg_decoder() == "gpu":
+            probs, feats = _vs_from_files_gpu(eng, paths)
+        else:
+            flat, offsets, hs, ws = _load_crops_cv2(paths, eng.device)
+            probs, feats = eng.vs_forward_ragged(flat, offsets, hs, ws)
     else:
         probs = torch.zeros((1, 7), device=eng.device)
         feats = torch.zeros((1, 512), device=eng.device, dtype=torch.float32)

@@ -133,12 +133,13 @@ def _staging(dev: torch.device, nbytes: int) -> torch.Tensor:
     return buf
 
 
-def _parse_cached(f: bytes, last):
+def _parse_cached(f, last):
     """Files written by one encoder at one size share their whole header byte for byte (cv2.imwrite: 623 bytes): the marker
-    walk runs once per distinct header, every other file costs one prefix comparison.  Returns (header info, scan offset)."""
-    if last is not None and f.startswith(last[0]):
+    walk runs once per distinct header, every other file costs one prefix comparison.  Returns (header info, scan offset).
+    `f`: bytes or a memoryview (the files of get_prob_video._read_files live in one pinned buffer)."""
+    if last is not None and f[:len(last[0])] == last[0]:
         return last
-    p = parse(f)
+    p = parse(bytes(f))
     hdr = bytes(f[:p.scan_start])
     hit = _header_cache.get(hdr)
     if hit is None:
@@ -149,20 +150,39 @@ def _parse_cached(f: bytes, last):
     return hit
 
 
-def decode_batch(files: Sequence[bytes], device, align_out: int = 16) -> Tuple[torch.Tensor, np.ndarray, np.ndarray, np.ndarray]:
+class PendingStatus:
+    """Device-side decode status of one decode_batch(..., defer_status=True) call: check() synchronises and raises
+    UnsupportedJpeg like the immediate form would have."""
+
+    def __init__(self, statuses, base: int = 0):
+        self.statuses, self.base = statuses, base
+
+    def check(self) -> None:
+        for status, idx in self.statuses:
+            s = int(status.item())
+            if s > 0:
+                raise UnsupportedJpeg(f"corrupt entropy-coded data in image {self.base + int(idx[s - 1])} of the batch")
+            if s < 0:
+                raise UnsupportedJpeg(f"restart markers in image {self.base + int(idx[-s - 1])} of the batch")
+
+
+def decode_batch(files: Sequence[bytes], device, align_out: int = 16, defer_status: bool = False):
     """Decode a batch of JPEG byte strings.  Returns (flat uint8 device buffer, byte offsets [n], heights [n], widths [n]):
     image i is out[offsets[i] : offsets[i] + h*w*3] viewed as [h, w, 3] in BGR order -- what cv2.imread returns, and the
-    ragged layout Engine.vs_forward_ragged / avcer_preprocess_u8 consume.  `align_out`: alignment of every image's offset."""
+    ragged layout Engine.vs_forward_ragged / avcer_preprocess_u8 consume.  `align_out`: alignment of every image's offset.
+    defer_status: do not synchronise on the decoder's status word; a fifth return value (PendingStatus) checks it later, so
+    the host can prepare the next batch while this one decodes."""
     dev = torch.device(device)
     n = len(files)
     if n == 0:
-        return torch.zeros(16, dtype=torch.uint8, device=dev), np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32)
+        empty = (torch.zeros(16, dtype=torch.uint8, device=dev), np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32))
+        return empty + (PendingStatus([]),) if defer_status else empty
     heads, starts, ends = [], [], []
     last = None
     for f in files:
         last = _parse_cached(f, last)
         heads.append(last)
-        end = f.rfind(b"\xff\xd9")
+        end = len(f) - 2 if f[-2:] == b"\xff\xd9" else bytes(f).rfind(b"\xff\xd9")      # EOI: normally the last two bytes
         starts.append(len(last[0]))
         ends.append(end if end >= len(last[0]) else len(f))
     heights = np.array([h[1].height for h in heads], dtype=np.int32)
@@ -242,12 +262,10 @@ def decode_batch(files: Sequence[bytes], device, align_out: int = 16) -> Tuple[t
             e1.record()
             PROFILE.append((e0, e1))
         statuses.append((status, idx))
-    for status, idx in statuses:
-        s = int(status.item())
-        if s > 0:
-            raise UnsupportedJpeg(f"corrupt entropy-coded data in image {idx[s - 1]} of the batch")
-        if s < 0:
-            raise UnsupportedJpeg(f"restart markers in image {idx[-s - 1]} of the batch")
+    pending = PendingStatus(statuses)
+    if defer_status:
+        return out, offsets, heights, widths, pending
+    pending.check()
     return out, offsets, heights, widths
 
 

@@ -278,10 +278,12 @@ class Engine:
             feats[s0:e0].copy_(f)
         return probs, feats
 
-    def vs_forward_ragged(self, flat_u8: torch.Tensor, offsets: np.ndarray, heights: np.ndarray, widths: np.ndarray):
-        """Crops of arbitrary size packed back to back in `flat_u8` (K1 does the NEAREST resize)."""
+    def vs_forward_ragged(self, flat_u8: torch.Tensor, offsets: np.ndarray, heights: np.ndarray, widths: np.ndarray,
+                          out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        """Crops of arbitrary size packed back to back in `flat_u8` (K1 does the NEAREST resize).  `out`: (probs [n,7],
+        feats [n,512]) slices to fill instead of the engine's own result buffers (a clip processed in chunks)."""
         n = len(offsets)
-        probs, feats = self._vs_outputs(n)
+        probs, feats = out if out is not None else self._vs_outputs(n)
         off = self._upload(np.asarray(offsets), np.int64)
         hh = self._upload(np.asarray(heights), np.int32)
         ww = self._upload(np.asarray(widths), np.int32)

@@ -485,6 +485,35 @@ def main():
         except Exception as e:  # pragma: no cover  (cv2 missing: the figure is optional)
             micro["jpeg_decode_1500_crops"] = {"skipped": f"{type(e).__name__}: {e}"}
 
+        # the file-based drop-in call a user of the reference makes for one config-4 clip: 1500 JPEG crops on disk ->
+        # get_prob_video.preprocess_video_and_predict (listdir, file reads, GPU JPEG decode, K1, VS, VD, DataFrames)
+        try:
+            import tempfile
+
+            import cv2
+
+            from avcer_b200 import config as acfg, get_prob_video as gpv
+
+            with tempfile.TemporaryDirectory(prefix="avcer_bench_") as td:
+                os.makedirs(os.path.join(td, "clip", "00"))
+                base = syn.make_crops(5, 50)
+                for i in range(1500):
+                    cv2.imwrite(os.path.join(td, "clip", "00", f"{i:06d}.jpg"), base[i % 50])
+                acfg.set_precision(args.precision)
+                acfg.set_state_dicts(vs=syn.make_vs_state_dict(0, "default"), vd=syn.make_vd_state_dict(1))
+                walls = []
+                for _ in range(4):
+                    t0 = time.perf_counter()
+                    df_dyn, df_stat = gpv.preprocess_video_and_predict(path_images=os.path.join(td, "clip"), save_path=td, fps=25,
+                                                                       total_frames=1500)
+                    walls.append(time.perf_counter() - t0)
+                acfg.reset()
+                micro["dropin_video_1500_jpeg_files"] = {"frames_per_s_wall": 1500 / min(walls[1:]), "ms_wall": min(walls[1:]) * 1e3,
+                                                         "first_call_ms": walls[0] * 1e3, "rows": int(len(df_stat)),
+                                                         "what": "get_prob_video.preprocess_video_and_predict on 1500 JPEG crops of one "
+                                                                 "clip on disk (page cache), wall clock of the whole call"}
+        except Exception as e:  # pragma: no cover
+            micro["dropin_video_1500_jpeg_files"] = {"skipped": f"{type(e).__name__}: {e}"}
         # the face detector that produces the crops (RetinaFace-ResNet50 on raw 1080p frames;
         # the reference: one batch-1 call per frame, data/get_face_images.py:45-61)
         try:

@@ -326,6 +326,13 @@ int avcer_jpeg_decode(const uint8_t* raw, const avcer_jpeg_image* images, int n,
                       int64_t total_blocks, int64_t total_pixels, uint8_t* data, int64_t* lens, int16_t* coefs,
                       uint8_t* planes, uint8_t* out, int32_t* status, void* stream);
 
+/* Host-side staging of the crop files (no device work): reads n files with `threads` workers into one caller-owned
+ * (normally pinned) buffer, file i at dst + offsets[i] (written here, 16-byte aligned), sizes[i] = its length; *needed =
+ * total bytes required (also set when capacity is too small, so the caller can grow the buffer and call again).
+ * Replaces the per-file read inside cv2.imread (get_prob_video.py:95) for the GPU-decoded path. */
+int avcer_read_files(const char* const* paths, int n, uint8_t* dst, int64_t capacity, int64_t* offsets,
+                     int64_t* sizes, int64_t* needed, int threads);
+
 /* ---- Face detector: RetinaFace-ResNet50 behind data/get_face_images.py:38-63.  The 1x1 / 3x3
  * convolutions of body, FPN, SSH and heads are avcer_contract calls; these are the layers it does not cover. ---- */
 /* Stem on raw video frames (retina_face_predictor.py:61-67 + torchvision resnet50 conv1/bn1/relu): frames [n,h,w,3] uint8

@@ -24,7 +24,7 @@
 namespace avcer {
 
 struct JpegImage {            // mirrors avcer_jpeg_image (include/avcer_b200.h)
-  long long data_off;         // byte offset of the un-stuffed entropy-coded segment in `data` (multiple of 4)
+  long long data_off;         // byte offset of the un-stuffed segment in `data` (multiple of 4); the stuffed one starts at raw + data_off + src_shift
   long long data_len;         // its length in bytes
   long long coef_off;         // first block of the image in the coefficient array (Y blocks, then Cb, then Cr)
   long long plane_off;        // byte offset of the Y plane in `planes` (Cb, Cr follow)
@@ -33,7 +33,7 @@ struct JpegImage {            // mirrors avcer_jpeg_image (include/avcer_b200.h)
   int mcus_w, mcus_h;
   int hs;                     // luma sampling factor per axis: 2 = 4:2:0, 1 = 4:4:4
   int qt_y, qt_c;             // quantisation table indices
-  int reserved;
+  int src_shift;              // 0..3: the segment may sit at any byte of `raw` (whole files uploaded as they are)
 };
 
 constexpr int LOOK = 10;      // look-ahead bits of the fast Huffman path
@@ -62,7 +62,7 @@ jpeg_unstuff_kernel(const unsigned char* __restrict__ raw, const JpegImage* __re
   __shared__ long long base_s;
   const int img = blockIdx.x;
   const long long off = imgs[img].data_off, len = imgs[img].data_len;
-  const unsigned char* src = raw + off;
+  const unsigned char* src = raw + off + imgs[img].src_shift;
   unsigned char* dst = data + off;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) base_s = 0;

@@ -36,11 +36,11 @@ _read_buf = None
 
 
 def _read_files(paths):
-    """File bytes of `paths` as memoryviews into ONE pinned host buffer, filled by the library's multi-threaded reader
-    (avcer_read_files).  The views are valid until the next call."""
+    """The files of `paths` read into ONE pinned host buffer by the library's multi-threaded reader (avcer_read_files).
+    Returns (buffer, offsets [n], sizes [n]); the buffer is reused by the next call (after its last upload has finished)."""
     import ctypes
 
-    from . import _lib
+    from . import _lib, jpeg
 
     global _read_buf
     n = len(paths)
@@ -49,6 +49,8 @@ def _read_files(paths):
     offsets = np.empty(n, dtype=np.int64)
     sizes = np.empty(n, dtype=np.int64)
     needed = ctypes.c_int64(0)
+    if _read_buf is not None:
+        jpeg.wait_uploaded(_read_buf)
     for attempt in range(2):
         cap = 0 if _read_buf is None else _read_buf.numel()
         rc = lib.avcer_read_files(arr, n, None if _read_buf is None else _read_buf.data_ptr(), cap, offsets.ctypes.data,
@@ -60,8 +62,7 @@ def _read_files(paths):
             continue
         msg = lib.avcer_last_error().decode()
         raise FileNotFoundError(msg) if "cannot" in msg else _lib.AvcerError(msg)
-    mv = memoryview(_read_buf.numpy())
-    return [mv[o:o + z] for o, z in zip(offsets.tolist(), sizes.tolist())]
+    return _read_buf, offsets, sizes
 
 
 def _unsupported(e):
@@ -81,14 +82,14 @@ def _vs_from_files_gpu(eng, paths):
     probs, feats = eng._vs_outputs(n)
     pending = []
     for s in range(0, n, CHUNK):
-        files = _read_files(paths[s:s + CHUNK])
+        buf, foff, fsize = _read_files(paths[s:s + CHUNK])
         try:
-            flat, offsets, hs, ws, st = jpeg.decode_batch(files, eng.device, defer_status=True)
+            flat, offsets, hs, ws, st = jpeg.decode_packed(buf, foff, fsize, eng.device, defer_status=True)
         except jpeg.UnsupportedJpeg as e:
             raise _unsupported(e) from e
         st.base = s
         pending.append(st)
-        eng.vs_forward_ragged(flat, offsets, hs, ws, out=(probs[s:s + len(files)], feats[s:s + len(files)]))
+        eng.vs_forward_ragged(flat, offsets, hs, ws, out=(probs[s:s + len(foff)], feats[s:s + len(foff)]))
     for st in pending:
         try:
             st.check()

@@ -24,7 +24,7 @@ ZIGZAG = np.array([0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 1
 
 IMAGE_DTYPE = np.dtype([("data_off", "<i8"), ("data_len", "<i8"), ("coef_off", "<i8"), ("plane_off", "<i8"), ("out_off", "<i8"),
                         ("width", "<i4"), ("height", "<i4"), ("mcus_w", "<i4"), ("mcus_h", "<i4"), ("hs", "<i4"), ("qt_y", "<i4"),
-                        ("qt_c", "<i4"), ("reserved", "<i4")], align=True)          # avcer_jpeg_image
+                        ("qt_c", "<i4"), ("src_shift", "<i4")], align=True)          # avcer_jpeg_image
 
 
 PROFILE = None          # measurement aid: a list receiving (event before, event after) around every avcer_jpeg_decode call
@@ -120,16 +120,22 @@ def unstuff(data: bytes) -> bytes:
 
 _header_cache = {}       # header bytes (SOI .. end of the SOS segment) -> ParsedJpeg without data
 _stage_bufs = {}         # device -> pinned uint8 staging buffer (grow-only)
-_stage_events = {}       # device -> event recorded after the last H2D copy out of the staging buffer
+_upload_events = {}      # data_ptr of a pinned host buffer -> event recorded after the last H2D copy out of it
+
+
+def wait_uploaded(buf: torch.Tensor) -> None:
+    """Block until the last decode_packed() that read `buf` has copied it to the device (the buffer may be refilled)."""
+    ev = _upload_events.get(buf.data_ptr())
+    if ev is not None:
+        ev.synchronize()
 
 
 def _staging(dev: torch.device, nbytes: int) -> torch.Tensor:
     buf = _stage_bufs.get(dev)
     if buf is None or buf.numel() < nbytes:
         buf = _stage_bufs[dev] = torch.empty(max(nbytes, 1 << 20) * 5 // 4, dtype=torch.uint8, pin_memory=True)
-        _stage_events[dev] = torch.cuda.Event()
     else:
-        _stage_events[dev].synchronize()          # the previous batch's copy has left the buffer
+        wait_uploaded(buf)                        # the previous batch's copy has left the buffer
     return buf
 
 
@@ -171,29 +177,63 @@ def decode_batch(files: Sequence[bytes], device, align_out: int = 16, defer_stat
     image i is out[offsets[i] : offsets[i] + h*w*3] viewed as [h, w, 3] in BGR order -- what cv2.imread returns, and the
     ragged layout Engine.vs_forward_ragged / avcer_preprocess_u8 consume.  `align_out`: alignment of every image's offset.
     defer_status: do not synchronise on the decoder's status word; a fifth return value (PendingStatus) checks it later, so
-    the host can prepare the next batch while this one decodes."""
+    the host can prepare the next batch while this one decodes.
+    The files are packed into one pinned staging buffer (one host copy) and handed to decode_packed."""
     dev = torch.device(device)
     n = len(files)
+    sizes = np.fromiter((len(f) for f in files), dtype=np.int64, count=n)
+    padded = (sizes + 15) // 16 * 16
+    file_off = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+    total = int(padded.sum())
+    stage = _staging(dev, total + 16)
+    stage_np = stage.numpy()
+    for f, o, z in zip(files, file_off.tolist(), sizes.tolist()):
+        stage_np[o:o + z] = np.frombuffer(f, dtype=np.uint8, count=z)
+    return decode_packed(stage, file_off, sizes, dev, align_out, defer_status)
+
+
+def decode_packed(stage: torch.Tensor, file_off: np.ndarray, file_size: np.ndarray, device, align_out: int = 16,
+                  defer_status: bool = False):
+    """decode_batch for files that already sit in ONE pinned host buffer (`stage`; file i = stage[file_off[i] : + file_size[i]],
+    e.g. filled by avcer_read_files): the whole buffer goes to the device in one copy and every image's entropy-coded segment
+    is addressed in place (avcer_jpeg_image.data_off = its position rounded down to a word, src_shift = the remainder) -- no
+    per-file staging copy.  wait_uploaded(stage) tells when the buffer may be refilled."""
+    dev = torch.device(device)
+    n = len(file_off)
     if n == 0:
         empty = (torch.zeros(16, dtype=torch.uint8, device=dev), np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32))
         return empty + (PendingStatus([]),) if defer_status else empty
+    mv = memoryview(stage.numpy())
     heads, starts, ends = [], [], []
     last = None
-    for f in files:
+    for o, z in zip(file_off.tolist(), file_size.tolist()):
+        f = mv[o:o + z]
         last = _parse_cached(f, last)
         heads.append(last)
-        end = len(f) - 2 if f[-2:] == b"\xff\xd9" else bytes(f).rfind(b"\xff\xd9")      # EOI: normally the last two bytes
+        end = z - 2 if f[-2:] == b"\xff\xd9" else bytes(f).rfind(b"\xff\xd9")      # EOI: normally the last two bytes
         starts.append(len(last[0]))
-        ends.append(end if end >= len(last[0]) else len(f))
+        ends.append(end if end >= len(last[0]) else z)
     heights = np.array([h[1].height for h in heads], dtype=np.int32)
     widths = np.array([h[1].width for h in heads], dtype=np.int32)
     hs = np.array([h[1].hs for h in heads], dtype=np.int32)
+    starts, ends = np.asarray(starts, dtype=np.int64), np.asarray(ends, dtype=np.int64)
     sizes = heights.astype(np.int64) * widths * 3
     padded = (sizes + align_out - 1) // align_out * align_out
     offsets = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64)
     out = torch.empty(int(padded.sum()) + 16, dtype=torch.uint8, device=dev)
     lib = _lib.load()
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    cur = torch.cuda.current_stream(dev)
+    stream = cur.cuda_stream
+    total = int(file_off[-1] + (file_size[-1] + 15) // 16 * 16) + 8
+    total = min(total, stage.numel())
+    raw = torch.empty(total, dtype=torch.uint8, device=dev)
+    raw.copy_(stage[:total], non_blocking=True)
+    ev = _upload_events.get(stage.data_ptr())
+    if ev is None:
+        ev = _upload_events[stage.data_ptr()] = torch.cuda.Event()
+    ev.record(cur)
+    data = torch.empty_like(raw)
+    src = np.asarray(file_off, dtype=np.int64) + starts               # first byte of every entropy-coded segment in `raw`
     # images that share their Huffman tables go in one launch (cv2.imwrite always uses the Annex-K tables)
     groups = {}
     for i, h in enumerate(heads):
@@ -213,14 +253,13 @@ def decode_batch(files: Sequence[bytes], device, align_out: int = 16, defer_stat
 
         qy = np.array([qslot(heads[i][1].qt_y) for i in idx], dtype=np.int32)
         qc = np.array([qslot(heads[i][1].qt_c) for i in idx], dtype=np.int32)
-        lens = np.array([ends[i] - starts[i] for i in idx], dtype=np.int64)
-        lens4 = (lens + 3) // 4 * 4
         w, h, s = widths[idx].astype(np.int64), heights[idx].astype(np.int64), hs[idx].astype(np.int64)
         mw, mh = -(-w // (8 * s)), -(-h // (8 * s))
         blocks = mw * mh * (s * s + 2)
         imgs = np.zeros(m, dtype=IMAGE_DTYPE)
-        imgs["data_off"] = np.concatenate([[0], np.cumsum(lens4)[:-1]])
-        imgs["data_len"] = lens
+        imgs["data_off"] = src[idx] & ~np.int64(3)
+        imgs["src_shift"] = (src[idx] & 3).astype(np.int32)           # src_shift
+        imgs["data_len"] = ends[idx] - starts[idx]
         imgs["coef_off"] = np.concatenate([[0], np.cumsum(blocks)[:-1]])
         imgs["plane_off"] = imgs["coef_off"] * 64
         imgs["out_off"] = offsets[idx]
@@ -228,18 +267,6 @@ def decode_batch(files: Sequence[bytes], device, align_out: int = 16, defer_stat
         imgs["qt_y"], imgs["qt_c"] = qy, qc
         prefix = np.concatenate([[0], np.cumsum(w * h)[:-1]]).astype(np.int64)
         coef_total, pix = int(blocks.sum()), int((w * h).sum())
-        # the entropy-coded segments go straight from the file buffers into one pinned staging buffer (one host copy, one H2D)
-        total = int(lens4.sum()) + 8
-        stage = _staging(dev, total)
-        stage_np = stage.numpy()
-        doff = imgs["data_off"]
-        for k, i in enumerate(idx):
-            o = int(doff[k])
-            stage_np[o: o + int(lens[k])] = np.frombuffer(files[i], dtype=np.uint8, count=int(lens[k]), offset=starts[i])
-        raw = torch.empty(total, dtype=torch.uint8, device=dev)
-        raw.copy_(stage[:total], non_blocking=True)
-        _stage_events[dev].record(torch.cuda.current_stream(dev))
-        data = torch.empty_like(raw)
         dlens = torch.empty(m, dtype=torch.int64, device=dev)
         meta = torch.from_numpy(imgs.view(np.uint8).reshape(-1)).to(dev)
         p0 = heads[idx[0]][1]

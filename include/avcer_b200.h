@@ -304,7 +304,8 @@ int avcer_cast(const void* x, int64_t n, int src_dtype, void* y, int dst_dtype, 
  * h2v2 fancy up-sampling and ycc_rgb_convert restated as integer kernels.
  * The HOST walks the marker segments (SOF0 / DQT / DHT / SOS) and fills, per image: */
 typedef struct {
-  int64_t data_off;   /* byte offset of the image's entropy-coded segment in `raw` (multiple of 4) */
+  int64_t data_off;   /* the image's entropy-coded segment starts at raw + data_off + src_shift; data_off is a multiple of 4
+                       * (its un-stuffed copy is written to data + data_off) */
   int64_t data_len;   /* its length in bytes */
   int64_t coef_off;   /* first 8x8 block of the image in `coefs` (all Y blocks row-major, then Cb, then Cr) */
   int64_t plane_off;  /* byte offset of the image's Y sample plane in `planes` (Cb and Cr planes follow); multiple of 8 */
@@ -313,7 +314,7 @@ typedef struct {
   int32_t mcus_w, mcus_h;  /* MCU grid: ceil(width / (8*hs)), ceil(height / (8*hs)) */
   int32_t hs;         /* luma sampling factor on both axes: 2 = 4:2:0, 1 = 4:4:4 */
   int32_t qt_y, qt_c; /* indices into qtables */
-  int32_t reserved;
+  int32_t src_shift;  /* 0..3, see data_off: lets whole files be uploaded as they are, header included */
 } avcer_jpeg_image;
 /* raw: all entropy-coded segments as they sit in the files (still byte-stuffed), image i at data_off / data_len;
  * huff_bits [4][16] / huff_vals [4][256]: the tables DC0, AC0, DC1, AC1 (luma, chroma) shared by the batch; qtables [*][64]

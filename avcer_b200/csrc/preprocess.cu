@@ -12,6 +12,7 @@
 // Memory-bound: one CTA converts 4 output rows of one crop; source rows are staged through shared
 // memory with 16-byte loads and every global store is a fully coalesced 16-byte vector.
 #include "common.h"
+#include <stdlib.h>
 
 namespace avcer {
 
@@ -126,23 +127,23 @@ preprocess_kernel(const uint8_t* __restrict__ src, const long long* __restrict__
 // Fast path for packed 224x224 crops (resize = identity; BASELINE configs): one CTA converts 16 rows.
 // 10752 contiguous input bytes are staged with three 16-byte loads in flight per thread, then every
 // thread emits seven fully coalesced 16-byte stores (two bf16 NHWC4 pixels each).
-constexpr int ROWS_I = 16;
-template <int LAYOUT>
+template <int LAYOUT, int ROWS_I = 16, int CS = 0>
 __global__ void __launch_bounds__(256)
 preprocess_identity_kernel(const uint8_t* __restrict__ src, void* __restrict__ dst) {
   __shared__ __align__(16) uint8_t sm[ROWS_I * OUT * 3];
   const int crop = blockIdx.y;
   const int y0 = blockIdx.x * ROWS_I;
   const uint4* g = reinterpret_cast<const uint4*>(src + (size_t)crop * OUT * OUT * 3 + (size_t)y0 * OUT * 3);
-  constexpr int NV = ROWS_I * OUT * 3 / 16;      // 672
-  uint4 tmp[3];
+  constexpr int NV = ROWS_I * OUT * 3 / 16;      // 672 for 16 rows
+  constexpr int NL = (NV + 255) / 256;
+  uint4 tmp[NL];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < NL; ++k) {
     const int i = threadIdx.x + k * 256;
     if (i < NV) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(tmp[k].x), "=r"(tmp[k].y), "=r"(tmp[k].z), "=r"(tmp[k].w) : "l"(g + i));
   }
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < NL; ++k) {
     const int i = threadIdx.x + k * 256;
     if (i < NV) reinterpret_cast<uint4*>(sm)[i] = tmp[k];
   }
@@ -151,8 +152,9 @@ preprocess_identity_kernel(const uint8_t* __restrict__ src, void* __restrict__ d
   if (LAYOUT == 1) {
     __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst) + (size_t)crop * PADH * PADW * 4;
 #pragma unroll
-    for (int it = 0; it < ROWS_I * (OUT / 2) / 256; ++it) {
+    for (int it = 0; it < (ROWS_I * (OUT / 2) + 255) / 256; ++it) {
       const int t = threadIdx.x + it * 256;
+      if (t >= ROWS_I * (OUT / 2)) break;
       const int r = t / (OUT / 2), q = t % (OUT / 2);
       const unsigned short* px = s16 + r * (OUT * 3 / 2) + q * 3;        // 6 bytes = 2 BGR pixels
       const unsigned a = px[0], b = px[1], c = px[2];
@@ -162,7 +164,8 @@ preprocess_identity_kernel(const uint8_t* __restrict__ src, void* __restrict__ d
       h2[1] = __floats2bfloat162_rn((float)(b & 0xff) - c_mean[2], 0.f);
       h2[2] = __floats2bfloat162_rn((float)(b >> 8) - c_mean[0], (float)(c & 0xff) - c_mean[1]);
       h2[3] = __floats2bfloat162_rn((float)(c >> 8) - c_mean[2], 0.f);
-      *reinterpret_cast<uint4*>(d + ((size_t)(y0 + r + PAD0) * PADW + PAD0 + 2 * q) * 4) = u;
+      uint4* o = reinterpret_cast<uint4*>(d + ((size_t)(y0 + r + PAD0) * PADW + PAD0 + 2 * q) * 4);
+      if (CS) __stcs(o, u); else *o = u;
     }
   } else {
     float* d = static_cast<float*>(dst) + (size_t)crop * PADH * PADW * 4;
@@ -248,9 +251,15 @@ extern "C" int avcer_preprocess_u8(const uint8_t* src, const int64_t* src_offset
   cudaStream_t st = as_stream(stream);
   const long long* offs = reinterpret_cast<const long long*>(src_offsets);
   if (src_offsets == nullptr && src_h == nullptr && dst_layout != 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-    dim3 gi(OUT / ROWS_I, n);
-    if (dst_layout == 1) preprocess_identity_kernel<1><<<gi, 256, 0, st>>>(src, dst);
-    else preprocess_identity_kernel<2><<<gi, 256, 0, st>>>(src, dst);
+    // AVCER_K1_STREAM=0: plain stores instead of streaming (st.global.cs) ones.  Streaming stores measured 116 -> 109 us at
+    // 1024 crops (0.62 -> 0.66 of the copy peak algorithmic); 8- or 32-row tiles instead of 16 made no difference.
+    static const int stream_stores = getenv("AVCER_K1_STREAM") ? atoi(getenv("AVCER_K1_STREAM")) : 1;
+    if (dst_layout == 1) {
+      if (stream_stores) preprocess_identity_kernel<1, 16, 1><<<dim3(OUT / 16, n), 256, 0, st>>>(src, dst);
+      else preprocess_identity_kernel<1, 16, 0><<<dim3(OUT / 16, n), 256, 0, st>>>(src, dst);
+    } else {
+      preprocess_identity_kernel<2><<<dim3(OUT / 16, n), 256, 0, st>>>(src, dst);
+    }
     return check_launch("preprocess_identity_kernel");
   }
   if (dst_layout == 0) preprocess_kernel<0><<<grid, 256, 0, st>>>(src, offs, src_h, src_w, maps, dst);

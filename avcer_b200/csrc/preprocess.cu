@@ -101,7 +101,10 @@ preprocess_kernel(const uint8_t* __restrict__ src, const long long* __restrict__
       h2[1] = __floats2bfloat162_rn(a[2], 0.f);
       h2[2] = __floats2bfloat162_rn(b[0], b[1]);
       h2[3] = __floats2bfloat162_rn(b[2], 0.f);
-      *reinterpret_cast<uint4*>(d + ((size_t)(y0 + r + PAD0) * PADW + PAD0 + 2 * q) * 4) = u;
+      uint4* o = reinterpret_cast<uint4*>(d + ((size_t)(y0 + r + PAD0) * PADW + PAD0 + 2 * q) * 4);
+      __stcs(o, u);
+      // full 32-byte sectors at both ends of the row (see preprocess_identity_kernel): the neighbouring border pixels are zero
+      if (q == 0 || q == OUT / 2 - 1) __stcs(q == 0 ? o - 1 : o + 1, make_uint4(0u, 0u, 0u, 0u));
     }
   } else if (LAYOUT == 2) {
     float* d = static_cast<float*>(dst) + (size_t)crop * PADH * PADW * 4;
@@ -166,6 +169,13 @@ preprocess_identity_kernel(const uint8_t* __restrict__ src, void* __restrict__ d
       h2[3] = __floats2bfloat162_rn((float)(c >> 8) - c_mean[2], 0.f);
       uint4* o = reinterpret_cast<uint4*>(d + ((size_t)(y0 + r + PAD0) * PADW + PAD0 + 2 * q) * 4);
       if (CS) __stcs(o, u); else *o = u;
+      if (q == 0 || q == OUT / 2 - 1) {
+        // The interior of a row starts 16 bytes into a 32-byte sector and ends 16 bytes into another one (2 border pixels +
+        // 224 pixels of 8 bytes): two PARTIAL sector writes per row, each a read-modify-write at the DRAM.  Rewriting the two
+        // neighbouring (zero) border pixels makes every sector of the row a full write: 116 -> 87 us per 1024 crops.
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        if (CS) __stcs(q == 0 ? o - 1 : o + 1, z); else *(q == 0 ? o - 1 : o + 1) = z;
+      }
     }
   } else {
     float* d = static_cast<float*>(dst) + (size_t)crop * PADH * PADW * 4;
@@ -251,8 +261,9 @@ extern "C" int avcer_preprocess_u8(const uint8_t* src, const int64_t* src_offset
   cudaStream_t st = as_stream(stream);
   const long long* offs = reinterpret_cast<const long long*>(src_offsets);
   if (src_offsets == nullptr && src_h == nullptr && dst_layout != 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-    // AVCER_K1_STREAM=0: plain stores instead of streaming (st.global.cs) ones.  Streaming stores measured 116 -> 109 us at
-    // 1024 crops (0.62 -> 0.66 of the copy peak algorithmic); 8- or 32-row tiles instead of 16 made no difference.
+    // AVCER_K1_STREAM=0: plain stores instead of streaming (st.global.cs) ones.  At 1024 crops: 116 us (0.62 of the copy peak
+    // algorithmic) originally; 109 us with streaming stores; 87 us (0.82) once the two partial 32-byte sectors per row were
+    // turned into full writes (see the kernel); 8- or 32-row tiles instead of 16 made no difference.
     static const int stream_stores = getenv("AVCER_K1_STREAM") ? atoi(getenv("AVCER_K1_STREAM")) : 1;
     if (dst_layout == 1) {
       if (stream_stores) preprocess_identity_kernel<1, 16, 1><<<dim3(OUT / 16, n), 256, 0, st>>>(src, dst);

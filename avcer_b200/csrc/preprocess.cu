@@ -130,7 +130,7 @@ preprocess_kernel(const uint8_t* __restrict__ src, const long long* __restrict__
 // Fast path for packed 224x224 crops (resize = identity; BASELINE configs): one CTA converts 16 rows.
 // 10752 contiguous input bytes are staged with three 16-byte loads in flight per thread, then every
 // thread emits seven fully coalesced 16-byte stores (two bf16 NHWC4 pixels each).
-template <int LAYOUT, int ROWS_I = 16, int CS = 0>
+template <int LAYOUT, int ROWS_I = 16, int CS = 0, int FULL_SECTORS = 1>
 __global__ void __launch_bounds__(256)
 preprocess_identity_kernel(const uint8_t* __restrict__ src, void* __restrict__ dst) {
   __shared__ __align__(16) uint8_t sm[ROWS_I * OUT * 3];
@@ -169,7 +169,7 @@ preprocess_identity_kernel(const uint8_t* __restrict__ src, void* __restrict__ d
       h2[3] = __floats2bfloat162_rn((float)(c >> 8) - c_mean[2], 0.f);
       uint4* o = reinterpret_cast<uint4*>(d + ((size_t)(y0 + r + PAD0) * PADW + PAD0 + 2 * q) * 4);
       if (CS) __stcs(o, u); else *o = u;
-      if (q == 0 || q == OUT / 2 - 1) {
+      if (FULL_SECTORS && (q == 0 || q == OUT / 2 - 1)) {
         // The interior of a row starts 16 bytes into a 32-byte sector and ends 16 bytes into another one (2 border pixels +
         // 224 pixels of 8 bytes): two PARTIAL sector writes per row, each a read-modify-write at the DRAM.  Rewriting the two
         // neighbouring (zero) border pixels makes every sector of the row a full write: 116 -> 87 us per 1024 crops.
@@ -266,7 +266,9 @@ extern "C" int avcer_preprocess_u8(const uint8_t* src, const int64_t* src_offset
     // turned into full writes (see the kernel); 8- or 32-row tiles instead of 16 made no difference.
     static const int stream_stores = getenv("AVCER_K1_STREAM") ? atoi(getenv("AVCER_K1_STREAM")) : 1;
     if (dst_layout == 1) {
-      if (stream_stores) preprocess_identity_kernel<1, 16, 1><<<dim3(OUT / 16, n), 256, 0, st>>>(src, dst);
+      static const int partial = getenv("AVCER_K1_PARTIAL") ? atoi(getenv("AVCER_K1_PARTIAL")) : 0;   // 1: the round-1 kernel (evidence runs)
+      if (partial) preprocess_identity_kernel<1, 16, 0, 0><<<dim3(OUT / 16, n), 256, 0, st>>>(src, dst);
+      else if (stream_stores) preprocess_identity_kernel<1, 16, 1><<<dim3(OUT / 16, n), 256, 0, st>>>(src, dst);
       else preprocess_identity_kernel<1, 16, 0><<<dim3(OUT / 16, n), 256, 0, st>>>(src, dst);
     } else {
       preprocess_identity_kernel<2><<<dim3(OUT / 16, n), 256, 0, st>>>(src, dst);

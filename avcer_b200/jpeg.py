@@ -35,7 +35,7 @@ class UnsupportedJpeg(ValueError):
 
 
 class ParsedJpeg:
-    __slots__ = ("width", "height", "hs", "qt_y", "qt_c", "huff_bits", "huff_vals", "data", "scan_start")
+    __slots__ = ("width", "height", "hs", "qt_y", "qt_c", "huff_bits", "huff_vals", "data", "scan_start", "dims_off")
 
 
 def _u16(b: bytes, i: int) -> int:
@@ -64,6 +64,7 @@ def parse(buf: bytes) -> ParsedJpeg:
             if seg[0] != 8:
                 raise UnsupportedJpeg("only 8-bit samples")
             height, width = _u16(seg, 1), _u16(seg, 3)
+            dims_off = i + 5                                       # file offset of the height / width bytes (2 + 2)
             comps = [(seg[6 + 3 * c], seg[7 + 3 * c] >> 4, seg[7 + 3 * c] & 15, seg[8 + 3 * c]) for c in range(seg[5])]
         elif 0xC1 <= m <= 0xCF and m not in (0xC4, 0xC8, 0xCC):
             raise UnsupportedJpeg(f"SOF marker 0x{m:02x}: only baseline sequential DCT (SOF0) is decoded on the GPU")
@@ -110,6 +111,7 @@ def parse(buf: bytes) -> ParsedJpeg:
     out.huff_vals = np.stack([t[1] for t in tabs])
     out.data = buf[i: end if end >= i else n]            # entropy-coded segment, still byte-stuffed (the device removes the stuffing)
     out.scan_start = i
+    out.dims_off = dims_off
     return out
 
 
@@ -140,20 +142,25 @@ def _staging(dev: torch.device, nbytes: int) -> torch.Tensor:
 
 
 def _parse_cached(f, last):
-    """Files written by one encoder at one size share their whole header byte for byte (cv2.imwrite: 623 bytes): the marker
-    walk runs once per distinct header, every other file costs one prefix comparison.  Returns (header info, scan offset).
-    `f`: bytes or a memoryview (the files of get_prob_video._read_files live in one pinned buffer)."""
-    if last is not None and f[:len(last[0])] == last[0]:
-        return last
+    """Files written by one encoder with one setting share their whole header byte for byte except the four height / width
+    bytes of SOF0 (cv2.imwrite: 623 bytes; the face crops of a clip all differ in size): the marker walk runs once per
+    distinct header family, every other file costs two slice comparisons.  Returns ((header bytes, ParsedJpeg of the family's
+    first file, Huffman table key), height, width).  `f`: bytes or a memoryview."""
+    if last is not None:
+        hdr, p = last[0][0], last[0][1]
+        d, n = p.dims_off, len(hdr)
+        if f[:d] == hdr[:d] and f[d + 4:n] == hdr[d + 4:n]:
+            return last[0], (f[d] << 8) | f[d + 1], (f[d + 2] << 8) | f[d + 3]
     p = parse(bytes(f))
     hdr = bytes(f[:p.scan_start])
-    hit = _header_cache.get(hdr)
+    key = hdr[:p.dims_off] + hdr[p.dims_off + 4:]
+    hit = _header_cache.get(key)
     if hit is None:
         if len(_header_cache) > 256:
             _header_cache.clear()
         p.data = None
-        hit = _header_cache[hdr] = (hdr, p, p.huff_bits.tobytes() + p.huff_vals.tobytes())
-    return hit
+        hit = _header_cache[key] = (hdr, p, p.huff_bits.tobytes() + p.huff_vals.tobytes())
+    return hit, p.height, p.width
 
 
 class PendingStatus:
@@ -204,17 +211,20 @@ def decode_packed(stage: torch.Tensor, file_off: np.ndarray, file_size: np.ndarr
         empty = (torch.zeros(16, dtype=torch.uint8, device=dev), np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32))
         return empty + (PendingStatus([]),) if defer_status else empty
     mv = memoryview(stage.numpy())
-    heads, starts, ends = [], [], []
+    heads, starts, ends, hh, ww = [], [], [], [], []
     last = None
     for o, z in zip(file_off.tolist(), file_size.tolist()):
         f = mv[o:o + z]
         last = _parse_cached(f, last)
-        heads.append(last)
+        head = last[0]
+        heads.append(head)
+        hh.append(last[1])
+        ww.append(last[2])
         end = z - 2 if f[-2:] == b"\xff\xd9" else bytes(f).rfind(b"\xff\xd9")      # EOI: normally the last two bytes
-        starts.append(len(last[0]))
-        ends.append(end if end >= len(last[0]) else z)
-    heights = np.array([h[1].height for h in heads], dtype=np.int32)
-    widths = np.array([h[1].width for h in heads], dtype=np.int32)
+        starts.append(len(head[0]))
+        ends.append(end if end >= len(head[0]) else z)
+    heights = np.array(hh, dtype=np.int32)
+    widths = np.array(ww, dtype=np.int32)
     hs = np.array([h[1].hs for h in heads], dtype=np.int32)
     starts, ends = np.asarray(starts, dtype=np.int64), np.asarray(ends, dtype=np.int64)
     sizes = heights.astype(np.int64) * widths * 3

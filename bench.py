@@ -496,9 +496,13 @@ def main():
 
             with tempfile.TemporaryDirectory(prefix="avcer_bench_") as td:
                 os.makedirs(os.path.join(td, "clip", "00"))
-                base = syn.make_crops(5, 50)
+                # face crops as a detector writes them: every file its own size (here 160 .. 319 px, cut out of 50 synthetic
+                # faces), so K1 resizes and the JPEG headers differ from file to file
+                base = syn.make_crops(5, 50, 320)
+                rs = np.random.default_rng(11)
                 for i in range(1500):
-                    cv2.imwrite(os.path.join(td, "clip", "00", f"{i:06d}.jpg"), base[i % 50])
+                    hh, ww = (int(v) for v in rs.integers(160, 320, 2))
+                    cv2.imwrite(os.path.join(td, "clip", "00", f"{i:06d}.jpg"), np.ascontiguousarray(base[i % 50][:hh, :ww]))
                 acfg.set_precision(args.precision)
                 acfg.set_state_dicts(vs=syn.make_vs_state_dict(0, "default"), vd=syn.make_vd_state_dict(1))
                 walls = []
@@ -510,8 +514,9 @@ def main():
                 acfg.reset()
                 micro["dropin_video_1500_jpeg_files"] = {"frames_per_s_wall": 1500 / min(walls[1:]), "ms_wall": min(walls[1:]) * 1e3,
                                                          "first_call_ms": walls[0] * 1e3, "rows": int(len(df_stat)),
-                                                         "what": "get_prob_video.preprocess_video_and_predict on 1500 JPEG crops of one "
-                                                                 "clip on disk (page cache), wall clock of the whole call"}
+                                                         "what": "get_prob_video.preprocess_video_and_predict on 1500 JPEG crops (160 - 319 px "
+                                                                 "a side, every file its own size) of one clip on disk (page cache), wall clock of the "
+                                                                 "whole call"}
         except Exception as e:  # pragma: no cover
             micro["dropin_video_1500_jpeg_files"] = {"skipped": f"{type(e).__name__}: {e}"}
         # the face detector that produces the crops (RetinaFace-ResNet50 on raw 1080p frames;
